@@ -1,0 +1,158 @@
+/* include/scopa_b200.h -- C ABI of libscopa_b200.so (sm_100a CUDA implementation of the Miniscopa
+ * hot path: env transitions + CFR / MCCFR / SDCFR traversals).
+ *
+ * The reference (rug-marl-group2/scopa) has no FFI or plugin interface: its boundary is a Python
+ * class API.  Each entry point below names the reference code it replaces (paths relative to
+ * /root/reference/); the Python drop-in classes in scopa_b200/ bind these symbols with ctypes and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; `d_` pointers are DEVICE pointers, `h_` pointers are HOST pointers
+ *     (pinned memory makes the copies asynchronous but is not required);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); device-pointer
+ *     entry points only enqueue work and return; host-pointer (`*_host`) entry points copy in,
+ *     launch, copy out and synchronise before returning;
+ *   - every function returns 0 on success and a negative ms_status on failure; the message is in
+ *     ms_last_error() (thread-local).  No CPU fallback exists: without a CUDA device every compute
+ *     entry point fails with MS_ERR_CUDA;
+ *   - caller owns all I/O buffers; handles are freed with the matching *_destroy.
+ */
+#ifndef SCOPA_B200_H
+#define SCOPA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_ABI_VERSION 1
+
+typedef enum {
+    MS_OK = 0,
+    MS_ERR_CUDA = -1,        /* CUDA runtime error (incl. no device) */
+    MS_ERR_ARG = -2,         /* bad argument */
+    MS_ERR_CAPACITY = -3,    /* tree / table capacity exceeded */
+    MS_ERR_STATE = -4        /* handle used in the wrong state */
+} ms_status;
+
+/* 16-byte packed game state; bit layout in scopa_b200/csrc/ms_state.cuh (also DESIGN.md). */
+typedef struct { uint32_t hands, table, captures, meta; } ms_state;
+
+int ms_abi_version(void);
+const char* ms_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (all streams) */
+uint64_t ms_launch_count(void);
+
+/* ---------------------------------------------------------------------------------- env ------
+ * ms_deal_from_seeds: MiniScopaEnv.reset(seed) for n games = MiniDeck(seed) shuffle with CPython's
+ *   MT19937 random.seed/random.shuffle, first 8 cards dealt 4+4, empty table
+ *   (src/envs/mini_scopa_game.py:15-33, :56-64, :131-138; seed 0 means 42, :132).
+ *   d_hand_order[g]: nibble i = i-th dealt card of player 0 (i<4) / player 1 (i>=4): the order in
+ *   which legal_actions() and the infoset string list the hand. */
+int ms_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_state* d_states, uint32_t* d_hand_order,
+                       void* stream);
+
+/* ms_step: MiniScopaEnv.step(action) on n independent states in place (src/envs/mini_scopa_game.py:140-167
+ *   incl. play_card :93-104, card_in_table :66-91, evaluate_game :106-114).  d_rewards ([n][2] f32,
+ *   may be NULL) receives the terminal rewards (0,0 while running); d_done ([n] u8, may be NULL)
+ *   the terminal flag.  Illegal action = pass; step on a terminal state = no-op. */
+int ms_step(ms_state* d_states, const uint8_t* d_actions, float* d_rewards, uint8_t* d_done, int64_t n,
+            void* stream);
+
+/* ms_legal_actions: MiniScopaState.legal_actions(player) (src/envs/openspiel_mini_scopa.py:22-47);
+ *   player = -1 means each state's current player.  d_mask ([n] u16, bit = action id),
+ *   d_ordered ([n][4] u8, hand order, 0xFF padded) and d_count ([n] u8) may each be NULL.
+ *   d_capture ([n][4] u8, may be NULL): for the k-th legal action, the table-position mask that
+ *   playing it would capture (0 = the card would be placed) -- the legal capture moves. */
+int ms_legal_actions(const ms_state* d_states, const uint32_t* d_hand_order, int player, uint16_t* d_mask,
+                     uint8_t* d_ordered, uint8_t* d_count, uint8_t* d_capture, int64_t n, void* stream);
+
+/* ms_capture: MiniScopaGame.card_in_table(card) for card id d_cards[g] against state g's table
+ *   (src/envs/mini_scopa_game.py:66-91) -> table-position mask (0 = no capture). */
+int ms_capture(const ms_state* d_states, const uint8_t* d_cards, uint8_t* d_table_pos_mask, int64_t n,
+               void* stream);
+
+/* ms_infoset_keys: packed form of information_state_string(player) (openspiel_mini_scopa.py:86-95);
+ *   player = -1 means current player; terminal states give key 0xFFFFFFFFFFFFFFFF ("TERMINAL"). */
+int ms_infoset_keys(const ms_state* d_states, int player, uint64_t* d_keys, int64_t n, void* stream);
+
+/* ms_rollout_random: config 2 of BASELINE.json -- n concurrent random-policy games played to the
+ *   end in one launch (reset already done: d_states/d_hand_order from ms_deal_from_seeds).  At each
+ *   ply the mover plays legal[mulhi32(x0, n_legal)] with x = Philox4x32-10(key = philox_seed,
+ *   ctr = (game id lo, hi, ply, "ROLL")), game id = game_offset + index.  Outputs (each may be
+ *   NULL): d_actions [n][8] u8, d_rewards [n][2] f32, d_final [n] final states. */
+int ms_rollout_random(const ms_state* d_states, const uint32_t* d_hand_order, int64_t n, uint64_t philox_seed,
+                      uint64_t game_offset, uint8_t* d_actions, float* d_rewards, ms_state* d_final,
+                      void* stream);
+
+/* Host-buffer forms (end-to-end: H2D, kernels, D2H, synchronise). */
+int ms_deal_from_seeds_host(const int64_t* h_seeds, int64_t n, ms_state* h_states, uint32_t* h_hand_order);
+int ms_step_host(ms_state* h_states, const uint8_t* h_actions, float* h_rewards, uint8_t* h_done, int64_t n);
+int ms_legal_actions_host(const ms_state* h_states, const uint32_t* h_hand_order, int player, uint16_t* h_mask,
+                          uint8_t* h_ordered, uint8_t* h_count, uint8_t* h_capture, int64_t n);
+int ms_infoset_keys_host(const ms_state* h_states, int player, uint64_t* h_keys, int64_t n);
+/* seeds in -> actions and rewards out: reset + 8 steps per game, all on the device */
+int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_seed, uint64_t game_offset,
+                           uint8_t* h_actions, float* h_rewards);
+
+/* ------------------------------------------------------------------------------ solvers ------
+ * ms_solver: one deal (root state) + its game tree + the slot-aligned infoset table, all resident
+ * in device memory.  Creation enumerates the tree on the device (level-synchronous expansion with
+ * the same step() as above) and assigns each infoset a dense slot in breadth-first first-occurrence
+ * order, which is identical on every GPU -> the regret/strategy arrays of different ranks are
+ * slot-aligned and can be all-reduced as they are.
+ *   replaces: the Python dicts CFRTrainer.info_set_map (src/algorithms/vanilla_cfr.py:49-54) and
+ *   MCCFRTrainer.info_sets (src/algorithms/mc_cfr.py:28-35). */
+typedef struct ms_solver ms_solver;
+
+int ms_solver_create(const ms_state* h_root, uint32_t hand_order, ms_solver** out);
+void ms_solver_destroy(ms_solver* s);
+int ms_solver_reset(ms_solver* s, void* stream);                 /* zero regrets / strategy sums */
+int ms_solver_counts(const ms_solver* s, int32_t* n_nodes, int32_t* n_slots, int32_t* n_levels);
+/* tree export (host buffers sized n_nodes): packed state, parent index (-1 root), level, slot
+ * (-1 for terminals), first-child index, child count */
+int ms_solver_export_tree(const ms_solver* s, ms_state* h_states, int32_t* h_parent, uint8_t* h_level,
+                          int32_t* h_slot, int32_t* h_child_begin, uint8_t* h_nchild);
+/* table export (host buffers sized n_slots): key, n_legal, legal ids in hand order [.][4],
+ * regret [.][4] f64, strategy [.][4] f64, touched flag (MCCFR creates nodes on first touch) */
+int ms_solver_export_table(const ms_solver* s, uint64_t* h_keys, uint8_t* h_nlegal, uint8_t* h_legal,
+                           double* h_regret, double* h_strategy, uint8_t* h_touched, void* stream);
+int ms_solver_import_table(ms_solver* s, const double* h_regret, const double* h_strategy, void* stream);
+/* device pointers to the slot-aligned arrays ([n_slots][4] f64 each) for collectives */
+int ms_solver_device_ptrs(ms_solver* s, double** d_regret, double** d_strategy, double** d_regret_delta,
+                          double** d_strategy_delta, size_t* n_doubles_each);
+
+/* ms_cfr_iterate: `iters` x (traverser 0, traverser 1) of CFRTrainer._cfr_recursive from the root
+ *   (src/algorithms/vanilla_cfr.py:56-99, :105-110), float64, order-exact (per-visit sigma refresh).
+ * ms_cfr_traverse: one call of _cfr_recursive(root, player, reach_p0, reach_p1); *h_value receives
+ *   the returned node utility (synchronises). */
+int ms_cfr_iterate(ms_solver* s, int32_t iters, void* stream);
+int ms_cfr_traverse(ms_solver* s, int32_t player, double reach_p0, double reach_p1, double* h_value, void* stream);
+
+/* ms_mccfr_inplace: `iters` reference iterations of MCCFRTrainer.iteration()
+ *   (src/algorithms/mc_cfr.py:37-92) with in-place table updates after every node, sampling from the
+ *   Philox "MCCF" stream with traversal id first_iter + i (DESIGN.md "Random streams").
+ * ms_mccfr_batch: n_trav independent traversals for `player` (0, 1, or 2 = both) against the
+ *   current (frozen) table, traversal ids first_trav..; regret / strategy deltas are accumulated
+ *   into the delta arrays (not applied).
+ * ms_mccfr_apply: table += delta; delta = 0 (call after the all-reduce of the delta arrays). */
+int ms_mccfr_inplace(ms_solver* s, int64_t iters, uint64_t philox_seed, uint64_t first_iter, void* stream);
+int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
+                   void* stream);
+int ms_mccfr_apply(ms_solver* s, void* stream);
+/* counters accumulated by the MCCFR kernels since the last reset: [0] traverser-node updates,
+ * [1] node visits (_sample calls), [2] env steps */
+int ms_solver_counters(ms_solver* s, uint64_t h_out[3], int reset, void* stream);
+
+/* ms_best_response: restated open_spiel best response against the table's average policy
+ *   (vanilla_cfr.py:112-118 calls exploitability.exploitability).  policy_kind 0 = LearnedCFRPolicy
+ *   (strategy_sum normalised if > 0, vanilla_cfr.py:32-39), 1 = ScopaLearnedPolicy (> 1e-12 and
+ *   touched, mc_cfr.py:118-130), 2 = uniform.  h_br_values[2]; exploitability = sum / 2. */
+int ms_best_response(ms_solver* s, int32_t policy_kind, double h_br_values[2], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCOPA_B200_H */

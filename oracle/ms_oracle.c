@@ -377,7 +377,7 @@ void ora_batch_deal(const int64_t* seeds, int64_t n, int* hands) {
     }
 }
 
-void ora_rollout_random(const int64_t* seeds, int64_t n, uint64_t philox_seed,
+void ora_rollout_random(const int64_t* seeds, int64_t n, uint64_t philox_seed, uint64_t game_offset,
                         uint8_t* actions, float* rewards, uint8_t* scopas, uint8_t* ncaps, int nthreads) {
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -392,10 +392,12 @@ void ora_rollout_random(const int64_t* seeds, int64_t n, uint64_t philox_seed,
         for (int ply = 0; ply < 8; ply++) {
             int pl = e.agent;
             int nl = e.nhand[pl];
-            uint32_t ctr[4] = {(uint32_t)(uint64_t)g, (uint32_t)((uint64_t)g >> 32), (uint32_t)ply, TAG_ROLL};
+            /* "ROLL" stream: one Philox block serves 4 plies: ctr = (game lo, hi, ply/4, tag), word ply%4 */
+            uint64_t gid = game_offset + (uint64_t)g;
+            uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(ply >> 2), TAG_ROLL};
             uint32_t o[4];
             philox4x32_10(ctr, key, o);
-            int a = nl > 0 ? e.hand[pl][(int)(((uint64_t)o[0] * (uint64_t)nl) >> 32)] : 0;
+            int a = nl > 0 ? e.hand[pl][(int)(((uint64_t)o[ply & 3] * (uint64_t)nl) >> 32)] : 0;
             actions[g * 8 + ply] = (uint8_t)a;
             ora_env_step(&e, a);
         }

@@ -68,7 +68,7 @@ def lib():
     L.ora_state_history_str.argtypes = [P(OraState), C.c_char_p, ci]
     L.ora_state_rewards.argtypes = [P(OraState), P(dbl)]
     L.ora_batch_deal.argtypes = [vp, i64, vp]
-    L.ora_rollout_random.argtypes = [vp, i64, u64, vp, vp, vp, vp, ci]
+    L.ora_rollout_random.argtypes = [vp, i64, u64, u64, vp, vp, vp, vp, ci]
     L.ora_table_new.restype = vp
     L.ora_table_free.argtypes = [vp]
     L.ora_table_size.argtypes = [vp]
@@ -283,14 +283,14 @@ def batch_deal(seeds):
     return out
 
 
-def rollout_random(seeds, philox_seed, nthreads=0):
+def rollout_random(seeds, philox_seed, nthreads=0, game_offset=0):
     seeds = np.ascontiguousarray(seeds, dtype=np.int64)
     n = len(seeds)
     actions = np.zeros((n, 8), dtype=np.uint8)
     rewards = np.zeros((n, 2), dtype=np.float32)
     scopas = np.zeros((n, 2), dtype=np.uint8)
     ncaps = np.zeros((n, 2), dtype=np.uint8)
-    lib().ora_rollout_random(seeds.ctypes.data, n, philox_seed, actions.ctypes.data, rewards.ctypes.data,
+    lib().ora_rollout_random(seeds.ctypes.data, n, philox_seed, game_offset, actions.ctypes.data, rewards.ctypes.data,
                              scopas.ctypes.data, ncaps.ctypes.data, nthreads)
     return actions, rewards, scopas, ncaps
 

@@ -1,0 +1,50 @@
+// scopa_b200/csrc/ms_common.cuh -- error plumbing shared by the C-ABI translation units.
+#pragma once
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/scopa_b200.h"
+
+namespace ms {
+
+char* last_error_buf();                      // thread-local, defined in ms_env.cu
+extern std::atomic<uint64_t> g_launches;     // kernels launched by this library
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define MS_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ms::fail(MS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                              \
+    } while (0)
+
+#define MS_LAUNCH_CHECK()                                                                     \
+    do {                                                                                      \
+        ms::g_launches.fetch_add(1, std::memory_order_relaxed);                               \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return ms::fail(MS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                  \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+    } while (0)
+
+constexpr int kNumSMs = 148;   // B200
+
+// grid for a grid-stride kernel: enough CTAs to cover n, capped at a multiple of the SM count
+inline int grid_for(int64_t n, int block, int ctas_per_sm) {
+    int64_t need = (n + block - 1) / block;
+    int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+}  // namespace ms

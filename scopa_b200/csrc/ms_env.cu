@@ -1,0 +1,455 @@
+// scopa_b200/csrc/ms_env.cu -- env kernels (deal, step, legal moves, capture, infoset keys, fused
+// random rollout) and their C-ABI entry points.  sm_100a only.
+//
+// All kernels are one-thread-per-game grid-stride loops over 16-byte packed states: a warp reads
+// and writes 512 contiguous bytes per state access (128-bit per lane), the rules run entirely in
+// registers (ms_state.cuh), and grids are sized in multiples of the 148 SMs.
+#include <cstring>
+#include <mutex>
+
+#include "ms_common.cuh"
+#include "ms_state.cuh"
+
+namespace ms {
+
+std::atomic<uint64_t> g_launches{0};
+char* last_error_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0  deal: CPython random.seed(int) + random.shuffle of the 16-card deck, one thread per seed.
+//   replaces MiniDeck.__init__ / MiniScopaGame.reset (src/envs/mini_scopa_game.py:25-28, :56-64).
+// random.seed(n) = MT19937 init_by_array(32-bit words of |n|): two dependent passes over the 624-word
+// state.  The first pass starts from init_genrand(19650218), which does not depend on the seed, so
+// that table is computed once on the host and read through L1 (same address across the warp).
+// The per-thread 624-word state lives in local memory (interleaved per lane -> coalesced lines).
+// Only the first ~16-20 outputs are needed, so the twist is evaluated lazily for those indices.
+__device__ uint32_t g_mt_init[624];
+
+struct MtLazy {
+    uint32_t* mt;
+    int kk;
+    bool twisted;
+    __device__ __forceinline__ uint32_t next() {
+        uint32_t y;
+        if (!twisted && kk < 227) {
+            // output kk of the first block depends on untouched words kk, kk+1, kk+397 only
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            y = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            kk++;
+        } else {
+            if (!twisted || kk >= 624) {   // astronomically rare (> 200 rejections): full twist
+                if (!twisted) {
+                    // state is still the seeded one; outputs 0..226 were produced lazily
+                    twisted = true;
+                } else {
+                    kk = 0;
+                }
+                int q;
+                for (q = 0; q < 227; q++) {
+                    uint32_t t = (mt[q] & 0x80000000u) | (mt[q + 1] & 0x7fffffffu);
+                    mt[q] = mt[q + 397] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
+                }
+                for (; q < 623; q++) {
+                    uint32_t t = (mt[q] & 0x80000000u) | (mt[q + 1] & 0x7fffffffu);
+                    mt[q] = mt[q - 227] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
+                }
+                uint32_t t = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+                mt[623] = mt[396] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
+            }
+            y = mt[kk++];
+        }
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+};
+
+__global__ void __launch_bounds__(128) deal_kernel(const long long* __restrict__ seeds, long long n,
+                                                   uint4* __restrict__ states, uint32_t* __restrict__ hand_order) {
+    uint32_t mt[624];
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        long long sd = seeds[g];
+        if (sd == 0) sd = 42;   // `seed or self.seed` (mini_scopa_game.py:132, default seed 42)
+        unsigned long long a = sd < 0 ? (unsigned long long)(-(sd + 1)) + 1ull : (unsigned long long)sd;
+        const uint32_t key0 = (uint32_t)a, key1 = (uint32_t)(a >> 32);
+        const bool two = key1 != 0u;   // key length: 32-bit words of |seed|, at least one
+
+        // init_by_array pass 1 (624 steps; i = 1..623 then wraps to i = 1)
+        uint32_t prev = g_mt_init[0];
+        for (int k = 0; k < 623; k++) {
+            uint32_t kj = (two && (k & 1)) ? key1 : key0;
+            uint32_t jj = two ? (uint32_t)(k & 1) : 0u;
+            uint32_t cur = (g_mt_init[k + 1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + kj + jj;
+            mt[k + 1] = cur;
+            prev = cur;
+        }
+        {   // step 624: mt[0] = mt[623]; i = 1; j = 623 % len
+            uint32_t kj = two ? key1 : key0;
+            uint32_t jj = two ? 1u : 0u;
+            uint32_t cur = (mt[1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + kj + jj;
+            mt[1] = cur;
+            prev = cur;
+        }
+        // pass 2 (623 steps: i = 2..623, wrap, i = 1)
+        for (int i = 2; i < 624; i++) {
+            uint32_t cur = (mt[i] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
+            mt[i] = cur;
+            prev = cur;
+        }
+        mt[1] = (mt[1] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - 1u;
+        mt[0] = 0x80000000u;
+
+        // random.shuffle: for i in reversed(range(1, 16)): j = randbelow(i + 1); swap
+        // randbelow(n): k = n.bit_length(); r = getrandbits(k) = word >> (32 - k); retry while r >= n
+        MtLazy gen{mt, 0, false};
+        unsigned long long perm = 0xFEDCBA9876543210ull;   // nibble i = card id i (deck order :26)
+        for (int i = 15; i >= 1; i--) {
+            const uint32_t nn = (uint32_t)i + 1u;
+            const int kbits = 32 - __clz(nn);
+            uint32_t r;
+            do { r = gen.next() >> (32 - kbits); } while (r >= nn);
+            unsigned long long ci = (perm >> (4 * i)) & 0xFull, cr = (perm >> (4 * r)) & 0xFull;
+            perm &= ~((0xFull << (4 * i)) | (0xFull << (4 * r)));
+            perm |= (cr << (4 * i)) | (ci << (4 * r));
+        }
+        uint32_t ord = (uint32_t)perm;   // first 8 dealt cards: 4 to player 0, 4 to player 1
+        uint32_t h0 = 0u, h1 = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            h0 |= 1u << ((ord >> (4 * i)) & 0xFu);
+            h1 |= 1u << ((ord >> (16 + 4 * i)) & 0xFu);
+        }
+        states[g] = st_make(h0, h1, 8u);
+        hand_order[g] = ord;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  step / legal / capture / key
+__global__ void __launch_bounds__(256) step_kernel(uint4* __restrict__ states, const uint8_t* __restrict__ actions,
+                                                   float2* __restrict__ rewards, uint8_t* __restrict__ done,
+                                                   long long n) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        MsState s = states[g];
+        step(s, (uint32_t)actions[g]);
+        states[g] = s;
+        const bool term = st_terminal(s);
+        if (rewards) {
+            float r0 = term ? reward0(s) : 0.f;
+            rewards[g] = make_float2(r0, -r0);
+        }
+        if (done) done[g] = term ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) legal_kernel(const uint4* __restrict__ states,
+                                                    const uint32_t* __restrict__ hand_order, int player,
+                                                    uint16_t* __restrict__ mask, uchar4* __restrict__ ordered,
+                                                    uint8_t* __restrict__ count, uchar4* __restrict__ capture,
+                                                    long long n) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        const MsState s = states[g];
+        const int p = player < 0 ? st_cur(s) : player;
+        uint32_t list;
+        const uint32_t nl = legal_list(s, hand_order[g], p, list);
+        uint32_t m = 0u;
+        uint8_t o[4] = {0xFF, 0xFF, 0xFF, 0xFF}, c[4] = {0, 0, 0, 0};
+        const uint32_t hand = st_hand(s, p);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if ((uint32_t)k < nl) {
+                uint32_t a = (list >> (4 * k)) & 0xFu;
+                m |= 1u << a;
+                o[k] = (uint8_t)a;
+                // the fallback action [0] on an empty hand is a pass: it captures nothing
+                c[k] = ((hand >> a) & 1u) ? (uint8_t)capture_mask(s.y, st_table_len(s), card_rank(a)) : 0;
+            }
+        }
+        if (mask) mask[g] = (uint16_t)m;
+        if (ordered) ordered[g] = make_uchar4(o[0], o[1], o[2], o[3]);
+        if (count) count[g] = (uint8_t)nl;
+        if (capture) capture[g] = make_uchar4(c[0], c[1], c[2], c[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) capture_kernel(const uint4* __restrict__ states,
+                                                      const uint8_t* __restrict__ cards,
+                                                      uint8_t* __restrict__ out, long long n) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        const MsState s = states[g];
+        out[g] = (uint8_t)capture_mask(s.y, st_table_len(s), card_rank(cards[g] & 0xFu));
+    }
+}
+
+__global__ void __launch_bounds__(256) keys_kernel(const uint4* __restrict__ states, int player,
+                                                   unsigned long long* __restrict__ keys, long long n) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        const MsState s = states[g];
+        const int p = player < 0 ? st_cur(s) : player;
+        keys[g] = st_terminal(s) ? 0xFFFFFFFFFFFFFFFFull : infoset_key(s, p);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  fused random rollout: the whole 8-ply game in registers; 20 B in, 8 B actions + 8 B rewards
+// (+16 B final state) out per game.
+__global__ void __launch_bounds__(256) rollout_kernel(const uint4* __restrict__ states,
+                                                      const uint32_t* __restrict__ hand_order, long long n,
+                                                      uint2 key, unsigned long long game_offset,
+                                                      uint2* __restrict__ actions8, float2* __restrict__ rewards,
+                                                      uint4* __restrict__ final_states) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        MsState s = states[g];
+        const uint32_t ho = hand_order[g];
+        const unsigned long long gid = game_offset + (unsigned long long)g;
+        uint32_t acts[2] = {0u, 0u};
+#pragma unroll
+        for (int blk = 0; blk < 2; blk++) {
+            const uint4 x = philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)blk, MS_TAG_ROLL), key);
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t list;
+                const uint32_t nl = legal_list(s, ho, st_cur(s), list);
+                const uint32_t idx = __umulhi(xs[q], nl);
+                const uint32_t a = (list >> (4u * idx)) & 0xFu;
+                step(s, a);
+                acts[blk] |= a << (8 * q);
+            }
+        }
+        if (actions8) actions8[g] = make_uint2(acts[0], acts[1]);
+        if (rewards) {
+            float r0 = st_terminal(s) ? reward0(s) : 0.f;
+            rewards[g] = make_float2(r0, -r0);
+        }
+        if (final_states) final_states[g] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static std::once_flag g_mt_once[64];
+
+static int ensure_mt_table() {
+    int dev = 0;
+    MS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(MS_ERR_ARG, "device index %d out of range", dev);
+    cudaError_t err = cudaSuccess;
+    std::call_once(g_mt_once[dev], [&]() {
+        uint32_t t[624];
+        t[0] = 19650218u;   // init_genrand(19650218), the seed-independent start of init_by_array
+        for (int i = 1; i < 624; i++) t[i] = 1812433253u * (t[i - 1] ^ (t[i - 1] >> 30)) + (uint32_t)i;
+        err = cudaMemcpyToSymbol(g_mt_init, t, sizeof(t));
+    });
+    if (err != cudaSuccess) return fail(MS_ERR_CUDA, "uploading MT table failed: %s", cudaGetErrorString(err));
+    return MS_OK;
+}
+
+// scratch for the host-buffer entry points (grown on demand, one per device, guarded by a mutex)
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+static Scratch g_scratch[64];
+static std::mutex g_scratch_mu;
+
+static int scratch_get(size_t bytes, char** out, cudaStream_t* stream) {
+    int dev = 0;
+    MS_CUDA(cudaGetDevice(&dev));
+    Scratch& sc = g_scratch[dev & 63];
+    if (!sc.stream) MS_CUDA(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
+    if (sc.bytes < bytes) {
+        if (sc.p) MS_CUDA(cudaFree(sc.p));
+        sc.p = nullptr; sc.bytes = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        MS_CUDA(cudaMalloc(&sc.p, want));
+        sc.bytes = want;
+    }
+    *out = (char*)sc.p;
+    *stream = sc.stream;
+    return MS_OK;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace ms
+
+using namespace ms;
+
+extern "C" {
+
+int ms_abi_version(void) { return MS_ABI_VERSION; }
+const char* ms_last_error(void) { return last_error_buf(); }
+uint64_t ms_launch_count(void) { return g_launches.load(); }
+
+int ms_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_state* d_states, uint32_t* d_hand_order, void* stream) {
+    if (n < 0 || (n > 0 && (!d_seeds || !d_states || !d_hand_order))) return fail(MS_ERR_ARG, "ms_deal_from_seeds: bad argument");
+    if (n == 0) return MS_OK;
+    int rc = ensure_mt_table();
+    if (rc) return rc;
+    // 128-thread CTAs, 2.5 KB of local state per thread; 16 CTAs/SM keeps 2048 threads resident
+    deal_kernel<<<grid_for(n, 128, 16), 128, 0, (cudaStream_t)stream>>>(
+        (const long long*)d_seeds, (long long)n, (uint4*)d_states, d_hand_order);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_step(ms_state* d_states, const uint8_t* d_actions, float* d_rewards, uint8_t* d_done, int64_t n, void* stream) {
+    if (n < 0 || (n > 0 && (!d_states || !d_actions))) return fail(MS_ERR_ARG, "ms_step: bad argument");
+    if (n == 0) return MS_OK;
+    step_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((uint4*)d_states, d_actions, (float2*)d_rewards,
+                                                                      d_done, (long long)n);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_legal_actions(const ms_state* d_states, const uint32_t* d_hand_order, int player, uint16_t* d_mask,
+                     uint8_t* d_ordered, uint8_t* d_count, uint8_t* d_capture, int64_t n, void* stream) {
+    if (n < 0 || player > 1 || (n > 0 && (!d_states || !d_hand_order))) return fail(MS_ERR_ARG, "ms_legal_actions: bad argument");
+    if (n == 0) return MS_OK;
+    legal_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_states, d_hand_order, player, d_mask,
+                                                                       (uchar4*)d_ordered, d_count, (uchar4*)d_capture,
+                                                                       (long long)n);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_capture(const ms_state* d_states, const uint8_t* d_cards, uint8_t* d_table_pos_mask, int64_t n, void* stream) {
+    if (n < 0 || (n > 0 && (!d_states || !d_cards || !d_table_pos_mask))) return fail(MS_ERR_ARG, "ms_capture: bad argument");
+    if (n == 0) return MS_OK;
+    capture_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_states, d_cards, d_table_pos_mask,
+                                                                         (long long)n);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_infoset_keys(const ms_state* d_states, int player, uint64_t* d_keys, int64_t n, void* stream) {
+    if (n < 0 || player > 1 || (n > 0 && (!d_states || !d_keys))) return fail(MS_ERR_ARG, "ms_infoset_keys: bad argument");
+    if (n == 0) return MS_OK;
+    keys_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_states, player,
+                                                                      (unsigned long long*)d_keys, (long long)n);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_rollout_random(const ms_state* d_states, const uint32_t* d_hand_order, int64_t n, uint64_t philox_seed,
+                      uint64_t game_offset, uint8_t* d_actions, float* d_rewards, ms_state* d_final, void* stream) {
+    if (n < 0 || (n > 0 && (!d_states || !d_hand_order))) return fail(MS_ERR_ARG, "ms_rollout_random: bad argument");
+    if (n == 0) return MS_OK;
+    rollout_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)d_states, d_hand_order, (long long)n, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
+        (unsigned long long)game_offset, (uint2*)d_actions, (float2*)d_rewards, (uint4*)d_final);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+// ---------------------------------------------------------------------------- host-buffer forms
+int ms_deal_from_seeds_host(const int64_t* h_seeds, int64_t n, ms_state* h_states, uint32_t* h_hand_order) {
+    if (n < 0 || (n > 0 && (!h_seeds || !h_states || !h_hand_order))) return fail(MS_ERR_ARG, "ms_deal_from_seeds_host: bad argument");
+    if (n == 0) return MS_OK;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    size_t o_seed = 0, o_st = align256(o_seed + 8 * n), o_ho = align256(o_st + 16 * n), tot = align256(o_ho + 4 * n);
+    char* d; cudaStream_t st;
+    int rc = scratch_get(tot, &d, &st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(d + o_seed, h_seeds, 8 * n, cudaMemcpyHostToDevice, st));
+    rc = ms_deal_from_seeds((const int64_t*)(d + o_seed), n, (ms_state*)(d + o_st), (uint32_t*)(d + o_ho), st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(h_states, d + o_st, 16 * n, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(h_hand_order, d + o_ho, 4 * n, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+int ms_step_host(ms_state* h_states, const uint8_t* h_actions, float* h_rewards, uint8_t* h_done, int64_t n) {
+    if (n < 0 || (n > 0 && (!h_states || !h_actions))) return fail(MS_ERR_ARG, "ms_step_host: bad argument");
+    if (n == 0) return MS_OK;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    size_t o_st = 0, o_a = align256(16 * n), o_r = align256(o_a + n), o_d = align256(o_r + 8 * n), tot = align256(o_d + n);
+    char* d; cudaStream_t st;
+    int rc = scratch_get(tot, &d, &st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(d + o_st, h_states, 16 * n, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d + o_a, h_actions, n, cudaMemcpyHostToDevice, st));
+    rc = ms_step((ms_state*)(d + o_st), (const uint8_t*)(d + o_a), (float*)(d + o_r), (uint8_t*)(d + o_d), n, st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(h_states, d + o_st, 16 * n, cudaMemcpyDeviceToHost, st));
+    if (h_rewards) MS_CUDA(cudaMemcpyAsync(h_rewards, d + o_r, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (h_done) MS_CUDA(cudaMemcpyAsync(h_done, d + o_d, n, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+int ms_legal_actions_host(const ms_state* h_states, const uint32_t* h_hand_order, int player, uint16_t* h_mask,
+                          uint8_t* h_ordered, uint8_t* h_count, uint8_t* h_capture, int64_t n) {
+    if (n < 0 || (n > 0 && (!h_states || !h_hand_order))) return fail(MS_ERR_ARG, "ms_legal_actions_host: bad argument");
+    if (n == 0) return MS_OK;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    size_t o_st = 0, o_ho = align256(16 * n), o_m = align256(o_ho + 4 * n), o_o = align256(o_m + 2 * n),
+           o_c = align256(o_o + 4 * n), o_cap = align256(o_c + n), tot = align256(o_cap + 4 * n);
+    char* d; cudaStream_t st;
+    int rc = scratch_get(tot, &d, &st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(d + o_st, h_states, 16 * n, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d + o_ho, h_hand_order, 4 * n, cudaMemcpyHostToDevice, st));
+    rc = ms_legal_actions((const ms_state*)(d + o_st), (const uint32_t*)(d + o_ho), player, (uint16_t*)(d + o_m),
+                          (uint8_t*)(d + o_o), (uint8_t*)(d + o_c), (uint8_t*)(d + o_cap), n, st);
+    if (rc) return rc;
+    if (h_mask) MS_CUDA(cudaMemcpyAsync(h_mask, d + o_m, 2 * n, cudaMemcpyDeviceToHost, st));
+    if (h_ordered) MS_CUDA(cudaMemcpyAsync(h_ordered, d + o_o, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (h_count) MS_CUDA(cudaMemcpyAsync(h_count, d + o_c, n, cudaMemcpyDeviceToHost, st));
+    if (h_capture) MS_CUDA(cudaMemcpyAsync(h_capture, d + o_cap, 4 * n, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+int ms_infoset_keys_host(const ms_state* h_states, int player, uint64_t* h_keys, int64_t n) {
+    if (n < 0 || (n > 0 && (!h_states || !h_keys))) return fail(MS_ERR_ARG, "ms_infoset_keys_host: bad argument");
+    if (n == 0) return MS_OK;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    size_t o_st = 0, o_k = align256(16 * n), tot = align256(o_k + 8 * n);
+    char* d; cudaStream_t st;
+    int rc = scratch_get(tot, &d, &st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(d + o_st, h_states, 16 * n, cudaMemcpyHostToDevice, st));
+    rc = ms_infoset_keys((const ms_state*)(d + o_st), player, (uint64_t*)(d + o_k), n, st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(h_keys, d + o_k, 8 * n, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_seed, uint64_t game_offset,
+                           uint8_t* h_actions, float* h_rewards) {
+    if (n < 0 || (n > 0 && !h_seeds)) return fail(MS_ERR_ARG, "ms_rollout_random_host: bad argument");
+    if (n == 0) return MS_OK;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    size_t o_seed = 0, o_st = align256(8 * n), o_ho = align256(o_st + 16 * n), o_a = align256(o_ho + 4 * n),
+           o_r = align256(o_a + 8 * n), tot = align256(o_r + 8 * n);
+    char* d; cudaStream_t st;
+    int rc = scratch_get(tot, &d, &st);
+    if (rc) return rc;
+    MS_CUDA(cudaMemcpyAsync(d + o_seed, h_seeds, 8 * n, cudaMemcpyHostToDevice, st));
+    rc = ms_deal_from_seeds((const int64_t*)(d + o_seed), n, (ms_state*)(d + o_st), (uint32_t*)(d + o_ho), st);
+    if (rc) return rc;
+    rc = ms_rollout_random((const ms_state*)(d + o_st), (const uint32_t*)(d + o_ho), n, philox_seed, game_offset,
+                           (uint8_t*)(d + o_a), (float*)(d + o_r), nullptr, st);
+    if (rc) return rc;
+    if (h_actions) MS_CUDA(cudaMemcpyAsync(h_actions, d + o_a, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (h_rewards) MS_CUDA(cudaMemcpyAsync(h_rewards, d + o_r, 8 * n, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+}  // extern "C"
