@@ -120,9 +120,12 @@ int ms_solver_export_tree(const ms_solver* s, ms_state* h_states, int32_t* h_par
 int ms_solver_export_table(const ms_solver* s, uint64_t* h_keys, uint8_t* h_nlegal, uint8_t* h_legal,
                            double* h_regret, double* h_strategy, uint8_t* h_touched, void* stream);
 int ms_solver_import_table(ms_solver* s, const double* h_regret, const double* h_strategy, void* stream);
-/* device pointers to the slot-aligned arrays ([n_slots][4] f64 each) for collectives */
-int ms_solver_device_ptrs(ms_solver* s, double** d_regret, double** d_strategy, double** d_regret_delta,
-                          double** d_strategy_delta, size_t* n_doubles_each);
+/* device pointers to the slot-aligned arrays for collectives: regret / strategy are [n_slots][4] f64
+ * (*n_table doubles each); delta is ONE contiguous buffer of *n_delta = 5 * n_slots doubles:
+ * [n_slots][4] regret deltas followed by [n_slots] update counts (the strategy delta of a batch is
+ * count * sigma because sigma is frozen for the batch) -> one all-reduce per iteration. */
+int ms_solver_device_ptrs(ms_solver* s, double** d_regret, double** d_strategy, double** d_delta, size_t* n_table,
+                          size_t* n_delta);
 
 /* ms_cfr_iterate: `iters` x (traverser 0, traverser 1) of CFRTrainer._cfr_recursive from the root
  *   (src/algorithms/vanilla_cfr.py:56-99, :105-110), float64, order-exact (per-visit sigma refresh).

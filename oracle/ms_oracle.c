@@ -283,7 +283,7 @@ void ora_env_reset(ora_env* e, int64_t seed, int has_seed) {
 void ora_env_init(ora_env* e, int64_t seed) {
     memset(e, 0, sizeof(*e));
     e->max_steps = 2 * 4;          /* :128 */
-    e->seed = (int)seed;
+    e->seed = seed;
     ora_env_reset(e, seed, 1);     /* :130 self.reset(seed) */
 }
 
@@ -867,4 +867,31 @@ float ora_sdcfr_traverse(const ora_mlp nets[2], int64_t seed, int player, ora_rn
     float v = sdcfr_rec(&c, &s);
     if (n_out) *n_out = c.n;
     return v;
+}
+
+/* ================================================================================ CPU baseline */
+/* bench.py's cpu_baseline / --impl reference leg: `nthreads` independent workers, each with its own
+ * pre-populated table, each running ntrav_per_thread traversal pairs (player 0 then player 1 against
+ * the frozen table) of the reference estimator.  Returns totals over all workers. */
+void ora_mccfr_bench(int64_t seed, int64_t ntrav_per_thread, int nthreads, uint64_t philox_seed,
+                     int64_t* updates, int64_t* visits) {
+    int64_t tu = 0, tv = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static) reduction(+ : tu, tv)
+    for (int w = 0; w < nthreads; w++) {
+        ora_table* t = ora_table_new();
+        ora_mccfr_populate(t, seed);
+        int64_t u = 0, v = 0;
+        for (int p = 0; p < 2; p++) {
+            int64_t uu = 0, vv = 0;
+            ora_mccfr_batch(t, seed, p, philox_seed, (uint64_t)w * (uint64_t)ntrav_per_thread, ntrav_per_thread, &uu, &vv);
+            u += uu; v += vv;
+        }
+        tu += u; tv += v;
+        ora_table_free(t);
+    }
+    if (updates) *updates = tu;
+    if (visits) *visits = tv;
 }

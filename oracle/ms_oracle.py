@@ -28,7 +28,7 @@ class OraEnv(C.Structure):
                 ("caps", (C.c_int * 16) * 2), ("ncaps", C.c_int * 2),
                 ("scopas", C.c_int * 2),
                 ("table", C.c_int * 16), ("ntable", C.c_int),
-                ("agent", C.c_int), ("step_count", C.c_int), ("max_steps", C.c_int), ("seed", C.c_int),
+                ("agent", C.c_int), ("step_count", C.c_int), ("max_steps", C.c_int), ("seed", C.c_int64),
                 ("rewards", C.c_double * 2), ("term", C.c_int * 2)]
 
 
@@ -96,6 +96,7 @@ def lib():
     L.ora_advantages_policy.argtypes = [P(OraMlp), vp, vp, vp, vp]
     L.ora_sdcfr_traverse.argtypes = [P(OraMlp), i64, ci, vp, u64, vp, vp, vp, ci, P(ci)]
     L.ora_sdcfr_traverse.restype = C.c_float
+    L.ora_mccfr_bench.argtypes = [i64, i64, ci, u64, P(i64), P(i64)]
     _lib = L
     return L
 
@@ -329,3 +330,9 @@ def sdcfr_traverse(mlps, player, rng, trav_id=0, seed=42, cap=64):
     v = lib().ora_sdcfr_traverse(nets, seed, player, rng.r, trav_id, feat.ctypes.data, target.ctypes.data,
                                  mask.ctypes.data, cap, C.byref(n))
     return float(v), feat[:n.value], target[:n.value], mask[:n.value]
+
+
+def mccfr_bench(ntrav_per_thread, nthreads, philox_seed=0, seed=42):
+    u, v = C.c_int64(), C.c_int64()
+    lib().ora_mccfr_bench(seed, ntrav_per_thread, nthreads, philox_seed, C.byref(u), C.byref(v))
+    return u.value, v.value

@@ -1,21 +1,1050 @@
-// placeholder translation unit: solver entry points are filled in incrementally
+// scopa_b200/csrc/ms_solver.cu -- one-deal solver state on the device: game-tree enumeration, the
+// slot-aligned infoset table, vanilla CFR (order-exact level-synchronous sweep), the reference's
+// sampled-CFR estimator (in-place and batched), and the best-response sweep.  sm_100a only.
+//
+// Replaces (paths relative to /root/reference/):
+//   CFRTrainer._cfr_recursive / train      src/algorithms/vanilla_cfr.py:56-120
+//   MCCFRTrainer._sample / iteration       src/algorithms/mc_cfr.py:37-92
+//   the dict-of-InfoNode tables            vanilla_cfr.py:49-54, mc_cfr.py:28-35
+//   exploitability.exploitability(...)     vanilla_cfr.py:112-118 (third-party open_spiel, restated)
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
 #include "ms_common.cuh"
-using namespace ms;
-extern "C" {
-#define NOT_YET(name) return fail(MS_ERR_STATE, name ": not implemented yet")
-int ms_solver_create(const ms_state*, uint32_t, ms_solver**) { NOT_YET("ms_solver_create"); }
-void ms_solver_destroy(ms_solver*) {}
-int ms_solver_reset(ms_solver*, void*) { NOT_YET("ms_solver_reset"); }
-int ms_solver_counts(const ms_solver*, int32_t*, int32_t*, int32_t*) { NOT_YET("ms_solver_counts"); }
-int ms_solver_export_tree(const ms_solver*, ms_state*, int32_t*, uint8_t*, int32_t*, int32_t*, uint8_t*) { NOT_YET("ms_solver_export_tree"); }
-int ms_solver_export_table(const ms_solver*, uint64_t*, uint8_t*, uint8_t*, double*, double*, uint8_t*, void*) { NOT_YET("ms_solver_export_table"); }
-int ms_solver_import_table(ms_solver*, const double*, const double*, void*) { NOT_YET("ms_solver_import_table"); }
-int ms_solver_device_ptrs(ms_solver*, double**, double**, double**, double**, size_t*) { NOT_YET("ms_solver_device_ptrs"); }
-int ms_cfr_iterate(ms_solver*, int32_t, void*) { NOT_YET("ms_cfr_iterate"); }
-int ms_cfr_traverse(ms_solver*, int32_t, double, double, double*, void*) { NOT_YET("ms_cfr_traverse"); }
-int ms_mccfr_inplace(ms_solver*, int64_t, uint64_t, uint64_t, void*) { NOT_YET("ms_mccfr_inplace"); }
-int ms_mccfr_batch(ms_solver*, int32_t, int64_t, uint64_t, uint64_t, void*) { NOT_YET("ms_mccfr_batch"); }
-int ms_mccfr_apply(ms_solver*, void*) { NOT_YET("ms_mccfr_apply"); }
-int ms_solver_counters(ms_solver*, uint64_t*, int, void*) { NOT_YET("ms_solver_counters"); }
-int ms_best_response(ms_solver*, int32_t, double*, void*) { NOT_YET("ms_best_response"); }
+#include "ms_state.cuh"
+
+namespace ms {
+
+constexpr int MAXN = 4096;   // tree nodes (a 4+4-card deal has 2229)
+constexpr int MAXL = 34;     // levels
+constexpr int MAXS = 1664;   // infoset slots
+
+// ------------------------------------------------------------------------------------------------
+// Tree enumeration: level-synchronous expansion with the same step()/legal_list() as the env
+// kernels.  Children are appended in hand (= legal_actions) order, so inside one level the node
+// index order equals the reference's depth-first visiting order restricted to that level.
+struct TreeOut {
+    uint4* state; int* parent; int* child_begin; uint8_t* nchild; unsigned long long* key;
+    uint16_t* legal; int8_t* rx2; int* level_begin; int* counts;   // counts: [0] nodes [1] levels [2] overflow
+};
+
+__global__ void __launch_bounds__(256) tree_expand_kernel(uint4 root, uint32_t hand_order, TreeOut t) {
+    __shared__ int s_begin, s_end, s_total, s_stop;
+    const int tid = threadIdx.x, bd = blockDim.x;
+    if (tid == 0) {
+        t.state[0] = root; t.parent[0] = -1; t.level_begin[0] = 0;
+        s_begin = 0; s_end = 1; s_stop = 0; t.counts[2] = 0;
+    }
+    __syncthreads();
+    int lvl = 0;
+    for (;; lvl++) {
+        const int begin = s_begin, end = s_end;
+        for (int i = begin + tid; i < end; i += bd) {
+            const MsState s = t.state[i];
+            const bool term = st_terminal(s);
+            uint32_t list = 0u;
+            const uint32_t nl = term ? 0u : legal_list(s, hand_order, st_cur(s), list);
+            t.nchild[i] = (uint8_t)nl;
+            t.legal[i] = (uint16_t)list;
+            t.key[i] = term ? 0xFFFFFFFFFFFFFFFFull : infoset_key(s, st_cur(s));
+            t.rx2[i] = term ? (int8_t)reward0_x2(s) : (int8_t)0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = end;
+            for (int i = begin; i < end; i++) { t.child_begin[i] = acc; acc += t.nchild[i]; }
+            if (acc > MAXN || lvl + 2 > MAXL) { t.counts[2] = 1; acc = end; }
+            s_total = acc;
+            if (acc == end) s_stop = 1;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        for (int i = begin + tid; i < end; i += bd) {
+            const int nc = t.nchild[i], cb = t.child_begin[i];
+            const uint32_t list = t.legal[i];
+            for (int k = 0; k < nc; k++) {
+                MsState c = t.state[i];
+                step(c, (list >> (4 * k)) & 0xFu);
+                t.state[cb + k] = c;
+                t.parent[cb + k] = i;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { t.level_begin[lvl + 1] = end; s_begin = end; s_end = s_total; }
+        __syncthreads();
+    }
+    if (tid == 0) { t.level_begin[lvl + 1] = s_end; t.counts[0] = s_end; t.counts[1] = lvl + 1; }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-side view of a solver (plain pointers; passed to kernels by value).
+struct SolverDev {
+    // tree
+    int n_nodes, n_levels, n_slots, root_cur;
+    uint4 root; uint32_t hand_order;
+    const int* level_begin;        // [n_levels + 1]
+    const uint16_t* child_begin;   // [n_nodes]
+    const uint8_t* nchild;         // [n_nodes]
+    const int16_t* node_slot;      // [n_nodes] (-1 terminal)
+    const int8_t* rx2;             // [n_nodes] 2 * reward of player 0 at terminals
+    // slots
+    const uint16_t* chain_begin;   // [n_slots + 1]
+    const uint16_t* chain_nodes;   // [n_decision] node ids, ascending inside a chain
+    const int* slot_level_begin;   // [n_levels + 1]
+    const uint8_t* slot_nlegal;    // [n_slots]
+    const uint8_t* slot_player;    // [n_slots]
+    // hash index key -> slot (open addressing, linear probing)
+    const unsigned long long* hkeys; const int16_t* hslots; int hcap;
+    // table
+    double* regret; double* strategy;   // [n_slots][4]
+    double* delta;                      // [n_slots][4] regret deltas, then [n_slots] update counts
+    uint8_t* touched;                   // [n_slots]
+    unsigned long long* counters;       // [0] updates [1] visits [2] env steps
+};
+
+// regret matching: InfoNode.get_strategy (vanilla_cfr.py:23-30) == current_strategy (mc_cfr.py:20-24)
+__device__ __forceinline__ void regret_match(const double* reg, int n, double* out) {
+    double pos[4];
+    double norm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        pos[i] = (i < n && reg[i] > 0.0) ? reg[i] : 0.0;
+        if (i < n) norm = __dadd_rn(norm, pos[i]);
+    }
+    const double uni = __ddiv_rn(1.0, (double)n);
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (norm > 0.0 ? __ddiv_rn(pos[i], norm) : uni) : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  vanilla CFR.  One CTA owns the whole iteration; tree values, reaches, regrets and current
+// strategies live in shared memory for all iterations of the launch.
+//
+// The reference refreshes an infoset's strategy after EVERY visit (vanilla_cfr.py:97), so one
+// traversal is a Gauss-Seidel sweep whose result depends on the depth-first visiting order
+// (SURVEY.md H3).  Exact level-synchronous restatement, per traversal for traverser tp:
+//   A  top-down : opponent reach of every node (the opponent's strategy cannot change during the
+//                 traversal: only tp's regrets are written);
+//   B  bottom-up: opponent levels take the expectation under the opponent's strategy; at traverser
+//                 levels each infoset walks ITS nodes in depth-first order (= ascending node index
+//                 within the level) as a sequential chain: u = sigma.u_children, regret += opp*(u_a-u),
+//                 sigma <- RM(regret); the sigma each node used is parked in its children's (now dead)
+//                 value slots;
+//   C  top-down : own reach from the parked sigmas, then strategy_sum += reach * sigma_used along
+//                 the same chains.
+// All arithmetic is float64 with explicit round-to-nearest mul/add/div (no FMA contraction) in the
+// reference's operation order -> results are bit-identical to numpy's.
+struct CfrSmem {
+    double* u; double* r; double* reg; double* sig;
+    uint16_t* child_begin; uint16_t* chain_nodes; uint16_t* chain_begin; int16_t* node_slot;
+    uint8_t* nchild; int8_t* rx2; uint8_t* nlegal;
+};
+
+__host__ __device__ inline size_t cfr_smem_bytes(int n_nodes, int n_slots, int n_dec) {
+    size_t b = 0;
+    b += sizeof(double) * (size_t)n_nodes * 2;
+    b += sizeof(double) * (size_t)n_slots * 8;
+    b += sizeof(uint16_t) * ((size_t)n_nodes + n_dec + n_slots + 1) + sizeof(int16_t) * (size_t)n_nodes;
+    b += (size_t)n_nodes * 2 + n_slots;
+    return b + 64;
+}
+
+__device__ __forceinline__ CfrSmem cfr_carve(unsigned char* base, int N, int S, int D) {
+    CfrSmem m;
+    m.u = (double*)base; m.r = m.u + N; m.reg = m.r + N; m.sig = m.reg + 4 * S;
+    m.child_begin = (uint16_t*)(m.sig + 4 * S);
+    m.chain_nodes = m.child_begin + N;
+    m.chain_begin = m.chain_nodes + D;
+    m.node_slot = (int16_t*)(m.chain_begin + S + 1);
+    m.nchild = (uint8_t*)(m.node_slot + N);
+    m.rx2 = (int8_t*)(m.nchild + N);
+    m.nlegal = (uint8_t*)(m.rx2 + N);
+    return m;
+}
+
+__device__ void cfr_traversal(const SolverDev& d, const CfrSmem& m, int tp, double r0, double r1,
+                              const int* s_lvl, const int* s_slvl) {
+    const int tid = threadIdx.x, bd = blockDim.x;
+    const int L = d.n_levels;
+    // ---- A: opponent reach
+    if (tid == 0) m.r[0] = (tp == 0) ? r1 : r0;
+    __syncthreads();
+    for (int l = 0; l + 1 < L; l++) {
+        const int cp = (d.root_cur + l) & 1;
+        for (int v = s_lvl[l] + tid; v < s_lvl[l + 1]; v += bd) {
+            const int nc = m.nchild[v];
+            if (nc == 0) continue;
+            const int cb = m.child_begin[v];
+            const double ro = m.r[v];
+            if (cp != tp) {
+                const double* sg = m.sig + 4 * m.node_slot[v];
+                for (int i = 0; i < nc; i++) m.r[cb + i] = __dmul_rn(ro, sg[i]);
+            } else {
+                for (int i = 0; i < nc; i++) m.r[cb + i] = ro;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- B: values bottom-up, regret chains at traverser levels
+    for (int l = L - 1; l >= 0; l--) {
+        const int cp = (d.root_cur + l) & 1;
+        for (int v = s_lvl[l] + tid; v < s_lvl[l + 1]; v += bd) {
+            const int nc = m.nchild[v];
+            if (nc == 0) {
+                const double r = 0.5 * (double)m.rx2[v];
+                m.u[v] = (tp == 0) ? r : -r;
+            } else if (cp != tp) {
+                const int cb = m.child_begin[v];
+                const double* sg = m.sig + 4 * m.node_slot[v];
+                double acc = 0.0;
+                for (int i = 0; i < nc; i++) acc = __dadd_rn(acc, __dmul_rn(sg[i], m.u[cb + i]));
+                m.u[v] = acc;
+            }
+        }
+        if (cp == tp) {
+            for (int s = s_slvl[l] + tid; s < s_slvl[l + 1]; s += bd) {
+                const int n = m.nlegal[s];
+                double reg[4], sg[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { reg[i] = m.reg[4 * s + i]; sg[i] = m.sig[4 * s + i]; }
+                for (int k = m.chain_begin[s]; k < m.chain_begin[s + 1]; k++) {
+                    const int v = m.chain_nodes[k];
+                    const int cb = m.child_begin[v];
+                    double au[4];
+                    double util = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (i < n) { au[i] = m.u[cb + i]; util = __dadd_rn(util, __dmul_rn(sg[i], au[i])); }
+                    const double opp = m.r[v];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (i < n) {
+                            reg[i] = __dadd_rn(reg[i], __dmul_rn(opp, __dadd_rn(au[i], -util)));
+                            m.u[cb + i] = sg[i];          // park sigma_used in the dead child slot
+                        }
+                    m.u[v] = util;
+                    regret_match(reg, n, sg);             // refreshed after every visit (:97)
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) { m.reg[4 * s + i] = reg[i]; m.sig[4 * s + i] = sg[i]; }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- C: own reach top-down, then strategy sums along the chains
+    if (tid == 0) m.r[0] = (tp == 0) ? r0 : r1;
+    __syncthreads();
+    for (int l = 0; l + 1 < L; l++) {
+        const int cp = (d.root_cur + l) & 1;
+        for (int v = s_lvl[l] + tid; v < s_lvl[l + 1]; v += bd) {
+            const int nc = m.nchild[v];
+            if (nc == 0) continue;
+            const int cb = m.child_begin[v];
+            const double rt = m.r[v];
+            if (cp == tp) for (int i = 0; i < nc; i++) m.r[cb + i] = __dmul_rn(rt, m.u[cb + i]);
+            else for (int i = 0; i < nc; i++) m.r[cb + i] = rt;
+        }
+        __syncthreads();
+    }
+    for (int s = tid; s < d.n_slots; s += bd) {
+        if (d.slot_player[s] != tp) continue;
+        const int n = m.nlegal[s];
+        double acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i] = d.strategy[4 * s + i];
+        for (int k = m.chain_begin[s]; k < m.chain_begin[s + 1]; k++) {
+            const int v = m.chain_nodes[k];
+            const int cb = m.child_begin[v];
+            const double rt = m.r[v];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < n) acc[i] = __dadd_rn(acc[i], __dmul_rn(rt, m.u[cb + i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) d.strategy[4 * s + i] = acc[i];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(512, 1) cfr_kernel(SolverDev d, int n_dec, int iters, int only_player, double r0,
+                                                     double r1, double* out_value) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_lvl[MAXL + 1], s_slvl[MAXL + 1];
+    const int tid = threadIdx.x, bd = blockDim.x;
+    const int N = d.n_nodes, S = d.n_slots;
+    CfrSmem m = cfr_carve(smem_raw, N, S, n_dec);
+    for (int i = tid; i <= d.n_levels; i += bd) { s_lvl[i] = d.level_begin[i]; s_slvl[i] = d.slot_level_begin[i]; }
+    for (int i = tid; i < N; i += bd) {
+        m.child_begin[i] = d.child_begin[i]; m.nchild[i] = d.nchild[i];
+        m.node_slot[i] = d.node_slot[i]; m.rx2[i] = d.rx2[i];
+    }
+    for (int i = tid; i < n_dec; i += bd) m.chain_nodes[i] = d.chain_nodes[i];
+    for (int i = tid; i <= S; i += bd) m.chain_begin[i] = d.chain_begin[i];
+    for (int s = tid; s < S; s += bd) {
+        const int n = d.slot_nlegal[s];
+        m.nlegal[s] = (uint8_t)n;
+        double reg[4], sg[4];
+        for (int i = 0; i < 4; i++) { reg[i] = d.regret[4 * s + i]; m.reg[4 * s + i] = reg[i]; }
+        regret_match(reg, n, sg);     // invariant: local_strategy == RM(regret_sum) between visits
+        for (int i = 0; i < 4; i++) m.sig[4 * s + i] = sg[i];
+    }
+    __syncthreads();
+    for (int it = 0; it < iters; it++) {
+        for (int tp = 0; tp < 2; tp++) {
+            if (only_player >= 0 && tp != only_player) continue;
+            cfr_traversal(d, m, tp, r0, r1, s_lvl, s_slvl);
+        }
+    }
+    for (int i = tid; i < 4 * S; i += bd) d.regret[i] = m.reg[i];
+    if (tid == 0 && out_value) *out_value = m.u[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  the reference's sampled-CFR estimator (mc_cfr.py:37-86).
+//
+// One thread = one traversal, run as an explicit depth-first search whose stack lives in shared
+// memory.  The recursion shape is the same for every traversal (1 + |hand| recursive calls at a
+// traverser node, 1 at an opponent node), so the lanes of a warp stay convergent.  Opponent nodes
+// are tail calls and need no frame; only traverser nodes push one:
+//   state (16 B) | opp reach f64 | own sampling prob f64 | slot, n_legal, legal list, child cursor |
+//   returned child values as exact bytes (a returned utility is always a terminal reward = k/2).
+// Infosets are found by probing the open-addressing key->slot index with the packed 64-bit key.
+// Sampling: u = u53(Philox4x32-10(key = seed, ctr = (traversal id lo, hi, call index, "MCCF"+tp)))
+// and numpy's cumsum / normalise / searchsorted-right rule, so that the CPU oracle can follow the
+// same stream (call index = order of _sample invocations inside the traversal).
+struct Frames {            // SoA: [frame][thread]
+    uint4* st; double* ro; double* sp; uint2* meta;
+    int stride;            // threads per CTA
+};
+// meta.x: slot (bits 0-11) | n_legal (12-14) | child cursor (15-17) | legal list (16 bits at 18..)  -> needs 34 bits;
+// so: meta.x = slot | n_legal << 12 | cursor << 16 ;  meta.y = legal list (16) | util byte << 16 ;  cfv bytes
+// are kept in a third word.
+struct Frames3 { uint32_t* cfv; };
+
+__device__ __forceinline__ int lookup_slot(const unsigned long long* hk, const int16_t* hs, int hcap,
+                                           unsigned long long key) {
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (uint32_t)(hcap - 1);
+    while (true) {
+        const unsigned long long k = hk[h];
+        if (k == key) return hs[h];
+        if (k == 0xFFFFFFFFFFFFFFFFull) return -1;
+        h = (h + 1) & (uint32_t)(hcap - 1);
+    }
+}
+
+// np.random.choice(legal, p=sigma): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right')
+__device__ __forceinline__ int sample_action(const double* sg, int n, double u) {
+    double cdf[4];
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { if (i < n) acc = __dadd_rn(acc, sg[i]); cdf[i] = acc; }
+    const double last = acc;
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (i < n && __ddiv_rn(cdf[i], last) <= u) idx++;
+    return idx < n ? idx : n - 1;
+}
+
+struct MccfrShared {
+    const unsigned long long* hk; const int16_t* hs; int hcap;
+    const double* sig;        // frozen strategies (batch mode), [S][4]
+    double* dreg;             // per-CTA private regret deltas (batch mode), [S][4]
+    uint32_t* dcnt;           // per-CTA update counts (batch mode), [S]
+    uint8_t* touched;         // per-CTA touched flags, [S]
+    double* reg; double* str; // in-place mode: the table itself
+};
+
+template <bool INPLACE>
+__device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp, unsigned long long trav,
+                               uint2 pkey, uint4* f_st, double* f_ro, double* f_sp, uint2* f_meta, uint32_t* f_cfv,
+                               int fstride, unsigned long long& n_upd, unsigned long long& n_vis,
+                               unsigned long long& n_step) {
+    MsState s = d.root;
+    double ro = 1.0, sp = 1.0;
+    int fi = -1;
+    uint32_t call = 0;
+    int ret_x2 = 0;
+    bool returning = false;
+    const uint32_t tag = MS_TAG_MCCF + (uint32_t)tp;
+    while (true) {
+        if (!returning) {
+            const uint32_t my_call = call++;
+            n_vis++;
+            if (st_terminal(s)) {
+                const int r = reward0_x2(s);
+                ret_x2 = (tp == 0) ? r : -r;
+                returning = true;
+                continue;
+            }
+            const int p = st_cur(s);
+            uint32_t list;
+            const uint32_t nl = legal_list(s, d.hand_order, p, list);
+            const int slot = lookup_slot(sh.hk, sh.hs, sh.hcap, infoset_key(s, p));
+            double sg[4];
+            if (INPLACE) regret_match(sh.reg + 4 * slot, (int)nl, sg);
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) sg[i] = sh.sig[4 * slot + i];
+            }
+            sh.touched[slot] = 1;     // node created on first touch, for both players (mc_cfr.py:52)
+            const uint4 x = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), my_call, tag), pkey);
+            const int ai = sample_action(sg, (int)nl, u53(x.x, x.y));
+            const uint32_t a = (list >> (4 * ai)) & 0xFu;
+            if (p != tp) {            // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
+                ro = __dmul_rn(ro, sg[ai]);
+                step(s, a); n_step++;
+                continue;
+            }
+            // traverser: push a frame, descend into the sampled action first (:58-67)
+            fi++;
+            const int o = fi * fstride;
+            f_st[o] = s; f_ro[o] = ro; f_sp[o] = sp;
+            f_meta[o] = make_uint2((uint32_t)slot | (nl << 12), list);
+            f_cfv[o] = 0u;
+            sp = __dmul_rn(sp, sg[ai]);
+            step(s, a); n_step++;
+            continue;
+        }
+        // ---- a child returned ret_x2 to the top frame
+        if (fi < 0) break;
+        const int o = fi * fstride;
+        uint2 meta = f_meta[o];
+        const int slot = (int)(meta.x & 0xFFFu);
+        const int nl = (int)((meta.x >> 12) & 0x7u);
+        int cur = (int)((meta.x >> 16) & 0x7u);
+        uint32_t cfvb = f_cfv[o];
+        if (cur == 0) meta.y = (meta.y & 0xFFFFu) | (((uint32_t)ret_x2 & 0xFFu) << 16);   // util of the sampled action
+        else cfvb |= ((uint32_t)ret_x2 & 0xFFu) << (8 * (cur - 1));
+        cur++;
+        double sg[4];
+        if (INPLACE) regret_match(sh.reg + 4 * slot, nl, sg);   // unchanged since entry: an infoset cannot recur below itself
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) sg[i] = sh.sig[4 * slot + i];
+        }
+        if (cur <= nl) {              // evaluate action i = cur-1 with a fresh sampled continuation (:71-78)
+            const int i = cur - 1;
+            meta.x = (meta.x & 0xFFFFu) | ((uint32_t)cur << 16);
+            f_meta[o] = meta; f_cfv[o] = cfvb;
+            s = f_st[o];
+            ro = f_ro[o];
+            sp = __dmul_rn(f_sp[o], sg[i]);
+            step(s, (meta.y >> (4 * i)) & 0xFu); n_step++;
+            returning = false;
+            continue;
+        }
+        // ---- all actions evaluated: regret / strategy update (:79-84)
+        double cfv[4];
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            cfv[i] = 0.5 * (double)(int)(int8_t)((cfvb >> (8 * i)) & 0xFFu);
+            if (i < nl) v = __dadd_rn(v, __dmul_rn(sg[i], cfv[i]));
+        }
+        const double fro = f_ro[o], fsp = f_sp[o];
+        const double w = fsp > 0.0 ? __ddiv_rn(fro, fsp) : 0.0;
+        if (INPLACE) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < nl) {
+                    sh.reg[4 * slot + i] = __dadd_rn(sh.reg[4 * slot + i], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+                    sh.str[4 * slot + i] = __dadd_rn(sh.str[4 * slot + i], __dmul_rn(1.0, sg[i]));  // reach_probs[tp] is always 1.0
+                }
+        } else {
+            if (nl > 1) {             // |A| = 1: cfv - v == 0 exactly
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (i < nl) atomicAdd(&sh.dreg[4 * slot + i], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+            }
+            atomicAdd(&sh.dcnt[slot], 1u);   // strategy delta = count * sigma (sigma is frozen for the batch)
+        }
+        n_upd++;
+        ret_x2 = (int)(int8_t)((meta.y >> 16) & 0xFFu);
+        fi--;
+        returning = true;
+    }
+}
+
+// in-place mode: one thread, table in shared memory, reference semantics (every update is visible to
+// the next node visit).  Used for parity / curve validation, not for throughput.
+__global__ void __launch_bounds__(32, 1) mccfr_inplace_kernel(SolverDev d, long long iters, uint2 pkey,
+                                                             unsigned long long first_iter, int nframes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = d.n_slots;
+    double* reg = (double*)smem_raw;
+    double* str = reg + 4 * S;
+    unsigned long long* hk = (unsigned long long*)(str + 4 * S);
+    uint4* f_st = (uint4*)(hk + d.hcap);
+    double* f_ro = (double*)(f_st + nframes);
+    double* f_sp = f_ro + nframes;
+    uint2* f_meta = (uint2*)(f_sp + nframes);
+    uint32_t* f_cfv = (uint32_t*)(f_meta + nframes);
+    int16_t* hs = (int16_t*)(f_cfv + nframes);
+    uint8_t* touched = (uint8_t*)(hs + d.hcap);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * S; i += 32) { reg[i] = d.regret[i]; str[i] = d.strategy[i]; }
+    for (int i = tid; i < d.hcap; i += 32) { hk[i] = d.hkeys[i]; hs[i] = d.hslots[i]; }
+    for (int i = tid; i < S; i += 32) touched[i] = d.touched[i];
+    __syncwarp();
+    if (tid == 0) {
+        MccfrShared sh{hk, hs, d.hcap, nullptr, nullptr, nullptr, touched, reg, str};
+        unsigned long long nu = 0, nv = 0, ns = 0;
+        for (long long it = 0; it < iters; it++)
+            for (int tp = 0; tp < 2; tp++)
+                mccfr_traverse<true>(d, sh, tp, first_iter + (unsigned long long)it, pkey, f_st, f_ro, f_sp, f_meta,
+                                     f_cfv, 1, nu, nv, ns);
+        atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns);
+    }
+    __syncwarp();
+    for (int i = tid; i < 4 * S; i += 32) { d.regret[i] = reg[i]; d.strategy[i] = str[i]; }
+    for (int i = tid; i < S; i += 32) d.touched[i] = touched[i];
+}
+
+constexpr int MCCFR_THREADS = 512;
+
+__host__ __device__ inline size_t mccfr_batch_smem(int S, int hcap, int nframes, int threads) {
+    size_t b = 0;
+    b += sizeof(double) * 8 * (size_t)S;                 // sigma + regret deltas
+    b += sizeof(unsigned long long) * (size_t)hcap;      // hash keys
+    b += (size_t)threads * nframes * (16 + 8 + 8 + 8 + 4);   // frames
+    b += sizeof(uint32_t) * (size_t)S;                   // counts
+    b += sizeof(int16_t) * (size_t)hcap;                 // hash slots
+    b += (size_t)S;                                      // touched
+    return b + 64;
+}
+
+// batch mode: sigma frozen for the launch; deltas accumulate in per-CTA shared tables and are
+// flushed to the global delta array with one fp64 RED per non-zero entry.
+__global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev d, int player, long long n_trav,
+                                                                    uint2 pkey, unsigned long long first_trav,
+                                                                    int nframes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = d.n_slots, T = blockDim.x, tid = threadIdx.x;
+    double* sig = (double*)smem_raw;
+    double* dreg = sig + 4 * S;
+    unsigned long long* hk = (unsigned long long*)(dreg + 4 * S);
+    uint4* f_st = (uint4*)(hk + d.hcap);
+    double* f_ro = (double*)(f_st + (size_t)T * nframes);
+    double* f_sp = f_ro + (size_t)T * nframes;
+    uint2* f_meta = (uint2*)(f_sp + (size_t)T * nframes);
+    uint32_t* f_cfv = (uint32_t*)(f_meta + (size_t)T * nframes);
+    uint32_t* dcnt = f_cfv + (size_t)T * nframes;
+    int16_t* hs = (int16_t*)(dcnt + S);
+    uint8_t* touched = (uint8_t*)(hs + d.hcap);
+
+    for (int s = tid; s < S; s += T) {
+        double reg[4], sg[4];
+        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+        regret_match(reg, d.slot_nlegal[s], sg);
+        for (int i = 0; i < 4; i++) { sig[4 * s + i] = sg[i]; dreg[4 * s + i] = 0.0; }
+        dcnt[s] = 0u; touched[s] = 0;
+    }
+    for (int i = tid; i < d.hcap; i += T) { hk[i] = d.hkeys[i]; hs[i] = d.hslots[i]; }
+    __syncthreads();
+
+    MccfrShared sh{hk, hs, d.hcap, sig, dreg, dcnt, touched, nullptr, nullptr};
+    unsigned long long nu = 0, nv = 0, ns = 0;
+    const long long gstride = (long long)gridDim.x * T;
+    for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += gstride) {
+        for (int tp = 0; tp < 2; tp++) {
+            if (player < 2 && tp != player) continue;
+            mccfr_traverse<false>(d, sh, tp, first_trav + (unsigned long long)k, pkey, f_st + tid, f_ro + tid, f_sp + tid,
+                                  f_meta + tid, f_cfv + tid, T, nu, nv, ns);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 4 * S; i += T) {
+        const double v = dreg[i];
+        if (v != 0.0) atomicAdd(&d.delta[i], v);
+    }
+    for (int s = tid; s < S; s += T) {
+        if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
+        if (touched[s]) d.touched[s] = 1;
+    }
+    // counters: warp reduce, one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) {
+        nu += __shfl_down_sync(0xffffffffu, nu, off);
+        nv += __shfl_down_sync(0xffffffffu, nv, off);
+        ns += __shfl_down_sync(0xffffffffu, ns, off);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
+}
+
+// table += delta; delta = 0.  strategy_sum += count * sigma with sigma = RM(regret BEFORE the update),
+// i.e. the strategy the batch was sampled with.
+__global__ void __launch_bounds__(256) mccfr_apply_kernel(SolverDev d) {
+    const int S = d.n_slots;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        double reg[4], sg[4];
+        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+        const int n = d.slot_nlegal[s];
+        const double cnt = d.delta[4 * S + s];
+        if (cnt != 0.0) {
+            regret_match(reg, n, sg);
+            for (int i = 0; i < n; i++) d.strategy[4 * s + i] = __dadd_rn(d.strategy[4 * s + i], __dmul_rn(cnt, sg[i]));
+        }
+        for (int i = 0; i < 4; i++) {
+            const double dv = d.delta[4 * s + i];
+            if (dv != 0.0) d.regret[4 * s + i] = __dadd_rn(reg[i], dv);
+            d.delta[4 * s + i] = 0.0;
+        }
+        d.delta[4 * S + s] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Best response against the table's average policy (restated open_spiel BestResponsePolicy, see
+// oracle/ms_exploit.py for the algorithm; third-party, parity unpinned).  Same level-synchronous
+// skeleton as CFR: counterfactual reach top-down, then bottom-up values with one argmax per
+// infoset of the best responder.
+__device__ __forceinline__ void avg_policy(const SolverDev& d, int s, int kind, double* out) {
+    const int n = d.slot_nlegal[s];
+    double st[4], tot = 0.0;
+    for (int i = 0; i < 4; i++) { st[i] = (i < n) ? d.strategy[4 * s + i] : 0.0; if (i < n) tot = __dadd_rn(tot, st[i]); }
+    bool use;
+    if (kind == 0) use = tot > 0.0;                                   // LearnedCFRPolicy / InfoNode.policy
+    else if (kind == 1) use = d.touched[s] && tot > 1e-12;            // ScopaLearnedPolicy (unseen key -> uniform)
+    else use = false;
+    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (use ? __ddiv_rn(st[i], tot) : __ddiv_rn(1.0, (double)n)) : 0.0;
+}
+
+__global__ void __launch_bounds__(512, 1) best_response_kernel(SolverDev d, int n_dec, int kind, double* out2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_lvl[MAXL + 1], s_slvl[MAXL + 1];
+    const int tid = threadIdx.x, bd = blockDim.x;
+    const int N = d.n_nodes, S = d.n_slots, L = d.n_levels;
+    CfrSmem m = cfr_carve(smem_raw, N, S, n_dec);   // reg is unused; sig holds the average policy
+    for (int i = tid; i <= L; i += bd) { s_lvl[i] = d.level_begin[i]; s_slvl[i] = d.slot_level_begin[i]; }
+    for (int i = tid; i < N; i += bd) {
+        m.child_begin[i] = d.child_begin[i]; m.nchild[i] = d.nchild[i];
+        m.node_slot[i] = d.node_slot[i]; m.rx2[i] = d.rx2[i];
+    }
+    for (int i = tid; i < n_dec; i += bd) m.chain_nodes[i] = d.chain_nodes[i];
+    for (int i = tid; i <= S; i += bd) m.chain_begin[i] = d.chain_begin[i];
+    for (int s = tid; s < S; s += bd) {
+        m.nlegal[s] = d.slot_nlegal[s];
+        double p[4];
+        avg_policy(d, s, kind, p);
+        for (int i = 0; i < 4; i++) m.sig[4 * s + i] = p[i];
+    }
+    __syncthreads();
+    for (int b = 0; b < 2; b++) {
+        if (tid == 0) m.r[0] = 1.0;
+        __syncthreads();
+        for (int l = 0; l + 1 < L; l++) {
+            const int cp = (d.root_cur + l) & 1;
+            for (int v = s_lvl[l] + tid; v < s_lvl[l + 1]; v += bd) {
+                const int nc = m.nchild[v];
+                if (nc == 0) continue;
+                const int cb = m.child_begin[v];
+                const double cf = m.r[v];
+                const double* pol = m.sig + 4 * m.node_slot[v];
+                for (int i = 0; i < nc; i++) m.r[cb + i] = (cp == b) ? cf : __dmul_rn(cf, pol[i]);
+            }
+            __syncthreads();
+        }
+        for (int l = L - 1; l >= 0; l--) {
+            const int cp = (d.root_cur + l) & 1;
+            for (int v = s_lvl[l] + tid; v < s_lvl[l + 1]; v += bd) {
+                const int nc = m.nchild[v];
+                if (nc == 0) {
+                    const double r = 0.5 * (double)m.rx2[v];
+                    m.u[v] = (b == 0) ? r : -r;
+                } else if (cp != b) {
+                    const int cb = m.child_begin[v];
+                    const double* pol = m.sig + 4 * m.node_slot[v];
+                    double acc = 0.0;
+                    for (int i = 0; i < nc; i++)
+                        if (pol[i] > 0.0) acc = __dadd_rn(acc, __dmul_rn(pol[i], m.u[cb + i]));
+                    m.u[v] = acc;
+                }
+            }
+            if (cp == b) {
+                for (int s = s_slvl[l] + tid; s < s_slvl[l + 1]; s += bd) {
+                    const int n = m.nlegal[s];
+                    int best = 0; double bestq = 0.0;
+                    for (int a = 0; a < n; a++) {
+                        double q = 0.0;
+                        for (int k = m.chain_begin[s]; k < m.chain_begin[s + 1]; k++) {
+                            const int v = m.chain_nodes[k];
+                            q = __dadd_rn(q, __dmul_rn(m.r[v], m.u[m.child_begin[v] + a]));
+                        }
+                        if (a == 0 || q > bestq) { best = a; bestq = q; }   // first maximum in legal order
+                    }
+                    for (int k = m.chain_begin[s]; k < m.chain_begin[s + 1]; k++) {
+                        const int v = m.chain_nodes[k];
+                        m.u[v] = m.u[m.child_begin[v] + best];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) out2[b] = m.u[0];
+        __syncthreads();
+    }
+}
+
+}  // namespace ms
+
+using namespace ms;
+
+// ------------------------------------------------------------------------------------------------
+struct ms_solver {
+    int device = 0;
+    ms_state root{};
+    uint32_t hand_order = 0;
+    int n_nodes = 0, n_levels = 0, n_slots = 0, n_dec = 0, hcap = 0, nframes = 4;
+    std::vector<int> level_begin, slot_level_begin;
+    // host copies for export
+    std::vector<ms_state> h_state; std::vector<int> h_parent, h_child_begin, h_slot; std::vector<uint8_t> h_nchild, h_level;
+    std::vector<unsigned long long> h_slot_key; std::vector<uint8_t> h_slot_nlegal, h_slot_legal;
+    char* d_block = nullptr;   // one allocation for everything
+    SolverDev dev{};
+    double* d_value = nullptr; // [2] scratch for returned values
+};
+
+namespace {
+
+template <typename T>
+T* carve(char*& p, size_t n) {
+    T* r = (T*)p;
+    p += (n * sizeof(T) + 255) & ~(size_t)255;
+    return r;
+}
+
+int solver_build(ms_solver* sv) {
+    // ---- 1. enumerate the tree on the device
+    char* tmp = nullptr;
+    size_t tb = (size_t)MAXN * (16 + 4 + 4 + 1 + 8 + 2 + 1) + 4096;
+    MS_CUDA(cudaMalloc(&tmp, tb + 4096));
+    char* p = tmp;
+    TreeOut t;
+    t.state = carve<uint4>(p, MAXN); t.parent = carve<int>(p, MAXN); t.child_begin = carve<int>(p, MAXN);
+    t.key = carve<unsigned long long>(p, MAXN); t.legal = carve<uint16_t>(p, MAXN);
+    t.nchild = carve<uint8_t>(p, MAXN); t.rx2 = carve<int8_t>(p, MAXN);
+    t.level_begin = carve<int>(p, MAXL + 2); t.counts = carve<int>(p, 4);
+    uint4 root = make_uint4(sv->root.hands, sv->root.table, sv->root.captures, sv->root.meta);
+    tree_expand_kernel<<<1, 256>>>(root, sv->hand_order, t);
+    MS_LAUNCH_CHECK();
+    int counts[4] = {0, 0, 0, 0};
+    MS_CUDA(cudaMemcpy(counts, t.counts, sizeof(int) * 3, cudaMemcpyDeviceToHost));
+    if (counts[2]) { cudaFree(tmp); return fail(MS_ERR_CAPACITY, "game tree exceeds %d nodes / %d levels", MAXN, MAXL); }
+    const int N = counts[0], L = counts[1];
+    sv->n_nodes = N; sv->n_levels = L;
+    sv->level_begin.resize(L + 1);
+    MS_CUDA(cudaMemcpy(sv->level_begin.data(), t.level_begin, sizeof(int) * (L + 1), cudaMemcpyDeviceToHost));
+    sv->h_state.resize(N); sv->h_parent.resize(N); sv->h_child_begin.resize(N); sv->h_nchild.resize(N);
+    std::vector<unsigned long long> key(N); std::vector<uint16_t> legal(N); std::vector<int8_t> rx2(N);
+    MS_CUDA(cudaMemcpy(sv->h_state.data(), t.state, 16 * (size_t)N, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(sv->h_parent.data(), t.parent, 4 * (size_t)N, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(sv->h_child_begin.data(), t.child_begin, 4 * (size_t)N, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(sv->h_nchild.data(), t.nchild, (size_t)N, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(key.data(), t.key, 8 * (size_t)N, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(legal.data(), t.legal, 2 * (size_t)N, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(rx2.data(), t.rx2, (size_t)N, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaFree(tmp));
+
+    // ---- 2. index the infosets on the host (pure bookkeeping: no game rules here).
+    // Slots are numbered in breadth-first first-occurrence order: deterministic, hence identical on
+    // every GPU -> slot-aligned arrays across ranks.
+    sv->h_level.assign(N, 0);
+    for (int l = 0; l < L; l++) for (int v = sv->level_begin[l]; v < sv->level_begin[l + 1]; v++) sv->h_level[v] = (uint8_t)l;
+    sv->h_slot.assign(N, -1);
+    std::unordered_map<unsigned long long, int> slot_of;
+    std::vector<int> slot_level;
+    std::vector<std::vector<int>> chains;
+    sv->h_slot_key.clear(); sv->h_slot_nlegal.clear(); sv->h_slot_legal.clear();
+    for (int v = 0; v < N; v++) {
+        if (sv->h_nchild[v] == 0) continue;
+        auto it = slot_of.find(key[v]);
+        int s;
+        if (it == slot_of.end()) {
+            s = (int)chains.size();
+            slot_of.emplace(key[v], s);
+            chains.emplace_back();
+            slot_level.push_back(sv->h_level[v]);
+            sv->h_slot_key.push_back(key[v]);
+            sv->h_slot_nlegal.push_back(sv->h_nchild[v]);
+            for (int i = 0; i < 4; i++)
+                sv->h_slot_legal.push_back(i < sv->h_nchild[v] ? (uint8_t)((legal[v] >> (4 * i)) & 0xF) : (uint8_t)0xFF);
+        } else {
+            s = it->second;
+            if (slot_level[s] != sv->h_level[v])
+                return fail(MS_ERR_ARG, "unsupported root: an infoset recurs at two depths (pass moves inside the tree)");
+            if (sv->h_slot_nlegal[s] != sv->h_nchild[v]) return fail(MS_ERR_ARG, "inconsistent legal count inside an infoset");
+        }
+        sv->h_slot[v] = s;
+        chains[s].push_back(v);
+    }
+    const int S = (int)chains.size();
+    if (S > MAXS) return fail(MS_ERR_CAPACITY, "%d infosets exceed the table capacity %d", S, MAXS);
+    sv->n_slots = S;
+    sv->slot_level_begin.assign(L + 1, S);
+    {
+        int s = 0;
+        for (int l = 0; l <= L; l++) {
+            while (s < S && slot_level[s] < l) s++;
+            sv->slot_level_begin[l] = s;
+        }
+    }
+    std::vector<uint16_t> chain_begin(S + 1), chain_nodes;
+    for (int s = 0; s < S; s++) {
+        chain_begin[s] = (uint16_t)chain_nodes.size();
+        for (int v : chains[s]) chain_nodes.push_back((uint16_t)v);
+    }
+    chain_begin[S] = (uint16_t)chain_nodes.size();
+    sv->n_dec = (int)chain_nodes.size();
+    int hcap = 1024;
+    while (hcap < 2 * S + 2) hcap *= 2;
+    sv->hcap = hcap;
+    std::vector<unsigned long long> hk(hcap, 0xFFFFFFFFFFFFFFFFull);
+    std::vector<int16_t> hs(hcap, -1);
+    for (int s = 0; s < S; s++) {
+        uint32_t h = (uint32_t)((sv->h_slot_key[s] * 0x9E3779B97F4A7C15ull) >> 40) & (uint32_t)(hcap - 1);
+        while (hk[h] != 0xFFFFFFFFFFFFFFFFull) h = (h + 1) & (uint32_t)(hcap - 1);
+        hk[h] = sv->h_slot_key[s]; hs[h] = (int16_t)s;
+    }
+    const int root_cur = (int)((sv->root.meta >> 17) & 1u);
+    // frames needed by the sampled traversals: decision levels of one player
+    int dl[2] = {0, 0};
+    for (int l = 0; l < L; l++) {
+        bool any = false;
+        for (int v = sv->level_begin[l]; v < sv->level_begin[l + 1]; v++) any |= sv->h_nchild[v] > 0;
+        if (any) dl[(root_cur + l) & 1]++;
+    }
+    sv->nframes = std::max(1, std::max(dl[0], dl[1]));
+
+    // ---- 3. upload
+    size_t total = 0;
+    auto sz = [&](size_t n) { size_t b = (n + 255) & ~(size_t)255; total += b; return b; };
+    sz(4 * (L + 1)); sz(2 * N); sz(N); sz(2 * N); sz(N); sz(2 * (S + 1)); sz(2 * sv->n_dec); sz(4 * (L + 1)); sz(S); sz(S);
+    sz(8 * hcap); sz(2 * hcap); sz(32 * S); sz(32 * S); sz(8 * (5 * S)); sz(S); sz(8 * 4); sz(16);
+    MS_CUDA(cudaMalloc(&sv->d_block, total + 4096));
+    MS_CUDA(cudaMemset(sv->d_block, 0, total + 4096));
+    p = sv->d_block;
+    std::vector<uint16_t> cb16(N); std::vector<int16_t> ns16(N); std::vector<uint8_t> splayer(S);
+    for (int v = 0; v < N; v++) { cb16[v] = (uint16_t)sv->h_child_begin[v]; ns16[v] = (int16_t)sv->h_slot[v]; }
+    for (int s = 0; s < S; s++) splayer[s] = (uint8_t)((sv->h_slot_key[s] >> 52) & 1ull);
+    SolverDev& d = sv->dev;
+    d.n_nodes = N; d.n_levels = L; d.n_slots = S; d.root_cur = root_cur; d.root = root; d.hand_order = sv->hand_order; d.hcap = hcap;
+#define UP(field, T, vec, n)                                                                    \
+    do { T* q = carve<T>(p, (n)); MS_CUDA(cudaMemcpy(q, (vec).data(), sizeof(T) * (n), cudaMemcpyHostToDevice)); d.field = q; } while (0)
+    UP(level_begin, int, sv->level_begin, (size_t)L + 1);
+    UP(child_begin, uint16_t, cb16, (size_t)N);
+    UP(nchild, uint8_t, sv->h_nchild, (size_t)N);
+    UP(node_slot, int16_t, ns16, (size_t)N);
+    UP(rx2, int8_t, rx2, (size_t)N);
+    UP(chain_begin, uint16_t, chain_begin, (size_t)S + 1);
+    UP(chain_nodes, uint16_t, chain_nodes, (size_t)sv->n_dec);
+    UP(slot_level_begin, int, sv->slot_level_begin, (size_t)L + 1);
+    UP(slot_nlegal, uint8_t, sv->h_slot_nlegal, (size_t)S);
+    UP(slot_player, uint8_t, splayer, (size_t)S);
+    UP(hkeys, unsigned long long, hk, (size_t)hcap);
+    UP(hslots, int16_t, hs, (size_t)hcap);
+#undef UP
+    d.regret = carve<double>(p, 4 * (size_t)S);
+    d.strategy = carve<double>(p, 4 * (size_t)S);
+    d.delta = carve<double>(p, 5 * (size_t)S);
+    d.touched = carve<uint8_t>(p, (size_t)S);
+    d.counters = carve<unsigned long long>(p, 4);
+    sv->d_value = carve<double>(p, 2);
+    return MS_OK;
+}
+
+int check_dev(const ms_solver* s) {
+    if (!s) return fail(MS_ERR_ARG, "null solver");
+    int dev = -1;
+    MS_CUDA(cudaGetDevice(&dev));
+    if (dev != s->device) return fail(MS_ERR_STATE, "solver lives on device %d but the current device is %d", s->device, dev);
+    return MS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ms_solver_create(const ms_state* h_root, uint32_t hand_order, ms_solver** out) {
+    if (!h_root || !out) return fail(MS_ERR_ARG, "ms_solver_create: bad argument");
+    ms_solver* sv = new ms_solver();
+    sv->root = *h_root; sv->hand_order = hand_order;
+    cudaError_t e = cudaGetDevice(&sv->device);
+    if (e != cudaSuccess) { delete sv; return fail(MS_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e)); }
+    int rc = solver_build(sv);
+    if (rc) { if (sv->d_block) cudaFree(sv->d_block); delete sv; return rc; }
+    *out = sv;
+    return MS_OK;
+}
+
+void ms_solver_destroy(ms_solver* s) {
+    if (!s) return;
+    if (s->d_block) cudaFree(s->d_block);
+    delete s;
+}
+
+int ms_solver_reset(ms_solver* s, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    const size_t S = s->n_slots;
+    cudaStream_t st = (cudaStream_t)stream;
+    MS_CUDA(cudaMemsetAsync(s->dev.regret, 0, 32 * S, st));
+    MS_CUDA(cudaMemsetAsync(s->dev.strategy, 0, 32 * S, st));
+    MS_CUDA(cudaMemsetAsync(s->dev.delta, 0, 40 * S, st));
+    MS_CUDA(cudaMemsetAsync(s->dev.touched, 0, S, st));
+    MS_CUDA(cudaMemsetAsync(s->dev.counters, 0, 32, st));
+    return MS_OK;
+}
+
+int ms_solver_counts(const ms_solver* s, int32_t* n_nodes, int32_t* n_slots, int32_t* n_levels) {
+    if (!s) return fail(MS_ERR_ARG, "null solver");
+    if (n_nodes) *n_nodes = s->n_nodes;
+    if (n_slots) *n_slots = s->n_slots;
+    if (n_levels) *n_levels = s->n_levels;
+    return MS_OK;
+}
+
+int ms_solver_export_tree(const ms_solver* s, ms_state* h_states, int32_t* h_parent, uint8_t* h_level, int32_t* h_slot,
+                          int32_t* h_child_begin, uint8_t* h_nchild) {
+    if (!s) return fail(MS_ERR_ARG, "null solver");
+    const size_t N = s->n_nodes;
+    if (h_states) memcpy(h_states, s->h_state.data(), 16 * N);
+    if (h_parent) memcpy(h_parent, s->h_parent.data(), 4 * N);
+    if (h_level) memcpy(h_level, s->h_level.data(), N);
+    if (h_slot) memcpy(h_slot, s->h_slot.data(), 4 * N);
+    if (h_child_begin) memcpy(h_child_begin, s->h_child_begin.data(), 4 * N);
+    if (h_nchild) memcpy(h_nchild, s->h_nchild.data(), N);
+    return MS_OK;
+}
+
+int ms_solver_export_table(const ms_solver* s, uint64_t* h_keys, uint8_t* h_nlegal, uint8_t* h_legal, double* h_regret,
+                           double* h_strategy, uint8_t* h_touched, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    const size_t S = s->n_slots;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h_keys) memcpy(h_keys, s->h_slot_key.data(), 8 * S);
+    if (h_nlegal) memcpy(h_nlegal, s->h_slot_nlegal.data(), S);
+    if (h_legal) memcpy(h_legal, s->h_slot_legal.data(), 4 * S);
+    if (h_regret) MS_CUDA(cudaMemcpyAsync(h_regret, s->dev.regret, 32 * S, cudaMemcpyDeviceToHost, st));
+    if (h_strategy) MS_CUDA(cudaMemcpyAsync(h_strategy, s->dev.strategy, 32 * S, cudaMemcpyDeviceToHost, st));
+    if (h_touched) MS_CUDA(cudaMemcpyAsync(h_touched, s->dev.touched, S, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+int ms_solver_import_table(ms_solver* s, const double* h_regret, const double* h_strategy, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    const size_t S = s->n_slots;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h_regret) MS_CUDA(cudaMemcpyAsync(s->dev.regret, h_regret, 32 * S, cudaMemcpyHostToDevice, st));
+    if (h_strategy) MS_CUDA(cudaMemcpyAsync(s->dev.strategy, h_strategy, 32 * S, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+int ms_solver_device_ptrs(ms_solver* s, double** d_regret, double** d_strategy, double** d_delta, size_t* n_table,
+                          size_t* n_delta) {
+    if (!s) return fail(MS_ERR_ARG, "null solver");
+    if (d_regret) *d_regret = s->dev.regret;
+    if (d_strategy) *d_strategy = s->dev.strategy;
+    if (d_delta) *d_delta = s->dev.delta;
+    if (n_table) *n_table = 4 * (size_t)s->n_slots;
+    if (n_delta) *n_delta = 5 * (size_t)s->n_slots;
+    return MS_OK;
+}
+
+static int launch_cfr(ms_solver* s, int iters, int only_player, double r0, double r1, double* d_out, cudaStream_t st) {
+    const size_t smem = cfr_smem_bytes(s->n_nodes, s->n_slots, s->n_dec);
+    if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "CFR working set %zu B exceeds shared memory", smem);
+    MS_CUDA(cudaFuncSetAttribute(cfr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfr_kernel<<<1, 512, smem, st>>>(s->dev, s->n_dec, iters, only_player, r0, r1, d_out);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_cfr_iterate(ms_solver* s, int32_t iters, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (iters < 0) return fail(MS_ERR_ARG, "iters < 0");
+    if (iters == 0) return MS_OK;
+    return launch_cfr(s, iters, -1, 1.0, 1.0, nullptr, (cudaStream_t)stream);
+}
+
+int ms_cfr_traverse(ms_solver* s, int32_t player, double reach_p0, double reach_p1, double* h_value, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (player < 0 || player > 1) return fail(MS_ERR_ARG, "player must be 0 or 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_cfr(s, 1, player, reach_p0, reach_p1, s->d_value, st);
+    if (rc) return rc;
+    if (h_value) {
+        MS_CUDA(cudaMemcpyAsync(h_value, s->d_value, 8, cudaMemcpyDeviceToHost, st));
+        MS_CUDA(cudaStreamSynchronize(st));
+    }
+    return MS_OK;
+}
+
+int ms_mccfr_inplace(ms_solver* s, int64_t iters, uint64_t philox_seed, uint64_t first_iter, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (iters < 0) return fail(MS_ERR_ARG, "iters < 0");
+    if (iters == 0) return MS_OK;
+    const int S = s->n_slots, nf = s->nframes;
+    size_t smem = 64 * (size_t)S + 8 * (size_t)s->hcap + (size_t)nf * 44 + 2 * (size_t)s->hcap + S + 64;
+    if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "MCCFR in-place working set %zu B exceeds shared memory", smem);
+    MS_CUDA(cudaFuncSetAttribute(mccfr_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mccfr_inplace_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(
+        s->dev, (long long)iters, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
+        (unsigned long long)first_iter, nf);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch: bad argument");
+    if (n_trav == 0) return MS_OK;
+    const size_t smem = mccfr_batch_smem(s->n_slots, s->hcap, s->nframes, MCCFR_THREADS);
+    if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "MCCFR batch working set %zu B exceeds shared memory", smem);
+    MS_CUDA(cudaFuncSetAttribute(mccfr_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((227 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const int grid = grid_for(n_trav, MCCFR_THREADS, per_sm);
+    mccfr_batch_kernel<<<grid, MCCFR_THREADS, smem, (cudaStream_t)stream>>>(
+        s->dev, player, (long long)n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
+        (unsigned long long)first_trav, s->nframes);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_mccfr_apply(ms_solver* s, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    mccfr_apply_kernel<<<(s->n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(s->dev);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_solver_counters(ms_solver* s, uint64_t h_out[3], int reset, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h_out) {
+        MS_CUDA(cudaMemcpyAsync(h_out, s->dev.counters, 24, cudaMemcpyDeviceToHost, st));
+        MS_CUDA(cudaStreamSynchronize(st));
+    }
+    if (reset) MS_CUDA(cudaMemsetAsync(s->dev.counters, 0, 32, st));
+    return MS_OK;
+}
+
+int ms_best_response(ms_solver* s, int32_t policy_kind, double h_br_values[2], void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (policy_kind < 0 || policy_kind > 2 || !h_br_values) return fail(MS_ERR_ARG, "ms_best_response: bad argument");
+    const size_t smem = cfr_smem_bytes(s->n_nodes, s->n_slots, s->n_dec);
+    if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "BR working set %zu B exceeds shared memory", smem);
+    cudaStream_t st = (cudaStream_t)stream;
+    MS_CUDA(cudaFuncSetAttribute(best_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    best_response_kernel<<<1, 512, smem, st>>>(s->dev, s->n_dec, policy_kind, s->d_value);
+    MS_LAUNCH_CHECK();
+    MS_CUDA(cudaMemcpyAsync(h_br_values, s->d_value, 16, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+}  // extern "C"
