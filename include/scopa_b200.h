@@ -54,6 +54,10 @@ uint64_t ms_launch_count(void);
 int ms_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_state* d_states, uint32_t* d_hand_order,
                        void* stream);
 
+/* test hook: the same result through the kernel's rarely-taken slow path (full MT19937 state) */
+int ms_debug_deal_slow_path(const int64_t* d_seeds, int64_t n, ms_state* d_states, uint32_t* d_hand_order,
+                            void* stream);
+
 /* ms_step: MiniScopaEnv.step(action) on n independent states in place (src/envs/mini_scopa_game.py:140-167
  *   incl. play_card :93-104, card_in_table :66-91, evaluate_game :106-114).  d_rewards ([n][2] f32,
  *   may be NULL) receives the terminal rewards (0,0 while running); d_done ([n] u8, may be NULL)

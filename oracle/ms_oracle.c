@@ -156,17 +156,21 @@ ora_rng* ora_rng_new(int kind, uint64_t seed) {
 }
 void ora_rng_free(ora_rng* r) { free(r); }
 
-static void rng_philox(const ora_rng* r, uint32_t out[4]) {
-    uint32_t ctr[4] = {(uint32_t)r->trav, (uint32_t)(r->trav >> 32), r->call, r->tag};
+/* Philox addressing of the traversal streams: one 4-word block serves two consecutive call indices:
+ * ctr = (traversal id lo, hi, call >> 1, tag); call c uses words 2*(c&1) and 2*(c&1)+1. */
+static void rng_philox(const ora_rng* r, uint32_t out2[2]) {
+    uint32_t ctr[4] = {(uint32_t)r->trav, (uint32_t)(r->trav >> 32), r->call >> 1, r->tag};
     uint32_t key[2] = {(uint32_t)r->seed, (uint32_t)(r->seed >> 32)};
-    philox4x32_10(ctr, key, out);
+    uint32_t o[4];
+    philox4x32_10(ctr, key, o);
+    out2[0] = o[2 * (r->call & 1u)]; out2[1] = o[2 * (r->call & 1u) + 1];
 }
 
 /* uniform double in [0,1): numpy random_sample == (a>>5, b>>6) 53-bit; same formula on Philox words */
 static double rng_double(ora_rng* r) {
     uint32_t a, b;
     if (r->kind == 0) { a = mt_next(&r->mt) >> 5; b = mt_next(&r->mt) >> 6; }
-    else { uint32_t o[4]; rng_philox(r, o); a = o[0] >> 5; b = o[1] >> 6; }
+    else { uint32_t o[2]; rng_philox(r, o); a = o[0] >> 5; b = o[1] >> 6; }
     return (a * 67108864.0 + b) / 9007199254740992.0;
 }
 
@@ -196,7 +200,7 @@ static int rng_choice_uniform(ora_rng* r, int n) {
         do { v = mt_next(&r->mt) & mask; } while (v > rng);
         return (int)v;
     }
-    uint32_t o[4]; rng_philox(r, o);
+    uint32_t o[2]; rng_philox(r, o);
     return (int)(((uint64_t)o[0] * (uint64_t)n) >> 32);
 }
 

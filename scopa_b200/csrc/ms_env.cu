@@ -22,56 +22,111 @@ char* last_error_buf() {
 // K0  deal: CPython random.seed(int) + random.shuffle of the 16-card deck, one thread per seed.
 //   replaces MiniDeck.__init__ / MiniScopaGame.reset (src/envs/mini_scopa_game.py:25-28, :56-64).
 // random.seed(n) = MT19937 init_by_array(32-bit words of |n|): two dependent passes over the 624-word
-// state.  The first pass starts from init_genrand(19650218), which does not depend on the seed, so
-// that table is computed once on the host and read through L1 (same address across the warp).
-// The per-thread 624-word state lives in local memory (interleaved per lane -> coalesced lines).
-// Only the first ~16-20 outputs are needed, so the twist is evaluated lazily for those indices.
+// state, the second reading every word the first wrote.  Storing that state per thread (2.5 KB) made
+// the first version of this kernel DRAM-bound on local memory (profiles/README.md, r01: 7.5 GB of
+// traffic per 1 M seeds).  Pass 1 is therefore RECOMPUTED instead of stored: it runs once to obtain the
+// two words pass 2 starts from, then again in lock-step with pass 2, whose results are kept only for
+// the ~2x40 state words the first outputs depend on (output j of the first block needs words j, j+1 and
+// j+397).  About 1.5x the integer work, no memory traffic.  Pass 1 starts from init_genrand(19650218),
+// which does not depend on the seed: that table is computed once on the host and read through L1.
 __device__ uint32_t g_mt_init[624];
+constexpr int DEAL_WIN = 40;   // MT outputs available on the fast path (a shuffle needs 15 + rejections)
 
-struct MtLazy {
-    uint32_t* mt;
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+// random.shuffle of the deck given a word source: for i in reversed(range(1, 16)): j = randbelow(i + 1);
+// swap.  randbelow(n): k = n.bit_length(); r = getrandbits(k) = word >> (32 - k); retry while r >= n.
+// Returns false if the source ran dry (fast path only).
+template <typename Gen>
+__device__ __forceinline__ bool shuffle_deck(Gen& gen, unsigned long long& perm) {
+    perm = 0xFEDCBA9876543210ull;   // nibble i = card id i (deck order, mini_scopa_game.py:26)
+    for (int i = 15; i >= 1; i--) {
+        const uint32_t nn = (uint32_t)i + 1u;
+        const int kbits = 32 - __clz(nn);
+        uint32_t r;
+        do {
+            uint32_t w;
+            if (!gen.next(w)) return false;
+            r = w >> (32 - kbits);
+        } while (r >= nn);
+        unsigned long long ci = (perm >> (4 * i)) & 0xFull, cr = (perm >> (4 * r)) & 0xFull;
+        perm &= ~((0xFull << (4 * i)) | (0xFull << (4 * r)));
+        perm |= (cr << (4 * i)) | (ci << (4 * r));
+    }
+    return true;
+}
+
+struct MtWindow {          // first DEAL_WIN outputs from the kept state words
+    const uint32_t* lo;    // mt[0 .. DEAL_WIN]
+    const uint32_t* hi;    // mt[397 .. 397 + DEAL_WIN - 1]
     int kk;
-    bool twisted;
-    __device__ __forceinline__ uint32_t next() {
-        uint32_t y;
-        if (!twisted && kk < 227) {
-            // output kk of the first block depends on untouched words kk, kk+1, kk+397 only
-            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-            y = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            kk++;
-        } else {
-            if (!twisted || kk >= 624) {   // astronomically rare (> 200 rejections): full twist
-                if (!twisted) {
-                    // state is still the seeded one; outputs 0..226 were produced lazily
-                    twisted = true;
-                } else {
-                    kk = 0;
-                }
-                int q;
-                for (q = 0; q < 227; q++) {
-                    uint32_t t = (mt[q] & 0x80000000u) | (mt[q + 1] & 0x7fffffffu);
-                    mt[q] = mt[q + 397] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
-                }
-                for (; q < 623; q++) {
-                    uint32_t t = (mt[q] & 0x80000000u) | (mt[q + 1] & 0x7fffffffu);
-                    mt[q] = mt[q - 227] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
-                }
-                uint32_t t = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
-                mt[623] = mt[396] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
-            }
-            y = mt[kk++];
-        }
-        y ^= (y >> 11);
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= (y >> 18);
-        return y;
+    __device__ __forceinline__ bool next(uint32_t& out) {
+        if (kk >= DEAL_WIN) return false;
+        uint32_t y = (lo[kk] & 0x80000000u) | (lo[kk + 1] & 0x7fffffffu);
+        y = hi[kk] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        kk++;
+        out = mt_temper(y);
+        return true;
     }
 };
 
-__global__ void __launch_bounds__(128) deal_kernel(const long long* __restrict__ seeds, long long n,
-                                                   uint4* __restrict__ states, uint32_t* __restrict__ hand_order) {
+struct MtFull {            // textbook generator over a full 624-word state (slow path)
+    uint32_t* mt;
+    int kk;
+    __device__ __forceinline__ bool next(uint32_t& out) {
+        if (kk >= 624) {
+            int q;
+            for (q = 0; q < 227; q++) {
+                uint32_t t = (mt[q] & 0x80000000u) | (mt[q + 1] & 0x7fffffffu);
+                mt[q] = mt[q + 397] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
+            }
+            for (; q < 623; q++) {
+                uint32_t t = (mt[q] & 0x80000000u) | (mt[q + 1] & 0x7fffffffu);
+                mt[q] = mt[q - 227] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
+            }
+            uint32_t t = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[623] = mt[396] ^ (t >> 1) ^ ((t & 1u) ? 0x9908b0dfu : 0u);
+            kk = 0;
+        }
+        out = mt_temper(mt[kk++]);
+        return true;
+    }
+};
+
+// Slow path (never taken in practice: needs > 25 rejected draws in one shuffle): the whole state in
+// local memory, textbook init_by_array + generator.
+__device__ __noinline__ unsigned long long deal_slow(uint32_t key0, uint32_t key1) {
     uint32_t mt[624];
+    const bool two = key1 != 0u;
+    for (int i = 0; i < 624; i++) mt[i] = g_mt_init[i];
+    int i = 1, j = 0;
+    for (int k = 0; k < 624; k++) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + ((j == 1) ? key1 : key0) + (uint32_t)j;
+        i++; j++;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+        if (j >= (two ? 2 : 1)) j = 0;
+    }
+    for (int k = 0; k < 623; k++) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        i++;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+    MtFull gen{mt, 624};
+    unsigned long long perm;
+    shuffle_deck(gen, perm);
+    return perm;
+}
+
+__global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__ seeds, long long n,
+                                                   uint4* __restrict__ states, uint32_t* __restrict__ hand_order) {
+    uint32_t lo[DEAL_WIN + 1], hi[DEAL_WIN];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
          g += (long long)gridDim.x * blockDim.x) {
         long long sd = seeds[g];
@@ -79,48 +134,56 @@ __global__ void __launch_bounds__(128) deal_kernel(const long long* __restrict__
         unsigned long long a = sd < 0 ? (unsigned long long)(-(sd + 1)) + 1ull : (unsigned long long)sd;
         const uint32_t key0 = (uint32_t)a, key1 = (uint32_t)(a >> 32);
         const bool two = key1 != 0u;   // key length: 32-bit words of |seed|, at least one
+        const uint32_t kodd = two ? key1 + 1u : key0;   // key[j] + j for odd steps (j = 1) / one-word keys
 
-        // init_by_array pass 1 (624 steps; i = 1..623 then wraps to i = 1)
-        uint32_t prev = g_mt_init[0];
+        // ---- pass 1, first run (nothing stored): step k writes word k+1 with key word j = k % len
+        uint32_t prev = g_mt_init[0], first1 = 0u;
         for (int k = 0; k < 623; k++) {
-            uint32_t kj = (two && (k & 1)) ? key1 : key0;
-            uint32_t jj = two ? (uint32_t)(k & 1) : 0u;
-            uint32_t cur = (g_mt_init[k + 1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + kj + jj;
-            mt[k + 1] = cur;
+            const uint32_t cur = (g_mt_init[k + 1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + ((k & 1) ? kodd : key0);
+            if (k == 0) first1 = cur;
             prev = cur;
         }
-        {   // step 624: mt[0] = mt[623]; i = 1; j = 623 % len
-            uint32_t kj = two ? key1 : key0;
-            uint32_t jj = two ? 1u : 0u;
-            uint32_t cur = (mt[1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + kj + jj;
-            mt[1] = cur;
-            prev = cur;
-        }
-        // pass 2 (623 steps: i = 2..623, wrap, i = 1)
-        for (int i = 2; i < 624; i++) {
-            uint32_t cur = (mt[i] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
-            mt[i] = cur;
-            prev = cur;
-        }
-        mt[1] = (mt[1] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - 1u;
-        mt[0] = 0x80000000u;
+        // step 624 wraps: mt[0] = mt[623]; word 1 is rewritten with j = 623 % len
+        const uint32_t m1w = (first1 ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;
 
-        // random.shuffle: for i in reversed(range(1, 16)): j = randbelow(i + 1); swap
-        // randbelow(n): k = n.bit_length(); r = getrandbits(k) = word >> (32 - k); retry while r >= n
-        MtLazy gen{mt, 0, false};
-        unsigned long long perm = 0xFEDCBA9876543210ull;   // nibble i = card id i (deck order :26)
-        for (int i = 15; i >= 1; i--) {
-            const uint32_t nn = (uint32_t)i + 1u;
-            const int kbits = 32 - __clz(nn);
-            uint32_t r;
-            do { r = gen.next() >> (32 - kbits); } while (r >= nn);
-            unsigned long long ci = (perm >> (4 * i)) & 0xFull, cr = (perm >> (4 * r)) & 0xFull;
-            perm &= ~((0xFull << (4 * i)) | (0xFull << (4 * r)));
-            perm |= (cr << (4 * i)) | (ci << (4 * r));
+        // ---- pass 2 (i = 2..623, then the wrap to i = 1) in lock-step with a second run of pass 1
+        uint32_t p1 = first1, p2 = m1w;
+        for (int i = 2; i < 624; i++) {
+            const uint32_t c1 = (g_mt_init[i] ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + (((i - 1) & 1) ? kodd : key0);
+            p1 = c1;
+            const uint32_t c2 = (c1 ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)i;
+            p2 = c2;
+            if (i <= DEAL_WIN) lo[i] = c2;
+            if (i >= 397 && i < 397 + DEAL_WIN) hi[i - 397] = c2;
         }
-        uint32_t ord = (uint32_t)perm;   // first 8 dealt cards: 4 to player 0, 4 to player 1
+        lo[1] = (m1w ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - 1u;
+        lo[0] = 0x80000000u;
+
+        MtWindow gen{lo, hi, 0};
+        unsigned long long perm;
+        if (!shuffle_deck(gen, perm)) perm = deal_slow(key0, key1);
+        const uint32_t ord = (uint32_t)perm;   // first 8 dealt cards: 4 to player 0, 4 to player 1
         uint32_t h0 = 0u, h1 = 0u;
 #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            h0 |= 1u << ((ord >> (4 * i)) & 0xFu);
+            h1 |= 1u << ((ord >> (16 + 4 * i)) & 0xFu);
+        }
+        states[g] = st_make(h0, h1, 8u);
+        hand_order[g] = ord;
+    }
+}
+
+// test hook: every seed through the slow path (exercised by tests/test_gpu_env.py)
+__global__ void __launch_bounds__(128) deal_slow_kernel(const long long* __restrict__ seeds, long long n,
+                                                        uint4* __restrict__ states, uint32_t* __restrict__ hand_order) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        long long sd = seeds[g];
+        if (sd == 0) sd = 42;
+        unsigned long long a = sd < 0 ? (unsigned long long)(-(sd + 1)) + 1ull : (unsigned long long)sd;
+        const uint32_t ord = (uint32_t)deal_slow((uint32_t)a, (uint32_t)(a >> 32));
+        uint32_t h0 = 0u, h1 = 0u;
         for (int i = 0; i < 4; i++) {
             h0 |= 1u << ((ord >> (4 * i)) & 0xFu);
             h1 |= 1u << ((ord >> (16 + 4 * i)) & 0xFu);
@@ -163,6 +226,7 @@ __global__ void __launch_bounds__(256) legal_kernel(const uint4* __restrict__ st
         uint32_t m = 0u;
         uint8_t o[4] = {0xFF, 0xFF, 0xFF, 0xFF}, c[4] = {0, 0, 0, 0};
         const uint32_t hand = st_hand(s, p);
+        const uint32_t tset = table_set(s.y, st_table_len(s));
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if ((uint32_t)k < nl) {
@@ -170,7 +234,7 @@ __global__ void __launch_bounds__(256) legal_kernel(const uint4* __restrict__ st
                 m |= 1u << a;
                 o[k] = (uint8_t)a;
                 // the fallback action [0] on an empty hand is a pass: it captures nothing
-                c[k] = ((hand >> a) & 1u) ? (uint8_t)capture_mask(s.y, st_table_len(s), card_rank(a)) : 0;
+                c[k] = ((hand >> a) & 1u) ? (uint8_t)capture_mask(s.y, st_table_len(s), a, tset) : 0;
             }
         }
         if (mask) mask[g] = (uint16_t)m;
@@ -186,7 +250,16 @@ __global__ void __launch_bounds__(256) capture_kernel(const uint4* __restrict__ 
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
          g += (long long)gridDim.x * blockDim.x) {
         const MsState s = states[g];
-        out[g] = (uint8_t)capture_mask(s.y, st_table_len(s), card_rank(cards[g] & 0xFu));
+        const uint32_t card = cards[g] & 0xFu, len = st_table_len(s);
+        const uint32_t tset = table_set(s.y, len);
+        uint32_t m = capture_mask(s.y, len, card, tset);
+        // card_in_table() of a card that itself lies on the table (never the case for a card played from
+        // a hand): it has the rank too, so the first of {card, twin} in table order is taken (:72-74)
+        if ((tset >> card) & 1u) {
+            const uint32_t self = 1u << nibble_pos(s.y, card);
+            m = ((tset >> card_twin(card)) & 1u) ? (m < self ? m : self) : self;
+        }
+        out[g] = (uint8_t)m;
     }
 }
 
@@ -212,6 +285,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const uint4* __restrict__ 
          g += (long long)gridDim.x * blockDim.x) {
         MsState s = states[g];
         const uint32_t ho = hand_order[g];
+        const uint32_t dealt = dealt_set(s);
         const unsigned long long gid = game_offset + (unsigned long long)g;
         uint32_t acts[2] = {0u, 0u};
 #pragma unroll
@@ -224,7 +298,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const uint4* __restrict__ 
                 const uint32_t nl = legal_list(s, ho, st_cur(s), list);
                 const uint32_t idx = __umulhi(xs[q], nl);
                 const uint32_t a = (list >> (4u * idx)) & 0xFu;
-                step(s, a);
+                step(s, a, table_set_from_dealt(s, dealt));
                 acts[blk] |= a << (8 * q);
             }
         }
@@ -298,9 +372,19 @@ int ms_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_state* d_states, ui
     if (n == 0) return MS_OK;
     int rc = ensure_mt_table();
     if (rc) return rc;
-    // 128-thread CTAs, 2.5 KB of local state per thread; 16 CTAs/SM keeps 2048 threads resident
-    deal_kernel<<<grid_for(n, 128, 16), 128, 0, (cudaStream_t)stream>>>(
+    deal_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         (const long long*)d_seeds, (long long)n, (uint4*)d_states, d_hand_order);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_debug_deal_slow_path(const int64_t* d_seeds, int64_t n, ms_state* d_states, uint32_t* d_hand_order, void* stream) {
+    if (n < 0 || (n > 0 && (!d_seeds || !d_states || !d_hand_order))) return fail(MS_ERR_ARG, "ms_debug_deal_slow_path: bad argument");
+    if (n == 0) return MS_OK;
+    int rc = ensure_mt_table();
+    if (rc) return rc;
+    deal_slow_kernel<<<grid_for(n, 128, 8), 128, 0, (cudaStream_t)stream>>>((const long long*)d_seeds, (long long)n,
+                                                                           (uint4*)d_states, d_hand_order);
     MS_LAUNCH_CHECK();
     return MS_OK;
 }

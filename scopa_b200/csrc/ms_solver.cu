@@ -348,9 +348,27 @@ __device__ __forceinline__ int sample_action(const double* sg, int n, double u) 
     return idx < n ? idx : n - 1;
 }
 
+// normalised cdf of one strategy, numpy's rule: cdf = cumsum(p); cdf /= cdf[-1]
+__device__ __forceinline__ void strategy_cdf(const double* sg, int n, double* cdf) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { if (i < n) acc = __dadd_rn(acc, sg[i]); cdf[i] = acc; }
+    const double last = acc;
+#pragma unroll
+    for (int i = 0; i < 4; i++) cdf[i] = (i < n) ? __ddiv_rn(cdf[i], last) : 2.0;
+}
+// searchsorted(cdf, u, side='right') on a precomputed normalised cdf (entries beyond n are 2.0)
+__device__ __forceinline__ int sample_cdf(const double* cdf, int n, double u) {
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) idx += (cdf[i] <= u) ? 1 : 0;
+    return idx < n ? idx : n - 1;
+}
+
 struct MccfrShared {
     const unsigned long long* hk; const int16_t* hs; int hcap;
     const double* sig;        // frozen strategies (batch mode), [S][4]
+    const double* cdf;        // their normalised cdfs (batch mode), [S][4]
     double* dreg;             // per-CTA private regret deltas (batch mode), [S][4]
     uint32_t* dcnt;           // per-CTA update counts (batch mode), [S]
     uint8_t* touched;         // per-CTA touched flags, [S]
@@ -363,8 +381,11 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
                                int fstride, unsigned long long& n_upd, unsigned long long& n_vis,
                                unsigned long long& n_step) {
     MsState s = d.root;
+    const uint32_t dealt = dealt_set(d.root);
     double ro = 1.0, sp = 1.0;
     int fi = -1;
+    uint4 xblk = make_uint4(0u, 0u, 0u, 0u);   // cached Philox block: serves call indices 2b and 2b+1
+    uint32_t xblk_id = 0xFFFFFFFFu;
     uint32_t call = 0;
     int ret_x2 = 0;
     bool returning = false;
@@ -390,12 +411,16 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
                 for (int i = 0; i < 4; i++) sg[i] = sh.sig[4 * slot + i];
             }
             sh.touched[slot] = 1;     // node created on first touch, for both players (mc_cfr.py:52)
-            const uint4 x = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), my_call, tag), pkey);
-            const int ai = sample_action(sg, (int)nl, u53(x.x, x.y));
+            if ((my_call >> 1) != xblk_id) {
+                xblk_id = my_call >> 1;
+                xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
+            }
+            const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
+            const int ai = INPLACE ? sample_action(sg, (int)nl, u) : sample_cdf(sh.cdf + 4 * slot, (int)nl, u);
             const uint32_t a = (list >> (4 * ai)) & 0xFu;
             if (p != tp) {            // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
                 ro = __dmul_rn(ro, sg[ai]);
-                step(s, a); n_step++;
+                step(s, a, table_set_from_dealt(s, dealt)); n_step++;
                 continue;
             }
             // traverser: push a frame, descend into the sampled action first (:58-67)
@@ -405,7 +430,7 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
             f_meta[o] = make_uint2((uint32_t)slot | (nl << 12), list);
             f_cfv[o] = 0u;
             sp = __dmul_rn(sp, sg[ai]);
-            step(s, a); n_step++;
+            step(s, a, table_set_from_dealt(s, dealt)); n_step++;
             continue;
         }
         // ---- a child returned ret_x2 to the top frame
@@ -432,7 +457,7 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
             s = f_st[o];
             ro = f_ro[o];
             sp = __dmul_rn(f_sp[o], sg[i]);
-            step(s, (meta.y >> (4 * i)) & 0xFu); n_step++;
+            step(s, (meta.y >> (4 * i)) & 0xFu, table_set_from_dealt(s, dealt)); n_step++;
             returning = false;
             continue;
         }
@@ -490,7 +515,7 @@ __global__ void __launch_bounds__(32, 1) mccfr_inplace_kernel(SolverDev d, long 
     for (int i = tid; i < S; i += 32) touched[i] = d.touched[i];
     __syncwarp();
     if (tid == 0) {
-        MccfrShared sh{hk, hs, d.hcap, nullptr, nullptr, nullptr, touched, reg, str};
+        MccfrShared sh{hk, hs, d.hcap, nullptr, nullptr, nullptr, nullptr, touched, reg, str};
         unsigned long long nu = 0, nv = 0, ns = 0;
         for (long long it = 0; it < iters; it++)
             for (int tp = 0; tp < 2; tp++)
@@ -507,7 +532,7 @@ constexpr int MCCFR_THREADS = 512;
 
 __host__ __device__ inline size_t mccfr_batch_smem(int S, int hcap, int nframes, int threads) {
     size_t b = 0;
-    b += sizeof(double) * 8 * (size_t)S;                 // sigma + regret deltas
+    b += sizeof(double) * 12 * (size_t)S;                // sigma + cdf + regret deltas
     b += sizeof(unsigned long long) * (size_t)hcap;      // hash keys
     b += (size_t)threads * nframes * (16 + 8 + 8 + 8 + 4);   // frames
     b += sizeof(uint32_t) * (size_t)S;                   // counts
@@ -524,7 +549,8 @@ __global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = d.n_slots, T = blockDim.x, tid = threadIdx.x;
     double* sig = (double*)smem_raw;
-    double* dreg = sig + 4 * S;
+    double* cdf = sig + 4 * S;
+    double* dreg = cdf + 4 * S;
     unsigned long long* hk = (unsigned long long*)(dreg + 4 * S);
     uint4* f_st = (uint4*)(hk + d.hcap);
     double* f_ro = (double*)(f_st + (size_t)T * nframes);
@@ -539,13 +565,15 @@ __global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev
         double reg[4], sg[4];
         for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
         regret_match(reg, d.slot_nlegal[s], sg);
-        for (int i = 0; i < 4; i++) { sig[4 * s + i] = sg[i]; dreg[4 * s + i] = 0.0; }
+        double cd[4];
+        strategy_cdf(sg, d.slot_nlegal[s], cd);
+        for (int i = 0; i < 4; i++) { sig[4 * s + i] = sg[i]; cdf[4 * s + i] = cd[i]; dreg[4 * s + i] = 0.0; }
         dcnt[s] = 0u; touched[s] = 0;
     }
     for (int i = tid; i < d.hcap; i += T) { hk[i] = d.hkeys[i]; hs[i] = d.hslots[i]; }
     __syncthreads();
 
-    MccfrShared sh{hk, hs, d.hcap, sig, dreg, dcnt, touched, nullptr, nullptr};
+    MccfrShared sh{hk, hs, d.hcap, sig, cdf, dreg, dcnt, touched, nullptr, nullptr};
     unsigned long long nu = 0, nv = 0, ns = 0;
     const long long gstride = (long long)gridDim.x * T;
     for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += gstride) {

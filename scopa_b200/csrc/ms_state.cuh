@@ -50,33 +50,68 @@ __device__ __forceinline__ MsState st_make(uint32_t hand0, uint32_t hand1, uint3
     return s;
 }
 
+// Each rank value appears on exactly two cards (mini_scopa_game.py:18-23), so the only table card
+// that can have the rank of a played card c is its twin: nibble c of this LUT.
+#define MS_TWIN_LUT 0x369872DCBE10FA54ull
+__device__ __forceinline__ uint32_t card_twin(uint32_t c) {
+    return (uint32_t)(MS_TWIN_LUT >> (4u * c)) & 0xFu;
+}
+
+// set of card ids on the table (from the ordered nibble list)
+__device__ __forceinline__ uint32_t table_set(uint32_t order, uint32_t len) {
+    uint32_t m = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if ((uint32_t)i >= len) break;
+        m |= 1u << ((order >> (4 * i)) & 0xFu);
+    }
+    return m;
+}
+
+// position (0..7) of the lowest nibble of `order` equal to `c` (caller guarantees there is one)
+__device__ __forceinline__ uint32_t nibble_pos(uint32_t order, uint32_t c) {
+    const uint32_t x = order ^ (c * 0x11111111u);
+    const uint32_t z = (x - 0x11111111u) & ~x & 0x88888888u;   // lowest flagged nibble is an exact zero nibble
+    return (uint32_t)(__ffs((int)z) - 1) >> 2;
+}
+
+// drop nibble p from an ordered nibble list (higher nibbles move down)
+__device__ __forceinline__ uint32_t nibble_remove(uint32_t order, uint32_t p) {
+    const uint32_t low = (1u << (4u * p)) - 1u;
+    return (order & low) | ((order >> 4) & ~low);
+}
+
 // Capture resolution -- MiniScopaGame.card_in_table (mini_scopa_game.py:66-91).
 // Returns the bitmask over TABLE POSITIONS (bit i = i-th oldest card) of the captured cards, 0 if
-// the card is placed.
-//   * equal rank present  -> exactly the first such card in table order (:72-74);
+// the card is placed.  `tset` = set of card ids on the table.
+//   * equal rank present  -> exactly the first such card in table order (:72-74); only the played
+//     card's twin can match, so this is one bit test plus a nibble search;
 //   * otherwise the reference's 1-D DP returns the first-found subset, which is the subset with the
 //     minimum numeric position mask (proof in DESIGN.md "Capture rule"): computed here with prefix
 //     reachable-sum bitsets R[i] (bit s set <=> some subset of the i oldest cards sums to s) and a
 //     top-down walk that takes card i only when the remaining target is NOT reachable without it.
-__device__ __forceinline__ uint32_t capture_mask(uint32_t order, uint32_t len, uint32_t rank) {
+//     Loops are bounded by the table length (early exit), which is warp-coherent in tree traversals.
+__device__ __forceinline__ uint32_t capture_mask(uint32_t order, uint32_t len, uint32_t card, uint32_t tset) {
+    const uint32_t twin = card_twin(card);
+    if ((tset >> twin) & 1u) return 1u << nibble_pos(order, twin);
+    if (len < 2u) return 0u;                 // a sum needs two cards (a single equal card is the twin)
+    const uint32_t rank = card_rank(card);
     uint32_t R[9];
-    uint32_t eq = 0u;
     R[0] = 1u;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        uint32_t ri = card_rank((order >> (4 * i)) & 0xFu);
-        bool live = (uint32_t)i < len;
-        if (live && ri == rank && eq == 0u) eq = 1u << i;
-        R[i + 1] = live ? ((R[i] | (R[i] << ri)) & 0x7FFu) : R[i];
+        if ((uint32_t)i >= len) { R[i + 1] = R[i]; continue; }
+        const uint32_t ri = card_rank((order >> (4 * i)) & 0xFu);
+        R[i + 1] = (R[i] | (R[i] << ri)) & 0x7FFu;
     }
-    if (eq) return eq;
     if (!((R[8] >> rank) & 1u)) return 0u;
     uint32_t t = rank, m = 0u;
 #pragma unroll
     for (int i = 7; i >= 0; i--) {
-        uint32_t ri = card_rank((order >> (4 * i)) & 0xFu);
-        bool take = ((uint32_t)i < len) && t > 0u && !((R[i] >> t) & 1u);
-        if (take) { m |= 1u << i; t -= ri; }
+        if ((uint32_t)i < len && t > 0u && !((R[i] >> t) & 1u)) {
+            m |= 1u << i;
+            t -= card_rank((order >> (4 * i)) & 0xFu);
+        }
     }
     return m;
 }
@@ -85,26 +120,26 @@ __device__ __forceinline__ uint32_t capture_mask(uint32_t order, uint32_t len, u
 // Illegal action (card not in the mover's hand, or id outside 0..15) = silent pass that still
 // advances step_count and the turn (:155-167).  A step on a terminal state is a no-op (:141-143).
 // Returns the table-position capture mask (0 when the card was placed or the move was a pass).
-__device__ __forceinline__ uint32_t step(MsState& s, uint32_t action) {
+// `tset` must be the set of card ids currently on the table (table_set(), or dealt & ~hands & ~caps).
+__device__ __forceinline__ uint32_t step(MsState& s, uint32_t action, uint32_t tset) {
     if (st_terminal(s)) return 0u;
     const int p = st_cur(s);
-    uint32_t hand = st_hand(s, p);
+    const uint32_t hand = st_hand(s, p);
     uint32_t capm = 0u;
     if (action < 16u && ((hand >> action) & 1u)) {
-        uint32_t len = st_table_len(s);
+        const uint32_t len = st_table_len(s);
         uint32_t order = s.y;
-        capm = capture_mask(order, len, card_rank(action));
+        capm = capture_mask(order, len, action, tset);
         if (capm) {
-            uint32_t keep = 0u, k = 0u, taken = 1u << action;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                uint32_t c = (order >> (4 * i)) & 0xFu;
-                if ((uint32_t)i < len) {
-                    if ((capm >> i) & 1u) taken |= 1u << c;
-                    else { keep |= c << (4u * k); k++; }
-                }
+            uint32_t taken = 1u << action, k = len, m = capm;
+            while (m) {                                    // captured positions, highest first
+                const uint32_t i = 31u - (uint32_t)__clz((int)m);
+                m ^= 1u << i;
+                taken |= 1u << ((order >> (4u * i)) & 0xFu);
+                order = nibble_remove(order, i);
+                k--;
             }
-            s.y = keep;
+            s.y = order;
             s.z |= taken << (16 * p);
             s.w = (s.w & ~0xFu) | k;
             if (k == 0u) s.w += 1u << (4 + 4 * p);        // scopa (:101-102)
@@ -115,10 +150,23 @@ __device__ __forceinline__ uint32_t step(MsState& s, uint32_t action) {
         s.x &= ~((1u << action) << (16 * p));             // hand.remove(card)
     }
     s.w += 1u << 12;                                      // step_count++
-    bool term = (s.x == 0u) || (st_step_count(s) >= st_max_steps(s));
+    const bool term = (s.x == 0u) || (st_step_count(s) >= st_max_steps(s));
     s.w ^= 1u << 17;                                      // next player
     if (term) s.w |= 1u << 18;
     return capm;
+}
+
+__device__ __forceinline__ uint32_t step(MsState& s, uint32_t action) {
+    return step(s, action, table_set(s.y, st_table_len(s)));
+}
+
+// every card of the deal that is in a hand, on the table or captured: constant along a game, so
+// table set = dealt & ~hands & ~captures without touching the ordered list
+__device__ __forceinline__ uint32_t dealt_set(const MsState& s) {
+    return ((s.x | (s.x >> 16) | s.z | (s.z >> 16)) & 0xFFFFu) | table_set(s.y, st_table_len(s));
+}
+__device__ __forceinline__ uint32_t table_set_from_dealt(const MsState& s, uint32_t dealt) {
+    return dealt & ~((s.x | (s.x >> 16) | s.z | (s.z >> 16)) & 0xFFFFu);
 }
 
 // evaluate_game (mini_scopa_game.py:106-114): s_i = |captures_i| + 2*scopas_i, r_i = s_i - mean.
