@@ -54,6 +54,11 @@ uint64_t ms_launch_count(void);
 int ms_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_state* d_states, uint32_t* d_hand_order,
                        void* stream);
 
+/* ms_deck_from_seeds: the whole shuffled deck MiniDeck(seed).cards (src/envs/mini_scopa_game.py:25-28):
+ *   d_deck[g] nibble i = card id at position i (the deal takes positions 0-7).  Unlike
+ *   ms_deal_from_seeds no seed substitution happens here (MiniDeck(0) really seeds with 0). */
+int ms_deck_from_seeds(const int64_t* d_seeds, int64_t n, uint64_t* d_deck, void* stream);
+
 /* test hook: the same result through the kernel's rarely-taken slow path (full MT19937 state) */
 int ms_debug_deal_slow_path(const int64_t* d_seeds, int64_t n, ms_state* d_states, uint32_t* d_hand_order,
                             void* stream);

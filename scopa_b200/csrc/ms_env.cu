@@ -125,12 +125,13 @@ __device__ __noinline__ unsigned long long deal_slow(uint32_t key0, uint32_t key
 }
 
 __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__ seeds, long long n,
-                                                   uint4* __restrict__ states, uint32_t* __restrict__ hand_order) {
+                                                   uint4* __restrict__ states, uint32_t* __restrict__ hand_order,
+                                                   unsigned long long* __restrict__ deck, int zero_means_42) {
     uint32_t lo[DEAL_WIN + 1], hi[DEAL_WIN];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
          g += (long long)gridDim.x * blockDim.x) {
         long long sd = seeds[g];
-        if (sd == 0) sd = 42;   // `seed or self.seed` (mini_scopa_game.py:132, default seed 42)
+        if (sd == 0 && zero_means_42) sd = 42;   // `seed or self.seed` (mini_scopa_game.py:132, default seed 42)
         unsigned long long a = sd < 0 ? (unsigned long long)(-(sd + 1)) + 1ull : (unsigned long long)sd;
         const uint32_t key0 = (uint32_t)a, key1 = (uint32_t)(a >> 32);
         const bool two = key1 != 0u;   // key length: 32-bit words of |seed|, at least one
@@ -169,8 +170,9 @@ __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__
             h0 |= 1u << ((ord >> (4 * i)) & 0xFu);
             h1 |= 1u << ((ord >> (16 + 4 * i)) & 0xFu);
         }
-        states[g] = st_make(h0, h1, 8u);
-        hand_order[g] = ord;
+        if (states) states[g] = st_make(h0, h1, 8u);
+        if (hand_order) hand_order[g] = ord;
+        if (deck) deck[g] = perm;
     }
 }
 
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(256) step_kernel(uint4* __restrict__ states, c
         const bool term = st_terminal(s);
         if (rewards) {
             float r0 = term ? reward0(s) : 0.f;
-            rewards[g] = make_float2(r0, -r0);
+            rewards[g] = make_float2(r0, 0.f - r0);   // r1 = s1 - mean: +0.0 on a tie, never -0.0
         }
         if (done) done[g] = term ? 1 : 0;
     }
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const uint4* __restrict__ 
         if (actions8) actions8[g] = make_uint2(acts[0], acts[1]);
         if (rewards) {
             float r0 = st_terminal(s) ? reward0(s) : 0.f;
-            rewards[g] = make_float2(r0, -r0);
+            rewards[g] = make_float2(r0, 0.f - r0);   // r1 = s1 - mean: +0.0 on a tie, never -0.0
         }
         if (final_states) final_states[g] = s;
     }
@@ -373,7 +375,18 @@ int ms_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_state* d_states, ui
     int rc = ensure_mt_table();
     if (rc) return rc;
     deal_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const long long*)d_seeds, (long long)n, (uint4*)d_states, d_hand_order);
+        (const long long*)d_seeds, (long long)n, (uint4*)d_states, d_hand_order, nullptr, 1);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_deck_from_seeds(const int64_t* d_seeds, int64_t n, uint64_t* d_deck, void* stream) {
+    if (n < 0 || (n > 0 && (!d_seeds || !d_deck))) return fail(MS_ERR_ARG, "ms_deck_from_seeds: bad argument");
+    if (n == 0) return MS_OK;
+    int rc = ensure_mt_table();
+    if (rc) return rc;
+    deal_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)d_seeds, (long long)n, nullptr, nullptr, (unsigned long long*)d_deck, 0);
     MS_LAUNCH_CHECK();
     return MS_OK;
 }

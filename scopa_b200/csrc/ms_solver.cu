@@ -193,8 +193,8 @@ __device__ void cfr_traversal(const SolverDev& d, const CfrSmem& m, int tp, doub
         for (int v = s_lvl[l] + tid; v < s_lvl[l + 1]; v += bd) {
             const int nc = m.nchild[v];
             if (nc == 0) {
-                const double r = 0.5 * (double)m.rx2[v];
-                m.u[v] = (tp == 0) ? r : -r;
+                const int rr = m.rx2[v];
+                m.u[v] = 0.5 * (double)(tp == 0 ? rr : -rr);     // +0.0 on ties for both players
             } else if (cp != tp) {
                 const int cb = m.child_begin[v];
                 const double* sg = m.sig + 4 * m.node_slot[v];
@@ -679,8 +679,8 @@ __global__ void __launch_bounds__(512, 1) best_response_kernel(SolverDev d, int 
             for (int v = s_lvl[l] + tid; v < s_lvl[l + 1]; v += bd) {
                 const int nc = m.nchild[v];
                 if (nc == 0) {
-                    const double r = 0.5 * (double)m.rx2[v];
-                    m.u[v] = (b == 0) ? r : -r;
+                    const int rr = m.rx2[v];
+                    m.u[v] = 0.5 * (double)(b == 0 ? rr : -rr);
                 } else if (cp != b) {
                     const int cb = m.child_begin[v];
                     const double* pol = m.sig + 4 * m.node_slot[v];

@@ -1,0 +1,83 @@
+"""CPU-only checks of the boundary: the C-ABI library loads, exports every symbol the header declares
+(and nothing the binding does not know), and the host-side codecs round-trip.  No compute calls."""
+import os
+import re
+import subprocess
+
+import numpy as np
+
+from conftest import ROOT, load_golden_json
+from scopa_b200 import _build, _lib, codec
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "scopa_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ms_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    _build.build_library()
+    lib = _lib.load()
+    assert lib.ms_abi_version() == 1
+    declared = _header_symbols()
+    assert declared == _lib.exported_symbols()
+    out = subprocess.run(["nm", "-D", "--defined-only", _build.LIB], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r"\bT (ms_[a-z0-9_]+)\b", out)))
+    assert exported == declared
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_library_is_sm100a_only_and_has_no_torch_types():
+    out = subprocess.run(["cuobjdump", "-lelf", _build.LIB], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+    hdr = open(os.path.join(ROOT, "include", "scopa_b200.h")).read()
+    assert "torch" not in hdr.lower() and "at::" not in hdr
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return
+    lib = _lib.load()
+    seeds = np.arange(4, dtype=np.int64)
+    st = np.zeros((4, 4), dtype=np.uint32)
+    ho = np.zeros(4, dtype=np.uint32)
+    rc = lib.ms_deal_from_seeds_host(seeds.ctypes.data, 4, st.ctypes.data, ho.ctypes.data)
+    assert rc == -1 and b"failed" in lib.ms_last_error()      # MS_ERR_CUDA: no device, no CPU fallback
+
+
+def test_codec_round_trips_reference_strings():
+    nodes = load_golden_json("env_tree_seed42.json.gz")["nodes"]
+    ho = codec.pack_nibbles([7, 9, 5, 6, 14, 10, 12, 8])        # seed-42 deal
+    seen = set()
+    for nd in nodes:
+        if nd["term"]:
+            continue
+        for p, k in ((0, "info0"), (1, "info1")):
+            s = nd[k]
+            if s in seen:
+                continue
+            seen.add(s)
+            key = codec.string_to_key(s)
+            assert codec.key_to_string(key, ho) == s
+            f = codec.key_fields(key)
+            assert f["player"] == p and f["table"] == nd["table"]
+            assert codec.hand_in_order(f["hand_mask"], ho, p) == nd["hands"][p]
+    assert codec.key_to_string(codec.TERMINAL_KEY, ho) == "TERMINAL"
+
+
+def test_pack_unpack_state():
+    w = codec.pack_state([0x00A1, 0x4400], [3, 9, 12], [0x0006, 0x0810], [1, 2], 5, 1, False, 16)
+    u = codec.unpack_state(w)
+    assert u == {"hand_mask": [0x00A1, 0x4400], "table": [3, 9, 12], "cap_mask": [0x0006, 0x0810], "scopas": [1, 2],
+                 "step_count": 5, "cur": 1, "terminal": False, "max_steps": 16}
+
+
+def test_pyspiel_compat_registry():
+    from scopa_b200 import pyspiel_compat as pyspiel
+    from scopa_b200.envs import openspiel_mini_scopa  # noqa: F401  (registers the game; no GPU work at import)
+    assert pyspiel.PlayerId.TERMINAL == -4
+    assert "load_game" in dir(pyspiel)
