@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -262,7 +262,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
-        return
+        return None
 
     mccfr_obj = {
         "metric": "mccfr_infoset_node_updates_per_sec", "value": mccfr_value, "unit": "infoset-node updates/s",
@@ -305,7 +305,7 @@ def run_ours(args):
     }
     if primary is mccfr_obj:
         line["node_visits_per_sec"] = mccfr_obj["node_visits_per_sec"]
-    print(json.dumps(line))
+    return line
 
 
 # ------------------------------------------------------------------------------------------- CPU side
@@ -343,7 +343,7 @@ def cpu_baselines(args, sample_seconds, threads=None):
 def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
-        return
+        return None
     K, W = args.steps, args.warmup
     from oracle import ms_oracle as ora
     ora.build()
@@ -383,7 +383,7 @@ def run_reference(args):
         "note": "the reference itself is single-threaded pure Python (survey-measured 2.8 k updates/s, 106 k env steps/s "
                 "on one core); this C port is about 80x faster per core and uses every core",
     }
-    print(json.dumps(line))
+    return line
 
 
 def main():
@@ -402,10 +402,19 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout must carry exactly ONE line (the JSON): libraries print there too (NCCL writes its version
+    # banner to stdout), so fd 1 points at stderr while the benchmark runs.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
