@@ -164,6 +164,32 @@ int ms_solver_counters(ms_solver* s, uint64_t h_out[3], int reset, void* stream)
  *   touched, mc_cfr.py:118-130), 2 = uniform.  h_br_values[2]; exploitability = sum / 2. */
 int ms_best_response(ms_solver* s, int32_t policy_kind, double h_br_values[2], void* stream);
 
+/* -------------------------------------------------------------------------------- SDCFR ------
+ * Advantage network = FlexibleNet mlp 34 -> 128 -> 64 -> 16 with ReLU (src/algorithms/deep_cfr/nets.py:151-235,
+ * :296-331; deep_cfr.py:24-52).  A net is passed as ONE fp32 blob of 13776 floats in nn.Linear order:
+ * w1[128][34] b1[128] w2[64][128] b2[64] w3[16][64] b3[16].
+ * precision 0 = fp32 on CUDA cores in the oracle's summation order (parity path);
+ * precision 1 = bf16 operands / fp32 accumulation on the tensor cores (tcgen05.mma, TMEM accumulators).
+ *
+ * ms_mlp_forward: batched AdvantageNetwork.get_advantages (deep_cfr.py:54-68) + positive_regret_policy
+ *   (nets.py:93-101): d_feat [n][34], d_mask [n][16] -> d_adv [n][16] (masked: adv*m - 1e6*(1-m)),
+ *   d_pol [n][16]; either output may be NULL.
+ * ms_sdcfr_traverse: n_trav independent calls of DeepCFR._external_sampling_cfr(root, player)
+ *   (deep_cfr.py:284-365) advanced level by level (the frontier of a level is one batched inference).
+ *   Opponent actions are sampled from the Philox "SDCF" stream with traversal ids first_trav.. .
+ *   Emits ms_sdcfr_samples_per_traversal(player) (= 41) training samples per traversal, what
+ *   AdvantageNetwork.add_experience stores (:70-75): d_feat [.][34], d_target [.][16] (regrets / max|regret|),
+ *   d_mask [.][16]; d_root_value [n_trav] (may be NULL) = the returned root values.
+ *   d_workspace: at least ms_sdcfr_workspace_bytes(n_trav) bytes of device memory. */
+int ms_sdcfr_samples_per_traversal(int player);
+size_t ms_sdcfr_workspace_bytes(int64_t n_trav);
+int ms_mlp_forward(const float* d_net, int precision, const float* d_feat, const float* d_mask, float* d_adv,
+                   float* d_pol, int64_t n, void* stream);
+int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, const float* d_net0, const float* d_net1,
+                      int precision, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* d_workspace,
+                      size_t workspace_bytes, float* d_feat, float* d_target, float* d_mask, float* d_root_value,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,591 @@
+// scopa_b200/csrc/ms_sdcfr.cu -- SDCFR: batched advantage-net inference and the level-batched
+// external-sampling traversal.  sm_100a only.
+//
+// Replaces (paths relative to /root/reference/):
+//   DeepCFR._state_to_features / _get_legal_actions_mask   src/algorithms/deep_cfr/deep_cfr.py:213-282
+//   AdvantageNetwork.get_advantages                         deep_cfr.py:54-68   (batch-1, one device sync per node)
+//   positive_regret_policy                                  src/algorithms/deep_cfr/nets.py:93-101
+//   DeepCFR._external_sampling_cfr                          deep_cfr.py:284-365
+//   FlexibleNet (mlp mode 34 -> 128 -> 64 -> 16, ReLU)      nets.py:151-235, 296-331
+//
+// The reference does one batch-1 MLP call (and a host<->device hop) per tree node.  Here B traversals
+// advance together, one tree level per launch: the frontier of a level (B x 1..24 nodes) is one batched
+// inference.  The recursion shape is data independent (a traverser node with h cards has exactly h
+// children, an opponent node 1), so level arrays are dense: child index = parent index * fan-out + i,
+// no compaction and no atomics; Philox call indices (= the reference's depth-first invocation order)
+// follow from the same shape.
+//
+// Two inference paths, selected by `precision`:
+//   0  fp32 on CUDA cores, separate multiply/add in the oracle's summation order (bit-comparable with
+//      oracle/ms_oracle.c; this is the parity path);
+//   1  bf16 operands / fp32 accumulation on the 5th-generation tensor cores (tcgen05.mma, accumulators
+//      in TMEM): the throughput path.
+#include <cuda_bf16.h>
+
+#include "ms_common.cuh"
+#include "ms_state.cuh"
+
+namespace ms {
+
+constexpr int SD_IN = 34, SD_H1 = 128, SD_H2 = 64, SD_OUT = 16;
+constexpr int SD_W1 = 0, SD_B1 = SD_W1 + SD_H1 * SD_IN, SD_W2 = SD_B1 + SD_H1, SD_B2 = SD_W2 + SD_H2 * SD_H1,
+              SD_W3 = SD_B2 + SD_H2, SD_B3 = SD_W3 + SD_OUT * SD_H2, SD_NW = SD_B3 + SD_OUT;   // 13776 floats
+constexpr int SD_TILE = 128;   // nodes per CTA tile = threads per CTA (thread t owns node/row t)
+
+struct SdShape {
+    int n[9];            // nodes per traversal at each level
+    int f[8];            // fan-out at each level (hand size at traverser levels, 1 at opponent levels)
+    uint32_t size[9];    // _external_sampling_cfr invocations in the subtree of a level-d node
+    int sample_off[8];   // first sample slot of a traverser level inside a traversal's block of samples
+    int samples;         // samples per traversal (41 for a 4+4 deal)
+    int player;
+};
+
+struct SdLevelPtrs { uint4* state; uint32_t* call; float* value; float4* pol; };
+
+struct SdArgs {
+    SdShape sh;
+    SdLevelPtrs lvl[9];
+    const float* net[2];          // fp32 parameter blobs (SD_NW floats each), per player
+    uint32_t hand_order;
+    uint2 pkey;
+    unsigned long long first_trav;
+    long long n_trav;
+    float* out_feat; float* out_target; float* out_mask; float* out_value;
+};
+
+// features of the CURRENT player's view (deep_cfr.py:304): hand one-hot[16] by action id, table
+// one-hot[16] (order dropped), [1.0 (player == current_player), 0.0]
+__device__ __forceinline__ void sd_features(const MsState& s, int cp, float* x) {
+    const uint32_t hand = st_hand(s, cp);
+    const uint32_t tset = table_set(s.y, st_table_len(s));
+#pragma unroll
+    for (int i = 0; i < 16; i++) { x[i] = (float)((hand >> i) & 1u); x[16 + i] = (float)((tset >> i) & 1u); }
+    x[32] = 1.f; x[33] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 CUDA-core MLP: weights in shared memory (every lane reads the same weight -> broadcast), the
+// thread's hidden activations in shared memory as [k][thread] (conflict free).  acc = b; acc += w*x in
+// index order with separate multiply and add (library is compiled with --fmad=false).
+struct SdSmemFp32 { float* w; float* h1; float* h2; };
+
+__device__ __forceinline__ void mlp_fp32(const SdSmemFp32& sm, const float* x, float* out) {
+    const int tid = threadIdx.x;
+    for (int o = 0; o < SD_H1; o++) {
+        float acc = sm.w[SD_B1 + o];
+        const float* wr = sm.w + SD_W1 + o * SD_IN;
+#pragma unroll
+        for (int i = 0; i < SD_IN; i++) acc += wr[i] * x[i];
+        sm.h1[o * SD_TILE + tid] = acc > 0.f ? acc : 0.f;
+    }
+    for (int o = 0; o < SD_H2; o += 4) {
+        float a0 = sm.w[SD_B2 + o], a1 = sm.w[SD_B2 + o + 1], a2 = sm.w[SD_B2 + o + 2], a3 = sm.w[SD_B2 + o + 3];
+        const float* w0 = sm.w + SD_W2 + o * SD_H1;
+        for (int k = 0; k < SD_H1; k++) {
+            const float h = sm.h1[k * SD_TILE + tid];
+            a0 += w0[k] * h; a1 += w0[SD_H1 + k] * h; a2 += w0[2 * SD_H1 + k] * h; a3 += w0[3 * SD_H1 + k] * h;
+        }
+        sm.h2[(o + 0) * SD_TILE + tid] = a0 > 0.f ? a0 : 0.f;
+        sm.h2[(o + 1) * SD_TILE + tid] = a1 > 0.f ? a1 : 0.f;
+        sm.h2[(o + 2) * SD_TILE + tid] = a2 > 0.f ? a2 : 0.f;
+        sm.h2[(o + 3) * SD_TILE + tid] = a3 > 0.f ? a3 : 0.f;
+    }
+#pragma unroll
+    for (int o = 0; o < SD_OUT; o++) {
+        float acc = sm.w[SD_B3 + o];
+        const float* wr = sm.w + SD_W3 + o * SD_H2;
+        for (int k = 0; k < SD_H2; k++) acc += wr[k] * sm.h2[k * SD_TILE + tid];
+        out[o] = acc;
+    }
+}
+
+constexpr size_t SD_SMEM_FP32 = sizeof(float) * (SD_NW + 16 + SD_H1 * SD_TILE + SD_H2 * SD_TILE);
+
+__device__ __forceinline__ SdSmemFp32 sd_carve_fp32(unsigned char* raw, const float* net) {
+    SdSmemFp32 sm;
+    sm.w = (float*)raw; sm.h1 = sm.w + SD_NW + 16; sm.h2 = sm.h1 + SD_H1 * SD_TILE;
+    for (int i = threadIdx.x; i < SD_NW; i += blockDim.x) sm.w[i] = net[i];
+    __syncthreads();
+    return sm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 path.  One CTA = 128 threads = one 128-row tile; thread t builds row t of the A operand
+// (features, then the ReLU'd hidden activations) in shared memory in the UMMA K-major no-swizzle
+// ("interleave") canonical layout -- 8x16-byte core matrices: element (m, k) of a K=16 slice lives at
+//   (m / 8) * SBO + (k / 8) * LBO + (m % 8) * 16 + (k % 8) * 2  bytes --
+// the weights W[out][in] (= nn.Linear's layout = K-major B operand) are staged once per CTA in the same
+// layout as bf16, one elected thread issues tcgen05.mma (M=128, N=128/64/16, K=16 per instruction)
+// into TMEM, completion is signalled through tcgen05.commit -> mbarrier, and thread t reads ITS
+// accumulator row back with tcgen05.ld 32x32b for the bias + ReLU epilogue.
+constexpr int SD_K1 = 48;                        // 34 padded to a multiple of 16
+constexpr uint32_t SD_TM_D1 = 0, SD_TM_D2 = 128, SD_TM_D3 = 192;   // TMEM column offsets (256 columns allocated)
+
+struct SdSmemTc {
+    __nv_bfloat16* a;      // A operand tile, 128 rows x up to 128 k   (32 KB)
+    __nv_bfloat16* w1;     // 128 x 48
+    __nv_bfloat16* w2;     // 64 x 128
+    __nv_bfloat16* w3;     // 16 x 64
+    float* bias;           // b1 | b2 | b3
+    unsigned long long* bar;
+    uint32_t* tmem_base;
+};
+constexpr size_t SD_SMEM_TC = 2 * (128 * 128 + 128 * SD_K1 + 64 * 128 + 16 * 64) + 4 * (128 + 64 + 16) + 64 + 1024;
+
+// canonical K-major no-swizzle tile with `rows` rows and K elements: core matrix (8 rows x 8 k) = 128 B;
+// K-adjacent core matrices are contiguous (LBO = 128 B), 8-row groups are K/8 core matrices apart
+__device__ __forceinline__ uint32_t sd_tile_off(int row, int k, int K) {
+    return (uint32_t)((row >> 3) * (K >> 3) * 128 + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2);
+}
+
+__device__ __forceinline__ uint64_t sd_smem_desc(const void* p, int K) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    const uint64_t lbo = 128 >> 4, sbo = (uint64_t)((K >> 3) * 128) >> 4;
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46);   // version 1, no swizzle
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128
+__device__ __forceinline__ uint32_t sd_idesc(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void sd_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+__device__ __forceinline__ void sd_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+__device__ __forceinline__ void sd_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" :: "r"(a), "r"(parity) : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns of the accumulator: thread = its lane (row)
+__device__ __forceinline__ void sd_tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ SdSmemTc sd_carve_tc(unsigned char* raw, const float* net) {
+    SdSmemTc sm;
+    unsigned char* p = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    sm.a = (__nv_bfloat16*)p; p += 2 * 128 * 128;
+    sm.w1 = (__nv_bfloat16*)p; p += 2 * 128 * SD_K1;
+    sm.w2 = (__nv_bfloat16*)p; p += 2 * 64 * 128;
+    sm.w3 = (__nv_bfloat16*)p; p += 2 * 16 * 64;
+    sm.bias = (float*)p; p += 4 * (128 + 64 + 16);
+    sm.bar = (unsigned long long*)p; p += 16;
+    sm.tmem_base = (uint32_t*)p;
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int i = tid; i < 128 * SD_K1; i += T) {
+        const int o = i / SD_K1, k = i % SD_K1;
+        *(__nv_bfloat16*)((char*)sm.w1 + sd_tile_off(o, k, SD_K1)) = __float2bfloat16(k < SD_IN ? net[SD_W1 + o * SD_IN + k] : 0.f);
+    }
+    for (int i = tid; i < 64 * 128; i += T) {
+        const int o = i / 128, k = i % 128;
+        *(__nv_bfloat16*)((char*)sm.w2 + sd_tile_off(o, k, 128)) = __float2bfloat16(net[SD_W2 + o * 128 + k]);
+    }
+    for (int i = tid; i < 16 * 64; i += T) {
+        const int o = i / 64, k = i % 64;
+        *(__nv_bfloat16*)((char*)sm.w3 + sd_tile_off(o, k, 64)) = __float2bfloat16(net[SD_W3 + o * 64 + k]);
+    }
+    for (int i = tid; i < 128; i += T) sm.bias[i] = net[SD_B1 + i];
+    for (int i = tid; i < 64; i += T) sm.bias[128 + i] = net[SD_B2 + i];
+    for (int i = tid; i < 16; i += T) sm.bias[192 + i] = net[SD_B3 + i];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(sm.bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < 32) {   // one warp allocates 256 TMEM columns and gives up the permit
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(sm.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    return sm;
+}
+
+__device__ __forceinline__ void sd_release_tc(const SdSmemTc& sm) {
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(*sm.tmem_base) : "memory");
+}
+
+// one layer: D[128 x N] = A[128 x K] * W[N x K]^T on the tensor cores; all 128 threads call it
+__device__ __forceinline__ void sd_layer_mma(const SdSmemTc& sm, const __nv_bfloat16* w, int K, int N, uint32_t tm_col,
+                                             uint32_t& phase) {
+    // the A tile was written with ordinary stores: make it visible to the async (tensor core) proxy
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (threadIdx.x == 0) {
+        const uint32_t tm = *sm.tmem_base + tm_col;
+        const uint32_t idesc = sd_idesc(N);
+        for (int k = 0; k < K; k += 16) {
+            const uint64_t da = sd_smem_desc((const char*)sm.a + (k >> 3) * 128, K);
+            const uint64_t db = sd_smem_desc((const char*)w + (k >> 3) * 128, K);
+            sd_mma(tm, da, db, idesc, k > 0);
+        }
+        sd_commit(sm.bar);
+    }
+    sd_wait(sm.bar, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+
+__device__ __forceinline__ void mlp_tc(const SdSmemTc& sm, const float* x, float* out, uint32_t& phase) {
+    const int tid = threadIdx.x;
+    const uint32_t lane_base = ((uint32_t)(tid & ~31)) << 16;      // TMEM address: lane in bits 31..16
+    // layer 1: A = features (K padded to 48)
+#pragma unroll
+    for (int k = 0; k < SD_K1; k++)
+        *(__nv_bfloat16*)((char*)sm.a + sd_tile_off(tid, k, SD_K1)) = __float2bfloat16(k < SD_IN ? x[k] : 0.f);
+    sd_layer_mma(sm, sm.w1, SD_K1, SD_H1, SD_TM_D1, phase);
+    for (int c = 0; c < SD_H1; c += 16) {
+        float v[16];
+        sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D1 + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float h = v[i] + sm.bias[c + i];
+            *(__nv_bfloat16*)((char*)sm.a + sd_tile_off(tid, c + i, SD_H1)) = __float2bfloat16(h > 0.f ? h : 0.f);
+        }
+    }
+    sd_layer_mma(sm, sm.w2, SD_H1, SD_H2, SD_TM_D2, phase);
+    for (int c = 0; c < SD_H2; c += 16) {
+        float v[16];
+        sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D2 + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float h = v[i] + sm.bias[128 + c + i];
+            *(__nv_bfloat16*)((char*)sm.a + sd_tile_off(tid, c + i, SD_H2)) = __float2bfloat16(h > 0.f ? h : 0.f);
+        }
+    }
+    sd_layer_mma(sm, sm.w3, SD_H2, SD_OUT, SD_TM_D3, phase);
+    float v[16];
+    sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D3, v);
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[i] = v[i] + sm.bias[192 + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// AdvantageNetwork.get_advantages masking (deep_cfr.py:66-67) + positive_regret_policy (nets.py:93-101)
+__device__ __forceinline__ void sd_policy(const float* raw, uint32_t legal_mask, float* adv, float* pol) {
+    float z = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float m = (float)((legal_mask >> i) & 1u);
+        adv[i] = raw[i] * m - 1e6f * (1.f - m);
+        const float pos = (adv[i] > 0.f ? adv[i] : 0.f) * m;
+        pol[i] = pos;
+        z += pos;
+    }
+    if (z < 1e-8f) z = 1e-8f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) pol[i] = pol[i] / z;
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(SD_TILE, 1) sd_mlp_kernel(const float* __restrict__ net, const float* __restrict__ feat,
+                                                            const float* __restrict__ mask, float* __restrict__ adv_out,
+                                                            float* __restrict__ pol_out, long long n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SdSmemFp32 s32{};
+    SdSmemTc stc{};
+    uint32_t phase = 0;
+    if (PREC == 0) s32 = sd_carve_fp32(smem_raw, net); else stc = sd_carve_tc(smem_raw, net);
+    const int tid = threadIdx.x;
+    const long long tiles = (n + SD_TILE - 1) / SD_TILE;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long g = tile * SD_TILE + tid;
+        float x[SD_IN], raw[16];
+        uint32_t lm = 0u;
+        for (int i = 0; i < SD_IN; i++) x[i] = g < n ? feat[g * SD_IN + i] : 0.f;
+        for (int i = 0; i < 16; i++) if (g < n && mask[g * 16 + i] != 0.f) lm |= 1u << i;
+        if (PREC == 0) mlp_fp32(s32, x, raw); else mlp_tc(stc, x, raw, phase);
+        if (g < n) {
+            float adv[16], pol[16];
+            sd_policy(raw, lm, adv, pol);
+            for (int i = 0; i < 16; i++) {
+                if (adv_out) adv_out[g * 16 + i] = adv[i];
+                if (pol_out) pol_out[g * 16 + i] = pol[i];
+            }
+        }
+    }
+    if (PREC == 1) sd_release_tc(stc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward level d: inference for every frontier node, then expand (traverser) or sample (opponent).
+template <int PREC>
+__global__ void __launch_bounds__(SD_TILE, 1) sd_forward_kernel(SdArgs a, int d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cp = d & 1;
+    const bool trav = (cp == a.sh.player);
+    SdSmemFp32 s32{};
+    SdSmemTc stc{};
+    uint32_t phase = 0;
+    if (PREC == 0) s32 = sd_carve_fp32(smem_raw, a.net[cp]); else stc = sd_carve_tc(smem_raw, a.net[cp]);
+    const int tid = threadIdx.x;
+    const long long total = a.n_trav * a.sh.n[d];
+    const long long tiles = (total + SD_TILE - 1) / SD_TILE;
+    const int f = a.sh.f[d];
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long g = tile * SD_TILE + tid;
+        const bool live = g < total;
+        MsState s = live ? a.lvl[d].state[g] : make_uint4(0u, 0u, 0u, 0u);
+        float x[SD_IN], raw[16];
+        sd_features(s, cp, x);
+        if (PREC == 0) mlp_fp32(s32, x, raw); else mlp_tc(stc, x, raw, phase);
+        if (!live) continue;
+        uint32_t list;
+        const uint32_t nl = legal_list(s, a.hand_order, cp, list);
+        uint32_t lm = 0u;
+        for (uint32_t i = 0; i < nl; i++) lm |= 1u << ((list >> (4 * i)) & 0xFu);
+        float adv[16], pol[16];
+        sd_policy(raw, lm, adv, pol);
+        const uint32_t call = a.lvl[d].call[g];
+        if (trav) {
+            float pl[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = 0; i < f; i++) {
+                const uint32_t act = (list >> (4 * i)) & 0xFu;
+                pl[i] = pol[act];
+                MsState c = s;
+                step(c, act);
+                a.lvl[d + 1].state[g * f + i] = c;
+                a.lvl[d + 1].call[g * f + i] = call + 1u + (uint32_t)i * a.sh.size[d + 1];
+            }
+            a.lvl[d].pol[g] = make_float4(pl[0], pl[1], pl[2], pl[3]);
+        } else {
+            // opponent: sample one action from the policy restricted to the legal list (deep_cfr.py:347-359)
+            float ap[4], sum = 0.f;
+            for (uint32_t i = 0; i < 4; i++) ap[i] = i < nl ? pol[(list >> (4 * i)) & 0xFu] : 0.f;
+            for (uint32_t i = 0; i < nl; i++) sum += ap[i];
+            const long long t = g / a.sh.n[d];
+            const unsigned long long trav_id = a.first_trav + (unsigned long long)t;
+            const uint4 xb = philox4x32_10(make_uint4((uint32_t)trav_id, (uint32_t)(trav_id >> 32), call >> 1,
+                                                      MS_TAG_SDCF + (uint32_t)a.sh.player), a.pkey);
+            const uint32_t w0 = (call & 1u) ? xb.z : xb.x, w1 = (call & 1u) ? xb.w : xb.y;
+            uint32_t ai;
+            if (sum == 0.f) ai = __umulhi(w0, nl);                    // np.random.choice(legal_actions)
+            else {
+                double cdf[4], acc = 0.0;
+                for (uint32_t i = 0; i < 4; i++) { if (i < nl) acc = __dadd_rn(acc, (double)(ap[i] / sum)); cdf[i] = acc; }
+                const double last = acc, u = u53(w0, w1);
+                ai = 0u;
+                for (uint32_t i = 0; i < nl; i++) if (__ddiv_rn(cdf[i], last) <= u) ai++;
+                if (ai >= nl) ai = nl - 1u;
+            }
+            MsState c = s;
+            step(c, (list >> (4 * ai)) & 0xFu);
+            a.lvl[d + 1].state[g] = c;
+            a.lvl[d + 1].call[g] = call + 1u;
+        }
+    }
+    if (PREC == 1) sd_release_tc(stc);
+}
+
+__global__ void __launch_bounds__(256) sd_init_kernel(SdArgs a, uint4 root) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < a.n_trav; t += (long long)gridDim.x * blockDim.x) {
+        a.lvl[0].state[t] = root;
+        a.lvl[0].call[t] = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) sd_terminal_kernel(SdArgs a) {
+    const long long total = a.n_trav * a.sh.n[8];
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const MsState s = a.lvl[8].state[g];
+        const int r = st_terminal(s) ? reward0_x2(s) : 0;
+        a.lvl[8].value[g] = 0.5f * (float)(a.sh.player == 0 ? r : -r);
+    }
+}
+
+// Backward level d: traverser nodes combine their children's values, form the regret target and emit a
+// sample (deep_cfr.py:321-346, :70-75); opponent nodes pass the sampled child's value up.
+__global__ void __launch_bounds__(256) sd_backward_kernel(SdArgs a, int d) {
+    const int cp = d & 1;
+    const bool trav = (cp == a.sh.player);
+    const long long total = a.n_trav * a.sh.n[d];
+    const int f = a.sh.f[d], nd = a.sh.n[d];
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        if (!trav) { a.lvl[d].value[g] = a.lvl[d + 1].value[g]; continue; }
+        const MsState s = a.lvl[d].state[g];
+        uint32_t list;
+        legal_list(s, a.hand_order, cp, list);
+        const float4 p4 = a.lvl[d].pol[g];
+        const float pl[4] = {p4.x, p4.y, p4.z, p4.w};
+        float value = 0.f, cfv[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) cfv[i] = 0.f;
+        uint32_t lm = 0u;
+        for (int i = 0; i < f; i++) {
+            const uint32_t act = (list >> (4 * i)) & 0xFu;
+            const float av = a.lvl[d + 1].value[g * f + i];
+            value += pl[i] * av;
+            cfv[act] = av;
+            lm |= 1u << act;
+        }
+        a.lvl[d].value[g] = value;
+        float reg[16], mx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) { reg[i] = cfv[i] - value; mx = fmaxf(mx, fabsf(reg[i])); }
+        if (mx > 0.f) {
+            const float dn = mx + 1e-8f;
+#pragma unroll
+            for (int i = 0; i < 16; i++) reg[i] = reg[i] / dn;
+        }
+        const long long t = g / nd, j = g % nd;
+        const long long slot = t * a.sh.samples + a.sh.sample_off[d] + j;
+        float x[SD_IN];
+        sd_features(s, cp, x);
+        for (int i = 0; i < SD_IN; i++) a.out_feat[slot * SD_IN + i] = x[i];
+        for (int i = 0; i < 16; i++) {
+            a.out_target[slot * 16 + i] = reg[i];
+            a.out_mask[slot * 16 + i] = (float)((lm >> i) & 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sd_root_value_kernel(SdArgs a) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < a.n_trav; t += (long long)gridDim.x * blockDim.x)
+        a.out_value[t] = a.lvl[0].value[t];
+}
+
+static void sd_shape(int player, SdShape& sh) {
+    sh.player = player;
+    sh.n[0] = 1;
+    for (int d = 0; d < 8; d++) {
+        sh.f[d] = ((d & 1) == player) ? (4 - d / 2) : 1;
+        sh.n[d + 1] = sh.n[d] * sh.f[d];
+    }
+    sh.size[8] = 1;
+    for (int d = 7; d >= 0; d--) sh.size[d] = 1u + (uint32_t)sh.f[d] * sh.size[d + 1];
+    int off = 0;
+    for (int d = 0; d < 8; d++) {
+        sh.sample_off[d] = off;
+        if ((d & 1) == player) off += sh.n[d];
+    }
+    sh.samples = off;
+}
+
+static size_t sd_workspace(long long n_trav, int player, SdArgs* a, char* base) {
+    SdShape sh;
+    sd_shape(player, sh);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    for (int d = 0; d <= 8; d++) {
+        const size_t nn = (size_t)n_trav * sh.n[d];
+        size_t o_state = take(16 * nn), o_call = take(4 * nn), o_val = take(4 * nn), o_pol = take(16 * nn);
+        if (a) {
+            a->lvl[d].state = (uint4*)(base + o_state); a->lvl[d].call = (uint32_t*)(base + o_call);
+            a->lvl[d].value = (float*)(base + o_val); a->lvl[d].pol = (float4*)(base + o_pol);
+        }
+    }
+    if (a) a->sh = sh;
+    return off;
+}
+
+}  // namespace ms
+
+using namespace ms;
+
+extern "C" {
+
+int ms_sdcfr_samples_per_traversal(int player) {
+    SdShape sh;
+    sd_shape(player & 1, sh);
+    return sh.samples;
+}
+
+size_t ms_sdcfr_workspace_bytes(int64_t n_trav) {
+    size_t a = sd_workspace(n_trav, 0, nullptr, nullptr), b = sd_workspace(n_trav, 1, nullptr, nullptr);
+    return a > b ? a : b;
+}
+
+int ms_mlp_forward(const float* d_net, int precision, const float* d_feat, const float* d_mask, float* d_adv,
+                   float* d_pol, int64_t n, void* stream) {
+    if (n < 0 || precision < 0 || precision > 1 || (n > 0 && (!d_net || !d_feat || !d_mask)))
+        return fail(MS_ERR_ARG, "ms_mlp_forward: bad argument");
+    if (n == 0) return MS_OK;
+    const int grid = grid_for(n, SD_TILE, 1);
+    if (precision == 0) {
+        MS_CUDA(cudaFuncSetAttribute(sd_mlp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_FP32));
+        sd_mlp_kernel<0><<<grid, SD_TILE, SD_SMEM_FP32, (cudaStream_t)stream>>>(d_net, d_feat, d_mask, d_adv, d_pol, (long long)n);
+    } else {
+        MS_CUDA(cudaFuncSetAttribute(sd_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
+        sd_mlp_kernel<1><<<grid, SD_TILE, SD_SMEM_TC, (cudaStream_t)stream>>>(d_net, d_feat, d_mask, d_adv, d_pol, (long long)n);
+    }
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, const float* d_net0, const float* d_net1,
+                      int precision, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* d_workspace,
+                      size_t workspace_bytes, float* d_feat, float* d_target, float* d_mask, float* d_root_value,
+                      void* stream) {
+    if (!h_root || player < 0 || player > 1 || precision < 0 || precision > 1 || n_trav < 0 || !d_net0 || !d_net1)
+        return fail(MS_ERR_ARG, "ms_sdcfr_traverse: bad argument");
+    if (n_trav == 0) return MS_OK;
+    if (!d_workspace || !d_feat || !d_target || !d_mask) return fail(MS_ERR_ARG, "ms_sdcfr_traverse: null buffer");
+    // the level shapes assume the reference's root: both hands full, player 0 to move, nothing played yet
+    const uint32_t h0 = h_root->hands & 0xFFFFu, h1 = h_root->hands >> 16;
+    if (__builtin_popcount(h0) != 4 || __builtin_popcount(h1) != 4 || ((h_root->meta >> 17) & 1u) || ((h_root->meta >> 12) & 0x1Fu))
+        return fail(MS_ERR_ARG, "ms_sdcfr_traverse: root must be a fresh 4+4-card deal with player 0 to move");
+    SdArgs a{};
+    const size_t need = sd_workspace(n_trav, player, &a, (char*)d_workspace);
+    if (need > workspace_bytes) return fail(MS_ERR_CAPACITY, "workspace too small: need %zu bytes", need);
+    a.net[0] = d_net0; a.net[1] = d_net1;
+    a.hand_order = hand_order;
+    a.pkey = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
+    a.first_trav = first_trav; a.n_trav = n_trav;
+    a.out_feat = d_feat; a.out_target = d_target; a.out_mask = d_mask; a.out_value = d_root_value;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint4 root = make_uint4(h_root->hands, h_root->table, h_root->captures, h_root->meta);
+    sd_init_kernel<<<grid_for(n_trav, 256, 4), 256, 0, st>>>(a, root);
+    MS_LAUNCH_CHECK();
+    if (precision == 0) MS_CUDA(cudaFuncSetAttribute(sd_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_FP32));
+    else MS_CUDA(cudaFuncSetAttribute(sd_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
+    for (int d = 0; d < 8; d++) {
+        const int grid = grid_for(n_trav * a.sh.n[d], SD_TILE, 1);
+        if (precision == 0) sd_forward_kernel<0><<<grid, SD_TILE, SD_SMEM_FP32, st>>>(a, d);
+        else sd_forward_kernel<1><<<grid, SD_TILE, SD_SMEM_TC, st>>>(a, d);
+        MS_LAUNCH_CHECK();
+    }
+    sd_terminal_kernel<<<grid_for(n_trav * a.sh.n[8], 256, 8), 256, 0, st>>>(a);
+    MS_LAUNCH_CHECK();
+    for (int d = 7; d >= 0; d--) {
+        sd_backward_kernel<<<grid_for(n_trav * a.sh.n[d], 256, 8), 256, 0, st>>>(a, d);
+        MS_LAUNCH_CHECK();
+    }
+    if (d_root_value) {
+        sd_root_value_kernel<<<grid_for(n_trav, 256, 4), 256, 0, st>>>(a);
+        MS_LAUNCH_CHECK();
+    }
+    return MS_OK;
+}
+
+}  // extern "C"

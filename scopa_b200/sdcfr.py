@@ -1,0 +1,73 @@
+"""Low-level SDCFR entry points over the C ABI: batched advantage-net inference and the level-batched
+external-sampling traversal (csrc/ms_sdcfr.cu)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NET_FLOATS = 13776
+FP32, TENSOR_CORE = 0, 1
+
+
+def flatten_net(net):
+    """FlexibleNet (mlp 34->128->64->16) -> one fp32 CUDA blob in nn.Linear order (w1 b1 w2 b2 w3 b3)."""
+    layers = [net.backbone[0].fc, net.backbone[1].fc, net.head]
+    parts = []
+    for l in layers:
+        parts += [l.weight.detach().reshape(-1), l.bias.detach().reshape(-1)]
+    blob = torch.cat(parts).to(dtype=torch.float32).contiguous()
+    assert blob.numel() == NET_FLOATS, blob.numel()
+    return blob
+
+
+def blob_from_arrays(w1, b1, w2, b2, w3, b3, device="cuda"):
+    parts = [np.asarray(a, dtype=np.float32).reshape(-1) for a in (w1, b1, w2, b2, w3, b3)]
+    blob = torch.from_numpy(np.concatenate(parts)).to(device)
+    assert blob.numel() == NET_FLOATS
+    return blob
+
+
+def mlp_forward(blob, feat, mask, precision=FP32):
+    """-> (advantages [n,16] masked like get_advantages, policy [n,16] = positive_regret_policy)."""
+    lib = _lib.load()
+    feat = feat.to(dtype=torch.float32).contiguous()
+    mask = mask.to(dtype=torch.float32).contiguous()
+    n = feat.shape[0]
+    adv = torch.empty((n, 16), dtype=torch.float32, device=feat.device)
+    pol = torch.empty((n, 16), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.check(lib.ms_mlp_forward(blob.data_ptr(), int(precision), feat.data_ptr(), mask.data_ptr(), adv.data_ptr(),
+                                      pol.data_ptr(), n, _lib.stream_ptr()))
+    return adv, pol
+
+
+class Traverser:
+    """Reusable workspace for batches of external-sampling traversals from one root."""
+
+    def __init__(self, root_words, hand_order, device="cuda"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.root = (C.c_uint32 * 4)(*[int(w) & 0xFFFFFFFF for w in root_words])
+        self.hand_order = int(hand_order) & 0xFFFFFFFF
+        self._ws = None
+        self.samples_per_traversal = [self.lib.ms_sdcfr_samples_per_traversal(p) for p in (0, 1)]
+
+    def run(self, player, blobs, n_trav, philox_seed=0, first_trav=0, precision=FP32):
+        """-> feat [n*41, 34], target [n*41, 16], mask [n*41, 16], root values [n] (CUDA float32 tensors)."""
+        need = self.lib.ms_sdcfr_workspace_bytes(int(n_trav))
+        with torch.cuda.device(self.device):
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            m = n_trav * self.samples_per_traversal[player]
+            feat = torch.empty((m, 34), dtype=torch.float32, device=self.device)
+            target = torch.empty((m, 16), dtype=torch.float32, device=self.device)
+            mask = torch.empty((m, 16), dtype=torch.float32, device=self.device)
+            value = torch.empty((n_trav,), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.ms_sdcfr_traverse(self.root, self.hand_order, int(player), blobs[0].data_ptr(),
+                                                  blobs[1].data_ptr(), int(precision), int(n_trav), int(philox_seed),
+                                                  int(first_trav), self._ws.data_ptr(), self._ws.numel(),
+                                                  feat.data_ptr(), target.data_ptr(), mask.data_ptr(), value.data_ptr(),
+                                                  _lib.stream_ptr()))
+        return feat, target, mask, value
