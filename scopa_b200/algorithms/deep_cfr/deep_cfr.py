@@ -1,0 +1,284 @@
+"""Drop-in for the reference's src/algorithms/deep_cfr/deep_cfr.py ("SDCFR").
+
+Same classes and surface (/root/reference/src/algorithms/deep_cfr/deep_cfr.py:24-504):
+AdvantageNetwork(.net, .buffer, get_advantages, add_experience, train), StrategyBuffer, RandomPolicy,
+DeepCFR(.advantage_nets, .strategy_buffers, .training_history, _state_to_features,
+_get_legal_actions_mask, _external_sampling_cfr, evaluate_vs_random, train, get_policy).
+
+What changes underneath: the traversal no longer calls a batch-1 MLP (and crosses PCIe) per tree node.
+`_external_sampling_cfr` runs `traversals_per_iteration` traversals level by level on the GPU with the
+frontier of each level as one batched inference (csrc/ms_sdcfr.cu; `precision="fp32"` = CUDA-core path in
+the reference's precision, `"bf16"` = tcgen05 tensor-core path), and the samples land in a device-resident
+replay buffer.  The optimiser step stays in PyTorch (Adam, masked MSE, clip-norm 1.0, as the reference).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from ... import codec, sdcfr
+from .._policy_base import root_of
+from .nets import FlexibleNet, positive_regret_policy
+
+HIDDEN = [128, 64]
+
+
+class DeviceReplayBuffer:
+    """deque(maxlen=100000) of (features, advantages, mask) kept as three CUDA ring tensors."""
+
+    def __init__(self, maxlen=100000, device="cuda"):
+        self.maxlen, self.device = maxlen, device
+        self.feat = torch.zeros((maxlen, 34), dtype=torch.float32, device=device)
+        self.target = torch.zeros((maxlen, 16), dtype=torch.float32, device=device)
+        self.mask = torch.zeros((maxlen, 16), dtype=torch.float32, device=device)
+        self.count = 0          # total ever appended
+
+    def __len__(self):
+        return min(self.count, self.maxlen)
+
+    def clear(self):
+        self.count = 0
+
+    def add_batch(self, feat, target, mask):
+        n = feat.shape[0]
+        if n > self.maxlen:
+            feat, target, mask, n = feat[-self.maxlen:], target[-self.maxlen:], mask[-self.maxlen:], self.maxlen
+        idx = (torch.arange(n, device=self.device) + self.count) % self.maxlen
+        self.feat[idx], self.target[idx], self.mask[idx] = feat, target, mask
+        self.count += n
+
+    def append(self, item):
+        f, a, m = (torch.as_tensor(np.asarray(x), dtype=torch.float32, device=self.device).reshape(1, -1) for x in item)
+        self.add_batch(f, a, m)
+
+    def sample(self, batch_size):
+        idx = torch.randperm(len(self), device=self.device)[:batch_size]     # random.sample: without replacement
+        return self.feat[idx], self.target[idx], self.mask[idx]
+
+    def __iter__(self):
+        n = len(self)
+        f, a, m = self.feat[:n].cpu().numpy(), self.target[:n].cpu().numpy(), self.mask[:n].cpu().numpy()
+        return iter([(f[i], a[i], m[i]) for i in range(n)])
+
+
+class AdvantageNetwork:
+    """Manages the advantage network for one player."""
+
+    def __init__(self, input_dim, num_actions, device="cuda", lr=5e-4, precision="fp32"):
+        self.device = device
+        self.num_actions = num_actions
+        self.precision = sdcfr.TENSOR_CORE if precision == "bf16" else sdcfr.FP32
+        self.net = FlexibleNet(mode="mlp", input_shape=(input_dim,), output_dim=num_actions, mlp_hidden=HIDDEN,
+                               mlp_act="relu", mlp_norm="none", mlp_dropout=0.0).to(device)
+        for layer in self.net.modules():
+            if isinstance(layer, nn.Linear):
+                nn.init.xavier_uniform_(layer.weight)
+                nn.init.constant_(layer.bias, 0.1)
+        self.optimizer = optim.Adam(self.net.parameters(), lr=lr)
+        self.criterion = nn.MSELoss()
+        self.buffer = DeviceReplayBuffer(100000, device)
+
+    def blob(self):
+        return sdcfr.flatten_net(self.net)
+
+    def get_advantages(self, state_features, legal_actions_mask):
+        """Get advantages for a batch of states (our batched inference kernel)."""
+        f = torch.as_tensor(np.asarray(state_features), dtype=torch.float32, device=self.device)
+        m = torch.as_tensor(np.asarray(legal_actions_mask), dtype=torch.float32, device=self.device)
+        if f.dim() == 1:
+            f, m = f.unsqueeze(0), m.unsqueeze(0)
+        adv, _ = sdcfr.mlp_forward(self.blob(), f, m, self.precision)
+        return adv.cpu().numpy()
+
+    def add_experience(self, state_features, advantages, legal_actions_mask):
+        advantages = np.asarray(advantages, dtype=np.float32)
+        if np.max(np.abs(advantages)) > 0:
+            advantages = advantages / (np.max(np.abs(advantages)) + 1e-8)
+        self.buffer.append((state_features, advantages, legal_actions_mask))
+
+    def train(self, batch_size=128, epochs=1):
+        if len(self.buffer) < batch_size:
+            batch_size = min(len(self.buffer), 32)
+            if batch_size == 0:
+                return 0.0
+        total_loss = 0.0
+        for _ in range(epochs):
+            states, target_adv, masks = self.buffer.sample(batch_size)
+            self.optimizer.zero_grad()
+            pred_adv = self.net(states)
+            loss = self.criterion(pred_adv * masks, target_adv * masks)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(self.net.parameters(), max_norm=1.0)
+            self.optimizer.step()
+            total_loss += loss.item()
+        return total_loss / epochs
+
+
+class StrategyBuffer:
+    """Stores past strategies for final policy computation."""
+
+    def __init__(self, max_size=100):
+        self.strategies = []
+        self.weights = []
+        self.max_size = max_size
+
+    def add_strategy(self, strategy_net, iteration):
+        if len(self.strategies) >= self.max_size:
+            self.strategies.pop(0)
+            self.weights.pop(0)
+        self.strategies.append(strategy_net)
+        self.weights.append(iteration + 1)
+
+    def get_average_policy(self, state_features, legal_actions_mask):
+        if not self.strategies:
+            mask = np.asarray(legal_actions_mask).astype(np.float32)
+            return mask / mask.sum()
+        dev = next(self.strategies[0].parameters()).device
+        x = torch.as_tensor(np.asarray(state_features), dtype=torch.float32, device=dev).unsqueeze(0)
+        m = torch.as_tensor(np.asarray(legal_actions_mask), dtype=torch.float32, device=dev).unsqueeze(0)
+        policy = torch.zeros_like(m)
+        total_weight = sum(self.weights)
+        with torch.no_grad():
+            for strategy, weight in zip(self.strategies, self.weights):
+                policy += positive_regret_policy(strategy(x), m) * (weight / total_weight)
+        return policy[0].cpu().numpy().astype(np.float32)
+
+
+class RandomPolicy:
+    """Simple random policy for evaluation."""
+
+    def action_probabilities(self, state, player_id=None):
+        if state.is_terminal():
+            return {}
+        if player_id is None:
+            player_id = state.current_player()
+        legal_actions = state.legal_actions(player_id)
+        prob = 1.0 / len(legal_actions)
+        return {action: prob for action in legal_actions}
+
+
+class DeepCFR:
+    """Main Deep CFR algorithm."""
+
+    def __init__(self, game, num_players=2, device="cuda", precision="fp32", traversals_per_iteration=1, seed=0,
+                 verbose=False):
+        self.game = game
+        self.num_players = num_players
+        self.device = device
+        self.precision = precision
+        self.traversals_per_iteration = int(traversals_per_iteration)
+        self.seed = int(seed)
+        self.verbose = verbose
+        self._trav_count = 0
+        self.input_dim = self._estimate_input_dim()
+        if verbose:
+            print(f"Estimated input dimension: {self.input_dim}")
+        self.advantage_nets = [AdvantageNetwork(self.input_dim, 16, device, precision=precision) for _ in range(num_players)]
+        self.strategy_buffers = [StrategyBuffer() for _ in range(num_players)]
+        self.training_history = {
+            "losses": [[] for _ in range(num_players)],
+            "values": [[] for _ in range(num_players)],
+            "buffer_sizes": [[] for _ in range(num_players)],
+            "eval_rewards": [],
+            "eval_scopas": [],
+        }
+        words, order = root_of(game)
+        self._root = (tuple(int(w) for w in words), int(order))
+        self._traverser = sdcfr.Traverser(words, order, device=device)
+
+    def _estimate_input_dim(self):
+        test_state = self.game.new_initial_state()
+        return len(self._state_to_features(test_state, 0))
+
+    def _state_to_features(self, state, player):
+        """hand one-hot[16] | table one-hot[16] | [player == current_player, 0.0]  (reference :213-275)."""
+        features = np.zeros(34, dtype=np.float32)
+        if state.is_terminal() or player < 0:
+            return features                                    # "TERMINAL" has no H[ / T[ parts -> zeros
+        g = state.env.game
+        for c in g.players[player].hand:
+            features[codec.card_id(c.rank, c.suit)] = 1.0
+        for c in g.table:
+            features[16 + codec.card_id(c.rank, c.suit)] = 1.0
+        features[32] = float(player == state.current_player())
+        return features
+
+    def _get_legal_actions_mask(self, state, player):
+        legal_actions = state.legal_actions(player)
+        mask = np.zeros(16, dtype=np.float32)
+        mask[legal_actions] = 1.0
+        return mask
+
+    def _external_sampling_cfr(self, state, player, depth=0, prob=1.0):
+        """External sampling CFR from the root: runs `traversals_per_iteration` traversals on the GPU, adds
+        their samples to the traverser's replay buffer, returns the (mean) root value."""
+        if state.is_terminal():
+            return float(state.rewards()[player])
+        words, order = state.env.packed()
+        if (tuple(int(w) for w in words), int(order)) != self._root:
+            raise NotImplementedError("_external_sampling_cfr on a non-root state")
+        n = self.traversals_per_iteration
+        blobs = [a.blob() for a in self.advantage_nets]
+        prec = sdcfr.TENSOR_CORE if self.precision == "bf16" else sdcfr.FP32
+        feat, target, mask, value = self._traverser.run(player, blobs, n, philox_seed=self.seed,
+                                                        first_trav=self._trav_count, precision=prec)
+        self._trav_count += n
+        self.advantage_nets[player].buffer.add_batch(feat, target, mask)
+        return float(value.mean().item())
+
+    def evaluate_vs_random(self, num_episodes=100):
+        total_reward = 0.0
+        total_trained_scopas = 0
+        total_random_scopas = 0
+        random_policy = RandomPolicy()
+        for episode in range(num_episodes):
+            trained_seat, random_seat = (0, 1) if episode < num_episodes / 2 else (1, 0)
+            state = self.game.new_initial_state()
+            while not state.is_terminal():
+                current_player = state.current_player()
+                if current_player == trained_seat:
+                    policy_probs = self.get_policy(state, current_player)
+                    legal_actions = state.legal_actions(current_player)
+                    action_probs = np.array([policy_probs[a] for a in legal_actions])
+                    if np.any(np.isnan(action_probs)) or np.sum(action_probs) <= 0:
+                        action_probs = np.ones(len(legal_actions)) / len(legal_actions)
+                    else:
+                        action_probs = action_probs / np.sum(action_probs)
+                    action = np.random.choice(legal_actions, p=action_probs)
+                else:
+                    action_probs = random_policy.action_probabilities(state, current_player)
+                    actions, probs = zip(*action_probs.items())
+                    action = np.random.choice(actions, p=probs)
+                state.apply_action(action)
+            total_reward += state.rewards()[trained_seat]
+            game = state.env.game
+            total_trained_scopas += game.players[trained_seat].scopas
+            total_random_scopas += game.players[random_seat].scopas
+        avg_reward = total_reward / num_episodes
+        scopas = [total_trained_scopas / num_episodes, total_random_scopas / num_episodes]
+        self.training_history["eval_rewards"].append(avg_reward)
+        self.training_history["eval_scopas"].append(scopas)
+        return avg_reward, scopas
+
+    def train(self, iterations=100, advantage_epochs=10, eval_freq=5, eval_episodes=50):
+        for iteration in range(iterations):
+            for player in range(self.num_players):
+                state = self.game.new_initial_state()
+                value = self._external_sampling_cfr(state, player)
+                loss = self.advantage_nets[player].train(epochs=advantage_epochs)
+                self.training_history["losses"][player].append(loss)
+                self.training_history["values"][player].append(value)
+                self.training_history["buffer_sizes"][player].append(len(self.advantage_nets[player].buffer))
+            if iteration > 0:
+                for player in range(self.num_players):
+                    strategy_net = FlexibleNet(mode="mlp", input_shape=(self.input_dim,), output_dim=16,
+                                               mlp_hidden=HIDDEN, mlp_act="relu", mlp_norm="none").to(self.device)
+                    strategy_net.load_state_dict(self.advantage_nets[player].net.state_dict())
+                    self.strategy_buffers[player].add_strategy(strategy_net, iteration)
+            if iteration % eval_freq == 0 and eval_episodes > 0:
+                self.evaluate_vs_random(num_episodes=eval_episodes)
+
+    def get_policy(self, state, player):
+        """Get average policy for a state."""
+        return self.strategy_buffers[player].get_average_policy(self._state_to_features(state, player),
+                                                                self._get_legal_actions_mask(state, player))

@@ -160,3 +160,41 @@ def test_mccfr_trainer_drop_in():
     tb = MCCFRTrainer(game=game, seed=5, traversals_per_iteration=2048)
     tb.train(iterations=30)
     assert len(tb.info_sets) == 738 and tb.exploitability() < 0.8
+
+
+def test_deep_cfr_drop_in():
+    import torch
+    from scopa_b200 import pyspiel_compat as pyspiel
+    from scopa_b200.envs import openspiel_mini_scopa  # noqa: F401
+    from scopa_b200.algorithms.deep_cfr import DeepCFR
+    g = np.load(os.path.join(GOLDEN, "sdcfr_seed0.npz"))
+    game = pyspiel.load_game("mini_scopa")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    d = DeepCFR(game, 2, "cuda")
+    assert d.input_dim == 34
+    # features / mask / advantages with the reference's weights loaded
+    for p in range(2):
+        sd = {k[len(f"net{p}."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f"net{p}.")}
+        d.advantage_nets[p].net.load_state_dict(sd)
+    s = game.new_initial_state()
+    f, m = d._state_to_features(s, 0), d._get_legal_actions_mask(s, 0)
+    assert np.array_equal(f, g["node_feat"][0]) and np.array_equal(m, g["node_mask"][0])
+    adv = d.advantage_nets[0].get_advantages(f, m)
+    np.testing.assert_allclose(adv[0], g["node_adv"][0], rtol=2e-5, atol=2e-6)
+    # one traversal per player like the reference: 41 samples each (deep_cfr.py:284-346)
+    for p in range(2):
+        v = d._external_sampling_cfr(game.new_initial_state(), p)
+        assert len(d.advantage_nets[p].buffer) == 41 and np.isfinite(v)
+    d.train(iterations=6, advantage_epochs=5, eval_freq=5, eval_episodes=10)
+    h = d.training_history
+    assert len(h["losses"][0]) == 6 and len(h["values"][1]) == 6 and h["buffer_sizes"][0][-1] == 41 * 7
+    assert len(h["eval_rewards"]) == 2 and len(d.strategy_buffers[0].strategies) == 5
+    assert d.strategy_buffers[0].weights == [2, 3, 4, 5, 6]
+    pol = d.get_policy(game.new_initial_state(), 0)
+    assert pol.dtype == np.float32 and pol.shape == (16,) and (pol >= 0).all() and pol.sum() < 1 + 1e-5
+    assert pol[[0, 1, 2, 3, 4, 8, 10]].sum() == 0
+    # batched + tensor-core configuration
+    d2 = DeepCFR(game, 2, "cuda", precision="bf16", traversals_per_iteration=512)
+    d2.train(iterations=3, advantage_epochs=4, eval_freq=100, eval_episodes=0)
+    assert d2.training_history["buffer_sizes"][1][-1] == 3 * 512 * 41
