@@ -253,6 +253,41 @@ def run_ours(args):
                "h2d_bytes_per_step": 8 * G, "d2h_bytes_per_step": 16 * G,
                "what": "ms_rollout_random_host: reset(seed) + 8 steps per game, host buffers in and out"}
 
+    # ------------------------------------------------------------------ SDCFR traversal (config 4)
+    from scopa_b200 import sdcfr as sd
+    T = args.sd_trav
+    torch.manual_seed(1234)
+    blobs = [(torch.randn(sd.NET_FLOATS, device=dev) * 0.15).contiguous() for _ in range(2)]   # random-init nets
+    trv = sd.Traverser(sv.root_words, sv.hand_order, device=dev)
+    sd_obj = None
+    for prec, pname in ((sd.TENSOR_CORE, "bf16_tcgen05"), (sd.FP32, "fp32_cuda_cores")):
+        for i in range(2):
+            trv.run(i & 1, blobs, T, philox_seed=args.seed, first_trav=rank * T, precision=prec)
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        l0 = _lib.launch_count()
+        for i in range(K):
+            flush_l2()
+            sev[i][0].record()
+            trv.run(0, blobs, T, philox_seed=args.seed, first_trav=(i * world + rank) * T, precision=prec)
+            trv.run(1, blobs, T, philox_seed=args.seed, first_trav=(i * world + rank) * T, precision=prec)
+            sev[i][1].record()
+        barrier()
+        sd_launches = _lib.launch_count() - l0
+        sd_ms = max_over_ranks(sum(a.elapsed_time(c) for a, c in sev))
+        inf = 187.0 * T * world * K                      # 105 + 82 advantage-net inferences per traversal pair
+        o = {"inferences_per_sec": inf / (sd_ms * 1e-3), "traversals_per_sec": 2.0 * T * world * K / (sd_ms * 1e-3),
+             "ms_per_step": sd_ms / K, "gpu_launches": int(sd_launches),
+             "algorithmic_tflops": inf * 27136.0 / (sd_ms * 1e-3) / 1e12}
+        if sd_obj is None:
+            sd_obj = {"metric": "sdcfr_advantage_net_inferences_per_sec", "unit": "inferences/s",
+                      "config": {"workload": f"BASELINE.json configs[3]: SDCFR external-sampling traversals, {T} per player per "
+                                             "GPU per step, level-batched frontier inference, random-init nets 34-128-64-16",
+                                 "note": "whole traversal timed (8 forward levels incl. env steps + sampling, 8 backward levels), "
+                                         "not the MMA alone; 27136 algorithmic FLOP per inference (un-padded)"}}
+        sd_obj[pname] = o
+    sd_obj["value"] = sd_obj["bf16_tcgen05"]["inferences_per_sec"]
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu_mccfr = cpu_env = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -302,6 +337,7 @@ def run_ours(args):
         "roofline": primary["roofline"], "cpu_baseline": primary["cpu_baseline"], "clocks": clocks,
         "wall_s_mccfr_region": wall,
         ("env" if primary is mccfr_obj else "mccfr"): secondary,
+        "sdcfr": sd_obj,
     }
     if primary is mccfr_obj:
         line["node_visits_per_sec"] = mccfr_obj["node_visits_per_sec"]
@@ -395,6 +431,7 @@ def main():
     ap.add_argument("--workload", default="mccfr", choices=["mccfr", "rollout"])
     ap.add_argument("--trav", type=int, default=262144, help="traversals per player per GPU per step")
     ap.add_argument("--games", type=int, default=1_000_000, help="concurrent games per GPU")
+    ap.add_argument("--sd-trav", type=int, default=16384, help="SDCFR traversals per player per GPU per step")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--ref-trav", type=int, default=1500)

@@ -404,19 +404,59 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
             uint32_t list;
             const uint32_t nl = legal_list(s, d.hand_order, p, list);
             const int slot = lookup_slot(sh.hk, sh.hs, sh.hcap, infoset_key(s, p));
+            sh.touched[slot] = 1;     // node created on first touch, for both players (mc_cfr.py:52)
+            if (nl == 1u) {
+                // Forced move (one legal action): sigma = [1.0], so the draw cannot change anything and no
+                // random word is generated (the call index still advances: the oracle's draw is a no-op too).
+                const uint32_t a1 = list & 0xFu;
+                if (p != tp) {            // opponent: reach *= 1.0
+                    step(s, a1, table_set_from_dealt(s, dealt)); n_step++;
+                    continue;
+                }
+                // Traverser's last card.  If the rest of the game is forced as well (the opponent holds at
+                // most one card) both recursive calls of the reference (:58-67 and :71-78) walk the same
+                // deterministic line, so it is played once and accounted twice.
+                MsState t1 = s;
+                step(t1, a1, table_set_from_dealt(t1, dealt));
+                MsState t2 = t1;
+                int below = 1, slot2 = -1;
+                bool forced = st_terminal(t1);
+                if (!forced && __popc(st_hand(t1, p ^ 1)) == 1) {
+                    uint32_t l2;
+                    legal_list(t1, d.hand_order, p ^ 1, l2);
+                    slot2 = lookup_slot(sh.hk, sh.hs, sh.hcap, infoset_key(t1, p ^ 1));
+                    step(t2, l2 & 0xFu, table_set_from_dealt(t2, dealt));
+                    forced = st_terminal(t2);
+                    below = 2;
+                }
+                if (forced) {
+                    if (slot2 >= 0) sh.touched[slot2] = 1;
+                    const int r = reward0_x2(t2);
+                    ret_x2 = (tp == 0) ? r : -r;
+                    // regret delta = w * (cfv - sigma.cfv) = w * 0 exactly; strategy_sum += 1.0 * sigma = 1.0
+                    if (INPLACE) sh.str[4 * slot] = __dadd_rn(sh.str[4 * slot], 1.0);
+                    else atomicAdd(&sh.dcnt[slot], 1u);
+                    n_upd++;
+                    n_vis += 2 * below; call += 2u * (uint32_t)below; n_step += below;   // visits: reference-equivalent; steps: executed
+                    returning = true;
+                    continue;
+                }
+            }
             double sg[4];
             if (INPLACE) regret_match(sh.reg + 4 * slot, (int)nl, sg);
             else {
 #pragma unroll
                 for (int i = 0; i < 4; i++) sg[i] = sh.sig[4 * slot + i];
             }
-            sh.touched[slot] = 1;     // node created on first touch, for both players (mc_cfr.py:52)
-            if ((my_call >> 1) != xblk_id) {
-                xblk_id = my_call >> 1;
-                xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
+            int ai = 0;
+            if (nl > 1u) {
+                if ((my_call >> 1) != xblk_id) {
+                    xblk_id = my_call >> 1;
+                    xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
+                }
+                const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
+                ai = INPLACE ? sample_action(sg, (int)nl, u) : sample_cdf(sh.cdf + 4 * slot, (int)nl, u);
             }
-            const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
-            const int ai = INPLACE ? sample_action(sg, (int)nl, u) : sample_cdf(sh.cdf + 4 * slot, (int)nl, u);
             const uint32_t a = (list >> (4 * ai)) & 0xFu;
             if (p != tp) {            // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
                 ro = __dmul_rn(ro, sg[ai]);

@@ -93,27 +93,35 @@ __device__ __forceinline__ uint32_t nibble_remove(uint32_t order, uint32_t p) {
 //     Loops are bounded by the table length (early exit), which is warp-coherent in tree traversals.
 __device__ __forceinline__ uint32_t capture_mask(uint32_t order, uint32_t len, uint32_t card, uint32_t tset) {
     const uint32_t twin = card_twin(card);
-    if ((tset >> twin) & 1u) return 1u << nibble_pos(order, twin);
-    if (len < 2u) return 0u;                 // a sum needs two cards (a single equal card is the twin)
-    const uint32_t rank = card_rank(card);
-    uint32_t R[9];
-    R[0] = 1u;
+    const bool twin_hit = (tset >> twin) & 1u;
+    const bool need_dp = !twin_hit && len >= 2u;   // a sum needs two cards (a single equal card is the twin)
+    // Loop bound shared by the converged lanes (the longest table among those that need the subset
+    // search): the loops below then run without divergence, lanes with shorter tables are predicated.
+    const uint32_t bound = __reduce_max_sync(__activemask(), need_dp ? len : 0u);
+    uint32_t m = 0u;
+    if (bound) {
+        const uint32_t rank = card_rank(card);
+        uint32_t R[9];
+        R[0] = 1u;
+        uint32_t Rall = 1u;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        if ((uint32_t)i >= len) { R[i + 1] = R[i]; continue; }
-        const uint32_t ri = card_rank((order >> (4 * i)) & 0xFu);
-        R[i + 1] = (R[i] | (R[i] << ri)) & 0x7FFu;
-    }
-    if (!((R[8] >> rank) & 1u)) return 0u;
-    uint32_t t = rank, m = 0u;
+        for (int i = 0; i < 8; i++) {
+            if ((uint32_t)i >= bound) break;
+            const uint32_t ri = card_rank((order >> (4 * i)) & 0xFu);
+            if ((uint32_t)i < len) Rall = (Rall | (Rall << ri)) & 0x7FFu;
+            R[i + 1] = Rall;
+        }
+        uint32_t t = (need_dp && ((Rall >> rank) & 1u)) ? rank : 0u;
 #pragma unroll
-    for (int i = 7; i >= 0; i--) {
-        if ((uint32_t)i < len && t > 0u && !((R[i] >> t) & 1u)) {
-            m |= 1u << i;
-            t -= card_rank((order >> (4 * i)) & 0xFu);
+        for (int i = 7; i >= 0; i--) {
+            if ((uint32_t)i >= bound) continue;
+            if ((uint32_t)i < len && t > 0u && !((R[i] >> t) & 1u)) {
+                m |= 1u << i;
+                t -= card_rank((order >> (4 * i)) & 0xFu);
+            }
         }
     }
-    return m;
+    return twin_hit ? (1u << nibble_pos(order, twin)) : m;
 }
 
 // MiniScopaEnv.step (mini_scopa_game.py:140-167) + MiniScopaGame.play_card (:93-104).
