@@ -47,6 +47,7 @@ struct SdArgs {
     SdShape sh;
     SdLevelPtrs lvl[9];
     const float* net[2];          // fp32 parameter blobs (SD_NW floats each), per player
+    const unsigned char* img[2];  // bf16 shared-memory images of the nets (tensor-core path)
     uint32_t hand_order;
     uint2 pkey;
     unsigned long long first_trav;
@@ -120,7 +121,14 @@ __device__ __forceinline__ SdSmemFp32 sd_carve_fp32(unsigned char* raw, const fl
 // into TMEM, completion is signalled through tcgen05.commit -> mbarrier, and thread t reads ITS
 // accumulator row back with tcgen05.ld 32x32b for the bias + ReLU epilogue.
 constexpr int SD_K1 = 48;                        // 34 padded to a multiple of 16
-constexpr uint32_t SD_TM_D1 = 0, SD_TM_D2 = 128, SD_TM_D3 = 192;   // TMEM column offsets (256 columns allocated)
+// TMEM: 128 columns per CTA.  The three accumulators reuse the same columns: an accumulator is fully
+// read back (and a CTA barrier passed) before the next layer's MMA is issued.
+constexpr uint32_t SD_TM_COLS = 128, SD_TM_D1 = 0, SD_TM_D2 = 0, SD_TM_D3 = 0;
+constexpr int SD_CTAS_PER_SM = 3;
+// bf16 operand image of one net, as it sits in shared memory (built once per call by sd_prep_kernel):
+// w1 [128 x 48] | w2 [64 x 128] | w3 [16 x 64] in the UMMA canonical layout, then the fp32 biases
+constexpr int SD_IMG_W1 = 0, SD_IMG_W2 = SD_IMG_W1 + 2 * 128 * 48, SD_IMG_W3 = SD_IMG_W2 + 2 * 64 * 128,
+              SD_IMG_BIAS = SD_IMG_W3 + 2 * 16 * 64, SD_IMG_BYTES = SD_IMG_BIAS + 4 * (128 + 64 + 16);
 
 struct SdSmemTc {
     __nv_bfloat16* a;      // A operand tile, 128 rows x up to 128 k   (32 KB)
@@ -131,7 +139,7 @@ struct SdSmemTc {
     unsigned long long* bar;
     uint32_t* tmem_base;
 };
-constexpr size_t SD_SMEM_TC = 2 * (128 * 128 + 128 * SD_K1 + 64 * 128 + 16 * 64) + 4 * (128 + 64 + 16) + 64 + 1024;
+constexpr size_t SD_SMEM_TC = 2 * 128 * 128 + SD_IMG_BYTES + 64 + 1024;
 
 // canonical K-major no-swizzle tile with `rows` rows and K elements: core matrix (8 rows x 8 k) = 128 B;
 // K-adjacent core matrices are contiguous (LBO = 128 B), 8-row groups are K/8 core matrices apart
@@ -186,38 +194,46 @@ __device__ __forceinline__ void sd_tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ SdSmemTc sd_carve_tc(unsigned char* raw, const float* net) {
-    SdSmemTc sm;
-    unsigned char* p = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
-    sm.a = (__nv_bfloat16*)p; p += 2 * 128 * 128;
-    sm.w1 = (__nv_bfloat16*)p; p += 2 * 128 * SD_K1;
-    sm.w2 = (__nv_bfloat16*)p; p += 2 * 64 * 128;
-    sm.w3 = (__nv_bfloat16*)p; p += 2 * 16 * 64;
-    sm.bias = (float*)p; p += 4 * (128 + 64 + 16);
-    sm.bar = (unsigned long long*)p; p += 16;
-    sm.tmem_base = (uint32_t*)p;
-    const int tid = threadIdx.x, T = blockDim.x;
+// builds the shared-memory image of a net (bf16, canonical layout) in global memory, once per call
+__global__ void __launch_bounds__(256) sd_prep_kernel(const float* __restrict__ net, unsigned char* __restrict__ img) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
     for (int i = tid; i < 128 * SD_K1; i += T) {
         const int o = i / SD_K1, k = i % SD_K1;
-        *(__nv_bfloat16*)((char*)sm.w1 + sd_tile_off(o, k, SD_K1)) = __float2bfloat16(k < SD_IN ? net[SD_W1 + o * SD_IN + k] : 0.f);
+        *(__nv_bfloat16*)(img + SD_IMG_W1 + sd_tile_off(o, k, SD_K1)) = __float2bfloat16(k < SD_IN ? net[SD_W1 + o * SD_IN + k] : 0.f);
     }
     for (int i = tid; i < 64 * 128; i += T) {
         const int o = i / 128, k = i % 128;
-        *(__nv_bfloat16*)((char*)sm.w2 + sd_tile_off(o, k, 128)) = __float2bfloat16(net[SD_W2 + o * 128 + k]);
+        *(__nv_bfloat16*)(img + SD_IMG_W2 + sd_tile_off(o, k, 128)) = __float2bfloat16(net[SD_W2 + o * 128 + k]);
     }
     for (int i = tid; i < 16 * 64; i += T) {
         const int o = i / 64, k = i % 64;
-        *(__nv_bfloat16*)((char*)sm.w3 + sd_tile_off(o, k, 64)) = __float2bfloat16(net[SD_W3 + o * 64 + k]);
+        *(__nv_bfloat16*)(img + SD_IMG_W3 + sd_tile_off(o, k, 64)) = __float2bfloat16(net[SD_W3 + o * 64 + k]);
     }
-    for (int i = tid; i < 128; i += T) sm.bias[i] = net[SD_B1 + i];
-    for (int i = tid; i < 64; i += T) sm.bias[128 + i] = net[SD_B2 + i];
-    for (int i = tid; i < 16; i += T) sm.bias[192 + i] = net[SD_B3 + i];
+    float* bias = (float*)(img + SD_IMG_BIAS);
+    for (int i = tid; i < 128; i += T) bias[i] = net[SD_B1 + i];
+    for (int i = tid; i < 64; i += T) bias[128 + i] = net[SD_B2 + i];
+    for (int i = tid; i < 16; i += T) bias[192 + i] = net[SD_B3 + i];
+}
+
+__device__ __forceinline__ SdSmemTc sd_carve_tc(unsigned char* raw, const unsigned char* img) {
+    SdSmemTc sm;
+    unsigned char* p = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    sm.a = (__nv_bfloat16*)p; p += 2 * 128 * 128;
+    unsigned char* wimg = p;
+    sm.w1 = (__nv_bfloat16*)(p + SD_IMG_W1);
+    sm.w2 = (__nv_bfloat16*)(p + SD_IMG_W2);
+    sm.w3 = (__nv_bfloat16*)(p + SD_IMG_W3);
+    sm.bias = (float*)(p + SD_IMG_BIAS); p += SD_IMG_BYTES;
+    sm.bar = (unsigned long long*)p; p += 16;
+    sm.tmem_base = (uint32_t*)p;
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int i = tid; i < SD_IMG_BYTES / 16; i += T) ((uint4*)wimg)[i] = ((const uint4*)img)[i];
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(sm.bar)));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (tid < 32) {   // one warp allocates 256 TMEM columns and gives up the permit
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n"
+    if (tid < 32) {   // one warp allocates the TMEM columns and gives up the permit
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n"
                      :: "r"((uint32_t)__cvta_generic_to_shared(sm.tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -231,7 +247,7 @@ __device__ __forceinline__ void sd_release_tc(const SdSmemTc& sm) {
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(*sm.tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" :: "r"(*sm.tmem_base) : "memory");
 }
 
 // one layer: D[128 x N] = A[128 x K] * W[N x K]^T on the tensor cores; all 128 threads call it
@@ -257,32 +273,43 @@ __device__ __forceinline__ void sd_layer_mma(const SdSmemTc& sm, const __nv_bflo
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 }
 
+// 8 consecutive k-elements of one row are 16 contiguous bytes in the canonical layout: one 128-bit store
+__device__ __forceinline__ void sd_store8(const SdSmemTc& sm, int row, int k0, int K, const float* v) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]),
+                   p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 q;
+    q.x = *(uint32_t*)&p0; q.y = *(uint32_t*)&p1; q.z = *(uint32_t*)&p2; q.w = *(uint32_t*)&p3;
+    *(uint4*)((char*)sm.a + sd_tile_off(row, k0, K)) = q;
+}
+
 __device__ __forceinline__ void mlp_tc(const SdSmemTc& sm, const float* x, float* out, uint32_t& phase) {
     const int tid = threadIdx.x;
     const uint32_t lane_base = ((uint32_t)(tid & ~31)) << 16;      // TMEM address: lane in bits 31..16
     // layer 1: A = features (K padded to 48)
 #pragma unroll
-    for (int k = 0; k < SD_K1; k++)
-        *(__nv_bfloat16*)((char*)sm.a + sd_tile_off(tid, k, SD_K1)) = __float2bfloat16(k < SD_IN ? x[k] : 0.f);
+    for (int k0 = 0; k0 < SD_K1; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (k0 + i < SD_IN) ? x[k0 + i] : 0.f;
+        sd_store8(sm, tid, k0, SD_K1, v);
+    }
     sd_layer_mma(sm, sm.w1, SD_K1, SD_H1, SD_TM_D1, phase);
     for (int c = 0; c < SD_H1; c += 16) {
         float v[16];
         sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D1 + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const float h = v[i] + sm.bias[c + i];
-            *(__nv_bfloat16*)((char*)sm.a + sd_tile_off(tid, c + i, SD_H1)) = __float2bfloat16(h > 0.f ? h : 0.f);
-        }
+        for (int i = 0; i < 16; i++) { const float h = v[i] + sm.bias[c + i]; v[i] = h > 0.f ? h : 0.f; }
+        sd_store8(sm, tid, c, SD_H1, v);
+        sd_store8(sm, tid, c + 8, SD_H1, v + 8);
     }
     sd_layer_mma(sm, sm.w2, SD_H1, SD_H2, SD_TM_D2, phase);
     for (int c = 0; c < SD_H2; c += 16) {
         float v[16];
         sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D2 + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const float h = v[i] + sm.bias[128 + c + i];
-            *(__nv_bfloat16*)((char*)sm.a + sd_tile_off(tid, c + i, SD_H2)) = __float2bfloat16(h > 0.f ? h : 0.f);
-        }
+        for (int i = 0; i < 16; i++) { const float h = v[i] + sm.bias[128 + c + i]; v[i] = h > 0.f ? h : 0.f; }
+        sd_store8(sm, tid, c, SD_H2, v);
+        sd_store8(sm, tid, c + 8, SD_H2, v + 8);
     }
     sd_layer_mma(sm, sm.w3, SD_H2, SD_OUT, SD_TM_D3, phase);
     float v[16];
@@ -309,14 +336,15 @@ __device__ __forceinline__ void sd_policy(const float* raw, uint32_t legal_mask,
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(SD_TILE, 1) sd_mlp_kernel(const float* __restrict__ net, const float* __restrict__ feat,
+__global__ void __launch_bounds__(SD_TILE, SD_CTAS_PER_SM) sd_mlp_kernel(const float* __restrict__ net, const unsigned char* __restrict__ img,
+                                                            const float* __restrict__ feat,
                                                             const float* __restrict__ mask, float* __restrict__ adv_out,
                                                             float* __restrict__ pol_out, long long n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SdSmemFp32 s32{};
     SdSmemTc stc{};
     uint32_t phase = 0;
-    if (PREC == 0) s32 = sd_carve_fp32(smem_raw, net); else stc = sd_carve_tc(smem_raw, net);
+    if (PREC == 0) s32 = sd_carve_fp32(smem_raw, net); else stc = sd_carve_tc(smem_raw, img);
     const int tid = threadIdx.x;
     const long long tiles = (n + SD_TILE - 1) / SD_TILE;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -341,14 +369,14 @@ __global__ void __launch_bounds__(SD_TILE, 1) sd_mlp_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 // Forward level d: inference for every frontier node, then expand (traverser) or sample (opponent).
 template <int PREC>
-__global__ void __launch_bounds__(SD_TILE, 1) sd_forward_kernel(SdArgs a, int d) {
+__global__ void __launch_bounds__(SD_TILE, SD_CTAS_PER_SM) sd_forward_kernel(SdArgs a, int d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cp = d & 1;
     const bool trav = (cp == a.sh.player);
     SdSmemFp32 s32{};
     SdSmemTc stc{};
     uint32_t phase = 0;
-    if (PREC == 0) s32 = sd_carve_fp32(smem_raw, a.net[cp]); else stc = sd_carve_tc(smem_raw, a.net[cp]);
+    if (PREC == 0) s32 = sd_carve_fp32(smem_raw, a.net[cp]); else stc = sd_carve_tc(smem_raw, a.img[cp]);
     const int tid = threadIdx.x;
     const long long total = a.n_trav * a.sh.n[d];
     const long long tiles = (total + SD_TILE - 1) / SD_TILE;
@@ -406,6 +434,20 @@ __global__ void __launch_bounds__(SD_TILE, 1) sd_forward_kernel(SdArgs a, int d)
         }
     }
     if (PREC == 1) sd_release_tc(stc);
+}
+
+// Opponent level where the mover holds a single card: the move is forced, so the advantage net's
+// output cannot influence anything and no inference is run (the reference still calls the net there).
+__global__ void __launch_bounds__(256) sd_forced_kernel(SdArgs a, int d) {
+    const long long total = a.n_trav * a.sh.n[d];
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        MsState s = a.lvl[d].state[g];
+        uint32_t list;
+        legal_list(s, a.hand_order, d & 1, list);
+        step(s, list & 0xFu);
+        a.lvl[d + 1].state[g] = s;
+        a.lvl[d + 1].call[g] = a.lvl[d].call[g] + 1u;
+    }
 }
 
 __global__ void __launch_bounds__(256) sd_init_kernel(SdArgs a, uint4 root) {
@@ -505,6 +547,10 @@ static size_t sd_workspace(long long n_trav, int player, SdArgs* a, char* base) 
             a->lvl[d].value = (float*)(base + o_val); a->lvl[d].pol = (float4*)(base + o_pol);
         }
     }
+    for (int p = 0; p < 2; p++) {
+        size_t o_img = take(SD_IMG_BYTES);
+        if (a) a->img[p] = (const unsigned char*)(base + o_img);
+    }
     if (a) a->sh = sh;
     return off;
 }
@@ -531,15 +577,21 @@ int ms_mlp_forward(const float* d_net, int precision, const float* d_feat, const
     if (n < 0 || precision < 0 || precision > 1 || (n > 0 && (!d_net || !d_feat || !d_mask)))
         return fail(MS_ERR_ARG, "ms_mlp_forward: bad argument");
     if (n == 0) return MS_OK;
-    const int grid = grid_for(n, SD_TILE, 1);
+    cudaStream_t st = (cudaStream_t)stream;
     if (precision == 0) {
         MS_CUDA(cudaFuncSetAttribute(sd_mlp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_FP32));
-        sd_mlp_kernel<0><<<grid, SD_TILE, SD_SMEM_FP32, (cudaStream_t)stream>>>(d_net, d_feat, d_mask, d_adv, d_pol, (long long)n);
+        sd_mlp_kernel<0><<<grid_for(n, SD_TILE, 1), SD_TILE, SD_SMEM_FP32, st>>>(d_net, nullptr, d_feat, d_mask, d_adv, d_pol, (long long)n);
+        MS_LAUNCH_CHECK();
     } else {
+        unsigned char* img = nullptr;
+        MS_CUDA(cudaMallocAsync((void**)&img, SD_IMG_BYTES, st));      // stream-ordered scratch for the operand image
+        sd_prep_kernel<<<8, 256, 0, st>>>(d_net, img);
+        MS_LAUNCH_CHECK();
         MS_CUDA(cudaFuncSetAttribute(sd_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
-        sd_mlp_kernel<1><<<grid, SD_TILE, SD_SMEM_TC, (cudaStream_t)stream>>>(d_net, d_feat, d_mask, d_adv, d_pol, (long long)n);
+        sd_mlp_kernel<1><<<grid_for(n, SD_TILE, SD_CTAS_PER_SM), SD_TILE, SD_SMEM_TC, st>>>(d_net, img, d_feat, d_mask, d_adv, d_pol, (long long)n);
+        MS_LAUNCH_CHECK();
+        MS_CUDA(cudaFreeAsync(img, st));
     }
-    MS_LAUNCH_CHECK();
     return MS_OK;
 }
 
@@ -568,11 +620,22 @@ int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, c
     sd_init_kernel<<<grid_for(n_trav, 256, 4), 256, 0, st>>>(a, root);
     MS_LAUNCH_CHECK();
     if (precision == 0) MS_CUDA(cudaFuncSetAttribute(sd_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_FP32));
-    else MS_CUDA(cudaFuncSetAttribute(sd_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
+    else {
+        MS_CUDA(cudaFuncSetAttribute(sd_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
+        for (int p = 0; p < 2; p++) {
+            sd_prep_kernel<<<8, 256, 0, st>>>(a.net[p], (unsigned char*)a.img[p]);
+            MS_LAUNCH_CHECK();
+        }
+    }
     for (int d = 0; d < 8; d++) {
-        const int grid = grid_for(n_trav * a.sh.n[d], SD_TILE, 1);
-        if (precision == 0) sd_forward_kernel<0><<<grid, SD_TILE, SD_SMEM_FP32, st>>>(a, d);
-        else sd_forward_kernel<1><<<grid, SD_TILE, SD_SMEM_TC, st>>>(a, d);
+        const bool forced_opp = ((d & 1) != player) && (4 - d / 2 == 1);   // the opponent's last card
+        if (forced_opp) {
+            sd_forced_kernel<<<grid_for(n_trav * a.sh.n[d], 256, 8), 256, 0, st>>>(a, d);
+        } else if (precision == 0) {
+            sd_forward_kernel<0><<<grid_for(n_trav * a.sh.n[d], SD_TILE, 1), SD_TILE, SD_SMEM_FP32, st>>>(a, d);
+        } else {
+            sd_forward_kernel<1><<<grid_for(n_trav * a.sh.n[d], SD_TILE, SD_CTAS_PER_SM), SD_TILE, SD_SMEM_TC, st>>>(a, d);
+        }
         MS_LAUNCH_CHECK();
     }
     sd_terminal_kernel<<<grid_for(n_trav * a.sh.n[8], 256, 8), 256, 0, st>>>(a);

@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(32, 1) mccfr_inplace_kernel(SolverDev d, long 
     for (int i = tid; i < S; i += 32) d.touched[i] = touched[i];
 }
 
-constexpr int MCCFR_THREADS = 512;
+constexpr int MCCFR_THREADS = 640;
 
 __host__ __device__ inline size_t mccfr_batch_smem(int S, int hcap, int nframes, int threads) {
     size_t b = 0;
