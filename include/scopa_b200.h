@@ -164,6 +164,16 @@ int ms_solver_counters(ms_solver* s, uint64_t h_out[3], int reset, void* stream)
  *   touched, mc_cfr.py:118-130), 2 = uniform.  h_br_values[2]; exploitability = sum / 2. */
 int ms_best_response(ms_solver* s, int32_t policy_kind, double h_br_values[2], void* stream);
 
+/* ms_solver_policy: the table's average policy per slot -> d_policy [n_slots][4] f64 (probabilities over the
+ *   legal actions in hand order; policy_kind as in ms_best_response).
+ * ms_eval_policies: batched evaluate_agent (vanilla_cfr.py:157-216, mc_cfr.py:146-206): n_games episodes from
+ *   the root, seat 0 acting with d_policy_seat0 and seat 1 with d_policy_seat1 (same [n_slots][4] layout),
+ *   sampled from the Philox "EVAL" stream with episode ids first_game.. .  Outputs (may be NULL):
+ *   d_reward0 [n] f32 = player 0's terminal reward, d_scopas [n][2] u8. */
+int ms_solver_policy(ms_solver* s, int32_t policy_kind, double* d_policy, void* stream);
+int ms_eval_policies(ms_solver* s, const double* d_policy_seat0, const double* d_policy_seat1, int64_t n_games,
+                     uint64_t philox_seed, uint64_t first_game, float* d_reward0, uint8_t* d_scopas, void* stream);
+
 /* -------------------------------------------------------------------------------- SDCFR ------
  * Advantage network = FlexibleNet mlp 34 -> 128 -> 64 -> 16 with ReLU (src/algorithms/deep_cfr/nets.py:151-235,
  * :296-331; deep_cfr.py:24-52).  A net is passed as ONE fp32 blob of 13776 floats in nn.Linear order:

@@ -108,13 +108,26 @@ class MCCFRTrainer:
         return self.solver.exploitability(1)
 
     def tabular_policy(self):
-        return ScopaLearnedPolicy(self.game, self.info_sets)
+        pol = ScopaLearnedPolicy(self.game, self.info_sets)
+        pol._solver = self.solver          # lets evaluate_agent play the episodes on the GPU
+        return pol
+
+
+def _mccfr_probs(node):
+    total = node.strategy_sum.sum()
+    if total > 1e-12:
+        return node.strategy_sum / total
+    return np.ones(len(node.legal_actions)) / len(node.legal_actions)
 
 
 class ScopaLearnedPolicy(Policy):
     def __init__(self, game, info_sets):
         super().__init__(game, list(range(game.num_players())))
         self.info_sets = info_sets
+        self._solver = None
+
+    def _device_table(self, solver):
+        return solver.policy_table_from_dict(self.info_sets, lambda p, s: (p, s), _mccfr_probs)
 
     def action_probabilities(self, state):
         if state.is_terminal():
@@ -139,6 +152,9 @@ class RandomPolicy(Policy):
 
     def __init__(self, game):
         super().__init__(game, list(range(game.num_players())))
+
+    def _device_table(self, solver):
+        return solver.uniform_policy()
 
     def action_probabilities(self, state):
         if state.is_terminal():

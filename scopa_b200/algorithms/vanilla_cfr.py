@@ -91,7 +91,9 @@ class CFRTrainer:
         return v
 
     def get_openspiel_policy(self):
-        return LearnedCFRPolicy(self.game, self.info_set_map)
+        pol = LearnedCFRPolicy(self.game, self.info_set_map)
+        pol._solver = self.solver          # lets evaluate_agent play the episodes on the GPU
+        return pol
 
     def exploitability(self):
         """Best-response exploitability of the current average policy (device sweep)."""
@@ -116,6 +118,10 @@ class LearnedCFRPolicy(Policy):
     def __init__(self, game, info_set_map):
         super().__init__(game, list(range(game.num_players())))
         self.info_set_map = info_set_map
+        self._solver = None
+
+    def _device_table(self, solver):
+        return solver.policy_table_from_dict(self.info_set_map, lambda p, s: s, lambda node: node.policy)
 
     def action_probabilities(self, state):
         if state.is_terminal():
@@ -136,14 +142,48 @@ class RandomPolicy(Policy):
     def __init__(self, game):
         super().__init__(game, list(range(game.num_players())))
 
+    def _device_table(self, solver):
+        return solver.uniform_policy()
+
     def action_probabilities(self, state):
         legal_actions = state.legal_actions()
         prob = 1.0 / len(legal_actions)
         return {action: prob for action in legal_actions}
 
 
-def evaluate_agent(game, trained_policy, opponent_policy, num_episodes=10000):
-    """Reference vanilla_cfr.py:157-216: episodes vs an opponent, seats swapped at half time."""
+def _evaluate_agent_device(solver, trained_policy, opponent_policy, num_episodes, seed):
+    """All episodes in two launches (agent in seat 0 for the first half, seat 1 for the second)."""
+    t_tab, o_tab = trained_policy._device_table(solver), opponent_policy._device_table(solver)
+    n0 = int(np.ceil(num_episodes / 2))                      # episodes with `episode < num_episodes / 2`
+    n1 = num_episodes - n0
+    r_a, s_a = solver.evaluate(t_tab, o_tab, n0, philox_seed=seed, first_game=0)
+    r_b, s_b = solver.evaluate(o_tab, t_tab, n1, philox_seed=seed, first_game=n0)
+    rew = np.concatenate([r_a.cpu().numpy().astype(np.float64), -r_b.cpu().numpy().astype(np.float64)])
+    s_a, s_b = s_a.cpu().numpy().astype(np.int64), s_b.cpu().numpy().astype(np.int64)
+    trained = np.concatenate([s_a[:, 0], s_b[:, 1]])
+    opp = np.concatenate([s_a[:, 1], s_b[:, 0]])
+    k = np.arange(1, num_episodes + 1)
+    ct, co = np.cumsum(trained), np.cumsum(opp)
+    avg_reward_history = (np.cumsum(rew) / k).tolist()
+    scopa_history = {'trained': (ct / k).tolist(), 'opponent': (co / k).tolist(), 'diff': ((ct - co) / k).tolist()}
+    avg_t, avg_o = trained.sum() / num_episodes, opp.sum() / num_episodes
+    scopa_stats = {'trained_avg': avg_t, 'opponent_avg': avg_o, 'difference': avg_t - avg_o, 'history': scopa_history,
+                   'data_collected': num_episodes > 0}
+    return rew.sum() / num_episodes, avg_reward_history, scopa_stats
+
+
+def evaluate_agent(game, trained_policy, opponent_policy, num_episodes=10000, seed=None):
+    """Reference vanilla_cfr.py:157-216: episodes vs an opponent, seats swapped at half time.
+
+    When both policies come from this package (tabular policies of a CUDA trainer, RandomPolicy) the episodes
+    are played on the GPU in two launches (Philox stream `seed`, default drawn from np.random so that
+    np.random.seed() still makes runs repeatable); any other policy object takes the reference's scalar loop."""
+    solver = getattr(trained_policy, "_solver", None) or getattr(opponent_policy, "_solver", None)
+    if (solver is not None and num_episodes > 0 and hasattr(trained_policy, "_device_table")
+            and hasattr(opponent_policy, "_device_table")):
+        if seed is None:
+            seed = int(np.random.randint(0, 2**31 - 1))
+        return _evaluate_agent_device(solver, trained_policy, opponent_policy, num_episodes, seed)
     total_winnings = 0
     avg_reward_history = []
     trained_scopas = 0

@@ -755,6 +755,50 @@ __global__ void __launch_bounds__(512, 1) best_response_kernel(SolverDev d, int 
     }
 }
 
+// the table's average policy per slot (probabilities over the legal actions in hand order)
+__global__ void __launch_bounds__(256) policy_kernel(SolverDev d, int kind, double* out) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < d.n_slots; s += gridDim.x * blockDim.x) {
+        double p[4];
+        avg_policy(d, s, kind, p);
+        for (int i = 0; i < 4; i++) out[4 * s + i] = p[i];
+    }
+}
+
+// Batched evaluate_agent (vanilla_cfr.py:157-216 / mc_cfr.py:146-206): one thread plays one episode from
+// the root, seat 0 acting with pol0 and seat 1 with pol1 (per-slot probabilities over the legal actions in
+// hand order), sampling with numpy's rule from the Philox "EVAL" stream (ctr = episode id, ply/2).
+#define MS_TAG_EVAL 0x4C415645u
+__global__ void __launch_bounds__(256) eval_kernel(SolverDev d, const double* __restrict__ pol0,
+                                                   const double* __restrict__ pol1, long long n, uint2 pkey,
+                                                   unsigned long long first, float* __restrict__ out_reward0,
+                                                   uchar2* __restrict__ scopas) {
+    const uint32_t dealt = dealt_set(d.root);
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
+        MsState s = d.root;
+        const unsigned long long eid = first + (unsigned long long)g;
+        uint4 xb = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t ply = 0; ply < 32u && !st_terminal(s); ply++) {
+            const int p = st_cur(s);
+            uint32_t list;
+            const uint32_t nl = legal_list(s, d.hand_order, p, list);
+            uint32_t ai = 0u;
+            if (nl > 1u) {
+                const int slot = lookup_slot(d.hkeys, d.hslots, d.hcap, infoset_key(s, p));
+                const double* pr = (p == 0 ? pol0 : pol1) + 4 * slot;
+                if ((ply & 1u) == 0u)
+                    xb = philox4x32_10(make_uint4((uint32_t)eid, (uint32_t)(eid >> 32), ply >> 1, MS_TAG_EVAL), pkey);
+                const double u = (ply & 1u) ? u53(xb.z, xb.w) : u53(xb.x, xb.y);
+                double sg[4];
+                for (int i = 0; i < 4; i++) sg[i] = pr[i];
+                ai = (uint32_t)sample_action(sg, (int)nl, u);
+            }
+            step(s, (list >> (4u * ai)) & 0xFu, table_set_from_dealt(s, dealt));
+        }
+        if (out_reward0) out_reward0[g] = st_terminal(s) ? reward0(s) : 0.f;
+        if (scopas) scopas[g] = make_uchar2((unsigned char)st_scopas(s, 0), (unsigned char)st_scopas(s, 1));
+    }
+}
+
 }  // namespace ms
 
 using namespace ms;
@@ -1098,6 +1142,27 @@ int ms_solver_counters(ms_solver* s, uint64_t h_out[3], int reset, void* stream)
         MS_CUDA(cudaStreamSynchronize(st));
     }
     if (reset) MS_CUDA(cudaMemsetAsync(s->dev.counters, 0, 32, st));
+    return MS_OK;
+}
+
+int ms_solver_policy(ms_solver* s, int32_t policy_kind, double* d_policy, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (policy_kind < 0 || policy_kind > 2 || !d_policy) return fail(MS_ERR_ARG, "ms_solver_policy: bad argument");
+    policy_kernel<<<(s->n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(s->dev, policy_kind, d_policy);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_eval_policies(ms_solver* s, const double* d_policy_seat0, const double* d_policy_seat1, int64_t n_games,
+                     uint64_t philox_seed, uint64_t first_game, float* d_reward0, uint8_t* d_scopas, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (n_games < 0 || !d_policy_seat0 || !d_policy_seat1) return fail(MS_ERR_ARG, "ms_eval_policies: bad argument");
+    if (n_games == 0) return MS_OK;
+    eval_kernel<<<grid_for(n_games, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        s->dev, d_policy_seat0, d_policy_seat1, (long long)n_games,
+        make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)), (unsigned long long)first_game, d_reward0,
+        (uchar2*)d_scopas);
+    MS_LAUNCH_CHECK();
     return MS_OK;
 }
 

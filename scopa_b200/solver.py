@@ -182,6 +182,38 @@ class Solver:
             _lib.check(self.lib.ms_best_response(self.h, int(policy_kind), out, self._stream()))
         return [out[0], out[1]]
 
+    def average_policy(self, policy_kind):
+        """-> torch float64 [S, 4]: the table's average policy per slot (device tensor)."""
+        out = torch.empty((self.n_slots, 4), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_solver_policy(self.h, int(policy_kind), out.data_ptr(), self._stream()))
+        return out
+
+    def uniform_policy(self):
+        return self.average_policy(2)
+
+    def policy_table_from_dict(self, mapping, key_fn, probs_fn):
+        """[S, 4] policy tensor from a host dict of InfoNode-like objects; slots missing from the dict are
+        uniform (LearnedCFRPolicy / ScopaLearnedPolicy fallbacks)."""
+        st = self.static_table()
+        tab = np.zeros((self.n_slots, 4))
+        for s in range(self.n_slots):
+            n = int(st["nlegal"][s])
+            node = mapping.get(key_fn(int(st["player"][s]), st["strings"][s]))
+            tab[s, :n] = probs_fn(node) if node is not None else 1.0 / n
+        return torch.from_numpy(tab).to(self.device)
+
+    def evaluate(self, policy_seat0, policy_seat1, n_games, philox_seed=0, first_game=0):
+        """Play n_games episodes on the device -> (reward of player 0 [n] f32, scopas [n, 2] u8) CUDA tensors."""
+        p0 = policy_seat0.to(dtype=torch.float64).contiguous()
+        p1 = policy_seat1.to(dtype=torch.float64).contiguous()
+        rew = torch.empty((n_games,), dtype=torch.float32, device=self.device)
+        sc = torch.empty((n_games, 2), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_eval_policies(self.h, p0.data_ptr(), p1.data_ptr(), int(n_games), int(philox_seed),
+                                                 int(first_game), rew.data_ptr(), sc.data_ptr(), self._stream()))
+        return rew, sc
+
     def exploitability(self, policy_kind):
         """(sum_b BR_b(root) - utility_sum) / num_players with utility_sum = 0 (zero-sum game)."""
         v = self.best_response_values(policy_kind)

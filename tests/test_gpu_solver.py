@@ -226,3 +226,58 @@ def test_mccfr_exploitability_curve_matches_reference_shape():
         assert abs(v - rv) < max(0.05, 4.0 * s), (m, v, rv, s)
     assert mean[-1] < mean[1] < mean[0]
     assert 0.40 < mean[-1] < 0.60            # the reference estimator's plateau (about 0.49)
+
+
+def _exact_value_p0(sv, pol0, pol1):
+    """Exact expected reward of player 0 when seat p acts with pol_p: plain tree evaluation on the host."""
+    t = sv.tree()
+    states = t["state"]
+    val = np.zeros(sv.n_nodes)
+    for v in range(sv.n_nodes - 1, -1, -1):
+        n, c0 = int(t["nchild"][v]), int(t["child_begin"][v])
+        w = states[v]
+        if n == 0:
+            s0 = bin(int(w[2]) & 0xFFFF).count("1") + 2 * ((int(w[3]) >> 4) & 0xF)
+            s1 = bin(int(w[2]) >> 16).count("1") + 2 * ((int(w[3]) >> 8) & 0xF)
+            val[v] = 0.5 * (s0 - s1)
+        else:
+            cur = (int(w[3]) >> 17) & 1
+            pr = (pol0 if cur == 0 else pol1)[int(t["slot"][v]), :n]
+            val[v] = float(np.dot(pr, val[c0:c0 + n]))
+    return val[0]
+
+
+def test_batched_policy_evaluation_matches_exact_expectation():
+    sv = Solver(seed=42)
+    sv.cfr_iterate(30)
+    trained, uni = sv.average_policy(0), sv.uniform_policy()
+    t_np, u_np = trained.cpu().numpy(), uni.cpu().numpy()
+    assert np.allclose(t_np.sum(1), 1) and np.allclose(u_np.sum(1), 1)
+    n = 400_000
+    for p0, p1, a, b in ((trained, uni, t_np, u_np), (uni, trained, u_np, t_np), (uni, uni, u_np, u_np)):
+        rew, sc = sv.evaluate(p0, p1, n, philox_seed=12)
+        exact = _exact_value_p0(sv, a, b)
+        r = rew.double()
+        se = float(r.std().item()) / np.sqrt(n)
+        assert abs(float(r.mean().item()) - exact) < 5 * se + 1e-9, (exact, float(r.mean().item()), se)
+        assert int(sc.max().item()) <= 4
+    # uniform vs uniform: player 0's on-policy value of the uniform profile (SURVEY 6: -0.9201)
+    assert abs(_exact_value_p0(sv, u_np, u_np) - (-0.9201)) < 1e-3
+
+
+def test_evaluate_agent_uses_the_device_path():
+    from scopa_b200 import pyspiel_compat as pyspiel
+    from scopa_b200.envs import openspiel_mini_scopa  # noqa: F401
+    from scopa_b200.algorithms.vanilla_cfr import CFRTrainer, RandomPolicy, evaluate_agent
+    game = pyspiel.load_game("mini_scopa")
+    tr = CFRTrainer(game)
+    tr.train(50)
+    np.random.seed(0)
+    avg, hist, stats = evaluate_agent(game, tr.get_openspiel_policy(), RandomPolicy(game), num_episodes=20001)
+    assert len(hist) == 20001 and abs(hist[-1] - avg) < 1e-12 and len(stats["history"]["diff"]) == 20001
+    # exact expectation of the seat-swapped protocol
+    sv = tr.solver
+    t_np, u_np = sv.average_policy(0).cpu().numpy(), sv.uniform_policy().cpu().numpy()
+    exact = (10001 * _exact_value_p0(sv, t_np, u_np) - 10000 * _exact_value_p0(sv, u_np, t_np)) / 20001
+    assert abs(avg - exact) < 0.08
+    assert stats["trained_avg"] > stats["opponent_avg"]
