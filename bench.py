@@ -253,6 +253,49 @@ def run_ours(args):
                "h2d_bytes_per_step": 8 * G, "d2h_bytes_per_step": 16 * G,
                "what": "ms_rollout_random_host: reset(seed) + 8 steps per game, host buffers in and out"}
 
+    # ------------------------------------------------------------------ step-granular env API (HBM-bound kernels)
+    # ms_step round-trips the 16-byte state through HBM: the one kernel family here whose real bound IS the HBM
+    # roofline (33 B/step + 8 B rewards + 1 B done = 42 B moved per step with all outputs requested)
+    NS = args.step_states
+    bs = BatchedMiniScopa(dev).reset(np.arange(1, NS + 1, dtype=np.int64))
+    _, ordered0, _ = bs.legal_actions()
+    acts_u8 = ordered0[:, 0].contiguous()                  # first legal card of every game
+    st_backup = bs.states.clone()
+    rew_s = torch.empty((NS, 2), dtype=torch.float32, device=dev)
+    done_t = torch.empty((NS,), dtype=torch.uint8, device=dev)
+    for i in range(W):
+        bs.step(acts_u8, rewards=rew_s, done=done_t)
+    stev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for i in range(K):
+        bs.states.copy_(st_backup)
+        flush_l2()
+        stev[i][0].record()
+        bs.step(acts_u8, rewards=rew_s, done=done_t)
+        stev[i][1].record()
+    barrier()
+    step_ms = sum(a.elapsed_time(c) for a, c in stev) / K
+    step_obj = {"kernel": "step_kernel", "env_steps_per_sec": NS / (step_ms * 1e-3), "kernel_ms": step_ms,
+                "bytes_per_step": 42, "achieved_gbs": 42.0 * NS / (step_ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": 42.0 * NS / (step_ms * 1e-3) / 1e9 / hbm_gbs,
+                "note": f"{NS} states ({16 * NS >> 20} MiB, larger than L2), one ply per launch, state + action in, "
+                        "state + rewards + done out"}
+    del bs, st_backup, rew_s, done_t
+
+    # ------------------------------------------------------------------ vanilla CFR (config 1)
+    cfr_sv = Solver(seed=42, device=dev)
+    cfr_sv.cfr_iterate(5)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    cfr_sv.cfr_iterate(200)
+    c1.record()
+    torch.cuda.synchronize()
+    cfr_obj = {"kernel": "cfr_kernel", "us_per_iteration": c0.elapsed_time(c1) * 1e3 / 200,
+               "node_visits_per_sec": 2 * 2229 * 200 / (c0.elapsed_time(c1) * 1e-3),
+               "note": "BASELINE.json configs[0]: vanilla CFR on the seed-42 deal, 200 iterations in one launch, float64, "
+                       "bit-identical to the reference's tables; the reference takes 389 ms per iteration on one CPU core"}
+
     # ------------------------------------------------------------------ SDCFR traversal (config 4)
     from scopa_b200 import sdcfr as sd
     T = args.sd_trav
@@ -338,6 +381,8 @@ def run_ours(args):
         "wall_s_mccfr_region": wall,
         ("env" if primary is mccfr_obj else "mccfr"): secondary,
         "sdcfr": sd_obj,
+        "env_step_api": step_obj,
+        "cfr": cfr_obj,
     }
     if primary is mccfr_obj:
         line["node_visits_per_sec"] = mccfr_obj["node_visits_per_sec"]
@@ -362,6 +407,10 @@ def cpu_baselines(args, sample_seconds, threads=None):
                  "sample": f"{per_thread} traversal pairs x {cores} independent workers ({u} updates, {dt:.2f} s); "
                            "oracle/ms_oracle.c, frozen-sigma batches",
                  "node_visits_per_sec": v / dt}
+    t0 = time.perf_counter()
+    tab = ora.Table()
+    tab.cfr_train(20)
+    cpu_mccfr["vanilla_cfr_ms_per_iteration_1core"] = (time.perf_counter() - t0) * 1e3 / 20
     seeds = np.arange(1, 200_001, dtype=np.int64)
     t0 = time.perf_counter()
     ora.rollout_random(seeds, args.seed, nthreads=cores)
@@ -432,6 +481,7 @@ def main():
     ap.add_argument("--trav", type=int, default=284160, help="traversals per player per GPU per step")
     ap.add_argument("--games", type=int, default=1_000_000, help="concurrent games per GPU")
     ap.add_argument("--sd-trav", type=int, default=16384, help="SDCFR traversals per player per GPU per step")
+    ap.add_argument("--step-states", type=int, default=16_000_000, help="states in the step-granular API measurement")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--ref-trav", type=int, default=1500)

@@ -403,3 +403,52 @@ if __name__ == "__main__":
         gen_policies_eval()
     if "sdcfr" in which:
         gen_sdcfr()
+
+
+# --------------------------------------------------------------------------- SDCFR curve (appended)
+def gen_sdcfr_curve():
+    """Exploitability (restated BR) of the reference DeepCFR's average policy after k iterations, 3 trials.
+    Seeds follow the reference's run_experiments.py:33-34 (torch / numpy seeded with trial_id * 42)."""
+    import contextlib
+    import torch
+    import deep_cfr as ref_dcfr
+    import ms_exploit
+    ref_dcfr.tqdm = lambda *a, **k: _NoBar()
+    game = pyspiel.load_game("mini_scopa")
+
+    class SdPolicy:
+        def __init__(self, d):
+            self.d, self.cache = d, {}
+
+        def action_probabilities(self, state):
+            cp = state.current_player()
+            key = state.information_state_string(cp)
+            legal = state.legal_actions(cp)
+            if key not in self.cache:
+                p = self.d.get_policy(state, cp)
+                ap = np.array([p[a] for a in legal], dtype=np.float64)
+                if np.any(np.isnan(ap)) or ap.sum() <= 0:          # evaluate_vs_random's fallback (:387-390)
+                    ap = np.ones(len(legal)) / len(legal)
+                else:
+                    ap = ap / ap.sum()
+                self.cache[key] = ap
+            return dict(zip(legal, self.cache[key]))
+
+    out = {"iterations": [5, 10, 20, 30], "trials": []}
+    for trial in range(3):
+        row = []
+        for iters in out["iterations"]:
+            torch.manual_seed(trial * 42)
+            np.random.seed(trial * 42)
+            random.seed(trial * 42)
+            with contextlib.redirect_stdout(io.StringIO()):
+                d = ref_dcfr.DeepCFR(game, 2, "cpu")
+                d.train(iterations=iters, advantage_epochs=5, eval_freq=10 ** 9)
+            row.append(ms_exploit.exploitability(game, SdPolicy(d)))
+            print(f"SDCFR trial {trial} iters {iters}: exploitability {row[-1]:.4f}", flush=True)
+        out["trials"].append(row)
+    dump_json("sdcfr_curve.json", out)
+
+
+if __name__ == "__main__" and "sdcfr_curve" in sys.argv[1:]:
+    gen_sdcfr_curve()

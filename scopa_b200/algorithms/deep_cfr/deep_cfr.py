@@ -278,6 +278,57 @@ class DeepCFR:
             if iteration % eval_freq == 0 and eval_episodes > 0:
                 self.evaluate_vs_random(num_episodes=eval_episodes)
 
+    # -- whole-game views of the average policy (device-batched; not in the reference) --------------------
+    def average_policy_table(self):
+        """[S, 4] float64 CUDA tensor: get_policy() of every infoset of the deal at once, restricted to the legal
+        actions in hand order and normalised the way evaluate_vs_random does (uniform if the sum is <= 0)."""
+        from ...solver import Solver
+        if getattr(self, "_solver", None) is None:
+            self._solver = Solver(self._root[0], self._root[1], device=self.device)
+        sv = self._solver
+        st = sv.static_table()
+        S = sv.n_slots
+        feat = np.zeros((S, 34), dtype=np.float32)
+        mask = np.zeros((S, 16), dtype=np.float32)
+        for s in range(S):
+            f = codec.key_fields(st["keys"][s])
+            for c in range(16):
+                feat[s, c] = (f["hand_mask"] >> c) & 1
+            for c in f["table"]:
+                feat[s, 16 + c] = 1.0
+            feat[s, 32] = 1.0
+            mask[s] = feat[s, :16]
+        x = torch.from_numpy(feat).to(self.device)
+        m = torch.from_numpy(mask).to(self.device)
+        legal = torch.from_numpy(np.where(st["legal"] == 255, 0, st["legal"]).astype(np.int64)).to(self.device)
+        nl = torch.from_numpy(st["nlegal"].astype(np.int64)).to(self.device)
+        player = torch.from_numpy(st["player"]).to(self.device)
+        pol16 = torch.zeros((S, 16), dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            for p in range(self.num_players):
+                buf = self.strategy_buffers[p]
+                rows = player == p
+                if not buf.strategies:
+                    pol16[rows] = m[rows] / m[rows].sum(1, keepdim=True)
+                    continue
+                tot = float(sum(buf.weights))
+                acc = torch.zeros((int(rows.sum()), 16), dtype=torch.float32, device=self.device)
+                for net, w in zip(buf.strategies, buf.weights):
+                    acc += positive_regret_policy(net(x[rows]), m[rows]) * (w / tot)
+                pol16[rows] = acc
+        tab = torch.gather(pol16.double(), 1, legal)
+        valid = torch.arange(4, device=self.device).unsqueeze(0) < nl.unsqueeze(1)
+        tab = tab * valid
+        ssum = tab.sum(1, keepdim=True)
+        uni = valid.double() / nl.unsqueeze(1).double()
+        return torch.where(ssum > 0, tab / ssum.clamp_min(1e-300), uni)
+
+    def exploitability(self):
+        """Best-response exploitability of the average policy (device sweep, restated open_spiel BR)."""
+        tab = self.average_policy_table()
+        self._solver.import_table(strategy=tab.cpu().numpy())
+        return self._solver.exploitability(0)
+
     def get_policy(self, state, player):
         """Get average policy for a state."""
         return self.strategy_buffers[player].get_average_policy(self._state_to_features(state, player),

@@ -201,11 +201,18 @@ __device__ void cfr_traversal(const SolverDev& d, const CfrSmem& m, int tp, doub
                 double acc = 0.0;
                 for (int i = 0; i < nc; i++) acc = __dadd_rn(acc, __dmul_rn(sg[i], m.u[cb + i]));
                 m.u[v] = acc;
+            } else if (nc == 1) {
+                // traverser node with one legal action: sigma = [1.0] before and after the visit and the
+                // regret delta is opp * (u - 1.0 * u) = 0, so there is no chain dependency: per-node work
+                const int cb = m.child_begin[v];
+                m.u[v] = __dadd_rn(0.0, __dmul_rn(1.0, m.u[cb]));
+                m.u[cb] = 1.0;                            // sigma_used, parked like the chain does
             }
         }
         if (cp == tp) {
             for (int s = s_slvl[l] + tid; s < s_slvl[l + 1]; s += bd) {
                 const int n = m.nlegal[s];
+                if (n == 1) continue;                     // handled per node above
                 double reg[4], sg[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) { reg[i] = m.reg[4 * s + i]; sg[i] = m.sig[4 * s + i]; }
