@@ -478,7 +478,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mccfr", choices=["mccfr", "rollout"])
-    ap.add_argument("--trav", type=int, default=284160, help="traversals per player per GPU per step")
+    ap.add_argument("--trav", type=int, default=340992, help="traversals per player per GPU per step")
     ap.add_argument("--games", type=int, default=1_000_000, help="concurrent games per GPU")
     ap.add_argument("--sd-trav", type=int, default=16384, help="SDCFR traversals per player per GPU per step")
     ap.add_argument("--step-states", type=int, default=16_000_000, help="states in the step-granular API measurement")

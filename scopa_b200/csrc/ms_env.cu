@@ -289,22 +289,24 @@ __global__ void __launch_bounds__(256) rollout_kernel(const uint4* __restrict__ 
         const uint32_t ho = hand_order[g];
         const uint32_t dealt = dealt_set(s);
         const unsigned long long gid = game_offset + (unsigned long long)g;
-        uint32_t acts[2] = {0u, 0u};
-#pragma unroll
-        for (int blk = 0; blk < 2; blk++) {
-            const uint4 x = philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)blk, MS_TAG_ROLL), key);
-            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint32_t list;
-                const uint32_t nl = legal_list(s, ho, st_cur(s), list);
-                const uint32_t idx = __umulhi(xs[q], nl);
-                const uint32_t a = (list >> (4u * idx)) & 0xFu;
-                step(s, a, table_set_from_dealt(s, dealt));
-                acts[blk] |= a << (8 * q);
-            }
+        // the ply loop is deliberately NOT unrolled: one copy of step() (about 6 KB of SASS) stays resident in
+        // the instruction cache instead of eight (the unrolled kernel was 50 KB, beyond the 32 KB L1.5 I-cache)
+        unsigned long long acts = 0ull;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+        for (int ply = 0; ply < 8; ply++) {
+            if ((ply & 3) == 0)
+                x = philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(ply >> 2), MS_TAG_ROLL), key);
+            const int q = ply & 3;
+            const uint32_t xw = q == 0 ? x.x : (q == 1 ? x.y : (q == 2 ? x.z : x.w));
+            uint32_t list;
+            const uint32_t nl = legal_list(s, ho, st_cur(s), list);
+            const uint32_t idx = __umulhi(xw, nl);
+            const uint32_t a = (list >> (4u * idx)) & 0xFu;
+            step(s, a, table_set_from_dealt(s, dealt));
+            acts |= (unsigned long long)a << (8 * ply);
         }
-        if (actions8) actions8[g] = make_uint2(acts[0], acts[1]);
+        if (actions8) actions8[g] = make_uint2((uint32_t)acts, (uint32_t)(acts >> 32));
         if (rewards) {
             float r0 = st_terminal(s) ? reward0(s) : 0.f;
             rewards[g] = make_float2(r0, 0.f - r0);   // r1 = s1 - mean: +0.0 on a tie, never -0.0

@@ -393,12 +393,18 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
     int fi = -1;
     uint4 xblk = make_uint4(0u, 0u, 0u, 0u);   // cached Philox block: serves call indices 2b and 2b+1
     uint32_t xblk_id = 0xFFFFFFFFu;
+    // Descents are deferred to the top of the loop so that step() -- the largest piece of code here -- is
+    // instantiated once instead of at every descent site (the kernel was 57 KB of SASS, beyond the 32 KB
+    // L1.5 instruction cache; ncu showed no_instruction stalls).
+    bool pend = false;
+    uint32_t pend_a = 0u;
     uint32_t call = 0;
     int ret_x2 = 0;
     bool returning = false;
     const uint32_t tag = MS_TAG_MCCF + (uint32_t)tp;
     while (true) {
         if (!returning) {
+            if (pend) { step(s, pend_a, table_set_from_dealt(s, dealt)); n_step++; pend = false; }
             const uint32_t my_call = call++;
             n_vis++;
             if (st_terminal(s)) {
@@ -417,24 +423,26 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
                 // random word is generated (the call index still advances: the oracle's draw is a no-op too).
                 const uint32_t a1 = list & 0xFu;
                 if (p != tp) {            // opponent: reach *= 1.0
-                    step(s, a1, table_set_from_dealt(s, dealt)); n_step++;
+                    pend_a = a1; pend = true;
                     continue;
                 }
                 // Traverser's last card.  If the rest of the game is forced as well (the opponent holds at
                 // most one card) both recursive calls of the reference (:58-67 and :71-78) walk the same
                 // deterministic line, so it is played once and accounted twice.
-                MsState t1 = s;
-                step(t1, a1, table_set_from_dealt(t1, dealt));
-                MsState t2 = t1;
-                int below = 1, slot2 = -1;
-                bool forced = st_terminal(t1);
-                if (!forced && __popc(st_hand(t1, p ^ 1)) == 1) {
+                MsState t2 = s;
+                int below = 0, slot2 = -1;
+                bool forced = false;
+                uint32_t act = a1;
+#pragma unroll 1
+                for (int k = 0; k < 2; k++) {
+                    step(t2, act, table_set_from_dealt(t2, dealt));
+                    below++;
+                    if (st_terminal(t2)) { forced = true; break; }
+                    if (k == 1 || __popc(st_hand(t2, p ^ 1)) != 1) break;
                     uint32_t l2;
-                    legal_list(t1, d.hand_order, p ^ 1, l2);
-                    slot2 = lookup_slot(sh.hk, sh.hs, sh.hcap, infoset_key(t1, p ^ 1));
-                    step(t2, l2 & 0xFu, table_set_from_dealt(t2, dealt));
-                    forced = st_terminal(t2);
-                    below = 2;
+                    legal_list(t2, d.hand_order, p ^ 1, l2);
+                    slot2 = lookup_slot(sh.hk, sh.hs, sh.hcap, infoset_key(t2, p ^ 1));
+                    act = l2 & 0xFu;
                 }
                 if (forced) {
                     if (slot2 >= 0) sh.touched[slot2] = 1;
@@ -467,7 +475,7 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
             const uint32_t a = (list >> (4 * ai)) & 0xFu;
             if (p != tp) {            // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
                 ro = __dmul_rn(ro, sg[ai]);
-                step(s, a, table_set_from_dealt(s, dealt)); n_step++;
+                pend_a = a; pend = true;
                 continue;
             }
             // traverser: push a frame, descend into the sampled action first (:58-67)
@@ -477,7 +485,7 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
             f_meta[o] = make_uint2((uint32_t)slot | (nl << 12), list);
             f_cfv[o] = 0u;
             sp = __dmul_rn(sp, sg[ai]);
-            step(s, a, table_set_from_dealt(s, dealt)); n_step++;
+            pend_a = a; pend = true;
             continue;
         }
         // ---- a child returned ret_x2 to the top frame
@@ -504,7 +512,7 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
             s = f_st[o];
             ro = f_ro[o];
             sp = __dmul_rn(f_sp[o], sg[i]);
-            step(s, (meta.y >> (4 * i)) & 0xFu, table_set_from_dealt(s, dealt)); n_step++;
+            pend_a = (meta.y >> (4 * i)) & 0xFu; pend = true;
             returning = false;
             continue;
         }
@@ -575,7 +583,7 @@ __global__ void __launch_bounds__(32, 1) mccfr_inplace_kernel(SolverDev d, long 
     for (int i = tid; i < S; i += 32) d.touched[i] = touched[i];
 }
 
-constexpr int MCCFR_THREADS = 640;
+constexpr int MCCFR_THREADS = 768;
 
 __host__ __device__ inline size_t mccfr_batch_smem(int S, int hcap, int nframes, int threads) {
     size_t b = 0;
