@@ -17,7 +17,7 @@ import numpy as np
 from ..sharding import allreduce_delta, shard_bounds
 from ..solver import Solver
 from ._policy_base import Policy, root_of
-from .vanilla_cfr import evaluate_agent  # noqa: F401  (identical in both reference modules)
+from ._evaluate import evaluate_agent  # noqa: F401  (one implementation for both trainers)
 
 
 @dataclass

@@ -29,7 +29,7 @@ char* last_error_buf() {
 // the ~2x40 state words the first outputs depend on (output j of the first block needs words j, j+1 and
 // j+397).  About 1.5x the integer work, no memory traffic.  Pass 1 starts from init_genrand(19650218),
 // which does not depend on the seed: that table is computed once on the host and read through L1.
-__device__ uint32_t g_mt_init[624];
+__constant__ uint32_t g_mt_init[624];   // uniform index -> constant-cache operand, no load instruction in the chain
 constexpr int DEAL_WIN = 40;   // MT outputs available on the fast path (a shuffle needs 15 + rejections)
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
@@ -127,7 +127,7 @@ __device__ __noinline__ unsigned long long deal_slow(uint32_t key0, uint32_t key
 __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__ seeds, long long n,
                                                    uint4* __restrict__ states, uint32_t* __restrict__ hand_order,
                                                    unsigned long long* __restrict__ deck, int zero_means_42) {
-    uint32_t lo[DEAL_WIN + 1], hi[DEAL_WIN];
+    uint32_t lo[DEAL_WIN + 2], hi[DEAL_WIN];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
          g += (long long)gridDim.x * blockDim.x) {
         long long sd = seeds[g];
@@ -138,25 +138,35 @@ __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__
         const uint32_t kodd = two ? key1 + 1u : key0;   // key[j] + j for odd steps (j = 1) / one-word keys
 
         // ---- pass 1, first run (nothing stored): step k writes word k+1 with key word j = k % len
-        uint32_t prev = g_mt_init[0], first1 = 0u;
-        for (int k = 0; k < 623; k++) {
-            const uint32_t cur = (g_mt_init[k + 1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + ((k & 1) ? kodd : key0);
-            if (k == 0) first1 = cur;
-            prev = cur;
+        // (unrolled so that the even/odd key word and the table offsets are compile-time operands)
+        uint32_t prev = (g_mt_init[1] ^ ((g_mt_init[0] ^ (g_mt_init[0] >> 30)) * 1664525u)) + key0;   // k = 0
+        const uint32_t first1 = prev;
+#pragma unroll 8
+        for (int k = 1; k < 623; k += 2) {
+            prev = (g_mt_init[k + 1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;      // odd k
+            prev = (g_mt_init[k + 2] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key0;      // even k
         }
         // step 624 wraps: mt[0] = mt[623]; word 1 is rewritten with j = 623 % len
         const uint32_t m1w = (first1 ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;
 
         // ---- pass 2 (i = 2..623, then the wrap to i = 1) in lock-step with a second run of pass 1
         uint32_t p1 = first1, p2 = m1w;
-        for (int i = 2; i < 624; i++) {
-            const uint32_t c1 = (g_mt_init[i] ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + (((i - 1) & 1) ? kodd : key0);
-            p1 = c1;
-            const uint32_t c2 = (c1 ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)i;
-            p2 = c2;
-            if (i <= DEAL_WIN) lo[i] = c2;
-            if (i >= 397 && i < 397 + DEAL_WIN) hi[i - 397] = c2;
-        }
+        auto lock_step = [&](int i, uint32_t kw) {
+            p1 = (g_mt_init[i] ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + kw;
+            p2 = (p1 ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)i;
+        };
+        // words 2..DEAL_WIN and 397..397+DEAL_WIN-1 are kept; the stretches between them are pure chain
+#pragma unroll 1
+        for (int i = 2; i <= DEAL_WIN; i += 2) { lock_step(i, kodd); lo[i] = p2; lock_step(i + 1, key0); lo[i + 1] = p2; }
+        static_assert(DEAL_WIN % 2 == 0, "window must be even");
+        lock_step(DEAL_WIN + 2, kodd);     // DEAL_WIN + 1 was the last one stored above; continue the chain
+#pragma unroll 8
+        for (int i = DEAL_WIN + 3; i < 397; i += 2) { lock_step(i, key0); lock_step(i + 1, kodd); }
+#pragma unroll 1
+        for (int i = 397; i < 397 + DEAL_WIN; i += 2) { lock_step(i, key0); hi[i - 397] = p2; lock_step(i + 1, kodd); hi[i - 396] = p2; }
+#pragma unroll 8
+        for (int i = 397 + DEAL_WIN; i < 623; i += 2) { lock_step(i, key0); lock_step(i + 1, kodd); }
+        lock_step(623, key0);
         lo[1] = (m1w ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - 1u;
         lo[0] = 0x80000000u;
 
@@ -536,18 +546,31 @@ int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_se
     std::lock_guard<std::mutex> lk(g_scratch_mu);
     size_t o_seed = 0, o_st = align256(8 * n), o_ho = align256(o_st + 16 * n), o_a = align256(o_ho + 4 * n),
            o_r = align256(o_a + 8 * n), tot = align256(o_r + 8 * n);
-    char* d; cudaStream_t st;
-    int rc = scratch_get(tot, &d, &st);
+    char* d; cudaStream_t st0;
+    int rc = scratch_get(tot, &d, &st0);
     if (rc) return rc;
-    MS_CUDA(cudaMemcpyAsync(d + o_seed, h_seeds, 8 * n, cudaMemcpyHostToDevice, st));
-    rc = ms_deal_from_seeds((const int64_t*)(d + o_seed), n, (ms_state*)(d + o_st), (uint32_t*)(d + o_ho), st);
-    if (rc) return rc;
-    rc = ms_rollout_random((const ms_state*)(d + o_st), (const uint32_t*)(d + o_ho), n, philox_seed, game_offset,
-                           (uint8_t*)(d + o_a), (float*)(d + o_r), nullptr, st);
-    if (rc) return rc;
-    if (h_actions) MS_CUDA(cudaMemcpyAsync(h_actions, d + o_a, 8 * n, cudaMemcpyDeviceToHost, st));
-    if (h_rewards) MS_CUDA(cudaMemcpyAsync(h_rewards, d + o_r, 8 * n, cudaMemcpyDeviceToHost, st));
-    MS_CUDA(cudaStreamSynchronize(st));
+    // Chunked over three streams so that the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of
+    // chunk c-1 overlap (separate copy engines per direction); the chunks are 128-byte aligned slices.
+    static cudaStream_t pipe[64][3] = {};
+    int dev = 0;
+    MS_CUDA(cudaGetDevice(&dev));
+    for (int i = 0; i < 3; i++)
+        if (!pipe[dev & 63][i]) MS_CUDA(cudaStreamCreateWithFlags(&pipe[dev & 63][i], cudaStreamNonBlocking));
+    const int64_t chunk = 262144;
+    int c = 0;
+    for (int64_t lo = 0; lo < n; lo += chunk, c++) {
+        const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
+        cudaStream_t st = pipe[dev & 63][c % 3];
+        MS_CUDA(cudaMemcpyAsync(d + o_seed + 8 * lo, h_seeds + lo, 8 * m, cudaMemcpyHostToDevice, st));
+        rc = ms_deal_from_seeds((const int64_t*)(d + o_seed) + lo, m, (ms_state*)(d + o_st) + lo, (uint32_t*)(d + o_ho) + lo, st);
+        if (rc) return rc;
+        rc = ms_rollout_random((const ms_state*)(d + o_st) + lo, (const uint32_t*)(d + o_ho) + lo, m, philox_seed,
+                               game_offset + (uint64_t)lo, (uint8_t*)(d + o_a) + 8 * lo, (float*)(d + o_r) + 2 * lo, nullptr, st);
+        if (rc) return rc;
+        if (h_actions) MS_CUDA(cudaMemcpyAsync(h_actions + 8 * lo, d + o_a + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, st));
+        if (h_rewards) MS_CUDA(cudaMemcpyAsync(h_rewards + 2 * lo, d + o_r + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 3; i++) MS_CUDA(cudaStreamSynchronize(pipe[dev & 63][i]));
     return MS_OK;
 }
 
