@@ -39,6 +39,8 @@ if ROOT not in sys.path:
 BYTES_PER_UPDATE_FP64 = 203.7      # 172 updates x 136 B + 291 opponent lookups x 40 B per reference iteration
 BYTES_PER_ENV_STEP = 34.0          # 16 B state load + 1 B action + 16 B state store (+ rewards on the last ply)
 FALLBACK_HBM_GBS = 6650.0
+# DRAM bytes per launch of the dominant kernels, from the committed ncu --set full captures (profiles/README.md)
+NCU_DRAM_BYTES_PER_LAUNCH = {"mccfr_batch_kernel": 117504, "rollout_kernel": 20052736}
 
 
 def load_peaks():
@@ -158,8 +160,14 @@ def run_ours(args):
     hbm_gbs, peak_src = load_peaks()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    sync_word = torch.zeros(1, device=dev)
+
     def flush_l2():
+        """Evict L2 between timed steps; with several ranks also line the ranks up again (stream-ordered
+        all-reduce of one word), so that a rank's timed step does not include waiting for another rank's flush."""
         flush_buf.fill_(1)
+        if world > 1:
+            dist.all_reduce(sync_word)
 
     def barrier():
         if world > 1:
@@ -186,15 +194,40 @@ def run_ours(args):
     # ------------------------------------------------------------------ MCCFR (configs 3 / 5)
     B = args.trav
     sv = Solver(seed=42, device=dev)
-    delta = sv.delta_tensor()
     S = sv.n_slots
+    # exchange of the delta buffer between ranks: "p2p" = ms_mccfr_apply_peers (every rank reads every rank's
+    # buffer over NVLink peer memory and applies the rank-ordered sum in one kernel), "nccl" = all-reduce + apply
+    collective = "none"
+    if world > 1:
+        collective = "nccl"
+        if args.collective in ("auto", "p2p"):
+            ok = torch.ones(1, device=dev)
+            try:
+                sv.attach_peers()
+            except Exception as e:          # e.g. no peer access between the GPUs of this box
+                print(f"[rank {rank}] peer attach failed, using NCCL: {e}", file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() > 0:
+                collective = "p2p"
+            elif args.collective == "p2p":
+                raise SystemExit("--collective p2p requested but peer memory is unavailable")
+            else:
+                sv = Solver(seed=42, device=dev)      # a clean, un-attached solver for the NCCL path
+    delta = sv.delta_tensor() if collective != "p2p" else None
+
+    def exchange_and_apply():
+        if collective == "p2p":
+            sv.apply_peers()
+        else:
+            if collective == "nccl":
+                dist.all_reduce(delta)      # one all-reduce of 5*S float64 per iteration (NVLink / NVSwitch)
+            sv.mccfr_apply()
 
     def mccfr_step(i):
         # global traversal ids: iteration i, rank r -> [ (i*world + r) * B, ... + B )
         sv.mccfr_batch(2, B, philox_seed=args.seed, first_trav=(i * world + rank) * B)
-        if world > 1:
-            dist.all_reduce(delta)          # one all-reduce of 5*S float64 per iteration (NVLink / NVSwitch)
-        sv.mccfr_apply()
+        exchange_and_apply()
 
     for i in range(W):
         mccfr_step(i)
@@ -211,9 +244,7 @@ def run_ours(args):
         kev[i][0].record()
         sv.mccfr_batch(2, B, philox_seed=args.seed, first_trav=((W + i) * world + rank) * B)
         kev[i][1].record()
-        if world > 1:
-            dist.all_reduce(delta)
-        sv.mccfr_apply()
+        exchange_and_apply()
         ev[i][1].record()
     barrier()
     wall = time.perf_counter() - wall0
@@ -382,7 +413,10 @@ def run_ours(args):
         "ms_per_step": ms_total / K, "e2e": mccfr_e2e, "gpu_launches": int(mccfr_launches),
         "node_visits_per_sec": visits_all / (ms_total * 1e-3), "env_steps_per_sec_inside_mccfr": steps_all / (ms_total * 1e-3),
         "roofline": {"bound": "hbm", "achieved": mccfr_roof_ach, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": mccfr_roof_ach / hbm_gbs, "traffic": None, "kernel": "mccfr_batch_kernel",
+                     "frac": mccfr_roof_ach / hbm_gbs, "traffic": NCU_DRAM_BYTES_PER_LAUNCH["mccfr_batch_kernel"],
+                     "traffic_source": "ncu --set full, profiles/mccfr_r01c_raw.csv: dram__bytes_read.sum + "
+                                       "dram__bytes_write.sum per launch (table staging only; independent of the batch size)",
+                     "kernel": "mccfr_batch_kernel",
                      "kernel_ms": ms_kernel, "peak_source": peak_src,
                      "note": "HBM-EQUIVALENT figure (203.7 algorithmic B/update, SURVEY 8(d)); the 53 KB table of a single "
                              "deal is shared-memory resident, so the real limiter is issue slots / shared-memory atomics "
@@ -390,7 +424,9 @@ def run_ours(args):
         "cpu_baseline": cpu_mccfr,
         "config": {"workload": "BASELINE.json configs[2]/[4]: MCCFR (reference estimator), seed-42 deal, "
                                f"{B} traversals per player per GPU per iteration, fp64 table", "traversals_per_step": 2 * B * world,
-                   "parallelism": f"dp{world}: traversals sharded by id, one NCCL all-reduce of {5 * S} f64 per iteration"
+                   "parallelism": f"dp{world}: traversals sharded by id, one exchange of {5 * S} f64 per iteration via " +
+                                  ("ms_mccfr_apply_peers (NVLink peer-memory reads + rank-ordered sum + apply in one kernel)"
+                                   if collective == "p2p" else "NCCL all-reduce")
                    if world > 1 else "single GPU",
                    "l2": "256 MiB flush between timed steps (working set is on-chip anyway)", "philox_seed": args.seed},
     }
@@ -398,7 +434,10 @@ def run_ours(args):
         "metric": "env_steps_per_sec", "value": env_value, "unit": "env steps/s", "ms_per_step": env_ms_total / K,
         "e2e": env_e2e, "gpu_launches": int(env_launches),
         "roofline": {"bound": "hbm", "achieved": env_roof_ach, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": env_roof_ach / hbm_gbs, "traffic": None, "kernel": "rollout_kernel", "kernel_ms": env_kernel_ms,
+                     "frac": env_roof_ach / hbm_gbs, "traffic": NCU_DRAM_BYTES_PER_LAUNCH["rollout_kernel"] * (G / 1e6),
+                     "traffic_source": "ncu --set full, profiles/env_r01c_raw.csv: 20.05 MB read per 1 M games (writes "
+                                       "stayed in L2 under ncu)",
+                     "kernel": "rollout_kernel", "kernel_ms": env_kernel_ms,
                      "peak_source": peak_src,
                      "note": "against the step-granular 34 B/step figure (SURVEY 8(d)); the fused kernel itself moves "
                              "36 B/game (4.5 B/step) and is integer-issue bound, not HBM bound"},
@@ -519,6 +558,8 @@ def main():
     ap.add_argument("--step-states", type=int, default=16_000_000, help="states in the step-granular API measurement")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU delta exchange: peer-memory kernel (p2p), NCCL all-reduce, or p2p with NCCL fallback")
     ap.add_argument("--ref-trav", type=int, default=1500)
     ap.add_argument("--ref-games", type=int, default=400_000)
     args = ap.parse_args()

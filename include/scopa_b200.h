@@ -154,6 +154,17 @@ int ms_mccfr_inplace(ms_solver* s, int64_t iters, uint64_t philox_seed, uint64_t
 int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
                    void* stream);
 int ms_mccfr_apply(ms_solver* s, void* stream);
+/* Peer-memory exchange (one process per GPU, NVLink / NVSwitch): instead of a library all-reduce + ms_mccfr_apply,
+ * every rank maps the other ranks' delta buffers (CUDA IPC) and ONE kernel per rank does barrier + sum over all
+ * ranks (in rank order: replicas stay bit-identical) + table update.
+ *   ms_solver_ipc_export: 64-byte cudaIpcMemHandle_t of this solver's device block + byte offsets of its two delta
+ *     buffers and of its flag array; exchange them between ranks (any out-of-band all-gather of 88 bytes per rank);
+ *   ms_solver_ipc_attach: `handles` = world x 64 bytes, `offsets` = world x 3 u64, in rank order (at most 8 ranks);
+ *   ms_mccfr_apply_peers: replaces {all-reduce, ms_mccfr_apply} after ms_mccfr_batch; deltas are double buffered by
+ *     iteration parity, so one cross-GPU barrier per iteration suffices.  Every rank must call it once per iteration. */
+int ms_solver_ipc_export(ms_solver* s, void* handle64, uint64_t offsets[3]);
+int ms_solver_ipc_attach(ms_solver* s, int32_t rank, int32_t world, const void* handles, const uint64_t* offsets);
+int ms_mccfr_apply_peers(ms_solver* s, void* stream);
 /* counters accumulated by the MCCFR kernels since the last reset: [0] traverser-node updates,
  * [1] node visits (_sample calls), [2] env steps */
 int ms_solver_counters(ms_solver* s, uint64_t h_out[3], int reset, void* stream);

@@ -41,13 +41,17 @@ class InfoNode:
 
 
 class MCCFRTrainer:
-    def __init__(self, game, seed=0, traversals_per_iteration=None, process_group=None, device="cuda"):
+    def __init__(self, game, seed=0, traversals_per_iteration=None, process_group=None, device="cuda",
+                 peer_memory=False):
         self.game = game
         words, order = root_of(game)
         self.solver = Solver(words, order, device=device)
         self.seed = int(seed)
         self.batch = traversals_per_iteration
         self.process_group = process_group
+        self.peer_memory = bool(peer_memory) and traversals_per_iteration is not None
+        if self.peer_memory:          # exchange deltas through NVLink peer memory instead of an NCCL all-reduce
+            self.solver.attach_peers(process_group)
         self._iter = 0
         self._map = {}
         self._dirty = False
@@ -90,9 +94,12 @@ class MCCFRTrainer:
             lo, n = shard_bounds(B, rank, world)
             for _ in range(iterations):
                 self.solver.mccfr_batch(2, n, philox_seed=self.seed, first_trav=self._iter * B + lo)
-                if world > 1:
-                    allreduce_delta(self.solver.delta_tensor(), self.process_group)
-                self.solver.mccfr_apply()
+                if self.peer_memory:
+                    self.solver.apply_peers()
+                else:
+                    if world > 1:
+                        allreduce_delta(self.solver.delta_tensor(), self.process_group)
+                    self.solver.mccfr_apply()
                 self._iter += 1
         self._dirty = True
 

@@ -678,6 +678,56 @@ __global__ void __launch_bounds__(256) mccfr_apply_kernel(SolverDev d) {
     }
 }
 
+// Multi-GPU exchange without a library collective: every rank reads every rank's delta buffer directly over
+// NVLink / NVSwitch peer memory (CUDA IPC mappings), sums them in rank order -- so all replicas compute the same
+// bits -- and applies the sum to its own table, all in this one kernel.
+//   * barrier: each rank stores the iteration number into its slot of every peer's flag array
+//     (st.release.sys after a system-scope fence) and spins until all slots of its own array have reached it;
+//   * the deltas are double buffered by iteration parity: by the time a rank passes the barrier of iteration i,
+//     every peer has finished reading buffer (i-1)&1 (its apply(i-1) precedes its signal(i) in stream order), so
+//     that buffer is zeroed here for iteration i+1;
+//   * peer loads use ld.global.cv: peer lines may sit stale in the local L1.
+constexpr int MS_MAX_PEERS = 8;
+struct PeerView {
+    const double* delta[MS_MAX_PEERS];          // peers' delta buffer of the current parity
+    unsigned long long* flags[MS_MAX_PEERS];    // peers' flag arrays ([world] u64 each)
+    unsigned long long* my_flags;
+    double* zero_me;                            // own delta buffer of the other parity
+    int rank, world;
+};
+
+__global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d, PeerView pv, unsigned long long epoch) {
+    const int tid = threadIdx.x, S = d.n_slots;
+    if (tid < pv.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(pv.flags[tid] + pv.rank), "l"(epoch) : "memory");
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(pv.my_flags + tid) : "memory");
+        } while (seen < epoch);
+    }
+    __syncthreads();
+    for (int s = tid; s < S; s += blockDim.x) {
+        double dv[4] = {0.0, 0.0, 0.0, 0.0}, cnt = 0.0;
+        for (int r = 0; r < pv.world; r++) {
+            const double* pd = pv.delta[r];
+            cnt = __dadd_rn(cnt, __ldcv(pd + 4 * S + s));
+#pragma unroll
+            for (int i = 0; i < 4; i++) dv[i] = __dadd_rn(dv[i], __ldcv(pd + 4 * s + i));
+        }
+        double reg[4], sg[4];
+        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+        const int n = d.slot_nlegal[s];
+        if (cnt != 0.0) {
+            regret_match(reg, n, sg);
+            for (int i = 0; i < n; i++) d.strategy[4 * s + i] = __dadd_rn(d.strategy[4 * s + i], __dmul_rn(cnt, sg[i]));
+        }
+        for (int i = 0; i < 4; i++)
+            if (dv[i] != 0.0) d.regret[4 * s + i] = __dadd_rn(reg[i], dv[i]);
+    }
+    for (int i = tid; i < 5 * S; i += blockDim.x) pv.zero_me[i] = 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Best response against the table's average policy (restated open_spiel BestResponsePolicy, see
 // oracle/ms_exploit.py for the algorithm; third-party, parity unpinned).  Same level-synchronous
@@ -831,6 +881,14 @@ struct ms_solver {
     char* d_block = nullptr;   // one allocation for everything
     SolverDev dev{};
     double* d_value = nullptr; // [2] scratch for returned values
+    // peer-memory exchange (ms_solver_ipc_export / _attach / ms_mccfr_apply_peers)
+    double* delta_buf[2] = {nullptr, nullptr};
+    unsigned long long* flags = nullptr;
+    int rank = 0, world = 1, parity = 0;
+    unsigned long long epoch = 0;
+    bool attached = false;
+    void* peer_base[MS_MAX_PEERS] = {};
+    uint64_t peer_off[MS_MAX_PEERS][3] = {};
 };
 
 namespace {
@@ -948,7 +1006,7 @@ int solver_build(ms_solver* sv) {
     size_t total = 0;
     auto sz = [&](size_t n) { size_t b = (n + 255) & ~(size_t)255; total += b; return b; };
     sz(4 * (L + 1)); sz(2 * N); sz(N); sz(2 * N); sz(N); sz(2 * (S + 1)); sz(2 * sv->n_dec); sz(4 * (L + 1)); sz(S); sz(S);
-    sz(8 * hcap); sz(2 * hcap); sz(32 * S); sz(32 * S); sz(8 * (5 * S)); sz(S); sz(8 * 4); sz(16);
+    sz(8 * hcap); sz(2 * hcap); sz(32 * S); sz(32 * S); sz(8 * (5 * S)); sz(8 * (5 * S)); sz(8 * MS_MAX_PEERS); sz(S); sz(8 * 4); sz(16);
     MS_CUDA(cudaMalloc(&sv->d_block, total + 4096));
     MS_CUDA(cudaMemset(sv->d_block, 0, total + 4096));
     p = sv->d_block;
@@ -975,6 +1033,9 @@ int solver_build(ms_solver* sv) {
     d.regret = carve<double>(p, 4 * (size_t)S);
     d.strategy = carve<double>(p, 4 * (size_t)S);
     d.delta = carve<double>(p, 5 * (size_t)S);
+    sv->delta_buf[0] = d.delta;
+    sv->delta_buf[1] = carve<double>(p, 5 * (size_t)S);
+    sv->flags = carve<unsigned long long>(p, MS_MAX_PEERS);
     d.touched = carve<uint8_t>(p, (size_t)S);
     d.counters = carve<unsigned long long>(p, 4);
     sv->d_value = carve<double>(p, 2);
@@ -1007,6 +1068,9 @@ int ms_solver_create(const ms_state* h_root, uint32_t hand_order, ms_solver** ou
 
 void ms_solver_destroy(ms_solver* s) {
     if (!s) return;
+    if (s->attached)
+        for (int r = 0; r < s->world; r++)
+            if (r != s->rank && s->peer_base[r]) cudaIpcCloseMemHandle(s->peer_base[r]);
     if (s->d_block) cudaFree(s->d_block);
     delete s;
 }
@@ -1017,7 +1081,8 @@ int ms_solver_reset(ms_solver* s, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MS_CUDA(cudaMemsetAsync(s->dev.regret, 0, 32 * S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.strategy, 0, 32 * S, st));
-    MS_CUDA(cudaMemsetAsync(s->dev.delta, 0, 40 * S, st));
+    MS_CUDA(cudaMemsetAsync(s->delta_buf[0], 0, 40 * S, st));
+    MS_CUDA(cudaMemsetAsync(s->delta_buf[1], 0, 40 * S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.touched, 0, S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.counters, 0, 32, st));
     return MS_OK;
@@ -1146,6 +1211,52 @@ int ms_mccfr_apply(ms_solver* s, void* stream) {
     int rc = check_dev(s); if (rc) return rc;
     mccfr_apply_kernel<<<(s->n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(s->dev);
     MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_solver_ipc_export(ms_solver* s, void* handle64, uint64_t offsets[3]) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (!handle64 || !offsets) return fail(MS_ERR_ARG, "ms_solver_ipc_export: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    MS_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, s->d_block));
+    offsets[0] = (uint64_t)((char*)s->delta_buf[0] - s->d_block);
+    offsets[1] = (uint64_t)((char*)s->delta_buf[1] - s->d_block);
+    offsets[2] = (uint64_t)((char*)s->flags - s->d_block);
+    return MS_OK;
+}
+
+int ms_solver_ipc_attach(ms_solver* s, int32_t rank, int32_t world, const void* handles, const uint64_t* offsets) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (world < 1 || world > MS_MAX_PEERS || rank < 0 || rank >= world || !handles || !offsets)
+        return fail(MS_ERR_ARG, "ms_solver_ipc_attach: bad argument (at most %d ranks)", MS_MAX_PEERS);
+    if (s->attached) return fail(MS_ERR_STATE, "solver is already attached to its peers");
+    for (int r = 0; r < world; r++) {
+        for (int k = 0; k < 3; k++) s->peer_off[r][k] = offsets[3 * r + k];
+        if (r == rank) { s->peer_base[r] = s->d_block; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * r, 64);
+        MS_CUDA(cudaIpcOpenMemHandle(&s->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    s->rank = rank; s->world = world; s->attached = true; s->parity = 0; s->epoch = 0;
+    return MS_OK;
+}
+
+int ms_mccfr_apply_peers(ms_solver* s, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (!s->attached) return fail(MS_ERR_STATE, "ms_mccfr_apply_peers: call ms_solver_ipc_attach first");
+    PeerView pv{};
+    for (int r = 0; r < s->world; r++) {
+        pv.delta[r] = (const double*)((char*)s->peer_base[r] + s->peer_off[r][s->parity]);
+        pv.flags[r] = (unsigned long long*)((char*)s->peer_base[r] + s->peer_off[r][2]);
+    }
+    pv.my_flags = s->flags;
+    pv.zero_me = s->delta_buf[s->parity ^ 1];
+    pv.rank = s->rank; pv.world = s->world;
+    s->epoch += 1;
+    mccfr_apply_peers_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(s->dev, pv, s->epoch);
+    MS_LAUNCH_CHECK();
+    s->parity ^= 1;                       // the next batch accumulates into the other buffer
+    s->dev.delta = s->delta_buf[s->parity];
     return MS_OK;
 }
 

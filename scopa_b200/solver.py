@@ -170,6 +170,32 @@ class Solver:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_mccfr_apply(self.h, self._stream()))
 
+    # ------------------------------------------------------------------------------- peer-memory exchange
+    def attach_peers(self, group=None):
+        """Map every rank's delta buffers into this process (CUDA IPC over NVLink / NVSwitch).  Collective: all
+        ranks of `group` must call it.  Afterwards use apply_peers() instead of {all_reduce, mccfr_apply}."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handle = (C.c_ubyte * 64)()
+        offs = (C.c_uint64 * 3)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_solver_ipc_export(self.h, handle, offs))
+        mine = (bytes(handle), [int(o) for o in offs])
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        handles = b"".join(h for h, _ in everyone)
+        flat = (C.c_uint64 * (3 * world))(*[o for _, oo in everyone for o in oo])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_solver_ipc_attach(self.h, rank, world, handles, flat))
+        self._delta_t = None        # the active delta buffer now alternates: delta_tensor() is no longer meaningful
+        self._peers = True
+        dist.barrier(group)
+
+    def apply_peers(self):
+        """barrier + sum of all ranks' deltas (rank order) + table update, one kernel per rank."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_mccfr_apply_peers(self.h, self._stream()))
+
     def counters(self, reset=False):
         out = (C.c_uint64 * 3)()
         with torch.cuda.device(self.device):
