@@ -154,6 +154,12 @@ int ms_mccfr_inplace(ms_solver* s, int64_t iters, uint64_t philox_seed, uint64_t
 int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
                    void* stream);
 int ms_mccfr_apply(ms_solver* s, void* stream);
+/* ms_mccfr_batch_mode: like ms_mccfr_batch with a choice of estimator: mode 0 = the reference's estimator
+ *   (mc_cfr.py:37-86), 1 = external sampling, 2 = outcome sampling (epsilon 0.6) -- the textbook estimators the
+ *   reference does not implement (update rules as published by Lanctot et al. 2009).  Same table, same delta
+ *   buffer, same apply step. */
+int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_trav, uint64_t philox_seed,
+                        uint64_t first_trav, void* stream);
 /* Peer-memory exchange (one process per GPU, NVLink / NVSwitch): instead of a library all-reduce + ms_mccfr_apply,
  * every rank maps the other ranks' delta buffers (CUDA IPC) and ONE kernel per rank does barrier + sum over all
  * ranks (in rank order: replicas stay bit-identical) + table update.

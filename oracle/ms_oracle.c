@@ -899,3 +899,97 @@ void ora_mccfr_bench(int64_t seed, int64_t ntrav_per_thread, int nthreads, uint6
     if (updates) *updates = tu;
     if (visits) *visits = tv;
 }
+
+/* ================================================================================ textbook MCCFR */
+/* Opt-in estimators that the reference does NOT implement (its MCCFRTrainer is the hybrid estimator above):
+ * external sampling and outcome sampling as published (Lanctot et al. 2009; same update rules as
+ * open_spiel/python/algorithms/external_sampling_mccfr.py with AverageType.SIMPLE and
+ * outcome_sampling_mccfr.py with epsilon = 0.6, baseline 0).  Batch semantics only: sigma frozen for the batch,
+ * deltas applied at the end.  Philox "MCCF" stream, call index = order of recursive invocations. */
+#define OS_EPSILON 0.6
+
+static double es_rec(mccfr_ctx* c, const ora_state* s) {
+    uint32_t my_call = c->rng->call++;
+    c->n_visits++;
+    if (s->is_terminal) { double r[2]; ora_state_rewards(s, r); return r[c->tp]; }
+    int player = ora_state_current_player(s);
+    char key[72]; mccfr_key(s, player, key, sizeof key);
+    int legal[4]; int n = ora_state_legal(s, player, legal);
+    ora_node* nd = table_get(c->t, key, legal, n);
+    int slot = (int)(nd - c->t->nodes);
+    double sigma[4];
+    regret_matching(nd->regret, n, sigma);
+    if (player != c->tp) {                 /* opponent: sample one action, average strategy updated here */
+        uint32_t saved = c->rng->call; c->rng->call = my_call;
+        int ai = rng_choice_p(c->rng, sigma, n);
+        c->rng->call = saved;
+        for (int i = 0; i < n; i++) c->dstr[slot][i] += sigma[i];
+        ora_state nx; ora_state_clone(s, &nx); ora_state_apply(&nx, legal[ai]);
+        return es_rec(c, &nx);
+    }
+    double cv[4], value = 0.0;
+    for (int i = 0; i < n; i++) {
+        ora_state nx; ora_state_clone(s, &nx); ora_state_apply(&nx, legal[i]);
+        cv[i] = es_rec(c, &nx);
+        value += sigma[i] * cv[i];
+    }
+    for (int i = 0; i < n; i++) c->dreg[slot][i] += cv[i] - value;
+    c->n_updates++;
+    return value;
+}
+
+static double os_rec(mccfr_ctx* c, const ora_state* s, double my_reach, double opp_reach, double sample_reach) {
+    uint32_t my_call = c->rng->call++;
+    c->n_visits++;
+    if (s->is_terminal) { double r[2]; ora_state_rewards(s, r); return r[c->tp]; }
+    int player = ora_state_current_player(s);
+    char key[72]; mccfr_key(s, player, key, sizeof key);
+    int legal[4]; int n = ora_state_legal(s, player, legal);
+    ora_node* nd = table_get(c->t, key, legal, n);
+    int slot = (int)(nd - c->t->nodes);
+    double sigma[4], sp[4];
+    regret_matching(nd->regret, n, sigma);
+    for (int i = 0; i < n; i++)
+        sp[i] = (player == c->tp) ? OS_EPSILON * (1.0 / n) + (1.0 - OS_EPSILON) * sigma[i] : sigma[i];
+    uint32_t saved = c->rng->call; c->rng->call = my_call;
+    int ai = rng_choice_p(c->rng, sp, n);
+    c->rng->call = saved;
+    double nmy = my_reach, nopp = opp_reach;
+    if (player == c->tp) nmy = my_reach * sigma[ai]; else nopp = opp_reach * sigma[ai];
+    ora_state nx; ora_state_clone(s, &nx); ora_state_apply(&nx, legal[ai]);
+    double child = os_rec(c, &nx, nmy, nopp, sample_reach * sp[ai]);
+    double est_a = child / sp[ai];                       /* estimated value of the sampled action, 0 for the others */
+    double value_estimate = sigma[ai] * est_a;
+    if (player == c->tp) {
+        double w = opp_reach / sample_reach;
+        double cf_value = value_estimate * w;
+        for (int i = 0; i < n; i++) {
+            double cf_action = (i == ai ? est_a : 0.0) * w;
+            c->dreg[slot][i] += cf_action - cf_value;
+            c->dstr[slot][i] += my_reach * sigma[i] / sample_reach;
+        }
+        c->n_updates++;
+    }
+    return value_estimate;
+}
+
+/* mode 1 = external sampling, 2 = outcome sampling; same calling convention as ora_mccfr_batch */
+void ora_mccfr_batch_mode(ora_table* t, int64_t seed, int mode, int player, uint64_t philox_seed,
+                          uint64_t first_trav, int64_t ntrav, int64_t* n_updates, int64_t* n_visits) {
+    double (*dreg)[4] = calloc((size_t)t->cap, sizeof(double[4]));
+    double (*dstr)[4] = calloc((size_t)t->cap, sizeof(double[4]));
+    ora_rng* rng = ora_rng_new(1, philox_seed);
+    mccfr_ctx c = {t, rng, player, dreg, dstr, 0, 0};
+    int n0 = t->n;
+    for (int64_t k = 0; k < ntrav; k++) {
+        ora_state s; ora_state_init(&s, seed);
+        rng->tag = TAG_MCCF + (uint32_t)player + 16u * (uint32_t)mode; rng->trav = first_trav + (uint64_t)k; rng->call = 0;
+        if (mode == 1) es_rec(&c, &s); else os_rec(&c, &s, 1.0, 1.0, 1.0);
+    }
+    if (t->n != n0) { fprintf(stderr, "ora_mccfr_batch_mode: table was not pre-populated\n"); abort(); }
+    for (int i = 0; i < t->n; i++)
+        for (int a = 0; a < 4; a++) { t->nodes[i].regret[a] += dreg[i][a]; t->nodes[i].strategy[a] += dstr[i][a]; }
+    if (n_updates) *n_updates = c.n_updates;
+    if (n_visits) *n_visits = c.n_visits;
+    ora_rng_free(rng); free(dreg); free(dstr);
+}

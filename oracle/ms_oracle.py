@@ -97,6 +97,7 @@ def lib():
     L.ora_sdcfr_traverse.argtypes = [P(OraMlp), i64, ci, vp, u64, vp, vp, vp, ci, P(ci)]
     L.ora_sdcfr_traverse.restype = C.c_float
     L.ora_mccfr_bench.argtypes = [i64, i64, ci, u64, P(i64), P(i64)]
+    L.ora_mccfr_batch_mode.argtypes = [vp, i64, ci, ci, u64, u64, i64, P(i64), P(i64)]
     _lib = L
     return L
 
@@ -258,6 +259,11 @@ class Table:
     def mccfr_batch(self, player, philox_seed, first_trav, ntrav, seed=42):
         nu, nv = C.c_int64(), C.c_int64()
         lib().ora_mccfr_batch(self.t, seed, player, philox_seed, first_trav, ntrav, C.byref(nu), C.byref(nv))
+        return nu.value, nv.value
+
+    def mccfr_batch_mode(self, mode, player, philox_seed, first_trav, ntrav, seed=42):
+        nu, nv = C.c_int64(), C.c_int64()
+        lib().ora_mccfr_batch_mode(self.t, seed, mode, player, philox_seed, first_trav, ntrav, C.byref(nu), C.byref(nv))
         return nu.value, nv.value
 
     def exploitability(self, policy_kind, seed=42):

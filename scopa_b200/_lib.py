@@ -49,6 +49,7 @@ _SIGS = {
     "ms_mccfr_inplace": ([vp, i64, u64, u64, vp], C.c_int),
     "ms_mccfr_batch": ([vp, i32, i64, u64, u64, vp], C.c_int),
     "ms_mccfr_apply": ([vp, vp], C.c_int),
+    "ms_mccfr_batch_mode": ([vp, i32, i32, i64, u64, u64, vp], C.c_int),
     "ms_solver_ipc_export": ([vp, vp, C.POINTER(u64)], C.c_int),
     "ms_solver_ipc_attach": ([vp, i32, i32, vp, C.POINTER(u64)], C.c_int),
     "ms_mccfr_apply_peers": ([vp, vp], C.c_int),

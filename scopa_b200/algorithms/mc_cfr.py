@@ -41,9 +41,16 @@ class InfoNode:
 
 
 class MCCFRTrainer:
+    ESTIMATORS = {"reference": 0, "external": 1, "outcome": 2}
+
     def __init__(self, game, seed=0, traversals_per_iteration=None, process_group=None, device="cuda",
-                 peer_memory=False):
+                 peer_memory=False, estimator="reference"):
+        """estimator: "reference" = the estimator of the reference's _sample (default); "external" / "outcome" =
+        textbook external / outcome sampling MCCFR (batched mode only: set traversals_per_iteration)."""
         self.game = game
+        self.mode = self.ESTIMATORS[estimator]
+        if self.mode and traversals_per_iteration is None:
+            raise ValueError("the textbook estimators run in batched mode: pass traversals_per_iteration")
         words, order = root_of(game)
         self.solver = Solver(words, order, device=device)
         self.seed = int(seed)
@@ -93,7 +100,7 @@ class MCCFRTrainer:
             B = int(self.batch)
             lo, n = shard_bounds(B, rank, world)
             for _ in range(iterations):
-                self.solver.mccfr_batch(2, n, philox_seed=self.seed, first_trav=self._iter * B + lo)
+                self.solver.mccfr_batch(2, n, philox_seed=self.seed, first_trav=self._iter * B + lo, mode=self.mode)
                 if self.peer_memory:
                     self.solver.apply_peers()
                 else:

@@ -656,6 +656,255 @@ __global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev
     if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Textbook estimators (opt-in; the reference's MCCFRTrainer is the hybrid estimator above).  Same table, same
+// frozen-sigma batch semantics, same delta layout -- regret deltas [S][4] plus one scalar per slot that
+// multiplies the frozen sigma in the apply step (a visit count for external sampling, a sum of importance
+// weights for outcome sampling) -- so ms_mccfr_apply / ms_mccfr_apply_peers serve all three.
+//
+// External sampling (Lanctot et al. 2009; update rules of open_spiel's external_sampling_mccfr.py with
+// AverageType.SIMPLE): the traverser expands every action, the opponent samples one; at traverser nodes
+// regret[a] += u_a - sum_b sigma_b u_b, at opponent nodes strategy_sum += sigma.  Child values are expectations
+// (doubles), so a frame holds 4 doubles next to the state.
+constexpr int ES_THREADS = 512;
+constexpr uint32_t MS_TAG_ES = MS_TAG_MCCF + 16u, MS_TAG_OS = MS_TAG_MCCF + 32u;
+
+__host__ __device__ inline size_t es_smem_bytes(int S, int hcap, int nframes, int threads) {
+    return sizeof(double) * 12 * (size_t)S + 8 * (size_t)hcap + (size_t)threads * nframes * (16 + 32 + 8) +
+           4 * (size_t)S + 2 * (size_t)hcap + (size_t)S + 64;
+}
+
+__device__ void es_traverse(const SolverDev& d, const MccfrShared& sh, int tp, unsigned long long trav, uint2 pkey,
+                            uint4* f_st, double* f_cv, uint2* f_meta, int fstride, unsigned long long& n_upd,
+                            unsigned long long& n_vis, unsigned long long& n_step) {
+    MsState s = d.root;
+    const uint32_t dealt = dealt_set(d.root);
+    int fi = -1;
+    uint32_t call = 0;
+    double ret = 0.0;
+    bool returning = false, pend = false;
+    uint32_t pend_a = 0u;
+    uint4 xblk = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t xblk_id = 0xFFFFFFFFu;
+    const uint32_t tag = MS_TAG_ES + (uint32_t)tp;
+    while (true) {
+        if (!returning) {
+            if (pend) { step(s, pend_a, table_set_from_dealt(s, dealt)); n_step++; pend = false; }
+            const uint32_t my_call = call++;
+            n_vis++;
+            if (st_terminal(s)) {
+                const int r = reward0_x2(s);
+                ret = 0.5 * (double)(tp == 0 ? r : -r);
+                returning = true;
+                continue;
+            }
+            const int p = st_cur(s);
+            uint32_t list;
+            const uint32_t nl = legal_list(s, d.hand_order, p, list);
+            const int slot = lookup_slot(sh.hk, sh.hs, sh.hcap, infoset_key(s, p));
+            sh.touched[slot] = 1;
+            if (p != tp) {                          // opponent: average strategy += sigma, sample, tail call
+                atomicAdd(&sh.dcnt[slot], 1u);
+                int ai = 0;
+                if (nl > 1u) {
+                    if ((my_call >> 1) != xblk_id) {
+                        xblk_id = my_call >> 1;
+                        xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
+                    }
+                    const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
+                    ai = sample_cdf(sh.cdf + 4 * slot, (int)nl, u);
+                }
+                pend_a = (list >> (4 * ai)) & 0xFu; pend = true;
+                continue;
+            }
+            fi++;                                   // traverser: expand every action
+            const int o = fi * fstride;
+            f_st[o] = s;
+            f_meta[o] = make_uint2((uint32_t)slot | (nl << 12), list);
+            pend_a = list & 0xFu; pend = true;
+            continue;
+        }
+        if (fi < 0) break;
+        const int o = fi * fstride;
+        uint2 meta = f_meta[o];
+        const int slot = (int)(meta.x & 0xFFFu);
+        const int nl = (int)((meta.x >> 12) & 0x7u);
+        int cur = (int)((meta.x >> 16) & 0x7u);
+        f_cv[(size_t)o * 4 + cur] = ret;
+        cur++;
+        if (cur < nl) {
+            f_meta[o] = make_uint2((meta.x & 0xFFFFu) | ((uint32_t)cur << 16), meta.y);
+            s = f_st[o];
+            pend_a = (meta.y >> (4 * cur)) & 0xFu; pend = true;
+            returning = false;
+            continue;
+        }
+        double cv[4], value = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            cv[i] = (i < nl) ? f_cv[(size_t)o * 4 + i] : 0.0;
+            if (i < nl) value = __dadd_rn(value, __dmul_rn(sh.sig[4 * slot + i], cv[i]));
+        }
+        if (nl > 1) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < nl) atomicAdd(&sh.dreg[4 * slot + i], __dadd_rn(cv[i], -value));
+        }
+        n_upd++;
+        ret = value;
+        fi--;
+        returning = true;
+    }
+}
+
+__global__ void __launch_bounds__(ES_THREADS, 1) mccfr_es_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
+                                                                 unsigned long long first_trav, int nframes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = d.n_slots, T = blockDim.x, tid = threadIdx.x;
+    double* sig = (double*)smem_raw;
+    double* cdf = sig + 4 * S;
+    double* dreg = cdf + 4 * S;
+    unsigned long long* hk = (unsigned long long*)(dreg + 4 * S);
+    uint4* f_st = (uint4*)(hk + d.hcap);
+    double* f_cv = (double*)(f_st + (size_t)T * nframes);
+    uint2* f_meta = (uint2*)(f_cv + (size_t)T * nframes * 4);
+    uint32_t* dcnt = (uint32_t*)(f_meta + (size_t)T * nframes);
+    int16_t* hs = (int16_t*)(dcnt + S);
+    uint8_t* touched = (uint8_t*)(hs + d.hcap);
+    for (int s = tid; s < S; s += T) {
+        double reg[4], sg[4], cd[4];
+        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+        regret_match(reg, d.slot_nlegal[s], sg);
+        strategy_cdf(sg, d.slot_nlegal[s], cd);
+        for (int i = 0; i < 4; i++) { sig[4 * s + i] = sg[i]; cdf[4 * s + i] = cd[i]; dreg[4 * s + i] = 0.0; }
+        dcnt[s] = 0u; touched[s] = 0;
+    }
+    for (int i = tid; i < d.hcap; i += T) { hk[i] = d.hkeys[i]; hs[i] = d.hslots[i]; }
+    __syncthreads();
+    MccfrShared sh{hk, hs, d.hcap, sig, cdf, dreg, dcnt, touched, nullptr, nullptr};
+    unsigned long long nu = 0, nv = 0, ns = 0;
+    for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += (long long)gridDim.x * T)
+        for (int tp = 0; tp < 2; tp++) {
+            if (player < 2 && tp != player) continue;
+            es_traverse(d, sh, tp, first_trav + (unsigned long long)k, pkey, f_st + tid, f_cv + (size_t)tid * 4, f_meta + tid,
+                        T, nu, nv, ns);
+        }
+    __syncthreads();
+    for (int i = tid; i < 4 * S; i += T) { const double v = dreg[i]; if (v != 0.0) atomicAdd(&d.delta[i], v); }
+    for (int s = tid; s < S; s += T) {
+        if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
+        if (touched[s]) d.touched[s] = 1;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        nu += __shfl_down_sync(0xffffffffu, nu, off);
+        nv += __shfl_down_sync(0xffffffffu, nv, off);
+        ns += __shfl_down_sync(0xffffffffu, ns, off);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
+}
+
+// Outcome sampling (update rules of open_spiel's outcome_sampling_mccfr.py: epsilon-on-policy exploration at the
+// traverser's nodes with epsilon = 0.6, baseline 0): one trajectory per traversal, no branching, so the per-depth
+// records live in registers / local memory and the updates are replayed on the way back.
+#define MS_OS_EPSILON 0.6
+__device__ void os_traverse(const SolverDev& d, const MccfrShared& sh, double* dwt, int tp, unsigned long long trav,
+                            uint2 pkey, unsigned long long& n_upd, unsigned long long& n_vis, unsigned long long& n_step) {
+    MsState s = d.root;
+    const uint32_t dealt = dealt_set(d.root);
+    const uint32_t tag = MS_TAG_OS + (uint32_t)tp;
+    double my_reach = 1.0, opp_reach = 1.0, sample_reach = 1.0;
+    int rslot[16], rmeta[16];                 // per ply: slot; n_legal | sampled index << 4 | traverser flag << 8
+    double rsig[16], rsp[16], rw[16], rmw[16];
+    int depth = 0;
+    uint32_t call = 0;
+    while (!st_terminal(s) && depth < 16) {
+        const uint32_t my_call = call++;
+        n_vis++;
+        const int p = st_cur(s);
+        uint32_t list;
+        const uint32_t nl = legal_list(s, d.hand_order, p, list);
+        const int slot = lookup_slot(sh.hk, sh.hs, sh.hcap, infoset_key(s, p));
+        sh.touched[slot] = 1;
+        double sg[4], sp[4];
+        const double uni = __ddiv_rn(1.0, (double)nl);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            sg[i] = sh.sig[4 * slot + i];
+            sp[i] = (p == tp) ? __dadd_rn(__dmul_rn(MS_OS_EPSILON, uni), __dmul_rn(1.0 - MS_OS_EPSILON, sg[i])) : sg[i];
+        }
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), my_call >> 1, tag), pkey);
+        const double u = (my_call & 1u) ? u53(x.z, x.w) : u53(x.x, x.y);
+        const int ai = sample_action(sp, (int)nl, u);
+        rslot[depth] = slot;
+        rmeta[depth] = (int)nl | (ai << 4) | ((p == tp) ? 256 : 0);
+        rsig[depth] = sg[ai]; rsp[depth] = sp[ai];
+        rw[depth] = __ddiv_rn(opp_reach, sample_reach);
+        rmw[depth] = __ddiv_rn(my_reach, sample_reach);
+        if (p == tp) my_reach = __dmul_rn(my_reach, sg[ai]); else opp_reach = __dmul_rn(opp_reach, sg[ai]);
+        sample_reach = __dmul_rn(sample_reach, sp[ai]);
+        step(s, (list >> (4 * ai)) & 0xFu, table_set_from_dealt(s, dealt)); n_step++;
+        depth++;
+    }
+    n_vis++;                                   // the terminal call
+    const int r = st_terminal(s) ? reward0_x2(s) : 0;
+    double value = 0.5 * (double)(tp == 0 ? r : -r);
+    for (int k = depth - 1; k >= 0; k--) {
+        const int nl = rmeta[k] & 15, ai = (rmeta[k] >> 4) & 15, slot = rslot[k];
+        const double est = __ddiv_rn(value, rsp[k]);
+        const double ve = __dmul_rn(rsig[k], est);
+        if (rmeta[k] & 256) {
+            const double cfv = __dmul_rn(ve, rw[k]);
+            for (int i = 0; i < nl; i++) {
+                const double cfa = __dmul_rn(i == ai ? est : 0.0, rw[k]);
+                atomicAdd(&sh.dreg[4 * slot + i], __dadd_rn(cfa, -cfv));
+            }
+            atomicAdd(&dwt[slot], rmw[k]);     // strategy_sum += (my_reach / sample_reach) * sigma, sigma applied later
+            n_upd++;
+        }
+        value = ve;
+    }
+}
+
+__global__ void __launch_bounds__(256) mccfr_os_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
+                                                       unsigned long long first_trav) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = d.n_slots, T = blockDim.x, tid = threadIdx.x;
+    double* sig = (double*)smem_raw;
+    double* dreg = sig + 4 * S;
+    double* dwt = dreg + 4 * S;
+    unsigned long long* hk = (unsigned long long*)(dwt + S);
+    int16_t* hs = (int16_t*)(hk + d.hcap);
+    uint8_t* touched = (uint8_t*)(hs + d.hcap);
+    for (int s = tid; s < S; s += T) {
+        double reg[4], sg[4];
+        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+        regret_match(reg, d.slot_nlegal[s], sg);
+        for (int i = 0; i < 4; i++) { sig[4 * s + i] = sg[i]; dreg[4 * s + i] = 0.0; }
+        dwt[s] = 0.0; touched[s] = 0;
+    }
+    for (int i = tid; i < d.hcap; i += T) { hk[i] = d.hkeys[i]; hs[i] = d.hslots[i]; }
+    __syncthreads();
+    MccfrShared sh{hk, hs, d.hcap, sig, nullptr, dreg, nullptr, touched, nullptr, nullptr};
+    unsigned long long nu = 0, nv = 0, ns = 0;
+    for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += (long long)gridDim.x * T)
+        for (int tp = 0; tp < 2; tp++) {
+            if (player < 2 && tp != player) continue;
+            os_traverse(d, sh, dwt, tp, first_trav + (unsigned long long)k, pkey, nu, nv, ns);
+        }
+    __syncthreads();
+    for (int i = tid; i < 4 * S; i += T) { const double v = dreg[i]; if (v != 0.0) atomicAdd(&d.delta[i], v); }
+    for (int s = tid; s < S; s += T) {
+        if (dwt[s] != 0.0) atomicAdd(&d.delta[4 * S + s], dwt[s]);
+        if (touched[s]) d.touched[s] = 1;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        nu += __shfl_down_sync(0xffffffffu, nu, off);
+        nv += __shfl_down_sync(0xffffffffu, nv, off);
+        ns += __shfl_down_sync(0xffffffffu, ns, off);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
+}
+
 // table += delta; delta = 0.  strategy_sum += count * sigma with sigma = RM(regret BEFORE the update),
 // i.e. the strategy the batch was sampled with.
 __global__ void __launch_bounds__(256) mccfr_apply_kernel(SolverDev d) {
@@ -1203,6 +1452,33 @@ int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox
     mccfr_batch_kernel<<<grid, MCCFR_THREADS, smem, (cudaStream_t)stream>>>(
         s->dev, player, (long long)n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
         (unsigned long long)first_trav, s->nframes);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_trav, uint64_t philox_seed,
+                        uint64_t first_trav, void* stream) {
+    if (mode == 0) return ms_mccfr_batch(s, player, n_trav, philox_seed, first_trav, stream);
+    int rc = check_dev(s); if (rc) return rc;
+    if (mode < 0 || mode > 2 || player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch_mode: bad argument");
+    if (n_trav == 0) return MS_OK;
+    const uint2 key = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
+    if (mode == 1) {
+        const size_t smem = es_smem_bytes(s->n_slots, s->hcap, s->nframes, ES_THREADS);
+        if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "ES working set %zu B exceeds shared memory", smem);
+        MS_CUDA(cudaFuncSetAttribute(mccfr_es_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mccfr_es_kernel<<<grid_for(n_trav, ES_THREADS, 1), ES_THREADS, smem, (cudaStream_t)stream>>>(
+            s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav, s->nframes);
+    } else {
+        const size_t smem = 72 * (size_t)s->n_slots + 10 * (size_t)s->hcap + s->n_slots + 64;
+        if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "OS working set %zu B exceeds shared memory", smem);
+        MS_CUDA(cudaFuncSetAttribute(mccfr_os_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        mccfr_os_kernel<<<grid_for(n_trav, 256, per_sm), 256, smem, (cudaStream_t)stream>>>(
+            s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav);
+    }
     MS_LAUNCH_CHECK();
     return MS_OK;
 }

@@ -161,10 +161,11 @@ class Solver:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_mccfr_inplace(self.h, int(iters), int(philox_seed), int(first_iter), self._stream()))
 
-    def mccfr_batch(self, player, n_trav, philox_seed=0, first_trav=0):
+    def mccfr_batch(self, player, n_trav, philox_seed=0, first_trav=0, mode=0):
+        """mode 0 = the reference's estimator, 1 = external sampling, 2 = outcome sampling (textbook, opt-in)."""
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.ms_mccfr_batch(self.h, int(player), int(n_trav), int(philox_seed), int(first_trav),
-                                               self._stream()))
+            _lib.check(self.lib.ms_mccfr_batch_mode(self.h, int(mode), int(player), int(n_trav), int(philox_seed),
+                                                    int(first_trav), self._stream()))
 
     def mccfr_apply(self):
         with torch.cuda.device(self.device):

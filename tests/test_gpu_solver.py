@@ -281,3 +281,45 @@ def test_evaluate_agent_uses_the_device_path():
     exact = (10001 * _exact_value_p0(sv, t_np, u_np) - 10000 * _exact_value_p0(sv, u_np, t_np)) / 20001
     assert abs(avg - exact) < 0.08
     assert stats["trained_avg"] > stats["opponent_avg"]
+
+
+@pytest.mark.parametrize("mode,player,ntrav", [(1, 0, 600), (1, 1, 600), (1, 2, 900), (2, 0, 4000), (2, 1, 4000), (2, 2, 5000)])
+def test_textbook_estimators_match_oracle(mode, player, ntrav):
+    """External sampling (mode 1) and outcome sampling (mode 2): the estimators the north star names, which the
+    reference does not implement.  GPU batch vs the C oracle on the same Philox stream, frozen sigma."""
+    sv = Solver(seed=42)
+    t = ora.Table()
+    t.mccfr_populate()
+    keys0, _, _, _, _ = t.arrays()
+    perm = _perm(sv, keys0, strip_player=True)
+    sv.mccfr_inplace(5, philox_seed=3)                      # a non-trivial common starting table
+    t.mccfr_iterate(5, ora.Rng(1, 3))
+    _, r0, s0, _, _ = t.arrays()
+    sv.counters(reset=True)
+    sv.mccfr_batch(player, ntrav, philox_seed=99, first_trav=40, mode=mode)
+    sv.mccfr_apply()
+    oreg, ostr, nu, nv = r0.copy(), s0.copy(), 0, 0
+    for p in ((0, 1) if player == 2 else (player,)):
+        t.set_arrays(r0, s0)
+        u, v = t.mccfr_batch_mode(mode, p, 99, 40, ntrav)
+        _, r1, s1, _, _ = t.arrays()
+        oreg += r1 - r0
+        ostr += s1 - s0
+        nu, nv = nu + u, nv + v
+    reg, strat, _ = sv.export()
+    np.testing.assert_allclose(reg[perm], oreg, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(strat[perm], ostr, rtol=1e-9, atol=1e-9)
+    c = sv.counters()
+    assert (c["updates"], c["visits"]) == (nu, nv)
+
+
+def test_external_sampling_converges_below_the_reference_plateau():
+    """The reference's estimator plateaus near 0.49 exploitability on this deal; textbook external sampling on the
+    same table keeps improving (oracle: 0.059 after 120 k traversals per player)."""
+    sv = Solver(seed=42)
+    B = 4096
+    for it in range(40):
+        sv.mccfr_batch(2, B, philox_seed=1, first_trav=it * B, mode=1)
+        sv.mccfr_apply()
+    e = sv.exploitability(1)
+    assert e < 0.12, e
