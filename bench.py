@@ -281,6 +281,32 @@ def run_ours(args):
                  "h2d_bytes_per_step": 2 * S * 4 * 8, "d2h_bytes_per_step": 2 * S * 4 * 8,
                  "what": "ms_solver_import_table (pinned host) + mccfr batch + all-reduce + apply + ms_solver_export_table"}
 
+    # ------------------------------------------------------------------ textbook external sampling (opt-in estimator)
+    es_obj = None
+    if rank == 0:
+        es_sv = Solver(seed=42, device=dev)
+        Bes = 148 * 512 * 2
+        for i in range(W):
+            es_sv.mccfr_batch(2, Bes, philox_seed=args.seed, first_trav=i * Bes, mode=1)
+            es_sv.mccfr_apply()
+        es_sv.counters(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(K):
+            es_sv.mccfr_batch(2, Bes, philox_seed=args.seed, first_trav=(W + i) * Bes, mode=1)
+            es_sv.mccfr_apply()
+        e1.record()
+        torch.cuda.synchronize()
+        es_cnt = es_sv.counters()
+        es_s = e0.elapsed_time(e1) * 1e-3
+        es_obj = {"estimator": "external sampling (Lanctot et al. 2009), not in the reference", "kernel": "mccfr_es_kernel",
+                  "traversals_per_sec": 2.0 * Bes * K / es_s, "regret_updates_per_sec": es_cnt["updates"] / es_s,
+                  "node_visits_per_sec": es_cnt["visits"] / es_s,
+                  "exploitability_after": {"traversals_per_player": (W + K) * Bes, "value": es_sv.exploitability(1)},
+                  "note": "the reference's own estimator plateaus near 0.49 exploitability on this deal"}
+        del es_sv
+
     # ------------------------------------------------------------------ env rollouts (config 2)
     G = args.games
     seeds_np = np.arange(1 + rank * G, 1 + (rank + 1) * G, dtype=np.int64)
@@ -457,6 +483,8 @@ def run_ours(args):
         "sdcfr": sd_obj,
         "env_step_api": step_obj,
         "cfr": cfr_obj,
+        "mccfr_external_sampling": es_obj,
+        "collective": collective,
     }
     if primary is mccfr_obj:
         line["node_visits_per_sec"] = mccfr_obj["node_visits_per_sec"]
