@@ -388,6 +388,22 @@ def run_ours(args):
                "note": "BASELINE.json configs[0]: vanilla CFR on the seed-42 deal, 200 iterations in one launch, float64, "
                        "bit-identical to the reference's tables; the reference takes 389 ms per iteration on one CPU core"}
 
+    # ------------------------------------------------------------------ atomic roofline
+    atom_obj = None
+    if rank == 0:
+        import ctypes
+        peaks = (ctypes.c_double * 3)()
+        _lib.check(_lib.load().ms_debug_atomic_peaks(peaks, _lib.stream_ptr()))
+        pairs_per_s = mccfr_value / world / 172.0          # traversal pairs per second on this GPU
+        # per traversal pair the batch kernel issues 118 shared-memory fp64 atomic adds (regret deltas of the
+        # traverser nodes with more than one action: (1*4 + 5*3 + 20*2) per player) and 172 u32 adds (visit counts)
+        atom_obj = {"measured_peaks_per_sec": {"smem_f64_atomic_add": peaks[0], "smem_u32_atomic_add": peaks[1],
+                                               "global_red_f64_l2_resident": peaks[2]},
+                    "mccfr_smem_f64_atomics_per_sec": 118.0 * pairs_per_s, "mccfr_smem_u32_atomics_per_sec": 172.0 * pairs_per_s,
+                    "frac_of_smem_f64_peak": 118.0 * pairs_per_s / peaks[0], "frac_of_smem_u32_peak": 172.0 * pairs_per_s / peaks[1],
+                    "note": "microbenchmark: 148 CTAs x 768 threads, pseudo-random addresses over a 738x4 table; shared-memory "
+                            "fp64 atomicAdd compiles to an ATOMS.CAST.SPIN.64 compare-and-swap loop, global fp64 to REDG.E.ADD.F64"}
+
     # ------------------------------------------------------------------ SDCFR traversal (config 4)
     from scopa_b200 import sdcfr as sd
     T = args.sd_trav
@@ -484,6 +500,7 @@ def run_ours(args):
         "env_step_api": step_obj,
         "cfr": cfr_obj,
         "mccfr_external_sampling": es_obj,
+        "atomics": atom_obj,
         "collective": collective,
     }
     if primary is mccfr_obj:

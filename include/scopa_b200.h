@@ -63,6 +63,11 @@ int ms_deck_from_seeds(const int64_t* d_seeds, int64_t n, uint64_t* d_deck, void
 int ms_debug_deal_slow_path(const int64_t* d_seeds, int64_t n, ms_state* d_states, uint32_t* d_hand_order,
                             void* stream);
 
+/* measurement hook: atomic-add throughput of this GPU on a table the size of the MCCFR delta table, pseudo-random
+ * addresses, all SMs busy: h_out[0] = shared-memory fp64 atomicAdd/s, [1] = shared-memory u32 atomicAdd/s,
+ * [2] = global (L2-resident) fp64 RED/s.  The atomic roofline SURVEY 8(d) asks for. */
+int ms_debug_atomic_peaks(double h_out[3], void* stream);
+
 /* ms_step: MiniScopaEnv.step(action) on n independent states in place (src/envs/mini_scopa_game.py:140-167
  *   incl. play_card :93-104, card_in_table :66-91, evaluate_game :106-114).  d_rewards ([n][2] f32,
  *   may be NULL) receives the terminal rewards (0,0 while running); d_done ([n] u8, may be NULL)

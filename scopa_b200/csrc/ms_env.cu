@@ -575,3 +575,76 @@ int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_se
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Atomic-throughput microbenchmarks (there is no published atomic peak for this part, so the
+// roofline the MCCFR kernel's atomics are compared with is measured on the box).  Addresses are pseudo-random
+// over a table the size of the MCCFR delta table (738 x 4 doubles) -- the uncontended / L2-resident case.
+namespace ms {
+constexpr int ATOM_TABLE = 738 * 4;
+
+__global__ void __launch_bounds__(768, 1) atom_smem_f64_kernel(double* sink, int iters) {
+    __shared__ double tab[ATOM_TABLE];
+    for (int i = threadIdx.x; i < ATOM_TABLE; i += blockDim.x) tab[i] = 0.0;
+    __syncthreads();
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int i = 0; i < iters; i++) {
+        x = x * 1664525u + 1013904223u;
+        atomicAdd(&tab[(x >> 8) % ATOM_TABLE], 1.0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sink[blockIdx.x] = tab[0] + tab[ATOM_TABLE - 1];
+}
+
+__global__ void __launch_bounds__(768, 1) atom_smem_u32_kernel(double* sink, int iters) {
+    __shared__ uint32_t tab[ATOM_TABLE];
+    for (int i = threadIdx.x; i < ATOM_TABLE; i += blockDim.x) tab[i] = 0u;
+    __syncthreads();
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int i = 0; i < iters; i++) {
+        x = x * 1664525u + 1013904223u;
+        atomicAdd(&tab[(x >> 8) % ATOM_TABLE], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sink[blockIdx.x] = (double)(tab[0] + tab[ATOM_TABLE - 1]);
+}
+
+__global__ void __launch_bounds__(768, 1) atom_global_f64_kernel(double* tab, int iters) {
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int i = 0; i < iters; i++) {
+        x = x * 1664525u + 1013904223u;
+        atomicAdd(&tab[(x >> 8) % ATOM_TABLE], 1.0);      // result unused -> RED.E.ADD.F64
+    }
+}
+}  // namespace ms
+
+extern "C" int ms_debug_atomic_peaks(double h_out[3], void* stream) {
+    if (!h_out) return fail(MS_ERR_ARG, "ms_debug_atomic_peaks: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d = nullptr;
+    MS_CUDA(cudaMalloc(&d, sizeof(double) * (ATOM_TABLE + kNumSMs)));
+    MS_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (ATOM_TABLE + kNumSMs), st));
+    cudaEvent_t e0, e1;
+    MS_CUDA(cudaEventCreate(&e0)); MS_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, grid = kNumSMs, block = 768;
+    const double ops = (double)iters * grid * block;
+    for (int which = 0; which < 3; which++) {
+        float ms_best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {          // first repetition is the warm-up
+            MS_CUDA(cudaEventRecord(e0, st));
+            if (which == 0) atom_smem_f64_kernel<<<grid, block, 0, st>>>(d + ATOM_TABLE, iters);
+            else if (which == 1) atom_smem_u32_kernel<<<grid, block, 0, st>>>(d + ATOM_TABLE, iters);
+            else atom_global_f64_kernel<<<grid, block, 0, st>>>(d, iters);
+            MS_LAUNCH_CHECK();
+            MS_CUDA(cudaEventRecord(e1, st));
+            MS_CUDA(cudaEventSynchronize(e1));
+            float ms_t = 0.f;
+            MS_CUDA(cudaEventElapsedTime(&ms_t, e0, e1));
+            if (rep > 0 && ms_t < ms_best) ms_best = ms_t;
+        }
+        h_out[which] = ops / (ms_best * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    MS_CUDA(cudaFree(d));
+    return MS_OK;
+}
