@@ -196,6 +196,22 @@ int ms_solver_policy(ms_solver* s, int32_t policy_kind, double* d_policy, void* 
 int ms_eval_policies(ms_solver* s, const double* d_policy_seat0, const double* d_policy_seat1, int64_t n_games,
                      uint64_t philox_seed, uint64_t first_game, float* d_reward0, uint8_t* d_scopas, void* stream);
 
+/* ------------------------------------------------------------------ team Miniscopa (2v2) ------
+ * The 4-player variant (src/envs/team_mini_scopa_game.py:44-243): all 16 cards dealt 4x4, 16 plies, teams {0,1}
+ * vs {2,3}, last-capturer sweep, team scoring.  32-byte packed state (layout in scopa_b200/csrc/ms_team.cu).
+ *   ms_team_deal_from_seeds: TeamMiniScopaEnv.reset(seed) (:167-169 -> TeamMiniScopaGame.reset :62-70; seed 0
+ *     means 42); d_hand_order[g] = the shuffled deck, nibble 4p+i = i-th card dealt to player p.
+ *   ms_team_step: TeamMiniScopaEnv.step (:171-205); d_rewards [n][4] f32 (team rewards t0,t0,t1,t1), d_done [n] u8.
+ *   ms_team_rollout_random: 16 uniform-random legal plies per game in one launch (Philox "TEAM" stream: ctr =
+ *     (game id lo, hi, ply/4, tag), word ply%4); d_actions [n][16] u8. */
+typedef struct { uint32_t w[8]; } ms_team_state;
+int ms_team_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_team_state* d_states, uint64_t* d_hand_order, void* stream);
+int ms_team_step(ms_team_state* d_states, const uint8_t* d_actions, float* d_rewards, uint8_t* d_done, int64_t n, void* stream);
+int ms_team_rollout_random(const ms_team_state* d_states, const uint64_t* d_hand_order, int64_t n, uint64_t philox_seed,
+                           uint64_t game_offset, uint8_t* d_actions, float* d_rewards, ms_team_state* d_final, void* stream);
+int ms_team_deal_from_seeds_host(const int64_t* h_seeds, int64_t n, ms_team_state* h_states, uint64_t* h_hand_order);
+int ms_team_step_host(ms_team_state* h_states, const uint8_t* h_actions, float* h_rewards, uint8_t* h_done, int64_t n);
+
 /* -------------------------------------------------------------------------------- SDCFR ------
  * Advantage network = FlexibleNet mlp 34 -> 128 -> 64 -> 16 with ReLU (src/algorithms/deep_cfr/nets.py:151-235,
  * :296-331; deep_cfr.py:24-52).  A net is passed as ONE fp32 blob of 13776 floats in nn.Linear order:

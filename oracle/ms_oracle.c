@@ -993,3 +993,101 @@ void ora_mccfr_batch_mode(ora_table* t, int64_t seed, int mode, int player, uint
     if (n_visits) *n_visits = c.n_visits;
     ora_rng_free(rng); free(dreg); free(dstr);
 }
+
+/* ================================================================================ team Miniscopa (2v2) */
+/* src/envs/team_mini_scopa_game.py:44-243, list-based like the rest of this file. */
+void ora_team_reset(ora_team_env* e, int64_t seed, int has_seed) {
+    int64_t s = (has_seed && seed != 0) ? seed : e->seed;        /* `seed or self.seed` (:168) */
+    int deck[16];
+    ora_deck(s, deck);
+    memset(e->ncaps, 0, sizeof e->ncaps);
+    memset(e->scopas, 0, sizeof e->scopas);
+    e->ntable = 0; e->last_capture_team = -1;
+    for (int p = 0; p < 4; p++) {
+        e->nhand[p] = 4;
+        for (int i = 0; i < 4; i++) e->hand[p][i] = deck[4 * p + i];
+        e->rewards[p] = 0; e->term[p] = 0;
+    }
+    e->agent = 0; e->step_count = 0;
+}
+
+void ora_team_init(ora_team_env* e, int64_t seed) {
+    memset(e, 0, sizeof *e);
+    e->max_steps = 16; e->seed = seed;
+    ora_team_reset(e, seed, 1);
+}
+
+static void team_evaluate(ora_team_env* e, double out[4]) {       /* evaluate_game (:118-148) */
+    if (e->ntable > 0 && e->last_capture_team >= 0) {
+        int p = 2 * e->last_capture_team;                         /* first player of that team */
+        for (int i = 0; i < e->ntable; i++) e->caps[p][e->ncaps[p]++] = e->table[i];
+    }
+    int sc[2] = {0, 0};
+    for (int p = 0; p < 4; p++) sc[p / 2] += e->ncaps[p] + 2 * e->scopas[p];
+    int total = sc[0] + sc[1];
+    if (total == 0) { out[0] = out[1] = out[2] = out[3] = 0; return; }
+    double mean = (double)total / 2;
+    out[0] = out[1] = sc[0] - mean; out[2] = out[3] = sc[1] - mean;
+}
+
+void ora_team_step(ora_team_env* e, int action) {                 /* step (:171-205) + play_card (:101-116) */
+    if (e->term[e->agent]) return;
+    int pl = e->agent, hp = -1;
+    if (action >= 0 && action < 16)
+        for (int i = 0; i < e->nhand[pl]; i++) if (e->hand[pl][i] == action) { hp = i; break; }
+    if (hp >= 0) {
+        int card = e->hand[pl][hp], pos[8];
+        int ncap = ora_card_in_table(e->table, e->ntable, card, pos);
+        if (ncap > 0) {
+            int keep[16], nk = 0;
+            for (int q = 0; q < ncap; q++) e->caps[pl][e->ncaps[pl]++] = e->table[pos[q]];
+            e->caps[pl][e->ncaps[pl]++] = card;
+            for (int i = 0; i < e->ntable; i++) {
+                int gone = 0;
+                for (int q = 0; q < ncap; q++) if (pos[q] == i) gone = 1;
+                if (!gone) keep[nk++] = e->table[i];
+            }
+            for (int i = 0; i < nk; i++) e->table[i] = keep[i];
+            e->ntable = nk;
+            e->last_capture_team = pl / 2;
+            if (nk == 0) e->scopas[pl] += 1;
+        } else {
+            e->table[e->ntable++] = card;
+        }
+        for (int i = hp; i + 1 < e->nhand[pl]; i++) e->hand[pl][i] = e->hand[pl][i + 1];
+        e->nhand[pl]--;
+    }
+    e->step_count += 1;
+    int empty = 1;
+    for (int p = 0; p < 4; p++) if (e->nhand[p]) empty = 0;
+    if (empty || e->step_count >= e->max_steps) {
+        double r[4]; team_evaluate(e, r);
+        for (int p = 0; p < 4; p++) { e->rewards[p] = r[p]; e->term[p] = 1; }
+    }
+    e->agent = (pl + 1) % 4;
+}
+
+#define TAG_TEAM 0x4D414554u
+void ora_team_rollout_random(const int64_t* seeds, int64_t n, uint64_t philox_seed, uint64_t game_offset,
+                             uint8_t* actions, float* rewards, uint8_t* scopas, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t g = 0; g < n; g++) {
+        ora_team_env e;
+        ora_team_init(&e, 42);
+        ora_team_reset(&e, seeds[g], 1);
+        uint32_t key[2] = {(uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)};
+        for (int ply = 0; ply < 16; ply++) {
+            uint64_t gid = game_offset + (uint64_t)g;
+            uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(ply >> 2), TAG_TEAM}, o[4];
+            philox4x32_10(ctr, key, o);
+            int pl = e.agent, nl = e.term[pl] ? 0 : e.nhand[pl];
+            int a = nl > 0 ? e.hand[pl][(int)(((uint64_t)o[ply & 3] * (uint64_t)nl) >> 32)] : 0;
+            actions[g * 16 + ply] = (uint8_t)a;
+            ora_team_step(&e, a);
+        }
+        for (int p = 0; p < 4; p++) { rewards[g * 4 + p] = (float)e.rewards[p]; if (scopas) scopas[g * 4 + p] = (uint8_t)e.scopas[p]; }
+    }
+}

@@ -32,6 +32,13 @@ class OraEnv(C.Structure):
                 ("rewards", C.c_double * 2), ("term", C.c_int * 2)]
 
 
+class OraTeamEnv(C.Structure):
+    _fields_ = [("hand", (C.c_int * 4) * 4), ("nhand", C.c_int * 4), ("caps", (C.c_int * 32) * 4), ("ncaps", C.c_int * 4),
+                ("scopas", C.c_int * 4), ("table", C.c_int * 16), ("ntable", C.c_int), ("last_capture_team", C.c_int),
+                ("agent", C.c_int), ("step_count", C.c_int), ("max_steps", C.c_int), ("seed", C.c_int64),
+                ("rewards", C.c_double * 4), ("term", C.c_int * 4)]
+
+
 class OraState(C.Structure):
     _fields_ = [("env", OraEnv), ("is_terminal", C.c_int), ("history", C.c_int * 40), ("nhist", C.c_int)]
 
@@ -97,6 +104,10 @@ def lib():
     L.ora_sdcfr_traverse.argtypes = [P(OraMlp), i64, ci, vp, u64, vp, vp, vp, ci, P(ci)]
     L.ora_sdcfr_traverse.restype = C.c_float
     L.ora_mccfr_bench.argtypes = [i64, i64, ci, u64, P(i64), P(i64)]
+    L.ora_team_init.argtypes = [P(OraTeamEnv), i64]
+    L.ora_team_reset.argtypes = [P(OraTeamEnv), i64, ci]
+    L.ora_team_step.argtypes = [P(OraTeamEnv), ci]
+    L.ora_team_rollout_random.argtypes = [vp, i64, u64, u64, vp, vp, vp, ci]
     L.ora_mccfr_batch_mode.argtypes = [vp, i64, ci, ci, u64, u64, i64, P(i64), P(i64)]
     _lib = L
     return L
@@ -342,3 +353,38 @@ def mccfr_bench(ntrav_per_thread, nthreads, philox_seed=0, seed=42):
     u, v = C.c_int64(), C.c_int64()
     lib().ora_mccfr_bench(seed, ntrav_per_thread, nthreads, philox_seed, C.byref(u), C.byref(v))
     return u.value, v.value
+
+
+class TeamEnv:
+    """ora_team_env with the snapshot shape of oracle/gen_golden_team.py."""
+
+    def __init__(self, seed=42):
+        self.e = OraTeamEnv()
+        lib().ora_team_init(C.byref(self.e), seed)
+
+    def reset(self, seed=None):
+        lib().ora_team_reset(C.byref(self.e), 0 if seed is None else seed, 0 if seed is None else 1)
+
+    def step(self, action):
+        lib().ora_team_step(C.byref(self.e), action)
+
+    def snapshot(self):
+        e = self.e
+        return {"table": [e.table[i] for i in range(e.ntable)],
+                "hands": [[e.hand[p][i] for i in range(e.nhand[p])] for p in range(4)],
+                "caps": [[e.caps[p][i] for i in range(e.ncaps[p])] for p in range(4)],
+                "scopas": [e.scopas[p] for p in range(4)],
+                "lct": None if e.last_capture_team < 0 else e.last_capture_team,
+                "agent": f"player_{e.agent}", "step": e.step_count,
+                "rew": [e.rewards[p] for p in range(4)], "term": [bool(e.term[p]) for p in range(4)]}
+
+
+def team_rollout_random(seeds, philox_seed, nthreads=0, game_offset=0):
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    n = len(seeds)
+    actions = np.zeros((n, 16), dtype=np.uint8)
+    rewards = np.zeros((n, 4), dtype=np.float32)
+    scopas = np.zeros((n, 4), dtype=np.uint8)
+    lib().ora_team_rollout_random(seeds.ctypes.data, n, philox_seed, game_offset, actions.ctypes.data, rewards.ctypes.data,
+                                  scopas.ctypes.data, nthreads)
+    return actions, rewards, scopas

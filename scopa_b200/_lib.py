@@ -58,6 +58,11 @@ _SIGS = {
     "ms_best_response": ([vp, i32, C.POINTER(dbl), vp], C.c_int),
     "ms_solver_policy": ([vp, i32, vp, vp], C.c_int),
     "ms_eval_policies": ([vp, vp, vp, i64, u64, u64, vp, vp, vp], C.c_int),
+    "ms_team_deal_from_seeds": ([vp, i64, vp, vp, vp], C.c_int),
+    "ms_team_step": ([vp, vp, vp, vp, i64, vp], C.c_int),
+    "ms_team_rollout_random": ([vp, vp, i64, u64, u64, vp, vp, vp, vp], C.c_int),
+    "ms_team_deal_from_seeds_host": ([vp, i64, vp, vp], C.c_int),
+    "ms_team_step_host": ([vp, vp, vp, vp, i64], C.c_int),
     "ms_sdcfr_samples_per_traversal": ([C.c_int], C.c_int),
     "ms_sdcfr_workspace_bytes": ([i64], C.c_size_t),
     "ms_mlp_forward": ([vp, C.c_int, vp, vp, vp, vp, i64, vp], C.c_int),

@@ -392,6 +392,22 @@ int ms_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_state* d_states, ui
     return MS_OK;
 }
 
+}  // extern "C"
+
+namespace ms {
+// deck with the env-level seed rule (`seed or self.seed`: 0 means 42) -- used by the team deal (ms_team.cu)
+int team_deck_from_seeds(const int64_t* d_seeds, int64_t n, uint64_t* d_deck, void* stream) {
+    int rc = ensure_mt_table();
+    if (rc) return rc;
+    deal_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)d_seeds, (long long)n, nullptr, nullptr, (unsigned long long*)d_deck, 1);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+}  // namespace ms
+
+extern "C" {
+
 int ms_deck_from_seeds(const int64_t* d_seeds, int64_t n, uint64_t* d_deck, void* stream) {
     if (n < 0 || (n > 0 && (!d_seeds || !d_deck))) return fail(MS_ERR_ARG, "ms_deck_from_seeds: bad argument");
     if (n == 0) return MS_OK;

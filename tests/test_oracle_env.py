@@ -93,3 +93,16 @@ def test_batch_deal_and_rollout_consistency():
         assert snap["term"] == [True, True]
         assert np.allclose(snap["rew"], rewards[g])
         assert rewards[g].sum() == 0
+
+
+def test_team_env_traces_from_reference():
+    """2v2 team Miniscopa (a "next" row): the oracle against 300 traces recorded from the unmodified reference,
+    incl. illegal actions, dead steps and the last-capturer sweep."""
+    traces = load_golden_json("team_env_traces.json.gz")["traces"]
+    for tr in traces:
+        e = ora.TeamEnv(42)
+        e.reset(tr["seed"])
+        assert e.snapshot() == tr["snaps"][0]
+        for a, snap in zip(tr["actions"], tr["snaps"][1:]):
+            e.step(a)
+            assert e.snapshot() == snap, (tr["seed"], tr["actions"])
