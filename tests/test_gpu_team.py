@@ -73,3 +73,27 @@ def test_team_env_drop_in():
             assert [st["rewards"][n] for n in env.possible_agents] == snap["rew"]
             assert [st["terminations"][n] for n in env.possible_agents] == snap["term"]
     assert env.game.get_team(3) == 1
+
+
+def test_tpi_wrapper_drop_in():
+    """The two-coordinator OpenSpiel view of the team game against traces recorded from the unmodified reference."""
+    from scopa_b200 import pyspiel_compat as pyspiel
+    from scopa_b200.envs import openspiel_team_mini_scopa  # noqa: F401
+    traces = load_golden_json("team_tpi_traces.json.gz")["traces"]
+    game = pyspiel.load_game("team_mini_scopa_tpi")
+    assert game.num_players() == 2
+
+    def rec(state):
+        return {"cp": state.current_player(), "term": state.is_terminal(), "legal": list(state.legal_actions()),
+                "legal0": list(state.legal_actions(0)), "legal1": list(state.legal_actions(1)),
+                "info0": state.information_state_string(0), "info1": state.information_state_string(1),
+                "hist": state.history_str(), "rew": [float(x) for x in state.rewards()]}
+
+    for k, tr in enumerate(traces[:30]):
+        state = game.new_initial_state()
+        assert rec(state) == tr["recs"][0]
+        for a, want in zip(tr["actions"], tr["recs"][1:]):
+            if k % 2:
+                state = state.clone()
+            state.apply_action(a)
+            assert rec(state) == want, (k, tr["actions"])
