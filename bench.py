@@ -388,6 +388,22 @@ def run_ours(args):
                "note": "BASELINE.json configs[0]: vanilla CFR on the seed-42 deal, 200 iterations in one launch, float64, "
                        "bit-identical to the reference's tables; the reference takes 389 ms per iteration on one CPU core"}
 
+    # throughput mode: 148 independent deals, one CTA (= one SM) per deal, one launch
+    from scopa_b200.solver import cfr_iterate_many
+    many = [Solver(seed=1000 + rank * 148 + i, device=dev) for i in range(148)]
+    cfr_iterate_many(many, 3)
+    torch.cuda.synchronize()
+    c0.record()
+    cfr_iterate_many(many, 100)
+    c1.record()
+    torch.cuda.synchronize()
+    nodes = sum(m_.n_nodes for m_ in many)
+    cfr_obj["many_deals"] = {"deals": 148, "iterations": 100, "ms": c0.elapsed_time(c1),
+                             "deal_iterations_per_sec": 148 * 100 / (c0.elapsed_time(c1) * 1e-3),
+                             "node_visits_per_sec": 2.0 * nodes * 100 / (c0.elapsed_time(c1) * 1e-3),
+                             "note": "ms_cfr_iterate_many: seeds 1000.., float64, each deal's tables identical to a solo run"}
+    del many
+
     # ------------------------------------------------------------------ atomic roofline
     atom_obj = None
     if rank == 0:

@@ -147,6 +147,9 @@ int ms_solver_device_ptrs(ms_solver* s, double** d_regret, double** d_strategy, 
  *   the returned node utility (synchronises). */
 int ms_cfr_iterate(ms_solver* s, int32_t iters, void* stream);
 int ms_cfr_traverse(ms_solver* s, int32_t player, double reach_p0, double reach_p1, double* h_value, void* stream);
+/* ms_cfr_iterate_many: `iters` CFR iterations on n independent solvers (deals) in ONE launch, one CTA per deal
+ *   (throughput mode: the per-deal sweep is latency bound, 148 of them run side by side). */
+int ms_cfr_iterate_many(ms_solver* const* solvers, int32_t n_solvers, int32_t iters, void* stream);
 
 /* ms_mccfr_inplace: `iters` reference iterations of MCCFRTrainer.iteration()
  *   (src/algorithms/mc_cfr.py:37-92) with in-place table updates after every node, sampling from the

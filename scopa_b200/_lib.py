@@ -46,6 +46,7 @@ _SIGS = {
     "ms_solver_import_table": ([vp, vp, vp, vp], C.c_int),
     "ms_solver_device_ptrs": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)], C.c_int),
     "ms_cfr_iterate": ([vp, i32, vp], C.c_int),
+    "ms_cfr_iterate_many": ([C.POINTER(vp), i32, i32, vp], C.c_int),
     "ms_cfr_traverse": ([vp, i32, dbl, dbl, C.POINTER(dbl), vp], C.c_int),
     "ms_mccfr_inplace": ([vp, i64, u64, u64, vp], C.c_int),
     "ms_mccfr_batch": ([vp, i32, i64, u64, u64, vp], C.c_int),

@@ -275,10 +275,27 @@ __device__ void cfr_traversal(const SolverDev& d, const CfrSmem& m, int tp, doub
     __syncthreads();
 }
 
+__device__ void cfr_run(const SolverDev& d, int n_dec, int iters, int only_player, double r0, double r1, double* out_value,
+                        unsigned char* smem_raw, int* s_lvl, int* s_slvl);
+
 __global__ void __launch_bounds__(512, 1) cfr_kernel(SolverDev d, int n_dec, int iters, int only_player, double r0,
                                                      double r1, double* out_value) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_lvl[MAXL + 1], s_slvl[MAXL + 1];
+    cfr_run(d, n_dec, iters, only_player, r0, r1, out_value, smem_raw, s_lvl, s_slvl);
+}
+
+// Throughput mode: independent deals solved side by side, one CTA per deal (one CTA per SM).
+struct CfrJob { SolverDev d; int n_dec; };
+__global__ void __launch_bounds__(512, 1) cfr_many_kernel(const CfrJob* __restrict__ jobs, int iters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_lvl[MAXL + 1], s_slvl[MAXL + 1];
+    const CfrJob job = jobs[blockIdx.x];
+    cfr_run(job.d, job.n_dec, iters, -1, 1.0, 1.0, nullptr, smem_raw, s_lvl, s_slvl);
+}
+
+__device__ void cfr_run(const SolverDev& d, int n_dec, int iters, int only_player, double r0, double r1, double* out_value,
+                        unsigned char* smem_raw, int* s_lvl, int* s_slvl) {
     const int tid = threadIdx.x, bd = blockDim.x;
     const int N = d.n_nodes, S = d.n_slots;
     CfrSmem m = cfr_carve(smem_raw, N, S, n_dec);
@@ -1408,6 +1425,29 @@ int ms_cfr_iterate(ms_solver* s, int32_t iters, void* stream) {
     if (iters < 0) return fail(MS_ERR_ARG, "iters < 0");
     if (iters == 0) return MS_OK;
     return launch_cfr(s, iters, -1, 1.0, 1.0, nullptr, (cudaStream_t)stream);
+}
+
+int ms_cfr_iterate_many(ms_solver* const* solvers, int32_t n_solvers, int32_t iters, void* stream) {
+    if (!solvers || n_solvers < 0 || iters < 0) return fail(MS_ERR_ARG, "ms_cfr_iterate_many: bad argument");
+    if (n_solvers == 0 || iters == 0) return MS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<CfrJob> jobs((size_t)n_solvers);
+    size_t smem = 0;
+    for (int i = 0; i < n_solvers; i++) {
+        int rc = check_dev(solvers[i]); if (rc) return rc;
+        jobs[i].d = solvers[i]->dev; jobs[i].n_dec = solvers[i]->n_dec;
+        smem = std::max(smem, cfr_smem_bytes(solvers[i]->n_nodes, solvers[i]->n_slots, solvers[i]->n_dec));
+    }
+    if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "CFR working set %zu B exceeds shared memory", smem);
+    CfrJob* d_jobs = nullptr;
+    MS_CUDA(cudaMallocAsync((void**)&d_jobs, sizeof(CfrJob) * (size_t)n_solvers, st));
+    MS_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CfrJob) * (size_t)n_solvers, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaStreamSynchronize(st));        // `jobs` is pageable host memory: finish the copy before it goes away
+    MS_CUDA(cudaFuncSetAttribute(cfr_many_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfr_many_kernel<<<n_solvers, 512, smem, st>>>(d_jobs, iters);
+    MS_LAUNCH_CHECK();
+    MS_CUDA(cudaFreeAsync(d_jobs, st));
+    return MS_OK;
 }
 
 int ms_cfr_traverse(ms_solver* s, int32_t player, double reach_p0, double reach_p1, double* h_value, void* stream) {

@@ -247,6 +247,15 @@ class Solver:
         return (v[0] + v[1]) / 2.0
 
 
+def cfr_iterate_many(solvers, iters):
+    """`iters` vanilla-CFR iterations on every solver (independent deals) in one launch, one CTA per deal."""
+    if not solvers:
+        return
+    arr = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+    with torch.cuda.device(solvers[0].device):
+        _lib.check(solvers[0].lib.ms_cfr_iterate_many(arr, len(solvers), int(iters), solvers[0]._stream()))
+
+
 def smoke_check(ora):
     """Used by __graft_entry__.smoke(): a few CFR iterations and an MCCFR batch against the oracle."""
     sv = Solver(seed=42, device="cuda:0")

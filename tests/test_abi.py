@@ -81,3 +81,26 @@ def test_pyspiel_compat_registry():
     from scopa_b200.envs import openspiel_mini_scopa  # noqa: F401  (registers the game; no GPU work at import)
     assert pyspiel.PlayerId.TERMINAL == -4
     assert "load_game" in dir(pyspiel)
+
+
+def test_argument_validation_needs_no_gpu():
+    """Bad arguments are refused before any CUDA call (MS_ERR_ARG = -2), with a message."""
+    import ctypes as C
+    lib = _lib.load()
+    buf = np.zeros(64, dtype=np.uint8)
+    p = buf.ctypes.data
+    assert lib.ms_step(None, None, None, None, 4, None) == -2 and b"ms_step" in lib.ms_last_error()
+    assert lib.ms_step(p, p, None, None, -1, None) == -2
+    assert lib.ms_legal_actions(p, p, 2, None, None, None, None, 1, None) == -2          # player must be -1, 0 or 1
+    assert lib.ms_rollout_random(None, None, 8, 0, 0, None, None, None, None) == -2
+    assert lib.ms_solver_create(None, 0, None) == -2
+    assert lib.ms_mlp_forward(None, 0, None, None, None, None, 5, None) == -2
+    assert lib.ms_mlp_forward(p, 7, p, p, None, None, 5, None) == -2                      # unknown precision
+    assert lib.ms_sdcfr_traverse(None, 0, 0, None, None, 0, 1, 0, 0, None, 0, None, None, None, None, None) == -2
+    assert lib.ms_team_step(None, None, None, None, 3, None) == -2
+    assert lib.ms_cfr_iterate_many(None, 3, 1, None) == -2
+    # empty batches succeed without touching the device
+    assert lib.ms_step(None, None, None, None, 0, None) == 0
+    assert lib.ms_rollout_random_host(None, 0, 0, 0, None, None) == 0
+    assert lib.ms_sdcfr_samples_per_traversal(0) == 41 and lib.ms_sdcfr_samples_per_traversal(1) == 41
+    assert lib.ms_sdcfr_workspace_bytes(1000) > 1000 * 129 * 16

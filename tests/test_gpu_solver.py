@@ -323,3 +323,16 @@ def test_external_sampling_converges_below_the_reference_plateau():
         sv.mccfr_apply()
     e = sv.exploitability(1)
     assert e < 0.12, e
+
+
+def test_cfr_many_deals_in_one_launch():
+    from scopa_b200.solver import cfr_iterate_many
+    seeds = [42, 1, 2, 3, 43, 999, 12345, 2**33 + 7]
+    many = [Solver(seed=s) for s in seeds]
+    cfr_iterate_many(many, 6)
+    for s, sv in zip(seeds, many):
+        one = Solver(seed=s)
+        one.cfr_iterate(6)
+        ra, sa, _ = sv.export()
+        rb, sb, _ = one.export()
+        assert np.array_equal(ra, rb) and np.array_equal(sa, sb), s
