@@ -241,6 +241,43 @@ int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, c
                       size_t workspace_bytes, float* d_feat, float* d_target, float* d_mask, float* d_root_value,
                       void* stream);
 
+/* ------------------------------------------------------------------- multi-deal MCCFR ------
+ * The reference solves one fixed deal (MCCFRTrainer(game), game.new_initial_state() = seed 42,
+ * src/algorithms/mc_cfr.py:88-92).  These entry points run the same _sample estimator (:37-86) on a game whose
+ * root is a uniform chance node over n_deals deals (MiniScopaEnv.reset(seed_d)), with ONE infoset table for all
+ * deals in device memory: open addressing on the 64-bit infoset key, 128 bytes per infoset, nodes created
+ * on first touch like mc_cfr.py:32-35.  Infosets are merged by information content (player, hand set, ordered
+ * table).  Table columns are indexed like the reference's arrays (by card id), compacted to the cards in hand:
+ * column = rank of the card id inside the hand mask.  No reference solver does this; with
+ * n_deals = 1 it is ms_mccfr_batch + ms_mccfr_apply on the same Philox streams.
+ *
+ * ms_md_create: d_seeds = n_deals device int64 seeds (dealt with ms_deal_from_seeds); capacity = 2^log2_capacity.
+ * ms_md_mccfr_batch: traversals first_trav .. first_trav+n_trav-1; traversal t plays deal
+ *   mulhi32(x0, n_deals), x = Philox4x32-10(key = philox_seed, ctr = (t lo, t hi, 0, "DEAL")), for player
+ *   0 / 1 / both (2), sampling like ms_mccfr_batch ("MCCF"+player stream).  Strategies are frozen for the launch;
+ *   deltas go to the table's delta columns with fp64 atomics and are folded in by ms_md_apply.
+ * ms_md_counters: [0] updates [1] node visits [2] env steps [3] infosets in the table [4] error flag; returns
+ *   MS_ERR_CAPACITY when an insert found the table full (synchronises the stream).
+ * ms_md_export: every occupied slot, in table order (unordered): d_keys [max_n], d_regret / d_strategy [max_n][4].
+ * ms_md_lookup: d_keys [n] -> d_regret / d_strategy [n][4] (zeros when absent), d_found [n]; outputs may be NULL. */
+typedef struct ms_mdsolver ms_mdsolver;
+int ms_md_create(const int64_t* d_seeds, int64_t n_deals, int32_t log2_capacity, void* stream, ms_mdsolver** out);
+void ms_md_destroy(ms_mdsolver* s);
+int ms_md_reset(ms_mdsolver* s, void* stream);
+int ms_md_info(const ms_mdsolver* s, int64_t* n_deals, int64_t* capacity, int64_t* table_bytes);
+int ms_md_mccfr_batch(ms_mdsolver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
+                      void* stream);
+int ms_md_apply(ms_mdsolver* s, void* stream);
+int ms_md_counters(ms_mdsolver* s, uint64_t h_out[5], int reset, void* stream);
+int ms_md_export(ms_mdsolver* s, uint64_t* d_keys, double* d_regret, double* d_strategy, int64_t max_n, int64_t* h_n,
+                 void* stream);
+int ms_md_lookup(ms_mdsolver* s, const uint64_t* d_keys, int64_t n, double* d_regret, double* d_strategy,
+                 uint8_t* d_found, void* stream);
+/* measurement hook: random-access ceilings of the table's pattern over a zeroed buffer of 2^log2_lines 128-byte
+ * lines, 148 x 768 threads: h_out[0] dependent 64-byte reads/s (one in flight per thread), [1] independent 64-byte
+ * reads/s (8 in flight per thread), [2] random lines/s receiving four fp64 RED.ADDs */
+int ms_debug_random_access_peaks(int32_t log2_lines, double h_out[3], void* stream);
+
 #ifdef __cplusplus
 }
 #endif

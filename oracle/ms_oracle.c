@@ -1091,3 +1091,179 @@ void ora_team_rollout_random(const int64_t* seeds, int64_t n, uint64_t philox_se
         for (int p = 0; p < 4; p++) { rewards[g * 4 + p] = (float)e.rewards[p]; if (scopas) scopas[g * 4 + p] = (uint8_t)e.scopas[p]; }
     }
 }
+
+/* ================================================================================ multi-deal MCCFR */
+/* No reference solver plays more than the seed-42 deal, so this section is "parity unpinned" beyond its
+ * D = 1 case: it is MCCFRTrainer._sample (src/algorithms/mc_cfr.py:37-86) run from a deal drawn uniformly from
+ * a list of seeds (Philox "DEAL" stream), with the info_sets dict (:28-35) keyed by the information itself
+ * -- "player|hand ids ascending|table ids in order" -- instead of the string whose hand order depends on the
+ * deal.  regret / strategy arrays are indexed like the reference's (by card id), compacted to the cards in
+ * hand.  Batch semantics as in ora_mccfr_batch: strategies frozen while a batch runs. */
+#define TAG_DEAL 0x4C414544u /* "DEAL" */
+
+typedef struct {
+    char key[64];
+    int player, nh, hand[4], nt, table[8];
+    double regret[4], strategy[4], dreg[4];
+    int64_t dcnt;
+} md_node;
+
+struct ora_mdtable {
+    md_node* nodes; int64_t n, cap;
+    int64_t* hidx; int64_t hcap;
+};
+
+ora_mdtable* ora_md_new(void) {
+    ora_mdtable* t = (ora_mdtable*)calloc(1, sizeof(*t));
+    t->cap = 1024; t->nodes = (md_node*)calloc((size_t)t->cap, sizeof(md_node));
+    t->hcap = 4096; t->hidx = (int64_t*)malloc(sizeof(int64_t) * (size_t)t->hcap);
+    for (int64_t i = 0; i < t->hcap; i++) t->hidx[i] = -1;
+    return t;
+}
+void ora_md_free(ora_mdtable* t) { if (t) { free(t->nodes); free(t->hidx); free(t); } }
+int64_t ora_md_size(const ora_mdtable* t) { return t->n; }
+const char* ora_md_key(const ora_mdtable* t, int64_t i) { return t->nodes[i].key; }
+int ora_md_nlegal(const ora_mdtable* t, int64_t i) { return t->nodes[i].nh; }
+double* ora_md_regret(ora_mdtable* t, int64_t i) { return t->nodes[i].regret; }
+double* ora_md_strategy(ora_mdtable* t, int64_t i) { return t->nodes[i].strategy; }
+/* the same information in the packed form the CUDA library uses for its keys (export format only) */
+uint64_t ora_md_packed_key(const ora_mdtable* t, int64_t i) {
+    const md_node* nd = &t->nodes[i];
+    uint64_t hand = 0, table = 0;
+    for (int k = 0; k < nd->nh; k++) hand |= 1ull << nd->hand[k];
+    for (int k = 0; k < nd->nt; k++) table |= (uint64_t)nd->table[k] << (4 * k);
+    return ((uint64_t)nd->player << 52) | (hand << 36) | ((uint64_t)nd->nt << 32) | table;
+}
+
+static void md_rehash(ora_mdtable* t) {
+    free(t->hidx);
+    t->hcap *= 2;
+    t->hidx = (int64_t*)malloc(sizeof(int64_t) * (size_t)t->hcap);
+    for (int64_t i = 0; i < t->hcap; i++) t->hidx[i] = -1;
+    for (int64_t i = 0; i < t->n; i++) {
+        uint32_t h = fnv1a(t->nodes[i].key) & (uint32_t)(t->hcap - 1);
+        while (t->hidx[h] >= 0) h = (h + 1) & (uint32_t)(t->hcap - 1);
+        t->hidx[h] = i;
+    }
+}
+
+static int cmp_int(const void* a, const void* b) { return *(const int*)a - *(const int*)b; }
+
+static int64_t md_get(ora_mdtable* t, const ora_state* s, int player) {
+    int hand[4]; int nh = s->env.nhand[player];
+    for (int k = 0; k < nh; k++) hand[k] = s->env.hand[player][k];
+    qsort(hand, (size_t)nh, sizeof(int), cmp_int);
+    char key[64]; int o = snprintf(key, sizeof key, "%d|", player);
+    for (int k = 0; k < nh; k++) o += snprintf(key + o, sizeof key - (size_t)o, k ? ",%d" : "%d", hand[k]);
+    o += snprintf(key + o, sizeof key - (size_t)o, "|");
+    for (int k = 0; k < s->env.ntable; k++) o += snprintf(key + o, sizeof key - (size_t)o, k ? ",%d" : "%d", s->env.table[k]);
+    uint32_t h = fnv1a(key) & (uint32_t)(t->hcap - 1);
+    while (t->hidx[h] >= 0) {
+        if (strcmp(t->nodes[t->hidx[h]].key, key) == 0) return t->hidx[h];
+        h = (h + 1) & (uint32_t)(t->hcap - 1);
+    }
+    if (t->n >= t->cap) {
+        t->cap *= 2;
+        t->nodes = (md_node*)realloc(t->nodes, (size_t)t->cap * sizeof(md_node));
+    }
+    md_node* nd = &t->nodes[t->n];
+    memset(nd, 0, sizeof(*nd));
+    strcpy(nd->key, key);
+    nd->player = player; nd->nh = nh; nd->nt = s->env.ntable;
+    for (int k = 0; k < nh; k++) nd->hand[k] = hand[k];
+    for (int k = 0; k < nd->nt; k++) nd->table[k] = s->env.table[k];
+    t->hidx[h] = t->n++;
+    if (t->n * 2 > t->hcap) md_rehash(t);
+    return t->n - 1;
+}
+
+typedef struct { ora_mdtable* t; ora_rng* rng; int tp; int64_t n_updates, n_visits; } md_ctx;
+
+/* column of a card inside a node: its rank among the node's (ascending) hand ids */
+static int md_column(const md_node* nd, int card) {
+    for (int k = 0; k < nd->nh; k++) if (nd->hand[k] == card) return k;
+    fprintf(stderr, "md_column: card not in hand\n"); abort();
+}
+
+static double md_sample(md_ctx* c, const ora_state* s, const double reach[2], const double samp[2]) {
+    uint32_t my_call = c->rng->call++;
+    c->n_visits++;
+    if (s->is_terminal) { double r[2]; ora_state_rewards(s, r); return r[c->tp]; }
+    int player = ora_state_current_player(s);
+    int legal[4]; int n = ora_state_legal(s, player, legal);      /* hand (= deal) order, like the reference */
+    /* infosets with a single legal action are not stored: sigma = [1.0], regret stays 0, and the reference's
+     * strategy_sum there is its visit count, which no consumer reads */
+    int64_t slot = n > 1 ? md_get(c->t, s, player) : -1;
+    int col[4] = {0, 0, 0, 0}; double by_col[4], sigma[4] = {1.0, 0.0, 0.0, 0.0};
+    if (slot >= 0) {
+        regret_matching(c->t->nodes[slot].regret, n, by_col);     /* :54, over the table's columns */
+        for (int i = 0; i < n; i++) { col[i] = md_column(&c->t->nodes[slot], legal[i]); sigma[i] = by_col[col[i]]; }
+    }
+    uint32_t saved = c->rng->call; c->rng->call = my_call;
+    int ai = rng_choice_p(c->rng, sigma, n);                      /* :55 */
+    c->rng->call = saved;
+    ora_state nx; ora_state_clone(s, &nx); ora_state_apply(&nx, legal[ai]);
+    double nreach[2] = {reach[0], reach[1]}, nsamp[2] = {samp[0], samp[1]};
+    if (player == c->tp) nsamp[player] *= sigma[ai];
+    else { nreach[player] *= sigma[ai]; nsamp[player] *= sigma[ai]; }
+    double util = md_sample(c, &nx, nreach, nsamp);               /* :67 */
+    if (player == c->tp) {
+        double cfv[4];
+        for (int i = 0; i < n; i++) {                             /* :71-78 */
+            ora_state tmp; ora_state_clone(s, &tmp); ora_state_apply(&tmp, legal[i]);
+            double tsamp[2] = {samp[0], samp[1]};
+            tsamp[player] *= sigma[i];
+            cfv[i] = md_sample(c, &tmp, reach, tsamp);
+        }
+        double v = 0.0;
+        for (int i = 0; i < n; i++) v += sigma[i] * cfv[i];
+        double opp = reach[1 - player];
+        double w = samp[player] > 0 ? opp / samp[player] : 0.0;
+        if (slot >= 0) {
+            md_node* nd = &c->t->nodes[slot];                     /* the array may have moved: re-index */
+            for (int i = 0; i < n; i++) nd->dreg[col[i]] += w * (cfv[i] - v);
+            nd->dcnt += 1;                                        /* strategy delta = reach[player] (= 1.0) * sigma */
+        }
+        c->n_updates++;
+    }
+    return util;
+}
+
+void ora_md_batch(ora_mdtable* t, const int64_t* seeds, int64_t n_deals, int player, uint64_t philox_seed,
+                  uint64_t first_trav, int64_t ntrav, int64_t* n_updates, int64_t* n_visits) {
+    ora_rng* rng = ora_rng_new(1, philox_seed);
+    md_ctx c = {t, rng, 0, 0, 0};
+    const uint32_t key[2] = {(uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)};
+    for (int64_t k = 0; k < ntrav; k++) {
+        uint64_t trav = first_trav + (uint64_t)k;
+        uint32_t ctr[4] = {(uint32_t)trav, (uint32_t)(trav >> 32), 0u, TAG_DEAL}, o[4];
+        philox4x32_10(ctr, key, o);
+        int64_t deal = (int64_t)(((uint64_t)o[0] * (uint64_t)n_deals) >> 32);
+        for (int tp = 0; tp < 2; tp++) {
+            if (player < 2 && tp != player) continue;
+            ora_state s; ora_state_init(&s, seeds[deal]);
+            c.tp = tp;
+            rng->tag = TAG_MCCF + (uint32_t)tp; rng->trav = trav; rng->call = 0;
+            double one[2] = {1.0, 1.0};
+            md_sample(&c, &s, one, one);
+        }
+    }
+    if (n_updates) *n_updates = c.n_updates;
+    if (n_visits) *n_visits = c.n_visits;
+    ora_rng_free(rng);
+}
+
+void ora_md_apply(ora_mdtable* t) {
+    for (int64_t i = 0; i < t->n; i++) {
+        md_node* nd = &t->nodes[i];
+        if (nd->dcnt == 0) continue;
+        double sigma[4];
+        regret_matching(nd->regret, nd->nh, sigma);
+        for (int a = 0; a < nd->nh; a++) {
+            nd->strategy[a] += (double)nd->dcnt * sigma[a];
+            nd->regret[a] += nd->dreg[a];
+            nd->dreg[a] = 0.0;
+        }
+        nd->dcnt = 0;
+    }
+}

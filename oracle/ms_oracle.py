@@ -109,6 +109,21 @@ def lib():
     L.ora_team_step.argtypes = [P(OraTeamEnv), ci]
     L.ora_team_rollout_random.argtypes = [vp, i64, u64, u64, vp, vp, vp, ci]
     L.ora_mccfr_batch_mode.argtypes = [vp, i64, ci, ci, u64, u64, i64, P(i64), P(i64)]
+    L.ora_md_new.restype = vp
+    L.ora_md_free.argtypes = [vp]
+    L.ora_md_size.argtypes = [vp]
+    L.ora_md_size.restype = i64
+    L.ora_md_key.argtypes = [vp, i64]
+    L.ora_md_key.restype = C.c_char_p
+    L.ora_md_packed_key.argtypes = [vp, i64]
+    L.ora_md_packed_key.restype = u64
+    L.ora_md_nlegal.argtypes = [vp, i64]
+    L.ora_md_regret.argtypes = [vp, i64]
+    L.ora_md_regret.restype = P(dbl)
+    L.ora_md_strategy.argtypes = [vp, i64]
+    L.ora_md_strategy.restype = P(dbl)
+    L.ora_md_batch.argtypes = [vp, vp, i64, ci, u64, u64, i64, P(i64), P(i64)]
+    L.ora_md_apply.argtypes = [vp]
     _lib = L
     return L
 
@@ -388,3 +403,43 @@ def team_rollout_random(seeds, philox_seed, nthreads=0, game_offset=0):
     lib().ora_team_rollout_random(seeds.ctypes.data, n, philox_seed, game_offset, actions.ctypes.data, rewards.ctypes.data,
                                   scopas.ctypes.data, nthreads)
     return actions, rewards, scopas
+
+
+class MultiDealTable:
+    """Multi-deal MCCFR table (chance root over `seeds`; parity unpinned beyond one deal)."""
+
+    def __init__(self, seeds):
+        self.seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+        self.t = lib().ora_md_new()
+
+    def __del__(self):
+        try:
+            lib().ora_md_free(self.t)
+        except Exception:
+            pass
+
+    def __len__(self):
+        return lib().ora_md_size(self.t)
+
+    def batch(self, player, philox_seed, first_trav, ntrav):
+        nu, nv = C.c_int64(0), C.c_int64(0)
+        lib().ora_md_batch(self.t, self.seeds.ctypes.data, len(self.seeds), player, philox_seed, first_trav, ntrav,
+                           C.byref(nu), C.byref(nv))
+        return nu.value, nv.value
+
+    def apply(self):
+        lib().ora_md_apply(self.t)
+
+    def arrays(self):
+        """-> string keys, packed keys (uint64), regret [n,4], strategy [n,4], nlegal [n] (first-touch order)"""
+        L, n = lib(), len(self)
+        keys, packed = [], np.zeros(n, dtype=np.uint64)
+        reg, strat, nl = np.zeros((n, 4)), np.zeros((n, 4)), np.zeros(n, dtype=np.int8)
+        for i in range(n):
+            keys.append(L.ora_md_key(self.t, i).decode())
+            packed[i] = L.ora_md_packed_key(self.t, i)
+            nl[i] = L.ora_md_nlegal(self.t, i)
+            r, s = L.ora_md_regret(self.t, i), L.ora_md_strategy(self.t, i)
+            for a in range(nl[i]):
+                reg[i, a], strat[i, a] = r[a], s[a]
+        return keys, packed, reg, strat, nl

@@ -69,6 +69,16 @@ _SIGS = {
     "ms_mlp_forward": ([vp, C.c_int, vp, vp, vp, vp, i64, vp], C.c_int),
     "ms_sdcfr_traverse": ([vp, C.c_uint32, C.c_int, vp, vp, C.c_int, i64, u64, u64, vp, C.c_size_t, vp, vp, vp, vp, vp],
                           C.c_int),
+    "ms_md_create": ([vp, i64, i32, vp, C.POINTER(vp)], C.c_int),
+    "ms_md_destroy": ([vp], None),
+    "ms_md_reset": ([vp, vp], C.c_int),
+    "ms_md_info": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], C.c_int),
+    "ms_md_mccfr_batch": ([vp, i32, i64, u64, u64, vp], C.c_int),
+    "ms_md_apply": ([vp, vp], C.c_int),
+    "ms_md_counters": ([vp, C.POINTER(u64), C.c_int, vp], C.c_int),
+    "ms_md_export": ([vp, vp, vp, vp, i64, C.POINTER(i64), vp], C.c_int),
+    "ms_md_lookup": ([vp, vp, i64, vp, vp, vp, vp], C.c_int),
+    "ms_debug_random_access_peaks": ([i32, C.POINTER(dbl), vp], C.c_int),
 }
 
 

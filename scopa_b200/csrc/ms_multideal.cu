@@ -1,0 +1,639 @@
+// scopa_b200/csrc/ms_multideal.cu -- the sampled-CFR estimator of the reference over MANY deals with one
+// HBM-resident open-addressing infoset table ("multi-deal / chance-sampled
+// root ... the regime where the HBM / atomic roofline is actually the bound").  sm_100a only.
+//
+// The reference solves one fixed deal (seed 42): MCCFRTrainer.iteration (src/algorithms/mc_cfr.py:88-92) calls
+// _sample (:37-86) on game.new_initial_state() for each player, and its info_sets dict (:28-35) holds 738 nodes
+// -- 53 KB, which ms_solver.cu keeps in shared memory.  Here the root is a chance node over D deals
+// (MiniScopaEnv.reset(seed_d), src/envs/mini_scopa_game.py:131-138): traversal t draws its deal from a Philox
+// stream, then runs the same _sample recursion for both players.  Infosets are merged by information content
+// (player, hand SET, ordered table = the 64-bit key of ms_state.cuh); the reference's string lists the hand in
+// deal order, which is presentation.  Regret / strategy arrays are indexed like the reference's (by card id),
+// compacted to the cards in hand: column = rank of the card id inside the hand mask.  Legal actions keep the
+// reference's order (deal order) for sampling, so with D = 1 this is the batch estimator of ms_solver.cu on
+// the same Philox streams (tests/test_gpu_multideal.py checks that, and the oracle follows it for D > 1).
+//
+// Table: capacity 2^k slots of 128 B, one cache line per infoset, four 32-byte sectors:
+//   [key u64 | visit count u32 | pad] [regret f64 x4] [regret delta f64 x4] [strategy sum f64 x4]
+// A node visit reads sectors 0-1 of one line (key probe + frozen regrets), an update issues fp64 RED.ADDs into
+// sector 2 and a u32 RED.ADD into sector 0; md_apply_kernel folds deltas in after the batch (same frozen-sigma
+// batch semantics as ms_mccfr_batch + ms_mccfr_apply).  Keys are claimed with atomicCAS (0 = empty: a key with
+// an empty hand is never a decision node), so the table is initialised by one memset.
+#include <cstring>
+
+#include "ms_common.cuh"
+#include "ms_state.cuh"
+
+namespace ms {
+
+struct __align__(128) MdSlot {
+    unsigned long long key;      // 0 = empty
+    unsigned int cnt;            // traverser visits in the running batch: strategy_sum += cnt * sigma
+    unsigned int pad0;
+    unsigned long long pad1, pad2;
+    double regret[4];
+    double delta[4];
+    double strategy[4];
+};
+static_assert(sizeof(MdSlot) == 128, "one cache line per infoset");
+
+struct MdDev {
+    MdSlot* slots;
+    unsigned long long mask;     // capacity - 1
+    int shift;                   // 64 - log2(capacity)
+    unsigned int max_probe;
+    const uint4* roots;          // [n_deals] dealt states
+    const uint32_t* hand_order;  // [n_deals]
+    unsigned int n_deals;
+    unsigned int* dirty;         // one bit per slot: touched by an update of the running batch (L2-resident: 16 MB at 2^27)
+    unsigned long long* counters;   // [0] updates [1] visits [2] env steps [3] infosets [4] overflow / invariant flag
+};
+
+constexpr uint32_t MS_TAG_DEAL = 0x4C414544u;   // "DEAL"
+constexpr int MD_THREADS = 768;
+constexpr int MD_FRAMES = 4;                    // traverser nodes on a path = cards in a hand
+constexpr int MD_SIG_FRAMES = 3;                // the 4th traverser node holds one card: sigma = [1]
+
+__device__ __forceinline__ unsigned long long md_hash(unsigned long long key, int shift) {
+    return (key * 0x9E3779B97F4A7C15ull) >> shift;
+}
+
+// Find the slot of `key`, claiming an empty one on first touch (mc_cfr.py:32-35 _get_node), and fetch its frozen
+// regrets (sectors 0-1 of the line, requested together with the key).  Linear probing, one line per round trip: a
+// key always sits in the first slot of its probe sequence that was free, the invariant lock-free insertion relies
+// on.  The DRAM-resident regime is bound by random line transactions (ms_debug_random_access_peaks: ~18 G lines/s
+// on a B200 whatever is asked of each line), so nothing is requested speculatively -- probing h and h+1 together was
+// measured and doubled the traversal time there -- and the table is sized for a low load factor instead, because a
+// warp waits for the slowest of its 32 lookups.
+// Returns -1 (and raises the overflow flag) when the probe limit is reached.
+__device__ __forceinline__ long long md_find_regrets(const MdDev& t, unsigned long long key, double* reg, uint32_t& n_ins) {
+    unsigned long long h = md_hash(key, t.shift);
+    for (unsigned int probe = 0; probe < t.max_probe; probe++) {
+        MdSlot* a = t.slots + h;
+        unsigned long long ka = __ldcg(&a->key);
+        const double2 a01 = __ldcg((const double2*)&a->regret[0]), a23 = __ldcg((const double2*)&a->regret[2]);
+        bool fresh = false;
+        if (ka == 0ull) { ka = atomicCAS(&a->key, 0ull, key); fresh = ka == 0ull; }
+        if (fresh || ka == key) {
+            n_ins += fresh ? 1u : 0u;
+            reg[0] = fresh ? 0.0 : a01.x; reg[1] = fresh ? 0.0 : a01.y;
+            reg[2] = fresh ? 0.0 : a23.x; reg[3] = fresh ? 0.0 : a23.y;
+            return (long long)h;
+        }
+        h = (h + 1ull) & t.mask;
+    }
+    t.counters[4] = 1ull;
+    reg[0] = reg[1] = reg[2] = reg[3] = 0.0;
+    return -1;
+}
+
+// regret matching over the columns of the table (ascending card id): mc_cfr.py:20-24
+__device__ __forceinline__ void md_regret_match(const double* reg, int n, double* out) {
+    double pos[4];
+    double norm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        pos[i] = (i < n && reg[i] > 0.0) ? reg[i] : 0.0;
+        if (i < n) norm = __dadd_rn(norm, pos[i]);
+    }
+    const double uni = __ddiv_rn(1.0, (double)n);
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (norm > 0.0 ? __ddiv_rn(pos[i], norm) : uni) : 0.0;
+}
+
+// column of legal action k: how many cards of the hand have a smaller id
+__device__ __forceinline__ int md_col(uint32_t hand, uint32_t list, int k) {
+    const uint32_t c = (list >> (4 * k)) & 0xFu;
+    return __popc(hand & ((1u << c) - 1u));
+}
+__device__ __forceinline__ double md_pick(const double* v, int col) {
+    return col == 0 ? v[0] : (col == 1 ? v[1] : (col == 2 ? v[2] : v[3]));
+}
+
+// The traversal's form of regret matching: sigma_k = pos[column of action k] * (1 / sum of pos), one division per
+// node instead of one per action (md_regret_match above, used by the apply step, divides; the two agree to an
+// ulp, far inside the 1e-9 the parity tests ask for).  Uniform when no regret is positive.
+__device__ __forceinline__ void md_sigma(const double* reg, int n, uint32_t hand, uint32_t list, double* sg) {
+    double pos[4];
+    double norm = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        pos[i] = (i < n && reg[i] > 0.0) ? reg[i] : 0.0;
+        norm = __dadd_rn(norm, pos[i]);
+    }
+    const bool any = norm > 0.0;
+    const double inv = __ddiv_rn(1.0, any ? norm : 1.0);
+    const double uni = n == 2 ? 0.5 : (n == 3 ? (1.0 / 3.0) : (n == 4 ? 0.25 : 1.0));
+#pragma unroll
+    for (int k = 0; k < 4; k++) sg[k] = (k < n) ? (any ? __dmul_rn(md_pick(pos, md_col(hand, list, k)), inv) : uni) : 0.0;
+}
+
+// np.random.choice(legal, p=sigma): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right') -- with the
+// normalisation moved to the other side of the comparison (cdf_i <= u * cdf_last)
+__device__ __forceinline__ int md_sample(const double* sg, int n, double u) {
+    double cdf[4];
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { if (i < n) acc = __dadd_rn(acc, sg[i]); cdf[i] = acc; }
+    const double thr = __dmul_rn(u, acc);
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (i < n && cdf[i] <= thr) idx++;
+    return idx < n ? idx : n - 1;
+}
+
+// Traversal frames: SoA in dynamic shared memory, [frame][thread], addressed from the compile-time CTA size so that
+// a frame access is one 32-bit offset computation (six 64-bit base pointers cost the kernel its register budget).
+extern __shared__ __align__(16) unsigned char md_smem[];
+template <int T>
+struct MdFrames {
+    int tid;
+    static constexpr int kRo = 16 * T * MD_FRAMES, kSp = kRo + 8 * T * MD_FRAMES, kSig = kSp + 8 * T * MD_FRAMES,
+                         kMeta = kSig + 32 * T * MD_SIG_FRAMES, kCfv = kMeta + 8 * T * MD_FRAMES,
+                         kBytes = kCfv + 4 * T * MD_FRAMES;
+    __device__ __forceinline__ uint4& st(int fi) const { return ((uint4*)md_smem)[fi * T + tid]; }
+    __device__ __forceinline__ double& ro(int fi) const { return ((double*)(md_smem + kRo))[fi * T + tid]; }
+    __device__ __forceinline__ double& sp(int fi) const { return ((double*)(md_smem + kSp))[fi * T + tid]; }
+    __device__ __forceinline__ double& sig(int fi, int k) const { return ((double*)(md_smem + kSig))[(fi * 4 + k) * T + tid]; }
+    __device__ __forceinline__ uint2& meta(int fi) const { return ((uint2*)(md_smem + kMeta))[fi * T + tid]; }
+    __device__ __forceinline__ uint32_t& cfv(int fi) const { return ((uint32_t*)(md_smem + kCfv))[fi * T + tid]; }
+};
+
+struct MdCounts { uint32_t upd, vis, step, ins; };   // per thread and launch: a thread runs far fewer than 2^32 visits
+
+// MCCFRTrainer._sample (mc_cfr.py:37-86) from the root of one deal, as an explicit depth-first search (the
+// recursion shape, the Philox addressing by call index and the forced-endgame shortcut are those of
+// mccfr_traverse in ms_solver.cu; what differs is where the table lives).
+template <int T>
+__device__ void md_traverse(const MdDev& t, const MsState root, const uint32_t hand_order, int tp,
+                            unsigned long long trav, uint2 pkey, const MdFrames<T>& f, MdCounts& c) {
+    MsState s = root;
+    const uint32_t dealt = dealt_set(root);
+    double ro = 1.0, sp = 1.0;
+    int fi = -1;
+    uint4 xblk = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t xblk_id = 0xFFFFFFFFu;
+    bool pend = false, returning = false;
+    uint32_t pend_a = 0u, call = 0u;
+    int ret_x2 = 0;
+    const uint32_t tag = MS_TAG_MCCF + (uint32_t)tp;
+    while (true) {
+        if (!returning) {
+            if (pend) { step(s, pend_a, table_set_from_dealt(s, dealt)); c.step++; pend = false; }
+            const uint32_t my_call = call++;
+            c.vis++;
+            if (st_terminal(s)) {
+                const int r = reward0_x2(s);
+                ret_x2 = (tp == 0) ? r : -r;
+                returning = true;
+                continue;
+            }
+            const int p = st_cur(s);
+            uint32_t list;
+            const uint32_t nl = legal_list(s, hand_order, p, list);
+            if (nl == 1u) {
+                // Forced move.  Infosets with one card in hand are NOT stored: their strategy is the constant
+                // [1.0], their regret stays 0 and the reference's strategy_sum there is its visit count, which
+                // no consumer reads (the policy is [1.0] either way).  They are about half of all node visits.
+                const uint32_t a1 = list & 0xFu;
+                if (p != tp) { pend_a = a1; pend = true; continue; }
+                // traverser's last card: if the rest of the game is forced too, both recursive calls of the
+                // reference walk the same line -- played once, accounted twice (see ms_solver.cu)
+                MsState t2 = s;
+                int below = 0;
+                bool forced = false;
+                uint32_t act = a1;
+#pragma unroll 1
+                for (int k = 0; k < 2; k++) {
+                    step(t2, act, table_set_from_dealt(t2, dealt));
+                    below++;
+                    if (st_terminal(t2)) { forced = true; break; }
+                    if (k == 1 || __popc(st_hand(t2, p ^ 1)) != 1) break;
+                    uint32_t l2;
+                    legal_list(t2, hand_order, p ^ 1, l2);
+                    act = l2 & 0xFu;
+                }
+                if (forced) {
+                    const int r = reward0_x2(t2);
+                    ret_x2 = (tp == 0) ? r : -r;
+                    c.upd++;                  // regret delta = w * 0 exactly; strategy_sum += 1.0 (not stored)
+                    c.vis += 2 * below; call += 2u * (uint32_t)below; c.step += below;
+                    returning = true;
+                    continue;
+                }
+                // not forced (cannot happen from an 8-ply root, kept for generality): general path below
+                fi++;
+                if (fi >= MD_FRAMES) { t.counters[4] = 2ull; return; }
+                f.st(fi) = s; f.ro(fi) = ro; f.sp(fi) = sp;
+                f.meta(fi) = make_uint2(0xFFFFFFFFu, list | (1u << 27));
+                f.cfv(fi) = 0u;
+                pend_a = a1; pend = true;
+                continue;
+            }
+            double reg[4], sg[4];
+            const long long slot = md_find_regrets(t, infoset_key(s, p), reg, c.ins);
+            md_sigma(reg, (int)nl, st_hand(s, p), list, sg);
+            if ((my_call >> 1) != xblk_id) {
+                xblk_id = my_call >> 1;
+                xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
+            }
+            const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
+            const int ai = md_sample(sg, (int)nl, u);
+            const uint32_t a = (list >> (4 * ai)) & 0xFu;
+            const double sga = ai == 0 ? sg[0] : (ai == 1 ? sg[1] : (ai == 2 ? sg[2] : sg[3]));
+            if (p != tp) {                // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
+                ro = __dmul_rn(ro, sga);
+                pend_a = a; pend = true;
+                continue;
+            }
+            fi++;
+            if (fi >= MD_SIG_FRAMES) { t.counters[4] = 2ull; return; }
+            f.st(fi) = s; f.ro(fi) = ro; f.sp(fi) = sp;
+            f.meta(fi) = make_uint2((uint32_t)slot, list | (nl << 27));
+            f.cfv(fi) = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) f.sig(fi, k) = sg[k];
+            sp = __dmul_rn(sp, sga);
+            pend_a = a; pend = true;
+            continue;
+        }
+        // ---- a child returned ret_x2 to the top frame
+        if (fi < 0) break;
+        uint2 meta = f.meta(fi);
+        const int nl = (int)((meta.y >> 27) & 0x7u);
+        int cur = (int)((meta.y >> 24) & 0x7u);
+        uint32_t cfvb = f.cfv(fi);
+        if (cur == 0) meta.y = (meta.y & 0xFF00FFFFu) | (((uint32_t)ret_x2 & 0xFFu) << 16);   // util of the sampled action
+        else cfvb |= ((uint32_t)ret_x2 & 0xFFu) << (8 * (cur - 1));
+        cur++;
+        double sg[4];
+        if (nl > 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) sg[k] = f.sig(fi, k);
+        } else { sg[0] = 1.0; sg[1] = sg[2] = sg[3] = 0.0; }
+        if (cur <= nl) {                  // evaluate action i = cur-1 with a fresh sampled continuation (:71-78)
+            const int i = cur - 1;
+            meta.y = (meta.y & 0xF8FFFFFFu) | ((uint32_t)cur << 24);
+            f.meta(fi) = meta; f.cfv(fi) = cfvb;
+            s = f.st(fi);
+            ro = f.ro(fi);
+            sp = __dmul_rn(f.sp(fi), i == 0 ? sg[0] : (i == 1 ? sg[1] : (i == 2 ? sg[2] : sg[3])));
+            pend_a = (meta.y >> (4 * i)) & 0xFu; pend = true;
+            returning = false;
+            continue;
+        }
+        // ---- all actions evaluated: regret / strategy deltas (:79-84)
+        const long long slot = (long long)(int)meta.x;
+        if (nl > 1 && slot >= 0) {        // |A| = 1: cfv - v == 0 exactly
+            double cfv[4];
+            double v = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                cfv[i] = 0.5 * (double)(int)(int8_t)((cfvb >> (8 * i)) & 0xFFu);
+                if (i < nl) v = __dadd_rn(v, __dmul_rn(sg[i], cfv[i]));
+            }
+            const double fro = f.ro(fi), fsp = f.sp(fi);
+            const double w = fsp > 0.0 ? __ddiv_rn(fro, fsp) : 0.0;
+            const uint32_t hand = st_hand(f.st(fi), tp);
+            const uint32_t list = meta.y & 0xFFFFu;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < nl) atomicAdd(&t.slots[slot].delta[md_col(hand, list, i)], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+        }
+        if (slot >= 0) {
+            atomicAdd(&t.slots[slot].cnt, 1u);
+            atomicOr(&t.dirty[slot >> 5], 1u << (slot & 31));
+        }
+        c.upd++;
+        ret_x2 = (int)(int8_t)((meta.y >> 16) & 0xFFu);
+        fi--;
+        returning = true;
+    }
+}
+
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) md_mccfr_kernel(MdDev t, int player, long long n_trav, uint2 pkey,
+                                                                 unsigned long long first_trav) {
+    constexpr int T = THREADS;
+    const int tid = threadIdx.x;
+    const MdFrames<T> f{tid};
+    MdCounts c{0u, 0u, 0u, 0u};
+    const long long gstride = (long long)gridDim.x * T;
+    for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += gstride) {
+        const unsigned long long trav = first_trav + (unsigned long long)k;
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), 0u, MS_TAG_DEAL), pkey);
+        const uint32_t deal = __umulhi(x.x, t.n_deals);
+        const MsState root = t.roots[deal];
+        const uint32_t ho = t.hand_order[deal];
+        for (int tp = 0; tp < 2; tp++) {
+            if (player < 2 && tp != player) continue;
+            md_traverse<T>(t, root, ho, tp, trav, pkey, f, c);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        c.upd += __shfl_down_sync(0xffffffffu, c.upd, off);
+        c.vis += __shfl_down_sync(0xffffffffu, c.vis, off);
+        c.step += __shfl_down_sync(0xffffffffu, c.step, off);
+        c.ins += __shfl_down_sync(0xffffffffu, c.ins, off);
+    }
+    if ((tid & 31) == 0) {
+        atomicAdd(&t.counters[0], c.upd); atomicAdd(&t.counters[1], c.vis);
+        atomicAdd(&t.counters[2], c.step);
+        if (c.ins) atomicAdd(&t.counters[3], c.ins);
+    }
+}
+
+// after a batch: strategy_sum += cnt * sigma(frozen regrets); regret += delta; delta = 0; cnt = 0.
+// Walks the dirty bitmap (one thread per 32 slots), so the cost follows the slots a batch updated, not the capacity.
+__global__ void __launch_bounds__(256) md_apply_kernel(MdDev t) {
+    const unsigned long long words = (t.mask + 1ull) >> 5;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long wi = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; wi < words; wi += stride) {
+        unsigned int w = t.dirty[wi];
+        if (w == 0u) continue;
+        t.dirty[wi] = 0u;
+        while (w) {
+            const int bit = __ffs((int)w) - 1;
+            w &= w - 1u;
+            MdSlot* sl = t.slots + (wi << 5) + bit;
+            const uint4 head = *(const uint4*)sl;                 // key (x, y) | cnt (z)
+            const unsigned int cnt = head.z;
+            const int n = __popc((head.y >> 4) & 0xFFFFu);        // hand mask = key bits 36-51
+            double reg[4], sg[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) reg[i] = sl->regret[i];
+            md_regret_match(reg, n, sg);
+            const double cn = (double)cnt;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (i < n) {
+                    sl->strategy[i] = __dadd_rn(sl->strategy[i], __dmul_rn(cn, sg[i]));
+                    const double dl = sl->delta[i];
+                    if (dl != 0.0) { sl->regret[i] = __dadd_rn(reg[i], dl); sl->delta[i] = 0.0; }
+                }
+            }
+            sl->cnt = 0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) md_export_kernel(MdDev t, unsigned long long* keys, double* regret,
+                                                        double* strategy, long long max_n, unsigned long long* n_out) {
+    const unsigned long long cap = t.mask + 1ull;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long h = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; h < cap; h += stride) {
+        const MdSlot* sl = t.slots + h;
+        const unsigned long long key = sl->key;
+        if (key == 0ull) continue;
+        const unsigned long long i = atomicAdd(n_out, 1ull);
+        if ((long long)i >= max_n) continue;
+        keys[i] = key;
+#pragma unroll
+        for (int a = 0; a < 4; a++) { regret[4 * i + a] = sl->regret[a]; strategy[4 * i + a] = sl->strategy[a]; }
+    }
+}
+
+__global__ void __launch_bounds__(256) md_lookup_kernel(MdDev t, const unsigned long long* __restrict__ keys, long long n,
+                                                        double* regret, double* strategy, uint8_t* found) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = keys[i];
+        unsigned long long h = md_hash(key, t.shift);
+        long long slot = -1;
+        for (unsigned int probe = 0; probe < t.max_probe; probe++) {
+            const unsigned long long k = t.slots[h].key;
+            if (k == key) { slot = (long long)h; break; }
+            if (k == 0ull) break;
+            h = (h + 1ull) & t.mask;
+        }
+        if (key == 0ull) slot = -1;
+        if (found) found[i] = slot >= 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            if (regret) regret[4 * i + a] = slot >= 0 ? t.slots[slot].regret[a] : 0.0;
+            if (strategy) strategy[4 * i + a] = slot >= 0 ? t.slots[slot].strategy[a] : 0.0;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Random-access ceilings of the table's access pattern, measured on the box (there is no published figure):
+// 148 x 768 threads touch pseudo-random 128-byte lines of a 2^k-line buffer.
+//   [0] dependent reads: the next address depends on the loaded data (one access in flight per thread -- the
+//       shape of a depth-first traversal), 64 bytes (key sector + regret sector) per access;
+//   [1] independent reads, 8 in flight per thread, 64 bytes per access (the DRAM / L2 random-access ceiling);
+//   [2] fp64 RED.ADD x4 into one sector of a random line (the regret-delta update).
+__global__ void __launch_bounds__(768, 1) rnd_dependent_kernel(const MdSlot* tab, unsigned long long mask, int iters,
+                                                               unsigned long long* sink) {
+    unsigned long long x = (blockIdx.x * 768ull + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345ull;
+    unsigned long long acc = 0;
+    for (int i = 0; i < iters; i++) {
+        const MdSlot* sl = tab + ((x >> 20) & mask);
+        const unsigned long long k = __ldcg(&sl->key);
+        const double2 r = __ldcg((const double2*)&sl->regret[0]);
+        acc += k + (unsigned long long)__double_as_longlong(r.x);
+        x = (x + k + 1ull) * 0xD1342543DE82EF95ull + 1442695040888963407ull;   // k is 0 in a zeroed buffer, but unknown to the compiler
+    }
+    if (acc == 0x123456789ull) *sink = acc;
+}
+__global__ void __launch_bounds__(768, 1) rnd_independent_kernel(const MdSlot* tab, unsigned long long mask, int iters,
+                                                                 unsigned long long* sink) {
+    unsigned long long x = (blockIdx.x * 768ull + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345ull;
+    unsigned long long acc = 0;
+    for (int i = 0; i < iters; i += 8) {
+        unsigned long long k[8]; double2 r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            x = x * 0xD1342543DE82EF95ull + 1442695040888963407ull;
+            const MdSlot* sl = tab + ((x >> 20) & mask);
+            k[j] = __ldcg(&sl->key);
+            r[j] = __ldcg((const double2*)&sl->regret[0]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += k[j] + (unsigned long long)__double_as_longlong(r[j].x);
+    }
+    if (acc == 0x123456789ull) *sink = acc;
+}
+__global__ void __launch_bounds__(768, 1) rnd_red_kernel(MdSlot* tab, unsigned long long mask, int iters) {
+    unsigned long long x = (blockIdx.x * 768ull + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345ull;
+    for (int i = 0; i < iters; i++) {
+        x = x * 0xD1342543DE82EF95ull + 1442695040888963407ull;
+        MdSlot* sl = tab + ((x >> 20) & mask);
+#pragma unroll
+        for (int a = 0; a < 4; a++) atomicAdd(&sl->delta[a], 1.0);
+    }
+}
+
+}  // namespace ms
+
+using namespace ms;
+
+struct ms_mdsolver {
+    MdDev dev;
+    int log2cap;
+    int64_t n_deals;
+    uint4* d_roots; uint32_t* d_hand_order;
+    unsigned long long* d_counters;    // 5 counters + 1 export cursor
+};
+
+extern "C" {
+
+int ms_md_create(const int64_t* d_seeds, int64_t n_deals, int32_t log2_capacity, void* stream, ms_mdsolver** out) {
+    if (!out) return fail(MS_ERR_ARG, "ms_md_create: out is NULL");
+    *out = nullptr;
+    if (!d_seeds || n_deals < 1 || n_deals > 0x7FFFFFFFll) return fail(MS_ERR_ARG, "ms_md_create: bad deal list");
+    if (log2_capacity < 10 || log2_capacity > 30) return fail(MS_ERR_ARG, "ms_md_create: log2_capacity must be in [10, 30]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(MS_ERR_CUDA, "ms_md_create: no CUDA device");
+    ms_mdsolver* s = new ms_mdsolver();
+    std::memset(s, 0, sizeof(*s));
+    s->log2cap = log2_capacity; s->n_deals = n_deals;
+    const size_t cap = (size_t)1 << log2_capacity;
+    cudaError_t e = cudaMalloc(&s->dev.slots, cap * sizeof(MdSlot));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_roots, (size_t)n_deals * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_hand_order, (size_t)n_deals * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&s->dev.dirty, (cap >> 5) * sizeof(unsigned int));
+    if (e != cudaSuccess) {
+        cudaFree(s->dev.slots); cudaFree(s->dev.dirty); cudaFree(s->d_roots); cudaFree(s->d_hand_order); cudaFree(s->d_counters);
+        delete s;
+        return fail(e == cudaErrorMemoryAllocation ? MS_ERR_CAPACITY : MS_ERR_CUDA, "ms_md_create: cudaMalloc failed: %s",
+                    cudaGetErrorString(e));
+    }
+    s->dev.mask = (unsigned long long)cap - 1ull;
+    s->dev.shift = 64 - log2_capacity;
+    s->dev.max_probe = cap < 8192 ? (unsigned int)cap : 8192u;
+    s->dev.roots = s->d_roots; s->dev.hand_order = s->d_hand_order;
+    s->dev.n_deals = (unsigned int)n_deals;
+    s->dev.counters = s->d_counters;
+    int rc = ms_deal_from_seeds(d_seeds, n_deals, (ms_state*)s->d_roots, s->d_hand_order, stream);
+    if (rc == MS_OK) rc = ms_md_reset(s, stream);
+    if (rc != MS_OK) { ms_md_destroy(s); return rc; }
+    *out = s;
+    return MS_OK;
+}
+
+void ms_md_destroy(ms_mdsolver* s) {
+    if (!s) return;
+    cudaFree(s->dev.slots); cudaFree(s->dev.dirty); cudaFree(s->d_roots); cudaFree(s->d_hand_order); cudaFree(s->d_counters);
+    delete s;
+}
+
+int ms_md_reset(ms_mdsolver* s, void* stream) {
+    if (!s) return fail(MS_ERR_ARG, "ms_md_reset: NULL handle");
+    MS_CUDA(cudaMemsetAsync(s->dev.slots, 0, ((size_t)1 << s->log2cap) * sizeof(MdSlot), (cudaStream_t)stream));
+    MS_CUDA(cudaMemsetAsync(s->dev.dirty, 0, (((size_t)1 << s->log2cap) >> 5) * sizeof(unsigned int), (cudaStream_t)stream));
+    MS_CUDA(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
+    return MS_OK;
+}
+
+int ms_md_mccfr_batch(ms_mdsolver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
+                      void* stream) {
+    if (!s) return fail(MS_ERR_ARG, "ms_md_mccfr_batch: NULL handle");
+    if (player < 0 || player > 2 || n_trav < 0 || n_trav > 10000000000ll)   // per-warp counters are 32-bit
+        return fail(MS_ERR_ARG, "ms_md_mccfr_batch: bad argument");
+    if (n_trav == 0) return MS_OK;
+    // 768 threads per CTA, one CTA per SM: measured 6.35 ms per 341 k traversal pairs at 65 536 deals against 6.9 ms
+    // with 640 or 512 threads (more registers, no spills, fewer chains in flight)
+    const int smem = MdFrames<MD_THREADS>::kBytes;
+    MS_CUDA(cudaFuncSetAttribute(md_mccfr_kernel<MD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    md_mccfr_kernel<MD_THREADS><<<grid_for(n_trav, MD_THREADS, 1), MD_THREADS, smem, (cudaStream_t)stream>>>(
+        s->dev, player, (long long)n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
+        (unsigned long long)first_trav);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_md_apply(ms_mdsolver* s, void* stream) {
+    if (!s) return fail(MS_ERR_ARG, "ms_md_apply: NULL handle");
+    const int64_t cap = (int64_t)1 << s->log2cap;
+    md_apply_kernel<<<grid_for(cap >> 5, 256, 8), 256, 0, (cudaStream_t)stream>>>(s->dev);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_md_counters(ms_mdsolver* s, uint64_t h_out[5], int reset, void* stream) {
+    if (!s || !h_out) return fail(MS_ERR_ARG, "ms_md_counters: bad argument");
+    MS_CUDA(cudaMemcpyAsync(h_out, s->d_counters, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (reset) {   // the traffic counters; the infoset count and the overflow flag describe the table and stay
+        MS_CUDA(cudaMemsetAsync(s->d_counters, 0, 3 * sizeof(unsigned long long), (cudaStream_t)stream));
+    }
+    if (h_out[4] == 1) return fail(MS_ERR_CAPACITY, "multi-deal infoset table is full (capacity 2^%d, %llu infosets)",
+                                   s->log2cap, (unsigned long long)h_out[3]);
+    if (h_out[4] == 2) return fail(MS_ERR_STATE, "multi-deal traversal left the 8-ply game shape");
+    return MS_OK;
+}
+
+int ms_md_export(ms_mdsolver* s, uint64_t* d_keys, double* d_regret, double* d_strategy, int64_t max_n, int64_t* h_n,
+                 void* stream) {
+    if (!s || !d_keys || !d_regret || !d_strategy || !h_n || max_n < 0) return fail(MS_ERR_ARG, "ms_md_export: bad argument");
+    MS_CUDA(cudaMemsetAsync(s->d_counters + 5, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    const int64_t cap = (int64_t)1 << s->log2cap;
+    md_export_kernel<<<grid_for(cap, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        s->dev, (unsigned long long*)d_keys, d_regret, d_strategy, (long long)max_n, s->d_counters + 5);
+    MS_LAUNCH_CHECK();
+    unsigned long long n = 0;
+    MS_CUDA(cudaMemcpyAsync(&n, s->d_counters + 5, sizeof(n), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *h_n = (int64_t)n;
+    if ((int64_t)n > max_n) return fail(MS_ERR_CAPACITY, "ms_md_export: %llu infosets, buffers hold %lld", n, (long long)max_n);
+    return MS_OK;
+}
+
+int ms_md_lookup(ms_mdsolver* s, const uint64_t* d_keys, int64_t n, double* d_regret, double* d_strategy,
+                 uint8_t* d_found, void* stream) {
+    if (!s || (!d_keys && n > 0) || n < 0) return fail(MS_ERR_ARG, "ms_md_lookup: bad argument");
+    if (n == 0) return MS_OK;
+    md_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        s->dev, (const unsigned long long*)d_keys, (long long)n, d_regret, d_strategy, d_found);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_md_info(const ms_mdsolver* s, int64_t* n_deals, int64_t* capacity, int64_t* table_bytes) {
+    if (!s) return fail(MS_ERR_ARG, "ms_md_info: NULL handle");
+    if (n_deals) *n_deals = s->n_deals;
+    if (capacity) *capacity = (int64_t)1 << s->log2cap;
+    if (table_bytes) *table_bytes = ((int64_t)1 << s->log2cap) * (int64_t)sizeof(MdSlot);
+    return MS_OK;
+}
+
+int ms_debug_random_access_peaks(int32_t log2_lines, double h_out[3], void* stream) {
+    if (!h_out || log2_lines < 10 || log2_lines > 30) return fail(MS_ERR_ARG, "ms_debug_random_access_peaks: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t lines = (size_t)1 << log2_lines;
+    MdSlot* d = nullptr;
+    unsigned long long* sink = nullptr;
+    MS_CUDA(cudaMalloc(&d, lines * sizeof(MdSlot)));
+    MS_CUDA(cudaMalloc(&sink, 8));
+    MS_CUDA(cudaMemsetAsync(d, 0, lines * sizeof(MdSlot), st));
+    cudaEvent_t e0, e1;
+    MS_CUDA(cudaEventCreate(&e0)); MS_CUDA(cudaEventCreate(&e1));
+    const int iters = 512, grid = kNumSMs, block = 768;
+    const double ops = (double)iters * grid * block;
+    for (int which = 0; which < 3; which++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {          // first repetition is the warm-up
+            MS_CUDA(cudaEventRecord(e0, st));
+            if (which == 0) rnd_dependent_kernel<<<grid, block, 0, st>>>(d, lines - 1, iters, sink);
+            else if (which == 1) rnd_independent_kernel<<<grid, block, 0, st>>>(d, lines - 1, iters, sink);
+            else rnd_red_kernel<<<grid, block, 0, st>>>(d, lines - 1, iters);
+            MS_LAUNCH_CHECK();
+            MS_CUDA(cudaEventRecord(e1, st));
+            MS_CUDA(cudaEventSynchronize(e1));
+            float t = 0.f;
+            MS_CUDA(cudaEventElapsedTime(&t, e0, e1));
+            if (rep > 0 && t < best) best = t;
+        }
+        h_out[which] = ops / (best * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    MS_CUDA(cudaFree(d)); MS_CUDA(cudaFree(sink));
+    return MS_OK;
+}
+
+}  // extern "C"

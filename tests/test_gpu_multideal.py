@@ -1,0 +1,191 @@
+"""GPU tests of the multi-deal MCCFR table, through the C ABI.
+
+No reference solver plays more than one deal, so the anchors are:
+  * one deal (seed 42): the HBM hash-table path must reproduce the one-deal batch solver (itself checked against the
+    reference-pinned oracle in test_gpu_solver.py) on the same Philox streams, 1e-9;
+  * several deals: the CPU oracle's restatement of the same specification (oracle/ms_oracle.c "multi-deal MCCFR"),
+    same infoset set, tables to 1e-9, same update / visit counts;
+  * learning: exploitability of the average policy in the chance-root game (restated best response, parity unpinned)
+    falls with training;
+  * a full table is reported as MS_ERR_CAPACITY, never a hang.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ms_exploit
+from oracle import ms_oracle as ora
+from scopa_b200 import _lib, multideal
+from scopa_b200.solver import Solver
+
+pytestmark = pytest.mark.gpu
+
+
+def test_one_deal_reproduces_batch_solver():
+    sv = Solver(seed=42)
+    md = multideal.MultiDealSolver([42], log2_capacity=12)
+    n = 4096
+    for b in range(3):
+        for p in (0, 1):
+            sv.mccfr_batch(p, n, philox_seed=5, first_trav=b * n)
+            sv.mccfr_apply()
+            md.mccfr_batch(n, philox_seed=5, first_trav=b * n, player=p)
+            md.apply()
+    reg, strat, touched = sv.export()
+    st = sv.static_table()
+    keys, mreg, mstrat = md.export()
+    stored = touched.astype(bool) & (st["nlegal"] > 1)          # one-card infosets are not materialised (sigma = [1])
+    assert md.counters()["infosets"] == len(keys) == int(stored.sum())
+    pos = {int(k): i for i, k in enumerate(keys)}
+    c1, c2 = sv.counters(), md.counters()
+    assert (c1["updates"], c1["visits"]) == (c2["updates"], c2["visits"])
+    worst = 0.0
+    for s in range(sv.n_slots):
+        if not stored[s]:
+            assert int(st["keys"][s]) not in pos
+            continue
+        i = pos[int(st["keys"][s])]
+        hand = sorted(int(c) for c in st["legal"][s][:st["nlegal"][s]])
+        for a in range(int(st["nlegal"][s])):
+            col = hand.index(int(st["legal"][s][a]))
+            worst = max(worst, abs(mreg[i, col] - reg[s, a]) / max(1.0, abs(reg[s, a])),
+                        abs(mstrat[i, col] - strat[s, a]) / max(1.0, abs(strat[s, a])))
+    assert worst < 1e-9, worst
+
+
+@pytest.mark.parametrize("player", [2, 0])
+def test_many_deals_match_oracle(player):
+    seeds = [42, 1, 43, 7, 2 ** 33 + 7, 12345, 99, 1000]
+    md = multideal.MultiDealSolver(seeds, log2_capacity=15)
+    om = ora.MultiDealTable(seeds)
+    n, nu, nv = 1500, 0, 0
+    for b in range(3):
+        md.mccfr_batch(n, philox_seed=9, first_trav=b * n, player=player)
+        md.apply()
+        u, v = om.batch(player, 9, b * n, n)
+        nu, nv = nu + u, nv + v
+        om.apply()
+    c = md.counters()
+    assert (c["updates"], c["visits"]) == (nu, nv)
+    keys, reg, strat = md.export()
+    _, okeys, oreg, ostrat, _ = om.arrays()
+    order = np.argsort(okeys, kind="stable")
+    assert np.array_equal(keys, okeys[order]), "infoset sets differ"
+    assert len(keys) > 2000 and c["infosets"] == len(keys)
+    np.testing.assert_allclose(reg, oreg[order], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(strat, ostrat[order], rtol=1e-9, atol=1e-9)
+    # lookups: present keys return the same rows, an absent key is reported
+    q = np.concatenate([keys[:100], np.array([(1 << 52) | (0xF << 36)], dtype=np.uint64)])
+    lreg, lstrat, found = md.lookup(q)
+    assert found.cpu().numpy().tolist() == [1] * 100 + [0]
+    assert np.array_equal(lreg.cpu().numpy()[:100], reg[:100]) and np.array_equal(lstrat.cpu().numpy()[:100], strat[:100])
+
+
+class _ChanceRootState:
+    """pyspiel.State protocol over the chance-root game (for the restated best response): the root draws a deal,
+    below it the oracle's one-deal states; infoset strings list the hand by ascending card id."""
+
+    def __init__(self, seeds, inner=None, deal=None):
+        self.seeds, self.inner, self.deal = seeds, inner, deal
+
+    def is_chance_node(self):
+        return self.inner is None
+
+    def chance_outcomes(self):
+        return [(i, 1.0 / len(self.seeds)) for i in range(len(self.seeds))]
+
+    def is_terminal(self):
+        return self.inner is not None and self.inner.is_terminal()
+
+    def current_player(self):
+        return -1 if self.inner is None else self.inner.current_player()
+
+    def legal_actions(self, player=None):
+        return list(range(len(self.seeds))) if self.inner is None else self.inner.legal_actions()
+
+    def child(self, a):
+        if self.inner is None:
+            return _ChanceRootState(self.seeds, ora.State(int(self.seeds[a])), a)
+        return _ChanceRootState(self.seeds, self.inner.child(a), self.deal)
+
+    def returns(self):
+        return self.inner.rewards()
+
+    def key(self, player):
+        e = self.inner.s.env
+        hand = sum(1 << e.hand[player][i] for i in range(e.nhand[player]))
+        table = [e.table[i] for i in range(e.ntable)]
+        return (player << 52) | (hand << 36) | (len(table) << 32) | sum(c << (4 * i) for i, c in enumerate(table))
+
+    def information_state_string(self, player=None):
+        player = self.inner.current_player() if player is None else player
+        return multideal.key_string(self.key(player))
+
+    def history_str(self):
+        return f"{self.deal}:{self.inner.history_str()}" if self.inner is not None else "root"
+
+
+class _Game:
+    def __init__(self, seeds):
+        self.seeds = seeds
+
+    def new_initial_state(self):
+        return _ChanceRootState(self.seeds)
+
+    def num_players(self):
+        return 2
+
+
+class _TablePolicy:
+    def __init__(self, md):
+        self.md, self.cache = md, {}
+
+    def action_probabilities(self, state):
+        p = state.current_player()
+        key = state.key(p)
+        if key not in self.cache:
+            self.cache[key] = self.md.average_policy([key])[0] if self.md is not None else None
+        row = self.cache[key]
+        hand = sorted(state.legal_actions())
+        if row is None:
+            return {a: 1.0 / len(hand) for a in hand}
+        return {a: float(row[hand.index(a)]) for a in state.legal_actions()}
+
+
+def test_exploitability_falls_in_the_chance_root_game():
+    seeds = [42, 1, 43]
+    game = _Game(seeds)
+    uniform = ms_exploit.exploitability(game, _TablePolicy(None))
+    md = multideal.MultiDealSolver(seeds)
+    n, done, curve = 2048, 0, []
+    for target in (1, 4, 16):
+        while done < target:
+            md.mccfr_batch(n, philox_seed=3, first_trav=done * n)
+            md.apply()
+            done += 1
+        curve.append(ms_exploit.exploitability(game, _TablePolicy(md)))
+    # the first batch plays the uniform strategy, so its average policy is uniform; then it falls
+    assert abs(curve[0] - uniform) < 1e-12 and curve[2] < curve[1] < 0.5 * uniform, (uniform, curve)
+    # the CPU oracle's tables for the same batches (ora.MultiDealTable, same Philox seed) give these values
+    np.testing.assert_allclose([uniform, curve[1], curve[2]], [1.8680555555555554, 0.7795025146405892, 0.6164106587760572],
+                               atol=1e-6)
+
+
+def test_full_table_is_an_error_not_a_hang():
+    md = multideal.MultiDealSolver(list(range(1, 9)), log2_capacity=10)     # 8 deals need ~2500 slots, 1024 given
+    md.mccfr_batch(4096, philox_seed=1)
+    with pytest.raises(_lib.MsError, match="full"):
+        md.counters()
+    torch.cuda.synchronize()
+
+
+def test_argument_validation():
+    with pytest.raises(ValueError):
+        multideal.MultiDealSolver([])
+    with pytest.raises(_lib.MsError):
+        multideal.MultiDealSolver([1], log2_capacity=40)
+    md = multideal.MultiDealSolver([1], log2_capacity=12)
+    with pytest.raises(_lib.MsError):
+        md.mccfr_batch(10, player=3)
+    md.mccfr_batch(0)
+    assert md.counters()["updates"] == 0 and md.table_bytes == 4096 * 128
