@@ -40,7 +40,8 @@ BYTES_PER_UPDATE_FP64 = 203.7      # 172 updates x 136 B + 291 opponent lookups 
 BYTES_PER_ENV_STEP = 34.0          # 16 B state load + 1 B action + 16 B state store (+ rewards on the last ply)
 FALLBACK_HBM_GBS = 6650.0
 # DRAM bytes per launch of the dominant kernels, from the committed ncu --set full captures (profiles/README.md)
-NCU_DRAM_BYTES_PER_LAUNCH = {"mccfr_batch_kernel": 117504, "rollout_kernel": 20052736}
+NCU_DRAM_BYTES_PER_LAUNCH = {"mccfr_batch_kernel": 117504, "rollout_kernel": 20052736,
+                             "md_mccfr_kernel": 1111869952}   # 65 536 deals, 340 992 traversal pairs (md_r01f_raw.csv)
 
 
 def load_peaks():
@@ -420,6 +421,64 @@ def run_ours(args):
                     "note": "microbenchmark: 148 CTAs x 768 threads, pseudo-random addresses over a 738x4 table; shared-memory "
                             "fp64 atomicAdd compiles to an ATOMS.CAST.SPIN.64 compare-and-swap loop, global fp64 to REDG.E.ADD.F64"}
 
+    # ------------------------------------------------------------------ multi-deal MCCFR
+    # The regime SURVEY 8(d) names as the one where the memory system is the bound: one infoset table for 65 536
+    # deals (5.1 M stored infosets, 0.66 GB of 128-byte lines, far beyond the 126 MB L2) in HBM.
+    md_obj = None
+    if rank == 0 and args.md_deals > 0:
+        import ctypes
+        from scopa_b200 import multideal
+        lg = args.md_log2_capacity
+        md = multideal.MultiDealSolver(np.arange(1, args.md_deals + 1), log2_capacity=lg, device=dev)
+        nb = args.md_trav
+        for i in range(12):                                  # fill the table: inserts are rare afterwards
+            md.mccfr_batch(nb, philox_seed=args.seed, first_trav=i * nb)
+            md.apply()
+        md.counters(reset=True)
+        mev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+        l0 = _lib.launch_count()
+        mev[0].record()
+        for i in range(K):
+            md.mccfr_batch(nb, philox_seed=args.seed, first_trav=(12 + i) * nb)
+            mev[2 * i + 1].record()
+            md.apply()
+            mev[2 * i + 2].record()
+        torch.cuda.synchronize()
+        md_launches = _lib.launch_count() - l0
+        mc = md.counters()
+        t_trav = sum(mev[2 * i].elapsed_time(mev[2 * i + 1]) for i in range(K)) / K
+        t_app = sum(mev[2 * i + 1].elapsed_time(mev[2 * i + 2]) for i in range(K)) / K
+        # ceiling: dependent 64-byte reads of random 128-byte lines over a buffer the size of the STORED infosets
+        lines_lg = max(10, int(np.ceil(np.log2(max(mc["infosets"], 1)))))
+        rp = (ctypes.c_double * 3)()
+        table_bytes = md.table_bytes
+        del md
+        torch.cuda.empty_cache()
+        _lib.check(_lib.load().ms_debug_random_access_peaks(lines_lg, rp, _lib.stream_ptr()))
+        # per traversal pair (data-independent recursion shape of the estimator, 4+4-card deals): 163 lookups of
+        # stored infosets (player 0 traversal: 26 own + 85 opponent nodes with >1 card; player 1: 26 + 26) and 52
+        # update groups (regret-delta REDs + visit count on the line just read)
+        touches = (163.0 + 52.0) * nb / (t_trav * 1e-3)
+        md_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
+                  "value": mc["updates"] / K / ((t_trav + t_app) * 1e-3),
+                  "stored_infoset_updates_per_sec": 52.0 * nb / ((t_trav + t_app) * 1e-3),
+                  "node_visits_per_sec": mc["visits"] / K / ((t_trav + t_app) * 1e-3),
+                  "ms_traverse": t_trav, "ms_apply": t_app, "gpu_launches": int(md_launches),
+                  "infosets": int(mc["infosets"]), "load_factor": mc["infosets"] / float(1 << lg), "table_bytes": int(table_bytes),
+                  "roofline": {"bound": "hbm", "kind": "random 128-byte line transactions", "achieved": touches / 1e9,
+                               "peak": rp[0] / 1e9, "unit": "G lines/s", "frac": touches / rp[0],
+                               "peak_source": f"ms_debug_random_access_peaks over 2^{lines_lg} lines (the stored infosets' footprint), "
+                                              "148 x 768 threads, dependent 64-byte reads, measured in this run",
+                               "independent_reads_peak": rp[1] / 1e9, "red_x4_lines_peak": rp[2] / 1e9,
+                               "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get("md_mccfr_kernel"), "kernel": "md_mccfr_kernel",
+                               "note": "line touches = 163 lookups + 52 update groups per traversal pair; hot (shallow) "
+                                       "infosets hit in L2 (ncu: 75 % of sectors), so the DRAM-resident ceiling is not the "
+                                       "binding one yet: the kernel is latency-bound (profiles/README.md section 6)"},
+                  "config": {"workload": f"MCCFR (reference estimator) over {args.md_deals} deals (seeds 1..), chance-sampled root, "
+                                         f"{nb} traversal pairs per step, one fp64 infoset table of 2^{lg} x 128 B in HBM",
+                             "note": "updates are reference-equivalent (172 per traversal pair); infosets with one card in hand "
+                                     "(120 of the 172) are not stored -- their strategy is the constant [1.0]"}}
+
     # ------------------------------------------------------------------ SDCFR traversal (config 4)
     from scopa_b200 import sdcfr as sd
     T = args.sd_trav
@@ -517,6 +576,7 @@ def run_ours(args):
         "cfr": cfr_obj,
         "mccfr_external_sampling": es_obj,
         "atomics": atom_obj,
+        "mccfr_multi_deal": md_obj,
         "collective": collective,
     }
     if primary is mccfr_obj:
@@ -617,6 +677,9 @@ def main():
     ap.add_argument("--games", type=int, default=1_000_000, help="concurrent games per GPU")
     ap.add_argument("--sd-trav", type=int, default=16384, help="SDCFR traversals per player per GPU per step")
     ap.add_argument("--step-states", type=int, default=16_000_000, help="states in the step-granular API measurement")
+    ap.add_argument("--md-deals", type=int, default=65536, help="deals in the multi-deal MCCFR section (0 = skip)")
+    ap.add_argument("--md-log2-capacity", type=int, default=26, help="multi-deal table slots (128 B each)")
+    ap.add_argument("--md-trav", type=int, default=340992, help="traversal pairs per multi-deal step")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],

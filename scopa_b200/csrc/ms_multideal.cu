@@ -151,13 +151,17 @@ struct MdFrames {
     int tid;
     static constexpr int kRo = 16 * T * MD_FRAMES, kSp = kRo + 8 * T * MD_FRAMES, kSig = kSp + 8 * T * MD_FRAMES,
                          kMeta = kSig + 32 * T * MD_SIG_FRAMES, kCfv = kMeta + 8 * T * MD_FRAMES,
-                         kBytes = kCfv + 4 * T * MD_FRAMES;
+                         kHo = kCfv + 4 * T * MD_FRAMES, kDealt = kHo + 4 * T, kBytes = kDealt + 4 * T;
     __device__ __forceinline__ uint4& st(int fi) const { return ((uint4*)md_smem)[fi * T + tid]; }
     __device__ __forceinline__ double& ro(int fi) const { return ((double*)(md_smem + kRo))[fi * T + tid]; }
     __device__ __forceinline__ double& sp(int fi) const { return ((double*)(md_smem + kSp))[fi * T + tid]; }
     __device__ __forceinline__ double& sig(int fi, int k) const { return ((double*)(md_smem + kSig))[(fi * 4 + k) * T + tid]; }
     __device__ __forceinline__ uint2& meta(int fi) const { return ((uint2*)(md_smem + kMeta))[fi * T + tid]; }
     __device__ __forceinline__ uint32_t& cfv(int fi) const { return ((uint32_t*)(md_smem + kCfv))[fi * T + tid]; }
+    // per-traversal constants read at every node: kept here rather than in registers the kernel does not have
+    // (a spilled copy costs an L2 round trip: the 28 KB of L1 left beside the frames does not hold the spill slots)
+    __device__ __forceinline__ uint32_t& hand_order() const { return ((uint32_t*)(md_smem + kHo))[tid]; }
+    __device__ __forceinline__ uint32_t& dealt() const { return ((uint32_t*)(md_smem + kDealt))[tid]; }
 };
 
 struct MdCounts { uint32_t upd, vis, step, ins; };   // per thread and launch: a thread runs far fewer than 2^32 visits
@@ -166,10 +170,9 @@ struct MdCounts { uint32_t upd, vis, step, ins; };   // per thread and launch: a
 // recursion shape, the Philox addressing by call index and the forced-endgame shortcut are those of
 // mccfr_traverse in ms_solver.cu; what differs is where the table lives).
 template <int T>
-__device__ void md_traverse(const MdDev& t, const MsState root, const uint32_t hand_order, int tp,
+__device__ void md_traverse(const MdDev& t, const MsState root, int tp,
                             unsigned long long trav, uint2 pkey, const MdFrames<T>& f, MdCounts& c) {
     MsState s = root;
-    const uint32_t dealt = dealt_set(root);
     double ro = 1.0, sp = 1.0;
     int fi = -1;
     uint4 xblk = make_uint4(0u, 0u, 0u, 0u);
@@ -180,7 +183,7 @@ __device__ void md_traverse(const MdDev& t, const MsState root, const uint32_t h
     const uint32_t tag = MS_TAG_MCCF + (uint32_t)tp;
     while (true) {
         if (!returning) {
-            if (pend) { step(s, pend_a, table_set_from_dealt(s, dealt)); c.step++; pend = false; }
+            if (pend) { step(s, pend_a, table_set_from_dealt(s, f.dealt())); c.step++; pend = false; }
             const uint32_t my_call = call++;
             c.vis++;
             if (st_terminal(s)) {
@@ -191,7 +194,7 @@ __device__ void md_traverse(const MdDev& t, const MsState root, const uint32_t h
             }
             const int p = st_cur(s);
             uint32_t list;
-            const uint32_t nl = legal_list(s, hand_order, p, list);
+            const uint32_t nl = legal_list(s, f.hand_order(), p, list);
             if (nl == 1u) {
                 // Forced move.  Infosets with one card in hand are NOT stored: their strategy is the constant
                 // [1.0], their regret stays 0 and the reference's strategy_sum there is its visit count, which
@@ -206,12 +209,12 @@ __device__ void md_traverse(const MdDev& t, const MsState root, const uint32_t h
                 uint32_t act = a1;
 #pragma unroll 1
                 for (int k = 0; k < 2; k++) {
-                    step(t2, act, table_set_from_dealt(t2, dealt));
+                    step(t2, act, table_set_from_dealt(t2, f.dealt()));
                     below++;
                     if (st_terminal(t2)) { forced = true; break; }
                     if (k == 1 || __popc(st_hand(t2, p ^ 1)) != 1) break;
                     uint32_t l2;
-                    legal_list(t2, hand_order, p ^ 1, l2);
+                    legal_list(t2, f.hand_order(), p ^ 1, l2);
                     act = l2 & 0xFu;
                 }
                 if (forced) {
@@ -326,10 +329,11 @@ __global__ void __launch_bounds__(THREADS, 1) md_mccfr_kernel(MdDev t, int playe
         const uint4 x = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), 0u, MS_TAG_DEAL), pkey);
         const uint32_t deal = __umulhi(x.x, t.n_deals);
         const MsState root = t.roots[deal];
-        const uint32_t ho = t.hand_order[deal];
+        f.hand_order() = t.hand_order[deal];
+        f.dealt() = dealt_set(root);
         for (int tp = 0; tp < 2; tp++) {
             if (player < 2 && tp != player) continue;
-            md_traverse<T>(t, root, ho, tp, trav, pkey, f, c);
+            md_traverse<T>(t, root, tp, trav, pkey, f, c);
         }
     }
     for (int off = 16; off > 0; off >>= 1) {
