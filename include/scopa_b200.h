@@ -215,6 +215,46 @@ int ms_team_rollout_random(const ms_team_state* d_states, const uint64_t* d_hand
 int ms_team_deal_from_seeds_host(const int64_t* h_seeds, int64_t n, ms_team_state* h_states, uint64_t* h_hand_order);
 int ms_team_step_host(ms_team_state* h_states, const uint8_t* h_actions, float* h_rewards, uint8_t* h_done, int64_t n);
 
+/* ------------------------------------------------------------------------ 40-card Scopa ------
+ * FullScopaEnv, two players (src/envs/full_scopa_game.py:21-342).  Card id = action id =
+ * suit_idx * 10 + rank - 1 (suits denari, coppe, spade, bastoni; :262-266).  32-byte packed state (bit layout in
+ * scopa_b200/csrc/ms_full.cu) + the shuffled deck beside it (four 64-bit words, ten 6-bit card ids each: the
+ * table is deck[0..3], round r deals deck[4 + 6 r + 3 p + i] to player p).
+ *   ms_full_deal_from_seeds: FullScopaEnv.reset(seed) (:243-250, :68-86; seed 0 means 42) = FullDeck(seed) shuffle with
+ *     CPython's MT19937 (:32-35), four cards to the table, three to each player.
+ *   ms_full_deck_from_seeds: FullDeck(seed).cards only (no seed substitution); slow_path != 0 forces the kernel's
+ *     rarely-taken full-state path (test hook).
+ *   ms_full_step: FullScopaEnv.step(action) (:252-296 incl. play_card :130-158, find_capture_combinations :101-128,
+ *     deal_new_round :92-99, evaluate_game :174-226, the 200-step safety limit).  A card the mover does not hold is a
+ *     silent pass; ids above 39 (IndexError in the reference) are passes too.  d_rewards [n][2] f32, d_done [n] u8.
+ *   ms_full_legal_actions: FullScopaState.legal_actions(player) (src/envs/openspiel_full_scopa.py:22-41), player -1 =
+ *     current: d_ordered [n][3] u8 (hand order, 0xFF padded), d_count [n] u8.
+ *   ms_full_rollout_random: n random-policy games played to the end (36 plies) in one launch; at each ply the mover
+ *     plays legal[mulhi32(x, n_legal)], x = Philox4x32-10(key = philox_seed, ctr = (game id lo, hi, ply / 4, "FULL")),
+ *     word ply % 4.  d_actions [n][36] u8, d_rewards [n][2] f32, d_final [n] (each may be NULL).
+ *   ms_full_table_overflow: 1 if any game so far held more than 16 cards on the table (the packed state's limit;
+ *     200 k random games peak at 11) -- such a game's state is invalid. */
+typedef struct { uint32_t w[8]; } ms_full_state;
+typedef struct { uint64_t w[4]; } ms_full_deck;
+int ms_full_deal_from_seeds(const int64_t* d_seeds, int64_t n, ms_full_state* d_states, ms_full_deck* d_decks, void* stream);
+int ms_full_deck_from_seeds(const int64_t* d_seeds, int64_t n, ms_full_deck* d_decks, int slow_path, void* stream);
+int ms_full_step(ms_full_state* d_states, const ms_full_deck* d_decks, const uint8_t* d_actions, float* d_rewards,
+                 uint8_t* d_done, int64_t n, void* stream);
+int ms_full_legal_actions(const ms_full_state* d_states, const ms_full_deck* d_decks, int player, uint8_t* d_ordered,
+                          uint8_t* d_count, int64_t n, void* stream);
+int ms_full_rollout_random(const ms_full_state* d_states, const ms_full_deck* d_decks, int64_t n, uint64_t philox_seed,
+                           uint64_t game_offset, uint8_t* d_actions, float* d_rewards, ms_full_state* d_final, void* stream);
+int ms_full_table_overflow(int* h_flag, void* stream);
+int ms_full_deal_from_seeds_host(const int64_t* h_seeds, int64_t n, ms_full_state* h_states, ms_full_deck* h_decks);
+int ms_full_step_host(ms_full_state* h_states, const ms_full_deck* h_decks, const uint8_t* h_actions, float* h_rewards,
+                      uint8_t* h_done, int64_t n);
+int ms_full_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_seed, uint64_t game_offset,
+                                uint8_t* h_actions, float* h_rewards);
+/* FullScopaGame.evaluate_game() on its own (:174-226): last-capturer sweep + scoring of what each state holds now;
+ * marks the states terminal.  h_rewards [n][2] f32 and h_detail [n][8] i32 (cards, denari, primiera sum, score of
+ * player 0 / 1, interleaved: c0 c1 d0 d1 p0 p1 s0 s1) may be NULL. */
+int ms_full_evaluate_host(ms_full_state* h_states, float* h_rewards, int32_t* h_detail, int64_t n);
+
 /* -------------------------------------------------------------------------------- SDCFR ------
  * Advantage network = FlexibleNet mlp 34 -> 128 -> 64 -> 16 with ReLU (src/algorithms/deep_cfr/nets.py:151-235,
  * :296-331; deep_cfr.py:24-52).  A net is passed as ONE fp32 blob of 13776 floats in nn.Linear order:

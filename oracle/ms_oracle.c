@@ -1267,3 +1267,163 @@ void ora_md_apply(ora_mdtable* t) {
         nd->dcnt = 0;
     }
 }
+
+/* ================================================================================ 40-card Scopa */
+/* FullDeck / FullScopaGame / FullScopaEnv (src/envs/full_scopa_game.py:21-342), two players.
+ * Card id = suit_idx * 10 + (rank - 1), suits = denari, coppe, spade, bastoni (:23-24, :262-266). */
+#define TAG_FULL 0x4C4C5546u /* "FULL" */
+
+static int full_rank(int c) { return c % 10 + 1; }
+
+void ora_full_deck(int64_t seed, int out40[40]) {           /* FullDeck.__init__ (:32-35) */
+    mt_t m; py_random_seed(&m, seed);
+    for (int i = 0; i < 40; i++) out40[i] = i;
+    for (int i = 39; i >= 1; i--) {                          /* random.shuffle */
+        int j = (int)py_randbelow(&m, (uint32_t)i + 1u);
+        int t = out40[i]; out40[i] = out40[j]; out40[j] = t;
+    }
+}
+
+static void full_deal_hands(ora_full_env* e) {               /* 3 cards to each player, player 0 first */
+    for (int p = 0; p < 2; p++) {
+        e->nhand[p] = 3;
+        for (int i = 0; i < 3; i++) e->hand[p][i] = e->deck[e->deck_pos++];
+    }
+}
+
+void ora_full_reset(ora_full_env* e, int64_t seed, int has_seed) {   /* FullScopaEnv.reset (:243-250) + game.reset (:68-86) */
+    int64_t sd = (has_seed && seed != 0) ? seed : e->seed;   /* `seed or self.seed` */
+    ora_full_deck(sd, e->deck);
+    e->deck_pos = 0;
+    e->ntable = 4;
+    for (int i = 0; i < 4; i++) e->table[i] = e->deck[e->deck_pos++];
+    for (int p = 0; p < 2; p++) { e->ncaps[p] = 0; e->scopas[p] = 0; }
+    full_deal_hands(e);
+    e->last_capture = -1; e->round_number = 0;
+    e->agent = 0; e->step_count = 0;
+    e->rewards[0] = e->rewards[1] = 0.0; e->term[0] = e->term[1] = 0;
+}
+
+void ora_full_init(ora_full_env* e, int64_t seed) {          /* FullScopaEnv.__init__ (:231-241) */
+    memset(e, 0, sizeof(*e));
+    e->seed = seed; e->max_steps = 200;
+    ora_full_reset(e, seed, 1);
+}
+
+/* find_capture_combinations (:101-128), first combination only (play_card takes combinations[0], :137-141):
+ * the first table card of equal rank, else the subset with the smallest position mask whose ranks sum to the
+ * target.  Returns the number of captured table positions written to pos_out (ascending). */
+int ora_full_capture(const int* table, int ntable, int card, int* pos_out) {
+    int target = full_rank(card);
+    for (int i = 0; i < ntable; i++)
+        if (full_rank(table[i]) == target) { pos_out[0] = i; return 1; }
+    for (uint32_t mask = 1; mask < (1u << ntable); mask++) {
+        int sum = 0;
+        for (int i = 0; i < ntable; i++) if (mask & (1u << i)) sum += full_rank(table[i]);
+        if (sum == target) {
+            int n = 0;
+            for (int i = 0; i < ntable; i++) if (mask & (1u << i)) pos_out[n++] = i;
+            return n;
+        }
+    }
+    return 0;
+}
+
+static int primiera_value(int rank) {                        /* :27-30 */
+    static const int v[11] = {0, 16, 12, 13, 14, 15, 18, 21, 10, 10, 10};
+    return v[rank];
+}
+
+static int full_primiera(const int* caps, int n) {           /* calculate_primiera_score (:160-172) */
+    int best[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; i++) {
+        int s = caps[i] / 10, v = primiera_value(full_rank(caps[i]));
+        if (v > best[s]) best[s] = v;
+    }
+    for (int s = 0; s < 4; s++) if (!best[s]) return 0;
+    return best[0] + best[1] + best[2] + best[3];
+}
+
+static void full_evaluate(ora_full_env* e, double out[2]) {  /* evaluate_game (:174-226) */
+    int scores[2] = {0, 0};
+    if (e->ntable > 0 && e->last_capture >= 0)               /* sweep: the table is NOT cleared (:187-188) */
+        for (int i = 0; i < e->ntable; i++) e->caps[e->last_capture][e->ncaps[e->last_capture]++] = e->table[i];
+    if (e->ncaps[0] != e->ncaps[1]) scores[e->ncaps[0] > e->ncaps[1] ? 0 : 1] += 1;          /* carte */
+    int den[2] = {0, 0}, sette = -1, prim[2];
+    for (int p = 0; p < 2; p++) {
+        for (int i = 0; i < e->ncaps[p]; i++) {
+            if (e->caps[p][i] < 10) den[p]++;
+            if (e->caps[p][i] == 6 && sette < 0) sette = p;
+        }
+        prim[p] = full_primiera(e->caps[p], e->ncaps[p]);
+    }
+    if (den[0] != den[1]) scores[den[0] > den[1] ? 0 : 1] += 1;                              /* denari */
+    if (sette >= 0) scores[sette] += 1;                                                      /* sette bello */
+    if ((prim[0] > 0 || prim[1] > 0) && prim[0] != prim[1]) scores[prim[0] > prim[1] ? 0 : 1] += 1;
+    scores[0] += e->scopas[0]; scores[1] += e->scopas[1];
+    int total = scores[0] + scores[1];
+    if (total == 0) { out[0] = out[1] = 0.0; return; }
+    double mean = total / 2.0;
+    out[0] = scores[0] - mean; out[1] = scores[1] - mean;
+}
+
+void ora_full_step(ora_full_env* e, int action) {            /* FullScopaEnv.step (:252-296) */
+    if (e->term[e->agent]) return;                           /* dead step */
+    int pl = e->agent, hp = -1;
+    for (int i = 0; i < e->nhand[pl]; i++) if (e->hand[pl][i] == action) { hp = i; break; }
+    if (hp >= 0 && action >= 0 && action < 40) {             /* play_card (:130-158) */
+        int pos[20];
+        int n = ora_full_capture(e->table, e->ntable, action, pos);
+        if (n > 0) {
+            for (int i = 0; i < n; i++) e->caps[pl][e->ncaps[pl]++] = e->table[pos[i]];
+            e->caps[pl][e->ncaps[pl]++] = action;
+            for (int i = n - 1; i >= 0; i--) {
+                for (int k = pos[i]; k + 1 < e->ntable; k++) e->table[k] = e->table[k + 1];
+                e->ntable--;
+            }
+            e->last_capture = pl;
+            if (e->ntable == 0) e->scopas[pl]++;
+        } else {
+            e->table[e->ntable++] = action;
+        }
+        for (int k = hp; k + 1 < e->nhand[pl]; k++) e->hand[pl][k] = e->hand[pl][k + 1];
+        e->nhand[pl]--;
+    }
+    e->step_count++;
+    if (e->nhand[0] == 0 && e->nhand[1] == 0) {
+        if (40 - e->deck_pos >= 6) { full_deal_hands(e); e->round_number++; }
+        else { full_evaluate(e, e->rewards); e->term[0] = e->term[1] = 1; }
+    }
+    if (e->step_count >= e->max_steps) { full_evaluate(e, e->rewards); e->term[0] = e->term[1] = 1; }
+    e->agent = 1 - e->agent;
+}
+
+/* random-policy games on the "FULL" Philox stream: ctr = (game id lo, hi, ply / 4, tag), word ply % 4,
+ * action = hand[mulhi32(x, |hand|)]; 36 plies.  actions [n][36] u8, rewards [n][2] f32, scopas [n][2] u8,
+ * ncaps [n][2] u8, maxtable [n] u8 (longest table seen). */
+void ora_full_rollout_random(const int64_t* seeds, int64_t n, uint64_t philox_seed, uint64_t game_offset,
+                             uint8_t* actions, float* rewards, uint8_t* scopas, uint8_t* ncaps, uint8_t* maxtable,
+                             int nthreads) {
+    const uint32_t key[2] = {(uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)};
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+    for (int64_t g = 0; g < n; g++) {
+        ora_full_env e; ora_full_init(&e, 42);
+        ora_full_reset(&e, seeds[g], 1);
+        int mt = e.ntable;
+        for (int ply = 0; ply < 36; ply++) {
+            uint64_t gid = game_offset + (uint64_t)g;
+            uint32_t ctr[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(ply >> 2), TAG_FULL}, o[4];
+            philox4x32_10(ctr, key, o);
+            int pl = e.agent, nl = e.nhand[pl];
+            int a = nl > 0 ? e.hand[pl][(int)(((uint64_t)o[ply & 3] * (uint64_t)nl) >> 32)] : 0;
+            actions[g * 36 + ply] = (uint8_t)a;
+            ora_full_step(&e, a);
+            if (e.ntable > mt) mt = e.ntable;
+        }
+        rewards[g * 2] = (float)e.rewards[0]; rewards[g * 2 + 1] = (float)e.rewards[1];
+        if (scopas) { scopas[g * 2] = (uint8_t)e.scopas[0]; scopas[g * 2 + 1] = (uint8_t)e.scopas[1]; }
+        if (ncaps) { ncaps[g * 2] = (uint8_t)e.ncaps[0]; ncaps[g * 2 + 1] = (uint8_t)e.ncaps[1]; }
+        if (maxtable) maxtable[g] = (uint8_t)mt;
+    }
+}

@@ -39,6 +39,14 @@ class OraTeamEnv(C.Structure):
                 ("rewards", C.c_double * 4), ("term", C.c_int * 4)]
 
 
+class OraFullEnv(C.Structure):
+    _fields_ = [("hand", (C.c_int * 3) * 2), ("nhand", C.c_int * 2), ("caps", (C.c_int * 96) * 2), ("ncaps", C.c_int * 2),
+                ("scopas", C.c_int * 2), ("table", C.c_int * 40), ("ntable", C.c_int), ("deck", C.c_int * 40),
+                ("deck_pos", C.c_int), ("last_capture", C.c_int), ("round_number", C.c_int), ("agent", C.c_int),
+                ("step_count", C.c_int), ("max_steps", C.c_int), ("seed", C.c_int64), ("rewards", C.c_double * 2),
+                ("term", C.c_int * 2)]
+
+
 class OraState(C.Structure):
     _fields_ = [("env", OraEnv), ("is_terminal", C.c_int), ("history", C.c_int * 40), ("nhist", C.c_int)]
 
@@ -109,6 +117,13 @@ def lib():
     L.ora_team_step.argtypes = [P(OraTeamEnv), ci]
     L.ora_team_rollout_random.argtypes = [vp, i64, u64, u64, vp, vp, vp, ci]
     L.ora_mccfr_batch_mode.argtypes = [vp, i64, ci, ci, u64, u64, i64, P(i64), P(i64)]
+    L.ora_full_deck.argtypes = [i64, P(ci)]
+    L.ora_full_init.argtypes = [P(OraFullEnv), i64]
+    L.ora_full_reset.argtypes = [P(OraFullEnv), i64, ci]
+    L.ora_full_step.argtypes = [P(OraFullEnv), ci]
+    L.ora_full_capture.argtypes = [P(ci), ci, ci, P(ci)]
+    L.ora_full_capture.restype = ci
+    L.ora_full_rollout_random.argtypes = [vp, i64, u64, u64, vp, vp, vp, vp, vp, ci]
     L.ora_md_new.restype = vp
     L.ora_md_free.argtypes = [vp]
     L.ora_md_size.argtypes = [vp]
@@ -443,3 +458,43 @@ class MultiDealTable:
             for a in range(nl[i]):
                 reg[i, a], strat[i, a] = r[a], s[a]
         return keys, packed, reg, strat, nl
+
+
+# --------------------------------------------------------------------------- 40-card Scopa
+def full_deck(seed):
+    out = (C.c_int * 40)()
+    lib().ora_full_deck(seed, out)
+    return list(out)
+
+
+class FullEnv:
+    """ora_full_env with the snapshot format of tests/golden/full_env_traces.json.gz."""
+
+    def __init__(self, seed=42):
+        self.e = OraFullEnv()
+        lib().ora_full_init(C.byref(self.e), seed)
+
+    def reset(self, seed=None):
+        lib().ora_full_reset(C.byref(self.e), 0 if seed is None else seed, 0 if seed is None else 1)
+
+    def step(self, action):
+        lib().ora_full_step(C.byref(self.e), action)
+
+    def snapshot(self):
+        e = self.e
+        return {"table": [e.table[i] for i in range(e.ntable)],
+                "hands": [[e.hand[p][i] for i in range(e.nhand[p])] for p in range(2)],
+                "caps": [[e.caps[p][i] for i in range(e.ncaps[p])] for p in range(2)],
+                "scopas": [e.scopas[0], e.scopas[1]], "deck": 40 - e.deck_pos, "round": e.round_number,
+                "last": None if e.last_capture < 0 else e.last_capture, "agent": f"player_{e.agent}", "step": e.step_count,
+                "rew": [e.rewards[0], e.rewards[1]], "term": [bool(e.term[0]), bool(e.term[1])]}
+
+
+def full_rollout_random(seeds, philox_seed, nthreads=0, game_offset=0):
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    n = len(seeds)
+    actions, rewards = np.zeros((n, 36), dtype=np.uint8), np.zeros((n, 2), dtype=np.float32)
+    scopas, ncaps, maxt = np.zeros((n, 2), dtype=np.uint8), np.zeros((n, 2), dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+    lib().ora_full_rollout_random(seeds.ctypes.data, n, philox_seed, game_offset, actions.ctypes.data, rewards.ctypes.data,
+                                  scopas.ctypes.data, ncaps.ctypes.data, maxt.ctypes.data, nthreads)
+    return actions, rewards, scopas, ncaps, maxt

@@ -69,6 +69,16 @@ _SIGS = {
     "ms_mlp_forward": ([vp, C.c_int, vp, vp, vp, vp, i64, vp], C.c_int),
     "ms_sdcfr_traverse": ([vp, C.c_uint32, C.c_int, vp, vp, C.c_int, i64, u64, u64, vp, C.c_size_t, vp, vp, vp, vp, vp],
                           C.c_int),
+    "ms_full_deal_from_seeds": ([vp, i64, vp, vp, vp], C.c_int),
+    "ms_full_deck_from_seeds": ([vp, i64, vp, C.c_int, vp], C.c_int),
+    "ms_full_step": ([vp, vp, vp, vp, vp, i64, vp], C.c_int),
+    "ms_full_legal_actions": ([vp, vp, C.c_int, vp, vp, i64, vp], C.c_int),
+    "ms_full_rollout_random": ([vp, vp, i64, u64, u64, vp, vp, vp, vp], C.c_int),
+    "ms_full_table_overflow": ([C.POINTER(C.c_int), vp], C.c_int),
+    "ms_full_deal_from_seeds_host": ([vp, i64, vp, vp], C.c_int),
+    "ms_full_step_host": ([vp, vp, vp, vp, vp, i64], C.c_int),
+    "ms_full_rollout_random_host": ([vp, i64, u64, u64, vp, vp], C.c_int),
+    "ms_full_evaluate_host": ([vp, vp, vp, i64], C.c_int),
     "ms_md_create": ([vp, i64, i32, vp, C.POINTER(vp)], C.c_int),
     "ms_md_destroy": ([vp], None),
     "ms_md_reset": ([vp, vp], C.c_int),

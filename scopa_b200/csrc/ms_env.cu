@@ -62,12 +62,13 @@ __device__ __forceinline__ bool shuffle_deck(Gen& gen, unsigned long long& perm)
     return true;
 }
 
-struct MtWindow {          // first DEAL_WIN outputs from the kept state words
-    const uint32_t* lo;    // mt[0 .. DEAL_WIN]
-    const uint32_t* hi;    // mt[397 .. 397 + DEAL_WIN - 1]
+struct MtWindow {          // first `win` outputs from the kept state words
+    const uint32_t* lo;    // mt[0 .. win]
+    const uint32_t* hi;    // mt[397 .. 397 + win - 1]
     int kk;
+    int win;
     __device__ __forceinline__ bool next(uint32_t& out) {
-        if (kk >= DEAL_WIN) return false;
+        if (kk >= win) return false;
         uint32_t y = (lo[kk] & 0x80000000u) | (lo[kk + 1] & 0x7fffffffu);
         y = hi[kk] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         kk++;
@@ -101,8 +102,8 @@ struct MtFull {            // textbook generator over a full 624-word state (slo
 
 // Slow path (never taken in practice: needs > 25 rejected draws in one shuffle): the whole state in
 // local memory, textbook init_by_array + generator.
-__device__ __noinline__ unsigned long long deal_slow(uint32_t key0, uint32_t key1) {
-    uint32_t mt[624];
+// textbook init_by_array over a full 624-word state (slow paths only)
+__device__ __noinline__ void mt_seed_full(uint32_t key0, uint32_t key1, uint32_t* mt) {
     const bool two = key1 != 0u;
     for (int i = 0; i < 624; i++) mt[i] = g_mt_init[i];
     int i = 1, j = 0;
@@ -118,10 +119,56 @@ __device__ __noinline__ unsigned long long deal_slow(uint32_t key0, uint32_t key
         if (i >= 624) { mt[0] = mt[623]; i = 1; }
     }
     mt[0] = 0x80000000u;
+}
+
+__device__ __noinline__ unsigned long long deal_slow(uint32_t key0, uint32_t key1) {
+    uint32_t mt[624];
+    mt_seed_full(key0, key1, mt);
     MtFull gen{mt, 624};
     unsigned long long perm;
     shuffle_deck(gen, perm);
     return perm;
+}
+
+// random.seed(n) for the key words of |n|: fills lo[0 .. WIN + 1] = mt[0 .. WIN + 1] and hi[0 .. WIN - 1] =
+// mt[397 .. 397 + WIN - 1] of the seeded state (see the header comment: pass 1 is recomputed, not stored).
+template <int WIN>
+__device__ __forceinline__ void mt_seed_window(uint32_t key0, uint32_t key1, uint32_t* lo, uint32_t* hi) {
+    static_assert(WIN % 2 == 0 && WIN + 397 < 623, "window must be even and inside the first generator block");
+    const bool two = key1 != 0u;   // key length: 32-bit words of |seed|, at least one
+    const uint32_t kodd = two ? key1 + 1u : key0;   // key[j] + j for odd steps (j = 1) / one-word keys
+
+    // ---- pass 1, first run (nothing stored): step k writes word k+1 with key word j = k % len
+    // (unrolled so that the even/odd key word and the table offsets are compile-time operands)
+    uint32_t prev = (g_mt_init[1] ^ ((g_mt_init[0] ^ (g_mt_init[0] >> 30)) * 1664525u)) + key0;   // k = 0
+    const uint32_t first1 = prev;
+#pragma unroll 8
+    for (int k = 1; k < 623; k += 2) {
+        prev = (g_mt_init[k + 1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;      // odd k
+        prev = (g_mt_init[k + 2] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key0;      // even k
+    }
+    // step 624 wraps: mt[0] = mt[623]; word 1 is rewritten with j = 623 % len
+    const uint32_t m1w = (first1 ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;
+
+    // ---- pass 2 (i = 2..623, then the wrap to i = 1) in lock-step with a second run of pass 1
+    uint32_t p1 = first1, p2 = m1w;
+    auto lock_step = [&](int i, uint32_t kw) {
+        p1 = (g_mt_init[i] ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + kw;
+        p2 = (p1 ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)i;
+    };
+    // words 2..WIN and 397..397+WIN-1 are kept; the stretches between them are pure chain
+#pragma unroll 1
+    for (int i = 2; i <= WIN; i += 2) { lock_step(i, kodd); lo[i] = p2; lock_step(i + 1, key0); lo[i + 1] = p2; }
+    lock_step(WIN + 2, kodd);     // WIN + 1 was the last one stored above; continue the chain
+#pragma unroll 8
+    for (int i = WIN + 3; i < 397; i += 2) { lock_step(i, key0); lock_step(i + 1, kodd); }
+#pragma unroll 1
+    for (int i = 397; i < 397 + WIN; i += 2) { lock_step(i, key0); hi[i - 397] = p2; lock_step(i + 1, kodd); hi[i - 396] = p2; }
+#pragma unroll 8
+    for (int i = 397 + WIN; i < 623; i += 2) { lock_step(i, key0); lock_step(i + 1, kodd); }
+    lock_step(623, key0);
+    lo[1] = (m1w ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - 1u;
+    lo[0] = 0x80000000u;
 }
 
 __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__ seeds, long long n,
@@ -134,43 +181,8 @@ __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__
         if (sd == 0 && zero_means_42) sd = 42;   // `seed or self.seed` (mini_scopa_game.py:132, default seed 42)
         unsigned long long a = sd < 0 ? (unsigned long long)(-(sd + 1)) + 1ull : (unsigned long long)sd;
         const uint32_t key0 = (uint32_t)a, key1 = (uint32_t)(a >> 32);
-        const bool two = key1 != 0u;   // key length: 32-bit words of |seed|, at least one
-        const uint32_t kodd = two ? key1 + 1u : key0;   // key[j] + j for odd steps (j = 1) / one-word keys
-
-        // ---- pass 1, first run (nothing stored): step k writes word k+1 with key word j = k % len
-        // (unrolled so that the even/odd key word and the table offsets are compile-time operands)
-        uint32_t prev = (g_mt_init[1] ^ ((g_mt_init[0] ^ (g_mt_init[0] >> 30)) * 1664525u)) + key0;   // k = 0
-        const uint32_t first1 = prev;
-#pragma unroll 8
-        for (int k = 1; k < 623; k += 2) {
-            prev = (g_mt_init[k + 1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;      // odd k
-            prev = (g_mt_init[k + 2] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key0;      // even k
-        }
-        // step 624 wraps: mt[0] = mt[623]; word 1 is rewritten with j = 623 % len
-        const uint32_t m1w = (first1 ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;
-
-        // ---- pass 2 (i = 2..623, then the wrap to i = 1) in lock-step with a second run of pass 1
-        uint32_t p1 = first1, p2 = m1w;
-        auto lock_step = [&](int i, uint32_t kw) {
-            p1 = (g_mt_init[i] ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + kw;
-            p2 = (p1 ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)i;
-        };
-        // words 2..DEAL_WIN and 397..397+DEAL_WIN-1 are kept; the stretches between them are pure chain
-#pragma unroll 1
-        for (int i = 2; i <= DEAL_WIN; i += 2) { lock_step(i, kodd); lo[i] = p2; lock_step(i + 1, key0); lo[i + 1] = p2; }
-        static_assert(DEAL_WIN % 2 == 0, "window must be even");
-        lock_step(DEAL_WIN + 2, kodd);     // DEAL_WIN + 1 was the last one stored above; continue the chain
-#pragma unroll 8
-        for (int i = DEAL_WIN + 3; i < 397; i += 2) { lock_step(i, key0); lock_step(i + 1, kodd); }
-#pragma unroll 1
-        for (int i = 397; i < 397 + DEAL_WIN; i += 2) { lock_step(i, key0); hi[i - 397] = p2; lock_step(i + 1, kodd); hi[i - 396] = p2; }
-#pragma unroll 8
-        for (int i = 397 + DEAL_WIN; i < 623; i += 2) { lock_step(i, key0); lock_step(i + 1, kodd); }
-        lock_step(623, key0);
-        lo[1] = (m1w ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - 1u;
-        lo[0] = 0x80000000u;
-
-        MtWindow gen{lo, hi, 0};
+        mt_seed_window<DEAL_WIN>(key0, key1, lo, hi);
+        MtWindow gen{lo, hi, 0, DEAL_WIN};
         unsigned long long perm;
         if (!shuffle_deck(gen, perm)) perm = deal_slow(key0, key1);
         const uint32_t ord = (uint32_t)perm;   // first 8 dealt cards: 4 to player 0, 4 to player 1
@@ -183,6 +195,76 @@ __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__
         if (states) states[g] = st_make(h0, h1, 8u);
         if (hand_order) hand_order[g] = ord;
         if (deck) deck[g] = perm;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 40-card deck: FullDeck(seed) = random.seed + random.shuffle of ids 0..39 (src/envs/full_scopa_game.py:32-35).
+// Packed as four 64-bit words, ten 6-bit card ids each (position p -> word p / 10, bits 6 * (p % 10)).
+constexpr int FULL_WIN = 128;   // a 40-card shuffle takes ~53 words on average (39 draws + rejections)
+
+struct Deck40 {
+    unsigned long long w[4];
+    __device__ __forceinline__ uint32_t get(int p) const {
+        const int q = p / 10;
+        const unsigned long long x = q == 0 ? w[0] : (q == 1 ? w[1] : (q == 2 ? w[2] : w[3]));
+        return (uint32_t)(x >> (6 * (p % 10))) & 0x3Fu;
+    }
+    __device__ __forceinline__ void set(int p, uint32_t c) {
+        const int q = p / 10, sh = 6 * (p % 10);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k == q) w[k] = (w[k] & ~(0x3Full << sh)) | ((unsigned long long)c << sh);
+    }
+};
+
+template <typename Gen>
+__device__ __forceinline__ bool shuffle_deck40(Gen& gen, Deck40& d) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        d.w[q] = 0ull;
+        for (int k = 0; k < 10; k++) d.w[q] |= (unsigned long long)(10 * q + k) << (6 * k);
+    }
+    for (int i = 39; i >= 1; i--) {
+        const uint32_t nn = (uint32_t)i + 1u;
+        const int kbits = 32 - __clz(nn);
+        uint32_t r;
+        do {
+            uint32_t w;
+            if (!gen.next(w)) return false;
+            r = w >> (32 - kbits);
+        } while (r >= nn);
+        const uint32_t ci = d.get(i), cr = d.get((int)r);
+        d.set(i, cr); d.set((int)r, ci);
+    }
+    return true;
+}
+
+__device__ __noinline__ void full_deck_slow(uint32_t key0, uint32_t key1, Deck40& d) {
+    uint32_t mt[624];
+    mt_seed_full(key0, key1, mt);
+    MtFull gen{mt, 624};
+    shuffle_deck40(gen, d);
+}
+
+__global__ void __launch_bounds__(128) full_deck_kernel(const long long* __restrict__ seeds, long long n,
+                                                        ulonglong4* __restrict__ decks, int zero_means_42, int force_slow) {
+    uint32_t lo[FULL_WIN + 2], hi[FULL_WIN];
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
+         g += (long long)gridDim.x * blockDim.x) {
+        long long sd = seeds[g];
+        if (sd == 0 && zero_means_42) sd = 42;   // `seed or self.seed` (full_scopa_game.py:244, default seed 42)
+        unsigned long long a = sd < 0 ? (unsigned long long)(-(sd + 1)) + 1ull : (unsigned long long)sd;
+        const uint32_t key0 = (uint32_t)a, key1 = (uint32_t)(a >> 32);
+        Deck40 d;
+        bool ok = false;
+        if (!force_slow) {
+            mt_seed_window<FULL_WIN>(key0, key1, lo, hi);
+            MtWindow gen{lo, hi, 0, FULL_WIN};
+            ok = shuffle_deck40(gen, d);
+        }
+        if (!ok) full_deck_slow(key0, key1, d);
+        decks[g] = make_ulonglong4(d.w[0], d.w[1], d.w[2], d.w[3]);
     }
 }
 
@@ -401,6 +483,18 @@ int team_deck_from_seeds(const int64_t* d_seeds, int64_t n, uint64_t* d_deck, vo
     if (rc) return rc;
     deal_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         (const long long*)d_seeds, (long long)n, nullptr, nullptr, (unsigned long long*)d_deck, 1);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+}  // namespace ms
+
+namespace ms {
+// FullDeck(seed) for n seeds (used by ms_full.cu); zero_means_42 = the env-level `seed or self.seed` rule
+int full_deck_from_seeds(const int64_t* d_seeds, int64_t n, void* d_decks, int zero_means_42, int force_slow, void* stream) {
+    int rc = ensure_mt_table();
+    if (rc) return rc;
+    full_deck_kernel<<<grid_for(n, 128, 8), 128, 0, (cudaStream_t)stream>>>(
+        (const long long*)d_seeds, (long long)n, (ulonglong4*)d_decks, zero_means_42, force_slow);
     MS_LAUNCH_CHECK();
     return MS_OK;
 }
