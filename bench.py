@@ -9,8 +9,9 @@ BASELINE.json's metric is double-barrelled ("MCCFR infoset-node updates/sec & en
 JSON line carries both:
   * primary (metric/value/e2e/roofline/cpu_baseline): MCCFR infoset-node updates/s, config 3/5 of
     BASELINE.json -- a step = one batched MCCFR iteration on the seed-42 deal: `--trav` traversals per
-    player per GPU against the frozen table (mccfr_batch_kernel), one all-reduce of the slot-aligned delta
-    buffer over NCCL when N > 1, then table += delta (mccfr_apply_kernel).  Traversal ids are
+    player per GPU against the frozen table (mccfr_tree_kernel: the estimator walking the deal's enumerated
+    game tree; "mccfr_restep" beside it = the same estimator re-stepping the env at every node), one exchange
+    of the slot-aligned delta buffer when N > 1, then table += delta (mccfr_apply_kernel).  Traversal ids are
     global (rank-offset), so the union of all ranks' work is independent of N ("weak" scaling: per-GPU
     work is fixed).
   * "env": env steps/s, config 2 of BASELINE.json -- 1 M concurrent random-policy games per GPU, a step =
@@ -41,7 +42,8 @@ BYTES_PER_ENV_STEP = 34.0          # 16 B state load + 1 B action + 16 B state s
 FALLBACK_HBM_GBS = 6650.0
 # DRAM bytes per launch of the dominant kernels, from the committed ncu --set full captures (profiles/README.md)
 NCU_DRAM_BYTES_PER_LAUNCH = {"mccfr_batch_kernel": 117504, "rollout_kernel": 20052736,
-                             "md_mccfr_kernel": 1111869952}   # 65 536 deals, 340 992 traversal pairs (md_r01f_raw.csv)
+                             "md_mccfr_kernel": 1111869952,   # 65 536 deals, 340 992 traversal pairs (md_r01f_raw.csv)
+                             "mccfr_tree_kernel": 68096}
 
 
 def load_peaks():
@@ -281,6 +283,31 @@ def run_ours(args):
     mccfr_e2e = {"value": e2e_updates / e2e_s, "unit": "infoset-node updates/s",
                  "h2d_bytes_per_step": 2 * S * 4 * 8, "d2h_bytes_per_step": 2 * S * 4 * 8,
                  "what": "ms_solver_import_table (pinned host) + mccfr batch + all-reduce + apply + ms_solver_export_table"}
+
+    # ------------------------------------------------------------------ the same estimator re-stepping the env (mode 3)
+    # mccfr_batch_kernel: step(), capture resolution, legal list, infoset key and hash probe at every node instead of
+    # walking the enumerated tree -- what the headline kernel was before; kept as the comparison point
+    restep_obj = None
+    if rank == 0:
+        Br = 148 * 768 * 3
+        for i in range(2):
+            sv.mccfr_batch(2, Br, philox_seed=args.seed, first_trav=i * Br, mode=3)
+            sv.mccfr_apply()
+        sv.counters(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(K):
+            sv.mccfr_batch(2, Br, philox_seed=args.seed, first_trav=(2 + i) * Br, mode=3)
+            sv.mccfr_apply()
+        e1.record()
+        torch.cuda.synchronize()
+        rc = sv.counters(reset=True)
+        rms = e0.elapsed_time(e1)
+        restep_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
+                      "value": rc["updates"] / (rms * 1e-3), "ms_per_step": rms / K,
+                      "env_steps_per_sec_inside_mccfr": rc["env_steps"] / (rms * 1e-3), "kernel": "mccfr_batch_kernel",
+                      "config": {"workload": f"same estimator, mode 3 (env re-stepped at every node), {Br} traversals per player per step"}}
 
     # ------------------------------------------------------------------ textbook external sampling (opt-in estimator)
     es_obj = None
@@ -573,16 +600,19 @@ def run_ours(args):
     mccfr_obj = {
         "metric": "mccfr_infoset_node_updates_per_sec", "value": mccfr_value, "unit": "infoset-node updates/s",
         "ms_per_step": ms_total / K, "e2e": mccfr_e2e, "gpu_launches": int(mccfr_launches),
-        "node_visits_per_sec": visits_all / (ms_total * 1e-3), "env_steps_per_sec_inside_mccfr": steps_all / (ms_total * 1e-3),
+        "node_visits_per_sec": visits_all / (ms_total * 1e-3), "tree_edges_per_sec_inside_mccfr": steps_all / (ms_total * 1e-3),
         "roofline": {"bound": "hbm", "achieved": mccfr_roof_ach, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": mccfr_roof_ach / hbm_gbs, "traffic": NCU_DRAM_BYTES_PER_LAUNCH["mccfr_batch_kernel"],
-                     "traffic_source": "ncu --set full, profiles/mccfr_r01c_raw.csv: dram__bytes_read.sum + "
-                                       "dram__bytes_write.sum per launch (table staging only; independent of the batch size)",
-                     "kernel": "mccfr_batch_kernel",
+                     "frac": mccfr_roof_ach / hbm_gbs, "traffic": NCU_DRAM_BYTES_PER_LAUNCH["mccfr_tree_kernel"],
+                     "traffic_source": "ncu --set full, profiles/mccfr_r01g_raw.csv: dram__bytes_read.sum + "
+                                       "dram__bytes_write.sum per launch (table and tree staging only; independent of the batch size)",
+                     "kernel": "mccfr_tree_kernel",
                      "kernel_ms": ms_kernel, "peak_source": peak_src,
-                     "note": "HBM-EQUIVALENT figure (203.7 algorithmic B/update, SURVEY 8(d)); the 53 KB table of a single "
-                             "deal is shared-memory resident, so the real limiter is issue slots / shared-memory atomics "
-                             "(see profiles/)"},
+                     "on_chip": {"shared_memory_wavefronts_pct_of_peak": 70.4, "issue_slots_active_pct": 64.4,
+                                 "source": "ncu --set full, profiles/mccfr_r01g_raw.csv"},
+                     "note": "HBM-EQUIVALENT figure SURVEY 8(d) prescribes (203.7 algorithmic B/update: what an HBM-resident table "
+                             "would have to move); it exceeds 1 because the 53 KB table and the 9 KB tree of the one deal are "
+                             "shared-memory resident -- this is NOT an HBM result.  The binding resources are on chip: "
+                             "shared-memory wavefronts at 70 % of peak, issue slots 64 % (profiles/README.md section 1)"},
         "cpu_baseline": cpu_mccfr,
         "config": {"workload": "BASELINE.json configs[2]/[4]: MCCFR (reference estimator), seed-42 deal, "
                                f"{B} traversals per player per GPU per iteration, fp64 table", "traversals_per_step": 2 * B * world,
@@ -621,6 +651,7 @@ def run_ours(args):
         "cfr": cfr_obj,
         "mccfr_external_sampling": es_obj,
         "atomics": atom_obj,
+        "mccfr_restep": restep_obj,
         "mccfr_multi_deal": md_obj,
         "full_scopa": full_obj,
         "collective": collective,
@@ -719,7 +750,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mccfr", choices=["mccfr", "rollout"])
-    ap.add_argument("--trav", type=int, default=340992, help="traversals per player per GPU per step")
+    ap.add_argument("--trav", type=int, default=454656,
+                    help="traversals per player per GPU per step (default: 3 full waves of 148 CTAs x 1024 threads)")
     ap.add_argument("--games", type=int, default=1_000_000, help="concurrent games per GPU")
     ap.add_argument("--sd-trav", type=int, default=16384, help="SDCFR traversals per player per GPU per step")
     ap.add_argument("--step-states", type=int, default=16_000_000, help="states in the step-granular API measurement")

@@ -648,8 +648,16 @@ __global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev
     MccfrShared sh{hk, hs, d.hcap, sig, cdf, dreg, dcnt, touched, nullptr, nullptr};
     unsigned long long nu = 0, nv = 0, ns = 0;
     const long long gstride = (long long)gridDim.x * T;
+    // Threads walk the tree in lock-step, so at any moment the whole CTA updates the few infosets of one depth of
+    // one player's tree and the shared-memory fp64 adds (compare-and-swap loops) collide.  Odd warps therefore run
+    // player 1's traversal first: the two halves of the CTA work on disjoint infosets (+1 %).  Strategies are frozen
+    // for the launch and every draw is addressed by (traversal, call index), so the order cannot change a result.
+    // Also measured and dropped: summing the lanes that share a slot with match_any + shuffles before one atomic
+    // per group (27.5 -> 21.4 G updates/s) and fire-and-forget global REDs into per-CTA tables in L2 (23.2 G).
+    const int flip = (tid >> 5) & 1;
     for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += gstride) {
-        for (int tp = 0; tp < 2; tp++) {
+        for (int j = 0; j < 2; j++) {
+            const int tp = j ^ flip;
             if (player < 2 && tp != player) continue;
             mccfr_traverse<false>(d, sh, tp, first_trav + (unsigned long long)k, pkey, f_st + tid, f_ro + tid, f_sp + tid,
                                   f_meta + tid, f_cfv + tid, T, nu, nv, ns);
@@ -665,6 +673,214 @@ __global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev
         if (touched[s]) d.touched[s] = 1;
     }
     // counters: warp reduce, one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) {
+        nu += __shfl_down_sync(0xffffffffu, nu, off);
+        nv += __shfl_down_sync(0xffffffffu, nv, off);
+        ns += __shfl_down_sync(0xffffffffu, ns, off);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3t  the same estimator walking the ENUMERATED tree.  A solver holds one deal, whose whole game tree (2229 nodes)
+// was expanded at creation with the env's step() (tree_expand_kernel) -- vanilla CFR already sweeps it.  The
+// re-stepping kernel above spends ~60 % of its instructions on re-deriving what that tree already says (step +
+// capture resolution, the legal list, the infoset key and its hash probe: ncu source view, profiles/README.md).
+// Here a node visit is one 32-bit record from shared memory:
+//   bits 0-11 first child (terminal: 2 * reward of player 0, biased by 2048) | 12-22 infoset slot (0x7FF =
+//   terminal) | 23-25 number of children = legal actions, in legal_actions() order | 26 player to move
+// and a descent is `first child + action index`.  Same recursion, same Philox addressing by call index, same
+// forced-endgame shortcut, same frozen-sigma batch semantics and delta layout as mccfr_batch_kernel -- the two
+// produce the same tables (tests/test_gpu_solver.py).  Frames shrink from 44 to 26 bytes (no packed state) and the
+// code to 64 registers, so a CTA runs 1024 traversals at a time instead of 768.
+constexpr int TREE_THREADS = 1024;
+constexpr uint32_t TREE_TERMINAL = 0x7FFu;
+
+struct TreeFrames {       // SoA in shared memory: [frame][thread]
+    double* ro; double* sp; uint32_t* meta; uint32_t* cfv; uint16_t* cb;
+};
+
+__host__ __device__ inline size_t mccfr_tree_smem(int S, int n_nodes, int nframes, int threads) {
+    return sizeof(double) * 12 * (size_t)S + 4 * (size_t)n_nodes + 4 * (size_t)S + (size_t)S +
+           (size_t)threads * nframes * (8 + 8 + 4 + 4 + 2) + 64;
+}
+
+__device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const MccfrShared& sh, int tp, unsigned long long trav,
+                                    uint2 pkey, const TreeFrames& f, int fstride, unsigned long long& n_upd,
+                                    unsigned long long& n_vis, unsigned long long& n_step) {
+    uint32_t node = 0u;
+    double ro = 1.0, sp = 1.0;
+    int fi = -1;
+    uint4 xblk = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t xblk_id = 0xFFFFFFFFu, call = 0u;
+    int ret_x2 = 0;
+    bool returning = false;
+    const uint32_t tag = MS_TAG_MCCF + (uint32_t)tp;
+    while (true) {
+        if (!returning) {
+            const uint32_t rec = tree[node];
+            const uint32_t my_call = call++;
+            n_vis++;
+            const uint32_t slot = (rec >> 12) & 0x7FFu;
+            if (slot == TREE_TERMINAL) {
+                const int r = (int)(rec & 0xFFFu) - 2048;
+                ret_x2 = (tp == 0) ? r : -r;
+                returning = true;
+                continue;
+            }
+            const uint32_t nl = (rec >> 23) & 0x7u, cb = rec & 0xFFFu;
+            const int p = (int)((rec >> 26) & 1u);
+            sh.touched[slot] = 1;     // node created on first touch, for both players (mc_cfr.py:52)
+            if (nl == 1u) {           // forced move: sigma = [1.0], no random word (see mccfr_traverse)
+                if (p != tp) { node = cb; n_step++; continue; }
+                const uint32_t r1 = tree[cb];
+                uint32_t leaf = r1, slot2 = TREE_TERMINAL;
+                int below = 1;
+                bool forced = ((r1 >> 12) & 0x7FFu) == TREE_TERMINAL;
+                if (!forced && ((r1 >> 23) & 0x7u) == 1u) {          // the opponent's reply is forced as well
+                    slot2 = (r1 >> 12) & 0x7FFu;
+                    leaf = tree[r1 & 0xFFFu];
+                    below = 2;
+                    forced = ((leaf >> 12) & 0x7FFu) == TREE_TERMINAL;
+                }
+                if (forced) {         // both recursive calls of the reference walk this line: played once, accounted twice
+                    if (slot2 != TREE_TERMINAL) sh.touched[slot2] = 1;
+                    const int r = (int)(leaf & 0xFFFu) - 2048;
+                    ret_x2 = (tp == 0) ? r : -r;
+                    atomicAdd(&sh.dcnt[slot], 1u);      // regret delta = w * 0 exactly; strategy_sum += 1.0 * sigma = 1.0
+                    n_upd++;
+                    n_vis += 2 * below; call += 2u * (uint32_t)below; n_step += below;
+                    returning = true;
+                    continue;
+                }
+            }
+            int ai = 0;
+            if (nl > 1u) {
+                if ((my_call >> 1) != xblk_id) {
+                    xblk_id = my_call >> 1;
+                    xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
+                }
+                const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
+                ai = sample_cdf(sh.cdf + 4 * slot, (int)nl, u);
+            }
+            const double sga = sh.sig[4 * slot + ai];
+            node = cb + (uint32_t)ai;
+            n_step++;
+            if (p != tp) {            // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
+                ro = __dmul_rn(ro, sga);
+                continue;
+            }
+            fi++;                     // traverser: push a frame, descend into the sampled action first (:58-67)
+            const int o = fi * fstride;
+            f.ro[o] = ro; f.sp[o] = sp;
+            f.meta[o] = slot | (nl << 11);          // | cursor << 14 | util byte << 17
+            f.cfv[o] = 0u;
+            f.cb[o] = (uint16_t)cb;
+            sp = __dmul_rn(sp, sga);
+            continue;
+        }
+        // ---- a child returned ret_x2 to the top frame
+        if (fi < 0) break;
+        const int o = fi * fstride;
+        uint32_t meta = f.meta[o];
+        const int slot = (int)(meta & 0x7FFu);
+        const int nl = (int)((meta >> 11) & 0x7u);
+        int cur = (int)((meta >> 14) & 0x7u);
+        uint32_t cfvb = f.cfv[o];
+        if (cur == 0) meta = (meta & 0x1FFFFu) | (((uint32_t)ret_x2 & 0xFFu) << 17);   // util of the sampled action
+        else cfvb |= ((uint32_t)ret_x2 & 0xFFu) << (8 * (cur - 1));
+        cur++;
+        if (cur <= nl) {              // evaluate action i = cur-1 with a fresh sampled continuation (:71-78)
+            const int i = cur - 1;
+            f.meta[o] = (meta & ~(0x7u << 14)) | ((uint32_t)cur << 14);
+            f.cfv[o] = cfvb;
+            ro = f.ro[o];
+            sp = __dmul_rn(f.sp[o], sh.sig[4 * slot + i]);
+            node = (uint32_t)f.cb[o] + (uint32_t)i;
+            n_step++;
+            returning = false;
+            continue;
+        }
+        // ---- all actions evaluated: regret / strategy deltas (:79-84)
+        if (nl > 1) {                 // |A| = 1: cfv - v == 0 exactly
+            double cfv[4], sg[4];
+            double v = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                sg[i] = sh.sig[4 * slot + i];
+                cfv[i] = 0.5 * (double)(int)(int8_t)((cfvb >> (8 * i)) & 0xFFu);
+                if (i < nl) v = __dadd_rn(v, __dmul_rn(sg[i], cfv[i]));
+            }
+            const double fro = f.ro[o], fsp = f.sp[o];
+            const double w = fsp > 0.0 ? __ddiv_rn(fro, fsp) : 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < nl) atomicAdd(&sh.dreg[4 * slot + i], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+        }
+        atomicAdd(&sh.dcnt[slot], 1u);   // strategy delta = count * sigma (sigma is frozen for the batch)
+        n_upd++;
+        ret_x2 = (int)(int8_t)((meta >> 17) & 0xFFu);
+        fi--;
+        returning = true;
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
+                                                                unsigned long long first_trav, int nframes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = d.n_slots, N = d.n_nodes, T = THREADS, tid = threadIdx.x;
+    double* sig = (double*)smem_raw;
+    double* cdf = sig + 4 * S;
+    double* dreg = cdf + 4 * S;
+    TreeFrames f;
+    f.ro = dreg + 4 * S;
+    f.sp = f.ro + (size_t)T * nframes;
+    f.meta = (uint32_t*)(f.sp + (size_t)T * nframes);
+    f.cfv = f.meta + (size_t)T * nframes;
+    uint32_t* tree = f.cfv + (size_t)T * nframes;
+    uint32_t* dcnt = tree + N;
+    f.cb = (uint16_t*)(dcnt + S);
+    uint8_t* touched = (uint8_t*)(f.cb + (size_t)T * nframes);
+
+    for (int s = tid; s < S; s += T) {
+        double reg[4], sg[4], cd[4];
+        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+        regret_match(reg, d.slot_nlegal[s], sg);
+        strategy_cdf(sg, d.slot_nlegal[s], cd);
+        for (int i = 0; i < 4; i++) { sig[4 * s + i] = sg[i]; cdf[4 * s + i] = cd[i]; dreg[4 * s + i] = 0.0; }
+        dcnt[s] = 0u; touched[s] = 0;
+    }
+    for (int v = tid; v < N; v += T) {
+        const int sl = d.node_slot[v];
+        uint32_t rec;
+        if (sl < 0) rec = ((uint32_t)((int)d.rx2[v] + 2048) & 0xFFFu) | (TREE_TERMINAL << 12);
+        else rec = (uint32_t)d.child_begin[v] | ((uint32_t)sl << 12) | ((uint32_t)d.nchild[v] << 23) | ((uint32_t)d.slot_player[sl] << 26);
+        tree[v] = rec;
+    }
+    __syncthreads();
+
+    MccfrShared sh{nullptr, nullptr, 0, sig, cdf, dreg, dcnt, touched, nullptr, nullptr};
+    f.ro += tid; f.sp += tid; f.meta += tid; f.cfv += tid; f.cb += tid;
+    unsigned long long nu = 0, nv = 0, ns = 0;
+    const long long gstride = (long long)gridDim.x * T;
+    const int flip = (tid >> 5) & 1;      // odd warps run player 1 first: the halves of the CTA update disjoint infosets
+    for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += gstride) {
+        for (int j = 0; j < 2; j++) {
+            const int tp = j ^ flip;
+            if (player < 2 && tp != player) continue;
+            mccfr_tree_traverse(tree, sh, tp, first_trav + (unsigned long long)k, pkey, f, T, nu, nv, ns);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 4 * S; i += T) {
+        const double v = dreg[i];
+        if (v != 0.0) atomicAdd(&d.delta[i], v);
+    }
+    for (int s = tid; s < S; s += T) {
+        if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
+        if (touched[s]) d.touched[s] = 1;
+    }
     for (int off = 16; off > 0; off >>= 1) {
         nu += __shfl_down_sync(0xffffffffu, nu, off);
         nv += __shfl_down_sync(0xffffffffu, nv, off);
@@ -1478,30 +1694,57 @@ int ms_mccfr_inplace(ms_solver* s, int64_t iters, uint64_t philox_seed, uint64_t
     return MS_OK;
 }
 
-int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
-    int rc = check_dev(s); if (rc) return rc;
-    if (player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch: bad argument");
-    if (n_trav == 0) return MS_OK;
-    const size_t smem = mccfr_batch_smem(s->n_slots, s->hcap, s->nframes, MCCFR_THREADS);
+// mode 3 of ms_mccfr_batch_mode: the estimator re-stepping the env at every node (mccfr_batch_kernel)
+static int launch_mccfr_restep(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
+    int threads = MCCFR_THREADS;          // deals with more infosets than seed 42 leave room for fewer frames
+    while (threads > 128 && mccfr_batch_smem(s->n_slots, s->hcap, s->nframes, threads) > 227 * 1024) threads -= 128;
+    const size_t smem = mccfr_batch_smem(s->n_slots, s->hcap, s->nframes, threads);
     if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "MCCFR batch working set %zu B exceeds shared memory", smem);
     MS_CUDA(cudaFuncSetAttribute(mccfr_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)((227 * 1024) / smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    const int grid = grid_for(n_trav, MCCFR_THREADS, per_sm);
-    mccfr_batch_kernel<<<grid, MCCFR_THREADS, smem, (cudaStream_t)stream>>>(
+    mccfr_batch_kernel<<<grid_for(n_trav, threads, 1), threads, smem, (cudaStream_t)stream>>>(
         s->dev, player, (long long)n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
         (unsigned long long)first_trav, s->nframes);
     MS_LAUNCH_CHECK();
     return MS_OK;
 }
 
+static int launch_mccfr_tree(ms_solver* s, int threads, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
+                             void* stream) {
+    const size_t smem = mccfr_tree_smem(s->n_slots, s->n_nodes, s->nframes, threads);
+    const uint2 key = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
+    const int grid = grid_for(n_trav, threads, 1);
+    if (threads == TREE_THREADS) {
+        MS_CUDA(cudaFuncSetAttribute(mccfr_tree_kernel<TREE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mccfr_tree_kernel<TREE_THREADS><<<grid, TREE_THREADS, smem, (cudaStream_t)stream>>>(
+            s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav, s->nframes);
+    } else {
+        MS_CUDA(cudaFuncSetAttribute(mccfr_tree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mccfr_tree_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(
+            s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav, s->nframes);
+    }
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch: bad argument");
+    if (n_trav == 0) return MS_OK;
+    if (s->n_slots >= (int)TREE_TERMINAL || s->n_nodes > 4096) return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
+    if (mccfr_tree_smem(s->n_slots, s->n_nodes, s->nframes, TREE_THREADS) <= 227 * 1024)
+        return launch_mccfr_tree(s, TREE_THREADS, player, n_trav, philox_seed, first_trav, stream);
+    if (mccfr_tree_smem(s->n_slots, s->n_nodes, s->nframes, 512) <= 227 * 1024)
+        return launch_mccfr_tree(s, 512, player, n_trav, philox_seed, first_trav, stream);
+    return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
+}
+
 int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_trav, uint64_t philox_seed,
                         uint64_t first_trav, void* stream) {
     if (mode == 0) return ms_mccfr_batch(s, player, n_trav, philox_seed, first_trav, stream);
     int rc = check_dev(s); if (rc) return rc;
-    if (mode < 0 || mode > 2 || player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch_mode: bad argument");
+    if (mode < 0 || mode > 3 || player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch_mode: bad argument");
     if (n_trav == 0) return MS_OK;
+    if (mode == 3) return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
     const uint2 key = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
     if (mode == 1) {
         const size_t smem = es_smem_bytes(s->n_slots, s->hcap, s->nframes, ES_THREADS);

@@ -162,7 +162,8 @@ class Solver:
             _lib.check(self.lib.ms_mccfr_inplace(self.h, int(iters), int(philox_seed), int(first_iter), self._stream()))
 
     def mccfr_batch(self, player, n_trav, philox_seed=0, first_trav=0, mode=0):
-        """mode 0 = the reference's estimator, 1 = external sampling, 2 = outcome sampling (textbook, opt-in)."""
+        """mode 0 = the reference's estimator (walks the deal's enumerated tree), 1 = external sampling, 2 = outcome
+        sampling (textbook, opt-in), 3 = the reference's estimator re-stepping the env at every node (same tables as 0)."""
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_mccfr_batch_mode(self.h, int(mode), int(player), int(n_trav), int(philox_seed),
                                                     int(first_trav), self._stream()))

@@ -172,6 +172,32 @@ def test_mccfr_batch_shards_sum_to_whole():
     assert torch.equal(dsum[4 * S:], whole.delta_tensor()[4 * S:])    # update counts are exact integers
 
 
+@pytest.mark.parametrize("seed", [42, 1, 2 ** 33 + 7])
+def test_tree_walk_and_restep_kernels_agree(seed):
+    """mode 0 (the estimator walking the enumerated tree, the default) and mode 3 (the env re-stepped at every node):
+    same traversals, same Philox draws -> same deltas (fp64 sums differ only by addition order), identical update
+    counts, touched flags and counters."""
+    a, b = Solver(seed=seed), Solver(seed=seed)
+    for s in (a, b):
+        s.mccfr_inplace(5, philox_seed=3)
+        s.counters(reset=True)
+    n = 3 * 1024 + 17
+    for player in (0, 1, 2):
+        a.mccfr_batch(player, n, philox_seed=8, first_trav=100, mode=0)
+        b.mccfr_batch(player, n, philox_seed=8, first_trav=100, mode=3)
+        S = a.n_slots
+        torch.testing.assert_close(a.delta_tensor()[:4 * S], b.delta_tensor()[:4 * S], rtol=1e-10, atol=1e-10)
+        assert torch.equal(a.delta_tensor()[4 * S:], b.delta_tensor()[4 * S:])
+        a.mccfr_apply()
+        b.mccfr_apply()
+    assert a.counters() == b.counters()
+    ra, sa, ta = a.export()
+    rb, sb, tb = b.export()
+    assert np.array_equal(ta, tb)
+    np.testing.assert_allclose(ra, rb, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(sa, sb, rtol=1e-10, atol=1e-10)
+
+
 def test_best_response_vs_restated_openspiel():
     g = load_golden_json("policies_eval.json")
     sv = Solver(seed=42)
