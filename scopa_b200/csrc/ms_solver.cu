@@ -700,8 +700,8 @@ struct TreeFrames {       // SoA in shared memory: [frame][thread]
     double* ro; double* sp; uint32_t* meta; uint32_t* cfv; uint16_t* cb;
 };
 
-__host__ __device__ inline size_t mccfr_tree_smem(int S, int n_nodes, int nframes, int threads) {
-    return sizeof(double) * 12 * (size_t)S + 4 * (size_t)n_nodes + 4 * (size_t)S + (size_t)S +
+__host__ __device__ inline size_t mccfr_tree_smem(int S, int n_nodes, int nframes, int threads, int ncopy) {
+    return sizeof(double) * (7 + 4 * (size_t)ncopy) * (size_t)S + 4 * (size_t)n_nodes + 4 * (size_t)S + (size_t)S +
            (size_t)threads * nframes * (8 + 8 + 4 + 4 + 2) + 64;
 }
 
@@ -761,7 +761,12 @@ __device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const Mcc
                     xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
                 }
                 const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
-                ai = sample_cdf(sh.cdf + 4 * slot, (int)nl, u);
+                // searchsorted(cdf, u, 'right') reading only the first nl-1 entries: cdf[nl-1] is exactly 1.0 > u.
+                // The kernel is bound by shared-memory wavefronts, and a lane's 32-byte cdf row is the widest read.
+                const double* cd = sh.cdf + 3 * slot;
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+                    if ((uint32_t)i + 1u < nl) ai += (cd[i] <= u) ? 1 : 0;
             }
             const double sga = sh.sig[4 * slot + ai];
             node = cb + (uint32_t)ai;
@@ -807,7 +812,7 @@ __device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const Mcc
             double v = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                sg[i] = sh.sig[4 * slot + i];
+                sg[i] = (i < nl) ? sh.sig[4 * slot + i] : 0.0;
                 cfv[i] = 0.5 * (double)(int)(int8_t)((cfvb >> (8 * i)) & 0xFFu);
                 if (i < nl) v = __dadd_rn(v, __dmul_rn(sg[i], cfv[i]));
             }
@@ -827,14 +832,14 @@ __device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const Mcc
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
-                                                                unsigned long long first_trav, int nframes) {
+                                                                unsigned long long first_trav, int nframes, int ncopy) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = d.n_slots, N = d.n_nodes, T = THREADS, tid = threadIdx.x;
     double* sig = (double*)smem_raw;
-    double* cdf = sig + 4 * S;
-    double* dreg = cdf + 4 * S;
+    double* cdf = sig + 4 * S;              // [S][3]: the last entry of a normalised cdf is 1.0 and is never read
+    double* dreg = cdf + 3 * S;             // ncopy copies of the delta table, chosen by lane (see below)
     TreeFrames f;
-    f.ro = dreg + 4 * S;
+    f.ro = dreg + (size_t)ncopy * 4 * S;
     f.sp = f.ro + (size_t)T * nframes;
     f.meta = (uint32_t*)(f.sp + (size_t)T * nframes);
     f.cfv = f.meta + (size_t)T * nframes;
@@ -848,9 +853,11 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int
         for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
         regret_match(reg, d.slot_nlegal[s], sg);
         strategy_cdf(sg, d.slot_nlegal[s], cd);
-        for (int i = 0; i < 4; i++) { sig[4 * s + i] = sg[i]; cdf[4 * s + i] = cd[i]; dreg[4 * s + i] = 0.0; }
+        for (int i = 0; i < 4; i++) sig[4 * s + i] = sg[i];
+        for (int i = 0; i < 3; i++) cdf[3 * s + i] = cd[i];
         dcnt[s] = 0u; touched[s] = 0;
     }
+    for (int i = tid; i < ncopy * 4 * S; i += T) dreg[i] = 0.0;
     for (int v = tid; v < N; v += T) {
         const int sl = d.node_slot[v];
         uint32_t rec;
@@ -860,7 +867,11 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int
     }
     __syncthreads();
 
-    MccfrShared sh{nullptr, nullptr, 0, sig, cdf, dreg, dcnt, touched, nullptr, nullptr};
+    // A shared-memory fp64 atomicAdd is a compare-and-swap loop, and the lanes of a warp walk the tree in lock-step: at
+    // an update they sit on a handful of infosets and the loops of one warp retry against each other (ncu r01g: 41 %
+    // of the kernel's shared-memory wavefronts).  Several copies of the delta table (as many of 4 / 2 / 1 as shared
+    // memory holds), chosen by lane id, divide that: 71.8 -> 87.2 G updates/s with two copies.
+    MccfrShared sh{nullptr, nullptr, 0, sig, cdf, dreg + (size_t)(tid & (ncopy - 1)) * 4 * S, dcnt, touched, nullptr, nullptr};
     f.ro += tid; f.sp += tid; f.meta += tid; f.cfv += tid; f.cb += tid;
     unsigned long long nu = 0, nv = 0, ns = 0;
     const long long gstride = (long long)gridDim.x * T;
@@ -874,7 +885,8 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int
     }
     __syncthreads();
     for (int i = tid; i < 4 * S; i += T) {
-        const double v = dreg[i];
+        double v = dreg[i];
+        for (int c = 1; c < ncopy; c++) v = __dadd_rn(v, dreg[(size_t)c * 4 * S + i]);
         if (v != 0.0) atomicAdd(&d.delta[i], v);
     }
     for (int s = tid; s < S; s += T) {
@@ -1355,7 +1367,7 @@ struct ms_solver {
     int device = 0;
     ms_state root{};
     uint32_t hand_order = 0;
-    int n_nodes = 0, n_levels = 0, n_slots = 0, n_dec = 0, hcap = 0, nframes = 4;
+    int n_nodes = 0, n_levels = 0, n_slots = 0, n_dec = 0, hcap = 0, nframes = 4, nframes_tree = 4;
     std::vector<int> level_begin, slot_level_begin;
     // host copies for export
     std::vector<ms_state> h_state; std::vector<int> h_parent, h_child_begin, h_slot; std::vector<uint8_t> h_nchild, h_level;
@@ -1483,6 +1495,29 @@ int solver_build(ms_solver* sv) {
         if (any) dl[(root_cur + l) & 1]++;
     }
     sv->nframes = std::max(1, std::max(dl[0], dl[1]));
+    // The tree-walking kernel pushes no frame at a traverser node whose single move leads to the end of the game
+    // through forced moves only (its endgame shortcut): on a fresh deal that is every traverser's last card, so
+    // three frames suffice instead of four.  Longest chain of frame-pushing nodes of one player, by DP over the tree.
+    {
+        std::vector<int> need0(N, 0), need1(N, 0);
+        for (int v = N - 1; v >= 0; v--) {
+            const int nc = sv->h_nchild[v];
+            if (nc == 0) continue;
+            const int cb = sv->h_child_begin[v];
+            int m0 = 0, m1 = 0;
+            for (int c = cb; c < cb + nc; c++) { m0 = std::max(m0, need0[c]); m1 = std::max(m1, need1[c]); }
+            bool forced = false;
+            if (nc == 1) {
+                if (sv->h_nchild[cb] == 0) forced = true;
+                else if (sv->h_nchild[cb] == 1 && sv->h_nchild[sv->h_child_begin[cb]] == 0) forced = true;
+            }
+            const int p = (int)((sv->h_state[v].meta >> 17) & 1u);
+            const int push = (nc == 1 && forced) ? 0 : 1;
+            need0[v] = m0 + (p == 0 ? push : 0);
+            need1[v] = m1 + (p == 1 ? push : 0);
+        }
+        sv->nframes_tree = std::max(1, std::max(need0[0], need1[0]));
+    }
 
     // ---- 3. upload
     size_t total = 0;
@@ -1708,19 +1743,19 @@ static int launch_mccfr_restep(ms_solver* s, int32_t player, int64_t n_trav, uin
     return MS_OK;
 }
 
-static int launch_mccfr_tree(ms_solver* s, int threads, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
-                             void* stream) {
-    const size_t smem = mccfr_tree_smem(s->n_slots, s->n_nodes, s->nframes, threads);
+static int launch_mccfr_tree(ms_solver* s, int threads, int ncopy, int32_t player, int64_t n_trav, uint64_t philox_seed,
+                             uint64_t first_trav, void* stream) {
+    const size_t smem = mccfr_tree_smem(s->n_slots, s->n_nodes, s->nframes_tree, threads, ncopy);
     const uint2 key = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
     const int grid = grid_for(n_trav, threads, 1);
     if (threads == TREE_THREADS) {
         MS_CUDA(cudaFuncSetAttribute(mccfr_tree_kernel<TREE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mccfr_tree_kernel<TREE_THREADS><<<grid, TREE_THREADS, smem, (cudaStream_t)stream>>>(
-            s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav, s->nframes);
+            s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav, s->nframes_tree, ncopy);
     } else {
         MS_CUDA(cudaFuncSetAttribute(mccfr_tree_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mccfr_tree_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(
-            s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav, s->nframes);
+            s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav, s->nframes_tree, ncopy);
     }
     MS_LAUNCH_CHECK();
     return MS_OK;
@@ -1731,10 +1766,10 @@ int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox
     if (player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch: bad argument");
     if (n_trav == 0) return MS_OK;
     if (s->n_slots >= (int)TREE_TERMINAL || s->n_nodes > 4096) return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
-    if (mccfr_tree_smem(s->n_slots, s->n_nodes, s->nframes, TREE_THREADS) <= 227 * 1024)
-        return launch_mccfr_tree(s, TREE_THREADS, player, n_trav, philox_seed, first_trav, stream);
-    if (mccfr_tree_smem(s->n_slots, s->n_nodes, s->nframes, 512) <= 227 * 1024)
-        return launch_mccfr_tree(s, 512, player, n_trav, philox_seed, first_trav, stream);
+    for (int threads : {TREE_THREADS, 512})
+        for (int ncopy : {4, 2, 1})
+            if (mccfr_tree_smem(s->n_slots, s->n_nodes, s->nframes_tree, threads, ncopy) <= 227 * 1024)
+                return launch_mccfr_tree(s, threads, ncopy, player, n_trav, philox_seed, first_trav, stream);
     return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
 }
 
