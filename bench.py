@@ -43,7 +43,7 @@ FALLBACK_HBM_GBS = 6650.0
 # DRAM bytes per launch of the dominant kernels, from the committed ncu --set full captures (profiles/README.md)
 NCU_DRAM_BYTES_PER_LAUNCH = {"mccfr_batch_kernel": 117504, "rollout_kernel": 20052736,
                              "md_mccfr_kernel": 1111869952,   # 65 536 deals, 340 992 traversal pairs (md_r01f_raw.csv)
-                             "mccfr_tree_kernel": 68096}
+                             "mccfr_tree_kernel": 69376}
 
 
 def load_peaks():
@@ -603,16 +603,16 @@ def run_ours(args):
         "node_visits_per_sec": visits_all / (ms_total * 1e-3), "tree_edges_per_sec_inside_mccfr": steps_all / (ms_total * 1e-3),
         "roofline": {"bound": "hbm", "achieved": mccfr_roof_ach, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": mccfr_roof_ach / hbm_gbs, "traffic": NCU_DRAM_BYTES_PER_LAUNCH["mccfr_tree_kernel"],
-                     "traffic_source": "ncu --set full, profiles/mccfr_r01g_raw.csv: dram__bytes_read.sum + "
+                     "traffic_source": "ncu --set full, profiles/mccfr_r01h_raw.csv: dram__bytes_read.sum + "
                                        "dram__bytes_write.sum per launch (table and tree staging only; independent of the batch size)",
                      "kernel": "mccfr_tree_kernel",
                      "kernel_ms": ms_kernel, "peak_source": peak_src,
-                     "on_chip": {"shared_memory_wavefronts_pct_of_peak": 70.4, "issue_slots_active_pct": 64.4,
-                                 "source": "ncu --set full, profiles/mccfr_r01g_raw.csv"},
+                     "on_chip": {"issue_slots_active_pct": 76.9, "shared_memory_wavefronts_pct_of_peak": 65.4,
+                                 "alu_pipe_pct": 53.6, "source": "ncu --set full, profiles/mccfr_r01h_raw.csv"},
                      "note": "HBM-EQUIVALENT figure SURVEY 8(d) prescribes (203.7 algorithmic B/update: what an HBM-resident table "
                              "would have to move); it exceeds 1 because the 53 KB table and the 9 KB tree of the one deal are "
                              "shared-memory resident -- this is NOT an HBM result.  The binding resources are on chip: "
-                             "shared-memory wavefronts at 70 % of peak, issue slots 64 % (profiles/README.md section 1)"},
+                             "issue slots 77 % busy, shared-memory wavefronts at 65 % of peak (profiles/README.md section 1)"},
         "cpu_baseline": cpu_mccfr,
         "config": {"workload": "BASELINE.json configs[2]/[4]: MCCFR (reference estimator), seed-42 deal, "
                                f"{B} traversals per player per GPU per iteration, fp64 table", "traversals_per_step": 2 * B * world,
