@@ -313,7 +313,7 @@ def run_ours(args):
     es_obj = None
     if rank == 0:
         es_sv = Solver(seed=42, device=dev)
-        Bes = 148 * 512 * 2
+        Bes = 148 * 1024 * 2
         for i in range(W):
             es_sv.mccfr_batch(2, Bes, philox_seed=args.seed, first_trav=i * Bes, mode=1)
             es_sv.mccfr_apply()
@@ -328,7 +328,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         es_cnt = es_sv.counters()
         es_s = e0.elapsed_time(e1) * 1e-3
-        es_obj = {"estimator": "external sampling (Lanctot et al. 2009), not in the reference", "kernel": "mccfr_es_kernel",
+        es_obj = {"estimator": "external sampling (Lanctot et al. 2009), not in the reference", "kernel": "mccfr_es_tree_kernel",
                   "traversals_per_sec": 2.0 * Bes * K / es_s, "regret_updates_per_sec": es_cnt["updates"] / es_s,
                   "node_visits_per_sec": es_cnt["visits"] / es_s,
                   "exploitability_after": {"traversals_per_player": (W + K) * Bes, "value": es_sv.exploitability(1)},

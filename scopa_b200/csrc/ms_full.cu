@@ -24,6 +24,8 @@
 //           difference s0 - s1 as a signed byte (rewards are +-(s0 - s1) / 2)
 // Beside each game: the shuffled deck (ms_full_deck, 4 x 64 bits, ten 6-bit ids per word).  The table is
 // deck[0..3]; round r deals deck[4 + 6 r + 3 p + i] to player p, so hands are presence bits, not card lists.
+#include <mutex>
+
 #include "ms_common.cuh"
 #include "ms_state.cuh"
 
@@ -354,13 +356,19 @@ __global__ void __launch_bounds__(256) full_rollout_kernel(const uint4* __restri
 // the deck kernel lives in ms_env.cu (it shares the MT19937 seeding with the 16-card deal)
 int full_deck_from_seeds(const int64_t* d_seeds, int64_t n, void* d_decks, int zero_means_42, int force_slow, void* stream);
 
-static unsigned int* g_overflow = nullptr;      // device flag: a table outgrew FS_MAX_TABLE
+// device flag "a table outgrew FS_MAX_TABLE", one per device (allocated on first use on that device)
+static unsigned int* g_overflow[64] = {};
+static std::mutex g_overflow_mu;
 static int full_overflow_flag(unsigned int** out) {
-    if (!g_overflow) {
-        MS_CUDA(cudaMalloc(&g_overflow, sizeof(unsigned int)));
-        MS_CUDA(cudaMemset(g_overflow, 0, sizeof(unsigned int)));
+    int dev = 0;
+    MS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(MS_ERR_ARG, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_overflow_mu);
+    if (!g_overflow[dev]) {
+        MS_CUDA(cudaMalloc(&g_overflow[dev], sizeof(unsigned int)));
+        MS_CUDA(cudaMemset(g_overflow[dev], 0, sizeof(unsigned int)));
     }
-    *out = g_overflow;
+    *out = g_overflow[dev];
     return MS_OK;
 }
 

@@ -1110,6 +1110,160 @@ __device__ void os_traverse(const SolverDev& d, const MccfrShared& sh, double* d
     }
 }
 
+// External sampling walking the enumerated tree (the form ms_mccfr_batch_mode(mode = 1) launches; mccfr_es_kernel
+// above, which re-steps the env, is kept for trees that do not fit).  Same update rules, same Philox addressing, same
+// node records, lane-indexed delta-table copies and frozen-sigma semantics as mccfr_tree_kernel.  A traverser node
+// with one legal action needs no frame: its value is its child's (1.0 * x = x exactly) and its regret delta is 0.
+struct EsTreeFrames { double* cv; uint32_t* meta; uint16_t* cb; };
+
+__host__ __device__ inline size_t es_tree_smem(int S, int n_nodes, int nframes, int threads, int ncopy) {
+    return sizeof(double) * (7 + 4 * (size_t)ncopy) * (size_t)S + 4 * (size_t)n_nodes + 4 * (size_t)S + (size_t)S +
+           (size_t)threads * nframes * (32 + 4 + 2) + 64;
+}
+
+__device__ void es_tree_traverse(const uint32_t* __restrict__ tree, const MccfrShared& sh, int tp, unsigned long long trav,
+                                 uint2 pkey, const EsTreeFrames& f, int fstride, unsigned long long& n_upd,
+                                 unsigned long long& n_vis, unsigned long long& n_step) {
+    uint32_t node = 0u, call = 0u;
+    int fi = -1;
+    double ret = 0.0;
+    bool returning = false;
+    uint4 xblk = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t xblk_id = 0xFFFFFFFFu;
+    const uint32_t tag = MS_TAG_ES + (uint32_t)tp;
+    while (true) {
+        if (!returning) {
+            const uint32_t rec = tree[node];
+            const uint32_t my_call = call++;
+            n_vis++;
+            const uint32_t slot = (rec >> 12) & 0x7FFu;
+            if (slot == TREE_TERMINAL) {
+                const int r = (int)(rec & 0xFFFu) - 2048;
+                ret = 0.5 * (double)(tp == 0 ? r : -r);
+                returning = true;
+                continue;
+            }
+            const uint32_t nl = (rec >> 23) & 0x7u, cb = rec & 0xFFFu;
+            const int p = (int)((rec >> 26) & 1u);
+            sh.touched[slot] = 1;
+            n_step++;
+            if (p != tp) {                          // opponent: average strategy += sigma, sample, tail call
+                atomicAdd(&sh.dcnt[slot], 1u);
+                int ai = 0;
+                if (nl > 1u) {
+                    if ((my_call >> 1) != xblk_id) {
+                        xblk_id = my_call >> 1;
+                        xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
+                    }
+                    const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
+                    const double* cd = sh.cdf + 3 * slot;
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+                        if ((uint32_t)i + 1u < nl) ai += (cd[i] <= u) ? 1 : 0;
+                }
+                node = cb + (uint32_t)ai;
+                continue;
+            }
+            if (nl == 1u) { n_upd++; node = cb; continue; }      // forced traverser move: value = the child's value
+            fi++;                                   // traverser: expand every action
+            const int o = fi * fstride;
+            f.meta[o] = slot | (nl << 11);          // | cursor << 14
+            f.cb[o] = (uint16_t)cb;
+            node = cb;
+            continue;
+        }
+        if (fi < 0) break;
+        const int o = fi * fstride;
+        uint32_t meta = f.meta[o];
+        const int slot = (int)(meta & 0x7FFu);
+        const int nl = (int)((meta >> 11) & 0x7u);
+        int cur = (int)((meta >> 14) & 0x7u);
+        f.cv[(size_t)(4 * fi + cur) * fstride] = ret;
+        cur++;
+        if (cur < nl) {
+            f.meta[o] = (meta & ~(0x7u << 14)) | ((uint32_t)cur << 14);
+            node = (uint32_t)f.cb[o] + (uint32_t)cur;
+            n_step++;
+            returning = false;
+            continue;
+        }
+        double cv[4], value = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            cv[i] = (i < nl) ? f.cv[(size_t)(4 * fi + i) * fstride] : 0.0;
+            if (i < nl) value = __dadd_rn(value, __dmul_rn(sh.sig[4 * slot + i], cv[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (i < nl) atomicAdd(&sh.dreg[4 * slot + i], __dadd_rn(cv[i], -value));
+        n_upd++;
+        ret = value;
+        fi--;
+        returning = true;
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) mccfr_es_tree_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
+                                                                   unsigned long long first_trav, int nframes, int ncopy) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = d.n_slots, N = d.n_nodes, T = THREADS, tid = threadIdx.x;
+    double* sig = (double*)smem_raw;
+    double* cdf = sig + 4 * S;              // [S][3]
+    double* dreg = cdf + 3 * S;             // ncopy copies, chosen by lane id
+    EsTreeFrames f;
+    f.cv = dreg + (size_t)ncopy * 4 * S;
+    f.meta = (uint32_t*)(f.cv + (size_t)T * nframes * 4);
+    uint32_t* tree = f.meta + (size_t)T * nframes;
+    uint32_t* dcnt = tree + N;
+    f.cb = (uint16_t*)(dcnt + S);
+    uint8_t* touched = (uint8_t*)(f.cb + (size_t)T * nframes);
+    for (int s = tid; s < S; s += T) {
+        double reg[4], sg[4], cd[4];
+        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+        regret_match(reg, d.slot_nlegal[s], sg);
+        strategy_cdf(sg, d.slot_nlegal[s], cd);
+        for (int i = 0; i < 4; i++) sig[4 * s + i] = sg[i];
+        for (int i = 0; i < 3; i++) cdf[3 * s + i] = cd[i];
+        dcnt[s] = 0u; touched[s] = 0;
+    }
+    for (int i = tid; i < ncopy * 4 * S; i += T) dreg[i] = 0.0;
+    for (int v = tid; v < N; v += T) {
+        const int sl = d.node_slot[v];
+        uint32_t rec;
+        if (sl < 0) rec = ((uint32_t)((int)d.rx2[v] + 2048) & 0xFFFu) | (TREE_TERMINAL << 12);
+        else rec = (uint32_t)d.child_begin[v] | ((uint32_t)sl << 12) | ((uint32_t)d.nchild[v] << 23) | ((uint32_t)d.slot_player[sl] << 26);
+        tree[v] = rec;
+    }
+    __syncthreads();
+    MccfrShared sh{nullptr, nullptr, 0, sig, cdf, dreg + (size_t)(tid & (ncopy - 1)) * 4 * S, dcnt, touched, nullptr, nullptr};
+    f.cv += tid; f.meta += tid; f.cb += tid;
+    unsigned long long nu = 0, nv = 0, ns = 0;
+    const int flip = (tid >> 5) & 1;
+    for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += (long long)gridDim.x * T)
+        for (int j = 0; j < 2; j++) {
+            const int tp = j ^ flip;
+            if (player < 2 && tp != player) continue;
+            es_tree_traverse(tree, sh, tp, first_trav + (unsigned long long)k, pkey, f, T, nu, nv, ns);
+        }
+    __syncthreads();
+    for (int i = tid; i < 4 * S; i += T) {
+        double v = dreg[i];
+        for (int c = 1; c < ncopy; c++) v = __dadd_rn(v, dreg[(size_t)c * 4 * S + i]);
+        if (v != 0.0) atomicAdd(&d.delta[i], v);
+    }
+    for (int s = tid; s < S; s += T) {
+        if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
+        if (touched[s]) d.touched[s] = 1;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        nu += __shfl_down_sync(0xffffffffu, nu, off);
+        nv += __shfl_down_sync(0xffffffffu, nv, off);
+        ns += __shfl_down_sync(0xffffffffu, ns, off);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
+}
+
 __global__ void __launch_bounds__(256) mccfr_os_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
                                                        unsigned long long first_trav) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1367,7 +1521,7 @@ struct ms_solver {
     int device = 0;
     ms_state root{};
     uint32_t hand_order = 0;
-    int n_nodes = 0, n_levels = 0, n_slots = 0, n_dec = 0, hcap = 0, nframes = 4, nframes_tree = 4;
+    int n_nodes = 0, n_levels = 0, n_slots = 0, n_dec = 0, hcap = 0, nframes = 4, nframes_tree = 4, nframes_es = 4;
     std::vector<int> level_begin, slot_level_begin;
     // host copies for export
     std::vector<ms_state> h_state; std::vector<int> h_parent, h_child_begin, h_slot; std::vector<uint8_t> h_nchild, h_level;
@@ -1517,6 +1671,19 @@ int solver_build(ms_solver* sv) {
             need1[v] = m1 + (p == 1 ? push : 0);
         }
         sv->nframes_tree = std::max(1, std::max(need0[0], need1[0]));
+        // external sampling pushes a frame at every traverser node with more than one legal action
+        std::fill(need0.begin(), need0.end(), 0); std::fill(need1.begin(), need1.end(), 0);
+        for (int v = N - 1; v >= 0; v--) {
+            const int nc = sv->h_nchild[v];
+            if (nc == 0) continue;
+            const int cb = sv->h_child_begin[v];
+            int m0 = 0, m1 = 0;
+            for (int c = cb; c < cb + nc; c++) { m0 = std::max(m0, need0[c]); m1 = std::max(m1, need1[c]); }
+            const int p = (int)((sv->h_state[v].meta >> 17) & 1u);
+            need0[v] = m0 + ((p == 0 && nc > 1) ? 1 : 0);
+            need1[v] = m1 + ((p == 1 && nc > 1) ? 1 : 0);
+        }
+        sv->nframes_es = std::max(1, std::max(need0[0], need1[0]));
     }
 
     // ---- 3. upload
@@ -1781,6 +1948,17 @@ int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_tr
     if (n_trav == 0) return MS_OK;
     if (mode == 3) return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
     const uint2 key = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
+    if (mode == 1 && s->n_slots < (int)TREE_TERMINAL && s->n_nodes <= 4096) {
+        for (int ncopy : {4, 2, 1}) {
+            const size_t smem = es_tree_smem(s->n_slots, s->n_nodes, s->nframes_es, TREE_THREADS, ncopy);
+            if (smem > 227 * 1024) continue;
+            MS_CUDA(cudaFuncSetAttribute(mccfr_es_tree_kernel<TREE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mccfr_es_tree_kernel<TREE_THREADS><<<grid_for(n_trav, TREE_THREADS, 1), TREE_THREADS, smem, (cudaStream_t)stream>>>(
+                s->dev, player, (long long)n_trav, key, (unsigned long long)first_trav, s->nframes_es, ncopy);
+            MS_LAUNCH_CHECK();
+            return MS_OK;
+        }
+    }
     if (mode == 1) {
         const size_t smem = es_smem_bytes(s->n_slots, s->hcap, s->nframes, ES_THREADS);
         if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "ES working set %zu B exceeds shared memory", smem);
