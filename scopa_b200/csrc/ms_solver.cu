@@ -705,6 +705,9 @@ __host__ __device__ inline size_t mccfr_tree_smem(int S, int n_nodes, int nframe
            (size_t)threads * nframes * (8 + 8 + 4 + 4 + 2) + 64;
 }
 
+// INPLACE = the reference's own schedule (one traversal at a time, every update visible to the next node visit:
+// sh.reg / sh.str are the table itself); otherwise frozen-sigma batch semantics (sh.sig / sh.cdf / sh.dreg / sh.dcnt).
+template <bool INPLACE>
 __device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const MccfrShared& sh, int tp, unsigned long long trav,
                                     uint2 pkey, const TreeFrames& f, int fstride, unsigned long long& n_upd,
                                     unsigned long long& n_vis, unsigned long long& n_step) {
@@ -747,7 +750,9 @@ __device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const Mcc
                     if (slot2 != TREE_TERMINAL) sh.touched[slot2] = 1;
                     const int r = (int)(leaf & 0xFFFu) - 2048;
                     ret_x2 = (tp == 0) ? r : -r;
-                    atomicAdd(&sh.dcnt[slot], 1u);      // regret delta = w * 0 exactly; strategy_sum += 1.0 * sigma = 1.0
+                    // regret delta = w * 0 exactly; strategy_sum += 1.0 * sigma = 1.0
+                    if (INPLACE) sh.str[4 * slot] = __dadd_rn(sh.str[4 * slot], 1.0);
+                    else atomicAdd(&sh.dcnt[slot], 1u);
                     n_upd++;
                     n_vis += 2 * below; call += 2u * (uint32_t)below; n_step += below;
                     returning = true;
@@ -755,20 +760,28 @@ __device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const Mcc
                 }
             }
             int ai = 0;
+            double sga = 1.0;
             if (nl > 1u) {
                 if ((my_call >> 1) != xblk_id) {
                     xblk_id = my_call >> 1;
                     xblk = philox4x32_10(make_uint4((uint32_t)trav, (uint32_t)(trav >> 32), xblk_id, tag), pkey);
                 }
                 const double u = (my_call & 1u) ? u53(xblk.z, xblk.w) : u53(xblk.x, xblk.y);
-                // searchsorted(cdf, u, 'right') reading only the first nl-1 entries: cdf[nl-1] is exactly 1.0 > u.
-                // The kernel is bound by shared-memory wavefronts, and a lane's 32-byte cdf row is the widest read.
-                const double* cd = sh.cdf + 3 * slot;
+                if (INPLACE) {
+                    double sg[4];
+                    regret_match(sh.reg + 4 * slot, (int)nl, sg);
+                    ai = sample_action(sg, (int)nl, u);
+                    sga = ai == 0 ? sg[0] : (ai == 1 ? sg[1] : (ai == 2 ? sg[2] : sg[3]));
+                } else {
+                    // searchsorted(cdf, u, 'right') reading only the first nl-1 entries: cdf[nl-1] is exactly 1.0 > u
+                    // (a lane's cdf row is the widest shared-memory read of a visit)
+                    const double* cd = sh.cdf + 3 * slot;
 #pragma unroll
-                for (int i = 0; i < 3; i++)
-                    if ((uint32_t)i + 1u < nl) ai += (cd[i] <= u) ? 1 : 0;
+                    for (int i = 0; i < 3; i++)
+                        if ((uint32_t)i + 1u < nl) ai += (cd[i] <= u) ? 1 : 0;
+                    sga = sh.sig[4 * slot + ai];
+                }
             }
-            const double sga = sh.sig[4 * slot + ai];
             node = cb + (uint32_t)ai;
             n_step++;
             if (p != tp) {            // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
@@ -800,19 +813,26 @@ __device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const Mcc
             f.meta[o] = (meta & ~(0x7u << 14)) | ((uint32_t)cur << 14);
             f.cfv[o] = cfvb;
             ro = f.ro[o];
-            sp = __dmul_rn(f.sp[o], sh.sig[4 * slot + i]);
+            double sgi;
+            if (INPLACE) {            // unchanged since entry: an infoset cannot recur below itself
+                double sg[4];
+                regret_match(sh.reg + 4 * slot, nl, sg);
+                sgi = i == 0 ? sg[0] : (i == 1 ? sg[1] : (i == 2 ? sg[2] : sg[3]));
+            } else sgi = sh.sig[4 * slot + i];
+            sp = __dmul_rn(f.sp[o], sgi);
             node = (uint32_t)f.cb[o] + (uint32_t)i;
             n_step++;
             returning = false;
             continue;
         }
         // ---- all actions evaluated: regret / strategy deltas (:79-84)
-        if (nl > 1) {                 // |A| = 1: cfv - v == 0 exactly
+        if (INPLACE || nl > 1) {      // batch mode skips |A| = 1: cfv - v == 0 exactly
             double cfv[4], sg[4];
             double v = 0.0;
+            if (INPLACE) regret_match(sh.reg + 4 * slot, nl, sg);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                sg[i] = (i < nl) ? sh.sig[4 * slot + i] : 0.0;
+                if (!INPLACE) sg[i] = (i < nl) ? sh.sig[4 * slot + i] : 0.0;
                 cfv[i] = 0.5 * (double)(int)(int8_t)((cfvb >> (8 * i)) & 0xFFu);
                 if (i < nl) v = __dadd_rn(v, __dmul_rn(sg[i], cfv[i]));
             }
@@ -820,14 +840,58 @@ __device__ void mccfr_tree_traverse(const uint32_t* __restrict__ tree, const Mcc
             const double w = fsp > 0.0 ? __ddiv_rn(fro, fsp) : 0.0;
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (i < nl) atomicAdd(&sh.dreg[4 * slot + i], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+                if (i < nl) {
+                    if (INPLACE) {
+                        sh.reg[4 * slot + i] = __dadd_rn(sh.reg[4 * slot + i], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+                        sh.str[4 * slot + i] = __dadd_rn(sh.str[4 * slot + i], __dmul_rn(1.0, sg[i]));   // reach_probs[tp] is always 1.0
+                    } else atomicAdd(&sh.dreg[4 * slot + i], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+                }
         }
-        atomicAdd(&sh.dcnt[slot], 1u);   // strategy delta = count * sigma (sigma is frozen for the batch)
+        if (!INPLACE) atomicAdd(&sh.dcnt[slot], 1u);   // strategy delta = count * sigma (sigma is frozen for the batch)
         n_upd++;
         ret_x2 = (int)(int8_t)((meta >> 17) & 0xFFu);
         fi--;
         returning = true;
     }
+}
+
+// in-place mode on the enumerated tree: one thread, the table itself in shared memory, reference semantics (every
+// update is visible to the next node visit) -- what MCCFRTrainer.iteration() runs by default
+__global__ void __launch_bounds__(32, 1) mccfr_inplace_tree_kernel(SolverDev d, long long iters, uint2 pkey,
+                                                                  unsigned long long first_iter, int nframes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = d.n_slots, N = d.n_nodes, tid = threadIdx.x;
+    double* reg = (double*)smem_raw;
+    double* str = reg + 4 * S;
+    TreeFrames f;
+    f.ro = str + 4 * S;
+    f.sp = f.ro + nframes;
+    f.meta = (uint32_t*)(f.sp + nframes);
+    f.cfv = f.meta + nframes;
+    uint32_t* tree = f.cfv + nframes;
+    f.cb = (uint16_t*)(tree + N);
+    uint8_t* touched = (uint8_t*)(f.cb + nframes);
+    for (int i = tid; i < 4 * S; i += 32) { reg[i] = d.regret[i]; str[i] = d.strategy[i]; }
+    for (int i = tid; i < S; i += 32) touched[i] = d.touched[i];
+    for (int v = tid; v < N; v += 32) {
+        const int sl = d.node_slot[v];
+        uint32_t rec;
+        if (sl < 0) rec = ((uint32_t)((int)d.rx2[v] + 2048) & 0xFFFu) | (TREE_TERMINAL << 12);
+        else rec = (uint32_t)d.child_begin[v] | ((uint32_t)sl << 12) | ((uint32_t)d.nchild[v] << 23) | ((uint32_t)d.slot_player[sl] << 26);
+        tree[v] = rec;
+    }
+    __syncwarp();
+    if (tid == 0) {
+        MccfrShared sh{nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, touched, reg, str};
+        unsigned long long nu = 0, nv = 0, ns = 0;
+        for (long long it = 0; it < iters; it++)
+            for (int tp = 0; tp < 2; tp++)
+                mccfr_tree_traverse<true>(tree, sh, tp, first_iter + (unsigned long long)it, pkey, f, 1, nu, nv, ns);
+        atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns);
+    }
+    __syncwarp();
+    for (int i = tid; i < 4 * S; i += 32) { d.regret[i] = reg[i]; d.strategy[i] = str[i]; }
+    for (int i = tid; i < S; i += 32) d.touched[i] = touched[i];
 }
 
 template <int THREADS>
@@ -880,7 +944,7 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int
         for (int j = 0; j < 2; j++) {
             const int tp = j ^ flip;
             if (player < 2 && tp != player) continue;
-            mccfr_tree_traverse(tree, sh, tp, first_trav + (unsigned long long)k, pkey, f, T, nu, nv, ns);
+            mccfr_tree_traverse<false>(tree, sh, tp, first_trav + (unsigned long long)k, pkey, f, T, nu, nv, ns);
         }
     }
     __syncthreads();
@@ -1885,6 +1949,17 @@ int ms_mccfr_inplace(ms_solver* s, int64_t iters, uint64_t philox_seed, uint64_t
     int rc = check_dev(s); if (rc) return rc;
     if (iters < 0) return fail(MS_ERR_ARG, "iters < 0");
     if (iters == 0) return MS_OK;
+    const uint2 key = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
+    if (s->n_slots < (int)TREE_TERMINAL && s->n_nodes <= 4096) {       // walk the enumerated tree (same results)
+        const size_t tsmem = 64 * (size_t)s->n_slots + (size_t)s->nframes_tree * 26 + 4 * (size_t)s->n_nodes + s->n_slots + 64;
+        if (tsmem <= 227 * 1024) {
+            MS_CUDA(cudaFuncSetAttribute(mccfr_inplace_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            mccfr_inplace_tree_kernel<<<1, 32, tsmem, (cudaStream_t)stream>>>(s->dev, (long long)iters, key,
+                                                                              (unsigned long long)first_iter, s->nframes_tree);
+            MS_LAUNCH_CHECK();
+            return MS_OK;
+        }
+    }
     const int S = s->n_slots, nf = s->nframes;
     size_t smem = 64 * (size_t)S + 8 * (size_t)s->hcap + (size_t)nf * 44 + 2 * (size_t)s->hcap + S + 64;
     if (smem > 227 * 1024) return fail(MS_ERR_CAPACITY, "MCCFR in-place working set %zu B exceeds shared memory", smem);
