@@ -334,6 +334,22 @@ def run_ours(args):
                   "exploitability_after": {"traversals_per_player": (W + K) * Bes, "value": es_sv.exploitability(1)},
                   "note": "the reference's own estimator plateaus near 0.49 exploitability on this deal"}
         del es_sv
+        # BASELINE.json configs[2]: "10M traversals, exploitability vs iteration" -- both estimators from an empty table,
+        # 4096 traversals per player per iteration (frozen-sigma batches), exploitability by the device best response
+        curve = {}
+        for mode_id, name, kind in ((1, "external_sampling", 1), (0, "reference_estimator", 1)):
+            csv_ = Solver(seed=42, device=dev)
+            done, pts, Bc = 0, [], 4096
+            t0 = time.perf_counter()
+            for target in (10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7):
+                while done < target:
+                    csv_.mccfr_batch(2, Bc, philox_seed=args.seed, first_trav=done, mode=mode_id)
+                    csv_.mccfr_apply()
+                    done += Bc
+                pts.append([done, csv_.exploitability(kind)])
+            curve[name] = {"traversals_per_player_vs_exploitability": pts, "wall_s": time.perf_counter() - t0}
+            del csv_
+        es_obj["exploitability_vs_traversals"] = curve
 
     # ------------------------------------------------------------------ env rollouts (config 2)
     G = args.games
