@@ -198,6 +198,33 @@ def test_tree_walk_and_restep_kernels_agree(seed):
     np.testing.assert_allclose(sa, sb, rtol=1e-10, atol=1e-10)
 
 
+@pytest.mark.parametrize("seed,plies", [(7, 1), (7, 3), (12345, 2), (99, 5), (3, 6)])
+def test_tree_walk_and_restep_kernels_agree_on_mid_game_roots(seed, plies):
+    """Solvers rooted at mid-game states (unequal hands, cards on the table, player 1 to move): the tree-walking kernels
+    size their frame stack from the enumerated tree, the re-stepping kernel from the level count; both must produce
+    the same deltas, update counts, touched flags and counters."""
+    from scopa_b200.batch import BatchedMiniScopa
+    b = BatchedMiniScopa("cuda").reset([seed])
+    actions, _ = b.rollout_random(philox_seed=seed)[:2]
+    for k in range(plies):
+        b.step(actions[:, k].contiguous())
+    words = b.states.cpu().numpy().view(np.uint32)[0]
+    ho = int(b.hand_order.cpu().numpy().view(np.uint32)[0])
+    a, c = Solver(root_words=words, hand_order=ho), Solver(root_words=words, hand_order=ho)
+    assert a.n_nodes == c.n_nodes > 1
+    n = 2048 + 5
+    for mode_a, mode_c in ((0, 3), (0, 3)):
+        a.mccfr_batch(2, n, philox_seed=4, first_trav=7, mode=mode_a)
+        c.mccfr_batch(2, n, philox_seed=4, first_trav=7, mode=mode_c)
+        S = a.n_slots
+        torch.testing.assert_close(a.delta_tensor()[:4 * S], c.delta_tensor()[:4 * S], rtol=1e-10, atol=1e-10)
+        assert torch.equal(a.delta_tensor()[4 * S:], c.delta_tensor()[4 * S:])
+        a.mccfr_apply()
+        c.mccfr_apply()
+    assert a.counters() == c.counters()
+    assert np.array_equal(a.export()[2], c.export()[2])
+
+
 def test_best_response_vs_restated_openspiel():
     g = load_golden_json("policies_eval.json")
     sv = Solver(seed=42)
