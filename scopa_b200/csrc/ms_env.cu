@@ -385,16 +385,33 @@ __global__ void __launch_bounds__(256) rollout_kernel(const uint4* __restrict__ 
         // the instruction cache instead of eight (the unrolled kernel was 50 KB, beyond the 32 KB L1.5 I-cache)
         unsigned long long acts = 0ull;
         uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        // Both hands as ordered nibble lists (deal order restricted to the cards still held: the order of
+        // legal_actions()), built once and edited as cards are played -- the per-ply legal_list() compaction was the
+        // largest single line of this kernel (11 % of its instructions, ncu source view).
+        uint32_t hl = 0u;
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            uint32_t lst;
+            MsState t = s;
+            t.w &= ~(1u << 18);                                 // list the hand even if the state is terminal
+            const uint32_t cnt = legal_list(t, ho, pl, lst);
+            if (st_hand(s, pl) != 0u && cnt) hl |= (lst & 0xFFFFu) << (16 * pl);
+        }
 #pragma unroll 1
         for (int ply = 0; ply < 8; ply++) {
             if ((ply & 3) == 0)
                 x = philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(ply >> 2), MS_TAG_ROLL), key);
             const int q = ply & 3;
             const uint32_t xw = q == 0 ? x.x : (q == 1 ? x.y : (q == 2 ? x.z : x.w));
-            uint32_t list;
-            const uint32_t nl = legal_list(s, ho, st_cur(s), list);
-            const uint32_t idx = __umulhi(xw, nl);
-            const uint32_t a = (list >> (4u * idx)) & 0xFu;
+            const int pl = st_cur(s);
+            const uint32_t nl = st_terminal(s) ? 0u : (uint32_t)__popc(st_hand(s, pl));
+            uint32_t a = 0u;                                    // empty hand: legal_actions() == [0]; terminal: no-op
+            if (nl) {
+                const uint32_t idx = __umulhi(xw, nl);
+                const uint32_t lst = (hl >> (16 * pl)) & 0xFFFFu;
+                a = (lst >> (4u * idx)) & 0xFu;
+                hl = (hl & ~(0xFFFFu << (16 * pl))) | (nibble_remove(lst, idx) << (16 * pl));
+            }
             step(s, a, table_set_from_dealt(s, dealt));
             acts |= (unsigned long long)a << (8 * ply);
         }
