@@ -94,21 +94,29 @@ __device__ __forceinline__ FsState fs_initial(const FsDeck& d) {
     return s;
 }
 
-// the i-th card dealt to player p in the state's round
-__device__ __forceinline__ uint32_t fs_hand_card(const FsState& s, const FsDeck& d, int p, int i) {
-    return fs_deck_card(d, 4 + 6 * (int)fs_round(s) + 3 * p + i);
+// the six cards dealt in the state's round, 6 bits each: card i of player p at bits 6 * (3 p + i).  Fused kernels
+// extract them once per round instead of going through the deck at every ply.
+__device__ __forceinline__ unsigned long long fs_round_cards(const FsState& s, const FsDeck& d) {
+    const int base = 4 + 6 * (int)fs_round(s);
+    unsigned long long hc = 0ull;
+#pragma unroll
+    for (int k = 0; k < 6; k++) hc |= (unsigned long long)fs_deck_card(d, base + k) << (6 * k);
+    return hc;
+}
+__device__ __forceinline__ uint32_t fs_hand_card(unsigned long long hc, int p, int i) {
+    return (uint32_t)(hc >> (6 * (3 * p + i))) & 0x3Fu;
 }
 
 // FullScopaState.legal_actions (openspiel_full_scopa.py:22-41): the hand in list (= deal) order; [0] when the hand
 // is empty and the game is not over; [] when it is.  Packs the ids into bytes of `list`, returns the count.
-__device__ __forceinline__ uint32_t fs_legal_list(const FsState& s, const FsDeck& d, int p, uint32_t& list) {
+__device__ __forceinline__ uint32_t fs_legal_list(const FsState& s, unsigned long long hc, int p, uint32_t& list) {
     list = 0u;
     if (fs_terminal(s)) return 0u;
     const uint32_t bits = fs_hand_bits(s, p);
     uint32_t n = 0u;
 #pragma unroll
     for (int i = 0; i < 3; i++)
-        if ((bits >> i) & 1u) { list |= fs_hand_card(s, d, p, i) << (8u * n); n++; }
+        if ((bits >> i) & 1u) { list |= fs_hand_card(hc, p, i) << (8u * n); n++; }
     return n ? n : 1u;
 }
 
@@ -197,14 +205,15 @@ __device__ __forceinline__ int fs_score_diff(const FsState& s) { return (int)(in
 // FullScopaEnv.step (:252-296) + FullScopaGame.play_card (:130-158).  A card the mover does not hold (or an id
 // outside 0..39, which raises IndexError in the reference) is a silent pass that still advances step_count and the
 // turn; a step on a finished game is a no-op (:253-255).  Returns false if the table outgrew the packed state.
-__device__ __forceinline__ bool fs_step(FsState& s, const FsDeck& d, uint32_t action) {
+// `hc` = fs_round_cards() of the state's round (stale once the step has dealt a new round).
+__device__ __forceinline__ bool fs_step(FsState& s, unsigned long long hc, uint32_t action) {
     if (fs_terminal(s)) return true;
     const int p = fs_cur(s);
     const uint32_t bits = fs_hand_bits(s, p);
     int hp = -1;
 #pragma unroll
     for (int i = 2; i >= 0; i--)
-        if (((bits >> i) & 1u) && fs_hand_card(s, d, p, i) == action) hp = i;
+        if (((bits >> i) & 1u) && fs_hand_card(hc, p, i) == action) hp = i;
     bool ok = true;
     if (hp >= 0) {
         unsigned long long lo = fs_tlo(s), hi = fs_thi(s);
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(256) full_step_kernel(uint4* __restrict__ stat
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
         FsState s = fs_load(states, g);
         const FsDeck d = fs_load_deck(decks, g);
-        if (!fs_step(s, d, actions[g])) *overflow = 1u;
+        if (!fs_step(s, fs_round_cards(s, d), actions[g])) *overflow = 1u;
         fs_store(states, g, s);
         const bool t = fs_terminal(s);
         if (rewards) {
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(256) full_legal_kernel(const uint4* __restrict
         const FsState s = fs_load(states, g);
         const FsDeck d = fs_load_deck(decks, g);
         uint32_t list;
-        const uint32_t nl = fs_legal_list(s, d, player < 0 ? fs_cur(s) : player, list);
+        const uint32_t nl = fs_legal_list(s, fs_round_cards(s, d), player < 0 ? fs_cur(s) : player, list);
         if (ordered) {
             for (int i = 0; i < 3; i++) ordered[3 * g + i] = (uint32_t)i < nl ? (uint8_t)((list >> (8 * i)) & 0xFFu) : (uint8_t)0xFF;
         }
@@ -323,6 +332,7 @@ __global__ void __launch_bounds__(256) full_rollout_kernel(const uint4* __restri
 #pragma unroll
         for (int i = 0; i < 9; i++) acts[i] = 0u;
         bool ok = true;
+        unsigned long long hc = fs_round_cards(s, d);
 #pragma unroll 1
         for (int blk = 0; blk < 9; blk++) {
             x = philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)blk, MS_TAG_FULL), key);
@@ -331,9 +341,11 @@ __global__ void __launch_bounds__(256) full_rollout_kernel(const uint4* __restri
             for (int q = 0; q < 4; q++) {
                 const uint32_t xw = q == 0 ? x.x : (q == 1 ? x.y : (q == 2 ? x.z : x.w));
                 uint32_t list;
-                const uint32_t nl = fs_legal_list(s, d, fs_cur(s), list);
+                const uint32_t nl = fs_legal_list(s, hc, fs_cur(s), list);
                 const uint32_t a = nl ? (list >> (8u * __umulhi(xw, nl))) & 0xFFu : 0u;
-                ok &= fs_step(s, d, a);
+                const uint32_t round_before = fs_round(s);
+                ok &= fs_step(s, hc, a);
+                if (fs_round(s) != round_before) hc = fs_round_cards(s, d);      // a new hand was dealt
                 packed |= a << (8 * q);
             }
 #pragma unroll
