@@ -467,7 +467,7 @@ def run_ours(args):
     # ------------------------------------------------------------------ multi-deal MCCFR
     # The regime SURVEY 8(d) names as the one where the memory system is the bound: one infoset table for 65 536
     # deals (5.1 M stored infosets, 0.66 GB of 128-byte lines, far beyond the 126 MB L2) in HBM.
-    md_obj = None
+    md_obj = mdb_obj = None
     if rank == 0 and args.md_deals > 0:
         import ctypes
         from scopa_b200 import multideal
@@ -495,6 +495,32 @@ def run_ours(args):
         lines_lg = max(10, int(np.ceil(np.log2(max(mc["infosets"], 1)))))
         rp = (ctypes.c_double * 3)()
         table_bytes = md.table_bytes
+        # the deal-blocked form on the same table: one deal per CTA visit, 3072 traversal pairs per visit staged on chip
+        VIS, PPV = 148, 3072
+        tb0 = time.perf_counter()
+        md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=0)     # first call builds the deal records
+        md.apply()
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - tb0
+        for i in range(1, 4):
+            md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=i * VIS)
+            md.apply()
+        md.counters(reset=True)
+        bev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        bev[0].record()
+        for i in range(K):
+            md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=(4 + i) * VIS)
+            md.apply()
+            bev[i + 1].record()
+        torch.cuda.synchronize()
+        bc = md.counters()
+        b_ms = bev[0].elapsed_time(bev[K]) / K
+        mdb_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
+                   "value": bc["updates"] / K / (b_ms * 1e-3), "ms_per_step": b_ms, "infosets": int(bc["infosets"]),
+                   "first_call_s_incl_describing_all_deals": build_s, "kernel": "md_blocked_kernel",
+                   "config": {"workload": f"same table and estimator, deal-blocked: {VIS} visits x {PPV} traversal pairs per step, one "
+                                          "deal per CTA visit staged in shared memory (tree, strategies, delta tables), table "
+                                          "read once and written once per visit"}}
         del md
         torch.cuda.empty_cache()
         _lib.check(_lib.load().ms_debug_random_access_peaks(lines_lg, rp, _lib.stream_ptr()))
@@ -669,6 +695,7 @@ def run_ours(args):
         "atomics": atom_obj,
         "mccfr_restep": restep_obj,
         "mccfr_multi_deal": md_obj,
+        "mccfr_multi_deal_blocked": mdb_obj,
         "full_scopa": full_obj,
         "collective": collective,
     }

@@ -307,6 +307,15 @@ int ms_md_reset(ms_mdsolver* s, void* stream);
 int ms_md_info(const ms_mdsolver* s, int64_t* n_deals, int64_t* capacity, int64_t* table_bytes);
 int ms_md_mccfr_batch(ms_mdsolver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
                       void* stream);
+/* ms_md_mccfr_blocked: the deal-blocked form.  Visit v (first_visit .. first_visit+n_visits-1) plays deal
+ *   mulhi32(x0, n_deals), x = Philox4x32-10(key = philox_seed, ctr = (v lo, v hi, 1, "DEAL")), with pairs_per_visit
+ *   traversals whose global ids are v * pairs_per_visit + i; one CTA stages the deal (enumerated tree, frozen strategies
+ *   of its infosets, private delta tables) in shared memory, runs the visit on chip like ms_mccfr_batch, and writes the
+ *   deltas back to the table once.  The first call describes every deal's tree and creates all its infosets with more
+ *   than one action in the table (so ms_md_export then lists untouched ones too, with zeros).  Same estimator, streams
+ *   and ms_md_apply as ms_md_mccfr_batch; with n_deals = 1 it equals ms_mccfr_batch on the same traversal ids. */
+int ms_md_mccfr_blocked(ms_mdsolver* s, int32_t player, int64_t first_visit, int64_t n_visits, int32_t pairs_per_visit,
+                        uint64_t philox_seed, void* stream);
 int ms_md_apply(ms_mdsolver* s, void* stream);
 int ms_md_counters(ms_mdsolver* s, uint64_t h_out[5], int reset, void* stream);
 int ms_md_export(ms_mdsolver* s, uint64_t* d_keys, double* d_regret, double* d_strategy, int64_t max_n, int64_t* h_n,

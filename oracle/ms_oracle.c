@@ -1427,3 +1427,47 @@ void ora_full_rollout_random(const int64_t* seeds, int64_t n, uint64_t philox_se
         if (maxtable) maxtable[g] = (uint8_t)mt;
     }
 }
+
+/* deal-blocked form of the multi-deal estimator: a visit draws ONE deal (Philox "DEAL" stream, counter word 2 = 1)
+ * and runs `pairs` traversals on it, global ids visit * pairs + i; every deal's infosets with more than one action
+ * exist in the table from the start (ora_md_populate). */
+static void md_populate_rec(ora_mdtable* t, const ora_state* s) {
+    if (s->is_terminal) return;
+    int player = ora_state_current_player(s);
+    int legal[4]; int n = ora_state_legal(s, player, legal);
+    if (n > 1) md_get(t, s, player);
+    for (int i = 0; i < n; i++) {
+        ora_state c; ora_state_clone(s, &c); ora_state_apply(&c, legal[i]);
+        md_populate_rec(t, &c);
+    }
+}
+void ora_md_populate(ora_mdtable* t, const int64_t* seeds, int64_t n_deals) {
+    for (int64_t d = 0; d < n_deals; d++) { ora_state s; ora_state_init(&s, seeds[d]); md_populate_rec(t, &s); }
+}
+
+void ora_md_batch_blocked(ora_mdtable* t, const int64_t* seeds, int64_t n_deals, int player, uint64_t philox_seed,
+                          uint64_t first_visit, int64_t n_visits, int64_t pairs, int64_t* n_updates, int64_t* n_visits_out) {
+    ora_rng* rng = ora_rng_new(1, philox_seed);
+    md_ctx c = {t, rng, 0, 0, 0};
+    const uint32_t key[2] = {(uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)};
+    for (int64_t v = 0; v < n_visits; v++) {
+        uint64_t visit = first_visit + (uint64_t)v;
+        uint32_t ctr[4] = {(uint32_t)visit, (uint32_t)(visit >> 32), 1u, TAG_DEAL}, o[4];
+        philox4x32_10(ctr, key, o);
+        int64_t deal = (int64_t)(((uint64_t)o[0] * (uint64_t)n_deals) >> 32);
+        for (int64_t i = 0; i < pairs; i++) {
+            uint64_t trav = visit * (uint64_t)pairs + (uint64_t)i;
+            for (int tp = 0; tp < 2; tp++) {
+                if (player < 2 && tp != player) continue;
+                ora_state s; ora_state_init(&s, seeds[deal]);
+                c.tp = tp;
+                rng->tag = TAG_MCCF + (uint32_t)tp; rng->trav = trav; rng->call = 0;
+                double one[2] = {1.0, 1.0};
+                md_sample(&c, &s, one, one);
+            }
+        }
+    }
+    if (n_updates) *n_updates = c.n_updates;
+    if (n_visits_out) *n_visits_out = c.n_visits;
+    ora_rng_free(rng);
+}

@@ -139,6 +139,8 @@ def lib():
     L.ora_md_strategy.restype = P(dbl)
     L.ora_md_batch.argtypes = [vp, vp, i64, ci, u64, u64, i64, P(i64), P(i64)]
     L.ora_md_apply.argtypes = [vp]
+    L.ora_md_populate.argtypes = [vp, vp, i64]
+    L.ora_md_batch_blocked.argtypes = [vp, vp, i64, ci, u64, u64, i64, i64, P(i64), P(i64)]
     _lib = L
     return L
 
@@ -444,6 +446,15 @@ class MultiDealTable:
 
     def apply(self):
         lib().ora_md_apply(self.t)
+
+    def populate(self):
+        lib().ora_md_populate(self.t, self.seeds.ctypes.data, len(self.seeds))
+
+    def batch_blocked(self, player, philox_seed, first_visit, n_visits, pairs):
+        nu, nv = C.c_int64(0), C.c_int64(0)
+        lib().ora_md_batch_blocked(self.t, self.seeds.ctypes.data, len(self.seeds), player, philox_seed, first_visit, n_visits,
+                                   pairs, C.byref(nu), C.byref(nv))
+        return nu.value, nv.value
 
     def arrays(self):
         """-> string keys, packed keys (uint64), regret [n,4], strategy [n,4], nlegal [n] (first-touch order)"""

@@ -84,6 +84,7 @@ _SIGS = {
     "ms_md_reset": ([vp, vp], C.c_int),
     "ms_md_info": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], C.c_int),
     "ms_md_mccfr_batch": ([vp, i32, i64, u64, u64, vp], C.c_int),
+    "ms_md_mccfr_blocked": ([vp, i32, i64, i64, i32, u64, vp], C.c_int),
     "ms_md_apply": ([vp, vp], C.c_int),
     "ms_md_counters": ([vp, C.POINTER(u64), C.c_int, vp], C.c_int),
     "ms_md_export": ([vp, vp, vp, vp, i64, C.POINTER(i64), vp], C.c_int),

@@ -23,6 +23,7 @@
 
 #include "ms_common.cuh"
 #include "ms_state.cuh"
+#include "ms_tree_walk.cuh"
 
 namespace ms {
 
@@ -471,6 +472,224 @@ __global__ void __launch_bounds__(768, 1) rnd_red_kernel(MdSlot* tab, unsigned l
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Deal-blocked form: the HBM table as the backing store of an on-chip solver.
+//
+// md_mccfr_kernel above samples a deal per traversal and touches the table in place: every node visit is a random
+// line transaction, and the dependent chain of a depth-first traversal keeps it latency-bound (section 11 of
+// DESIGN.md).  Here a CTA takes one deal at a time and runs a whole block of traversals on it (`pairs_per_visit`,
+// thousands), exactly like the one-deal solver: the deal's enumerated tree, the frozen strategies of its infosets,
+// their cdfs and the private delta tables live in shared memory (mccfr_tree_traverse of ms_tree_walk.cuh does the
+// walking), and the HBM table is read once when the visit starts (one gather of the deal's <= 501 infoset lines) and
+// written once when it ends (REDs of the non-zero deltas and visit counts).  Random-line traffic per traversal drops
+// by three orders of magnitude.  Chance sampling is per visit: visit v plays deal
+// mulhi32(x0, D), x = Philox4x32-10(key = seed, ctr = (v lo, v hi, 1, "DEAL")); its traversals have the global
+// ids v * pairs_per_visit + i and use the same "MCCF" streams as everywhere else.
+//
+// Fresh 4+4-card deals all have the same tree SHAPE (levels of 1, 4, 16, 48, 144, 288, 576, 576, 576 nodes with 4, 4,
+// 3, 3, 2, 2, 1, 1 legal actions; node i of a level has children begin[L+1] + i * n_legal + a, a in legal_actions()
+// order), so a deal is described by: the local infoset index of each of its 501 multi-action nodes, the table slot,
+// action count and column permutation (legal order -> ascending card id) of each local infoset, and the 576
+// terminal rewards.  md_build_kernel derives that once per deal with the env's step() and claims the table slots.
+constexpr int MDB_NODES = 2229, MDB_MULTI = 501, MDB_LEAVES = 576, MDB_FIRST_LEAF = 1653, MDB_LOCAL = 512;
+constexpr int MDB_SLOTS = MDB_LOCAL + 2 * 576;      // + one private dummy slot per one-card node (levels 6, 7)
+__device__ __constant__ int c_mdb_begin[10] = {0, 1, 5, 21, 69, 213, 501, 1077, 1653, 2229};
+__device__ __constant__ int c_mdb_nl[9] = {4, 4, 3, 3, 2, 2, 1, 1, 0};
+
+struct MdDealInfo {
+    uint32_t local_slot[MDB_LOCAL];     // bits 0-29 table slot | 30-31 number of actions - 2
+    uint16_t node_local[MDB_LOCAL];     // nodes 0..500 -> local infoset index
+    uint8_t local_perm[MDB_LOCAL];      // 2 bits per legal action: its column (rank of the card id in the hand)
+    int8_t rx2[MDB_LEAVES];             // 2 * reward of player 0 at the 576 leaves
+    uint32_t n_local;
+    uint32_t pad[3];
+};
+static_assert(sizeof(MdDealInfo) % 16 == 0, "deal records are copied with 128-bit accesses");
+
+__global__ void __launch_bounds__(256) md_build_kernel(MdDev t, MdDealInfo* __restrict__ info) {
+    __shared__ uint4 lvl[2][576];
+    __shared__ unsigned long long hkey[1024];
+    __shared__ uint16_t hloc[1024];
+    __shared__ uint8_t hmeta[1024];          // perm of the infoset claimed at this hash position
+    __shared__ uint8_t hnl[1024];
+    __shared__ int part[257];
+    const int tid = threadIdx.x;
+    for (unsigned int deal = blockIdx.x; deal < t.n_deals; deal += gridDim.x) {
+        MdDealInfo* out = info + deal;
+        const uint32_t ho = t.hand_order[deal];
+        for (int i = tid; i < 1024; i += 256) hkey[i] = 0ull;
+        if (tid == 0) lvl[0][0] = t.roots[deal];
+        __syncthreads();
+        for (int L = 0; L < 8; L++) {
+            const uint4* cur = lvl[L & 1];
+            uint4* nxt = lvl[(L + 1) & 1];
+            const int W = c_mdb_begin[L + 1] - c_mdb_begin[L], nl = c_mdb_nl[L], pl = L & 1;
+            for (int i = tid; i < W; i += 256) {
+                const MsState s = cur[i];
+                uint32_t list;
+                legal_list(s, ho, pl, list);
+                if (L < 6) {
+                    const unsigned long long key = infoset_key(s, pl);
+                    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 54);
+                    while (true) {
+                        const unsigned long long k = atomicCAS(&hkey[h], 0ull, key);
+                        if (k == 0ull || k == key) break;
+                        h = (h + 1u) & 1023u;
+                    }
+                    uint32_t perm = 0u;
+                    for (int a = 0; a < nl; a++) perm |= (uint32_t)md_col(st_hand(s, pl), list, a) << (2 * a);
+                    hmeta[h] = (uint8_t)perm; hnl[h] = (uint8_t)nl;       // every node of an infoset writes the same
+                    out->node_local[c_mdb_begin[L] + i] = (uint16_t)h;    // hash position for now, local index below
+                }
+                for (int a = 0; a < nl; a++) {
+                    MsState c = s;
+                    step(c, (list >> (4 * a)) & 0xFu);
+                    nxt[i * nl + a] = c;
+                    if (L == 7) out->rx2[i * nl + a] = (int8_t)reward0_x2(c);
+                }
+            }
+            __syncthreads();
+        }
+        // hash positions -> dense local indices, in position order
+        int mine = 0;
+        for (int j = 0; j < 4; j++) mine += hkey[4 * tid + j] != 0ull;
+        part[tid + 1] = mine;
+        if (tid == 0) part[0] = 0;
+        __syncthreads();
+        if (tid == 0) for (int j = 1; j <= 256; j++) part[j] += part[j - 1];
+        __syncthreads();
+        int idx = part[tid];
+        uint32_t ins = 0u;
+        for (int j = 0; j < 4; j++) {
+            const int h = 4 * tid + j;
+            if (hkey[h] != 0ull) {
+                hloc[h] = (uint16_t)idx;
+                double unused[4];
+                const long long slot = md_find_regrets(t, hkey[h], unused, ins);     // claims the slot on first sight
+                out->local_slot[idx] = ((uint32_t)(slot < 0 ? 0 : slot) & 0x3FFFFFFFu) | ((uint32_t)(hnl[h] - 2) << 30);
+                out->local_perm[idx] = hmeta[h];
+                idx++;
+            }
+        }
+        if (ins) atomicAdd(&t.counters[3], (unsigned long long)ins);
+        if (tid == 0) out->n_local = (uint32_t)part[256];
+        __syncthreads();
+        for (int n = tid; n < MDB_MULTI; n += 256) out->node_local[n] = hloc[out->node_local[n]];
+        __syncthreads();
+    }
+}
+
+constexpr int MDB_THREADS = 1024, MDB_COPIES = 4, MDB_FRAMES = 3;
+
+__host__ __device__ inline size_t mdb_smem_bytes() {
+    return sizeof(double) * (7 + 4 * MDB_COPIES) * MDB_LOCAL + 4 * MDB_NODES + 4 * MDB_SLOTS + MDB_SLOTS +
+           sizeof(MdDealInfo) + (size_t)MDB_THREADS * MDB_FRAMES * (8 + 8 + 4 + 4 + 2) + 64;
+}
+
+__global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, const MdDealInfo* __restrict__ info, int player,
+                                                                  unsigned long long first_visit, long long n_visits,
+                                                                  int pairs_per_visit, uint2 pkey) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T = MDB_THREADS, SL = MDB_LOCAL;
+    const int tid = threadIdx.x;
+    double* sig = (double*)smem_raw;                       // [SL][4] frozen strategies, legal (= deal) order
+    double* cdf = sig + 4 * SL;                            // [SL][3]
+    double* dreg = cdf + 3 * SL;                           // MDB_COPIES x [SL][4], chosen by lane id
+    TreeFrames f;
+    f.ro = dreg + MDB_COPIES * 4 * SL;
+    f.sp = f.ro + T * MDB_FRAMES;
+    MdDealInfo* di = (MdDealInfo*)(f.sp + T * MDB_FRAMES);
+    f.meta = (uint32_t*)(di + 1);
+    f.cfv = f.meta + T * MDB_FRAMES;
+    uint32_t* tree = f.cfv + T * MDB_FRAMES;
+    uint32_t* dcnt = tree + MDB_NODES;
+    f.cb = (uint16_t*)(dcnt + MDB_SLOTS);
+    uint8_t* touched = (uint8_t*)(f.cb + T * MDB_FRAMES);
+
+    // the deal-independent part of the node records
+    for (int n = tid; n < MDB_NODES; n += T) {
+        int L = 0;
+        while (n >= c_mdb_begin[L + 1]) L++;
+        const int i = n - c_mdb_begin[L], nl = c_mdb_nl[L];
+        uint32_t rec;
+        if (L == 8) rec = TREE_TERMINAL << 12;
+        else rec = (uint32_t)(c_mdb_begin[L + 1] + i * nl) | ((uint32_t)nl << 23) | ((uint32_t)(L & 1) << 26) |
+                   ((uint32_t)(L >= 6 ? MDB_LOCAL + (n - MDB_MULTI) : 0) << 12);
+        tree[n] = rec;
+    }
+    MccfrShared sh{nullptr, nullptr, 0, sig, cdf, dreg + (size_t)(tid & (MDB_COPIES - 1)) * 4 * SL, dcnt, touched, nullptr, nullptr};
+    f.ro += tid; f.sp += tid; f.meta += tid; f.cfv += tid; f.cb += tid;
+    unsigned long long nu = 0, nv = 0, ns = 0;
+    const int flip = (tid >> 5) & 1;
+
+    for (long long vi = blockIdx.x; vi < n_visits; vi += gridDim.x) {
+        const unsigned long long visit = first_visit + (unsigned long long)vi;
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)visit, (uint32_t)(visit >> 32), 1u, MS_TAG_DEAL), pkey);
+        const uint32_t deal = __umulhi(x.x, t.n_deals);
+        __syncthreads();                                   // the previous visit is flushed
+        {   // stage the deal record
+            const uint4* src = (const uint4*)(info + deal);
+            uint4* dst = (uint4*)di;
+            for (int i = tid; i < (int)(sizeof(MdDealInfo) / 16); i += T) dst[i] = src[i];
+        }
+        for (int i = tid; i < MDB_COPIES * 4 * SL; i += T) dreg[i] = 0.0;
+        for (int i = tid; i < MDB_SLOTS; i += T) dcnt[i] = 0u;
+        __syncthreads();
+        const int n_local = (int)di->n_local;
+        for (int n = tid; n < MDB_MULTI; n += T) tree[n] = (tree[n] & ~(0x7FFu << 12)) | ((uint32_t)di->node_local[n] << 12);
+        for (int n = tid; n < MDB_LEAVES; n += T)
+            tree[MDB_FIRST_LEAF + n] = ((uint32_t)((int)di->rx2[n] + 2048) & 0xFFFu) | (TREE_TERMINAL << 12);
+        for (int j = tid; j < n_local; j += T) {           // gather: one table line per infoset of the deal
+            const uint32_t ls = di->local_slot[j];
+            const MdSlot* sl = t.slots + (ls & 0x3FFFFFFFu);
+            const int nl = (int)(ls >> 30) + 2;
+            const double2 r01 = __ldcg((const double2*)&sl->regret[0]), r23 = __ldcg((const double2*)&sl->regret[2]);
+            const double reg[4] = {r01.x, r01.y, r23.x, r23.y};
+            double sc[4], sg[4], cd[4];
+            md_regret_match(reg, nl, sc);                  // over the table's columns, like the apply step
+            const uint32_t perm = di->local_perm[j];
+#pragma unroll
+            for (int k = 0; k < 4; k++) sg[k] = (k < nl) ? md_pick(sc, (int)((perm >> (2 * k)) & 3u)) : 0.0;
+            strategy_cdf(sg, nl, cd);
+#pragma unroll
+            for (int k = 0; k < 4; k++) sig[4 * j + k] = sg[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) cdf[3 * j + k] = cd[k];
+        }
+        __syncthreads();
+        for (int k = tid; k < pairs_per_visit; k += T) {
+            const unsigned long long trav = visit * (unsigned long long)pairs_per_visit + (unsigned long long)k;
+            for (int j = 0; j < 2; j++) {
+                const int tp = j ^ flip;
+                if (player < 2 && tp != player) continue;
+                mccfr_tree_traverse<false>(tree, sh, tp, trav, pkey, f, T, nu, nv, ns);
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < n_local; j += T) {           // scatter: deltas and visit counts back to the table
+            const unsigned int cnt = dcnt[j];
+            if (cnt == 0u) continue;
+            const uint32_t ls = di->local_slot[j];
+            const long long slot = (long long)(ls & 0x3FFFFFFFu);
+            const int nl = (int)(ls >> 30) + 2;
+            const uint32_t perm = di->local_perm[j];
+            for (int k = 0; k < nl; k++) {
+                double v = dreg[4 * j + k];
+                for (int c = 1; c < MDB_COPIES; c++) v = __dadd_rn(v, dreg[(size_t)c * 4 * SL + 4 * j + k]);
+                if (v != 0.0) atomicAdd(&t.slots[slot].delta[(perm >> (2 * k)) & 3u], v);
+            }
+            atomicAdd(&t.slots[slot].cnt, cnt);
+            atomicOr(&t.dirty[slot >> 5], 1u << (slot & 31));
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        nu += __shfl_down_sync(0xffffffffu, nu, off);
+        nv += __shfl_down_sync(0xffffffffu, nv, off);
+        ns += __shfl_down_sync(0xffffffffu, ns, off);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&t.counters[0], nu); atomicAdd(&t.counters[1], nv); atomicAdd(&t.counters[2], ns); }
+}
+
 }  // namespace ms
 
 using namespace ms;
@@ -481,6 +700,7 @@ struct ms_mdsolver {
     int64_t n_deals;
     uint4* d_roots; uint32_t* d_hand_order;
     unsigned long long* d_counters;    // 5 counters + 1 export cursor
+    MdDealInfo* d_info;                // per-deal tree descriptions of the deal-blocked form (built on first use)
 };
 
 extern "C" {
@@ -523,6 +743,7 @@ int ms_md_create(const int64_t* d_seeds, int64_t n_deals, int32_t log2_capacity,
 void ms_md_destroy(ms_mdsolver* s) {
     if (!s) return;
     cudaFree(s->dev.slots); cudaFree(s->dev.dirty); cudaFree(s->d_roots); cudaFree(s->d_hand_order); cudaFree(s->d_counters);
+    cudaFree(s->d_info);
     delete s;
 }
 
@@ -531,6 +752,11 @@ int ms_md_reset(ms_mdsolver* s, void* stream) {
     MS_CUDA(cudaMemsetAsync(s->dev.slots, 0, ((size_t)1 << s->log2cap) * sizeof(MdSlot), (cudaStream_t)stream));
     MS_CUDA(cudaMemsetAsync(s->dev.dirty, 0, (((size_t)1 << s->log2cap) >> 5) * sizeof(unsigned int), (cudaStream_t)stream));
     MS_CUDA(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
+    if (s->d_info) {            // the deal descriptions name table slots: they die with the table's keys
+        MS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        MS_CUDA(cudaFree(s->d_info));
+        s->d_info = nullptr;
+    }
     return MS_OK;
 }
 
@@ -594,6 +820,28 @@ int ms_md_lookup(ms_mdsolver* s, const uint64_t* d_keys, int64_t n, double* d_re
     if (n == 0) return MS_OK;
     md_lookup_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         s->dev, (const unsigned long long*)d_keys, (long long)n, d_regret, d_strategy, d_found);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_md_mccfr_blocked(ms_mdsolver* s, int32_t player, int64_t first_visit, int64_t n_visits, int32_t pairs_per_visit,
+                        uint64_t philox_seed, void* stream) {
+    if (!s) return fail(MS_ERR_ARG, "ms_md_mccfr_blocked: NULL handle");
+    if (player < 0 || player > 2 || first_visit < 0 || n_visits < 0 || pairs_per_visit < 1 || pairs_per_visit > (1 << 24))
+        return fail(MS_ERR_ARG, "ms_md_mccfr_blocked: bad argument");
+    if (n_visits == 0) return MS_OK;
+    if (s->log2cap > 30) return fail(MS_ERR_ARG, "ms_md_mccfr_blocked: table slots must fit 30 bits");
+    if (!s->d_info) {                                      // describe every deal's tree once; claims the table slots
+        MS_CUDA(cudaMalloc(&s->d_info, (size_t)s->n_deals * sizeof(MdDealInfo)));
+        md_build_kernel<<<grid_for(s->n_deals * 256, 256, 4), 256, 0, (cudaStream_t)stream>>>(s->dev, s->d_info);
+        MS_LAUNCH_CHECK();
+    }
+    const int smem = (int)mdb_smem_bytes();
+    MS_CUDA(cudaFuncSetAttribute(md_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = (int)(n_visits < kNumSMs ? n_visits : kNumSMs);
+    md_blocked_kernel<<<grid, MDB_THREADS, smem, (cudaStream_t)stream>>>(
+        s->dev, s->d_info, player, (unsigned long long)first_visit, (long long)n_visits, pairs_per_visit,
+        make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)));
     MS_LAUNCH_CHECK();
     return MS_OK;
 }

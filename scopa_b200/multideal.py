@@ -90,6 +90,15 @@ class MultiDealSolver:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_md_mccfr_batch(self.h, player, n_trav, philox_seed, first_trav, self._stream()))
 
+    def mccfr_blocked(self, n_visits, pairs_per_visit=3072, philox_seed=0, first_visit=0, player=2):
+        """Deal-blocked form: each visit draws one deal and runs `pairs_per_visit` traversals on it entirely on chip
+        (the deal's tree and the strategies of its infosets staged in shared memory, deltas written back once).
+        Traversal ids are visit * pairs_per_visit + i.  The first call describes every deal's tree and creates all of
+        its multi-action infosets in the table."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_md_mccfr_blocked(self.h, player, first_visit, n_visits, pairs_per_visit, philox_seed,
+                                                    self._stream()))
+
     def apply(self):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_md_apply(self.h, self._stream()))

