@@ -68,6 +68,10 @@ int ms_debug_deal_slow_path(const int64_t* d_seeds, int64_t n, ms_state* d_state
  * [2] = global (L2-resident) fp64 RED/s.  The atomic roofline SURVEY 8(d) asks for. */
 int ms_debug_atomic_peaks(double h_out[3], void* stream);
 
+/* tuning hook: games per pipeline stage of the *_host rollout entry points (H2D / kernels / D2H of consecutive
+ * stages overlap).  games <= 0 restores the default.  Returns the value now in effect. */
+int64_t ms_debug_set_host_chunk(int64_t games);
+
 /* ms_step: MiniScopaEnv.step(action) on n independent states in place (src/envs/mini_scopa_game.py:140-167
  *   incl. play_card :93-104, card_in_table :66-91, evaluate_game :106-114).  d_rewards ([n][2] f32,
  *   may be NULL) receives the terminal rewards (0,0 while running); d_done ([n] u8, may be NULL)

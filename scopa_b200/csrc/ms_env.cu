@@ -28,9 +28,15 @@ char* last_error_buf() {
 // two words pass 2 starts from, then again in lock-step with pass 2, whose results are kept only for
 // the ~2x40 state words the first outputs depend on (output j of the first block needs words j, j+1 and
 // j+397).  About 1.5x the integer work, no memory traffic.  Pass 1 starts from init_genrand(19650218),
-// which does not depend on the seed: that table is computed once on the host and read through L1.
-__constant__ uint32_t g_mt_init[624];   // uniform index -> constant-cache operand, no load instruction in the chain
-constexpr int DEAL_WIN = 40;   // MT outputs available on the fast path (a shuffle needs 15 + rejections)
+// which does not depend on the seed: that table is computed once on the host, staged in shared memory by
+// every CTA and read with one 128-bit broadcast load per four chain steps (profiles/deal_variants.cu
+// measures the variants: the chain runs at the integer-ALU rate, 3 ALU + 2 multiplier-pipe instructions
+// per step).
+__constant__ uint32_t g_mt_init[624];
+// MT outputs available on the fast path.  A 16-card shuffle takes 19 draws on average (15 + rejections); the exact
+// tail (convolution of the 15 geometric laws) is P(> 40) = 3.2e-4, P(> 48) = 4e-6, P(> 64) = 2.9e-10.  A window of
+// 40 sent one warp in a hundred through the slow path below and doubled the kernel's time.
+constexpr int DEAL_WIN = 64;
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= (y >> 11);
@@ -62,21 +68,6 @@ __device__ __forceinline__ bool shuffle_deck(Gen& gen, unsigned long long& perm)
     return true;
 }
 
-struct MtWindow {          // first `win` outputs from the kept state words
-    const uint32_t* lo;    // mt[0 .. win]
-    const uint32_t* hi;    // mt[397 .. 397 + win - 1]
-    int kk;
-    int win;
-    __device__ __forceinline__ bool next(uint32_t& out) {
-        if (kk >= win) return false;
-        uint32_t y = (lo[kk] & 0x80000000u) | (lo[kk + 1] & 0x7fffffffu);
-        y = hi[kk] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        kk++;
-        out = mt_temper(y);
-        return true;
-    }
-};
-
 struct MtFull {            // textbook generator over a full 624-word state (slow path)
     uint32_t* mt;
     int kk;
@@ -100,7 +91,7 @@ struct MtFull {            // textbook generator over a full 624-word state (slo
     }
 };
 
-// Slow path (never taken in practice: needs > 25 rejected draws in one shuffle): the whole state in
+// Slow path (a shuffle that needs more than DEAL_WIN draws: 3 in 10^10 seeds): the whole state in
 // local memory, textbook init_by_array + generator.
 // textbook init_by_array over a full 624-word state (slow paths only)
 __device__ __noinline__ void mt_seed_full(uint32_t key0, uint32_t key1, uint32_t* mt) {
@@ -132,48 +123,99 @@ __device__ __noinline__ unsigned long long deal_slow(uint32_t key0, uint32_t key
 
 // random.seed(n) for the key words of |n|: fills lo[0 .. WIN + 1] = mt[0 .. WIN + 1] and hi[0 .. WIN - 1] =
 // mt[397 .. 397 + WIN - 1] of the seeded state (see the header comment: pass 1 is recomputed, not stored).
-template <int WIN>
-__device__ __forceinline__ void mt_seed_window(uint32_t key0, uint32_t key1, uint32_t* lo, uint32_t* hi) {
-    static_assert(WIN % 2 == 0 && WIN + 397 < 623, "window must be even and inside the first generator block");
-    const bool two = key1 != 0u;   // key length: 32-bit words of |seed|, at least one
-    const uint32_t kodd = two ? key1 + 1u : key0;   // key[j] + j for odd steps (j = 1) / one-word keys
+// T4 = the init_genrand(19650218) table in shared memory.  Word i is written by step k = i - 1 with key word
+// j = k % len, so even words take key[1] + 1 (or key[0] for one-word keys) and odd words key[0].
+#define MS_P1STEP(x, t, kw) (x) = ((t) ^ (((x) ^ ((x) >> 30)) * 1664525u)) + (kw)
+#define MS_P2STEP(y, p, i) (y) = ((p) ^ (((y) ^ ((y) >> 30)) * 1566083941u)) - (uint32_t)(i)
+#define MS_LOCK4(body)                                                   \
+    {                                                                    \
+        const uint4 t = T4[q];                                           \
+        const int i = 4 * q;                                             \
+        MS_P1STEP(p1, t.x, kodd); MS_P2STEP(p2, p1, i);     body(i)      \
+        MS_P1STEP(p1, t.y, key0); MS_P2STEP(p2, p1, i + 1); body(i + 1)  \
+        MS_P1STEP(p1, t.z, kodd); MS_P2STEP(p2, p1, i + 2); body(i + 2)  \
+        MS_P1STEP(p1, t.w, key0); MS_P2STEP(p2, p1, i + 3); body(i + 3)  \
+    }
+#define MS_KEEP_NONE(w)
+#define MS_KEEP_LO(w) if ((w) <= WIN + 1) lo[(w)] = p2;
+#define MS_KEEP_HI(w) if ((w) >= 397 && (w) < 397 + WIN) hi[(w) - 397] = p2;
 
-    // ---- pass 1, first run (nothing stored): step k writes word k+1 with key word j = k % len
-    // (unrolled so that the even/odd key word and the table offsets are compile-time operands)
-    uint32_t prev = (g_mt_init[1] ^ ((g_mt_init[0] ^ (g_mt_init[0] >> 30)) * 1664525u)) + key0;   // k = 0
+template <int WIN>
+__device__ __forceinline__ void mt_seed_window(const uint4* __restrict__ T4, uint32_t key0, uint32_t key1,
+                                               uint32_t* lo, uint32_t* hi) {
+    static_assert(WIN % 4 == 0 && WIN + 4 < 396 && 397 + WIN < 620, "window must be inside the first generator block");
+    const bool two = key1 != 0u;   // key length: 32-bit words of |seed|, at least one
+    const uint32_t kodd = two ? key1 + 1u : key0;   // key[j] + j for j = 1 / one-word keys
+
+    // ---- pass 1, first run (nothing stored)
+    const uint4 t0 = T4[0];
+    uint32_t prev = (t0.y ^ ((t0.x ^ (t0.x >> 30)) * 1664525u)) + key0;   // word 1
     const uint32_t first1 = prev;
-#pragma unroll 8
-    for (int k = 1; k < 623; k += 2) {
-        prev = (g_mt_init[k + 1] ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;      // odd k
-        prev = (g_mt_init[k + 2] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key0;      // even k
+    MS_P1STEP(prev, t0.z, kodd);
+    MS_P1STEP(prev, t0.w, key0);
+#pragma unroll 4
+    for (int q = 1; q < 156; q++) {
+        const uint4 t = T4[q];
+        MS_P1STEP(prev, t.x, kodd); MS_P1STEP(prev, t.y, key0); MS_P1STEP(prev, t.z, kodd); MS_P1STEP(prev, t.w, key0);
     }
     // step 624 wraps: mt[0] = mt[623]; word 1 is rewritten with j = 623 % len
     const uint32_t m1w = (first1 ^ ((prev ^ (prev >> 30)) * 1664525u)) + kodd;
 
-    // ---- pass 2 (i = 2..623, then the wrap to i = 1) in lock-step with a second run of pass 1
+    // ---- pass 2 (words 2..623, then the wrap to word 1) in lock-step with a second run of pass 1
     uint32_t p1 = first1, p2 = m1w;
-    auto lock_step = [&](int i, uint32_t kw) {
-        p1 = (g_mt_init[i] ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + kw;
-        p2 = (p1 ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)i;
-    };
-    // words 2..WIN and 397..397+WIN-1 are kept; the stretches between them are pure chain
+    MS_P1STEP(p1, t0.z, kodd); MS_P2STEP(p2, p1, 2); lo[2] = p2;
+    MS_P1STEP(p1, t0.w, key0); MS_P2STEP(p2, p1, 3); lo[3] = p2;
+    constexpr int Q_LO = (WIN + 2 + 3) / 4;       // groups 1 .. Q_LO - 1 hold the kept words 4 .. WIN + 1
+    constexpr int Q_HI = (397 + WIN + 3) / 4;     // groups 99 .. Q_HI - 1 hold the kept words 397 .. 397 + WIN - 1
 #pragma unroll 1
-    for (int i = 2; i <= WIN; i += 2) { lock_step(i, kodd); lo[i] = p2; lock_step(i + 1, key0); lo[i + 1] = p2; }
-    lock_step(WIN + 2, kodd);     // WIN + 1 was the last one stored above; continue the chain
-#pragma unroll 8
-    for (int i = WIN + 3; i < 397; i += 2) { lock_step(i, key0); lock_step(i + 1, kodd); }
+    for (int q = 1; q < Q_LO; q++) MS_LOCK4(MS_KEEP_LO)
+#pragma unroll 4
+    for (int q = Q_LO; q < 99; q++) MS_LOCK4(MS_KEEP_NONE)
 #pragma unroll 1
-    for (int i = 397; i < 397 + WIN; i += 2) { lock_step(i, key0); hi[i - 397] = p2; lock_step(i + 1, kodd); hi[i - 396] = p2; }
-#pragma unroll 8
-    for (int i = 397 + WIN; i < 623; i += 2) { lock_step(i, key0); lock_step(i + 1, kodd); }
-    lock_step(623, key0);
+    for (int q = 99; q < Q_HI; q++) MS_LOCK4(MS_KEEP_HI)
+#pragma unroll 4
+    for (int q = Q_HI; q < 156; q++) MS_LOCK4(MS_KEEP_NONE)
     lo[1] = (m1w ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - 1u;
     lo[0] = 0x80000000u;
+}
+
+__device__ __forceinline__ void stage_mt_table(uint4* T4) {
+    for (int i = threadIdx.x; i < 624; i += blockDim.x) ((uint32_t*)T4)[i] = g_mt_init[i];
+    __syncthreads();
+}
+
+// random.shuffle on the fast path.  The reference's loop is "for each position: draw until accepted"
+// (random.py: shuffle -> _randbelow_with_getrandbits).  Run in that order, a warp pays its worst lane's
+// rejections at EVERY position and the lanes read different outputs; here every lane looks at output kk
+// in the same iteration and either accepts it for its current position or not -- the same draws in the
+// same order per lane, uniform addressing, and a warp's trip count is its worst lane's TOTAL number of draws.
+// Returns false if the window ran dry.
+template <int WIN>
+__device__ __forceinline__ bool shuffle_deck_window(const uint32_t* lo, const uint32_t* hi, unsigned long long& perm) {
+    perm = 0xFEDCBA9876543210ull;   // nibble i = card id i (deck order, mini_scopa_game.py:26)
+    int i = 15;
+    uint32_t a = lo[0];
+    for (int kk = 0; kk < WIN && i >= 1; kk++) {
+        const uint32_t b = lo[kk + 1];
+        uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+        y = hi[kk] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        a = b;
+        const uint32_t nn = (uint32_t)i + 1u;
+        const uint32_t r = mt_temper(y) >> __clz(nn);   // getrandbits(nn.bit_length())
+        if (r < nn) {
+            const unsigned long long d = ((perm >> (4 * i)) ^ (perm >> (4 * r))) & 0xFull;
+            perm ^= (d << (4 * i)) | (d << (4 * r));
+            i--;
+        }
+    }
+    return i < 1;
 }
 
 __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__ seeds, long long n,
                                                    uint4* __restrict__ states, uint32_t* __restrict__ hand_order,
                                                    unsigned long long* __restrict__ deck, int zero_means_42) {
+    __shared__ uint4 T4[156];
+    stage_mt_table(T4);
     uint32_t lo[DEAL_WIN + 2], hi[DEAL_WIN];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
          g += (long long)gridDim.x * blockDim.x) {
@@ -181,10 +223,9 @@ __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__
         if (sd == 0 && zero_means_42) sd = 42;   // `seed or self.seed` (mini_scopa_game.py:132, default seed 42)
         unsigned long long a = sd < 0 ? (unsigned long long)(-(sd + 1)) + 1ull : (unsigned long long)sd;
         const uint32_t key0 = (uint32_t)a, key1 = (uint32_t)(a >> 32);
-        mt_seed_window<DEAL_WIN>(key0, key1, lo, hi);
-        MtWindow gen{lo, hi, 0, DEAL_WIN};
+        mt_seed_window<DEAL_WIN>(T4, key0, key1, lo, hi);
         unsigned long long perm;
-        if (!shuffle_deck(gen, perm)) perm = deal_slow(key0, key1);
+        if (!shuffle_deck_window<DEAL_WIN>(lo, hi, perm)) perm = deal_slow(key0, key1);
         const uint32_t ord = (uint32_t)perm;   // first 8 dealt cards: 4 to player 0, 4 to player 1
         uint32_t h0 = 0u, h1 = 0u;
 #pragma unroll
@@ -201,7 +242,7 @@ __global__ void __launch_bounds__(256) deal_kernel(const long long* __restrict__
 // ------------------------------------------------------------------------------------------------
 // 40-card deck: FullDeck(seed) = random.seed + random.shuffle of ids 0..39 (src/envs/full_scopa_game.py:32-35).
 // Packed as four 64-bit words, ten 6-bit card ids each (position p -> word p / 10, bits 6 * (p % 10)).
-constexpr int FULL_WIN = 128;   // a 40-card shuffle takes ~53 words on average (39 draws + rejections)
+constexpr int FULL_WIN = 128;   // a 40-card shuffle takes 60 draws on average (39 + rejections); P(> 128) = 8e-14
 
 struct Deck40 {
     unsigned long long w[4];
@@ -240,6 +281,31 @@ __device__ __forceinline__ bool shuffle_deck40(Gen& gen, Deck40& d) {
     return true;
 }
 
+// fast path: the same draws with the warp-uniform loop order of shuffle_deck_window
+__device__ __forceinline__ bool shuffle_deck40_window(const uint32_t* lo, const uint32_t* hi, Deck40& d) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        d.w[q] = 0ull;
+        for (int k = 0; k < 10; k++) d.w[q] |= (unsigned long long)(10 * q + k) << (6 * k);
+    }
+    int i = 39;
+    uint32_t a = lo[0];
+    for (int kk = 0; kk < FULL_WIN && i >= 1; kk++) {
+        const uint32_t b = lo[kk + 1];
+        uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+        y = hi[kk] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        a = b;
+        const uint32_t nn = (uint32_t)i + 1u;
+        const uint32_t r = mt_temper(y) >> __clz(nn);
+        if (r < nn) {
+            const uint32_t ci = d.get(i), cr = d.get((int)r);
+            d.set(i, cr); d.set((int)r, ci);
+            i--;
+        }
+    }
+    return i < 1;
+}
+
 __device__ __noinline__ void full_deck_slow(uint32_t key0, uint32_t key1, Deck40& d) {
     uint32_t mt[624];
     mt_seed_full(key0, key1, mt);
@@ -249,6 +315,8 @@ __device__ __noinline__ void full_deck_slow(uint32_t key0, uint32_t key1, Deck40
 
 __global__ void __launch_bounds__(128) full_deck_kernel(const long long* __restrict__ seeds, long long n,
                                                         ulonglong4* __restrict__ decks, int zero_means_42, int force_slow) {
+    __shared__ uint4 T4[156];
+    stage_mt_table(T4);
     uint32_t lo[FULL_WIN + 2], hi[FULL_WIN];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
          g += (long long)gridDim.x * blockDim.x) {
@@ -259,9 +327,8 @@ __global__ void __launch_bounds__(128) full_deck_kernel(const long long* __restr
         Deck40 d;
         bool ok = false;
         if (!force_slow) {
-            mt_seed_window<FULL_WIN>(key0, key1, lo, hi);
-            MtWindow gen{lo, hi, 0, FULL_WIN};
-            ok = shuffle_deck40(gen, d);
+            mt_seed_window<FULL_WIN>(T4, key0, key1, lo, hi);
+            ok = shuffle_deck40_window(lo, hi, d);
         }
         if (!ok) full_deck_slow(key0, key1, d);
         decks[g] = make_ulonglong4(d.w[0], d.w[1], d.w[2], d.w[3]);
@@ -468,6 +535,9 @@ static int scratch_get(size_t bytes, char** out, cudaStream_t* stream) {
     return MS_OK;
 }
 
+constexpr int64_t MS_HOST_CHUNK_DEFAULT = 262144;
+std::atomic<int64_t> g_host_chunk{MS_HOST_CHUNK_DEFAULT};   // games per pipeline stage of the *_host rollouts
+
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace ms
@@ -666,6 +736,11 @@ int ms_infoset_keys_host(const ms_state* h_states, int player, uint64_t* h_keys,
     return MS_OK;
 }
 
+int64_t ms_debug_set_host_chunk(int64_t games) {
+    g_host_chunk.store(games > 0 ? ((games + 127) / 128) * 128 : MS_HOST_CHUNK_DEFAULT);
+    return g_host_chunk.load();
+}
+
 int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_seed, uint64_t game_offset,
                            uint8_t* h_actions, float* h_rewards) {
     if (n < 0 || (n > 0 && !h_seeds)) return fail(MS_ERR_ARG, "ms_rollout_random_host: bad argument");
@@ -683,7 +758,7 @@ int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_se
     MS_CUDA(cudaGetDevice(&dev));
     for (int i = 0; i < 3; i++)
         if (!pipe[dev & 63][i]) MS_CUDA(cudaStreamCreateWithFlags(&pipe[dev & 63][i], cudaStreamNonBlocking));
-    const int64_t chunk = 262144;
+    const int64_t chunk = g_host_chunk.load();
     int c = 0;
     for (int64_t lo = 0; lo < n; lo += chunk, c++) {
         const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
