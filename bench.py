@@ -565,10 +565,17 @@ def run_ours(args):
         torch.cuda.synchronize()
         f_ms = sum(a.elapsed_time(c) for a, c in fev) / K
         h_seeds = np.arange(1, FG + 1, dtype=np.int64)
-        h_act, h_rew = np.zeros((FG, fs.PLIES), dtype=np.uint8), np.zeros((FG, 2), dtype=np.float32)
+        # e2e: seeds in pinned host memory -> deck + deal + 36-ply rollout on device -> actions + rewards in pinned host memory
+        p_seeds = torch.from_numpy(h_seeds).pin_memory()
+        p_act = torch.empty((FG, fs.PLIES), dtype=torch.uint8).pin_memory()
+        p_rew = torch.empty((FG, 2), dtype=torch.float32).pin_memory()
+        flib = _lib.load()
+        _lib.check(flib.ms_full_rollout_random_host(p_seeds.data_ptr(), FG, args.seed, 0, p_act.data_ptr(), p_rew.data_ptr()))
+        f_reps = max(3, min(K, 10))
         t0 = time.perf_counter()
-        _lib.check(_lib.load().ms_full_rollout_random_host(h_seeds.ctypes.data, FG, args.seed, 0, h_act.ctypes.data, h_rew.ctypes.data))
-        f_e2e = time.perf_counter() - t0
+        for i in range(f_reps):
+            _lib.check(flib.ms_full_rollout_random_host(p_seeds.data_ptr(), FG, args.seed + i, 0, p_act.data_ptr(), p_rew.data_ptr()))
+        f_e2e = (time.perf_counter() - t0) / f_reps
         cpu_full = None
         if world == 1 and not args.no_cpu:
             from oracle import ms_oracle as ora              # CPU leg: the checker timed as the baseline
@@ -581,7 +588,9 @@ def run_ours(args):
                         "sample": "200 000 games x 36 plies, OpenMP over all host threads"}
         full_obj = {"metric": "env_steps_per_sec", "unit": "env steps/s", "value": FG * fs.PLIES / (f_ms * 1e-3), "ms_per_step": f_ms,
                     "e2e": {"value": FG * fs.PLIES / f_e2e, "unit": "env steps/s", "h2d_bytes_per_step": 8 * FG,
-                            "d2h_bytes_per_step": (fs.PLIES + 8) * FG},
+                            "d2h_bytes_per_step": (fs.PLIES + 8) * FG,
+                            "what": "ms_full_rollout_random_host: FullDeck(seed) + deal + 36 plies per game, pinned host buffers in and out, "
+                                    "H2D / kernels / D2H pipelined over three streams"},
                     "roofline": {"bound": "hbm", "achieved": FG * fs.PLIES * 65.0 / (f_ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                                  "frac": FG * fs.PLIES * 65.0 / (f_ms * 1e-3) / 1e9 / hbm_gbs, "traffic": None,
                                  "kernel": "full_rollout_kernel", "peak_source": peak_src,

@@ -82,3 +82,20 @@ for chunk in ([0] if not has_chunk else [32768, 65536, 131072, 262144, 524288, 1
         lib.ms_debug_set_host_chunk(chunk)
     t = wall_time(lambda: rollout_random_host(h_seeds, 1, 0, h_act, h_rew))
     print(f"ms_rollout_random_host chunk {chunk:>8}: {t:.3f} ms = {8e-9 * G / (t * 1e-3):.2f} G env steps/s")
+
+# ---- 40-card game: FullDeck(seed) + deal + 36-ply rollout
+from scopa_b200 import full as fs  # noqa: E402
+
+p_act = torch.empty((G, fs.PLIES), dtype=torch.uint8).pin_memory()
+fb = fs.BatchedFullScopa(dev)
+t_fdeal = ev_time(lambda: fb.reset(d_seeds), reps=10)
+t_froll = ev_time(lambda: fb.rollout_random(philox_seed=1), reps=10)
+print(f"full deck + init kernels 1 M seeds : {t_fdeal:.3f} ms")
+print(f"full_rollout_kernel 1 M games      : {t_froll:.3f} ms")
+for chunk in ([0] if not has_chunk else [65536, 131072, 262144, 524288]):
+    if has_chunk:
+        lib.ms_debug_set_host_chunk(chunk)
+    t = wall_time(lambda: _lib.check(lib.ms_full_rollout_random_host(h_seeds.data_ptr(), G, 1, 0, p_act.data_ptr(), h_rew.data_ptr())), reps=10)
+    print(f"ms_full_rollout_random_host chunk {chunk:>8}: {t:.3f} ms = {36e-9 * G / (t * 1e-3):.2f} G env steps/s")
+if has_chunk:
+    lib.ms_debug_set_host_chunk(0)

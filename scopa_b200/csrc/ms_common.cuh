@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <mutex>
 
 #include "../../include/scopa_b200.h"
 
@@ -36,6 +37,15 @@ inline int fail(int code, const char* fmt, ...) {
             return ms::fail(MS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                  \
                             cudaGetErrorString(_e), __FILE__, __LINE__);                      \
     } while (0)
+
+// Plumbing of the *_host entry points (defined in ms_env.cu): one grow-only device scratch buffer per device,
+// guarded by g_scratch_mu for the duration of a call, three non-blocking streams so that the H2D copy of stage
+// c+1, the kernels of stage c and the D2H copy of stage c-1 overlap, and the stage size in games.
+extern std::mutex g_scratch_mu;
+int scratch_get(size_t bytes, char** out, cudaStream_t* stream);
+int host_pipe_streams(cudaStream_t out[3]);
+int64_t host_chunk();
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 constexpr int kNumSMs = 148;   // B200
 

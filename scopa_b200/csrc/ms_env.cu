@@ -516,9 +516,9 @@ struct Scratch {
     cudaStream_t stream = nullptr;
 };
 static Scratch g_scratch[64];
-static std::mutex g_scratch_mu;
+std::mutex g_scratch_mu;
 
-static int scratch_get(size_t bytes, char** out, cudaStream_t* stream) {
+int scratch_get(size_t bytes, char** out, cudaStream_t* stream) {
     int dev = 0;
     MS_CUDA(cudaGetDevice(&dev));
     Scratch& sc = g_scratch[dev & 63];
@@ -537,8 +537,18 @@ static int scratch_get(size_t bytes, char** out, cudaStream_t* stream) {
 
 constexpr int64_t MS_HOST_CHUNK_DEFAULT = 262144;
 std::atomic<int64_t> g_host_chunk{MS_HOST_CHUNK_DEFAULT};   // games per pipeline stage of the *_host rollouts
+int64_t host_chunk() { return g_host_chunk.load(); }
 
-static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+int host_pipe_streams(cudaStream_t out[3]) {
+    static cudaStream_t pipe[64][3] = {};
+    int dev = 0;
+    MS_CUDA(cudaGetDevice(&dev));
+    for (int i = 0; i < 3; i++) {
+        if (!pipe[dev & 63][i]) MS_CUDA(cudaStreamCreateWithFlags(&pipe[dev & 63][i], cudaStreamNonBlocking));
+        out[i] = pipe[dev & 63][i];
+    }
+    return MS_OK;
+}
 
 }  // namespace ms
 
@@ -753,16 +763,14 @@ int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_se
     if (rc) return rc;
     // Chunked over three streams so that the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of
     // chunk c-1 overlap (separate copy engines per direction); the chunks are 128-byte aligned slices.
-    static cudaStream_t pipe[64][3] = {};
-    int dev = 0;
-    MS_CUDA(cudaGetDevice(&dev));
-    for (int i = 0; i < 3; i++)
-        if (!pipe[dev & 63][i]) MS_CUDA(cudaStreamCreateWithFlags(&pipe[dev & 63][i], cudaStreamNonBlocking));
+    cudaStream_t pipe[3];
+    rc = host_pipe_streams(pipe);
+    if (rc) return rc;
     const int64_t chunk = g_host_chunk.load();
     int c = 0;
     for (int64_t lo = 0; lo < n; lo += chunk, c++) {
         const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
-        cudaStream_t st = pipe[dev & 63][c % 3];
+        cudaStream_t st = pipe[c % 3];
         MS_CUDA(cudaMemcpyAsync(d + o_seed + 8 * lo, h_seeds + lo, 8 * m, cudaMemcpyHostToDevice, st));
         rc = ms_deal_from_seeds((const int64_t*)(d + o_seed) + lo, m, (ms_state*)(d + o_st) + lo, (uint32_t*)(d + o_ho) + lo, st);
         if (rc) return rc;
@@ -772,7 +780,7 @@ int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_se
         if (h_actions) MS_CUDA(cudaMemcpyAsync(h_actions + 8 * lo, d + o_a + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, st));
         if (h_rewards) MS_CUDA(cudaMemcpyAsync(h_rewards + 2 * lo, d + o_r + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < 3; i++) MS_CUDA(cudaStreamSynchronize(pipe[dev & 63][i]));
+    for (int i = 0; i < 3; i++) MS_CUDA(cudaStreamSynchronize(pipe[i]));
     return MS_OK;
 }
 

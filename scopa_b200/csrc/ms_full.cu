@@ -512,17 +512,31 @@ int ms_full_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t phil
                                 uint8_t* h_actions, float* h_rewards) {
     if (n < 0 || (n > 0 && !h_seeds)) return fail(MS_ERR_ARG, "ms_full_rollout_random_host: bad argument");
     if (n == 0) return MS_OK;
-    char* d = nullptr;
-    const size_t o_s = 32 * (size_t)n, o_r = o_s + 32 * (size_t)n, o_k = o_r + 8 * (size_t)n, o_a = o_k + 8 * (size_t)n;
-    MS_CUDA(cudaMalloc(&d, o_a + 36 * (size_t)n));
-    MS_CUDA(cudaMemcpy(d + o_k, h_seeds, 8 * (size_t)n, cudaMemcpyHostToDevice));
-    int rc = ms_full_deal_from_seeds((const int64_t*)(d + o_k), n, (ms_full_state*)(d + o_s), (ms_full_deck*)d, nullptr);
-    if (!rc) rc = ms_full_rollout_random((const ms_full_state*)(d + o_s), (const ms_full_deck*)d, n, philox_seed, game_offset,
-                                         (uint8_t*)(d + o_a), (float*)(d + o_r), nullptr, nullptr);
-    if (rc) { cudaFree(d); return rc; }
-    if (h_actions) MS_CUDA(cudaMemcpy(h_actions, d + o_a, 36 * (size_t)n, cudaMemcpyDeviceToHost));
-    if (h_rewards) MS_CUDA(cudaMemcpy(h_rewards, d + o_r, 8 * (size_t)n, cudaMemcpyDeviceToHost));
-    MS_CUDA(cudaFree(d));
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    const size_t o_k = align256(32 * (size_t)n), o_s = align256(o_k + 8 * (size_t)n), o_r = align256(o_s + 32 * (size_t)n),
+                 o_a = align256(o_r + 8 * (size_t)n), tot = align256(o_a + 36 * (size_t)n);   // decks | seeds | states | rewards | actions
+    char* d; cudaStream_t st0;
+    int rc = scratch_get(tot, &d, &st0);
+    if (rc) return rc;
+    // same three-stream pipeline as ms_rollout_random_host: H2D of stage c+1, kernels of stage c, D2H of stage c-1
+    cudaStream_t pipe[3];
+    rc = host_pipe_streams(pipe);
+    if (rc) return rc;
+    const int64_t chunk = host_chunk();
+    int c = 0;
+    for (int64_t lo = 0; lo < n; lo += chunk, c++) {
+        const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
+        cudaStream_t st = pipe[c % 3];
+        MS_CUDA(cudaMemcpyAsync(d + o_k + 8 * lo, h_seeds + lo, 8 * m, cudaMemcpyHostToDevice, st));
+        rc = ms_full_deal_from_seeds((const int64_t*)(d + o_k) + lo, m, (ms_full_state*)(d + o_s) + lo, (ms_full_deck*)d + lo, st);
+        if (rc) return rc;
+        rc = ms_full_rollout_random((const ms_full_state*)(d + o_s) + lo, (const ms_full_deck*)d + lo, m, philox_seed,
+                                    game_offset + (uint64_t)lo, (uint8_t*)(d + o_a) + 36 * lo, (float*)(d + o_r) + 2 * lo, nullptr, st);
+        if (rc) return rc;
+        if (h_actions) MS_CUDA(cudaMemcpyAsync(h_actions + 36 * lo, d + o_a + 36 * lo, 36 * m, cudaMemcpyDeviceToHost, st));
+        if (h_rewards) MS_CUDA(cudaMemcpyAsync(h_rewards + 2 * lo, d + o_r + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 3; i++) MS_CUDA(cudaStreamSynchronize(pipe[i]));
     return MS_OK;
 }
 

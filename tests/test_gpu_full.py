@@ -124,6 +124,14 @@ def test_rollout_matches_oracle_at_scale():
     h_act, h_rew = np.zeros((1000, 36), dtype=np.uint8), np.zeros((1000, 2), dtype=np.float32)
     full._lib.check(full._lib.load().ms_full_rollout_random_host(seeds.ctypes.data, 1000, 77, 3, h_act.ctypes.data, h_rew.ctypes.data))
     assert np.array_equal(h_act, o_act[:1000]) and np.array_equal(h_rew, o_rew[:1000])
+    lib = full._lib.load()
+    try:                                                        # several pipeline stages, ragged last one
+        lib.ms_debug_set_host_chunk(384)
+        h_act[:], h_rew[:] = 0, 0
+        full._lib.check(lib.ms_full_rollout_random_host(seeds.ctypes.data, 1000, 77, 3, h_act.ctypes.data, h_rew.ctypes.data))
+        assert np.array_equal(h_act, o_act[:1000]) and np.array_equal(h_rew, o_rew[:1000])
+    finally:
+        lib.ms_debug_set_host_chunk(0)
 
 
 def test_game_helpers_on_device():
