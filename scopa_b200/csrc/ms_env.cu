@@ -281,13 +281,13 @@ __device__ __forceinline__ bool shuffle_deck40(Gen& gen, Deck40& d) {
     return true;
 }
 
-// fast path: the same draws with the warp-uniform loop order of shuffle_deck_window
-__device__ __forceinline__ bool shuffle_deck40_window(const uint32_t* lo, const uint32_t* hi, Deck40& d) {
+// fast path: the same draws with the warp-uniform loop order of shuffle_deck_window.  The deck being shuffled
+// lives in shared memory, one 32-bit word per card, column = thread (bank = lane: conflict-free whatever the
+// row), so a swap is two loads and two stores instead of select chains over four packed 64-bit registers.
+constexpr int FULL_DECK_THREADS = 128;
+__device__ __forceinline__ bool shuffle_deck40_window(const uint32_t* lo, const uint32_t* hi, uint32_t* col, Deck40& d) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        d.w[q] = 0ull;
-        for (int k = 0; k < 10; k++) d.w[q] |= (unsigned long long)(10 * q + k) << (6 * k);
-    }
+    for (int p = 0; p < 40; p++) col[p * FULL_DECK_THREADS] = (uint32_t)p;
     int i = 39;
     uint32_t a = lo[0];
     for (int kk = 0; kk < FULL_WIN && i >= 1; kk++) {
@@ -298,10 +298,18 @@ __device__ __forceinline__ bool shuffle_deck40_window(const uint32_t* lo, const 
         const uint32_t nn = (uint32_t)i + 1u;
         const uint32_t r = mt_temper(y) >> __clz(nn);
         if (r < nn) {
-            const uint32_t ci = d.get(i), cr = d.get((int)r);
-            d.set(i, cr); d.set((int)r, ci);
+            const uint32_t ci = col[i * FULL_DECK_THREADS], cr = col[r * FULL_DECK_THREADS];
+            col[i * FULL_DECK_THREADS] = cr;
+            col[r * FULL_DECK_THREADS] = ci;
             i--;
         }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        unsigned long long w = 0ull;
+#pragma unroll
+        for (int k = 0; k < 10; k++) w |= (unsigned long long)col[(10 * q + k) * FULL_DECK_THREADS] << (6 * k);
+        d.w[q] = w;
     }
     return i < 1;
 }
@@ -313,9 +321,10 @@ __device__ __noinline__ void full_deck_slow(uint32_t key0, uint32_t key1, Deck40
     shuffle_deck40(gen, d);
 }
 
-__global__ void __launch_bounds__(128) full_deck_kernel(const long long* __restrict__ seeds, long long n,
+__global__ void __launch_bounds__(FULL_DECK_THREADS) full_deck_kernel(const long long* __restrict__ seeds, long long n,
                                                         ulonglong4* __restrict__ decks, int zero_means_42, int force_slow) {
     __shared__ uint4 T4[156];
+    __shared__ uint32_t deck_s[40 * FULL_DECK_THREADS];
     stage_mt_table(T4);
     uint32_t lo[FULL_WIN + 2], hi[FULL_WIN];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n;
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(128) full_deck_kernel(const long long* __restr
         bool ok = false;
         if (!force_slow) {
             mt_seed_window<FULL_WIN>(T4, key0, key1, lo, hi);
-            ok = shuffle_deck40_window(lo, hi, d);
+            ok = shuffle_deck40_window(lo, hi, deck_s + threadIdx.x, d);
         }
         if (!ok) full_deck_slow(key0, key1, d);
         decks[g] = make_ulonglong4(d.w[0], d.w[1], d.w[2], d.w[3]);
@@ -590,7 +599,7 @@ namespace ms {
 int full_deck_from_seeds(const int64_t* d_seeds, int64_t n, void* d_decks, int zero_means_42, int force_slow, void* stream) {
     int rc = ensure_mt_table();
     if (rc) return rc;
-    full_deck_kernel<<<grid_for(n, 128, 8), 128, 0, (cudaStream_t)stream>>>(
+    full_deck_kernel<<<grid_for(n, FULL_DECK_THREADS, 8), FULL_DECK_THREADS, 0, (cudaStream_t)stream>>>(
         (const long long*)d_seeds, (long long)n, (ulonglong4*)d_decks, zero_means_42, force_slow);
     MS_LAUNCH_CHECK();
     return MS_OK;
