@@ -256,8 +256,9 @@ __device__ __forceinline__ bool fs_step(FsState& s, unsigned long long hc, uint3
     }
     const bool end_steps = fs_step_count(s) >= FS_MAX_STEPS;                     // safety limit (:286-290)
     if (end_cards || end_steps) {
-        fs_evaluate(s, false);
-        if (end_cards && end_steps) fs_evaluate(s, true);
+        const int reps = (end_cards && end_steps) ? 2 : 1;                       // one inlined copy of the scoring code
+#pragma unroll 1
+        for (int rep = 0; rep < reps; rep++) fs_evaluate(s, rep == 1);
     }
     s.w[5] ^= 1u << 29;                                                          // next agent (:293)
     return ok;
@@ -328,35 +329,30 @@ __global__ void __launch_bounds__(256) full_rollout_kernel(const uint4* __restri
         const FsDeck d = fs_load_deck(decks, g);
         const unsigned long long gid = game_offset + (unsigned long long)g;
         uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        uint32_t acts[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) acts[i] = 0u;
         bool ok = true;
         unsigned long long hc = fs_round_cards(s, d);
+        uint32_t* out = actions ? (uint32_t*)(actions + 36 * g) : nullptr;       // 36 bytes per game: 4-byte aligned
+        uint32_t packed = 0u;
+        // ONE step() site in a rolled loop: unrolled by four this kernel was 100 KB of SASS and its top stall was
+        // instruction fetch (profiles/README.md section 7)
 #pragma unroll 1
-        for (int blk = 0; blk < 9; blk++) {
-            x = philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)blk, MS_TAG_FULL), key);
-            uint32_t packed = 0u;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t xw = q == 0 ? x.x : (q == 1 ? x.y : (q == 2 ? x.z : x.w));
-                uint32_t list;
-                const uint32_t nl = fs_legal_list(s, hc, fs_cur(s), list);
-                const uint32_t a = nl ? (list >> (8u * __umulhi(xw, nl))) & 0xFFu : 0u;
-                const uint32_t round_before = fs_round(s);
-                ok &= fs_step(s, hc, a);
-                if (fs_round(s) != round_before) hc = fs_round_cards(s, d);      // a new hand was dealt
-                packed |= a << (8 * q);
+        for (int ply = 0; ply < 36; ply++) {
+            const int q = ply & 3;
+            if (q == 0) x = philox4x32_10(make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(ply >> 2), MS_TAG_FULL), key);
+            const uint32_t xw = q == 0 ? x.x : (q == 1 ? x.y : (q == 2 ? x.z : x.w));
+            uint32_t list;
+            const uint32_t nl = fs_legal_list(s, hc, fs_cur(s), list);
+            const uint32_t a = nl ? (list >> (8u * __umulhi(xw, nl))) & 0xFFu : 0u;
+            const uint32_t round_before = fs_round(s);
+            ok &= fs_step(s, hc, a);
+            if (fs_round(s) != round_before) hc = fs_round_cards(s, d);          // a new hand was dealt
+            packed |= a << (8 * q);
+            if (q == 3) {
+                if (out) out[ply >> 2] = packed;
+                packed = 0u;
             }
-#pragma unroll
-            for (int i = 0; i < 9; i++) if (i == blk) acts[i] = packed;
         }
         if (!ok) *overflow = 1u;
-        if (actions) {
-            uint32_t* out = (uint32_t*)(actions + 36 * g);       // 36 bytes per game: 4-byte aligned
-#pragma unroll
-            for (int i = 0; i < 9; i++) out[i] = acts[i];
-        }
         if (rewards) {
             const float r0 = fs_terminal(s) ? 0.5f * (float)fs_score_diff(s) : 0.f;
             rewards[g] = make_float2(r0, 0.f - r0);
