@@ -120,25 +120,40 @@ __device__ __forceinline__ uint32_t fs_legal_list(const FsState& s, unsigned lon
     return n ? n : 1u;
 }
 
-// find_capture_combinations(card)[0] as a mask over table positions (0 = the card is placed)
-__device__ __forceinline__ uint32_t fs_capture_mask(unsigned long long lo, unsigned long long hi, uint32_t len, uint32_t card) {
+// find_capture_combinations(card)[0] as a mask over table positions (0 = the card is placed).
+// `scr` = this thread's column of a shared-memory scratch array, FS_THREADS apart, FS_MAX_TABLE entries:
+// entry i = (reachable-sum bitset of the i oldest cards) | (rank of card i) << 11.  The first version kept the
+// prefix bitsets in a local-memory array and fetched every table card with a variable 64-bit shift; its capture
+// (profiles/README.md section 7) put a quarter of the kernel's instructions on those two lines, at 12 of 32 lanes
+// (the loops ran to each lane's own table length).  Here the table slides through a register six bits at a time,
+// the loops run to a bound shared by the converged lanes, and the backtrack is one shared-memory load per card.
+constexpr int FS_THREADS = 256;
+__device__ __forceinline__ uint32_t fs_capture_mask(unsigned long long lo, unsigned long long hi, uint32_t len, uint32_t card,
+                                                    uint16_t* scr) {
     const uint32_t target = fs_rank(card);
-    uint16_t reach[FS_MAX_TABLE + 1];        // reach[i]: bit v set <=> some subset of the i oldest cards sums to v
-    uint32_t r = 1u, first_equal = 0xFFu;
-    reach[0] = 1;
-    for (uint32_t i = 0; i < len; i++) {
-        const uint32_t ri = fs_rank(fs_table_card(lo, hi, (int)i));
-        if (ri == target && first_equal == 0xFFu) first_equal = i;
-        r = (r | (r << ri)) & 0x7FFu;
-        reach[i + 1] = (uint16_t)r;
+    const uint32_t bound = __reduce_max_sync(__activemask(), len);
+    uint32_t r = 1u, first_equal = 0xFFu;       // r: bit v set <=> some subset of the cards seen so far sums to v
+    unsigned long long cur = lo;
+    for (uint32_t i = 0; i < bound; i++) {
+        if (i == 10u) cur = hi;
+        const uint32_t ri = fs_rank((uint32_t)cur & 0x3Fu);
+        cur >>= 6;
+        scr[i * FS_THREADS] = (uint16_t)(r | (ri << 11));
+        if (i < len) {
+            if (ri == target && first_equal == 0xFFu) first_equal = i;
+            r = (r | (r << ri)) & 0x7FFu;
+        }
     }
     if (first_equal != 0xFFu) return 1u << first_equal;              // exact rank match has priority (:107-110)
-    if (!((r >> target) & 1u)) return 0u;
-    uint32_t m = 0u, t = target;
-    for (int i = (int)len - 1; i >= 0 && t > 0u; i--) {              // smallest mask: take card i only when it is needed
-        if (!((reach[i] >> t) & 1u)) {
-            m |= 1u << i;
-            t -= fs_rank(fs_table_card(lo, hi, i));
+    uint32_t t = ((r >> target) & 1u) ? target : 0u;
+    uint32_t m = 0u;
+    if (__any_sync(__activemask(), t > 0u)) {
+        for (int i = (int)bound - 1; i >= 0; i--) {                  // smallest mask: take card i only when it is needed
+            const uint32_t e = scr[i * FS_THREADS];
+            if ((uint32_t)i < len && t > 0u && !((e >> t) & 1u)) {
+                m |= 1u << i;
+                t -= e >> 11;
+            }
         }
     }
     return m;
@@ -206,7 +221,7 @@ __device__ __forceinline__ int fs_score_diff(const FsState& s) { return (int)(in
 // outside 0..39, which raises IndexError in the reference) is a silent pass that still advances step_count and the
 // turn; a step on a finished game is a no-op (:253-255).  Returns false if the table outgrew the packed state.
 // `hc` = fs_round_cards() of the state's round (stale once the step has dealt a new round).
-__device__ __forceinline__ bool fs_step(FsState& s, unsigned long long hc, uint32_t action) {
+__device__ __forceinline__ bool fs_step(FsState& s, unsigned long long hc, uint32_t action, uint16_t* scr) {
     if (fs_terminal(s)) return true;
     const int p = fs_cur(s);
     const uint32_t bits = fs_hand_bits(s, p);
@@ -218,7 +233,7 @@ __device__ __forceinline__ bool fs_step(FsState& s, unsigned long long hc, uint3
     if (hp >= 0) {
         unsigned long long lo = fs_tlo(s), hi = fs_thi(s);
         uint32_t len = fs_table_len(s);
-        uint32_t m = fs_capture_mask(lo, hi, len, action);
+        uint32_t m = fs_capture_mask(lo, hi, len, action, scr);
         if (m) {
             unsigned long long taken = 1ull << action;
             while (m) {                                   // captured positions, highest first
@@ -269,13 +284,14 @@ __global__ void __launch_bounds__(256) full_init_kernel(const ulonglong4* __rest
         fs_store(states, g, fs_initial(fs_load_deck(decks, g)));
 }
 
-__global__ void __launch_bounds__(256) full_step_kernel(uint4* __restrict__ states, const ulonglong4* __restrict__ decks,
+__global__ void __launch_bounds__(FS_THREADS) full_step_kernel(uint4* __restrict__ states, const ulonglong4* __restrict__ decks,
                                                         const uint8_t* __restrict__ actions, float2* __restrict__ rewards,
                                                         uint8_t* __restrict__ done, long long n, unsigned int* overflow) {
+    __shared__ uint16_t scratch[FS_MAX_TABLE * FS_THREADS];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
         FsState s = fs_load(states, g);
         const FsDeck d = fs_load_deck(decks, g);
-        if (!fs_step(s, fs_round_cards(s, d), actions[g])) *overflow = 1u;
+        if (!fs_step(s, fs_round_cards(s, d), actions[g], scratch + threadIdx.x)) *overflow = 1u;
         fs_store(states, g, s);
         const bool t = fs_terminal(s);
         if (rewards) {
@@ -320,10 +336,11 @@ __global__ void __launch_bounds__(256) full_evaluate_kernel(uint4* __restrict__ 
 
 // n random-policy games played to the end (36 plies) in one launch; "FULL" Philox stream:
 // ctr = (game id lo, hi, ply / 4, tag), word ply % 4, action = legal[mulhi32(x, n_legal)].
-__global__ void __launch_bounds__(256) full_rollout_kernel(const uint4* __restrict__ states, const ulonglong4* __restrict__ decks,
+__global__ void __launch_bounds__(FS_THREADS) full_rollout_kernel(const uint4* __restrict__ states, const ulonglong4* __restrict__ decks,
                                                            long long n, uint2 key, unsigned long long game_offset,
                                                            uint8_t* __restrict__ actions, float2* __restrict__ rewards,
                                                            uint4* __restrict__ final_states, unsigned int* overflow) {
+    __shared__ uint16_t scratch[FS_MAX_TABLE * FS_THREADS];
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
         FsState s = fs_load(states, g);
         const FsDeck d = fs_load_deck(decks, g);
@@ -344,7 +361,7 @@ __global__ void __launch_bounds__(256) full_rollout_kernel(const uint4* __restri
             const uint32_t nl = fs_legal_list(s, hc, fs_cur(s), list);
             const uint32_t a = nl ? (list >> (8u * __umulhi(xw, nl))) & 0xFFu : 0u;
             const uint32_t round_before = fs_round(s);
-            ok &= fs_step(s, hc, a);
+            ok &= fs_step(s, hc, a, scratch + threadIdx.x);
             if (fs_round(s) != round_before) hc = fs_round_cards(s, d);          // a new hand was dealt
             packed |= a << (8 * q);
             if (q == 3) {
@@ -409,7 +426,7 @@ int ms_full_step(ms_full_state* d_states, const ms_full_deck* d_decks, const uin
     unsigned int* ov;
     int rc = full_overflow_flag(&ov);
     if (rc) return rc;
-    full_step_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((uint4*)d_states, (const ulonglong4*)d_decks, d_actions,
+    full_step_kernel<<<grid_for(n, FS_THREADS, 8), FS_THREADS, 0, (cudaStream_t)stream>>>((uint4*)d_states, (const ulonglong4*)d_decks, d_actions,
                                                                            (float2*)d_rewards, d_done, (long long)n, ov);
     MS_LAUNCH_CHECK();
     return MS_OK;
@@ -432,7 +449,7 @@ int ms_full_rollout_random(const ms_full_state* d_states, const ms_full_deck* d_
     unsigned int* ov;
     int rc = full_overflow_flag(&ov);
     if (rc) return rc;
-    full_rollout_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    full_rollout_kernel<<<grid_for(n, FS_THREADS, 8), FS_THREADS, 0, (cudaStream_t)stream>>>(
         (const uint4*)d_states, (const ulonglong4*)d_decks, (long long)n, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
         (unsigned long long)game_offset, d_actions, (float2*)d_rewards, (uint4*)d_final, ov);
     MS_LAUNCH_CHECK();
