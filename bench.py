@@ -341,7 +341,7 @@ def run_ours(args):
             csv_ = Solver(seed=42, device=dev)
             done, pts, Bc = 0, [], 4096
             t0 = time.perf_counter()
-            for target in (10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7):
+            for target in [t for t in (10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7) if t <= args.curve_max]:
                 while done < target:
                     csv_.mccfr_batch(2, Bc, philox_seed=args.seed, first_trav=done, mode=mode_id)
                     csv_.mccfr_apply()
@@ -805,12 +805,14 @@ def main():
     ap.add_argument("--trav", type=int, default=454656,
                     help="traversals per player per GPU per step (default: 3 full waves of 148 CTAs x 1024 threads)")
     ap.add_argument("--games", type=int, default=1_000_000, help="concurrent games per GPU")
-    ap.add_argument("--sd-trav", type=int, default=16384, help="SDCFR traversals per player per GPU per step")
+    ap.add_argument("--sd-trav", type=int, default=65536, help="SDCFR traversals per player per GPU per step")
     ap.add_argument("--step-states", type=int, default=16_000_000, help="states in the step-granular API measurement")
     ap.add_argument("--full-games", type=int, default=1_000_000, help="concurrent 40-card Scopa games (0 = skip)")
     ap.add_argument("--md-deals", type=int, default=65536, help="deals in the multi-deal MCCFR section (0 = skip)")
     ap.add_argument("--md-log2-capacity", type=int, default=26, help="multi-deal table slots (128 B each)")
     ap.add_argument("--md-trav", type=int, default=340992, help="traversal pairs per multi-deal step")
+    ap.add_argument("--curve-max", type=int, default=10 ** 7,
+                    help="last point of the exploitability-vs-traversals curves (traversals per player; 0 = skip the curves)")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],

@@ -468,46 +468,86 @@ __global__ void __launch_bounds__(256) sd_terminal_kernel(SdArgs a) {
 
 // Backward level d: traverser nodes combine their children's values, form the regret target and emit a
 // sample (deep_cfr.py:321-346, :70-75); opponent nodes pass the sampled child's value up.
+// A sample is 66 floats (34 features, 16 targets, 16 mask entries) in three row-major arrays.  Written by the
+// thread that owns the node, every store instruction of a warp touched 32 different rows (32 partial sectors):
+// the launch list showed these kernels at 0.6 TB/s and 44 % of a traversal.  The rows of a warp are staged in
+// shared memory instead and written out by the whole warp, consecutive lanes on consecutive floats.
 __global__ void __launch_bounds__(256) sd_backward_kernel(SdArgs a, int d) {
+    __shared__ float stage[8][32 * 35];
+    __shared__ long long slot_s[8][32];
     const int cp = d & 1;
     const bool trav = (cp == a.sh.player);
     const long long total = a.n_trav * a.sh.n[d];
     const int f = a.sh.f[d], nd = a.sh.n[d];
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-        if (!trav) { a.lvl[d].value[g] = a.lvl[d + 1].value[g]; continue; }
-        const MsState s = a.lvl[d].state[g];
-        uint32_t list;
-        legal_list(s, a.hand_order, cp, list);
-        const float4 p4 = a.lvl[d].pol[g];
-        const float pl[4] = {p4.x, p4.y, p4.z, p4.w};
-        float value = 0.f, cfv[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) cfv[i] = 0.f;
+    if (!trav) {
+        for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x)
+            a.lvl[d].value[g] = a.lvl[d + 1].value[g];
+        return;
+    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* st = stage[wib];
+    long long* sl = slot_s[wib];
+    for (long long base = blockIdx.x * (long long)blockDim.x + 32 * wib; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long g = base + lane;
+        const bool valid = g < total;
+        const int nrows = (int)((total - base) < 32 ? (total - base) : 32);
+        float x[SD_IN], reg[16];
         uint32_t lm = 0u;
-        for (int i = 0; i < f; i++) {
-            const uint32_t act = (list >> (4 * i)) & 0xFu;
-            const float av = a.lvl[d + 1].value[g * f + i];
-            value += pl[i] * av;
-            cfv[act] = av;
-            lm |= 1u << act;
-        }
-        a.lvl[d].value[g] = value;
-        float reg[16], mx = 0.f;
+        long long slot = 0;
+        if (valid) {
+            const MsState s = a.lvl[d].state[g];
+            uint32_t list;
+            legal_list(s, a.hand_order, cp, list);
+            const float4 p4 = a.lvl[d].pol[g];
+            const float pl[4] = {p4.x, p4.y, p4.z, p4.w};
+            float value = 0.f, cfv[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) { reg[i] = cfv[i] - value; mx = fmaxf(mx, fabsf(reg[i])); }
-        if (mx > 0.f) {
-            const float dn = mx + 1e-8f;
+            for (int i = 0; i < 16; i++) cfv[i] = 0.f;
+            for (int i = 0; i < f; i++) {
+                const uint32_t act = (list >> (4 * i)) & 0xFu;
+                const float av = a.lvl[d + 1].value[g * f + i];
+                value += pl[i] * av;
+                cfv[act] = av;
+                lm |= 1u << act;
+            }
+            a.lvl[d].value[g] = value;
+            float mx = 0.f;
 #pragma unroll
-            for (int i = 0; i < 16; i++) reg[i] = reg[i] / dn;
+            for (int i = 0; i < 16; i++) { reg[i] = cfv[i] - value; mx = fmaxf(mx, fabsf(reg[i])); }
+            if (mx > 0.f) {
+                const float dn = mx + 1e-8f;
+#pragma unroll
+                for (int i = 0; i < 16; i++) reg[i] = reg[i] / dn;
+            }
+            const long long t = g / nd, j = g % nd;
+            slot = t * a.sh.samples + a.sh.sample_off[d] + j;
+            sd_features(s, cp, x);
         }
-        const long long t = g / nd, j = g % nd;
-        const long long slot = t * a.sh.samples + a.sh.sample_off[d] + j;
-        float x[SD_IN];
-        sd_features(s, cp, x);
-        for (int i = 0; i < SD_IN; i++) a.out_feat[slot * SD_IN + i] = x[i];
-        for (int i = 0; i < 16; i++) {
-            a.out_target[slot * 16 + i] = reg[i];
-            a.out_mask[slot * 16 + i] = (float)((lm >> i) & 1u);
+        __syncwarp();                       // the previous iteration's readers are done with the stage
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < SD_IN; i++) st[lane * 35 + i] = x[i];
+            sl[lane] = slot;
+        }
+        __syncwarp();
+        for (int e = lane; e < nrows * SD_IN; e += 32) {
+            const int r = e / SD_IN, c = e - r * SD_IN;
+            a.out_feat[sl[r] * SD_IN + c] = st[r * 35 + c];
+        }
+        __syncwarp();
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                st[lane * 33 + i] = reg[i];
+                st[lane * 33 + 16 + i] = (float)((lm >> i) & 1u);
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < nrows * 16; e += 32) {
+            const int r = e >> 4, c = e & 15;
+            const long long o = sl[r] * 16 + c;
+            a.out_target[o] = st[r * 33 + c];
+            a.out_mask[o] = st[r * 33 + 16 + c];
         }
     }
 }
