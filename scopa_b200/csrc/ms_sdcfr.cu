@@ -194,6 +194,22 @@ __device__ __forceinline__ void sd_tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive columns in one instruction: half the load -> wait round trips of the hidden-layer epilogues
+__device__ __forceinline__ void sd_tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
 // builds the shared-memory image of a net (bf16, canonical layout) in global memory, once per call
 __global__ void __launch_bounds__(256) sd_prep_kernel(const float* __restrict__ net, unsigned char* __restrict__ img) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
@@ -294,22 +310,31 @@ __device__ __forceinline__ void mlp_tc(const SdSmemTc& sm, const float* x, float
         sd_store8(sm, tid, k0, SD_K1, v);
     }
     sd_layer_mma(sm, sm.w1, SD_K1, SD_H1, SD_TM_D1, phase);
-    for (int c = 0; c < SD_H1; c += 16) {
-        float v[16];
-        sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D1 + c, v);
+    const float4* bias4 = (const float4*)sm.bias;                  // 16-byte aligned inside the weight image
+    for (int c = 0; c < SD_H1; c += 32) {
+        float v[32];
+        sd_tmem_ld32(*sm.tmem_base + lane_base + SD_TM_D1 + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; i++) { const float h = v[i] + sm.bias[c + i]; v[i] = h > 0.f ? h : 0.f; }
-        sd_store8(sm, tid, c, SD_H1, v);
-        sd_store8(sm, tid, c + 8, SD_H1, v + 8);
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = bias4[(c + i) >> 2];
+            v[i] = fmaxf(v[i] + b.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b.y, 0.f);
+            v[i + 2] = fmaxf(v[i + 2] + b.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b.w, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) sd_store8(sm, tid, c + i, SD_H1, v + i);
     }
     sd_layer_mma(sm, sm.w2, SD_H1, SD_H2, SD_TM_D2, phase);
-    for (int c = 0; c < SD_H2; c += 16) {
-        float v[16];
-        sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D2 + c, v);
+    for (int c = 0; c < SD_H2; c += 32) {
+        float v[32];
+        sd_tmem_ld32(*sm.tmem_base + lane_base + SD_TM_D2 + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; i++) { const float h = v[i] + sm.bias[128 + c + i]; v[i] = h > 0.f ? h : 0.f; }
-        sd_store8(sm, tid, c, SD_H2, v);
-        sd_store8(sm, tid, c + 8, SD_H2, v + 8);
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = bias4[(128 + c + i) >> 2];
+            v[i] = fmaxf(v[i] + b.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b.y, 0.f);
+            v[i + 2] = fmaxf(v[i + 2] + b.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b.w, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) sd_store8(sm, tid, c + i, SD_H2, v + i);
     }
     sd_layer_mma(sm, sm.w3, SD_H2, SD_OUT, SD_TM_D3, phase);
     float v[16];
@@ -331,8 +356,10 @@ __device__ __forceinline__ void sd_policy(const float* raw, uint32_t legal_mask,
         z += pos;
     }
     if (z < 1e-8f) z = 1e-8f;
+    // 0 / z is exactly 0, but a zero numerator sends the IEEE division into its special-case subroutine: with 12+
+    // of the 16 slots illegal that subroutine was 15 % of the forward kernel's instructions (profiles/README.md 3)
 #pragma unroll
-    for (int i = 0; i < 16; i++) pol[i] = pol[i] / z;
+    for (int i = 0; i < 16; i++) pol[i] = pol[i] > 0.f ? pol[i] / z : 0.f;
 }
 
 template <int PREC>
@@ -421,7 +448,7 @@ __global__ void __launch_bounds__(SD_TILE, SD_CTAS_PER_SM) sd_forward_kernel(SdA
             if (sum == 0.f) ai = __umulhi(w0, nl);                    // np.random.choice(legal_actions)
             else {
                 double cdf[4], acc = 0.0;
-                for (uint32_t i = 0; i < 4; i++) { if (i < nl) acc = __dadd_rn(acc, (double)(ap[i] / sum)); cdf[i] = acc; }
+                for (uint32_t i = 0; i < 4; i++) { if (i < nl) acc = __dadd_rn(acc, (double)(ap[i] > 0.f ? ap[i] / sum : 0.f)); cdf[i] = acc; }
                 const double last = acc, u = u53(w0, w1);
                 ai = 0u;
                 for (uint32_t i = 0; i < nl; i++) if (__ddiv_rn(cdf[i], last) <= u) ai++;
@@ -517,7 +544,7 @@ __global__ void __launch_bounds__(256) sd_backward_kernel(SdArgs a, int d) {
             if (mx > 0.f) {
                 const float dn = mx + 1e-8f;
 #pragma unroll
-                for (int i = 0; i < 16; i++) reg[i] = reg[i] / dn;
+                for (int i = 0; i < 16; i++) reg[i] = reg[i] != 0.f ? reg[i] / dn : reg[i];
             }
             const long long t = g / nd, j = g % nd;
             slot = t * a.sh.samples + a.sh.sample_off[d] + j;
