@@ -124,7 +124,13 @@ constexpr int SD_K1 = 48;                        // 34 padded to a multiple of 1
 // TMEM: 128 columns per CTA.  The three accumulators reuse the same columns: an accumulator is fully
 // read back (and a CTA barrier passed) before the next layer's MMA is issued.
 constexpr uint32_t SD_TM_COLS = 128, SD_TM_D1 = 0, SD_TM_D2 = 0, SD_TM_D3 = 0;
-constexpr int SD_CTAS_PER_SM = 3;
+// A CTA of the tensor-core path is TWO warpgroups, each working on its own 128-row tile with its own A buffer,
+// mbarrier and 128 TMEM columns, sharing one copy of the weight image: 96 KB of shared memory per CTA, two CTAs
+// per SM = four tiles in flight per SM (one tile per CTA allowed three: the kernel is bound by the per-tile
+// dependency chain, so tiles in flight are what count).  The warpgroups never meet inside the tile loop: they
+// synchronise on named barriers (id 1 + warpgroup, 128 threads).
+constexpr int SD_TC_WG = 2, SD_TC_THREADS = SD_TC_WG * SD_TILE, SD_TC_CTAS_PER_SM = 2;
+constexpr int SD_CTAS_PER_SM = 3;   // fp32 path launch bound (its shared memory allows one)
 // bf16 operand image of one net, as it sits in shared memory (built once per call by sd_prep_kernel):
 // w1 [128 x 48] | w2 [64 x 128] | w3 [16 x 64] in the UMMA canonical layout, then the fp32 biases
 constexpr int SD_IMG_W1 = 0, SD_IMG_W2 = SD_IMG_W1 + 2 * 128 * 48, SD_IMG_W3 = SD_IMG_W2 + 2 * 64 * 128,
@@ -138,8 +144,14 @@ struct SdSmemTc {
     float* bias;           // b1 | b2 | b3
     unsigned long long* bar;
     uint32_t* tmem_base;
+    uint32_t tm_off;       // this warpgroup's first TMEM column
+    int wg;                // warpgroup index inside the CTA
 };
-constexpr size_t SD_SMEM_TC = 2 * 128 * 128 + SD_IMG_BYTES + 64 + 1024;
+constexpr size_t SD_SMEM_TC = SD_TC_WG * 2 * 128 * 128 + SD_IMG_BYTES + 64 + 1024;
+
+__device__ __forceinline__ void sd_wg_sync(int wg) {
+    asm volatile("bar.sync %0, 128;\n" :: "r"(1 + wg) : "memory");
+}
 
 // canonical K-major no-swizzle tile with `rows` rows and K elements: core matrix (8 rows x 8 k) = 128 B;
 // K-adjacent core matrices are contiguous (LBO = 128 B), 8-row groups are K/8 core matrices apart
@@ -234,22 +246,26 @@ __global__ void __launch_bounds__(256) sd_prep_kernel(const float* __restrict__ 
 __device__ __forceinline__ SdSmemTc sd_carve_tc(unsigned char* raw, const unsigned char* img) {
     SdSmemTc sm;
     unsigned char* p = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
-    sm.a = (__nv_bfloat16*)p; p += 2 * 128 * 128;
+    sm.wg = threadIdx.x >> 7;
+    sm.tm_off = (uint32_t)sm.wg * SD_TM_COLS;
+    sm.a = (__nv_bfloat16*)(p + sm.wg * 2 * 128 * 128); p += SD_TC_WG * 2 * 128 * 128;
     unsigned char* wimg = p;
     sm.w1 = (__nv_bfloat16*)(p + SD_IMG_W1);
     sm.w2 = (__nv_bfloat16*)(p + SD_IMG_W2);
     sm.w3 = (__nv_bfloat16*)(p + SD_IMG_W3);
     sm.bias = (float*)(p + SD_IMG_BIAS); p += SD_IMG_BYTES;
-    sm.bar = (unsigned long long*)p; p += 16;
+    unsigned long long* bars = (unsigned long long*)p; p += 8 * SD_TC_WG;
+    sm.bar = bars + sm.wg;
     sm.tmem_base = (uint32_t*)p;
     const int tid = threadIdx.x, T = blockDim.x;
     for (int i = tid; i < SD_IMG_BYTES / 16; i += T) ((uint4*)wimg)[i] = ((const uint4*)img)[i];
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(sm.bar)));
+        for (int w = 0; w < SD_TC_WG; w++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(bars + w)));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (tid < 32) {   // one warp allocates the TMEM columns and gives up the permit
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n"
+    if (tid < 32) {   // one warp allocates the TMEM columns (128 per warpgroup) and gives up the permit
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n"
                      :: "r"((uint32_t)__cvta_generic_to_shared(sm.tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -263,19 +279,19 @@ __device__ __forceinline__ void sd_release_tc(const SdSmemTc& sm) {
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" :: "r"(*sm.tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(*sm.tmem_base) : "memory");
 }
 
-// one layer: D[128 x N] = A[128 x K] * W[N x K]^T on the tensor cores; all 128 threads call it
+// one layer: D[128 x N] = A[128 x K] * W[N x K]^T on the tensor cores; all 128 threads of a warpgroup call it
 __device__ __forceinline__ void sd_layer_mma(const SdSmemTc& sm, const __nv_bfloat16* w, int K, int N, uint32_t tm_col,
                                              uint32_t& phase) {
     // the A tile was written with ordinary stores: make it visible to the async (tensor core) proxy
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
+    sd_wg_sync(sm.wg);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    if (threadIdx.x == 0) {
-        const uint32_t tm = *sm.tmem_base + tm_col;
+    if ((threadIdx.x & 127) == 0) {
+        const uint32_t tm = *sm.tmem_base + sm.tm_off + tm_col;
         const uint32_t idesc = sd_idesc(N);
         for (int k = 0; k < K; k += 16) {
             const uint64_t da = sd_smem_desc((const char*)sm.a + (k >> 3) * 128, K);
@@ -299,8 +315,8 @@ __device__ __forceinline__ void sd_store8(const SdSmemTc& sm, int row, int k0, i
 }
 
 __device__ __forceinline__ void mlp_tc(const SdSmemTc& sm, const float* x, float* out, uint32_t& phase) {
-    const int tid = threadIdx.x;
-    const uint32_t lane_base = ((uint32_t)(tid & ~31)) << 16;      // TMEM address: lane in bits 31..16
+    const int tid = threadIdx.x & 127;                             // row of this warpgroup's tile
+    const uint32_t lane_base = (((uint32_t)(tid & ~31)) << 16) + sm.tm_off;   // TMEM address: lane in bits 31..16
     // layer 1: A = features (K padded to 48)
 #pragma unroll
     for (int k0 = 0; k0 < SD_K1; k0 += 8) {
@@ -363,7 +379,7 @@ __device__ __forceinline__ void sd_policy(const float* raw, uint32_t legal_mask,
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(SD_TILE, SD_CTAS_PER_SM) sd_mlp_kernel(const float* __restrict__ net, const unsigned char* __restrict__ img,
+__global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1 ? SD_TC_CTAS_PER_SM : SD_CTAS_PER_SM) sd_mlp_kernel(const float* __restrict__ net, const unsigned char* __restrict__ img,
                                                             const float* __restrict__ feat,
                                                             const float* __restrict__ mask, float* __restrict__ adv_out,
                                                             float* __restrict__ pol_out, long long n) {
@@ -372,9 +388,10 @@ __global__ void __launch_bounds__(SD_TILE, SD_CTAS_PER_SM) sd_mlp_kernel(const f
     SdSmemTc stc{};
     uint32_t phase = 0;
     if (PREC == 0) s32 = sd_carve_fp32(smem_raw, net); else stc = sd_carve_tc(smem_raw, img);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (SD_TILE - 1);                 // row inside this warpgroup's tile
+    constexpr int NWG = PREC == 1 ? SD_TC_WG : 1;                // tiles a CTA works on side by side
     const long long tiles = (n + SD_TILE - 1) / SD_TILE;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (long long tile = (long long)blockIdx.x * NWG + (threadIdx.x >> 7); tile < tiles; tile += (long long)gridDim.x * NWG) {
         const long long g = tile * SD_TILE + tid;
         float x[SD_IN], raw[16];
         uint32_t lm = 0u;
@@ -396,7 +413,7 @@ __global__ void __launch_bounds__(SD_TILE, SD_CTAS_PER_SM) sd_mlp_kernel(const f
 // ---------------------------------------------------------------------------------------------
 // Forward level d: inference for every frontier node, then expand (traverser) or sample (opponent).
 template <int PREC>
-__global__ void __launch_bounds__(SD_TILE, SD_CTAS_PER_SM) sd_forward_kernel(SdArgs a, int d) {
+__global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1 ? SD_TC_CTAS_PER_SM : SD_CTAS_PER_SM) sd_forward_kernel(SdArgs a, int d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cp = d & 1;
     const bool trav = (cp == a.sh.player);
@@ -404,11 +421,12 @@ __global__ void __launch_bounds__(SD_TILE, SD_CTAS_PER_SM) sd_forward_kernel(SdA
     SdSmemTc stc{};
     uint32_t phase = 0;
     if (PREC == 0) s32 = sd_carve_fp32(smem_raw, a.net[cp]); else stc = sd_carve_tc(smem_raw, a.img[cp]);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (SD_TILE - 1);                 // row inside this warpgroup's tile
+    constexpr int NWG = PREC == 1 ? SD_TC_WG : 1;                // tiles a CTA works on side by side
     const long long total = a.n_trav * a.sh.n[d];
     const long long tiles = (total + SD_TILE - 1) / SD_TILE;
     const int f = a.sh.f[d];
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (long long tile = (long long)blockIdx.x * NWG + (threadIdx.x >> 7); tile < tiles; tile += (long long)gridDim.x * NWG) {
         const long long g = tile * SD_TILE + tid;
         const bool live = g < total;
         MsState s = live ? a.lvl[d].state[g] : make_uint4(0u, 0u, 0u, 0u);
@@ -655,7 +673,7 @@ int ms_mlp_forward(const float* d_net, int precision, const float* d_feat, const
         sd_prep_kernel<<<8, 256, 0, st>>>(d_net, img);
         MS_LAUNCH_CHECK();
         MS_CUDA(cudaFuncSetAttribute(sd_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
-        sd_mlp_kernel<1><<<grid_for(n, SD_TILE, SD_CTAS_PER_SM), SD_TILE, SD_SMEM_TC, st>>>(d_net, img, d_feat, d_mask, d_adv, d_pol, (long long)n);
+        sd_mlp_kernel<1><<<grid_for(n, SD_TC_THREADS, SD_TC_CTAS_PER_SM), SD_TC_THREADS, SD_SMEM_TC, st>>>(d_net, img, d_feat, d_mask, d_adv, d_pol, (long long)n);
         MS_LAUNCH_CHECK();
         MS_CUDA(cudaFreeAsync(img, st));
     }
@@ -701,7 +719,7 @@ int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, c
         } else if (precision == 0) {
             sd_forward_kernel<0><<<grid_for(n_trav * a.sh.n[d], SD_TILE, 1), SD_TILE, SD_SMEM_FP32, st>>>(a, d);
         } else {
-            sd_forward_kernel<1><<<grid_for(n_trav * a.sh.n[d], SD_TILE, SD_CTAS_PER_SM), SD_TILE, SD_SMEM_TC, st>>>(a, d);
+            sd_forward_kernel<1><<<grid_for(n_trav * a.sh.n[d], SD_TC_THREADS, SD_TC_CTAS_PER_SM), SD_TC_THREADS, SD_SMEM_TC, st>>>(a, d);
         }
         MS_LAUNCH_CHECK();
     }
