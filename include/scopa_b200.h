@@ -285,6 +285,20 @@ int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, c
                       size_t workspace_bytes, float* d_feat, float* d_target, float* d_mask, float* d_root_value,
                       void* stream);
 
+/* ms_sdcfr_train: `epochs` optimiser steps of AdvantageNetwork.train (deep_cfr.py:77-110) in ONE launch: per epoch
+ *   gather the minibatch d_idx[epoch][0..batch) (rows of the replay buffer d_feat [n_rows][34], d_target / d_mask
+ *   [n_rows][16]; batch <= 128, rows distinct = random.sample), forward, loss = MSELoss(pred * mask, target * mask),
+ *   backward, clip_grad_norm_(max_norm), Adam(lr, (beta1, beta2), eps) without weight decay or amsgrad.  d_net (the
+ *   fp32 blob above) and Adam's d_adam_m / d_adam_v [13776] are updated in place; steps_done = optimiser steps taken
+ *   before this call (bias correction).  d_loss [epochs] receives each minibatch's loss; an epoch whose indices are
+ *   out of range writes NaN there and changes nothing.  d_workspace: ms_sdcfr_train_workspace_bytes() bytes.
+ *   fp32 throughout; weights, minibatch and activations stay in the shared memory of one SM across the epochs. */
+size_t ms_sdcfr_train_workspace_bytes(void);
+int ms_sdcfr_train(float* d_net, float* d_adam_m, float* d_adam_v, int64_t steps_done, const float* d_feat,
+                   const float* d_target, const float* d_mask, int64_t n_rows, const int32_t* d_idx, int32_t batch,
+                   int32_t epochs, double lr, double beta1, double beta2, double eps, double max_norm, float* d_loss,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------- multi-deal MCCFR ------
  * The reference solves one fixed deal (MCCFRTrainer(game), game.new_initial_state() = seed 42,
  * src/algorithms/mc_cfr.py:88-92).  These entry points run the same _sample estimator (:37-86) on a game whose

@@ -70,6 +70,9 @@ _SIGS = {
     "ms_mlp_forward": ([vp, C.c_int, vp, vp, vp, vp, i64, vp], C.c_int),
     "ms_sdcfr_traverse": ([vp, C.c_uint32, C.c_int, vp, vp, C.c_int, i64, u64, u64, vp, C.c_size_t, vp, vp, vp, vp, vp],
                           C.c_int),
+    "ms_sdcfr_train_workspace_bytes": ([], C.c_size_t),
+    "ms_sdcfr_train": ([vp, vp, vp, i64, vp, vp, vp, i64, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, C.c_size_t, vp],
+                       C.c_int),
     "ms_full_deal_from_seeds": ([vp, i64, vp, vp, vp], C.c_int),
     "ms_full_deck_from_seeds": ([vp, i64, vp, C.c_int, vp], C.c_int),
     "ms_full_step": ([vp, vp, vp, vp, vp, i64, vp], C.c_int),

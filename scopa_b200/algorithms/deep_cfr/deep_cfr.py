@@ -9,7 +9,9 @@ What changes underneath: the traversal no longer calls a batch-1 MLP (and crosse
 `_external_sampling_cfr` runs `traversals_per_iteration` traversals level by level on the GPU with the
 frontier of each level as one batched inference (csrc/ms_sdcfr.cu; `precision="fp32"` = CUDA-core path in
 the reference's precision, `"bf16"` = tcgen05 tensor-core path), and the samples land in a device-resident
-replay buffer.  The optimiser step stays in PyTorch (Adam, masked MSE, clip-norm 1.0, as the reference).
+replay buffer.  The optimiser (Adam, masked MSE, clip-norm 1.0, as the reference) is PyTorch's by default;
+`optimizer="fused"` runs all epochs of a train() call in one launch of sd_train_kernel (csrc/ms_sd_train.cuh):
+same arithmetic in fp32, minibatches drawn without replacement from torch's CUDA generator.
 """
 import numpy as np
 import torch
@@ -64,7 +66,9 @@ class DeviceReplayBuffer:
 class AdvantageNetwork:
     """Manages the advantage network for one player."""
 
-    def __init__(self, input_dim, num_actions, device="cuda", lr=5e-4, precision="fp32"):
+    def __init__(self, input_dim, num_actions, device="cuda", lr=5e-4, precision="fp32", optimizer="torch"):
+        if optimizer not in ("torch", "fused"):
+            raise ValueError(f"optimizer must be 'torch' or 'fused', not {optimizer!r}")
         self.device = device
         self.num_actions = num_actions
         self.precision = sdcfr.TENSOR_CORE if precision == "bf16" else sdcfr.FP32
@@ -77,9 +81,13 @@ class AdvantageNetwork:
         self.optimizer = optim.Adam(self.net.parameters(), lr=lr)
         self.criterion = nn.MSELoss()
         self.buffer = DeviceReplayBuffer(100000, device)
+        self._fused = None
+        if optimizer == "fused":
+            # the module's parameters become views of one flat blob that the kernel updates in place
+            self._fused = sdcfr.FusedAdam(sdcfr.flatten_parameters_(self.net), lr=lr)
 
     def blob(self):
-        return sdcfr.flatten_net(self.net)
+        return self._fused.blob if self._fused is not None else sdcfr.flatten_net(self.net)
 
     def get_advantages(self, state_features, legal_actions_mask):
         """Get advantages for a batch of states (our batched inference kernel)."""
@@ -101,6 +109,8 @@ class AdvantageNetwork:
             batch_size = min(len(self.buffer), 32)
             if batch_size == 0:
                 return 0.0
+        if self._fused is not None:
+            return self._train_fused(batch_size, epochs)
         total_loss = 0.0
         for _ in range(epochs):
             states, target_adv, masks = self.buffer.sample(batch_size)
@@ -112,6 +122,19 @@ class AdvantageNetwork:
             self.optimizer.step()
             total_loss += loss.item()
         return total_loss / epochs
+
+
+    def _train_fused(self, batch_size, epochs):
+        """All epochs in one launch; one device->host read (the mean loss) per call instead of one per epoch."""
+        b = self.buffer
+        loss = self._fused.step(b.feat, b.target, b.mask, self._sample_rows(batch_size, epochs))
+        return float(loss.mean().item())
+
+    def _sample_rows(self, batch_size, epochs):
+        """[epochs, batch_size] int32: per epoch `batch_size` distinct buffer rows (random.sample) = the top-k positions
+        of iid uniforms."""
+        u = torch.rand((epochs, len(self.buffer)), device=self.device)
+        return u.topk(batch_size, dim=1).indices.to(torch.int32).contiguous()
 
 
 class StrategyBuffer:
@@ -161,7 +184,7 @@ class DeepCFR:
     """Main Deep CFR algorithm."""
 
     def __init__(self, game, num_players=2, device="cuda", precision="fp32", traversals_per_iteration=1, seed=0,
-                 verbose=False):
+                 verbose=False, optimizer="torch"):
         self.game = game
         self.num_players = num_players
         self.device = device
@@ -173,7 +196,8 @@ class DeepCFR:
         self.input_dim = self._estimate_input_dim()
         if verbose:
             print(f"Estimated input dimension: {self.input_dim}")
-        self.advantage_nets = [AdvantageNetwork(self.input_dim, 16, device, precision=precision) for _ in range(num_players)]
+        self.advantage_nets = [AdvantageNetwork(self.input_dim, 16, device, precision=precision, optimizer=optimizer)
+                               for _ in range(num_players)]
         self.strategy_buffers = [StrategyBuffer() for _ in range(num_players)]
         self.training_history = {
             "losses": [[] for _ in range(num_players)],

@@ -71,3 +71,66 @@ class Traverser:
                                                   feat.data_ptr(), target.data_ptr(), mask.data_ptr(), value.data_ptr(),
                                                   _lib.stream_ptr()))
         return feat, target, mask, value
+
+
+class FusedAdam:
+    """State of the fused optimiser (`ms_sdcfr_train`): Adam moments and step count of ONE advantage net whose
+    parameters live in a flat fp32 blob.  `step()` runs `epochs` optimiser steps of AdvantageNetwork.train
+    (/root/reference/src/algorithms/deep_cfr/deep_cfr.py:77-110) in one kernel launch."""
+
+    def __init__(self, blob, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, _entry=None):
+        """`_entry` (tests only): a host function with ms_sdcfr_train's signature, e.g. the emulated kernel of
+        tests/emu -- the tensors then live on the CPU.  The product path always launches the CUDA kernel."""
+        assert blob.dtype == torch.float32 and blob.numel() == NET_FLOATS and blob.is_contiguous()
+        self._emulated = _entry is not None
+        if self._emulated:
+            assert not blob.is_cuda
+            self._entry, ws_bytes = _entry, NET_FLOATS * 4
+        else:
+            if not blob.is_cuda:
+                raise _lib.MsError("FusedAdam needs a CUDA blob: scopa_b200 has no CPU path")
+            lib = _lib.load()
+            self._entry, ws_bytes = lib.ms_sdcfr_train, lib.ms_sdcfr_train_workspace_bytes()
+        self.blob = blob
+        self.m = torch.zeros_like(blob)
+        self.v = torch.zeros_like(blob)
+        self.steps_done = 0
+        self.lr, self.betas, self.eps, self.max_norm = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(max_norm)
+        self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=blob.device)
+
+    def step(self, feat, target, mask, idx):
+        """idx [epochs, batch] int32 rows of (feat [n,34], target [n,16], mask [n,16]) -> losses [epochs]; all tensors on
+        the blob's device."""
+        assert idx.dtype == torch.int32 and idx.dim() == 2 and idx.is_contiguous() and idx.device == self.blob.device
+        for t, w in ((feat, 34), (target, 16), (mask, 16)):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.shape[1] == w and t.device == self.blob.device
+        n_rows = min(feat.shape[0], target.shape[0], mask.shape[0])
+        epochs, batch = idx.shape
+        loss = torch.empty((epochs,), dtype=torch.float32, device=self.blob.device)
+        args = (self.blob.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.steps_done, feat.data_ptr(),
+                target.data_ptr(), mask.data_ptr(), n_rows, idx.data_ptr(), batch, epochs, self.lr, self.betas[0],
+                self.betas[1], self.eps, self.max_norm, loss.data_ptr(), self._ws.data_ptr(), self._ws.numel())
+        if self._emulated:
+            rc = self._entry(*args, None)
+            if rc != 0:
+                raise _lib.MsError(f"emulated ms_sdcfr_train returned {rc}")
+        else:
+            with torch.cuda.device(self.blob.device):
+                _lib.check(self._entry(*args, _lib.stream_ptr()))
+        self.steps_done += epochs
+        return loss
+
+
+def flatten_parameters_(net):
+    """Re-homes the parameters of a FlexibleNet (mlp 34->128->64->16) as views into one flat fp32 blob (nn.Linear
+    order) and returns the blob: the fused optimiser then updates the module in place and `flatten_net` costs nothing."""
+    blob = flatten_net(net).clone()
+    layers = [net.backbone[0].fc, net.backbone[1].fc, net.head]
+    off = 0
+    for l in layers:
+        for p in (l.weight, l.bias):
+            n = p.numel()
+            p.data = blob[off:off + n].view(p.shape)
+            off += n
+    assert off == NET_FLOATS
+    return blob

@@ -1,0 +1,47 @@
+"""Builds the host emulation of sd_train_kernel (libsd_train_emu.so) and the torch-free GPU checker
+(sd_train_check) into tests/emu/_build/.  Test infrastructure only."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.path.join(HERE, "_build")
+EMU_LIB = os.path.join(OUT, "libsd_train_emu.so")
+CHECK_BIN = os.path.join(OUT, "sd_train_check")
+# fmaf must be ONE rounding (the GPU's FFMA) and nothing else may be contracted
+CXXFLAGS = ["-O2", "-ffp-contract=off", "-mfma", "-std=c++17", "-pthread"]
+
+
+def _newer(target, deps):
+    return (not os.path.exists(target)) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
+
+
+def build_emu():
+    os.makedirs(OUT, exist_ok=True)
+    deps = [os.path.join(HERE, "sd_train_emu.cpp"), os.path.join(HERE, "cta_emu.h"),
+            os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_train.cuh")]
+    if _newer(EMU_LIB, deps):
+        subprocess.run(["g++"] + CXXFLAGS + ["-fPIC", "-shared", "-o", EMU_LIB, deps[0]], check=True)
+    return EMU_LIB
+
+
+def build_check():
+    """needs libscopa_b200.so (scopa_b200/_build.py) and the CUDA runtime headers; links both libraries by rpath"""
+    build_emu()
+    lib_dir = os.path.join(ROOT, "scopa_b200")
+    src = os.path.join(HERE, "sd_train_check.cpp")
+    deps = [src, EMU_LIB, os.path.join(lib_dir, "libscopa_b200.so")]
+    if _newer(CHECK_BIN, deps):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        cuda = os.path.dirname(os.path.dirname(os.path.realpath(nvcc)))
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", CHECK_BIN, src, f"-I{cuda}/include", f"-L{cuda}/lib64",
+                        f"-L{lib_dir}", f"-L{OUT}", "-lscopa_b200", "-lsd_train_emu", "-lcudart", "-lm",
+                        "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../../scopa_b200", f"-Wl,-rpath,{cuda}/lib64"],
+                       check=True)
+    return CHECK_BIN
+
+
+if __name__ == "__main__":
+    print(build_emu())
+    print(build_check())

@@ -1,0 +1,36 @@
+// tests/emu/sd_train_emu.cpp -- sd_train_kernel (scopa_b200/csrc/ms_sd_train.cuh) executed on the host through
+// cta_emu.h.  Built by tests/test_sd_train_emu.py with g++ -O2 -ffp-contract=off -mfma (fmaf = one rounding, as FFMA).
+#include "cta_emu.h"
+// libscopa_b200.so exports a host stub with the kernel's mangled name; when both libraries sit in one process the
+// dynamic linker would bind the emulation's calls to that stub.  The emulation therefore lives in its own namespace.
+#define ms ms_emu
+#include "../../scopa_b200/csrc/ms_sd_train.cuh"
+
+extern "C" int emu_sd_train(float* net, float* adam_m, float* adam_v, long long steps_done, const float* feat,
+                            const float* target, const float* mask, long long n_rows, const int* idx, int batch,
+                            int epochs, double lr, double beta1, double beta2, double eps, double max_norm, float* loss,
+                            float* grad) {
+    ms::SdTrainArgs a;
+    a.net = net; a.adam_m = adam_m; a.adam_v = adam_v;
+    a.feat = feat; a.target = target; a.mask = mask; a.n_rows = n_rows;
+    a.idx = idx; a.batch = batch; a.epochs = epochs;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
+    a.b1pow = std::pow(beta1, (double)steps_done);
+    a.b2pow = std::pow(beta2, (double)steps_done);
+    a.loss = loss; a.grad = grad;
+    return emu_launch_cta(ms::sd_train_kernel, a, ms::sdt::kThreads);
+}
+
+extern "C" int emu_sd_train_smem_bytes() { return ms::sdt::kSmemBytes; }
+
+// Same signature as the C ABI's ms_sdcfr_train (include/scopa_b200.h), host pointers instead of device pointers:
+// lets tests drive the Python binding (scopa_b200.sdcfr.FusedAdam) end to end on a machine without a GPU.
+extern "C" int emu_ms_sdcfr_train(float* net, float* adam_m, float* adam_v, long long steps_done, const float* feat,
+                                  const float* target, const float* mask, long long n_rows, const int* idx, int batch,
+                                  int epochs, double lr, double beta1, double beta2, double eps, double max_norm,
+                                  float* loss, void* workspace, size_t workspace_bytes, void* /*stream*/) {
+    if (workspace_bytes < sizeof(float) * ms::sdt::kNetFloats || batch < 1 || batch > ms::sdt::kMaxBatch) return -2;
+    if (epochs == 0) return 0;
+    return emu_sd_train(net, adam_m, adam_v, steps_done, feat, target, mask, n_rows, idx, batch, epochs, lr, beta1, beta2,
+                        eps, max_norm, loss, static_cast<float*>(workspace));
+}

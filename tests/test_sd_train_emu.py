@@ -1,0 +1,187 @@
+"""sd_train_kernel (scopa_b200/csrc/ms_sd_train.cuh), executed on the HOST through tests/emu/cta_emu.h, against the
+reference's own arithmetic: torch (CPU) running AdvantageNetwork.train's step -- MSELoss(pred * mask, target * mask),
+clip_grad_norm_(1.0), Adam(5e-4) (/root/reference/src/algorithms/deep_cfr/deep_cfr.py:77-110).  torch is the oracle here
+(the reference *is* torch code); its sgemm summation order is unspecified, hence tolerances: 1e-6 relative on the loss,
+1e-6 absolute on parameters that move by ~5e-4 per step.  The GPU build of the same source is compared with this
+emulation bit for bit in tests/test_gpu_sd_train.py."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build as emu_build  # noqa: E402
+
+NF = 13776
+fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = C.CDLL(emu_build.build_emu())
+    lib.emu_sd_train.argtypes = [fp, fp, fp, C.c_longlong, fp, fp, fp, C.c_longlong, ip, C.c_int, C.c_int] + [C.c_double] * 5 + [fp, fp]
+    lib.emu_sd_train.restype = C.c_int
+    return lib
+
+
+def P(a):
+    return a.ctypes.data_as(fp)
+
+
+def make_net(seed):
+    torch.manual_seed(seed)
+    net = nn.Sequential(nn.Linear(34, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 16))
+    for l in net:
+        if isinstance(l, nn.Linear):               # AdvantageNetwork's init (deep_cfr.py:40-44)
+            nn.init.xavier_uniform_(l.weight)
+            nn.init.constant_(l.bias, 0.1)
+    return net
+
+
+def blob_of(net):
+    return np.concatenate([p.detach().numpy().reshape(-1) for p in net.parameters()]).astype(np.float32).copy()
+
+
+def make_problem(rng, n_rows, batch, epochs, scale=1.0):
+    feat = (rng.random((n_rows, 34)) < 0.25).astype(np.float32)
+    mask = np.zeros((n_rows, 16), np.float32)
+    for r in range(n_rows):
+        mask[r, rng.choice(16, rng.integers(1, 5), replace=False)] = 1
+    target = (rng.uniform(-1, 1, (n_rows, 16)) * mask * scale).astype(np.float32)
+    idx = np.stack([rng.choice(n_rows, batch, replace=False) for _ in range(epochs)]).astype(np.int32)
+    return feat, target, mask, idx
+
+
+def torch_steps(net, feat, target, mask, idx):
+    opt = torch.optim.Adam(net.parameters(), lr=5e-4)
+    crit = nn.MSELoss()
+    losses, norms = [], []
+    for row in idx:
+        s, t, m = (torch.from_numpy(x[row]) for x in (feat, target, mask))
+        opt.zero_grad()
+        loss = crit(net(s) * m, t * m)
+        loss.backward()
+        norms.append(float(torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)))
+        opt.step()
+        losses.append(loss.item())
+    return np.array(losses), norms, opt
+
+
+def emu_steps(emu, blob, m, v, steps_done, feat, target, mask, idx):
+    idx = np.ascontiguousarray(idx)
+    loss = np.zeros(idx.shape[0], np.float32)
+    grad = np.zeros(NF, np.float32)
+    rc = emu.emu_sd_train(P(blob), P(m), P(v), steps_done, P(feat), P(target), P(mask), feat.shape[0],
+                          idx.ctypes.data_as(ip), idx.shape[1], idx.shape[0], 5e-4, 0.9, 0.999, 1e-8, 1.0, P(loss), P(grad))
+    assert rc == 0
+    return loss
+
+
+@pytest.mark.parametrize("batch,epochs,n_rows,scale", [(128, 6, 2000, 1.0), (32, 4, 100, 1.0), (7, 3, 7, 1.0), (1, 3, 1, 1.0),
+                                                      (128, 5, 500, 40.0), (5, 4, 9, 40.0)])
+def test_emulated_kernel_matches_torch(emu, batch, epochs, n_rows, scale):
+    rng = np.random.default_rng(batch * 1000 + epochs)
+    net = make_net(batch)
+    blob, m, v = blob_of(net), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+    start = blob.copy()
+    feat, target, mask, idx = make_problem(rng, n_rows, batch, epochs, scale)
+    t_loss, norms, opt = torch_steps(net, feat, target, mask, idx)
+    e_loss = emu_steps(emu, blob, m, v, 0, feat, target, mask, idx)
+    if scale > 1:
+        assert max(norms) > 1.0                      # the clip must have engaged in these cases
+    np.testing.assert_allclose(e_loss, t_loss, rtol=2e-6)
+    ref = blob_of(net)
+    assert np.abs(ref - start).max() > 1e-4          # the parameters did move
+    np.testing.assert_allclose(blob, ref, rtol=0, atol=1e-6)
+    t_m = np.concatenate([opt.state[p]["exp_avg"].numpy().reshape(-1) for p in net.parameters()])
+    t_v = np.concatenate([opt.state[p]["exp_avg_sq"].numpy().reshape(-1) for p in net.parameters()])
+    np.testing.assert_allclose(m, t_m, rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(v, t_v, rtol=1e-4, atol=1e-10)
+
+
+def test_split_calls_equal_one_call(emu):
+    """steps_done hands the bias correction over: 3 + 4 steps in two launches == 7 steps in one, bit for bit."""
+    rng = np.random.default_rng(5)
+    feat, target, mask, idx = make_problem(rng, 300, 64, 7)
+    a, b = blob_of(make_net(1)), blob_of(make_net(1))
+    ma, va, mb, vb = (np.zeros(NF, np.float32) for _ in range(4))
+    la = emu_steps(emu, a, ma, va, 0, feat, target, mask, idx)
+    lb = np.concatenate([emu_steps(emu, b, mb, vb, 0, feat, target, mask, idx[:3]),
+                         emu_steps(emu, b, mb, vb, 3, feat, target, mask, idx[3:])])
+    assert np.array_equal(a, b) and np.array_equal(ma, mb) and np.array_equal(va, vb) and np.array_equal(la, lb)
+
+
+def test_repeatable(emu):
+    """The emulation runs 512 truly asynchronous threads: a missing barrier in the kernel shows up as run-to-run noise."""
+    rng = np.random.default_rng(9)
+    feat, target, mask, idx = make_problem(rng, 400, 128, 3)
+    outs = []
+    for _ in range(4):
+        blob, m, v = blob_of(make_net(2)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+        loss = emu_steps(emu, blob, m, v, 0, feat, target, mask, idx)
+        outs.append((blob, m, v, loss))
+    for o in outs[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(o, outs[0]))
+
+
+def test_out_of_range_rows_skip_the_step(emu):
+    rng = np.random.default_rng(11)
+    feat, target, mask, idx = make_problem(rng, 50, 16, 3)
+    idx[1, 4] = 50                                     # one past the end, middle epoch only
+    blob, m, v = blob_of(make_net(3)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+    loss = emu_steps(emu, blob, m, v, 0, feat, target, mask, idx)
+    assert np.isnan(loss[1]) and np.isfinite(loss[0]) and np.isfinite(loss[2])
+    good = np.ascontiguousarray(idx[[0, 2]])
+    blob2, m2, v2 = blob_of(make_net(3)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+    loss2 = emu_steps(emu, blob2, m2, v2, 0, feat, target, mask, good)
+    assert np.array_equal(blob, blob2) and np.array_equal(loss[[0, 2]], loss2)
+
+
+def test_python_binding_drives_the_emulated_kernel(emu):
+    """scopa_b200.sdcfr.FusedAdam / AdvantageNetwork(optimizer='fused') end to end on the CPU: the emulator exports an
+    entry with ms_sdcfr_train's exact signature, bound with the argtypes of scopa_b200._lib, so argument order, the
+    parameter re-homing (flatten_parameters_) and the minibatch sampler are what the GPU path uses."""
+    from scopa_b200 import _lib, sdcfr
+    from scopa_b200.algorithms.deep_cfr.deep_cfr import AdvantageNetwork
+
+    entry = emu.emu_ms_sdcfr_train
+    entry.argtypes, entry.restype = _lib._SIGS["ms_sdcfr_train"]
+    torch.manual_seed(4)
+    fused, plain = AdvantageNetwork(34, 16, device="cpu"), AdvantageNetwork(34, 16, device="cpu")
+    plain.net.load_state_dict(fused.net.state_dict())
+    fused._fused = sdcfr.FusedAdam(sdcfr.flatten_parameters_(fused.net), lr=5e-4, _entry=entry)
+    assert fused.blob() is fused._fused.blob
+    rng = np.random.default_rng(3)
+    feat, target, mask, _ = make_problem(rng, 700, 1, 1)
+    for adv in (fused, plain):
+        adv.buffer.add_batch(*(torch.from_numpy(x) for x in (feat, target, mask)))
+    rows = fused._sample_rows(128, 5)
+    assert rows.shape == (5, 128) and rows.dtype == torch.int32 and int(rows.max()) < 700 and int(rows.min()) >= 0
+    assert all(len(set(r.tolist())) == 128 for r in rows)                   # without replacement
+    # the same minibatches through both optimisers
+    fused._sample_rows = lambda batch_size, epochs: rows
+    loss_fused = fused.train(batch_size=128, epochs=5)
+    it = iter(rows.long())
+
+    def same_rows(batch_size):
+        r = next(it)
+        return plain.buffer.feat[r], plain.buffer.target[r], plain.buffer.mask[r]
+
+    plain.buffer.sample = same_rows
+    loss_plain = plain.train(batch_size=128, epochs=5)
+    assert abs(loss_fused - loss_plain) < 2e-6 * abs(loss_plain)
+    for (n1, p1), (n2, p2) in zip(fused.net.named_parameters(), plain.net.named_parameters()):
+        assert n1 == n2 and torch.allclose(p1, p2, rtol=0, atol=1e-6), n1
+    # the module's parameters ARE the blob the kernel updated (views), and snapshots copy them
+    assert np.allclose(sdcfr.flatten_net(fused.net).numpy(), fused._fused.blob.numpy(), rtol=0, atol=0)
+    assert fused._fused.steps_done == 5
+    # small buffer: the reference's fallback batch size min(len, 32)
+    small = AdvantageNetwork(34, 16, device="cpu")
+    small._fused = sdcfr.FusedAdam(sdcfr.flatten_parameters_(small.net), _entry=entry)
+    small.buffer.add_batch(*(torch.from_numpy(x[:20]) for x in (feat, target, mask)))
+    assert np.isfinite(small.train(batch_size=128, epochs=2)) and small._fused.steps_done == 2
+    assert AdvantageNetwork(34, 16, device="cpu").train() == 0.0             # empty buffer
