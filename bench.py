@@ -636,6 +636,11 @@ def run_ours(args):
                                          "not the MMA alone; 27136 algorithmic FLOP per inference (un-padded)"}}
         sd_obj[pname] = o
     sd_obj["value"] = sd_obj["bf16_tcgen05"]["inferences_per_sec"]
+    if rank == 0:
+        try:
+            sd_obj["train"] = bench_sd_train(dev, _lib)
+        except Exception as e:      # an auxiliary section must not take the headline line down with it
+            sd_obj["train"] = {"error": repr(e)}
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu_mccfr = cpu_env = None
@@ -714,6 +719,49 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------- CPU side
+def bench_sd_train(dev, _lib, epochs=10, calls=20, rows=100_000):
+    """AdvantageNetwork.train (deep_cfr.py:77-110), `epochs` optimiser steps per call on a full replay buffer:
+    the fused kernel (one launch per call) beside the PyTorch step it replaces (about 40 launches and one
+    device->host read per epoch).  Wall clock around synchronised calls: that is what DeepCFR.train waits for."""
+    import torch
+    from scopa_b200.algorithms.deep_cfr.deep_cfr import AdvantageNetwork
+    torch.manual_seed(7)
+    out = {"config": {"workload": f"{epochs} optimiser steps per train() call, minibatch 128 drawn from a replay buffer of "
+                                  f"{rows} rows, net 34-128-64-16 fp32, masked MSE + clip-norm 1.0 + Adam 5e-4",
+                      "flop_per_step": 3 * 2 * 128 * 13568 - 2 * 128 * 34 * 128}}
+    feat = (torch.rand((rows, 34), device=dev) < 0.25).float()
+    mask = (torch.rand((rows, 16), device=dev) < 0.2).float()
+    target = (torch.rand((rows, 16), device=dev) * 2 - 1) * mask
+    for name in ("fused", "torch"):
+        adv = AdvantageNetwork(34, 16, device=dev, optimizer=name)
+        adv.buffer.add_batch(feat, target, mask)
+        for _ in range(3):
+            adv.train(batch_size=128, epochs=epochs)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            loss = adv.train(batch_size=128, epochs=epochs)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[name] = {"us_per_step": 1e6 * dt / (calls * epochs), "ms_per_call": 1e3 * dt / calls, "last_loss": loss,
+                     "our_launches_per_call": (_lib.launch_count() - l0) / calls}
+        if name == "fused":     # the kernel alone (CUDA events around the launches, minibatch rows drawn beforehand)
+            idx = adv._sample_rows(128, epochs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(calls):
+                adv._fused.step(adv.buffer.feat, adv.buffer.target, adv.buffer.mask, idx)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name]["kernel_us_per_step"] = 1e3 * e0.elapsed_time(e1) / (calls * epochs)
+    out["speedup_vs_torch_step"] = out["torch"]["us_per_step"] / out["fused"]["us_per_step"]
+    out["note"] = ("sd_train_kernel: one CTA keeps the 13 776 weights, the minibatch and all activations in shared memory "
+                   "for every epoch of the call; bit-identical to the host emulation of the same source "
+                   "(tests/emu), which is pinned to torch on the CPU")
+    return out
+
+
 def cpu_baselines(args, sample_seconds, threads=None):
     """Times the CPU restatement (oracle/, a C port of the reference's algorithm) on the host cores."""
     from oracle import ms_oracle as ora

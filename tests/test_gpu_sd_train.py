@@ -1,0 +1,105 @@
+"""ms_sdcfr_train (sd_train_kernel, csrc/ms_sd_train.cuh) on the device.
+
+1. Bit parity: tests/emu/sd_train_check runs a seeded problem through the C ABI and through the host emulation of the
+   same kernel source; parameters, Adam moments and losses must be identical words.  (The emulation is pinned to the
+   reference's arithmetic -- torch -- in tests/test_sd_train_emu.py.)
+2. The Python binding on CUDA tensors against torch.optim.Adam on the same minibatches (fp32 tolerance: torch's sgemm
+   summation order differs).
+3. DeepCFR(optimizer="fused") trains through the drop-in API.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build as emu_build  # noqa: E402
+
+from scopa_b200 import sdcfr  # noqa: E402
+from scopa_b200.algorithms.deep_cfr.deep_cfr import AdvantageNetwork, DeepCFR  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("batch,epochs,n_rows", [(128, 6, 4096), (128, 1, 300), (32, 5, 100), (7, 3, 7), (1, 2, 1), (100, 4, 300)])
+def test_device_kernel_equals_emulation_bit_for_bit(batch, epochs, n_rows):
+    from scopa_b200 import _lib
+    _lib.load()                                       # libscopa_b200.so must exist before the checker links against it
+    exe = emu_build.build_check()
+    res = subprocess.run([exe, str(batch), str(epochs), str(n_rows), "0"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "differing words net 0 m 0 v 0 loss 0" in res.stdout, res.stdout
+
+
+def test_binding_matches_torch_adam_on_cuda():
+    torch.manual_seed(0)
+    rng = np.random.default_rng(0)
+    fused, plain = AdvantageNetwork(34, 16, device="cuda", optimizer="fused"), AdvantageNetwork(34, 16, device="cuda")
+    plain.net.load_state_dict(fused.net.state_dict())
+    n = 3000
+    feat = torch.from_numpy((rng.random((n, 34)) < 0.25).astype(np.float32)).cuda()
+    mask = torch.zeros((n, 16), device="cuda")
+    mask[torch.arange(n, device="cuda"), torch.from_numpy(rng.integers(0, 16, n)).cuda()] = 1
+    mask[torch.arange(n, device="cuda"), torch.from_numpy(rng.integers(0, 16, n)).cuda()] = 1
+    target = torch.from_numpy(rng.uniform(-1, 1, (n, 16)).astype(np.float32)).cuda() * mask
+    for adv in (fused, plain):
+        adv.buffer.add_batch(feat, target, mask)
+    rows = fused._sample_rows(128, 8)
+    assert rows.is_cuda and rows.shape == (8, 128)
+    fused._sample_rows = lambda batch_size, epochs: rows
+    it = iter(rows.long())
+
+    def same_rows(batch_size):
+        r = next(it)
+        return plain.buffer.feat[r], plain.buffer.target[r], plain.buffer.mask[r]
+
+    plain.buffer.sample = same_rows
+    before = sdcfr.flatten_net(plain.net).clone()
+    lf, lp = fused.train(batch_size=128, epochs=8), plain.train(batch_size=128, epochs=8)
+    assert abs(lf - lp) < 1e-5 * abs(lp), (lf, lp)
+    a, b = sdcfr.flatten_net(fused.net), sdcfr.flatten_net(plain.net)
+    assert float((b - before).abs().max()) > 1e-3                     # eight Adam steps of 5e-4
+    assert float((a - b).abs().max()) < 5e-6
+    assert fused._fused.steps_done == 8 and fused.blob() is fused._fused.blob
+    # inference reads the blob the optimiser just updated
+    adv_f, _ = sdcfr.mlp_forward(fused.blob(), feat[:64], mask[:64], sdcfr.FP32)
+    adv_p, _ = sdcfr.mlp_forward(plain.blob(), feat[:64], mask[:64], sdcfr.FP32)
+    assert float(((adv_f - adv_p) * mask[:64]).abs().max()) < 1e-4
+
+
+def test_bad_rows_are_reported_not_applied():
+    torch.manual_seed(1)
+    net = AdvantageNetwork(34, 16, device="cuda", optimizer="fused")
+    opt = net._fused
+    feat, target, mask = (torch.rand((10, w), device="cuda") for w in (34, 16, 16))
+    idx = torch.tensor([[0, 1, 2, 3], [4, 5, 10, 6]], dtype=torch.int32, device="cuda")      # row 10 does not exist
+    w0 = opt.blob.clone()
+    loss = opt.step(feat, target, mask, idx[1:].contiguous())
+    assert torch.isnan(loss).all() and torch.equal(opt.blob, w0)
+    loss = opt.step(feat, target, mask, idx[:1].contiguous())
+    assert torch.isfinite(loss).all() and not torch.equal(opt.blob, w0)
+
+
+def test_deepcfr_trains_with_the_fused_optimiser():
+    from scopa_b200 import pyspiel_compat as pyspiel
+    from scopa_b200.envs import openspiel_mini_scopa  # noqa: F401  (registers mini_scopa)
+    torch.manual_seed(0)
+    game = pyspiel.load_game("mini_scopa")
+    d = DeepCFR(game, device="cuda", traversals_per_iteration=256, seed=3, optimizer="fused")
+    w0 = [a.blob().clone() for a in d.advantage_nets]
+    d.train(iterations=3, advantage_epochs=6, eval_freq=10, eval_episodes=0)
+    for p in (0, 1):
+        assert len(d.training_history["losses"][p]) == 3 and all(np.isfinite(d.training_history["losses"][p]))
+        assert d.advantage_nets[p]._fused.steps_done == 18
+        assert not torch.equal(d.advantage_nets[p].blob(), w0[p])
+        assert len(d.strategy_buffers[p].strategies) == 2
+        # snapshots are copies, not views of the live blob
+        snap = sdcfr.flatten_net(d.strategy_buffers[p].strategies[0])
+        assert snap.data_ptr() != d.advantage_nets[p].blob().data_ptr()
+    s = game.new_initial_state()
+    pol = d.get_policy(s, 0)
+    assert pol.shape == (16,) and (pol >= 0).all() and pol.sum() < 1 + 1e-5
