@@ -299,6 +299,19 @@ int ms_sdcfr_train(float* d_net, float* d_adam_m, float* d_adam_v, int64_t steps
                    int32_t epochs, double lr, double beta1, double beta2, double eps, double max_norm, float* d_loss,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ms_sdcfr_average_policy: StrategyBuffer.get_average_policy (deep_cfr.py:136-160) for n_rows states and ALL n_nets
+ *   stored strategy nets at once: d_policy[row] = sum over k (ascending) of positive_regret_policy(net_k(d_feat[row]),
+ *   d_mask[row]) * d_weights[k], positive_regret_policy = relu(adv) * mask / max(sum, 1e-8) (nets.py:93-101).
+ *   d_nets [n_nets][13776] fp32 blobs; d_weights [n_nets] = weight_k / total_weight as fp32 (the reference multiplies
+ *   a float32 array by that Python float); d_feat [n_rows][34], d_mask [n_rows][16], d_policy [n_rows][16].
+ *   Two launches: one CTA per net (net in shared memory, rows in chunks of 64), then the sum over nets in k order.
+ *   d_workspace: ms_sdcfr_average_policy_workspace_bytes(n_nets, n_rows) bytes.  The empty buffer (uniform policy,
+ *   :138-141) is the caller's case: n_nets must be >= 1. */
+size_t ms_sdcfr_average_policy_workspace_bytes(int32_t n_nets, int64_t n_rows);
+int ms_sdcfr_average_policy(const float* d_nets, const float* d_weights, int32_t n_nets, const float* d_feat,
+                            const float* d_mask, int64_t n_rows, float* d_policy, void* d_workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------- multi-deal MCCFR ------
  * The reference solves one fixed deal (MCCFRTrainer(game), game.new_initial_state() = seed 42,
  * src/algorithms/mc_cfr.py:88-92).  These entry points run the same _sample estimator (:37-86) on a game whose

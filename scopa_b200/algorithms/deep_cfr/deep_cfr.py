@@ -138,12 +138,20 @@ class AdvantageNetwork:
 
 
 class StrategyBuffer:
-    """Stores past strategies for final policy computation."""
+    """Stores past strategies for final policy computation.
+
+    Same lists as the reference (`strategies`, `weights`, `max_size`; deep_cfr.py:118-160).  When the stored nets live on
+    a CUDA device the average policy of ALL of them is two kernel launches (`ms_sdcfr_average_policy`: one CTA per net)
+    instead of one batch-1 forward per net; the nets are snapshots, so their flattened weights are cached per module."""
+
+    _entry = None           # tests only: emulated entry point (see sdcfr.average_policy)
 
     def __init__(self, max_size=100):
         self.strategies = []
         self.weights = []
         self.max_size = max_size
+        self._blob_of = {}          # id(module) -> (module, flat fp32 blob)
+        self._stack_key, self._stack = None, None
 
     def add_strategy(self, strategy_net, iteration):
         if len(self.strategies) >= self.max_size:
@@ -152,6 +160,28 @@ class StrategyBuffer:
         self.strategies.append(strategy_net)
         self.weights.append(iteration + 1)
 
+    def _stacked(self):
+        """([K, 13776] blobs, [K] fp32 weights / total) of the current lists; rebuilt only when the lists changed."""
+        key = (tuple(id(s) for s in self.strategies), tuple(self.weights))
+        if key != self._stack_key:
+            live = set(key[0])
+            self._blob_of = {i: v for i, v in self._blob_of.items() if i in live}
+            for s_ in self.strategies:
+                if id(s_) not in self._blob_of:
+                    self._blob_of[id(s_)] = (s_, sdcfr.flatten_net(s_))
+            nets = torch.stack([self._blob_of[i][1] for i in key[0]]).contiguous()
+            total_weight = sum(self.weights)
+            # the reference multiplies a float32 array by the Python float weight / total_weight
+            w = torch.tensor([np.float32(w_ / total_weight) for w_ in self.weights], dtype=torch.float32, device=nets.device)
+            self._stack_key, self._stack = key, (nets, w)
+        return self._stack
+
+    def average_policy_batch(self, feat, mask):
+        """feat [n, 34], mask [n, 16] tensors on the nets' device -> [n, 16] average policy (needs >= 1 strategy)."""
+        nets, w = self._stacked()
+        return sdcfr.average_policy(nets, w, feat.to(torch.float32).contiguous(), mask.to(torch.float32).contiguous(),
+                                    _entry=self._entry)
+
     def get_average_policy(self, state_features, legal_actions_mask):
         if not self.strategies:
             mask = np.asarray(legal_actions_mask).astype(np.float32)
@@ -159,6 +189,9 @@ class StrategyBuffer:
         dev = next(self.strategies[0].parameters()).device
         x = torch.as_tensor(np.asarray(state_features), dtype=torch.float32, device=dev).unsqueeze(0)
         m = torch.as_tensor(np.asarray(legal_actions_mask), dtype=torch.float32, device=dev).unsqueeze(0)
+        if dev.type == "cuda" or self._entry is not None:
+            return self.average_policy_batch(x, m)[0].cpu().numpy().astype(np.float32)
+        # strategy nets that a caller keeps on the CPU: the reference's own loop (torch on the CPU)
         policy = torch.zeros_like(m)
         total_weight = sum(self.weights)
         with torch.no_grad():
@@ -335,11 +368,7 @@ class DeepCFR:
                 if not buf.strategies:
                     pol16[rows] = m[rows] / m[rows].sum(1, keepdim=True)
                     continue
-                tot = float(sum(buf.weights))
-                acc = torch.zeros((int(rows.sum()), 16), dtype=torch.float32, device=self.device)
-                for net, w in zip(buf.strategies, buf.weights):
-                    acc += positive_regret_policy(net(x[rows]), m[rows]) * (w / tot)
-                pol16[rows] = acc
+                pol16[rows] = buf.average_policy_batch(x[rows], m[rows])
         tab = torch.gather(pol16.double(), 1, legal)
         valid = torch.arange(4, device=self.device).unsqueeze(0) < nl.unsqueeze(1)
         tab = tab * valid

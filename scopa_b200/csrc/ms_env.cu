@@ -501,20 +501,23 @@ __global__ void __launch_bounds__(256) rollout_kernel(const uint4* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-static std::once_flag g_mt_once[64];
+static std::mutex g_mt_mu;
+static bool g_mt_done[64] = {};
 
+// uploads the seed-independent MT19937 start table once per device; a failed upload is retried by the next call
+// (a once_flag would be consumed by the failure and later launches would read an empty table)
 static int ensure_mt_table() {
     int dev = 0;
     MS_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(MS_ERR_ARG, "device index %d out of range", dev);
-    cudaError_t err = cudaSuccess;
-    std::call_once(g_mt_once[dev], [&]() {
-        uint32_t t[624];
-        t[0] = 19650218u;   // init_genrand(19650218), the seed-independent start of init_by_array
-        for (int i = 1; i < 624; i++) t[i] = 1812433253u * (t[i - 1] ^ (t[i - 1] >> 30)) + (uint32_t)i;
-        err = cudaMemcpyToSymbol(g_mt_init, t, sizeof(t));
-    });
+    std::lock_guard<std::mutex> lk(g_mt_mu);
+    if (g_mt_done[dev]) return MS_OK;
+    uint32_t t[624];
+    t[0] = 19650218u;   // init_genrand(19650218), the seed-independent start of init_by_array
+    for (int i = 1; i < 624; i++) t[i] = 1812433253u * (t[i - 1] ^ (t[i - 1] >> 30)) + (uint32_t)i;
+    cudaError_t err = cudaMemcpyToSymbol(g_mt_init, t, sizeof(t));
     if (err != cudaSuccess) return fail(MS_ERR_CUDA, "uploading MT table failed: %s", cudaGetErrorString(err));
+    g_mt_done[dev] = true;
     return MS_OK;
 }
 

@@ -1,7 +1,9 @@
-// scopa_b200/csrc/ms_sd_train.cu -- C ABI of the fused advantage-net optimiser (kernel in ms_sd_train.cuh).
+// scopa_b200/csrc/ms_sd_train.cu -- C ABI of the fused advantage-net optimiser (kernel in ms_sd_train.cuh) and of the
+// all-nets average policy (kernels in ms_sd_avgpol.cuh).
 #include <cmath>
 
 #include "ms_common.cuh"
+#include "ms_sd_avgpol.cuh"
 #include "ms_sd_train.cuh"
 
 extern "C" {
@@ -37,6 +39,37 @@ int ms_sdcfr_train(float* d_net, float* d_adam_m, float* d_adam_v, int64_t steps
     a.loss = d_loss;
     a.grad = static_cast<float*>(d_workspace);
     sd_train_kernel<<<1, sdt::kThreads, sdt::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(a);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+size_t ms_sdcfr_average_policy_workspace_bytes(int32_t n_nets, int64_t n_rows) {
+    if (n_nets < 0 || n_rows < 0) return 0;
+    return (size_t)n_nets * (size_t)n_rows * ms::sdt::kOut * sizeof(float);
+}
+
+int ms_sdcfr_average_policy(const float* d_nets, const float* d_weights, int32_t n_nets, const float* d_feat,
+                            const float* d_mask, int64_t n_rows, float* d_policy, void* d_workspace,
+                            size_t workspace_bytes, void* stream) {
+    using namespace ms;
+    if (n_nets < 1 || n_rows < 0) return fail(MS_ERR_ARG, "ms_sdcfr_average_policy: n_nets %d, n_rows %lld", n_nets, (long long)n_rows);
+    if (n_rows == 0) return MS_OK;
+    if (!d_nets || !d_weights || !d_feat || !d_mask || !d_policy || !d_workspace)
+        return fail(MS_ERR_ARG, "ms_sdcfr_average_policy: null pointer");
+    if (workspace_bytes < ms_sdcfr_average_policy_workspace_bytes(n_nets, n_rows))
+        return fail(MS_ERR_ARG, "ms_sdcfr_average_policy: workspace of %zu bytes, need %zu", workspace_bytes,
+                    ms_sdcfr_average_policy_workspace_bytes(n_nets, n_rows));
+    SdAvgPolArgs a;
+    a.nets = d_nets; a.weights = d_weights; a.n_nets = n_nets;
+    a.feat = d_feat; a.mask = d_mask; a.n_rows = n_rows;
+    a.scratch = static_cast<float*>(d_workspace);
+    a.policy = d_policy;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MS_CUDA(cudaFuncSetAttribute(sd_avgpol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sda::kPolSmemBytes));
+    const int grid = n_nets < kNumSMs ? n_nets : kNumSMs;          // one net per CTA, one CTA per SM
+    sd_avgpol_kernel<<<grid, sda::kPolThreads, sda::kPolSmemBytes, st>>>(a);
+    MS_LAUNCH_CHECK();
+    sd_avgpol_reduce_kernel<<<grid_for(n_rows * sdt::kOut, 256, 8), 256, 0, st>>>(a);
     MS_LAUNCH_CHECK();
     return MS_OK;
 }

@@ -134,3 +134,33 @@ def flatten_parameters_(net):
             off += n
     assert off == NET_FLOATS
     return blob
+
+
+def average_policy(nets, weights, feat, mask, _entry=None):
+    """StrategyBuffer.get_average_policy for a batch (`ms_sdcfr_average_policy`): nets [K, 13776] fp32 blobs, weights
+    [K] fp32 (= weight_k / total_weight), feat [n, 34], mask [n, 16] -> policy [n, 16]; every tensor on the same CUDA
+    device.  `_entry` (tests only): a host function with the entry point's signature (the emulated kernels of
+    tests/emu), tensors on the CPU."""
+    dev = nets.device
+    assert nets.dim() == 2 and nets.shape[1] == NET_FLOATS and weights.shape == (nets.shape[0],)
+    assert feat.dim() == 2 and feat.shape[1] == 34 and mask.shape == (feat.shape[0], 16)
+    for t in (nets, weights, feat, mask):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.device == dev
+    k, n = nets.shape[0], feat.shape[0]
+    policy = torch.empty((n, 16), dtype=torch.float32, device=dev)
+    if n == 0:
+        return policy
+    ws = torch.empty(max(1, k * n * 16), dtype=torch.float32, device=dev)
+    args = (nets.data_ptr(), weights.data_ptr(), k, feat.data_ptr(), mask.data_ptr(), n, policy.data_ptr(), ws.data_ptr(),
+            ws.numel() * 4)
+    if _entry is not None:
+        assert not nets.is_cuda
+        rc = _entry(*args, None)
+        if rc != 0:
+            raise _lib.MsError(f"emulated ms_sdcfr_average_policy returned {rc}")
+    else:
+        if not nets.is_cuda:
+            raise _lib.MsError("average_policy needs CUDA tensors: scopa_b200 has no CPU path")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ms_sdcfr_average_policy(*args, _lib.stream_ptr()))
+    return policy

@@ -56,3 +56,17 @@ static int emu_launch_cta(Kernel k, const Args& args, unsigned threads) {
     pthread_barrier_destroy(&emu_barrier);
     return 0;
 }
+
+// kernel<<<blocks, threads>>>(args) for kernels whose blocks do not communicate: the blocks run one after another
+template <class Kernel, class Args>
+static int emu_launch_grid(Kernel k, const Args& args, unsigned blocks, unsigned threads) {
+    gridDim = {blocks, 1, 1};
+    for (unsigned b = 0; b < blocks; ++b) {
+        blockIdx = {b, 0, 0};
+        int rc = emu_launch_cta(k, args, threads);
+        if (rc) return rc;
+    }
+    blockIdx = {0, 0, 0};
+    gridDim = {1, 1, 1};
+    return 0;
+}

@@ -12,6 +12,8 @@
 
 #include "../../include/scopa_b200.h"
 
+extern "C" int emu_ms_sdcfr_average_policy(const float*, const float*, int, const float*, const float*, long long, float*,
+                                           void*, size_t, void*);
 extern "C" int emu_sd_train(float*, float*, float*, long long, const float*, const float*, const float*, long long,
                             const int*, int, int, double, double, double, double, double, float*, float*);
 
@@ -31,7 +33,74 @@ static float uni() { return (rnd() & 0xFFFFFF) / 16777216.0f; }
         }                                                                                   \
     } while (0)
 
+// sd_train_check avgpol [n_nets] [n_rows] [timing_reps]: ms_sdcfr_average_policy on the device against the emulation
+static int check_avgpol(int K, int n, int reps) {
+    const int NF = 13776;
+    std::vector<float> nets((size_t)K * NF), w(K), feat((size_t)n * 34), mask((size_t)n * 16, 0.f), pol_e((size_t)n * 16),
+        ws_e((size_t)K * n * 16);
+    for (auto& x : nets) x = (2 * uni() - 1) * 0.2f;
+    double tot = 0;
+    for (int k = 0; k < K; ++k) tot += k + 2;
+    for (int k = 0; k < K; ++k) w[k] = (float)((k + 2) / tot);
+    for (auto& x : feat) x = uni() < 0.3f ? 1.f : 0.f;
+    for (int r = 0; r < n; ++r)
+        for (int j = 0, nl = 1 + rnd() % 4; j < nl; ++j) mask[(size_t)r * 16 + rnd() % 16] = 1.f;
+    const bool timing_only = getenv("SD_CHECK_TIMING_ONLY") != nullptr;     // skip the (slow) emulation of big cases
+    if (!timing_only &&
+        emu_ms_sdcfr_average_policy(nets.data(), w.data(), K, feat.data(), mask.data(), n, pol_e.data(), ws_e.data(),
+                                    ws_e.size() * 4, nullptr)) {
+        printf("emulation failed\n");
+        return 2;
+    }
+    if (getenv("SD_TRAIN_EMU_ONLY")) {
+        double s = 0;
+        for (float x : pol_e) s += x;
+        printf("emu avgpol: sum of policies %.6f over %d rows\n", s, n);
+        return 0;
+    }
+    float *d_nets, *d_w, *d_feat, *d_mask, *d_pol;
+    void* d_ws;
+    size_t wsb = ms_sdcfr_average_policy_workspace_bytes(K, n);
+    CK(cudaMalloc(&d_nets, nets.size() * 4)); CK(cudaMalloc(&d_w, K * 4)); CK(cudaMalloc(&d_feat, feat.size() * 4));
+    CK(cudaMalloc(&d_mask, mask.size() * 4)); CK(cudaMalloc(&d_pol, pol_e.size() * 4)); CK(cudaMalloc(&d_ws, wsb));
+    CK(cudaMemcpy(d_nets, nets.data(), nets.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_w, w.data(), K * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_feat, feat.data(), feat.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_mask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice));
+    int rc = ms_sdcfr_average_policy(d_nets, d_w, K, d_feat, d_mask, n, d_pol, d_ws, wsb, nullptr);
+    if (rc) {
+        printf("ms_sdcfr_average_policy failed: %d %s\n", rc, ms_last_error());
+        return 2;
+    }
+    CK(cudaDeviceSynchronize());
+    std::vector<float> pol_g(pol_e.size());
+    CK(cudaMemcpy(pol_g.data(), d_pol, pol_g.size() * 4, cudaMemcpyDeviceToHost));
+    size_t d = 0;
+    double s = 0;
+    for (size_t i = 0; i < pol_g.size(); ++i) {
+        if (!timing_only) d += memcmp(&pol_g[i], &pol_e[i], 4) != 0;
+        s += pol_g[i];
+    }
+    printf("avgpol nets %d rows %d: differing words %zu of %zu%s; sum of policies %.6f\n", K, n, d, pol_g.size(),
+           timing_only ? " (NOT compared: timing only)" : "", s);
+    if (reps > 0) {
+        cudaEvent_t t0, t1;
+        CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+        for (int i = 0; i < 3; ++i) ms_sdcfr_average_policy(d_nets, d_w, K, d_feat, d_mask, n, d_pol, d_ws, wsb, nullptr);
+        CK(cudaEventRecord(t0));
+        for (int i = 0; i < reps; ++i) ms_sdcfr_average_policy(d_nets, d_w, K, d_feat, d_mask, n, d_pol, d_ws, wsb, nullptr);
+        CK(cudaEventRecord(t1));
+        CK(cudaEventSynchronize(t1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, t0, t1));
+        printf("timing: %.2f us per call (%d nets x %d rows, two launches)\n", 1e3 * ms / reps, K, n);
+    }
+    return d ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "avgpol"))
+        return check_avgpol(argc > 2 ? atoi(argv[2]) : 8, argc > 3 ? atoi(argv[3]) : 70, argc > 4 ? atoi(argv[4]) : 0);
     const int batch = argc > 1 ? atoi(argv[1]) : 128, epochs = argc > 2 ? atoi(argv[2]) : 6;
     const int n_rows = argc > 3 ? atoi(argv[3]) : 4096, reps = argc > 4 ? atoi(argv[4]) : 50;
     const int NF = 13776;

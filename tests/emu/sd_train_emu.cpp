@@ -5,6 +5,7 @@
 // dynamic linker would bind the emulation's calls to that stub.  The emulation therefore lives in its own namespace.
 #define ms ms_emu
 #include "../../scopa_b200/csrc/ms_sd_train.cuh"
+#include "../../scopa_b200/csrc/ms_sd_avgpol.cuh"
 
 extern "C" int emu_sd_train(float* net, float* adam_m, float* adam_v, long long steps_done, const float* feat,
                             const float* target, const float* mask, long long n_rows, const int* idx, int batch,
@@ -33,4 +34,21 @@ extern "C" int emu_ms_sdcfr_train(float* net, float* adam_m, float* adam_v, long
     if (epochs == 0) return 0;
     return emu_sd_train(net, adam_m, adam_v, steps_done, feat, target, mask, n_rows, idx, batch, epochs, lr, beta1, beta2,
                         eps, max_norm, loss, static_cast<float*>(workspace));
+}
+
+// Same signature as ms_sdcfr_average_policy (include/scopa_b200.h) with host pointers.  `grid` CTAs like the device
+// launch (min(n_nets, 148)); the emulation runs them one after another.
+extern "C" int emu_ms_sdcfr_average_policy(const float* nets, const float* weights, int n_nets, const float* feat,
+                                           const float* mask, long long n_rows, float* policy, void* workspace,
+                                           size_t workspace_bytes, void* /*stream*/) {
+    if (n_nets < 1 || n_rows < 0) return -2;
+    if (n_rows == 0) return 0;
+    if (workspace_bytes < (size_t)n_nets * (size_t)n_rows * 16 * sizeof(float)) return -2;
+    ms::SdAvgPolArgs a;
+    a.nets = nets; a.weights = weights; a.n_nets = n_nets; a.feat = feat; a.mask = mask; a.n_rows = n_rows;
+    a.scratch = static_cast<float*>(workspace); a.policy = policy;
+    const unsigned grid = n_nets < 148 ? n_nets : 148;
+    int rc = emu_launch_grid(ms::sd_avgpol_kernel, a, grid, ms::sda::kPolThreads);
+    if (rc) return rc;
+    return emu_launch_grid(ms::sd_avgpol_reduce_kernel, a, 2, 256);
 }

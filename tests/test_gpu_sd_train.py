@@ -103,3 +103,51 @@ def test_deepcfr_trains_with_the_fused_optimiser():
     s = game.new_initial_state()
     pol = d.get_policy(s, 0)
     assert pol.shape == (16,) and (pol >= 0).all() and pol.sum() < 1 + 1e-5
+
+
+@pytest.mark.parametrize("n_nets,n_rows", [(3, 1), (8, 70), (20, 200)])
+def test_average_policy_kernels_equal_emulation_bit_for_bit(n_nets, n_rows):
+    from scopa_b200 import _lib
+    _lib.load()
+    exe = emu_build.build_check()
+    res = subprocess.run([exe, "avgpol", str(n_nets), str(n_rows), "0"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "differing words 0 of" in res.stdout, res.stdout
+
+
+def test_strategy_buffer_average_policy_on_cuda():
+    """StrategyBuffer.get_average_policy / average_policy_batch (two launches for all nets) against the reference's loop
+    of per-net forwards, here torch on the same device."""
+    from scopa_b200.algorithms.deep_cfr.deep_cfr import HIDDEN, StrategyBuffer
+    from scopa_b200.algorithms.deep_cfr.nets import FlexibleNet, positive_regret_policy
+    torch.manual_seed(5)
+    rng = np.random.default_rng(5)
+    buf = StrategyBuffer(max_size=100)
+    for it in range(1, 13):
+        net = FlexibleNet(mode="mlp", input_shape=(34,), output_dim=16, mlp_hidden=HIDDEN, mlp_act="relu", mlp_norm="none").cuda()
+        for l in net.modules():
+            if isinstance(l, nn.Linear):
+                nn.init.xavier_uniform_(l.weight)
+                nn.init.normal_(l.bias, 0.0, 0.3)
+        buf.add_strategy(net, it)
+    n = 200
+    feat = (rng.random((n, 34)) < 0.3).astype(np.float32)
+    mask = np.zeros((n, 16), np.float32)
+    for r in range(n):
+        mask[r, rng.choice(16, rng.integers(1, 5), replace=False)] = 1
+    x, m = torch.from_numpy(feat).cuda(), torch.from_numpy(mask).cuda()
+    want = torch.zeros_like(m)
+    tot = sum(buf.weights)
+    with torch.no_grad():
+        for net, w in zip(buf.strategies, buf.weights):
+            want += positive_regret_policy(net(x), m) * (w / tot)
+    got = buf.average_policy_batch(x, m)
+    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-6)
+    one = buf.get_average_policy(feat[3], mask[3])
+    assert one.dtype == np.float32 and one.shape == (16,) and np.all(one[mask[3] == 0] == 0)
+    np.testing.assert_allclose(one, want[3].cpu().numpy(), rtol=2e-5, atol=2e-6)
+    # the cache follows the lists
+    buf.strategies.pop(0)
+    buf.weights.pop(0)
+    got2 = buf.average_policy_batch(x, m)
+    assert not torch.equal(got, got2) and len(buf._blob_of) == 11

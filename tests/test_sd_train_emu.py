@@ -185,3 +185,44 @@ def test_python_binding_drives_the_emulated_kernel(emu):
     small.buffer.add_batch(*(torch.from_numpy(x[:20]) for x in (feat, target, mask)))
     assert np.isfinite(small.train(batch_size=128, epochs=2)) and small._fused.steps_done == 2
     assert AdvantageNetwork(34, 16, device="cpu").train() == 0.0             # empty buffer
+
+
+def test_average_policy_kernels_match_the_reference_loop(emu):
+    """sd_avgpol_kernel + sd_avgpol_reduce_kernel (emulated) through StrategyBuffer against the reference's loop of
+    batch-1 forwards (deep_cfr.py:136-160, here: torch on the CPU): single decisions, a batch that is not a multiple of
+    the 64-row chunk, the max_size eviction and the cache invalidation when the lists change."""
+    from scopa_b200 import _lib
+    from scopa_b200.algorithms.deep_cfr.deep_cfr import HIDDEN, StrategyBuffer
+    from scopa_b200.algorithms.deep_cfr.nets import FlexibleNet
+
+    entry = emu.emu_ms_sdcfr_average_policy
+    entry.argtypes, entry.restype = _lib._SIGS["ms_sdcfr_average_policy"]
+    torch.manual_seed(8)
+    rng = np.random.default_rng(8)
+
+    def snapshot():
+        net = FlexibleNet(mode="mlp", input_shape=(34,), output_dim=16, mlp_hidden=HIDDEN, mlp_act="relu", mlp_norm="none")
+        for l in net.modules():
+            if isinstance(l, nn.Linear):
+                nn.init.xavier_uniform_(l.weight)
+                nn.init.normal_(l.bias, 0.0, 0.3)
+        return net
+
+    fast, ref = StrategyBuffer(max_size=4), StrategyBuffer(max_size=4)
+    fast._entry = entry
+    feat, _, mask, _ = make_problem(rng, 130, 1, 1)
+    assert np.array_equal(fast.get_average_policy(feat[0], mask[0]), mask[0] / mask[0].sum())     # empty buffer: uniform
+    for it in range(1, 7):                       # six snapshots into a buffer of four: the two oldest are evicted
+        net = snapshot()
+        fast.add_strategy(net, it)
+        ref.add_strategy(net, it)
+        for r in (0, 5):
+            a, b = fast.get_average_policy(feat[r], mask[r]), ref.get_average_policy(feat[r], mask[r])
+            assert a.dtype == np.float32 and a.shape == (16,)
+            np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-6)   # pos / z amplifies the sgemm-order rounding of the advantages
+            assert np.all(a[mask[r] == 0] == 0)
+    assert fast.weights == [4, 5, 6, 7] and len(fast._blob_of) == 4
+    got = fast.average_policy_batch(torch.from_numpy(feat), torch.from_numpy(mask)).numpy()
+    want = np.stack([ref.get_average_policy(feat[r], mask[r]) for r in range(130)])
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)
+    assert float(got.sum(1).max()) < 1 + 1e-5
