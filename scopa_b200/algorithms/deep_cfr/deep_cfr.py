@@ -336,9 +336,10 @@ class DeepCFR:
                 self.evaluate_vs_random(num_episodes=eval_episodes)
 
     # -- whole-game views of the average policy (device-batched; not in the reference) --------------------
-    def average_policy_table(self):
-        """[S, 4] float64 CUDA tensor: get_policy() of every infoset of the deal at once, restricted to the legal
-        actions in hand order and normalised the way evaluate_vs_random does (uniform if the sum is <= 0)."""
+    def _policy_inputs(self):
+        """Features / masks / legal-action lists of every infoset of the deal as device tensors (static: built once)."""
+        if getattr(self, "_pol_in", None) is not None:
+            return self._pol_in
         from ...solver import Solver
         if getattr(self, "_solver", None) is None:
             self._solver = Solver(self._root[0], self._root[1], device=self.device)
@@ -360,6 +361,14 @@ class DeepCFR:
         legal = torch.from_numpy(np.where(st["legal"] == 255, 0, st["legal"]).astype(np.int64)).to(self.device)
         nl = torch.from_numpy(st["nlegal"].astype(np.int64)).to(self.device)
         player = torch.from_numpy(st["player"]).to(self.device)
+        self._pol_in = (x, m, legal, nl, player)
+        return self._pol_in
+
+    def average_policy_table(self):
+        """[S, 4] float64 CUDA tensor: get_policy() of every infoset of the deal at once, restricted to the legal
+        actions in hand order and normalised the way evaluate_vs_random does (uniform if the sum is <= 0)."""
+        x, m, legal, nl, player = self._policy_inputs()
+        S = x.shape[0]
         pol16 = torch.zeros((S, 16), dtype=torch.float32, device=self.device)
         with torch.no_grad():
             for p in range(self.num_players):
