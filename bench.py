@@ -636,6 +636,18 @@ def run_ours(args):
                                          "not the MMA alone; 27136 algorithmic FLOP per inference (un-padded)"}}
         sd_obj[pname] = o
     sd_obj["value"] = sd_obj["bf16_tcgen05"]["inferences_per_sec"]
+    try:       # tensor roofline of the SDCFR section: un-padded algorithmic FLOP of whole traversals over the sustained bf16 peak
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            _pk = json.load(f)
+        tf_peak, tf_src = float(_pk.get("bf16_tflops_sustained") or _pk["bf16_tflops"]), "measured, sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        tf_peak, tf_src = 2250.0, "fallback: nominal dense bf16 (B200_PROFILING.md)"
+    sd_obj["roofline"] = {"bound": "tensor", "achieved": sd_obj["bf16_tcgen05"]["algorithmic_tflops"], "peak": tf_peak,
+                          "unit": "TFLOP/s", "frac": sd_obj["bf16_tcgen05"]["algorithmic_tflops"] / tf_peak, "traffic": None,
+                          "kernel": "sd_forward_kernel<1>", "peak_source": tf_src,
+                          "note": "numerator = 27 136 FLOP x inferences of WHOLE traversals (env steps, sampling, backward levels "
+                                  "and sample emission included in the time), so this is a floor on the tensor-pipe share; "
+                                  "K = 34 / N = 16 layers pad to MMA tiles (profiles/README.md section 3)"}
     if rank == 0:
         try:
             sd_obj["train"] = bench_sd_train(dev, _lib)
