@@ -217,7 +217,7 @@ class DeepCFR:
     """Main Deep CFR algorithm."""
 
     def __init__(self, game, num_players=2, device="cuda", precision="fp32", traversals_per_iteration=1, seed=0,
-                 verbose=False, optimizer="torch"):
+                 verbose=False, optimizer="torch", device_eval=False):
         self.game = game
         self.num_players = num_players
         self.device = device
@@ -225,6 +225,7 @@ class DeepCFR:
         self.traversals_per_iteration = int(traversals_per_iteration)
         self.seed = int(seed)
         self.verbose = verbose
+        self.device_eval = bool(device_eval)
         self._trav_count = 0
         self.input_dim = self._estimate_input_dim()
         if verbose:
@@ -283,7 +284,31 @@ class DeepCFR:
         self.advantage_nets[player].buffer.add_batch(feat, target, mask)
         return float(value.mean().item())
 
-    def evaluate_vs_random(self, num_episodes=100):
+    def _evaluate_vs_random_device(self, num_episodes):
+        """All episodes in two launches of the policy-evaluation kernel (`ms_eval_policies`, the path evaluate_agent uses
+        for the tabular trainers): seat 0 for the first half of the episodes, seat 1 afterwards, like the loop below.
+        The average policy of every infoset comes from `average_policy_table()`; actions are drawn from a Philox stream
+        whose seed is taken from np.random (so np.random.seed() still makes a run repeatable)."""
+        tab = self.average_policy_table()
+        sv = self._solver
+        uni = sv.uniform_policy()
+        n0 = int(np.ceil(num_episodes / 2))                       # episodes with episode < num_episodes / 2
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+        r_a, s_a = sv.evaluate(tab, uni, n0, philox_seed=seed, first_game=0)
+        r_b, s_b = sv.evaluate(uni, tab, num_episodes - n0, philox_seed=seed, first_game=n0)
+        total_reward = float(r_a.double().sum().item()) - float(r_b.double().sum().item())   # zero-sum: r1 = -r0
+        s_a, s_b = s_a.long(), s_b.long()
+        trained = int(s_a[:, 0].sum().item()) + int(s_b[:, 1].sum().item())
+        opponent = int(s_a[:, 1].sum().item()) + int(s_b[:, 0].sum().item())
+        avg_reward = total_reward / num_episodes
+        scopas = [trained / num_episodes, opponent / num_episodes]
+        self.training_history["eval_rewards"].append(avg_reward)
+        self.training_history["eval_scopas"].append(scopas)
+        return avg_reward, scopas
+
+    def evaluate_vs_random(self, num_episodes=100, on_device=None):
+        if (self.device_eval if on_device is None else on_device) and num_episodes > 0:
+            return self._evaluate_vs_random_device(num_episodes)
         total_reward = 0.0
         total_trained_scopas = 0
         total_random_scopas = 0
