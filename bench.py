@@ -653,6 +653,10 @@ def run_ours(args):
             sd_obj["train"] = bench_sd_train(dev, _lib)
         except Exception as e:      # an auxiliary section must not take the headline line down with it
             sd_obj["train"] = {"error": repr(e)}
+        try:
+            sd_obj["drop_in_train"] = bench_sd_dropin(dev)
+        except Exception as e:
+            sd_obj["drop_in_train"] = {"error": repr(e)}
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu_mccfr = cpu_env = None
@@ -771,6 +775,34 @@ def bench_sd_train(dev, _lib, epochs=10, calls=20, rows=100_000):
     out["note"] = ("sd_train_kernel: one CTA keeps the 13 776 weights, the minibatch and all activations in shared memory "
                    "for every epoch of the call; bit-identical to the host emulation of the same source "
                    "(tests/emu), which is pinned to torch on the CPU")
+    return out
+
+
+def bench_sd_dropin(dev, iterations=20):
+    """DeepCFR.train through the drop-in API in the reference's own configuration (BASELINE.json configs[3]: one
+    traversal per player per iteration, 10 optimiser epochs, evaluation against random every 5 iterations with 50
+    episodes; deep_cfr.py:431-490), wall clock per iteration: the default build of the class (PyTorch optimiser,
+    episode-loop evaluation) beside optimizer="fused" + device_eval=True."""
+    import torch
+    from scopa_b200 import pyspiel_compat as pyspiel
+    from scopa_b200.envs import openspiel_mini_scopa  # noqa: F401  (registers "mini_scopa")
+    from scopa_b200.algorithms.deep_cfr import DeepCFR
+    game = pyspiel.load_game("mini_scopa")
+    out = {"config": {"workload": f"DeepCFR(game).train(iterations={iterations}, advantage_epochs=10, eval_freq=5), 50 evaluation "
+                                  "episodes, 1 traversal per player per iteration, fp32 inference"}}
+    for name, kw in (("default", {}), ("fused_optimizer_device_eval", {"optimizer": "fused", "device_eval": True})):
+        torch.manual_seed(3)
+        np.random.seed(3)
+        d = DeepCFR(game, 2, dev, seed=3, **kw)
+        d.train(iterations=5, advantage_epochs=10, eval_freq=5, eval_episodes=50)        # warm-up (incl. one evaluation)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d.train(iterations=iterations, advantage_epochs=10, eval_freq=5, eval_episodes=50)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[name] = {"ms_per_iteration": 1e3 * dt / iterations, "iterations_per_sec": iterations / dt,
+                     "last_eval_reward_vs_random": d.training_history["eval_rewards"][-1]}
+    out["speedup"] = out["default"]["ms_per_iteration"] / out["fused_optimizer_device_eval"]["ms_per_iteration"]
     return out
 
 
