@@ -16,6 +16,7 @@ same arithmetic in fp32, minibatches drawn without replacement from torch's CUDA
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 import torch.optim as optim
 
 from ... import codec, sdcfr
@@ -137,6 +138,56 @@ class AdvantageNetwork:
         return u.topk(batch_size, dim=1).indices.to(torch.int32).contiguous()
 
 
+class NetSnapshot:
+    """A stored strategy net as ONE cloned weight blob (a single device copy) instead of a freshly constructed
+    FlexibleNet + load_state_dict (about 0.8 ms of host time per snapshot, more than a whole fused train() call).
+    Calling it forwards a batch like the module would; anything else a caller might ask of the stored net
+    (`parameters()`, `state_dict()`, `.backbone`, ...) materialises the FlexibleNet once, with its parameters as views
+    of the blob."""
+
+    _SHAPES = ((128, 34), (128,), (64, 128), (64,), (16, 64), (16,))
+
+    def __init__(self, blob, input_dim=34):
+        assert blob.numel() == sdcfr.NET_FLOATS and input_dim == 34
+        self._blob = blob.detach().clone()
+        self._input_dim = input_dim
+        self._module = None
+
+    def _views(self):
+        out, off = [], 0
+        for shp in self._SHAPES:
+            n = int(np.prod(shp))
+            out.append(self._blob[off:off + n].view(shp))
+            off += n
+        return out
+
+    def __call__(self, x):
+        w1, b1, w2, b2, w3, b3 = self._views()
+        return F.linear(F.relu(F.linear(F.relu(F.linear(x, w1, b1)), w2, b2)), w3, b3)
+
+    def module(self):
+        if self._module is None:
+            net = FlexibleNet(mode="mlp", input_shape=(self._input_dim,), output_dim=16, mlp_hidden=HIDDEN, mlp_act="relu",
+                              mlp_norm="none").to(self._blob.device)
+            params = [net.backbone[0].fc.weight, net.backbone[0].fc.bias, net.backbone[1].fc.weight,
+                      net.backbone[1].fc.bias, net.head.weight, net.head.bias]
+            for p, v in zip(params, self._views()):
+                p.data = v
+            self._module = net
+        return self._module
+
+    def parameters(self):
+        return self.module().parameters()
+
+    def state_dict(self, *args, **kwargs):
+        return self.module().state_dict(*args, **kwargs)
+
+    def __getattr__(self, name):                 # reached only when normal lookup fails
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.module(), name)
+
+
 class StrategyBuffer:
     """Stores past strategies for final policy computation.
 
@@ -168,7 +219,8 @@ class StrategyBuffer:
             self._blob_of = {i: v for i, v in self._blob_of.items() if i in live}
             for s_ in self.strategies:
                 if id(s_) not in self._blob_of:
-                    self._blob_of[id(s_)] = (s_, sdcfr.flatten_net(s_))
+                    blob = getattr(s_, "_blob", None)            # NetSnapshot: already flat
+                    self._blob_of[id(s_)] = (s_, blob if blob is not None else sdcfr.flatten_net(s_))
             nets = torch.stack([self._blob_of[i][1] for i in key[0]]).contiguous()
             total_weight = sum(self.weights)
             # the reference multiplies a float32 array by the Python float weight / total_weight
@@ -186,7 +238,8 @@ class StrategyBuffer:
         if not self.strategies:
             mask = np.asarray(legal_actions_mask).astype(np.float32)
             return mask / mask.sum()
-        dev = next(self.strategies[0].parameters()).device
+        first = self.strategies[0]
+        dev = first._blob.device if isinstance(first, NetSnapshot) else next(first.parameters()).device
         x = torch.as_tensor(np.asarray(state_features), dtype=torch.float32, device=dev).unsqueeze(0)
         m = torch.as_tensor(np.asarray(legal_actions_mask), dtype=torch.float32, device=dev).unsqueeze(0)
         if dev.type == "cuda" or self._entry is not None:
@@ -353,9 +406,13 @@ class DeepCFR:
                 self.training_history["buffer_sizes"][player].append(len(self.advantage_nets[player].buffer))
             if iteration > 0:
                 for player in range(self.num_players):
-                    strategy_net = FlexibleNet(mode="mlp", input_shape=(self.input_dim,), output_dim=16,
-                                               mlp_hidden=HIDDEN, mlp_act="relu", mlp_norm="none").to(self.device)
-                    strategy_net.load_state_dict(self.advantage_nets[player].net.state_dict())
+                    adv = self.advantage_nets[player]
+                    if adv._fused is not None:               # fused configuration: one device copy per snapshot
+                        strategy_net = NetSnapshot(adv.blob(), self.input_dim)
+                    else:
+                        strategy_net = FlexibleNet(mode="mlp", input_shape=(self.input_dim,), output_dim=16,
+                                                   mlp_hidden=HIDDEN, mlp_act="relu", mlp_norm="none").to(self.device)
+                        strategy_net.load_state_dict(adv.net.state_dict())
                     self.strategy_buffers[player].add_strategy(strategy_net, iteration)
             if iteration % eval_freq == 0 and eval_episodes > 0:
                 self.evaluate_vs_random(num_episodes=eval_episodes)

@@ -226,3 +226,46 @@ def test_average_policy_kernels_match_the_reference_loop(emu):
     want = np.stack([ref.get_average_policy(feat[r], mask[r]) for r in range(130)])
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)
     assert float(got.sum(1).max()) < 1 + 1e-5
+
+
+def test_net_snapshot_behaves_like_the_stored_module(emu):
+    """NetSnapshot (the fused configuration's stored strategy net: one blob copy) against a FlexibleNet copy made the
+    reference's way (construct + load_state_dict, deep_cfr.py:460-472)."""
+    from scopa_b200 import _lib, sdcfr
+    from scopa_b200.algorithms.deep_cfr.deep_cfr import HIDDEN, NetSnapshot, StrategyBuffer
+    from scopa_b200.algorithms.deep_cfr.nets import FlexibleNet
+
+    torch.manual_seed(12)
+    live = FlexibleNet(mode="mlp", input_shape=(34,), output_dim=16, mlp_hidden=HIDDEN, mlp_act="relu", mlp_norm="none")
+    blob = sdcfr.flatten_parameters_(live)
+    snap = NetSnapshot(blob)
+    copy_ = FlexibleNet(mode="mlp", input_shape=(34,), output_dim=16, mlp_hidden=HIDDEN, mlp_act="relu", mlp_norm="none")
+    copy_.load_state_dict(live.state_dict())
+    x = torch.rand(9, 34)
+    with torch.no_grad():
+        want = copy_(x)
+        assert torch.equal(snap(x), want)
+        blob += 1.0                                         # the live net trains on: the snapshot must not follow
+        assert torch.equal(snap(x), want) and not torch.equal(live(x), want)
+        assert snap._module is None                         # nothing above needed the nn.Module
+        # module-shaped access materialises a FlexibleNet over the same blob
+        assert [tuple(p.shape) for p in snap.parameters()] == [tuple(p.shape) for p in copy_.parameters()]
+        assert set(snap.state_dict()) == set(copy_.state_dict())
+        assert all(torch.equal(snap.state_dict()[k], copy_.state_dict()[k]) for k in copy_.state_dict())
+        assert torch.equal(snap.backbone[0].fc.weight, copy_.backbone[0].fc.weight) and torch.equal(snap.module()(x), want)
+        assert snap.backbone[0].fc.weight.data_ptr() == snap._blob.data_ptr()
+    with pytest.raises(AttributeError):
+        snap.no_such_attribute
+    # inside a StrategyBuffer: same average policy as module snapshots, through the emulated kernels
+    entry = emu.emu_ms_sdcfr_average_policy
+    entry.argtypes, entry.restype = _lib._SIGS["ms_sdcfr_average_policy"]
+    a, b = StrategyBuffer(), StrategyBuffer()
+    a._entry = b._entry = entry
+    rng = np.random.default_rng(1)
+    feat, _, mask, _ = make_problem(rng, 3, 1, 1)
+    for it in (1, 2, 3):
+        net = FlexibleNet(mode="mlp", input_shape=(34,), output_dim=16, mlp_hidden=HIDDEN, mlp_act="relu", mlp_norm="none")
+        a.add_strategy(net, it)
+        b.add_strategy(NetSnapshot(sdcfr.flatten_net(net)), it)
+    for r in range(3):
+        assert np.array_equal(a.get_average_policy(feat[r], mask[r]), b.get_average_policy(feat[r], mask[r]))
