@@ -296,6 +296,7 @@ class DeepCFR:
         words, order = root_of(game)
         self._root = (tuple(int(w) for w in words), int(order))
         self._traverser = sdcfr.Traverser(words, order, device=device)
+        self._root_state = None
 
     def _estimate_input_dim(self):
         test_state = self.game.new_initial_state()
@@ -398,8 +399,11 @@ class DeepCFR:
     def train(self, iterations=100, advantage_epochs=10, eval_freq=5, eval_episodes=50):
         for iteration in range(iterations):
             for player in range(self.num_players):
-                state = self.game.new_initial_state()
-                value = self._external_sampling_cfr(state, player)
+                # the traversal only reads the root (the reference builds a fresh one per traversal, :443; here that
+                # is a deal on the device plus a read-back, so one root object serves every iteration)
+                if self._root_state is None:
+                    self._root_state = self.game.new_initial_state()
+                value = self._external_sampling_cfr(self._root_state, player)
                 loss = self.advantage_nets[player].train(epochs=advantage_epochs)
                 self.training_history["losses"][player].append(loss)
                 self.training_history["values"][player].append(value)
