@@ -748,7 +748,9 @@ def bench_sd_train(dev, _lib, epochs=10, calls=20, rows=100_000):
     feat = (torch.rand((rows, 34), device=dev) < 0.25).float()
     mask = (torch.rand((rows, 16), device=dev) < 0.2).float()
     target = (torch.rand((rows, 16), device=dev) * 2 - 1) * mask
-    for name in ("fused", "torch"):
+    # the cluster form has not run on a GPU yet (written after the round's GPU budget was spent): opt-in here
+    variants = ("fused", "torch") + (("fused-cluster",) if os.environ.get("SCOPA_B200_BENCH_CLUSTER") == "1" else ())
+    for name in variants:
         adv = AdvantageNetwork(34, 16, device=dev, optimizer=name)
         adv.buffer.add_batch(feat, target, mask)
         for _ in range(3):
@@ -762,7 +764,7 @@ def bench_sd_train(dev, _lib, epochs=10, calls=20, rows=100_000):
         dt = time.perf_counter() - t0
         out[name] = {"us_per_step": 1e6 * dt / (calls * epochs), "ms_per_call": 1e3 * dt / calls, "last_loss": loss,
                      "our_launches_per_call": (_lib.launch_count() - l0) / calls}
-        if name == "fused":     # the kernel alone (CUDA events around the launches, minibatch rows drawn beforehand)
+        if name != "torch":     # the kernel alone (CUDA events around the launches, minibatch rows drawn beforehand)
             idx = adv._sample_rows(128, epochs)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

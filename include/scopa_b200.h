@@ -299,6 +299,16 @@ int ms_sdcfr_train(float* d_net, float* d_adam_m, float* d_adam_v, int64_t steps
                    int32_t epochs, double lr, double beta1, double beta2, double eps, double max_norm, float* d_loss,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ms_sdcfr_train_cluster: the same optimiser steps as ms_sdcfr_train (same arguments; d_workspace is not used) on a
+ *   thread-block cluster of 8 CTAs = 8 SMs: CTA c runs forward / backward on minibatch rows 16c..16c+15 with its own
+ *   copy of the weights, the eight partial gradients are added through distributed shared memory, CTA c applies Adam
+ *   to parameter slice c and stores the new values into all eight weight copies; three cluster barriers per step.
+ *   Gradients are summed in a different order than in ms_sdcfr_train, so the two agree to fp32 rounding, not bitwise. */
+int ms_sdcfr_train_cluster(float* d_net, float* d_adam_m, float* d_adam_v, int64_t steps_done, const float* d_feat,
+                           const float* d_target, const float* d_mask, int64_t n_rows, const int32_t* d_idx, int32_t batch,
+                           int32_t epochs, double lr, double beta1, double beta2, double eps, double max_norm,
+                           float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ms_sdcfr_average_policy: StrategyBuffer.get_average_policy (deep_cfr.py:136-160) for n_rows states and ALL n_nets
  *   stored strategy nets at once: d_policy[row] = sum over k (ascending) of positive_regret_policy(net_k(d_feat[row]),
  *   d_mask[row]) * d_weights[k], positive_regret_policy = relu(adv) * mask / max(sum, 1e-8) (nets.py:93-101).

@@ -73,6 +73,8 @@ _SIGS = {
     "ms_sdcfr_train_workspace_bytes": ([], C.c_size_t),
     "ms_sdcfr_train": ([vp, vp, vp, i64, vp, vp, vp, i64, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, C.c_size_t, vp],
                        C.c_int),
+    "ms_sdcfr_train_cluster": ([vp, vp, vp, i64, vp, vp, vp, i64, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, C.c_size_t, vp],
+                               C.c_int),
     "ms_sdcfr_average_policy_workspace_bytes": ([i32, i64], C.c_size_t),
     "ms_sdcfr_average_policy": ([vp, vp, i32, vp, vp, i64, vp, vp, C.c_size_t, vp], C.c_int),
     "ms_full_deal_from_seeds": ([vp, i64, vp, vp, vp], C.c_int),

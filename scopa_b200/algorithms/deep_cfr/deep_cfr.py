@@ -11,7 +11,8 @@ frontier of each level as one batched inference (csrc/ms_sdcfr.cu; `precision="f
 the reference's precision, `"bf16"` = tcgen05 tensor-core path), and the samples land in a device-resident
 replay buffer.  The optimiser (Adam, masked MSE, clip-norm 1.0, as the reference) is PyTorch's by default;
 `optimizer="fused"` runs all epochs of a train() call in one launch of sd_train_kernel (csrc/ms_sd_train.cuh):
-same arithmetic in fp32, minibatches drawn without replacement from torch's CUDA generator.
+same arithmetic in fp32, minibatches drawn without replacement from torch's CUDA generator; `"fused-cluster"` is the
+8-CTA cluster form of that kernel (csrc/ms_sd_train_cluster.cuh).
 """
 import numpy as np
 import torch
@@ -68,8 +69,8 @@ class AdvantageNetwork:
     """Manages the advantage network for one player."""
 
     def __init__(self, input_dim, num_actions, device="cuda", lr=5e-4, precision="fp32", optimizer="torch"):
-        if optimizer not in ("torch", "fused"):
-            raise ValueError(f"optimizer must be 'torch' or 'fused', not {optimizer!r}")
+        if optimizer not in ("torch", "fused", "fused-cluster"):
+            raise ValueError(f"optimizer must be 'torch', 'fused' or 'fused-cluster', not {optimizer!r}")
         self.device = device
         self.num_actions = num_actions
         self.precision = sdcfr.TENSOR_CORE if precision == "bf16" else sdcfr.FP32
@@ -83,9 +84,10 @@ class AdvantageNetwork:
         self.criterion = nn.MSELoss()
         self.buffer = DeviceReplayBuffer(100000, device)
         self._fused = None
-        if optimizer == "fused":
+        if optimizer != "torch":
             # the module's parameters become views of one flat blob that the kernel updates in place
-            self._fused = sdcfr.FusedAdam(sdcfr.flatten_parameters_(self.net), lr=lr)
+            self._fused = sdcfr.FusedAdam(sdcfr.flatten_parameters_(self.net), lr=lr,
+                                          kernel="cluster" if optimizer == "fused-cluster" else "cta")
 
     def blob(self):
         return self._fused.blob if self._fused is not None else sdcfr.flatten_net(self.net)

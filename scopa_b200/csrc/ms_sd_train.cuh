@@ -123,19 +123,21 @@ __device__ __forceinline__ void cta_gemm(int M, int N, int K, const float* A, in
     }
 }
 
-// sum of v over the CTA in a fixed order; every thread gets the same float.  red: kThreads + 32 floats.
+// sum of v over a CTA of NT threads in a fixed order; every thread gets the same float.  red: NT + 32 floats.
+template <int NT>
 __device__ __forceinline__ float cta_sum(float v, float* red) {
-    const int tid = (int)threadIdx.x, per = kThreads / 32;
+    static_assert(NT % 32 == 0, "whole warps");
+    const int tid = (int)threadIdx.x, per = NT / 32;
     red[tid] = v;
     __syncthreads();
     if (tid < 32) {
         float s = 0.f;
         for (int j = 0; j < per; ++j) s += red[tid * per + j];
-        red[kThreads + tid] = s;
+        red[NT + tid] = s;
     }
     __syncthreads();
     float s = 0.f;
-    for (int j = 0; j < 32; ++j) s += red[kThreads + j];
+    for (int j = 0; j < 32; ++j) s += red[NT + j];
     __syncthreads();
     return s;
 }
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(sdt::kThreads, 1) sd_train_kernel(SdTrainArgs 
             }
             S[SD + i * LDO + j] = d;
         });
-        const float loss = cta_sum(sq, S + SRED) * inv_n;    // (barriers inside: d is complete afterwards)
+        const float loss = cta_sum<kThreads>(sq, S + SRED) * inv_n;    // (barriers inside: d is complete afterwards)
         if (tid == 0) a.loss[ep] = loss;
         // ---- backward: layer 3
         cta_gemm<4, 4>(kOut, kH2, Mp, S + SD, 1, LDO, S + SH2, 1, LD2,
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(sdt::kThreads, 1) sd_train_kernel(SdTrainArgs 
             float g = a.grad[e];
             part += g * g;
         }
-        const float norm = sqrtf(cta_sum(part, S + SRED));
+        const float norm = sqrtf(cta_sum<kThreads>(part, S + SRED));
         const float coef = fminf(fmax_norm / (norm + 1e-6f), 1.0f);
         b1pow *= a.beta1;
         b2pow *= a.beta2;

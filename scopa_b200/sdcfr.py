@@ -78,8 +78,9 @@ class FusedAdam:
     parameters live in a flat fp32 blob.  `step()` runs `epochs` optimiser steps of AdvantageNetwork.train
     (/root/reference/src/algorithms/deep_cfr/deep_cfr.py:77-110) in one kernel launch."""
 
-    def __init__(self, blob, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, _entry=None):
-        """`_entry` (tests only): a host function with ms_sdcfr_train's signature, e.g. the emulated kernel of
+    def __init__(self, blob, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, kernel="cta", _entry=None):
+        """`kernel`: "cta" = sd_train_kernel (one CTA), "cluster" = sd_train_cluster_kernel (8 CTAs exchanging gradients
+        and weights through distributed shared memory; `ms_sdcfr_train_cluster`).  `_entry` (tests only): a host function with ms_sdcfr_train's signature, e.g. the emulated kernel of
         tests/emu -- the tensors then live on the CPU.  The product path always launches the CUDA kernel."""
         assert blob.dtype == torch.float32 and blob.numel() == NET_FLOATS and blob.is_contiguous()
         self._emulated = _entry is not None
@@ -89,8 +90,11 @@ class FusedAdam:
         else:
             if not blob.is_cuda:
                 raise _lib.MsError("FusedAdam needs a CUDA blob: scopa_b200 has no CPU path")
+            if kernel not in ("cta", "cluster"):
+                raise ValueError(f"kernel must be 'cta' or 'cluster', not {kernel!r}")
             lib = _lib.load()
-            self._entry, ws_bytes = lib.ms_sdcfr_train, lib.ms_sdcfr_train_workspace_bytes()
+            self._entry = lib.ms_sdcfr_train if kernel == "cta" else lib.ms_sdcfr_train_cluster
+            ws_bytes = lib.ms_sdcfr_train_workspace_bytes()
         self.blob = blob
         self.m = torch.zeros_like(blob)
         self.v = torch.zeros_like(blob)

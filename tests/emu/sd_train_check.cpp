@@ -14,8 +14,11 @@
 
 extern "C" int emu_ms_sdcfr_average_policy(const float*, const float*, int, const float*, const float*, long long, float*,
                                            void*, size_t, void*);
-extern "C" int emu_sd_train(float*, float*, float*, long long, const float*, const float*, const float*, long long,
-                            const int*, int, int, double, double, double, double, double, float*, float*);
+extern "C" int emu_ms_sdcfr_train(float*, float*, float*, long long, const float*, const float*, const float*, long long,
+                                  const int*, int, int, double, double, double, double, double, float*, void*, size_t, void*);
+extern "C" int emu_ms_sdcfr_train_cluster(float*, float*, float*, long long, const float*, const float*, const float*,
+                                          long long, const int*, int, int, double, double, double, double, double, float*,
+                                          void*, size_t, void*);
 
 static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
 static uint32_t rnd() {
@@ -101,8 +104,18 @@ static int check_avgpol(int K, int n, int reps) {
 int main(int argc, char** argv) {
     if (argc > 1 && !strcmp(argv[1], "avgpol"))
         return check_avgpol(argc > 2 ? atoi(argv[2]) : 8, argc > 3 ? atoi(argv[3]) : 70, argc > 4 ? atoi(argv[4]) : 0);
+    // sd_train_check [cluster] [batch] [epochs] [n_rows] [timing_reps]: "cluster" selects ms_sdcfr_train_cluster
+    const bool cluster = argc > 1 && !strcmp(argv[1], "cluster");
+    if (cluster) { --argc; ++argv; }
     const int batch = argc > 1 ? atoi(argv[1]) : 128, epochs = argc > 2 ? atoi(argv[2]) : 6;
     const int n_rows = argc > 3 ? atoi(argv[3]) : 4096, reps = argc > 4 ? atoi(argv[4]) : 50;
+    typedef int (*train_fn)(float*, float*, float*, int64_t, const float*, const float*, const float*, int64_t, const int32_t*,
+                            int32_t, int32_t, double, double, double, double, double, float*, void*, size_t, void*);
+    typedef int (*emu_fn)(float*, float*, float*, long long, const float*, const float*, const float*, long long, const int*,
+                          int, int, double, double, double, double, double, float*, void*, size_t, void*);
+    const train_fn dev_train = cluster ? ms_sdcfr_train_cluster : ms_sdcfr_train;
+    const emu_fn emu_train = cluster ? emu_ms_sdcfr_train_cluster : emu_ms_sdcfr_train;
+    const char* which = cluster ? "cluster kernel" : "one-CTA kernel";
     const int NF = 13776;
     std::vector<float> net(NF), m(NF, 0.f), v(NF, 0.f), feat((size_t)n_rows * 34), target((size_t)n_rows * 16),
         mask((size_t)n_rows * 16), loss_e(epochs), grad(NF);
@@ -132,8 +145,8 @@ int main(int argc, char** argv) {
     }
     if (getenv("SD_TRAIN_EMU_ONLY")) {
         std::vector<float> h = net;
-        emu_sd_train(h.data(), m.data(), v.data(), 0, feat.data(), target.data(), mask.data(), n_rows, idx.data(), batch,
-                     epochs, 5e-4, 0.9, 0.999, 1e-8, 1.0, loss_e.data(), grad.data());
+        emu_train(h.data(), m.data(), v.data(), 0, feat.data(), target.data(), mask.data(), n_rows, idx.data(), batch,
+                  epochs, 5e-4, 0.9, 0.999, 1e-8, 1.0, loss_e.data(), grad.data(), grad.size() * 4, nullptr);
         for (int e = 0; e < epochs; ++e) printf("emu loss[%d] %.9g (%a)\n", e, loss_e[e], loss_e[e]);
         return 0;
     }
@@ -154,13 +167,13 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
     // two calls (steps_done 0, then epochs/2) to cover the bias-correction hand-over
     const int e1 = epochs / 2, e2 = epochs - e1;
-    int rc = ms_sdcfr_train(d_net, d_m, d_v, 0, d_feat, d_target, d_mask, n_rows, d_idx, batch, e1, 5e-4, 0.9, 0.999, 1e-8,
+    int rc = dev_train(d_net, d_m, d_v, 0, d_feat, d_target, d_mask, n_rows, d_idx, batch, e1, 5e-4, 0.9, 0.999, 1e-8,
                             1.0, d_loss, d_ws, ws, nullptr);
     if (rc == 0)
-        rc = ms_sdcfr_train(d_net, d_m, d_v, e1, d_feat, d_target, d_mask, n_rows, d_idx + (size_t)e1 * batch, batch, e2,
+        rc = dev_train(d_net, d_m, d_v, e1, d_feat, d_target, d_mask, n_rows, d_idx + (size_t)e1 * batch, batch, e2,
                             5e-4, 0.9, 0.999, 1e-8, 1.0, d_loss + e1, d_ws, ws, nullptr);
     if (rc) {
-        printf("ms_sdcfr_train failed: %d %s\n", rc, ms_last_error());
+        printf("%s failed: %d %s\n", which, rc, ms_last_error());
         return 2;
     }
     CK(cudaDeviceSynchronize());
@@ -171,11 +184,11 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(g_loss.data(), d_loss, epochs * 4, cudaMemcpyDeviceToHost));
     // ---- host emulation of the same kernel source
     std::vector<float> h_net = net;
-    if (emu_sd_train(h_net.data(), m.data(), v.data(), 0, feat.data(), target.data(), mask.data(), n_rows, idx.data(), batch,
-                     e1, 5e-4, 0.9, 0.999, 1e-8, 1.0, loss_e.data(), grad.data()) ||
-        emu_sd_train(h_net.data(), m.data(), v.data(), e1, feat.data(), target.data(), mask.data(), n_rows,
-                     idx.data() + (size_t)e1 * batch, batch, e2, 5e-4, 0.9, 0.999, 1e-8, 1.0, loss_e.data() + e1,
-                     grad.data())) {
+    if (emu_train(h_net.data(), m.data(), v.data(), 0, feat.data(), target.data(), mask.data(), n_rows, idx.data(), batch, e1,
+                  5e-4, 0.9, 0.999, 1e-8, 1.0, loss_e.data(), grad.data(), grad.size() * 4, nullptr) ||
+        emu_train(h_net.data(), m.data(), v.data(), e1, feat.data(), target.data(), mask.data(), n_rows,
+                  idx.data() + (size_t)e1 * batch, batch, e2, 5e-4, 0.9, 0.999, 1e-8, 1.0, loss_e.data() + e1, grad.data(),
+                  grad.size() * 4, nullptr)) {
         printf("emulation failed\n");
         return 2;
     }
@@ -187,19 +200,19 @@ int main(int argc, char** argv) {
     size_t dn = ndiff(g_net, h_net), dm = ndiff(g_m, m), dv = ndiff(g_v, v), dl = ndiff(g_loss, loss_e);
     double moved = 0;
     for (int i = 0; i < NF; ++i) moved = fmax(moved, fabs((double)g_net[i] - net[i]));
-    printf("batch %d epochs %d rows %d: differing words net %zu m %zu v %zu loss %zu (of %d / %d); max |param change| %.3g; "
-           "loss[0] %.6f loss[last] %.6f\n", batch, epochs, n_rows, dn, dm, dv, dl, NF, epochs, moved, g_loss[0],
+    printf("%s, batch %d epochs %d rows %d: differing words net %zu m %zu v %zu loss %zu (of %d / %d); max |param change| %.3g; "
+           "loss[0] %.6f loss[last] %.6f\n", which, batch, epochs, n_rows, dn, dm, dv, dl, NF, epochs, moved, g_loss[0],
            g_loss[epochs - 1]);
     // ---- timing: `reps` launches of `epochs` steps
     if (reps > 0) {
         cudaEvent_t t0, t1;
         CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
         for (int w = 0; w < 3; ++w)
-            ms_sdcfr_train(d_net, d_m, d_v, epochs, d_feat, d_target, d_mask, n_rows, d_idx, batch, epochs, 5e-4, 0.9, 0.999,
+            dev_train(d_net, d_m, d_v, epochs, d_feat, d_target, d_mask, n_rows, d_idx, batch, epochs, 5e-4, 0.9, 0.999,
                            1e-8, 1.0, d_loss, d_ws, ws, nullptr);
         CK(cudaEventRecord(t0));
         for (int r = 0; r < reps; ++r)
-            ms_sdcfr_train(d_net, d_m, d_v, epochs, d_feat, d_target, d_mask, n_rows, d_idx, batch, epochs, 5e-4, 0.9, 0.999,
+            dev_train(d_net, d_m, d_v, epochs, d_feat, d_target, d_mask, n_rows, d_idx, batch, epochs, 5e-4, 0.9, 0.999,
                            1e-8, 1.0, d_loss, d_ws, ws, nullptr);
         CK(cudaEventRecord(t1));
         CK(cudaEventSynchronize(t1));

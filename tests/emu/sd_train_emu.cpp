@@ -6,6 +6,7 @@
 #define ms ms_emu
 #include "../../scopa_b200/csrc/ms_sd_train.cuh"
 #include "../../scopa_b200/csrc/ms_sd_avgpol.cuh"
+#include "../../scopa_b200/csrc/ms_sd_train_cluster.cuh"
 
 extern "C" int emu_sd_train(float* net, float* adam_m, float* adam_v, long long steps_done, const float* feat,
                             const float* target, const float* mask, long long n_rows, const int* idx, int batch,
@@ -51,4 +52,23 @@ extern "C" int emu_ms_sdcfr_average_policy(const float* nets, const float* weigh
     int rc = emu_launch_grid(ms::sd_avgpol_kernel, a, grid, ms::sda::kPolThreads);
     if (rc) return rc;
     return emu_launch_grid(ms::sd_avgpol_reduce_kernel, a, 2, 256);
+}
+
+// ms_sdcfr_train_cluster's signature; the 8 CTAs of the cluster run concurrently (8 x 256 host threads)
+extern "C" int emu_ms_sdcfr_train_cluster(float* net, float* adam_m, float* adam_v, long long steps_done, const float* feat,
+                                          const float* target, const float* mask, long long n_rows, const int* idx,
+                                          int batch, int epochs, double lr, double beta1, double beta2, double eps,
+                                          double max_norm, float* loss, void* workspace, size_t workspace_bytes,
+                                          void* /*stream*/) {
+    if (workspace_bytes < sizeof(float) * ms::sdt::kNetFloats || batch < 1 || batch > ms::sdt::kMaxBatch) return -2;
+    if (epochs == 0) return 0;
+    ms::SdTrainArgs a;
+    a.net = net; a.adam_m = adam_m; a.adam_v = adam_v;
+    a.feat = feat; a.target = target; a.mask = mask; a.n_rows = n_rows;
+    a.idx = idx; a.batch = batch; a.epochs = epochs;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_norm = max_norm;
+    a.b1pow = std::pow(beta1, (double)steps_done);
+    a.b2pow = std::pow(beta2, (double)steps_done);
+    a.loss = loss; a.grad = static_cast<float*>(workspace);
+    return emu_launch_cluster(ms::sd_train_cluster_kernel, a, ms::sdc::kCluster, ms::sdc::kCThreads);
 }

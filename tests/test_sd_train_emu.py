@@ -269,3 +269,71 @@ def test_net_snapshot_behaves_like_the_stored_module(emu):
         b.add_strategy(NetSnapshot(sdcfr.flatten_net(net)), it)
     for r in range(3):
         assert np.array_equal(a.get_average_policy(feat[r], mask[r]), b.get_average_policy(feat[r], mask[r]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sd_train_cluster_kernel (csrc/ms_sd_train_cluster.cuh): 8 CTAs emulated concurrently (8 x 256 host threads), cluster
+# barrier = a barrier over all of them, distributed shared memory = the other blocks' buffers.
+
+def cluster_steps(emu, blob, m, v, steps_done, feat, target, mask, idx):
+    from scopa_b200 import _lib
+    f = emu.emu_ms_sdcfr_train_cluster
+    f.argtypes, f.restype = _lib._SIGS["ms_sdcfr_train_cluster"]
+    idx = np.ascontiguousarray(idx)
+    loss, ws = np.zeros(idx.shape[0], np.float32), np.zeros(NF, np.float32)
+    rc = f(blob.ctypes.data, m.ctypes.data, v.ctypes.data, steps_done, feat.ctypes.data, target.ctypes.data, mask.ctypes.data,
+           feat.shape[0], idx.ctypes.data, idx.shape[1], idx.shape[0], 5e-4, 0.9, 0.999, 1e-8, 1.0, loss.ctypes.data,
+           ws.ctypes.data, ws.nbytes, None)
+    assert rc == 0
+    return loss
+
+
+@pytest.mark.parametrize("batch,epochs,n_rows,scale", [(128, 4, 1000, 1.0), (32, 3, 100, 1.0), (17, 3, 40, 40.0), (1, 2, 1, 1.0),
+                                                      (100, 3, 300, 40.0)])
+def test_emulated_cluster_kernel_matches_torch(emu, batch, epochs, n_rows, scale):
+    """Rows are split 16 per CTA (batch 17: one CTA with 16 rows, one with 1, six with none; batch 100: the 7th CTA has 4)."""
+    rng = np.random.default_rng(batch * 1000 + epochs)
+    net = make_net(batch)
+    blob, m, v = blob_of(net), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+    feat, target, mask, idx = make_problem(rng, n_rows, batch, epochs, scale)
+    t_loss, norms, opt = torch_steps(net, feat, target, mask, idx)
+    c_loss = cluster_steps(emu, blob, m, v, 0, feat, target, mask, idx)
+    if scale > 1:
+        assert max(norms) > 1.0
+    np.testing.assert_allclose(c_loss, t_loss, rtol=2e-6)
+    np.testing.assert_allclose(blob, blob_of(net), rtol=0, atol=1e-6)
+    t_m = np.concatenate([opt.state[p]["exp_avg"].numpy().reshape(-1) for p in net.parameters()])
+    t_v = np.concatenate([opt.state[p]["exp_avg_sq"].numpy().reshape(-1) for p in net.parameters()])
+    np.testing.assert_allclose(m, t_m, rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(v, t_v, rtol=1e-4, atol=1e-10)
+
+
+def test_cluster_kernel_repeatable_split_and_bad_rows(emu):
+    rng = np.random.default_rng(21)
+    feat, target, mask, idx = make_problem(rng, 300, 50, 5)
+    runs = []
+    for _ in range(3):                                   # 2048 asynchronous host threads: a missing barrier shows as noise
+        blob, m, v = blob_of(make_net(6)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+        loss = cluster_steps(emu, blob, m, v, 0, feat, target, mask, idx)
+        runs.append((blob, m, v, loss))
+    for r in runs[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(r, runs[0]))
+    # 2 + 3 steps in two launches == 5 in one (moments and bias correction are handed over through global memory)
+    blob, m, v = blob_of(make_net(6)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+    l2 = np.concatenate([cluster_steps(emu, blob, m, v, 0, feat, target, mask, idx[:2]),
+                         cluster_steps(emu, blob, m, v, 2, feat, target, mask, idx[2:])])
+    assert all(np.array_equal(x, y) for x, y in zip((blob, m, v, l2), runs[0]))
+    # the one-CTA kernel sums the gradient in another order: same result to fp32 rounding
+    blob1, m1, v1 = blob_of(make_net(6)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+    l1 = emu_steps(emu, blob1, m1, v1, 0, feat, target, mask, idx)
+    np.testing.assert_allclose(l1, runs[0][3], rtol=2e-6)
+    np.testing.assert_allclose(blob1, runs[0][0], rtol=0, atol=1e-6)
+    # a bad row in ANY CTA's share skips the step in all of them
+    bad = idx.copy()
+    bad[1, 40] = 300                                     # row 40 belongs to CTA 2
+    blob, m, v = blob_of(make_net(6)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+    lb = cluster_steps(emu, blob, m, v, 0, feat, target, mask, bad)
+    assert np.isnan(lb[1]) and np.isfinite(lb[[0, 2, 3, 4]]).all()
+    blob_g, m_g, v_g = blob_of(make_net(6)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+    lg = cluster_steps(emu, blob_g, m_g, v_g, 0, feat, target, mask, np.ascontiguousarray(idx[[0, 2, 3, 4]]))
+    assert np.array_equal(blob, blob_g) and np.array_equal(lb[[0, 2, 3, 4]], lg)
