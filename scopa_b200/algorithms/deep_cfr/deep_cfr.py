@@ -126,7 +126,6 @@ class AdvantageNetwork:
             total_loss += loss.item()
         return total_loss / epochs
 
-
     def _train_fused(self, batch_size, epochs):
         """All epochs in one launch; one device->host read (the mean loss) per call instead of one per epoch."""
         b = self.buffer

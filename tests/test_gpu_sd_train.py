@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
-import build as emu_build  # noqa: E402
+import emu_build  # noqa: E402
 
 from scopa_b200 import sdcfr  # noqa: E402
 from scopa_b200.algorithms.deep_cfr.deep_cfr import AdvantageNetwork, DeepCFR  # noqa: E402

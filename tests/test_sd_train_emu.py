@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
-import build as emu_build  # noqa: E402
+import emu_build  # noqa: E402
 
 NF = 13776
 fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
