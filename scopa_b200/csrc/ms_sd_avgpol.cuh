@@ -3,7 +3,8 @@
 // two launches:   policy[row] = sum_k  positive_regret_policy(net_k(feat[row]), mask[row]) * (weight_k / total_weight)
 // with positive_regret_policy = relu(adv) * mask / max(sum, 1e-8) (nets.py:93-101).  The reference (and a PyTorch
 // restatement of it) runs one batch-1 forward per stored net: up to 100 nets x ~10 launches per decision of
-// evaluate_vs_random.  Here CTA k keeps net k (13 776 floats) in shared memory, forwards the rows in chunks of 64 with
+// evaluate_vs_random.  Here CTA (k, y) keeps net k (13 776 floats) in shared memory, forwards its share of the rows (64-row
+// chunks y, y + gridDim.y, ...) with
 // the same fp32 fmaf GEMM routine as sd_train_kernel, and writes its weighted policy to scratch[k][row][16];
 // sd_avgpol_reduce_kernel then adds the K layers in k order (the reference's `policy +=` order), so the result does not
 // depend on scheduling.  Same emulation-compatible subset of CUDA as ms_sd_train.cuh (tests/emu).
@@ -44,7 +45,8 @@ __global__ void __launch_bounds__(sda::kPolThreads, 1) sd_avgpol_kernel(SdAvgPol
         for (int e = tid; e < kNetFloats; e += T) S[smem_of(e)] = net[e];
         const float wk = a.weights[k];
         float* out = a.scratch + (long long)k * a.n_rows * kOut;
-        for (long long r0 = 0; r0 < a.n_rows; r0 += kRows) {
+        // blockIdx.y / gridDim.y split the 64-row chunks of one net over several CTAs (few nets, many rows)
+        for (long long r0 = (long long)blockIdx.y * kRows; r0 < a.n_rows; r0 += (long long)gridDim.y * kRows) {
             const int R = (int)((a.n_rows - r0) < kRows ? (a.n_rows - r0) : kRows);
             const int Rp = (R + 3) & ~3;
             __syncthreads();                              // parameters loaded / previous chunk consumed

@@ -95,8 +95,14 @@ int ms_sdcfr_average_policy(const float* d_nets, const float* d_weights, int32_t
     a.policy = d_policy;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MS_CUDA(cudaFuncSetAttribute(sd_avgpol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sda::kPolSmemBytes));
-    const int grid = n_nets < kNumSMs ? n_nets : kNumSMs;          // one net per CTA, one CTA per SM
-    sd_avgpol_kernel<<<grid, sda::kPolThreads, sda::kPolSmemBytes, st>>>(a);
+    // grid.x = nets (one net per CTA, 1 CTA per SM at 119 KB of shared memory); grid.y splits a net's 64-row chunks over
+    // more CTAs until about two waves of the 148 SMs are in flight (matters while the buffer holds few nets)
+    const int gx = n_nets < kNumSMs ? n_nets : kNumSMs;
+    const int64_t n_chunks = (n_rows + sda::kRows - 1) / sda::kRows;
+    int64_t gy = (2 * kNumSMs + gx - 1) / gx;
+    if (gy > n_chunks) gy = n_chunks;
+    if (gy > 65535) gy = 65535;
+    sd_avgpol_kernel<<<dim3((unsigned)gx, (unsigned)gy), sda::kPolThreads, sda::kPolSmemBytes, st>>>(a);
     MS_LAUNCH_CHECK();
     sd_avgpol_reduce_kernel<<<grid_for(n_rows * sdt::kOut, 256, 8), 256, 0, st>>>(a);
     MS_LAUNCH_CHECK();

@@ -47,13 +47,13 @@ static inline T* ms_cluster_map(T* p, unsigned rank) {
 }
 
 template <class Kernel, class Args>
-struct emu_launch_ctx { Kernel k; const Args* a; unsigned tid, block, slot; };
+struct emu_launch_ctx { Kernel k; const Args* a; unsigned tid, block, block_y, slot; };
 
 template <class Kernel, class Args>
 static void* emu_thread_main(void* p) {
     auto* c = static_cast<emu_launch_ctx<Kernel, Args>*>(p);
     threadIdx = {c->tid, 0, 0};
-    blockIdx = {c->block, 0, 0};
+    blockIdx = {c->block, c->block_y, 0};
     emu_block_slot = c->slot;
     c->k(*c->a);
     return nullptr;
@@ -61,7 +61,8 @@ static void* emu_thread_main(void* p) {
 
 // `blocks` concurrent blocks (slots 0 .. blocks-1) of `threads` threads each; block b reports blockIdx.x = first_block + b
 template <class Kernel, class Args>
-static int emu_run_blocks(Kernel k, const Args& args, unsigned first_block, unsigned blocks, unsigned threads) {
+static int emu_run_blocks(Kernel k, const Args& args, unsigned first_block, unsigned blocks, unsigned threads,
+                          unsigned block_y = 0) {
     if (blocks < 1 || blocks > EMU_MAX_CLUSTER) return -3;
     blockDim = {threads, 1, 1};
     emu_cluster_size = blocks;
@@ -75,7 +76,7 @@ static int emu_run_blocks(Kernel k, const Args& args, unsigned first_block, unsi
     pthread_attr_init(&attr);
     pthread_attr_setstacksize(&attr, 256 * 1024);
     for (unsigned i = 0; i < total; ++i) {
-        ctx[i] = {k, &args, i % threads, first_block + i / threads, i / threads};
+        ctx[i] = {k, &args, i % threads, first_block + i / threads, block_y, i / threads};
         if (pthread_create(&th[i], &attr, emu_thread_main<Kernel, Args>, &ctx[i]))
             return -2;   // a partial start would dead-lock on the barriers; the caller treats it as fatal
     }
@@ -93,14 +94,15 @@ static int emu_launch_cta(Kernel k, const Args& args, unsigned threads) {
     return emu_run_blocks(k, args, 0, 1, threads);
 }
 
-// kernel<<<blocks, threads>>>(args) for kernels whose blocks do not communicate: the blocks run one after another
+// kernel<<<dim3(blocks, blocks_y), threads>>>(args) for kernels whose blocks do not communicate: one after another
 template <class Kernel, class Args>
-static int emu_launch_grid(Kernel k, const Args& args, unsigned blocks, unsigned threads) {
-    gridDim = {blocks, 1, 1};
-    for (unsigned b = 0; b < blocks; ++b) {
-        int rc = emu_run_blocks(k, args, b, 1, threads);
-        if (rc) return rc;
-    }
+static int emu_launch_grid(Kernel k, const Args& args, unsigned blocks, unsigned threads, unsigned blocks_y = 1) {
+    gridDim = {blocks, blocks_y, 1};
+    for (unsigned y = 0; y < blocks_y; ++y)
+        for (unsigned b = 0; b < blocks; ++b) {
+            int rc = emu_run_blocks(k, args, b, 1, threads, y);
+            if (rc) return rc;
+        }
     gridDim = {1, 1, 1};
     return 0;
 }

@@ -38,7 +38,7 @@ extern "C" int emu_ms_sdcfr_train(float* net, float* adam_m, float* adam_v, long
 }
 
 // Same signature as ms_sdcfr_average_policy (include/scopa_b200.h) with host pointers.  `grid` CTAs like the device
-// launch (min(n_nets, 148)); the emulation runs them one after another.
+// launch; the emulation runs them one after another.
 extern "C" int emu_ms_sdcfr_average_policy(const float* nets, const float* weights, int n_nets, const float* feat,
                                            const float* mask, long long n_rows, float* policy, void* workspace,
                                            size_t workspace_bytes, void* /*stream*/) {
@@ -48,8 +48,11 @@ extern "C" int emu_ms_sdcfr_average_policy(const float* nets, const float* weigh
     ms::SdAvgPolArgs a;
     a.nets = nets; a.weights = weights; a.n_nets = n_nets; a.feat = feat; a.mask = mask; a.n_rows = n_rows;
     a.scratch = static_cast<float*>(workspace); a.policy = policy;
-    const unsigned grid = n_nets < 148 ? n_nets : 148;
-    int rc = emu_launch_grid(ms::sd_avgpol_kernel, a, grid, ms::sda::kPolThreads);
+    const unsigned gx = n_nets < 148 ? n_nets : 148;                    // the device launch's grid (ms_sd_train.cu)
+    const long long n_chunks = (n_rows + ms::sda::kRows - 1) / ms::sda::kRows;
+    long long gy = (2 * 148 + gx - 1) / gx;
+    if (gy > n_chunks) gy = n_chunks;
+    int rc = emu_launch_grid(ms::sd_avgpol_kernel, a, gx, ms::sda::kPolThreads, (unsigned)gy);
     if (rc) return rc;
     return emu_launch_grid(ms::sd_avgpol_reduce_kernel, a, 2, 256);
 }

@@ -105,7 +105,7 @@ def test_deepcfr_trains_with_the_fused_optimiser():
     assert pol.shape == (16,) and (pol >= 0).all() and pol.sum() < 1 + 1e-5
 
 
-@pytest.mark.parametrize("n_nets,n_rows", [(3, 1), (8, 70), (20, 200)])
+@pytest.mark.parametrize("n_nets,n_rows", [(3, 1), (8, 70), (20, 200), (2, 300)])
 def test_average_policy_kernels_equal_emulation_bit_for_bit(n_nets, n_rows):
     from scopa_b200 import _lib
     _lib.load()
