@@ -309,6 +309,15 @@ int ms_sdcfr_train_cluster(float* d_net, float* d_adam_m, float* d_adam_v, int64
                            int32_t epochs, double lr, double beta1, double beta2, double eps, double max_norm,
                            float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ms_sdcfr_sample_rows: the minibatches of AdvantageNetwork.train (random.sample(self.buffer, batch_size) once per
+ *   epoch, deep_cfr.py:88) for all epochs of a call in one launch: d_idx [epochs][batch] receives, per epoch, `batch`
+ *   DISTINCT rows of [0, n_rows), every such batch equally likely, as a function of (seed, first_epoch + epoch, n_rows,
+ *   batch) alone: Philox4x32-10 with key = seed, ctr = (step lo, step hi, position | attempt << 8, "SDTR"),
+ *   row = mulhi32(x0, n_rows), positions that collide with a lower position draw again.  first_epoch = optimiser steps
+ *   done before the call.  batch <= 128, batch <= n_rows < 2^31.  Feed d_idx to ms_sdcfr_train / _cluster. */
+int ms_sdcfr_sample_rows(int32_t* d_idx, int32_t batch, int32_t epochs, int64_t n_rows, uint64_t seed, uint64_t first_epoch,
+                         void* stream);
+
 /* ms_sdcfr_average_policy: StrategyBuffer.get_average_policy (deep_cfr.py:136-160) for n_rows states and ALL n_nets
  *   stored strategy nets at once: d_policy[row] = sum over k (ascending) of positive_regret_policy(net_k(d_feat[row]),
  *   d_mask[row]) * d_weights[k], positive_regret_policy = relu(adv) * mask / max(sum, 1e-8) (nets.py:93-101).

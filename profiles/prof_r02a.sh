@@ -9,7 +9,8 @@ for a in "128 10 100000 100" "128 1 100000 200" "32 10 100 100"; do $C $a; done
 for a in "avgpol 20 200 100"; do $C $a; done
 # 2b. the cluster form of the optimiser: first run on a device (bit parity with its 8-CTA emulation, then timing)
 for a in "cluster 17 3 40 0" "cluster 128 6 4096 100" "cluster 128 1 4096 200" "cluster 32 10 100 100"; do timeout 120 $C $a; done
-SCOPA_B200_UNVERIFIED=1 python -m pytest tests/test_gpu_sd_train.py -x -q -m gpu -k cluster 2>&1 | tail -3
+for a in "sample 128 10 100000 200" "sample 128 3 130 0" "sample 32 3 32 0"; do timeout 60 $C $a; done
+SCOPA_B200_UNVERIFIED=1 python -m pytest tests/test_gpu_sd_train.py -x -q -m gpu -k "cluster or sampler" 2>&1 | tail -3
 SD_CHECK_TIMING_ONLY=1 $C avgpol 100 1 500
 SD_CHECK_TIMING_ONLY=1 $C avgpol 100 738 100
 # 3. full captures (each after its plain run above exited 0): optimiser kernel, average-policy kernel

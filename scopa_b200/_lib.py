@@ -75,6 +75,7 @@ _SIGS = {
                        C.c_int),
     "ms_sdcfr_train_cluster": ([vp, vp, vp, i64, vp, vp, vp, i64, vp, i32, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, C.c_size_t, vp],
                                C.c_int),
+    "ms_sdcfr_sample_rows": ([vp, i32, i32, i64, u64, u64, vp], C.c_int),
     "ms_sdcfr_average_policy_workspace_bytes": ([i32, i64], C.c_size_t),
     "ms_sdcfr_average_policy": ([vp, vp, i32, vp, vp, i64, vp, vp, C.c_size_t, vp], C.c_int),
     "ms_full_deal_from_seeds": ([vp, i64, vp, vp, vp], C.c_int),

@@ -68,7 +68,8 @@ class DeviceReplayBuffer:
 class AdvantageNetwork:
     """Manages the advantage network for one player."""
 
-    def __init__(self, input_dim, num_actions, device="cuda", lr=5e-4, precision="fp32", optimizer="torch"):
+    def __init__(self, input_dim, num_actions, device="cuda", lr=5e-4, precision="fp32", optimizer="torch",
+                 sampler_seed=None):
         if optimizer not in ("torch", "fused", "fused-cluster"):
             raise ValueError(f"optimizer must be 'torch', 'fused' or 'fused-cluster', not {optimizer!r}")
         self.device = device
@@ -84,6 +85,10 @@ class AdvantageNetwork:
         self.criterion = nn.MSELoss()
         self.buffer = DeviceReplayBuffer(100000, device)
         self._fused = None
+        # fused optimisers only: None = minibatch rows from torch's CUDA generator (rand + top-k), an int = rows from the
+        # Philox stream of ms_sdcfr_sample_rows (one launch, repeatable, independent of torch's generator state)
+        self.sampler_seed = sampler_seed
+        self._sample_entry = None       # tests only (emulated ms_sdcfr_sample_rows)
         if optimizer != "torch":
             # the module's parameters become views of one flat blob that the kernel updates in place
             self._fused = sdcfr.FusedAdam(sdcfr.flatten_parameters_(self.net), lr=lr,
@@ -135,6 +140,8 @@ class AdvantageNetwork:
     def _sample_rows(self, batch_size, epochs):
         """[epochs, batch_size] int32: per epoch `batch_size` distinct buffer rows (random.sample) = the top-k positions
         of iid uniforms."""
+        if self.sampler_seed is not None:
+            return self._fused.sample_rows(batch_size, epochs, len(self.buffer), self.sampler_seed, _entry=self._sample_entry)
         u = torch.rand((epochs, len(self.buffer)), device=self.device)
         return u.topk(batch_size, dim=1).indices.to(torch.int32).contiguous()
 
@@ -271,7 +278,7 @@ class DeepCFR:
     """Main Deep CFR algorithm."""
 
     def __init__(self, game, num_players=2, device="cuda", precision="fp32", traversals_per_iteration=1, seed=0,
-                 verbose=False, optimizer="torch", device_eval=False):
+                 verbose=False, optimizer="torch", device_eval=False, sampler_seed=None):
         self.game = game
         self.num_players = num_players
         self.device = device
@@ -284,8 +291,9 @@ class DeepCFR:
         self.input_dim = self._estimate_input_dim()
         if verbose:
             print(f"Estimated input dimension: {self.input_dim}")
-        self.advantage_nets = [AdvantageNetwork(self.input_dim, 16, device, precision=precision, optimizer=optimizer)
-                               for _ in range(num_players)]
+        self.advantage_nets = [AdvantageNetwork(self.input_dim, 16, device, precision=precision, optimizer=optimizer,
+                                                sampler_seed=None if sampler_seed is None else int(sampler_seed) * 2 + p)
+                               for p in range(num_players)]
         self.strategy_buffers = [StrategyBuffer() for _ in range(num_players)]
         self.training_history = {
             "losses": [[] for _ in range(num_players)],

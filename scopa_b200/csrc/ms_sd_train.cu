@@ -4,6 +4,7 @@
 
 #include "ms_common.cuh"
 #include "ms_sd_avgpol.cuh"
+#include "ms_sd_sample.cuh"
 #include "ms_sd_train.cuh"
 #include "ms_sd_train_cluster.cuh"
 
@@ -105,6 +106,22 @@ int ms_sdcfr_average_policy(const float* d_nets, const float* d_weights, int32_t
     sd_avgpol_kernel<<<dim3((unsigned)gx, (unsigned)gy), sda::kPolThreads, sda::kPolSmemBytes, st>>>(a);
     MS_LAUNCH_CHECK();
     sd_avgpol_reduce_kernel<<<grid_for(n_rows * sdt::kOut, 256, 8), 256, 0, st>>>(a);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_sdcfr_sample_rows(int32_t* d_idx, int32_t batch, int32_t epochs, int64_t n_rows, uint64_t seed, uint64_t first_epoch,
+                         void* stream) {
+    using namespace ms;
+    if (!d_idx) return fail(MS_ERR_ARG, "ms_sdcfr_sample_rows: null pointer");
+    if (batch < 1 || batch > sds::kSampleThreads || epochs < 0)
+        return fail(MS_ERR_ARG, "ms_sdcfr_sample_rows: batch %d (1..128), epochs %d", batch, epochs);
+    if (n_rows < batch || n_rows >= (int64_t)1 << 31)
+        return fail(MS_ERR_ARG, "ms_sdcfr_sample_rows: n_rows %lld must lie in [batch, 2^31)", (long long)n_rows);
+    if (epochs == 0) return MS_OK;
+    SdSampleArgs a;
+    a.idx = d_idx; a.batch = batch; a.epochs = epochs; a.n_rows = n_rows; a.seed = seed; a.first_epoch = first_epoch;
+    sd_sample_rows_kernel<<<epochs < 1024 ? epochs : 1024, sds::kSampleThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     MS_LAUNCH_CHECK();
     return MS_OK;
 }

@@ -102,6 +102,20 @@ class FusedAdam:
         self.lr, self.betas, self.eps, self.max_norm = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(max_norm)
         self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=blob.device)
 
+    def sample_rows(self, batch, epochs, n_rows, seed, _entry=None):
+        """[epochs, batch] int32 minibatch rows for the next `epochs` optimiser steps (`ms_sdcfr_sample_rows`: distinct
+        rows per epoch from the Philox stream (seed, global step); one launch).  `_entry`: emulated entry point (tests)."""
+        idx = torch.empty((epochs, batch), dtype=torch.int32, device=self.blob.device)
+        args = (idx.data_ptr(), int(batch), int(epochs), int(n_rows), int(seed) & (2 ** 64 - 1), int(self.steps_done))
+        if self._emulated:
+            rc = _entry(*args, None)
+            if rc != 0:
+                raise _lib.MsError(f"emulated ms_sdcfr_sample_rows returned {rc}")
+        else:
+            with torch.cuda.device(self.blob.device):
+                _lib.check(_lib.load().ms_sdcfr_sample_rows(*args, _lib.stream_ptr()))
+        return idx
+
     def step(self, feat, target, mask, idx):
         """idx [epochs, batch] int32 rows of (feat [n,34], target [n,16], mask [n,16]) -> losses [epochs]; all tensors on
         the blob's device."""

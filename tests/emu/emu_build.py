@@ -22,7 +22,8 @@ def build_emu():
     deps = [os.path.join(HERE, "sd_train_emu.cpp"), os.path.join(HERE, "cta_emu.h"),
             os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_train.cuh"),
             os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_avgpol.cuh"),
-            os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_train_cluster.cuh")]
+            os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_train_cluster.cuh"),
+            os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_sample.cuh")]
     if _newer(EMU_LIB, deps):
         subprocess.run(["g++"] + CXXFLAGS + ["-fPIC", "-shared", "-o", EMU_LIB, deps[0]], check=True)
     return EMU_LIB

@@ -14,6 +14,7 @@
 
 extern "C" int emu_ms_sdcfr_average_policy(const float*, const float*, int, const float*, const float*, long long, float*,
                                            void*, size_t, void*);
+extern "C" int emu_ms_sdcfr_sample_rows(int*, int, int, long long, unsigned long long, unsigned long long, void*);
 extern "C" int emu_ms_sdcfr_train(float*, float*, float*, long long, const float*, const float*, const float*, long long,
                                   const int*, int, int, double, double, double, double, double, float*, void*, size_t, void*);
 extern "C" int emu_ms_sdcfr_train_cluster(float*, float*, float*, long long, const float*, const float*, const float*,
@@ -101,7 +102,46 @@ static int check_avgpol(int K, int n, int reps) {
     return d ? 1 : 0;
 }
 
+// sd_train_check sample [batch] [epochs] [n_rows] [timing_reps]: ms_sdcfr_sample_rows on the device against the emulation
+static int check_sample(int batch, int epochs, long long n_rows, int reps) {
+    std::vector<int> e((size_t)epochs * batch), g((size_t)epochs * batch);
+    const unsigned long long seed = 0x1234567890ull, first = 17;
+    if (emu_ms_sdcfr_sample_rows(e.data(), batch, epochs, n_rows, seed, first, nullptr)) {
+        printf("emulation failed\n");
+        return 2;
+    }
+    int* d_idx;
+    CK(cudaMalloc(&d_idx, g.size() * 4));
+    int rc = ms_sdcfr_sample_rows(d_idx, batch, epochs, n_rows, seed, first, nullptr);
+    if (rc) {
+        printf("ms_sdcfr_sample_rows failed: %d %s\n", rc, ms_last_error());
+        return 2;
+    }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(g.data(), d_idx, g.size() * 4, cudaMemcpyDeviceToHost));
+    size_t d = 0;
+    for (size_t i = 0; i < g.size(); ++i) d += g[i] != e[i];
+    printf("sample batch %d epochs %d rows %lld: differing words %zu of %zu; first rows %d %d %d\n", batch, epochs, n_rows, d,
+           g.size(), g[0], g.size() > 1 ? g[1] : -1, g.size() > 2 ? g[2] : -1);
+    if (reps > 0) {
+        cudaEvent_t t0, t1;
+        CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+        for (int i = 0; i < 3; ++i) ms_sdcfr_sample_rows(d_idx, batch, epochs, n_rows, seed, first, nullptr);
+        CK(cudaEventRecord(t0));
+        for (int i = 0; i < reps; ++i) ms_sdcfr_sample_rows(d_idx, batch, epochs, n_rows, seed, first + i, nullptr);
+        CK(cudaEventRecord(t1));
+        CK(cudaEventSynchronize(t1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, t0, t1));
+        printf("timing: %.2f us per call (%d epochs x %d rows of %lld)\n", 1e3 * ms / reps, epochs, batch, n_rows);
+    }
+    return d ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "sample"))
+        return check_sample(argc > 2 ? atoi(argv[2]) : 128, argc > 3 ? atoi(argv[3]) : 10, argc > 4 ? atoll(argv[4]) : 100000,
+                            argc > 5 ? atoi(argv[5]) : 0);
     if (argc > 1 && !strcmp(argv[1], "avgpol"))
         return check_avgpol(argc > 2 ? atoi(argv[2]) : 8, argc > 3 ? atoi(argv[3]) : 70, argc > 4 ? atoi(argv[4]) : 0);
     // sd_train_check [cluster] [batch] [epochs] [n_rows] [timing_reps]: "cluster" selects ms_sdcfr_train_cluster

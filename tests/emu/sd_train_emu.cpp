@@ -7,6 +7,7 @@
 #include "../../scopa_b200/csrc/ms_sd_train.cuh"
 #include "../../scopa_b200/csrc/ms_sd_avgpol.cuh"
 #include "../../scopa_b200/csrc/ms_sd_train_cluster.cuh"
+#include "../../scopa_b200/csrc/ms_sd_sample.cuh"
 
 extern "C" int emu_sd_train(float* net, float* adam_m, float* adam_v, long long steps_done, const float* feat,
                             const float* target, const float* mask, long long n_rows, const int* idx, int batch,
@@ -74,4 +75,14 @@ extern "C" int emu_ms_sdcfr_train_cluster(float* net, float* adam_m, float* adam
     a.b2pow = std::pow(beta2, (double)steps_done);
     a.loss = loss; a.grad = static_cast<float*>(workspace);
     return emu_launch_cluster(ms::sd_train_cluster_kernel, a, ms::sdc::kCluster, ms::sdc::kCThreads);
+}
+
+// ms_sdcfr_sample_rows' signature with a host pointer
+extern "C" int emu_ms_sdcfr_sample_rows(int* idx, int batch, int epochs, long long n_rows, unsigned long long seed,
+                                        unsigned long long first_epoch, void* /*stream*/) {
+    if (!idx || batch < 1 || batch > ms::sds::kSampleThreads || epochs < 0 || n_rows < batch || n_rows >= (1ll << 31)) return -2;
+    if (epochs == 0) return 0;
+    ms::SdSampleArgs a;
+    a.idx = idx; a.batch = batch; a.epochs = epochs; a.n_rows = n_rows; a.seed = seed; a.first_epoch = first_epoch;
+    return emu_launch_grid(ms::sd_sample_rows_kernel, a, epochs < 1024 ? epochs : 1024, ms::sds::kSampleThreads);
 }

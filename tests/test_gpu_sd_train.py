@@ -205,3 +205,30 @@ def test_deepcfr_trains_with_the_cluster_optimiser():
     for p in (0, 1):
         assert all(np.isfinite(d.training_history["losses"][p])) and d.advantage_nets[p]._fused.steps_done == 18
         assert not torch.equal(d.advantage_nets[p].blob(), w0[p])
+
+
+@unverified
+@pytest.mark.parametrize("batch,epochs,n_rows", [(128, 10, 100000), (128, 3, 130), (32, 4, 41), (32, 3, 32), (1, 3, 1)])
+def test_sampler_kernel_equals_emulation(batch, epochs, n_rows):
+    """ms_sdcfr_sample_rows (written after the GPU budget was spent, like the cluster kernel): device rows == emulated rows
+    (the emulation equals the draw-for-draw restatement in tests/test_sd_train_emu.py)."""
+    from scopa_b200 import _lib
+    _lib.load()
+    exe = emu_build.build_check()
+    res = subprocess.run([exe, "sample", str(batch), str(epochs), str(n_rows), "0"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "differing words 0 of" in res.stdout, res.stdout
+
+
+@unverified
+def test_deepcfr_with_the_philox_sampler_is_repeatable():
+    from scopa_b200 import pyspiel_compat as pyspiel
+    from scopa_b200.envs import openspiel_mini_scopa  # noqa: F401
+    game = pyspiel.load_game("mini_scopa")
+    blobs = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        d = DeepCFR(game, device="cuda", traversals_per_iteration=64, seed=3, optimizer="fused", sampler_seed=9)
+        d.train(iterations=3, advantage_epochs=4, eval_freq=10, eval_episodes=0)
+        blobs.append([a.blob().clone() for a in d.advantage_nets])
+    assert all(torch.equal(x, y) for x, y in zip(*blobs))

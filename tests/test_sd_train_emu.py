@@ -337,3 +337,100 @@ def test_cluster_kernel_repeatable_split_and_bad_rows(emu):
     blob_g, m_g, v_g = blob_of(make_net(6)), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
     lg = cluster_steps(emu, blob_g, m_g, v_g, 0, feat, target, mask, np.ascontiguousarray(idx[[0, 2, 3, 4]]))
     assert np.array_equal(blob, blob_g) and np.array_equal(lb[[0, 2, 3, 4]], lg)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sd_sample_rows_kernel (csrc/ms_sd_sample.cuh): the minibatch rows of all epochs in one launch.
+
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al. 2011), plain Python integers."""
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = (p1 >> 32) ^ c1 ^ k0, p1 & 0xFFFFFFFF, (p0 >> 32) ^ c3 ^ k1, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def sample_rows_restated(batch, epochs, n_rows, seed, first_epoch):
+    """The kernel's procedure as its header states it, sequentially."""
+    out = np.zeros((epochs, batch), np.int32)
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    for ep in range(epochs):
+        E = first_epoch + ep
+        attempt, row, dirty = [0] * batch, [0] * batch, [True] * batch
+        while any(dirty):
+            for m in range(batch):
+                if dirty[m]:
+                    x = philox4x32_10((E & 0xFFFFFFFF, E >> 32, m | (attempt[m] << 8), 0x52544453), key)[0]
+                    row[m] = (x * n_rows) >> 32
+                    attempt[m] += 1
+            dirty = [any(row[j] == row[m] for j in range(m)) for m in range(batch)]
+        out[ep] = row
+    return out
+
+
+def emu_sample(emu, batch, epochs, n_rows, seed, first_epoch=0):
+    from scopa_b200 import _lib
+    f = emu.emu_ms_sdcfr_sample_rows
+    f.argtypes, f.restype = _lib._SIGS["ms_sdcfr_sample_rows"]
+    idx = np.full((epochs, batch), -7, np.int32)
+    assert f(idx.ctypes.data, batch, epochs, n_rows, seed, first_epoch, None) == 0
+    return idx
+
+
+def test_philox_known_answer():
+    # Random123's published vectors for philox4x32-10
+    assert philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == \
+        (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+
+
+@pytest.mark.parametrize("batch,epochs,n_rows,seed,first", [(128, 5, 100000, 1234, 0), (128, 3, 130, 7, 40), (32, 4, 41, 99, 3),
+                                                           (32, 3, 32, 5, 0), (1, 3, 1, 1, 0), (7, 2, 9, 2 ** 40 + 3, 2 ** 33)])
+def test_emulated_sampler_equals_the_restatement(emu, batch, epochs, n_rows, seed, first):
+    got = emu_sample(emu, batch, epochs, n_rows, seed, first)
+    assert np.array_equal(got, sample_rows_restated(batch, epochs, n_rows, seed, first))
+    assert got.min() >= 0 and got.max() < n_rows
+    assert all(len(set(r.tolist())) == batch for r in got)          # random.sample: distinct rows
+
+
+def test_sampler_stream_properties(emu):
+    # consecutive calls continue the stream: epochs [0, 5) == [0, 2) + [2, 5)
+    a = emu_sample(emu, 64, 5, 5000, 11, 0)
+    assert np.array_equal(a, np.concatenate([emu_sample(emu, 64, 2, 5000, 11, 0), emu_sample(emu, 64, 3, 5000, 11, 2)]))
+    assert not np.array_equal(a, emu_sample(emu, 64, 5, 5000, 12, 0))                   # another seed, another stream
+    # every row equally likely: 400 epochs x 32 of 64 rows -> each row is drawn about 200 times (sd = 10)
+    counts = np.bincount(emu_sample(emu, 32, 400, 64, 3, 0).reshape(-1), minlength=64)
+    assert counts.sum() == 400 * 32 and counts.min() > 150 and counts.max() < 250
+
+
+def test_python_binding_of_the_sampler(emu):
+    """AdvantageNetwork(sampler_seed=...) -> FusedAdam.sample_rows -> (emulated) ms_sdcfr_sample_rows: the rows follow the
+    optimiser's step count, feed the (emulated) optimiser kernel, and a run is repeatable from its seed."""
+    from scopa_b200 import _lib, sdcfr
+    from scopa_b200.algorithms.deep_cfr.deep_cfr import AdvantageNetwork
+
+    train, sample = emu.emu_ms_sdcfr_train, emu.emu_ms_sdcfr_sample_rows
+    train.argtypes, train.restype = _lib._SIGS["ms_sdcfr_train"]
+    sample.argtypes, sample.restype = _lib._SIGS["ms_sdcfr_sample_rows"]
+    rng = np.random.default_rng(13)
+    feat, target, mask, _ = make_problem(rng, 500, 1, 1)
+
+    def run():
+        torch.manual_seed(21)
+        adv = AdvantageNetwork(34, 16, device="cpu", sampler_seed=77)
+        adv._fused = sdcfr.FusedAdam(sdcfr.flatten_parameters_(adv.net), _entry=train)
+        adv._sample_entry = sample
+        adv.buffer.add_batch(*(torch.from_numpy(x) for x in (feat, target, mask)))
+        rows0 = adv._sample_rows(128, 3)
+        losses = [adv.train(batch_size=128, epochs=3), adv.train(batch_size=128, epochs=2)]
+        return rows0.numpy(), losses, adv._fused.blob.clone(), adv._fused.steps_done
+
+    r1, l1, b1, n1 = run()
+    r2, l2, b2, n2 = run()
+    assert np.array_equal(r1, sample_rows_restated(128, 3, 500, 77, 0)) and n1 == 5
+    assert np.array_equal(r1, r2) and l1 == l2 and torch.equal(b1, b2)           # repeatable from the seed alone
+    assert all(np.isfinite(l1))
