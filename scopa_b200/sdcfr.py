@@ -135,6 +135,8 @@ class FusedAdam:
         else:
             with torch.cuda.device(self.blob.device):
                 _lib.check(self._entry(*args, _lib.stream_ptr()))
+        # (an epoch with out-of-range rows is skipped by the kernel and reported as NaN; it still counts here -- such rows
+        # are a caller bug, not a state to resume from)
         self.steps_done += epochs
         return loss
 
