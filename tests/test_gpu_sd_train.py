@@ -146,10 +146,10 @@ def test_strategy_buffer_average_policy_on_cuda():
         for net, w in zip(buf.strategies, buf.weights):
             want += positive_regret_policy(net(x), m) * (w / tot)
     got = buf.average_policy_batch(x, m)
-    torch.testing.assert_close(got, want, rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)       # wiring check; bit parity is the test above
     one = buf.get_average_policy(feat[3], mask[3])
     assert one.dtype == np.float32 and one.shape == (16,) and np.all(one[mask[3] == 0] == 0)
-    np.testing.assert_allclose(one, want[3].cpu().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(one, want[3].cpu().numpy(), rtol=1e-4, atol=1e-5)
     # the cache follows the lists
     buf.strategies.pop(0)
     buf.weights.pop(0)
