@@ -47,8 +47,12 @@ class DeviceReplayBuffer:
         n = feat.shape[0]
         if n > self.maxlen:
             feat, target, mask, n = feat[-self.maxlen:], target[-self.maxlen:], mask[-self.maxlen:], self.maxlen
-        idx = (torch.arange(n, device=self.device) + self.count) % self.maxlen
-        self.feat[idx], self.target[idx], self.mask[idx] = feat, target, mask
+        start = self.count % self.maxlen                    # ring position of the first new row
+        head = min(n, self.maxlen - start)                  # rows that fit before the ring wraps
+        for dst, src in ((self.feat, feat), (self.target, target), (self.mask, mask)):
+            dst[start:start + head] = src[:head]            # plain slice copies: no index tensors, no scatter kernels
+            if head < n:
+                dst[:n - head] = src[head:]
         self.count += n
 
     def append(self, item):

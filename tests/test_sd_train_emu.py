@@ -434,3 +434,28 @@ def test_python_binding_of_the_sampler(emu):
     assert np.array_equal(r1, sample_rows_restated(128, 3, 500, 77, 0)) and n1 == 5
     assert np.array_equal(r1, r2) and l1 == l2 and torch.equal(b1, b2)           # repeatable from the seed alone
     assert all(np.isfinite(l1))
+
+
+def test_device_replay_buffer_is_a_deque_of_maxlen():
+    """DeviceReplayBuffer (ring of three tensors, slice copies) against collections.deque(maxlen=...) -- the reference's
+    buffer (deep_cfr.py:36) -- through wrap-arounds, oversize batches and single appends."""
+    from collections import deque
+    from scopa_b200.algorithms.deep_cfr.deep_cfr import DeviceReplayBuffer
+    rng = np.random.default_rng(4)
+    buf, ref = DeviceReplayBuffer(50, "cpu"), deque(maxlen=50)
+    tag = 0
+    for n in (7, 30, 20, 50, 3, 120, 1, 49, 2):
+        f = np.zeros((n, 34), np.float32)
+        f[:, 0] = np.arange(tag, tag + n)
+        t, m = rng.random((n, 16)).astype(np.float32), rng.random((n, 16)).astype(np.float32)
+        tag += n
+        if n == 1:
+            buf.append((f[0], t[0], m[0]))
+        else:
+            buf.add_batch(torch.from_numpy(f), torch.from_numpy(t), torch.from_numpy(m))
+        for i in range(n):
+            ref.append((f[i], t[i], m[i]))
+        assert len(buf) == len(ref)
+        have = sorted(((r[0][0], r[1].tobytes(), r[2].tobytes()) for r in buf))
+        want = sorted(((r[0][0], r[1].tobytes(), r[2].tobytes()) for r in ref))
+        assert have == want                                  # same multiset of rows (a minibatch is a random subset)
