@@ -459,3 +459,35 @@ def test_device_replay_buffer_is_a_deque_of_maxlen():
         have = sorted(((r[0][0], r[1].tobytes(), r[2].tobytes()) for r in buf))
         want = sorted(((r[0][0], r[1].tobytes(), r[2].tobytes()) for r in ref))
         assert have == want                                  # same multiset of rows (a minibatch is a random subset)
+
+
+def test_numpy_oracle_pinned_to_torch_and_kernels_to_the_oracle(emu):
+    """oracle/sd_train.py (explicit matrix algebra, no autograd) == torch (the reference's arithmetic) == emulated kernels."""
+    from oracle import sd_train as ora
+    rng = np.random.default_rng(31)
+    for batch, epochs, n_rows, scale in ((128, 5, 800, 1.0), (32, 3, 60, 40.0)):
+        net = make_net(batch + 1)
+        start = blob_of(net)
+        feat, target, mask, idx = make_problem(rng, n_rows, batch, epochs, scale)
+        t_loss, _, opt = torch_steps(net, feat, target, mask, idx)
+        o_blob, o_m, o_v = start.copy(), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+        o_loss = ora.train_steps(o_blob, o_m, o_v, 0, feat, target, mask, idx)
+        np.testing.assert_allclose(o_loss, t_loss, rtol=2e-6)
+        np.testing.assert_allclose(o_blob, blob_of(net), rtol=0, atol=1e-6)
+        e_blob, e_m, e_v = start.copy(), np.zeros(NF, np.float32), np.zeros(NF, np.float32)
+        e_loss = emu_steps(emu, e_blob, e_m, e_v, 0, feat, target, mask, idx)
+        np.testing.assert_allclose(e_loss, o_loss, rtol=2e-6)
+        np.testing.assert_allclose(e_blob, o_blob, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(e_m, o_m, rtol=1e-4, atol=1e-8)
+    # average policy: oracle vs the emulated two-kernel path
+    from scopa_b200 import _lib
+    f = emu.emu_ms_sdcfr_average_policy
+    f.argtypes, f.restype = _lib._SIGS["ms_sdcfr_average_policy"]
+    blobs = np.stack([blob_of(make_net(s)) for s in (3, 4, 5)])
+    weights = [2, 3, 4]
+    w32 = np.array([np.float32(w / sum(weights)) for w in weights], np.float32)
+    feat, _, mask, _ = make_problem(rng, 90, 1, 1)
+    pol, ws = np.zeros((90, 16), np.float32), np.zeros(3 * 90 * 16, np.float32)
+    assert f(blobs.ctypes.data, w32.ctypes.data, 3, feat.ctypes.data, mask.ctypes.data, 90, pol.ctypes.data, ws.ctypes.data,
+             ws.nbytes, None) == 0
+    np.testing.assert_allclose(pol, ora.average_policy(blobs, weights, feat, mask), rtol=2e-5, atol=2e-6)
