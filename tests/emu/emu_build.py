@@ -29,6 +29,25 @@ def build_emu():
     return EMU_LIB
 
 
+STATE_LIB = os.path.join(OUT, "libms_state_host.so")
+
+
+def _cuda_root():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return os.path.dirname(os.path.dirname(os.path.realpath(nvcc)))
+
+
+def build_state_host():
+    """the product's rule header (csrc/ms_state.cuh) compiled for the host; needs only the CUDA headers (vector types)"""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "ms_state_host.cpp")
+    deps = [src, os.path.join(ROOT, "scopa_b200", "csrc", "ms_state.cuh")]
+    if _newer(STATE_LIB, deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", "-o", STATE_LIB, src],
+                       check=True)
+    return STATE_LIB
+
+
 def build_check():
     """needs libscopa_b200.so (scopa_b200/_build.py) and the CUDA runtime headers; links both libraries by rpath"""
     build_emu()
@@ -47,4 +66,5 @@ def build_check():
 
 if __name__ == "__main__":
     print(build_emu())
+    print(build_state_host())
     print(build_check())
