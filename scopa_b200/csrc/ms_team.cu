@@ -168,6 +168,8 @@ int team_deck_from_seeds(const int64_t* d_seeds, int64_t n, uint64_t* d_deck, vo
 
 }  // namespace ms
 
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_team_host.cpp compiles everything above for the host (CPU checks of the rules)
+
 using namespace ms;
 
 extern "C" {
@@ -237,3 +239,4 @@ int ms_team_deal_from_seeds_host(const int64_t* h_seeds, int64_t n, ms_team_stat
 }
 
 }  // extern "C"
+#endif  // MS_HOST_RULES_ONLY

@@ -48,6 +48,21 @@ def build_state_host():
     return STATE_LIB
 
 
+TEAM_LIB = os.path.join(OUT, "libms_team_host.so")
+
+
+def build_team_host():
+    """the product's 2v2 team code (csrc/ms_team.cu: rules AND the three kernels) compiled for the host"""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "ms_team_host.cpp")
+    csrc = os.path.join(ROOT, "scopa_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("ms_team.cu", "ms_state.cuh", "ms_common.cuh")]
+    if _newer(TEAM_LIB, deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", "-o", TEAM_LIB, src],
+                       check=True)
+    return TEAM_LIB
+
+
 def build_check():
     """needs libscopa_b200.so (scopa_b200/_build.py) and the CUDA runtime headers; links both libraries by rpath"""
     build_emu()
@@ -67,4 +82,5 @@ def build_check():
 if __name__ == "__main__":
     print(build_emu())
     print(build_state_host())
+    print(build_team_host())
     print(build_check())
