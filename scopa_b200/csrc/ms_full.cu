@@ -378,6 +378,11 @@ __global__ void __launch_bounds__(FS_THREADS) full_rollout_kernel(const uint4* _
     }
 }
 
+}  // namespace ms
+
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_full_host.cpp compiles everything above for the host (CPU checks of the rules)
+namespace ms {
+
 // the deck kernel lives in ms_env.cu (it shares the MT19937 seeding with the 16-card deal)
 int full_deck_from_seeds(const int64_t* d_seeds, int64_t n, void* d_decks, int zero_means_42, int force_slow, void* stream);
 
@@ -554,3 +559,4 @@ int ms_full_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t phil
 }
 
 }  // extern "C"
+#endif  // MS_HOST_RULES_ONLY

@@ -63,6 +63,21 @@ def build_team_host():
     return TEAM_LIB
 
 
+FULL_LIB = os.path.join(OUT, "libms_full_host.so")
+
+
+def build_full_host():
+    """the product's 40-card Scopa code (csrc/ms_full.cu: rules AND the init/step/legal/evaluate/rollout kernels) for the host"""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "ms_full_host.cpp")
+    csrc = os.path.join(ROOT, "scopa_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("ms_full.cu", "ms_common.cuh")]
+    if _newer(FULL_LIB, deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", "-o", FULL_LIB, src],
+                       check=True)
+    return FULL_LIB
+
+
 def build_check():
     """needs libscopa_b200.so (scopa_b200/_build.py) and the CUDA runtime headers; links both libraries by rpath"""
     build_emu()
@@ -83,4 +98,5 @@ if __name__ == "__main__":
     print(build_emu())
     print(build_state_host())
     print(build_team_host())
+    print(build_full_host())
     print(build_check())
