@@ -500,6 +500,10 @@ __global__ void __launch_bounds__(256) rollout_kernel(const uint4* __restrict__ 
     }
 }
 
+}  // namespace ms
+
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_env_host.cpp compiles every kernel above for the host (CPU checks)
+namespace ms {
 // ------------------------------------------------------------------------------------------------
 static std::mutex g_mt_mu;
 static bool g_mt_done[64] = {};
@@ -870,3 +874,4 @@ extern "C" int ms_debug_atomic_peaks(double h_out[3], void* stream) {
     MS_CUDA(cudaFree(d));
     return MS_OK;
 }
+#endif  // MS_HOST_RULES_ONLY

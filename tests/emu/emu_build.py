@@ -78,6 +78,21 @@ def build_full_host():
     return FULL_LIB
 
 
+ENV_LIB = os.path.join(OUT, "libms_env_host.so")
+
+
+def build_env_host():
+    """the product's env kernels (csrc/ms_env.cu: deal / full deck / step / legal / capture / keys / rollout) for the host"""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "ms_env_host.cpp")
+    csrc = os.path.join(ROOT, "scopa_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("ms_env.cu", "ms_state.cuh", "ms_common.cuh")]
+    if _newer(ENV_LIB, deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", "-o", ENV_LIB, src],
+                       check=True)
+    return ENV_LIB
+
+
 def build_check():
     """needs libscopa_b200.so (scopa_b200/_build.py) and the CUDA runtime headers; links both libraries by rpath"""
     build_emu()
@@ -99,4 +114,5 @@ if __name__ == "__main__":
     print(build_state_host())
     print(build_team_host())
     print(build_full_host())
+    print(build_env_host())
     print(build_check())

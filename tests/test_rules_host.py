@@ -18,9 +18,11 @@ import emu_build  # noqa: E402
 vp = C.c_void_p
 
 
-@pytest.fixture(scope="module")
-def rules():
-    lib = C.CDLL(emu_build.build_state_host())
+@pytest.fixture(scope="module", params=["rule header + restated loops", "ms_env.cu kernels"])
+def rules(request):
+    """the same exports from two builds: tests/emu/ms_state_host.cpp (ms_state.cuh + the kernels' loops restated) and
+    tests/emu/ms_env_host.cpp (step_kernel / legal_kernel / capture_kernel / keys_kernel of ms_env.cu themselves)"""
+    lib = C.CDLL(emu_build.build_state_host() if request.param.startswith("rule") else emu_build.build_env_host())
     lib.host_step.argtypes = [vp, vp, vp, vp, C.c_longlong]
     lib.host_legal.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, C.c_longlong]
     lib.host_capture.argtypes = [vp, vp, vp, C.c_longlong]
