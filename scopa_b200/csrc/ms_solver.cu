@@ -16,6 +16,10 @@
 #include "ms_state.cuh"
 #include "ms_tree_walk.cuh"
 
+#ifndef MS_DYN_SMEM   // the host emulation of tests/emu/ms_solver_host.cpp supplies its own (one buffer per block)
+#define MS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace ms {
 
 constexpr int MAXN = 4096;   // tree nodes (a 4+4-card deal has 2229)
@@ -268,7 +272,7 @@ __device__ void cfr_run(const SolverDev& d, int n_dec, int iters, int only_playe
 
 __global__ void __launch_bounds__(512, 1) cfr_kernel(SolverDev d, int n_dec, int iters, int only_player, double r0,
                                                      double r1, double* out_value) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     __shared__ int s_lvl[MAXL + 1], s_slvl[MAXL + 1];
     cfr_run(d, n_dec, iters, only_player, r0, r1, out_value, smem_raw, s_lvl, s_slvl);
 }
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(512, 1) cfr_kernel(SolverDev d, int n_dec, int
 // Throughput mode: independent deals solved side by side, one CTA per deal (one CTA per SM).
 struct CfrJob { SolverDev d; int n_dec; };
 __global__ void __launch_bounds__(512, 1) cfr_many_kernel(const CfrJob* __restrict__ jobs, int iters) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     __shared__ int s_lvl[MAXL + 1], s_slvl[MAXL + 1];
     const CfrJob job = jobs[blockIdx.x];
     cfr_run(job.d, job.n_dec, iters, -1, 1.0, 1.0, nullptr, smem_raw, s_lvl, s_slvl);
@@ -312,6 +316,11 @@ __device__ void cfr_run(const SolverDev& d, int n_dec, int iters, int only_playe
     for (int i = tid; i < 4 * S; i += bd) d.regret[i] = m.reg[i];
     if (tid == 0 && out_value) *out_value = m.u[0];
 }
+
+}  // namespace ms
+
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_solver_host.cpp compiles the tree enumeration and vanilla CFR above for the host
+namespace ms {
 
 // ------------------------------------------------------------------------------------------------
 // K3  the reference's sampled-CFR estimator (mc_cfr.py:37-86).
@@ -526,7 +535,7 @@ __device__ void mccfr_traverse(const SolverDev& d, const MccfrShared& sh, int tp
 // the next node visit).  Used for parity / curve validation, not for throughput.
 __global__ void __launch_bounds__(32, 1) mccfr_inplace_kernel(SolverDev d, long long iters, uint2 pkey,
                                                              unsigned long long first_iter, int nframes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     const int S = d.n_slots;
     double* reg = (double*)smem_raw;
     double* str = reg + 4 * S;
@@ -575,7 +584,7 @@ __host__ __device__ inline size_t mccfr_batch_smem(int S, int hcap, int nframes,
 __global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev d, int player, long long n_trav,
                                                                     uint2 pkey, unsigned long long first_trav,
                                                                     int nframes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     const int S = d.n_slots, T = blockDim.x, tid = threadIdx.x;
     double* sig = (double*)smem_raw;
     double* cdf = sig + 4 * S;
@@ -654,7 +663,7 @@ __global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev
 // update is visible to the next node visit) -- what MCCFRTrainer.iteration() runs by default
 __global__ void __launch_bounds__(32, 1) mccfr_inplace_tree_kernel(SolverDev d, long long iters, uint2 pkey,
                                                                   unsigned long long first_iter, int nframes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     const int S = d.n_slots, N = d.n_nodes, tid = threadIdx.x;
     double* reg = (double*)smem_raw;
     double* str = reg + 4 * S;
@@ -692,7 +701,7 @@ __global__ void __launch_bounds__(32, 1) mccfr_inplace_tree_kernel(SolverDev d, 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
                                                                 unsigned long long first_trav, int nframes, int ncopy) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     const int S = d.n_slots, N = d.n_nodes, T = THREADS, tid = threadIdx.x;
     double* sig = (double*)smem_raw;
     double* cdf = sig + 4 * S;              // [S][3]: the last entry of a normalised cdf is 1.0 and is never read
@@ -863,7 +872,7 @@ __device__ void es_traverse(const SolverDev& d, const MccfrShared& sh, int tp, u
 
 __global__ void __launch_bounds__(ES_THREADS, 1) mccfr_es_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
                                                                  unsigned long long first_trav, int nframes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     const int S = d.n_slots, T = blockDim.x, tid = threadIdx.x;
     double* sig = (double*)smem_raw;
     double* cdf = sig + 4 * S;
@@ -1065,7 +1074,7 @@ __device__ void es_tree_traverse(const uint32_t* __restrict__ tree, const MccfrS
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) mccfr_es_tree_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
                                                                    unsigned long long first_trav, int nframes, int ncopy) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     const int S = d.n_slots, N = d.n_nodes, T = THREADS, tid = threadIdx.x;
     double* sig = (double*)smem_raw;
     double* cdf = sig + 4 * S;              // [S][3]
@@ -1125,7 +1134,7 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_es_tree_kernel(SolverDev d, 
 
 __global__ void __launch_bounds__(256) mccfr_os_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
                                                        unsigned long long first_trav) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     const int S = d.n_slots, T = blockDim.x, tid = threadIdx.x;
     double* sig = (double*)smem_raw;
     double* dreg = sig + 4 * S;
@@ -1252,7 +1261,7 @@ __device__ __forceinline__ void avg_policy(const SolverDev& d, int s, int kind, 
 }
 
 __global__ void __launch_bounds__(512, 1) best_response_kernel(SolverDev d, int n_dec, int kind, double* out2) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     __shared__ int s_lvl[MAXL + 1], s_slvl[MAXL + 1];
     const int tid = threadIdx.x, bd = blockDim.x;
     const int N = d.n_nodes, S = d.n_slots, L = d.n_levels;
@@ -1949,3 +1958,4 @@ int ms_best_response(ms_solver* s, int32_t policy_kind, double h_br_values[2], v
 }
 
 }  // extern "C"
+#endif  // MS_HOST_RULES_ONLY

@@ -93,6 +93,22 @@ def build_env_host():
     return ENV_LIB
 
 
+SOLVER_LIB = os.path.join(OUT, "libms_solver_host.so")
+
+
+def build_solver_host():
+    """the product's tree enumeration + vanilla-CFR kernels (csrc/ms_solver.cu) on the CTA emulator; IEEE double, no contraction"""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "ms_solver_host.cpp")
+    csrc = os.path.join(ROOT, "scopa_b200", "csrc")
+    deps = [src, os.path.join(HERE, "cta_emu.h")] + [os.path.join(csrc, f) for f in ("ms_solver.cu", "ms_tree_walk.cuh",
+                                                                                     "ms_state.cuh", "ms_common.cuh")]
+    if _newer(SOLVER_LIB, deps):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
+                        f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", SOLVER_LIB, src], check=True)
+    return SOLVER_LIB
+
+
 def build_check():
     """needs libscopa_b200.so (scopa_b200/_build.py) and the CUDA runtime headers; links both libraries by rpath"""
     build_emu()
@@ -115,4 +131,5 @@ if __name__ == "__main__":
     print(build_team_host())
     print(build_full_host())
     print(build_env_host())
+    print(build_solver_host())
     print(build_check())

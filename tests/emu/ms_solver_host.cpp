@@ -1,0 +1,181 @@
+// tests/emu/ms_solver_host.cpp -- the PRODUCT's game-tree enumeration and vanilla-CFR kernels (scopa_b200/csrc/
+// ms_solver.cu: tree_expand_kernel <<<1, 256>>>, cfr_kernel <<<1, 512>>> with cfr_run / cfr_traversal, and regret_match of
+// ms_tree_walk.cuh) executed on the host by the CTA emulator of tests/emu/cta_emu.h: one pthread per CUDA thread,
+// pthread barriers for __syncthreads, one buffer for the dynamic shared memory.  __dadd_rn / __dmul_rn / __ddiv_rn are
+// IEEE double add / mul / div (this file is compiled with -ffp-contract=off), so the emulated kernel must produce the
+// same float64 bits as the device -- and as numpy in the reference (tests/test_solver_host.py checks the latter against
+// tables recorded from the unmodified reference).
+// Between the two kernels the library indexes the infosets on the host (solver_build in ms_solver.cu: "pure
+// bookkeeping, no game rules"); that step is restated here from its description: slots in breadth-first
+// first-occurrence order, per-slot chains of node ids in ascending order, slots grouped by tree level.
+// Test infrastructure.
+#include <cstdint>
+#include <cuda_runtime.h>   // vector types for the host compiler
+#include <unordered_map>
+#include <vector>
+
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline unsigned __activemask() { return 1u; }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }   // only ever a shared loop bound
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+// ms_tree_walk.cuh (included by ms_solver.cu, not exercised here) needs the names to exist
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline double atomicAdd(double* p, double v) {
+    unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
+    unsigned long long old = __atomic_load_n(q, __ATOMIC_RELAXED), want;
+    double cur;
+    do {
+        __builtin_memcpy(&cur, &old, 8);
+        cur += v;
+        __builtin_memcpy(&want, &cur, 8);
+    } while (!__atomic_compare_exchange_n(q, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    __builtin_memcpy(&cur, &old, 8);
+    return cur;
+}
+#undef __device__
+#undef __global__
+#undef __host__
+#undef __shared__
+#undef __forceinline__
+#undef __launch_bounds__
+#undef __align__
+#include "cta_emu.h"
+#define __host__
+#define __align__(n) alignas(n)
+
+#define MS_HOST_RULES_ONLY
+#include "../../scopa_b200/csrc/ms_solver.cu"
+
+namespace ms {   // declared in ms_common.cuh, defined in ms_env.cu in the library
+std::atomic<uint64_t> g_launches{0};
+char* last_error_buf() { static thread_local char buf[512]; return buf; }
+}
+
+namespace {
+using namespace ms;
+
+struct ExpandArgs { uint4 root; uint32_t hand_order; TreeOut t; };
+void expand_entry(ExpandArgs a) { tree_expand_kernel(a.root, a.hand_order, a.t); }
+struct CfrArgs { SolverDev d; int n_dec, iters, only_player; double r0, r1; double* out; };
+void cfr_entry(CfrArgs a) { cfr_kernel(a.d, a.n_dec, a.iters, a.only_player, a.r0, a.r1, a.out); }
+
+struct HostSolver {
+    std::vector<uint4> state; std::vector<int> parent, child_begin32, level_begin, slot_level_begin;
+    std::vector<uint8_t> nchild, slot_nlegal, slot_player, slot_legal, touched;
+    std::vector<unsigned long long> key, slot_key, counters;
+    std::vector<uint16_t> legal, child_begin, chain_begin, chain_nodes;
+    std::vector<int8_t> rx2;
+    std::vector<int16_t> node_slot;
+    std::vector<double> regret, strategy, delta;
+    int N = 0, L = 0, S = 0, n_dec = 0;
+    SolverDev dev{};
+} H;
+}  // namespace
+
+extern "C" {
+
+int host_solver_build(const uint32_t* root4, uint32_t hand_order, int* n_nodes, int* n_slots, int* n_levels) {
+    H = HostSolver();
+    H.state.resize(MAXN); H.parent.resize(MAXN); H.child_begin32.resize(MAXN); H.nchild.resize(MAXN); H.key.resize(MAXN);
+    H.legal.resize(MAXN); H.rx2.resize(MAXN); H.level_begin.assign(MAXL + 2, 0);
+    int counts[4] = {0, 0, 0, 0};
+    ExpandArgs ea;
+    ea.root = make_uint4(root4[0], root4[1], root4[2], root4[3]);
+    ea.hand_order = hand_order;
+    ea.t.state = H.state.data(); ea.t.parent = H.parent.data(); ea.t.child_begin = H.child_begin32.data();
+    ea.t.nchild = H.nchild.data(); ea.t.key = H.key.data(); ea.t.legal = H.legal.data(); ea.t.rx2 = H.rx2.data();
+    ea.t.level_begin = H.level_begin.data(); ea.t.counts = counts;
+    if (emu_launch_cta(expand_entry, ea, 256)) return -1;
+    if (counts[2]) return -2;
+    const int N = counts[0], L = counts[1];
+    H.N = N; H.L = L;
+    // infoset slots: breadth-first first occurrence; chains: the slot's nodes in ascending index order
+    std::vector<int> level(N, 0), slot_level;
+    for (int l = 0; l < L; l++) for (int v = H.level_begin[l]; v < H.level_begin[l + 1]; v++) level[v] = l;
+    std::unordered_map<unsigned long long, int> slot_of;
+    std::vector<std::vector<int>> chains;
+    H.node_slot.assign(N, -1);
+    for (int v = 0; v < N; v++) {
+        if (!H.nchild[v]) continue;
+        auto it = slot_of.find(H.key[v]);
+        int s;
+        if (it == slot_of.end()) {
+            s = (int)chains.size();
+            slot_of.emplace(H.key[v], s);
+            chains.emplace_back();
+            slot_level.push_back(level[v]);
+            H.slot_key.push_back(H.key[v]);
+            H.slot_nlegal.push_back(H.nchild[v]);
+            H.slot_player.push_back((uint8_t)((H.key[v] >> 52) & 1ull));
+            for (int i = 0; i < 4; i++) H.slot_legal.push_back(i < H.nchild[v] ? (uint8_t)((H.legal[v] >> (4 * i)) & 0xF) : (uint8_t)0xFF);
+        } else {
+            s = it->second;
+            if (slot_level[s] != level[v] || H.slot_nlegal[s] != H.nchild[v]) return -3;
+        }
+        H.node_slot[v] = (int16_t)s;
+        chains[s].push_back(v);
+    }
+    const int S = (int)chains.size();
+    H.S = S;
+    H.slot_level_begin.assign(L + 1, S);
+    for (int l = 0, s = 0; l <= L; l++) {
+        while (s < S && slot_level[s] < l) s++;
+        H.slot_level_begin[l] = s;
+    }
+    for (int s = 0; s < S; s++) {
+        H.chain_begin.push_back((uint16_t)H.chain_nodes.size());
+        for (int v : chains[s]) H.chain_nodes.push_back((uint16_t)v);
+    }
+    H.chain_begin.push_back((uint16_t)H.chain_nodes.size());
+    H.n_dec = (int)H.chain_nodes.size();
+    H.child_begin.resize(N);
+    for (int v = 0; v < N; v++) H.child_begin[v] = (uint16_t)H.child_begin32[v];
+    H.regret.assign(4 * (size_t)S, 0.0); H.strategy.assign(4 * (size_t)S, 0.0); H.delta.assign(5 * (size_t)S, 0.0);
+    H.touched.assign(S, 0); H.counters.assign(4, 0);
+    SolverDev& d = H.dev;
+    d.n_nodes = N; d.n_levels = L; d.n_slots = S; d.root_cur = (int)((root4[3] >> 17) & 1u);
+    d.root = ea.root; d.hand_order = hand_order;
+    d.level_begin = H.level_begin.data(); d.child_begin = H.child_begin.data(); d.nchild = H.nchild.data();
+    d.node_slot = H.node_slot.data(); d.rx2 = H.rx2.data();
+    d.chain_begin = H.chain_begin.data(); d.chain_nodes = H.chain_nodes.data(); d.slot_level_begin = H.slot_level_begin.data();
+    d.slot_nlegal = H.slot_nlegal.data(); d.slot_player = H.slot_player.data();
+    d.hkeys = nullptr; d.hslots = nullptr; d.hcap = 0;
+    d.regret = H.regret.data(); d.strategy = H.strategy.data(); d.delta = H.delta.data();
+    d.touched = H.touched.data(); d.counters = H.counters.data();
+    *n_nodes = N; *n_slots = S; *n_levels = L;
+    return 0;
+}
+
+void host_solver_tree(uint32_t* states, int* parent, int* child_begin, uint8_t* nchild, int* slot, int* level_begin) {
+    for (int v = 0; v < H.N; v++) {
+        states[4 * v] = H.state[v].x; states[4 * v + 1] = H.state[v].y; states[4 * v + 2] = H.state[v].z; states[4 * v + 3] = H.state[v].w;
+        parent[v] = H.parent[v]; child_begin[v] = H.child_begin32[v]; nchild[v] = H.nchild[v]; slot[v] = H.node_slot[v];
+    }
+    for (int l = 0; l <= H.L; l++) level_begin[l] = H.level_begin[l];
+}
+
+void host_solver_export(unsigned long long* keys, uint8_t* nlegal, uint8_t* legal4, double* regret, double* strategy) {
+    for (int s = 0; s < H.S; s++) {
+        if (keys) keys[s] = H.slot_key[s];
+        if (nlegal) nlegal[s] = H.slot_nlegal[s];
+        for (int i = 0; i < 4; i++) {
+            if (legal4) legal4[4 * s + i] = H.slot_legal[4 * s + i];
+            if (regret) regret[4 * s + i] = H.regret[4 * s + i];
+            if (strategy) strategy[4 * s + i] = H.strategy[4 * s + i];
+        }
+    }
+}
+
+// ms_cfr_iterate / ms_cfr_traverse: cfr_kernel<<<1, 512, cfr_smem_bytes(...)>>>
+int host_cfr(int iters, int only_player, double r0, double r1, double* out_value) {
+    if (cfr_smem_bytes(H.N, H.S, H.n_dec) > EMU_SMEM_BYTES) return -4;
+    CfrArgs a{H.dev, H.n_dec, iters, only_player, r0, r1, out_value};
+    return emu_launch_cta(cfr_entry, a, 512);
+}
+
+}  // extern "C"
