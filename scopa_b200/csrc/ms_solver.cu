@@ -317,11 +317,6 @@ __device__ void cfr_run(const SolverDev& d, int n_dec, int iters, int only_playe
     if (tid == 0 && out_value) *out_value = m.u[0];
 }
 
-}  // namespace ms
-
-#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_solver_host.cpp compiles the tree enumeration and vanilla CFR above for the host
-namespace ms {
-
 // ------------------------------------------------------------------------------------------------
 // K3  the reference's sampled-CFR estimator (mc_cfr.py:37-86).
 //
@@ -566,6 +561,10 @@ __global__ void __launch_bounds__(32, 1) mccfr_inplace_kernel(SolverDev d, long 
     for (int i = tid; i < S; i += 32) d.touched[i] = touched[i];
 }
 
+}  // namespace ms
+
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_solver_host.cpp compiles everything above (tree enumeration, vanilla CFR, the
+namespace ms {               // in-place reference-semantics MCCFR kernel) for the host
 constexpr int MCCFR_THREADS = 768;
 
 __host__ __device__ inline size_t mccfr_batch_smem(int S, int hcap, int nframes, int threads) {

@@ -23,8 +23,9 @@ static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }   /
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
-// ms_tree_walk.cuh (included by ms_solver.cu, not exercised here) needs the names to exist
+// counters, and the batch kernels' delta tables (ms_tree_walk.cuh, not exercised here)
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline double atomicAdd(double* p, double v) {
     unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
     unsigned long long old = __atomic_load_n(q, __ATOMIC_RELAXED), want;
@@ -47,6 +48,7 @@ static inline double atomicAdd(double* p, double v) {
 #include "cta_emu.h"
 #define __host__
 #define __align__(n) alignas(n)
+static inline void __syncwarp() { __syncthreads(); }   // only used by the one-warp kernels (<<<1, 32>>>): the warp is the block
 
 #define MS_HOST_RULES_ONLY
 #include "../../scopa_b200/csrc/ms_solver.cu"
@@ -63,6 +65,8 @@ struct ExpandArgs { uint4 root; uint32_t hand_order; TreeOut t; };
 void expand_entry(ExpandArgs a) { tree_expand_kernel(a.root, a.hand_order, a.t); }
 struct CfrArgs { SolverDev d; int n_dec, iters, only_player; double r0, r1; double* out; };
 void cfr_entry(CfrArgs a) { cfr_kernel(a.d, a.n_dec, a.iters, a.only_player, a.r0, a.r1, a.out); }
+struct InplaceArgs { SolverDev d; long long iters; uint2 key; unsigned long long first_iter; int nframes; };
+void inplace_entry(InplaceArgs a) { mccfr_inplace_kernel(a.d, a.iters, a.key, a.first_iter, a.nframes); }
 
 struct HostSolver {
     std::vector<uint4> state; std::vector<int> parent, child_begin32, level_begin, slot_level_begin;
@@ -72,7 +76,8 @@ struct HostSolver {
     std::vector<int8_t> rx2;
     std::vector<int16_t> node_slot;
     std::vector<double> regret, strategy, delta;
-    int N = 0, L = 0, S = 0, n_dec = 0;
+    std::vector<unsigned long long> hkeys; std::vector<int16_t> hslots;
+    int N = 0, L = 0, S = 0, n_dec = 0, hcap = 0, nframes = 1;
     SolverDev dev{};
 } H;
 }  // namespace
@@ -144,7 +149,26 @@ int host_solver_build(const uint32_t* root4, uint32_t hand_order, int* n_nodes, 
     d.node_slot = H.node_slot.data(); d.rx2 = H.rx2.data();
     d.chain_begin = H.chain_begin.data(); d.chain_nodes = H.chain_nodes.data(); d.slot_level_begin = H.slot_level_begin.data();
     d.slot_nlegal = H.slot_nlegal.data(); d.slot_player = H.slot_player.data();
-    d.hkeys = nullptr; d.hslots = nullptr; d.hcap = 0;
+    // key -> slot index probed by lookup_slot (open addressing, linear probing; a wrong restatement of the hash makes
+    // every lookup miss), and the frames the sampled traversal needs: decision levels of one player
+    int hcap = 1024;
+    while (hcap < 2 * S + 2) hcap *= 2;
+    H.hcap = hcap;
+    H.hkeys.assign(hcap, 0xFFFFFFFFFFFFFFFFull); H.hslots.assign(hcap, -1);
+    for (int s = 0; s < S; s++) {
+        uint32_t h = (uint32_t)((H.slot_key[s] * 0x9E3779B97F4A7C15ull) >> 40) & (uint32_t)(hcap - 1);
+        while (H.hkeys[h] != 0xFFFFFFFFFFFFFFFFull) h = (h + 1) & (uint32_t)(hcap - 1);
+        H.hkeys[h] = H.slot_key[s]; H.hslots[h] = (int16_t)s;
+    }
+    int dl[2] = {0, 0};
+    for (int l = 0; l < L; l++) {
+        bool any = false;
+        for (int v = H.level_begin[l]; v < H.level_begin[l + 1]; v++) any |= H.nchild[v] > 0;
+        if (any) dl[(d.root_cur + l) & 1]++;
+    }
+    H.nframes = dl[0] > dl[1] ? dl[0] : dl[1];
+    if (H.nframes < 1) H.nframes = 1;
+    d.hkeys = H.hkeys.data(); d.hslots = H.hslots.data(); d.hcap = hcap;
     d.regret = H.regret.data(); d.strategy = H.strategy.data(); d.delta = H.delta.data();
     d.touched = H.touched.data(); d.counters = H.counters.data();
     *n_nodes = N; *n_slots = S; *n_levels = L;
@@ -176,6 +200,19 @@ int host_cfr(int iters, int only_player, double r0, double r1, double* out_value
     if (cfr_smem_bytes(H.N, H.S, H.n_dec) > EMU_SMEM_BYTES) return -4;
     CfrArgs a{H.dev, H.n_dec, iters, only_player, r0, r1, out_value};
     return emu_launch_cta(cfr_entry, a, 512);
+}
+
+// ms_mccfr_inplace (re-stepping form): mccfr_inplace_kernel<<<1, 32, smem>>>
+int host_mccfr_inplace(long long iters, unsigned long long philox_seed, unsigned long long first_iter) {
+    const size_t smem = 64 * (size_t)H.S + 8 * (size_t)H.hcap + (size_t)H.nframes * 44 + 2 * (size_t)H.hcap + H.S + 64;
+    if (smem > EMU_SMEM_BYTES) return -4;
+    InplaceArgs a{H.dev, iters, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)), first_iter, H.nframes};
+    return emu_launch_cta(inplace_entry, a, 32);
+}
+
+void host_solver_counters(unsigned long long* out3, uint8_t* touched) {
+    for (int i = 0; i < 3; i++) out3[i] = H.counters[i];
+    if (touched) for (int s = 0; s < H.S; s++) touched[s] = H.touched[s];
 }
 
 }  // extern "C"

@@ -135,3 +135,28 @@ def test_cfr_traverse_is_one_recursive_call(lib):
     b = sv.table()
     assert np.array_equal(a["regret"], b["regret"]) and np.array_equal(a["strategy"], b["strategy"])
     assert all(np.isfinite(v) and abs(v) <= 4.5 for pair in vals for v in pair)
+
+
+def test_mccfr_inplace_matches_oracle_stream(lib):
+    """mccfr_inplace_kernel (the reference's sampled estimator with reference semantics: every update visible to the next
+    node visit; mc_cfr.py:37-86) on the oracle's Philox stream: the same float64 bits, the same first-touch set as the
+    reference's dict, and SURVEY 3.2's per-iteration counts (703 calls, 172 updates)."""
+    lib.host_mccfr_inplace.argtypes = [C.c_longlong, C.c_ulonglong, C.c_ulonglong]
+    lib.host_solver_counters.argtypes = [vp, vp]
+    sv = HostSolver(lib, 42)
+    strings = sv.table()["strings"]
+    t = ora.Table()
+    rng = ora.Rng(1, 777)
+    done = 0
+    for it in (1, 3, 25):
+        assert lib.host_mccfr_inplace(it - done, 777, done) == 0
+        t.mccfr_iterate(it - done, rng, first_iter=done)
+        done = it
+        tab = sv.table()
+        cnt, touched = np.zeros(3, np.uint64), np.zeros(sv.n_slots, np.uint8)
+        lib.host_solver_counters(cnt.ctypes.data, touched.ctypes.data)
+        keys, oreg, ostrat, _, _ = t.arrays()
+        perm = _perm(strings, [k.split("|", 1)[1] for k in keys])
+        assert int(touched.sum()) == len(keys) and touched[perm].all()
+        assert np.array_equal(tab["regret"][perm], oreg) and np.array_equal(tab["strategy"][perm], ostrat)
+    assert int(cnt[1]) == 703 * 25 and int(cnt[0]) == 172 * 25
