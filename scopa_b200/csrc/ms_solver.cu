@@ -561,10 +561,6 @@ __global__ void __launch_bounds__(32, 1) mccfr_inplace_kernel(SolverDev d, long 
     for (int i = tid; i < S; i += 32) d.touched[i] = touched[i];
 }
 
-}  // namespace ms
-
-#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_solver_host.cpp compiles everything above (tree enumeration, vanilla CFR, the
-namespace ms {               // in-place reference-semantics MCCFR kernel) for the host
 constexpr int MCCFR_THREADS = 768;
 
 __host__ __device__ inline size_t mccfr_batch_smem(int S, int hcap, int nframes, int threads) {
@@ -1192,6 +1188,11 @@ __global__ void __launch_bounds__(256) mccfr_apply_kernel(SolverDev d) {
         d.delta[4 * S + s] = 0.0;
     }
 }
+
+}  // namespace ms
+
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_solver_host.cpp compiles everything above (tree enumeration, vanilla CFR, the
+namespace ms {               // sampled-CFR kernels and the apply step) for the host's CTA emulator
 
 // Multi-GPU exchange without a library collective: every rank reads every rank's delta buffer directly over
 // NVLink / NVSwitch peer memory (CUDA IPC mappings), sums them in rank order -- so all replicas compute the same

@@ -49,6 +49,18 @@ static inline double atomicAdd(double* p, double v) {
 #define __host__
 #define __align__(n) alignas(n)
 static inline void __syncwarp() { __syncthreads(); }   // only used by the one-warp kernels (<<<1, 32>>>): the warp is the block
+// __shfl_down_sync(full mask, v, off) as used by the kernels' final counter reductions, which every thread of the block
+// executes the same number of times: exchange through a block-wide buffer between two block barriers
+static unsigned long long emu_shfl_buf[EMU_MAX_CLUSTER][2048];
+static inline unsigned long long __shfl_down_sync(unsigned, unsigned long long v, int off) {
+    unsigned long long* b = emu_shfl_buf[emu_block_slot];
+    const unsigned t = threadIdx.x, lane = t & 31u;
+    b[t] = v;
+    __syncthreads();
+    const unsigned long long r = (lane + (unsigned)off < 32u && t + (unsigned)off < blockDim.x) ? b[t + off] : v;
+    __syncthreads();
+    return r;
+}
 
 #define MS_HOST_RULES_ONLY
 #include "../../scopa_b200/csrc/ms_solver.cu"
@@ -67,6 +79,13 @@ struct CfrArgs { SolverDev d; int n_dec, iters, only_player; double r0, r1; doub
 void cfr_entry(CfrArgs a) { cfr_kernel(a.d, a.n_dec, a.iters, a.only_player, a.r0, a.r1, a.out); }
 struct InplaceArgs { SolverDev d; long long iters; uint2 key; unsigned long long first_iter; int nframes; };
 void inplace_entry(InplaceArgs a) { mccfr_inplace_kernel(a.d, a.iters, a.key, a.first_iter, a.nframes); }
+void inplace_tree_entry(InplaceArgs a) { mccfr_inplace_tree_kernel(a.d, a.iters, a.key, a.first_iter, a.nframes); }
+struct BatchArgs { SolverDev d; int player; long long n_trav; uint2 key; unsigned long long first_trav; int nframes, ncopy; };
+void tree_entry(BatchArgs a) { mccfr_tree_kernel<TREE_THREADS>(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes, a.ncopy); }
+void restep_entry(BatchArgs a) { mccfr_batch_kernel(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes); }
+void es_tree_entry(BatchArgs a) { mccfr_es_tree_kernel<TREE_THREADS>(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes, a.ncopy); }
+void os_entry(BatchArgs a) { mccfr_os_kernel(a.d, a.player, a.n_trav, a.key, a.first_trav); }
+void apply_entry(SolverDev d) { mccfr_apply_kernel(d); }
 
 struct HostSolver {
     std::vector<uint4> state; std::vector<int> parent, child_begin32, level_begin, slot_level_begin;
@@ -77,7 +96,7 @@ struct HostSolver {
     std::vector<int16_t> node_slot;
     std::vector<double> regret, strategy, delta;
     std::vector<unsigned long long> hkeys; std::vector<int16_t> hslots;
-    int N = 0, L = 0, S = 0, n_dec = 0, hcap = 0, nframes = 1;
+    int N = 0, L = 0, S = 0, n_dec = 0, hcap = 0, nframes = 1, nframes_tree = 1, nframes_es = 1;
     SolverDev dev{};
 } H;
 }  // namespace
@@ -169,6 +188,30 @@ int host_solver_build(const uint32_t* root4, uint32_t hand_order, int* n_nodes, 
     H.nframes = dl[0] > dl[1] ? dl[0] : dl[1];
     if (H.nframes < 1) H.nframes = 1;
     d.hkeys = H.hkeys.data(); d.hslots = H.hslots.data(); d.hcap = hcap;
+    // frames of the tree-walking kernels (solver_build, step 2): the reference estimator pushes no frame at a traverser
+    // node whose single move leads to the end of the game through forced moves only; external sampling pushes one at
+    // every traverser node with more than one action.  Longest such chain of one player, bottom-up over the tree.
+    {
+        std::vector<int> a0(N, 0), a1(N, 0), e0(N, 0), e1(N, 0);
+        for (int v = N - 1; v >= 0; v--) {
+            const int nc = H.nchild[v];
+            if (!nc) continue;
+            const int cb = H.child_begin32[v];
+            int m0 = 0, m1 = 0, x0 = 0, x1 = 0;
+            for (int c = cb; c < cb + nc; c++) {
+                if (a0[c] > m0) m0 = a0[c];
+                if (a1[c] > m1) m1 = a1[c];
+                if (e0[c] > x0) x0 = e0[c];
+                if (e1[c] > x1) x1 = e1[c];
+            }
+            const bool forced = nc == 1 && (H.nchild[cb] == 0 || (H.nchild[cb] == 1 && H.nchild[H.child_begin32[cb]] == 0));
+            const int p = (int)((H.state[v].w >> 17) & 1u), push = forced ? 0 : 1;
+            a0[v] = m0 + (p == 0 ? push : 0); a1[v] = m1 + (p == 1 ? push : 0);
+            e0[v] = x0 + ((p == 0 && nc > 1) ? 1 : 0); e1[v] = x1 + ((p == 1 && nc > 1) ? 1 : 0);
+        }
+        H.nframes_tree = std::max(1, std::max(a0[0], a1[0]));
+        H.nframes_es = std::max(1, std::max(e0[0], e1[0]));
+    }
     d.regret = H.regret.data(); d.strategy = H.strategy.data(); d.delta = H.delta.data();
     d.touched = H.touched.data(); d.counters = H.counters.data();
     *n_nodes = N; *n_slots = S; *n_levels = L;
@@ -210,8 +253,50 @@ int host_mccfr_inplace(long long iters, unsigned long long philox_seed, unsigned
     return emu_launch_cta(inplace_entry, a, 32);
 }
 
-void host_solver_counters(unsigned long long* out3, uint8_t* touched) {
-    for (int i = 0; i < 3; i++) out3[i] = H.counters[i];
+// ms_mccfr_inplace (default form): mccfr_inplace_tree_kernel<<<1, 32, smem>>>
+int host_mccfr_inplace_tree(long long iters, unsigned long long philox_seed, unsigned long long first_iter) {
+    const size_t smem = 64 * (size_t)H.S + (size_t)H.nframes_tree * 26 + 4 * (size_t)H.N + H.S + 64;
+    if (smem > EMU_SMEM_BYTES) return -4;
+    InplaceArgs a{H.dev, iters, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)), first_iter, H.nframes_tree};
+    return emu_launch_cta(inplace_tree_entry, a, 32);
+}
+
+// ms_mccfr_batch_mode: 0 = mccfr_tree_kernel (the headline kernel), 3 = mccfr_batch_kernel (re-stepping), 1 = external
+// sampling on the tree, 2 = outcome sampling; grids as grid_for(n_trav, threads, 1), blocks one after another
+int host_mccfr_batch(int mode, int player, long long n_trav, unsigned long long philox_seed, unsigned long long first_trav) {
+    BatchArgs a{H.dev, player, n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)), first_trav, 0, 1};
+    auto grid = [&](int threads) { long long g = (n_trav + threads - 1) / threads; return (unsigned)(g < 1 ? 1 : (g > 148 ? 148 : g)); };
+    if (mode == 0 || mode == 1) {
+        a.nframes = mode == 0 ? H.nframes_tree : H.nframes_es;
+        for (int ncopy : {4, 2, 1}) {
+            const size_t smem = mode == 0 ? mccfr_tree_smem(H.S, H.N, a.nframes, TREE_THREADS, ncopy)
+                                          : es_tree_smem(H.S, H.N, a.nframes, TREE_THREADS, ncopy);
+            if (smem > 227 * 1024) continue;
+            a.ncopy = ncopy;
+            return emu_launch_grid(mode == 0 ? tree_entry : es_tree_entry, a, grid(TREE_THREADS), TREE_THREADS);
+        }
+        return -4;
+    }
+    if (mode == 3) {
+        a.nframes = H.nframes;
+        int threads = MCCFR_THREADS;
+        while (threads > 128 && mccfr_batch_smem(H.S, H.hcap, H.nframes, threads) > 227 * 1024) threads -= 128;
+        return emu_launch_grid(restep_entry, a, grid(threads), threads);
+    }
+    if (mode == 2) return emu_launch_grid(os_entry, a, grid(256), 256);
+    return -5;
+}
+
+int host_mccfr_apply() { return emu_launch_grid(apply_entry, H.dev, (unsigned)((H.S + 255) / 256), 256); }
+
+double host_solver_delta_abs_sum() {
+    double t = 0.0;
+    for (double v : H.delta) t += v < 0 ? -v : v;
+    return t;
+}
+
+void host_solver_counters(unsigned long long* out3, uint8_t* touched, int reset) {
+    for (int i = 0; i < 3; i++) { out3[i] = H.counters[i]; if (reset) H.counters[i] = 0; }
     if (touched) for (int s = 0; s < H.S; s++) touched[s] = H.touched[s];
 }
 

@@ -61,6 +61,11 @@ def lib():
     L.host_solver_tree.argtypes = [vp] * 6
     L.host_solver_export.argtypes = [vp] * 5
     L.host_cfr.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, vp]
+    L.host_mccfr_inplace.argtypes = [C.c_longlong, C.c_ulonglong, C.c_ulonglong]
+    L.host_mccfr_inplace_tree.argtypes = [C.c_longlong, C.c_ulonglong, C.c_ulonglong]
+    L.host_mccfr_batch.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_ulonglong, C.c_ulonglong]
+    L.host_solver_counters.argtypes = [vp, vp, C.c_int]
+    L.host_solver_delta_abs_sum.restype = C.c_double
     return L
 
 
@@ -137,26 +142,99 @@ def test_cfr_traverse_is_one_recursive_call(lib):
     assert all(np.isfinite(v) and abs(v) <= 4.5 for pair in vals for v in pair)
 
 
-def test_mccfr_inplace_matches_oracle_stream(lib):
-    """mccfr_inplace_kernel (the reference's sampled estimator with reference semantics: every update visible to the next
-    node visit; mc_cfr.py:37-86) on the oracle's Philox stream: the same float64 bits, the same first-touch set as the
-    reference's dict, and SURVEY 3.2's per-iteration counts (703 calls, 172 updates)."""
-    lib.host_mccfr_inplace.argtypes = [C.c_longlong, C.c_ulonglong, C.c_ulonglong]
-    lib.host_solver_counters.argtypes = [vp, vp]
+def _counters(sv, reset=False):
+    cnt, touched = np.zeros(3, np.uint64), np.zeros(sv.n_slots, np.uint8)
+    sv.lib.host_solver_counters(cnt.ctypes.data, touched.ctypes.data, int(reset))
+    return {"updates": int(cnt[0]), "visits": int(cnt[1]), "env_steps": int(cnt[2])}, touched
+
+
+@pytest.mark.parametrize("kernel", ["mccfr_inplace_tree_kernel", "mccfr_inplace_kernel"])
+def test_mccfr_inplace_matches_oracle_stream(lib, kernel):
+    """The reference's sampled estimator with reference semantics (every update visible to the next node visit;
+    mc_cfr.py:37-86) -- the tree-walking form MCCFRTrainer.iteration() runs by default and the form re-stepping the env --
+    on the oracle's Philox stream: the same float64 bits, the same first-touch set as the reference's dict, and SURVEY
+    3.2's per-iteration counts (703 calls, 172 updates)."""
+    run = lib.host_mccfr_inplace_tree if kernel == "mccfr_inplace_tree_kernel" else lib.host_mccfr_inplace
     sv = HostSolver(lib, 42)
     strings = sv.table()["strings"]
     t = ora.Table()
     rng = ora.Rng(1, 777)
     done = 0
     for it in (1, 3, 25):
-        assert lib.host_mccfr_inplace(it - done, 777, done) == 0
+        assert run(it - done, 777, done) == 0
         t.mccfr_iterate(it - done, rng, first_iter=done)
         done = it
         tab = sv.table()
-        cnt, touched = np.zeros(3, np.uint64), np.zeros(sv.n_slots, np.uint8)
-        lib.host_solver_counters(cnt.ctypes.data, touched.ctypes.data)
+        cnt, touched = _counters(sv)
         keys, oreg, ostrat, _, _ = t.arrays()
         perm = _perm(strings, [k.split("|", 1)[1] for k in keys])
         assert int(touched.sum()) == len(keys) and touched[perm].all()
         assert np.array_equal(tab["regret"][perm], oreg) and np.array_equal(tab["strategy"][perm], ostrat)
-    assert int(cnt[1]) == 703 * 25 and int(cnt[0]) == 172 * 25
+    assert cnt["visits"] == 703 * 25 and cnt["updates"] == 172 * 25
+
+
+@pytest.mark.parametrize("mode,player,ntrav", [(0, 0, 1), (0, 1, 700), (0, 2, 1500), (3, 0, 700), (3, 2, 900)])
+def test_mccfr_batch_matches_oracle_frozen_sigma(lib, mode, player, ntrav):
+    """mccfr_tree_kernel<1024> (mode 0: the headline kernel of bench.py) and mccfr_batch_kernel (mode 3), then
+    mccfr_apply_kernel, against the oracle's frozen-sigma batch on the same Philox ids: tables to 1e-9 (fp64 sums in
+    another order), update / visit / step counts exactly."""
+    sv = HostSolver(lib, 42)
+    strings = sv.table()["strings"]
+    t = ora.Table()
+    t.mccfr_populate()
+    keys0, _, _, _, _ = t.arrays()
+    perm = _perm(strings, [k.split("|", 1)[1] for k in keys0])
+    assert lib.host_mccfr_inplace_tree(6, 9, 0) == 0           # a non-trivial common starting table
+    t.mccfr_iterate(6, ora.Rng(1, 9))
+    _counters(sv, reset=True)
+    assert lib.host_mccfr_batch(mode, player, ntrav, 31337, 1000) == 0
+    tab0 = sv.table()
+    _, oreg0, ostrat0, _, _ = t.arrays()
+    assert np.array_equal(tab0["regret"][perm], oreg0)          # deltas are not applied yet
+    assert lib.host_mccfr_apply() == 0
+    oreg, ostrat, nu, nv = oreg0.copy(), ostrat0.copy(), 0, 0
+    for p in ((0, 1) if player == 2 else (player,)):            # both players against the SAME frozen table
+        t.set_arrays(oreg0, ostrat0)
+        u, v = t.mccfr_batch(p, 31337, 1000, ntrav)
+        _, r1, s1, _, _ = t.arrays()
+        oreg += r1 - oreg0
+        ostrat += s1 - ostrat0
+        nu, nv = nu + u, nv + v
+    tab = sv.table()
+    np.testing.assert_allclose(tab["regret"][perm], oreg, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(tab["strategy"][perm], ostrat, rtol=1e-9, atol=1e-9)
+    cnt, _ = _counters(sv)
+    assert (cnt["updates"], cnt["visits"]) == (nu, nv)
+    assert cnt["env_steps"] == {0: 290, 1: 231, 2: 521}[player] * ntrav
+    assert lib.host_solver_delta_abs_sum() == 0.0               # apply cleared the delta buffer
+
+
+@pytest.mark.parametrize("mode,player,ntrav", [(1, 0, 600), (1, 2, 900), (2, 1, 2000), (2, 2, 2500)])
+def test_textbook_estimators_match_oracle(lib, mode, player, ntrav):
+    """External sampling on the tree (mode 1, mccfr_es_tree_kernel) and outcome sampling (mode 2, mccfr_os_kernel): the
+    estimators the north star names and the reference lacks, against the C oracle on the same Philox stream."""
+    sv = HostSolver(lib, 42)
+    strings = sv.table()["strings"]
+    t = ora.Table()
+    t.mccfr_populate()
+    keys0, _, _, _, _ = t.arrays()
+    perm = _perm(strings, [k.split("|", 1)[1] for k in keys0])
+    assert lib.host_mccfr_inplace_tree(5, 3, 0) == 0
+    t.mccfr_iterate(5, ora.Rng(1, 3))
+    _, r0, s0, _, _ = t.arrays()
+    _counters(sv, reset=True)
+    assert lib.host_mccfr_batch(mode, player, ntrav, 99, 40) == 0
+    assert lib.host_mccfr_apply() == 0
+    oreg, ostr, nu, nv = r0.copy(), s0.copy(), 0, 0
+    for p in ((0, 1) if player == 2 else (player,)):
+        t.set_arrays(r0, s0)
+        u, v = t.mccfr_batch_mode(mode, p, 99, 40, ntrav)
+        _, r1, s1, _, _ = t.arrays()
+        oreg += r1 - r0
+        ostr += s1 - s0
+        nu, nv = nu + u, nv + v
+    tab = sv.table()
+    np.testing.assert_allclose(tab["regret"][perm], oreg, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(tab["strategy"][perm], ostr, rtol=1e-9, atol=1e-9)
+    cnt, _ = _counters(sv)
+    assert (cnt["updates"], cnt["visits"]) == (nu, nv)
