@@ -1189,11 +1189,6 @@ __global__ void __launch_bounds__(256) mccfr_apply_kernel(SolverDev d) {
     }
 }
 
-}  // namespace ms
-
-#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_solver_host.cpp compiles everything above (tree enumeration, vanilla CFR, the
-namespace ms {               // sampled-CFR kernels and the apply step) for the host's CTA emulator
-
 // Multi-GPU exchange without a library collective: every rank reads every rank's delta buffer directly over
 // NVLink / NVSwitch peer memory (CUDA IPC mappings), sums them in rank order -- so all replicas compute the same
 // bits -- and applies the sum to its own table, all in this one kernel.
@@ -1212,6 +1207,7 @@ struct PeerView {
     int rank, world;
 };
 
+#ifndef MS_HOST_RULES_ONLY   // PTX in the body: not part of the host build of tests/emu/ms_solver_host.cpp
 __global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d, PeerView pv, unsigned long long epoch) {
     const int tid = threadIdx.x, S = d.n_slots;
     if (tid < pv.world) {
@@ -1243,6 +1239,7 @@ __global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d,
     }
     for (int i = tid; i < 5 * S; i += blockDim.x) pv.zero_me[i] = 0.0;
 }
+#endif  // MS_HOST_RULES_ONLY
 
 // ------------------------------------------------------------------------------------------------
 // Best response against the table's average policy (restated open_spiel BestResponsePolicy, see
@@ -1382,6 +1379,8 @@ __global__ void __launch_bounds__(256) eval_kernel(SolverDev d, const double* __
 
 }  // namespace ms
 
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_solver_host.cpp compiles every kernel above (but the peer exchange) for the
+                             // host's CTA emulator; below: the library's host side (CUDA runtime calls, launches, C ABI)
 using namespace ms;
 
 // ------------------------------------------------------------------------------------------------

@@ -86,6 +86,12 @@ void restep_entry(BatchArgs a) { mccfr_batch_kernel(a.d, a.player, a.n_trav, a.k
 void es_tree_entry(BatchArgs a) { mccfr_es_tree_kernel<TREE_THREADS>(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes, a.ncopy); }
 void os_entry(BatchArgs a) { mccfr_os_kernel(a.d, a.player, a.n_trav, a.key, a.first_trav); }
 void apply_entry(SolverDev d) { mccfr_apply_kernel(d); }
+struct BrArgs { SolverDev d; int n_dec, kind; double* out2; };
+void br_entry(BrArgs a) { best_response_kernel(a.d, a.n_dec, a.kind, a.out2); }
+struct PolArgs { SolverDev d; int kind; double* out; };
+void policy_entry(PolArgs a) { policy_kernel(a.d, a.kind, a.out); }
+struct EvalArgs { SolverDev d; const double* pol0; const double* pol1; long long n; uint2 key; unsigned long long first; float* rew; uchar2* scopas; };
+void eval_entry(EvalArgs a) { eval_kernel(a.d, a.pol0, a.pol1, a.n, a.key, a.first, a.rew, a.scopas); }
 
 struct HostSolver {
     std::vector<uint4> state; std::vector<int> parent, child_begin32, level_begin, slot_level_begin;
@@ -288,6 +294,24 @@ int host_mccfr_batch(int mode, int player, long long n_trav, unsigned long long 
 }
 
 int host_mccfr_apply() { return emu_launch_grid(apply_entry, H.dev, (unsigned)((H.S + 255) / 256), 256); }
+
+// ms_best_response: best_response_kernel<<<1, 512, cfr_smem_bytes(...)>>>
+int host_best_response(int kind, double* out2) {
+    if (cfr_smem_bytes(H.N, H.S, H.n_dec) > EMU_SMEM_BYTES) return -4;
+    BrArgs a{H.dev, H.n_dec, kind, out2};
+    return emu_launch_cta(br_entry, a, 512);
+}
+
+// ms_solver_policy / ms_eval_policies (a few blocks of 256 threads instead of the device's grid: same grid-stride loops)
+int host_policy(int kind, double* out) {
+    PolArgs a{H.dev, kind, out};
+    return emu_launch_grid(policy_entry, a, (unsigned)((H.S + 255) / 256), 256);
+}
+int host_eval(const double* pol0, const double* pol1, long long n, unsigned long long philox_seed, unsigned long long first,
+              float* rew, uint8_t* scopas) {
+    EvalArgs a{H.dev, pol0, pol1, n, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)), first, rew, (uchar2*)scopas};
+    return emu_launch_grid(eval_entry, a, 4, 256);
+}
 
 double host_solver_delta_abs_sum() {
     double t = 0.0;

@@ -13,7 +13,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, load_golden_json
 from oracle import ms_oracle as ora
 from scopa_b200 import codec
 
@@ -66,6 +66,9 @@ def lib():
     L.host_mccfr_batch.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_ulonglong, C.c_ulonglong]
     L.host_solver_counters.argtypes = [vp, vp, C.c_int]
     L.host_solver_delta_abs_sum.restype = C.c_double
+    L.host_best_response.argtypes = [C.c_int, vp]
+    L.host_policy.argtypes = [C.c_int, vp]
+    L.host_eval.argtypes = [vp, vp, C.c_longlong, C.c_ulonglong, C.c_ulonglong, vp, vp]
     return L
 
 
@@ -238,3 +241,64 @@ def test_textbook_estimators_match_oracle(lib, mode, player, ntrav):
     np.testing.assert_allclose(tab["strategy"][perm], ostr, rtol=1e-9, atol=1e-9)
     cnt, _ = _counters(sv)
     assert (cnt["updates"], cnt["visits"]) == (nu, nv)
+
+
+def _exploitability(lib, kind):
+    out = np.zeros(2)
+    assert lib.host_best_response(kind, out.ctypes.data) == 0
+    return (out[0] + out[1]) / 2.0
+
+
+def test_best_response_vs_restated_openspiel(lib):
+    """best_response_kernel against the documented restatement of open_spiel's exploitability (oracle/ms_exploit.py,
+    values in tests/golden/policies_eval.json; third-party, parity unpinned) after CFR, and against the C oracle on an
+    MCCFR table (policy kind 1: touched infosets with a 1e-12 threshold, uniform elsewhere)."""
+    g = load_golden_json("policies_eval.json")
+    sv = HostSolver(lib, 42)
+    assert abs(_exploitability(lib, 2) - g["uniform"]) < 1e-12
+    done = 0
+    for it in (1, 2, 5, 10, 20, 50):
+        sv.cfr(it - done)
+        done = it
+        assert abs(_exploitability(lib, 0) - g["cfr"][str(it)]) < 1e-9, it
+    sv = HostSolver(lib, 42)
+    t = ora.Table()
+    assert lib.host_mccfr_inplace_tree(40, 4, 0) == 0
+    t.mccfr_iterate(40, ora.Rng(1, 4))
+    e_ora, _ = t.exploitability(1)
+    assert abs(_exploitability(lib, 1) - e_ora) < 1e-9
+
+
+def test_batched_policy_evaluation_matches_exact_expectation(lib):
+    """policy_kernel + eval_kernel (evaluate_agent's episodes, vanilla_cfr.py:157-216, one thread per episode): the
+    Monte-Carlo mean against the exact tree expectation of the same two policies."""
+    sv = HostSolver(lib, 42)
+    sv.cfr(30)
+    S = sv.n_slots
+    trained, uni = np.zeros((S, 4)), np.zeros((S, 4))
+    assert lib.host_policy(0, trained.ctypes.data) == 0 and lib.host_policy(2, uni.ctypes.data) == 0
+    assert np.allclose(trained.sum(1), 1) and np.allclose(uni.sum(1), 1)
+    t = sv.tree()
+
+    def exact(pol0, pol1):
+        val = np.zeros(sv.n_nodes)
+        for v in range(sv.n_nodes - 1, -1, -1):
+            n, c0, w = int(t["nchild"][v]), int(t["child_begin"][v]), t["state"][v]
+            if n == 0:
+                s0 = bin(int(w[2]) & 0xFFFF).count("1") + 2 * ((int(w[3]) >> 4) & 0xF)
+                s1 = bin(int(w[2]) >> 16).count("1") + 2 * ((int(w[3]) >> 8) & 0xF)
+                val[v] = 0.5 * (s0 - s1)
+            else:
+                pr = (pol0 if (int(w[3]) >> 17) & 1 == 0 else pol1)[int(t["slot"][v]), :n]
+                val[v] = float(np.dot(pr, val[c0:c0 + n]))
+        return val[0]
+
+    n = 60_000
+    for a, b in ((trained, uni), (uni, trained), (uni, uni)):
+        rew, sc = np.zeros(n, np.float32), np.zeros((n, 2), np.uint8)
+        assert lib.host_eval(a.ctypes.data, b.ctypes.data, n, 12, 0, rew.ctypes.data, sc.ctypes.data) == 0
+        r = rew.astype(np.float64)
+        se = r.std() / np.sqrt(n)
+        assert abs(r.mean() - exact(a, b)) < 5 * se + 1e-9, (exact(a, b), r.mean(), se)
+        assert int(sc.max()) <= 4
+    assert abs(exact(uni, uni) - (-0.9201)) < 1e-3             # SURVEY 6: on-policy value of the uniform profile
