@@ -86,6 +86,8 @@ void restep_entry(BatchArgs a) { mccfr_batch_kernel(a.d, a.player, a.n_trav, a.k
 void es_tree_entry(BatchArgs a) { mccfr_es_tree_kernel<TREE_THREADS>(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes, a.ncopy); }
 void os_entry(BatchArgs a) { mccfr_os_kernel(a.d, a.player, a.n_trav, a.key, a.first_trav); }
 void apply_entry(SolverDev d) { mccfr_apply_kernel(d); }
+struct ManyArgs { const CfrJob* jobs; int iters; };
+void cfr_many_entry(ManyArgs a) { cfr_many_kernel(a.jobs, a.iters); }
 struct BrArgs { SolverDev d; int n_dec, kind; double* out2; };
 void br_entry(BrArgs a) { best_response_kernel(a.d, a.n_dec, a.kind, a.out2); }
 struct PolArgs { SolverDev d; int kind; double* out; };
@@ -294,6 +296,14 @@ int host_mccfr_batch(int mode, int player, long long n_trav, unsigned long long 
 }
 
 int host_mccfr_apply() { return emu_launch_grid(apply_entry, H.dev, (unsigned)((H.S + 255) / 256), 256); }
+
+// ms_cfr_iterate_many: cfr_many_kernel<<<n_jobs, 512, smem>>>, one CTA per job.  The shim holds one solver, so the jobs
+// are `n_jobs` references to it and the emulator runs the CTAs one after another: n_jobs x iters iterations in all.
+int host_cfr_many(int n_jobs, int iters) {
+    std::vector<CfrJob> jobs((size_t)n_jobs, CfrJob{H.dev, H.n_dec});
+    ManyArgs a{jobs.data(), iters};
+    return emu_launch_grid(cfr_many_entry, a, (unsigned)n_jobs, 512);
+}
 
 // ms_best_response: best_response_kernel<<<1, 512, cfr_smem_bytes(...)>>>
 int host_best_response(int kind, double* out2) {

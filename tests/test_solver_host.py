@@ -66,6 +66,7 @@ def lib():
     L.host_mccfr_batch.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_ulonglong, C.c_ulonglong]
     L.host_solver_counters.argtypes = [vp, vp, C.c_int]
     L.host_solver_delta_abs_sum.restype = C.c_double
+    L.host_cfr_many.argtypes = [C.c_int, C.c_int]
     L.host_best_response.argtypes = [C.c_int, vp]
     L.host_policy.argtypes = [C.c_int, vp]
     L.host_eval.argtypes = [vp, vp, C.c_longlong, C.c_ulonglong, C.c_ulonglong, vp, vp]
@@ -128,6 +129,18 @@ def test_vanilla_cfr_other_deals_vs_oracle(lib, seed):
     assert len(keys) == sv.n_slots
     perm = _perm(tab["strings"], [k.split("|", 1)[1] if "|" in k else k for k in keys])
     assert np.array_equal(tab["regret"][perm], oreg) and np.array_equal(tab["strategy"][perm], ostrat)
+
+
+def test_cfr_many_kernel_is_cfr_run_per_job(lib):
+    """cfr_many_kernel (one CTA per job, ms_cfr_iterate_many): here three CTAs, run one after another on the same
+    table, two iterations each == six iterations of cfr_kernel."""
+    a = HostSolver(lib, 43)
+    a.cfr(6)
+    want = a.table()
+    b = HostSolver(lib, 43)
+    assert lib.host_cfr_many(3, 2) == 0
+    got = b.table()
+    assert np.array_equal(got["regret"], want["regret"]) and np.array_equal(got["strategy"], want["strategy"])
 
 
 def test_cfr_traverse_is_one_recursive_call(lib):
