@@ -25,6 +25,10 @@
 #include "ms_state.cuh"
 #include "ms_tree_walk.cuh"
 
+#ifndef MS_DYN_SMEM   // the host emulation (tests/emu) supplies its own: one buffer per emulated block
+#define MS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace ms {
 
 struct __align__(128) MdSlot {
@@ -146,7 +150,9 @@ __device__ __forceinline__ int md_sample(const double* sg, int n, double u) {
 
 // Traversal frames: SoA in dynamic shared memory, [frame][thread], addressed from the compile-time CTA size so that
 // a frame access is one 32-bit offset computation (six 64-bit base pointers cost the kernel its register budget).
+#ifndef md_smem   // tests/emu/ms_multideal_host.cpp maps the name onto the emulated block's shared-memory buffer
 extern __shared__ __align__(16) unsigned char md_smem[];
+#endif
 template <int T>
 struct MdFrames {
     int tid;
@@ -589,7 +595,7 @@ __host__ __device__ inline size_t mdb_smem_bytes() {
 __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, const MdDealInfo* __restrict__ info, int player,
                                                                   unsigned long long first_visit, long long n_visits,
                                                                   int pairs_per_visit, uint2 pkey) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     constexpr int T = MDB_THREADS, SL = MDB_LOCAL;
     const int tid = threadIdx.x;
     double* sig = (double*)smem_raw;                       // [SL][4] frozen strategies, legal (= deal) order
@@ -692,6 +698,8 @@ __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, con
 
 }  // namespace ms
 
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_multideal_host.cpp compiles every kernel above for the host's CTA emulator;
+                             // below: the library's host side (CUDA runtime calls, launches, C ABI)
 using namespace ms;
 
 struct ms_mdsolver {
@@ -889,3 +897,4 @@ int ms_debug_random_access_peaks(int32_t log2_lines, double h_out[3], void* stre
 }
 
 }  // extern "C"
+#endif  // MS_HOST_RULES_ONLY

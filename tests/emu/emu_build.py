@@ -109,6 +109,22 @@ def build_solver_host():
     return SOLVER_LIB
 
 
+MD_LIB = os.path.join(OUT, "libms_multideal_host.so")
+
+
+def build_multideal_host():
+    """the product's multi-deal MCCFR kernels (csrc/ms_multideal.cu) on the CTA emulator, table in host memory"""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "ms_multideal_host.cpp")
+    csrc = os.path.join(ROOT, "scopa_b200", "csrc")
+    deps = [src, os.path.join(HERE, "cta_emu.h")] + [os.path.join(csrc, f) for f in ("ms_multideal.cu", "ms_tree_walk.cuh",
+                                                                                     "ms_state.cuh", "ms_common.cuh")]
+    if _newer(MD_LIB, deps):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
+                        f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", MD_LIB, src], check=True)
+    return MD_LIB
+
+
 def build_check():
     """needs libscopa_b200.so (scopa_b200/_build.py) and the CUDA runtime headers; links both libraries by rpath"""
     build_emu()
@@ -132,4 +148,5 @@ if __name__ == "__main__":
     print(build_full_host())
     print(build_env_host())
     print(build_solver_host())
+    print(build_multideal_host())
     print(build_check())
