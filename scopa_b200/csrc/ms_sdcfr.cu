@@ -25,6 +25,10 @@
 #include "ms_common.cuh"
 #include "ms_state.cuh"
 
+#ifndef MS_DYN_SMEM   // the host emulation (tests/emu) supplies its own: one buffer per emulated block
+#define MS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace ms {
 
 constexpr int SD_IN = 34, SD_H1 = 128, SD_H2 = 64, SD_OUT = 16;
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1
                                                             const float* __restrict__ feat,
                                                             const float* __restrict__ mask, float* __restrict__ adv_out,
                                                             float* __restrict__ pol_out, long long n) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     SdSmemFp32 s32{};
     SdSmemTc stc{};
     uint32_t phase = 0;
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1
 // Forward level d: inference for every frontier node, then expand (traverser) or sample (opponent).
 template <int PREC>
 __global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1 ? SD_TC_CTAS_PER_SM : SD_CTAS_PER_SM) sd_forward_kernel(SdArgs a, int d) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MS_DYN_SMEM(smem_raw);
     const int cp = d & 1;
     const bool trav = (cp == a.sh.player);
     SdSmemFp32 s32{};
@@ -642,6 +646,8 @@ static size_t sd_workspace(long long n_trav, int player, SdArgs* a, char* base) 
 
 }  // namespace ms
 
+#ifndef MS_HOST_RULES_ONLY   // tests/emu/ms_sdcfr_host.cpp compiles the kernels above for the host's CTA emulator (fp32 path);
+                             // below: the library's host side (CUDA runtime calls, launches, C ABI)
 using namespace ms;
 
 extern "C" {
@@ -737,3 +743,4 @@ int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, c
 }
 
 }  // extern "C"
+#endif  // MS_HOST_RULES_ONLY

@@ -125,6 +125,21 @@ def build_multideal_host():
     return MD_LIB
 
 
+SD_LIB = os.path.join(OUT, "libms_sdcfr_host.so")
+
+
+def build_sdcfr_host():
+    """the product's SDCFR kernels, fp32 path (csrc/ms_sdcfr.cu) on the CTA emulator; separate mul / add like --fmad=false"""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "ms_sdcfr_host.cpp")
+    csrc = os.path.join(ROOT, "scopa_b200", "csrc")
+    deps = [src, os.path.join(HERE, "cta_emu.h")] + [os.path.join(csrc, f) for f in ("ms_sdcfr.cu", "ms_state.cuh", "ms_common.cuh")]
+    if _newer(SD_LIB, deps):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
+                        f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", SD_LIB, src], check=True)
+    return SD_LIB
+
+
 def build_check():
     """needs libscopa_b200.so (scopa_b200/_build.py) and the CUDA runtime headers; links both libraries by rpath"""
     build_emu()
@@ -149,4 +164,5 @@ if __name__ == "__main__":
     print(build_env_host())
     print(build_solver_host())
     print(build_multideal_host())
+    print(build_sdcfr_host())
     print(build_check())
