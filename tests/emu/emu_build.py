@@ -30,6 +30,7 @@ def build_emu():
 
 
 STATE_LIB = os.path.join(OUT, "libms_state_host.so")
+HOST_H = os.path.join(HERE, "host_intrinsics.h")   # intrinsic shims shared by the ms_*_host.cpp builds
 
 
 def _cuda_root():
@@ -41,9 +42,9 @@ def build_state_host():
     """the product's rule header (csrc/ms_state.cuh) compiled for the host; needs only the CUDA headers (vector types)"""
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(HERE, "ms_state_host.cpp")
-    deps = [src, os.path.join(ROOT, "scopa_b200", "csrc", "ms_state.cuh")]
+    deps = [src, HOST_H, os.path.join(ROOT, "scopa_b200", "csrc", "ms_state.cuh")]
     if _newer(STATE_LIB, deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", "-o", STATE_LIB, src],
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", STATE_LIB, src],
                        check=True)
     return STATE_LIB
 
@@ -56,9 +57,9 @@ def build_team_host():
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(HERE, "ms_team_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("ms_team.cu", "ms_state.cuh", "ms_common.cuh")]
+    deps = [src, HOST_H] + [os.path.join(csrc, f) for f in ("ms_team.cu", "ms_state.cuh", "ms_common.cuh")]
     if _newer(TEAM_LIB, deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", "-o", TEAM_LIB, src],
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", TEAM_LIB, src],
                        check=True)
     return TEAM_LIB
 
@@ -71,9 +72,9 @@ def build_full_host():
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(HERE, "ms_full_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("ms_full.cu", "ms_common.cuh")]
+    deps = [src, HOST_H] + [os.path.join(csrc, f) for f in ("ms_full.cu", "ms_common.cuh")]
     if _newer(FULL_LIB, deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", "-o", FULL_LIB, src],
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", FULL_LIB, src],
                        check=True)
     return FULL_LIB
 
@@ -86,9 +87,9 @@ def build_env_host():
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(HERE, "ms_env_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("ms_env.cu", "ms_state.cuh", "ms_common.cuh")]
+    deps = [src, HOST_H] + [os.path.join(csrc, f) for f in ("ms_env.cu", "ms_state.cuh", "ms_common.cuh")]
     if _newer(ENV_LIB, deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", "-o", ENV_LIB, src],
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", ENV_LIB, src],
                        check=True)
     return ENV_LIB
 
@@ -101,7 +102,7 @@ def build_solver_host():
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(HERE, "ms_solver_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
-    deps = [src, os.path.join(HERE, "cta_emu.h")] + [os.path.join(csrc, f) for f in ("ms_solver.cu", "ms_tree_walk.cuh",
+    deps = [src, HOST_H, os.path.join(HERE, "cta_emu.h"), os.path.join(HERE, "cta_emu_warp.h")] + [os.path.join(csrc, f) for f in ("ms_solver.cu", "ms_tree_walk.cuh",
                                                                                      "ms_state.cuh", "ms_common.cuh")]
     if _newer(SOLVER_LIB, deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
@@ -117,7 +118,7 @@ def build_multideal_host():
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(HERE, "ms_multideal_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
-    deps = [src, os.path.join(HERE, "cta_emu.h")] + [os.path.join(csrc, f) for f in ("ms_multideal.cu", "ms_tree_walk.cuh",
+    deps = [src, HOST_H, os.path.join(HERE, "cta_emu.h"), os.path.join(HERE, "cta_emu_warp.h")] + [os.path.join(csrc, f) for f in ("ms_multideal.cu", "ms_tree_walk.cuh",
                                                                                      "ms_state.cuh", "ms_common.cuh")]
     if _newer(MD_LIB, deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
@@ -133,7 +134,7 @@ def build_sdcfr_host():
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(HERE, "ms_sdcfr_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
-    deps = [src, os.path.join(HERE, "cta_emu.h")] + [os.path.join(csrc, f) for f in ("ms_sdcfr.cu", "ms_state.cuh", "ms_common.cuh")]
+    deps = [src, HOST_H, os.path.join(HERE, "cta_emu.h"), os.path.join(HERE, "cta_emu_warp.h")] + [os.path.join(csrc, f) for f in ("ms_sdcfr.cu", "ms_state.cuh", "ms_common.cuh")]
     if _newer(SD_LIB, deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
                         f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", SD_LIB, src], check=True)

@@ -7,31 +7,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-static inline int __popc(unsigned x) { return __builtin_popcount(x); }
-static inline int __ffs(int x) { return __builtin_ffs(x); }
-static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
-static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
-static inline unsigned __activemask() { return 1u; }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }
-static inline void __syncthreads() {}
-#undef __device__
-#undef __global__
-#undef __shared__
-#undef __constant__
-#undef __forceinline__
-#undef __noinline__
-#undef __launch_bounds__
-#undef __align__
-#define __device__
-#define __global__
-#define __shared__ static
-#define __constant__
-#define __forceinline__ inline
-#define __noinline__
-#define __launch_bounds__(...)
-#define __align__(n) alignas(n)
-struct host_idx { unsigned x; };
-static const host_idx blockIdx = {0}, threadIdx = {0}, blockDim = {1}, gridDim = {1};
+#define MS_HOST_ONE_THREAD
+#include "host_intrinsics.h"
 
 #define MS_HOST_RULES_ONLY
 #include "../../scopa_b200/csrc/ms_env.cu"

@@ -11,62 +11,11 @@
 #include <cuda_runtime.h>
 #include <vector>
 
-static inline int __popc(unsigned x) { return __builtin_popcount(x); }
-static inline int __ffs(int x) { return __builtin_ffs(x); }
-static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
-static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
-static inline unsigned __activemask() { return 1u; }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }   // only ever a shared loop bound
-static inline double __dadd_rn(double a, double b) { return a + b; }
-static inline double __dmul_rn(double a, double b) { return a * b; }
-static inline double __ddiv_rn(double a, double b) { return a / b; }
-template <class T> static inline T __ldcg(const T* p) { return *p; }
-static inline long long __double_as_longlong(double d) { long long v; __builtin_memcpy(&v, &d, 8); return v; }
-static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
-static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
-    __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
-    return cmp;                                   // the value found: `cmp` itself on success, the other owner's key otherwise
-}
-static inline double atomicAdd(double* p, double v) {
-    unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
-    unsigned long long old = __atomic_load_n(q, __ATOMIC_RELAXED), want;
-    double cur;
-    do {
-        __builtin_memcpy(&cur, &old, 8);
-        cur += v;
-        __builtin_memcpy(&want, &cur, 8);
-    } while (!__atomic_compare_exchange_n(q, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
-    __builtin_memcpy(&cur, &old, 8);
-    return cur;
-}
-#undef __device__
-#undef __global__
-#undef __host__
-#undef __shared__
-#undef __constant__
-#undef __forceinline__
-#undef __launch_bounds__
-#undef __align__
+#include "host_intrinsics.h"
 #include "cta_emu.h"
-#define __host__
-#define __constant__
-#define __align__(n) alignas(n)
 #define md_smem emu_dyn_smem[emu_block_slot]
 static inline void __syncwarp() { __syncthreads(); }
-// full-mask shuffles of the final counter reductions (every thread of the block executes them equally often)
-static unsigned long long emu_shfl_buf[EMU_MAX_CLUSTER][2048];
-static inline unsigned long long __shfl_down_sync(unsigned, unsigned long long v, int off) {
-    unsigned long long* b = emu_shfl_buf[emu_block_slot];
-    const unsigned t = threadIdx.x, lane = t & 31u;
-    b[t] = v;
-    __syncthreads();
-    const unsigned long long r = (lane + (unsigned)off < 32u && t + (unsigned)off < blockDim.x) ? b[t + off] : v;
-    __syncthreads();
-    return r;
-}
+#include "cta_emu_warp.h"
 
 #define MS_HOST_RULES_ONLY
 #include "../../scopa_b200/csrc/ms_multideal.cu"

@@ -12,29 +12,8 @@
 #include <cuda_bf16.h>
 #include <vector>
 
-static inline int __popc(unsigned x) { return __builtin_popcount(x); }
-static inline int __ffs(int x) { return __builtin_ffs(x); }
-static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
-static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
-static inline unsigned __activemask() { return 1u; }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }   // only ever a shared loop bound
-static inline double __dadd_rn(double a, double b) { return a + b; }
-static inline double __dmul_rn(double a, double b) { return a * b; }
-static inline double __ddiv_rn(double a, double b) { return a / b; }
-static inline float __uint_as_float(unsigned v) { float f; __builtin_memcpy(&f, &v, 4); return f; }
-static inline size_t __cvta_generic_to_shared(const void*) { return 0; }       // feeds the tcgen05 / mbarrier PTX only
-#undef __device__
-#undef __global__
-#undef __host__
-#undef __shared__
-#undef __constant__
-#undef __forceinline__
-#undef __launch_bounds__
-#undef __align__
+#include "host_intrinsics.h"
 #include "cta_emu.h"
-#define __host__
-#define __constant__
-#define __align__(n) alignas(n)
 static pthread_barrier_t emu_warp_barrier[64];
 static inline void __syncwarp() { pthread_barrier_wait(&emu_warp_barrier[threadIdx.x >> 5]); }
 

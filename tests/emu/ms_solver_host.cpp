@@ -14,53 +14,10 @@
 #include <unordered_map>
 #include <vector>
 
-static inline int __popc(unsigned x) { return __builtin_popcount(x); }
-static inline int __ffs(int x) { return __builtin_ffs(x); }
-static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
-static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
-static inline unsigned __activemask() { return 1u; }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }   // only ever a shared loop bound
-static inline double __dadd_rn(double a, double b) { return a + b; }
-static inline double __dmul_rn(double a, double b) { return a * b; }
-static inline double __ddiv_rn(double a, double b) { return a / b; }
-// counters, and the batch kernels' delta tables (ms_tree_walk.cuh, not exercised here)
-static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline double atomicAdd(double* p, double v) {
-    unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
-    unsigned long long old = __atomic_load_n(q, __ATOMIC_RELAXED), want;
-    double cur;
-    do {
-        __builtin_memcpy(&cur, &old, 8);
-        cur += v;
-        __builtin_memcpy(&want, &cur, 8);
-    } while (!__atomic_compare_exchange_n(q, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
-    __builtin_memcpy(&cur, &old, 8);
-    return cur;
-}
-#undef __device__
-#undef __global__
-#undef __host__
-#undef __shared__
-#undef __forceinline__
-#undef __launch_bounds__
-#undef __align__
+#include "host_intrinsics.h"
 #include "cta_emu.h"
-#define __host__
-#define __align__(n) alignas(n)
 static inline void __syncwarp() { __syncthreads(); }   // only used by the one-warp kernels (<<<1, 32>>>): the warp is the block
-// __shfl_down_sync(full mask, v, off) as used by the kernels' final counter reductions, which every thread of the block
-// executes the same number of times: exchange through a block-wide buffer between two block barriers
-static unsigned long long emu_shfl_buf[EMU_MAX_CLUSTER][2048];
-static inline unsigned long long __shfl_down_sync(unsigned, unsigned long long v, int off) {
-    unsigned long long* b = emu_shfl_buf[emu_block_slot];
-    const unsigned t = threadIdx.x, lane = t & 31u;
-    b[t] = v;
-    __syncthreads();
-    const unsigned long long r = (lane + (unsigned)off < 32u && t + (unsigned)off < blockDim.x) ? b[t + off] : v;
-    __syncthreads();
-    return r;
-}
+#include "cta_emu_warp.h"
 
 #define MS_HOST_RULES_ONLY
 #include "../../scopa_b200/csrc/ms_solver.cu"

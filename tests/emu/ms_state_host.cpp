@@ -8,16 +8,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>   // vector types (uint4, make_uint4) for the host compiler
 
-static inline int __popc(unsigned x) { return __builtin_popcount(x); }
-static inline int __ffs(int x) { return __builtin_ffs(x); }
-static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
-static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
-static inline unsigned __activemask() { return 1u; }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }
-#undef __device__
-#undef __forceinline__
-#define __device__
-#define __forceinline__ inline
+#define MS_HOST_ONE_THREAD
+#include "host_intrinsics.h"
 
 #include "../../scopa_b200/csrc/ms_state.cuh"
 
