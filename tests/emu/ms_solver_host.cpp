@@ -280,6 +280,9 @@ int host_eval(const double* pol0, const double* pol1, long long n, unsigned long
     return emu_launch_grid(eval_entry, a, 4, 256);
 }
 
+// the slot-aligned delta buffer the multi-GPU exchange sums over ranks: [S][4] regret deltas, then [S] update counts
+void host_solver_delta(double* out5S) { for (size_t i = 0; i < H.delta.size(); i++) out5S[i] = H.delta[i]; }
+
 double host_solver_delta_abs_sum() {
     double t = 0.0;
     for (double v : H.delta) t += v < 0 ? -v : v;

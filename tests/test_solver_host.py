@@ -315,3 +315,24 @@ def test_batched_policy_evaluation_matches_exact_expectation(lib):
         assert abs(r.mean() - exact(a, b)) < 5 * se + 1e-9, (exact(a, b), r.mean(), se)
         assert int(sc.max()) <= 4
     assert abs(exact(uni, uni) - (-0.9201)) < 1e-3             # on-policy value of the uniform profile
+
+
+def test_mccfr_batch_shards_sum_to_whole(lib):
+    """What the multi-GPU path relies on, on the headline kernel itself: traversals [0, n) split across
+    ranks by traversal id give delta buffers whose SUM equals the single-rank buffer (same frozen table, same Philox
+    ids) -- regret deltas to 1e-9 (fp64 sums in another order), update counts exactly."""
+    lib.host_solver_delta.argtypes = [vp]
+
+    def deltas(first, n):
+        sv = HostSolver(lib, 42)
+        assert lib.host_mccfr_inplace_tree(4, 2, 0) == 0          # the same starting table on every "rank"
+        assert lib.host_mccfr_batch(0, 2, n, 5, first) == 0
+        out = np.zeros(5 * sv.n_slots)
+        lib.host_solver_delta(out.ctypes.data)
+        return out, sv.n_slots
+
+    whole, S = deltas(0, 3000)
+    a, _ = deltas(0, 1500)
+    b, _ = deltas(1500, 1500)
+    np.testing.assert_allclose(a + b, whole, rtol=1e-9, atol=1e-9)
+    assert np.array_equal((a + b)[4 * S:], whole[4 * S:]) and whole[4 * S:].sum() > 0
