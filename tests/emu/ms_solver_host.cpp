@@ -283,6 +283,8 @@ int host_eval(const double* pol0, const double* pol1, long long n, unsigned long
 // the slot-aligned delta buffer the multi-GPU exchange sums over ranks: [S][4] regret deltas, then [S] update counts
 void host_solver_delta(double* out5S) { for (size_t i = 0; i < H.delta.size(); i++) out5S[i] = H.delta[i]; }
 
+void host_solver_set_delta(const double* in5S) { for (size_t i = 0; i < H.delta.size(); i++) H.delta[i] = in5S[i]; }
+
 double host_solver_delta_abs_sum() {
     double t = 0.0;
     for (double v : H.delta) t += v < 0 ? -v : v;
