@@ -9,20 +9,27 @@ BASELINE.json's metric is double-barrelled ("MCCFR infoset-node updates/sec & en
 JSON line carries both:
   * primary (metric/value/e2e/roofline/cpu_baseline): MCCFR infoset-node updates/s, config 3/5 of
     BASELINE.json -- a step = one batched MCCFR iteration on the seed-42 deal: `--trav` traversals per
-    player per GPU against the frozen table (mccfr_tree_kernel: the estimator walking the deal's enumerated
-    game tree; "mccfr_restep" beside it = the same estimator re-stepping the env at every node), one exchange
-    of the slot-aligned delta buffer when N > 1, then table += delta (mccfr_apply_kernel).  Traversal ids are
-    global (rank-offset), so the union of all ranks' work is independent of N ("weak" scaling: per-GPU
-    work is fixed).
+    player per GPU against the frozen table, one exchange of the slot-aligned delta buffer when N > 1,
+    then table += delta.  Traversal ids are global (rank-offset), so the union of all ranks' work is
+    independent of N ("weak" scaling: per-GPU work is fixed).
   * "env": env steps/s, config 2 of BASELINE.json -- 1 M concurrent random-policy games per GPU, a step =
     one fused rollout launch (8 plies per game) over deals already resident in HBM; its own e2e
     (seeds on the host -> actions + rewards on the host), roofline and CPU baseline.
 `--workload rollout` swaps which of the two is reported as the primary metric.
 
---impl reference times the CPU restatement of the reference (oracle/, kind "port": the reference itself
-is pure Python and /root/reference does not exist on the GPU box) on all host cores, same metric/config.
+Layout of a run.  The two sections above are COLLECTIVE-SYMMETRIC: every rank executes the same sequence of
+collectives, and they are the only sections that run when N > 1.  Everything else (other estimators, the
+exploitability curves, the step-granular env API, vanilla CFR, multi-deal MCCFR, 40-card Scopa, SDCFR, the CPU
+baselines) is single-GPU reporting: it runs only when N == 1, never issues a collective, and each section is
+wrapped so that a failure shows up as {"error": ...} under its key instead of taking the line down.
+
+--impl reference times the reference's CPU implementation of the path on the box's host cores, same metric and
+config: oracle/_ref (the unmodified reference, byte-compiled by oracle/make_ref.py; single-threaded Python, one
+process per core) when it is there, else the C restatement oracle/ms_oracle.c ("port") on all cores.
 """
 import argparse
+import datetime
+import hashlib
 import json
 import os
 import subprocess
@@ -40,10 +47,7 @@ if ROOT not in sys.path:
 BYTES_PER_UPDATE_FP64 = 203.7      # 172 updates x 136 B + 291 opponent lookups x 40 B per reference iteration
 BYTES_PER_ENV_STEP = 34.0          # 16 B state load + 1 B action + 16 B state store (+ rewards on the last ply)
 FALLBACK_HBM_GBS = 6650.0
-# DRAM bytes per launch of the dominant kernels, from the committed ncu --set full captures (profiles/README.md)
-NCU_DRAM_BYTES_PER_LAUNCH = {"mccfr_batch_kernel": 117504, "rollout_kernel": 20052736,
-                             "md_mccfr_kernel": 1111869952,   # 65 536 deals, 340 992 traversal pairs (md_r01f_raw.csv)
-                             "mccfr_tree_kernel": 69376}
+UPDATES_PER_PAIR, VISITS_PER_PAIR = 172, 703     # the reference estimator's recursion shape on a 4+4-card deal
 
 
 def load_peaks():
@@ -53,6 +57,29 @@ def load_peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_sha(files):
+    """sha256 over the kernel sources a committed ncu capture describes: a capture whose recorded hash differs from the
+    tree's is reported as stale instead of being printed as if it described the running kernel."""
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def load_capture(name):
+    """profiles/captures.json: per kernel, figures read off a committed `ncu --set full` report (written by
+    profiles/summarise_capture.py from the exported raw CSV), with the kernel sources' hash at capture time."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "captures.json")) as f:
+            cap = json.load(f)[name]
+        cap = dict(cap)
+        cap["stale"] = kernel_source_sha(cap["source_files"]) != cap["source_sha16"]
+        return cap
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -145,253 +172,523 @@ def dist_env():
     return rank, world, local
 
 
-# ------------------------------------------------------------------------------------------- ours
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def headline_config(args, world, collective=None):
+    """`config` of the JSON line: the same object for the CUDA arm and for --impl reference."""
+    cfg = {"workload": "BASELINE.json configs[2]/[4]: MCCFR (the reference's estimator, mc_cfr.py:37-86), seed-42 deal, "
+                       f"{args.trav} traversals per player per GPU per iteration against a frozen table, fp64 table",
+           "traversals_per_step": 2 * args.trav * world,
+           "parallelism": (f"dp{world}: traversals sharded by id, one exchange of the slot-aligned fp64 delta buffer per iteration"
+                           if world > 1 else "single GPU"),
+           "l2": "256 MiB flush between timed steps (the working set is on-chip anyway)", "philox_seed": args.seed}
+    if collective is not None:
+        cfg["collective"] = collective
+    return cfg
+
+
+def env_config(args, world):
+    return {"workload": f"BASELINE.json configs[1]: {args.games} concurrent random-policy games per GPU, 8 plies each, "
+                        "deals resident in HBM", "l2": "256 MiB flush between timed steps", "games_per_gpu": args.games}
+
+
+class Cx:
+    """What every section needs: rank/world, device, the L2 flush and the cross-rank reductions.  `flush_l2(sync=True)`
+    issues a collective and may only be called from collective-symmetric code; everything else flushes locally."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank, self.world, self.local = dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- scopa_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # a collective mismatch must fail in minutes, not hang until the driver's limit
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
+        self.hbm_gbs, self.peak_src = load_peaks()
+        self.flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+        self.sync_word = torch.zeros(1, device=self.dev)
+        self.K, self.W = args.steps, args.warmup
+
+    def flush_l2(self, sync=False):
+        """Evict L2 between timed steps.  sync=True (symmetric sections only) also lines the ranks up again with a
+        stream-ordered all-reduce of one word, so a rank's timed step does not include another rank's flush."""
+        self.flush_buf.fill_(1)
+        if sync and self.world > 1:
+            self.dist.all_reduce(self.sync_word)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX)
+
+    def min_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MIN)
+
+    def sum_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM)
+
+    def events(self, n):
+        ev = self.torch.cuda.Event
+        return [(ev(enable_timing=True), ev(enable_timing=True)) for _ in range(n)]
+
+
+# =========================================================================================== symmetric sections
+def attach_peers_all_ranks(cx, sv):
+    """Solver.attach_peers with every failure turned into a group decision: no rank is ever left alone in a collective.
+    -> True when every rank mapped every peer's buffers."""
+    import ctypes as C
     from scopa_b200 import _lib
-    from scopa_b200.batch import BatchedMiniScopa, rollout_random_host
-    from scopa_b200.solver import Solver
+    dist, torch = cx.dist, cx.torch
+    handle, offs = (C.c_ubyte * 64)(), (C.c_uint64 * 3)()
+    ok = 1.0
+    try:
+        with torch.cuda.device(cx.dev):
+            _lib.check(sv.lib.ms_solver_ipc_export(sv.h, handle, offs))
+    except Exception as e:
+        print(f"[rank {cx.rank}] ipc export failed: {e}", file=sys.stderr)
+        ok = 0.0
+    if cx.min_over_ranks(ok) < 1.0:
+        return False
+    everyone = [None] * cx.world
+    dist.all_gather_object(everyone, (bytes(handle), [int(o) for o in offs]))
+    try:
+        handles = b"".join(h for h, _ in everyone)
+        flat = (C.c_uint64 * (3 * cx.world))(*[o for _, oo in everyone for o in oo])
+        with torch.cuda.device(cx.dev):
+            _lib.check(sv.lib.ms_solver_ipc_attach(sv.h, cx.rank, cx.world, handles, flat))
+        sv._delta_t = None
+        sv._peers = True
+    except Exception as e:          # e.g. no peer access between the GPUs of this box
+        print(f"[rank {cx.rank}] peer attach failed: {e}", file=sys.stderr)
+        ok = 0.0
+    return cx.min_over_ranks(ok) >= 1.0
 
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- scopa_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    hbm_gbs, peak_src = load_peaks()
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    sync_word = torch.zeros(1, device=dev)
-
-    def flush_l2():
-        """Evict L2 between timed steps; with several ranks also line the ranks up again (stream-ordered
-        all-reduce of one word), so that a rank's timed step does not include waiting for another rank's flush."""
-        flush_buf.fill_(1)
-        if world > 1:
-            dist.all_reduce(sync_word)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    K, W = args.steps, args.warmup
-    sampler = ClockSampler(local)
-
-    # ------------------------------------------------------------------ MCCFR (configs 3 / 5)
-    B = args.trav
-    sv = Solver(seed=42, device=dev)
-    S = sv.n_slots
-    # exchange of the delta buffer between ranks: "p2p" = ms_mccfr_apply_peers (every rank reads every rank's
-    # buffer over NVLink peer memory and applies the rank-ordered sum in one kernel), "nccl" = all-reduce + apply
-    collective = "none"
-    if world > 1:
-        collective = "nccl"
-        if args.collective in ("auto", "p2p"):
-            ok = torch.ones(1, device=dev)
-            try:
-                sv.attach_peers()
-            except Exception as e:          # e.g. no peer access between the GPUs of this box
-                print(f"[rank {rank}] peer attach failed, using NCCL: {e}", file=sys.stderr)
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() > 0:
-                collective = "p2p"
-            elif args.collective == "p2p":
-                raise SystemExit("--collective p2p requested but peer memory is unavailable")
-            else:
-                sv = Solver(seed=42, device=dev)      # a clean, un-attached solver for the NCCL path
-    delta = sv.delta_tensor() if collective != "p2p" else None
-
-    def exchange_and_apply():
-        if collective == "p2p":
-            sv.apply_peers()
-        else:
-            if collective == "nccl":
-                dist.all_reduce(delta)      # one all-reduce of 5*S float64 per iteration (NVLink / NVSwitch)
-            sv.mccfr_apply()
-
-    def mccfr_step(i):
-        # global traversal ids: iteration i, rank r -> [ (i*world + r) * B, ... + B )
-        sv.mccfr_batch(2, B, philox_seed=args.seed, first_trav=(i * world + rank) * B)
-        exchange_and_apply()
-
-    for i in range(W):
-        mccfr_step(i)
+def time_mccfr(cx, sv, exchange, B, seed, it0, warm, steps):
+    """`warm` untimed + `steps` timed iterations of {batch kernel, exchange, apply}; -> dict of device times (ms) and
+    counters, max over ranks for the step time.  `exchange(sv)` is one of the three forms below."""
+    torch = cx.torch
+    from scopa_b200 import _lib
+    rank, world = cx.rank, cx.world
+    for i in range(warm):
+        sv.mccfr_batch(2, B, philox_seed=seed, first_trav=((it0 + i) * world + rank) * B)
+        exchange(sv)
     sv.counters(reset=True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    launches0 = _lib.launch_count()
-    sampler.start()
+    ev, kev = cx.events(steps), cx.events(steps)
+    cx.barrier()
+    l0 = _lib.launch_count()
     wall0 = time.perf_counter()
-    for i in range(K):
-        flush_l2()
+    for i in range(steps):
+        cx.flush_l2(sync=True)
         ev[i][0].record()
         kev[i][0].record()
-        sv.mccfr_batch(2, B, philox_seed=args.seed, first_trav=((W + i) * world + rank) * B)
+        sv.mccfr_batch(2, B, philox_seed=seed, first_trav=((it0 + warm + i) * world + rank) * B)
         kev[i][1].record()
-        exchange_and_apply()
+        exchange(sv)
         ev[i][1].record()
-    barrier()
+    cx.barrier()
     wall = time.perf_counter() - wall0
-    mccfr_launches = _lib.launch_count() - launches0
-    ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
-    ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / K
+    launches = _lib.launch_count() - l0
+    ms_total = cx.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / steps
     cnt = sv.counters()
-    updates_all = sum_over_ranks(cnt["updates"])
-    visits_all = sum_over_ranks(cnt["visits"])
-    steps_all = sum_over_ranks(cnt["env_steps"])
-    mccfr_value = updates_all / (ms_total * 1e-3)
-    upd_per_launch = cnt["updates"] / K
-    mccfr_roof_ach = upd_per_launch * BYTES_PER_UPDATE_FP64 / (ms_kernel * 1e-3) / 1e9
+    return {"ms_total": ms_total, "ms_kernel": ms_kernel, "launches": int(launches), "wall": wall, "cnt": cnt,
+            "updates_all": cx.sum_over_ranks(cnt["updates"]), "visits_all": cx.sum_over_ranks(cnt["visits"]),
+            "edges_all": cx.sum_over_ranks(cnt["env_steps"]), "next_it": it0 + warm + steps}
+
+
+def section_mccfr(cx, sampler):
+    """Headline: batched MCCFR on the seed-42 deal (configs 3 / 5).  Collective-symmetric."""
+    torch, dist, args = cx.torch, cx.dist, cx.args
+    from scopa_b200 import _lib
+    from scopa_b200.solver import Solver
+    K, W, B, world, rank = cx.K, cx.W, args.trav, cx.world, cx.rank
+    sv = Solver(seed=42, device=cx.dev)
+    S = sv.n_slots
+    delta = sv.delta_tensor()
+
+    def ex_local(s):
+        s.mccfr_apply()
+
+    def ex_nccl(s):
+        dist.all_reduce(delta)          # one all-reduce of the fp64 delta buffer per iteration (NVLink / NVSwitch)
+        s.mccfr_apply()
+
+    def ex_p2p(s):
+        s.apply_peers()
+
+    # the exchange of the headline number: NCCL unless --collective p2p; the peer-memory kernel is timed beside it
+    sv_p2p, p2p_ok, p2p_note = None, False, None
+    if world > 1 and args.collective in ("p2p", "both"):
+        sv_p2p = Solver(seed=42, device=cx.dev)
+        p2p_ok = attach_peers_all_ranks(cx, sv_p2p)
+        if not p2p_ok:
+            p2p_note = "peer attach failed on at least one rank (stderr has the reason)"
+            if args.collective == "p2p":
+                raise SystemExit("--collective p2p requested but peer memory is unavailable")
+    if world == 1:
+        collective, exchange, hsv = "none", ex_local, sv
+    elif args.collective == "p2p":
+        collective, exchange, hsv = "p2p", ex_p2p, sv_p2p
+    else:
+        collective, exchange, hsv = "nccl", ex_nccl, sv
+
+    sampler.start()
+    r = time_mccfr(cx, hsv, exchange, B, args.seed, 0, W, K)
+    value = r["updates_all"] / (r["ms_total"] * 1e-3)
+    upd_per_launch = r["cnt"]["updates"] / K
 
     # e2e: the whole solver state crosses PCIe every step (table in from pinned host memory, table out)
     h_reg = torch.zeros((S, 4), dtype=torch.float64).pin_memory()
     h_str = torch.zeros((S, 4), dtype=torch.float64).pin_memory()
-    reg0, str0, _ = sv.export()
+    reg0, str0, _ = hsv.export()
     h_reg.copy_(torch.from_numpy(reg0)); h_str.copy_(torch.from_numpy(str0))
     lib = _lib.load()
     e2e_steps = max(3, min(K, 10))
-    barrier()
-    sv.counters(reset=True)
+    cx.barrier()
+    hsv.counters(reset=True)
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        _lib.check(lib.ms_solver_import_table(sv.h, h_reg.data_ptr(), h_str.data_ptr(), sv._stream()))
-        mccfr_step(W + K + i)
-        _lib.check(lib.ms_solver_export_table(sv.h, None, None, None, h_reg.data_ptr(), h_str.data_ptr(), None,
-                                              sv._stream()))
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_updates = sum_over_ranks(sv.counters()["updates"])
-    mccfr_e2e = {"value": e2e_updates / e2e_s, "unit": "infoset-node updates/s",
-                 "h2d_bytes_per_step": 2 * S * 4 * 8, "d2h_bytes_per_step": 2 * S * 4 * 8,
-                 "what": "ms_solver_import_table (pinned host) + mccfr batch + all-reduce + apply + ms_solver_export_table"}
+        _lib.check(lib.ms_solver_import_table(hsv.h, h_reg.data_ptr(), h_str.data_ptr(), hsv._stream()))
+        hsv.mccfr_batch(2, B, philox_seed=args.seed, first_trav=((r["next_it"] + i) * world + rank) * B)
+        exchange(hsv)
+        _lib.check(lib.ms_solver_export_table(hsv.h, None, None, None, h_reg.data_ptr(), h_str.data_ptr(), None,
+                                              hsv._stream()))
+    cx.barrier()
+    e2e_s = cx.max_over_ranks(time.perf_counter() - t0)
+    e2e_updates = cx.sum_over_ranks(hsv.counters()["updates"])
+    e2e = {"value": e2e_updates / e2e_s, "unit": "infoset-node updates/s",
+           "h2d_bytes_per_step": 2 * S * 4 * 8, "d2h_bytes_per_step": 2 * S * 4 * 8,
+           "what": "ms_solver_import_table (pinned host) + mccfr batch + exchange + apply + ms_solver_export_table"}
 
-    # ------------------------------------------------------------------ the same estimator re-stepping the env (mode 3)
-    # mccfr_batch_kernel: step(), capture resolution, legal list, infoset key and hash probe at every node instead of
-    # walking the enumerated tree -- what the headline kernel was before; kept as the comparison point
-    restep_obj = None
-    if rank == 0:
-        Br = 148 * 768 * 3
-        for i in range(2):
-            sv.mccfr_batch(2, Br, philox_seed=args.seed, first_trav=i * Br, mode=3)
-            sv.mccfr_apply()
-        sv.counters(reset=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(K):
-            sv.mccfr_batch(2, Br, philox_seed=args.seed, first_trav=(2 + i) * Br, mode=3)
-            sv.mccfr_apply()
-        e1.record()
-        torch.cuda.synchronize()
-        rc = sv.counters(reset=True)
-        rms = e0.elapsed_time(e1)
-        restep_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
-                      "value": rc["updates"] / (rms * 1e-3), "ms_per_step": rms / K,
-                      "env_steps_per_sec_inside_mccfr": rc["env_steps"] / (rms * 1e-3), "kernel": "mccfr_batch_kernel",
-                      "config": {"workload": f"same estimator, mode 3 (env re-stepped at every node), {Br} traversals per player per step"}}
+    # N > 1: the same step with each exchange form, so the line names what limits the scaling curve
+    exchange_ms = None
+    if world > 1:
+        exchange_ms = {"headline": collective}
+        it = r["next_it"] + e2e_steps
+        short = max(5, min(K, 10))
+        for name, fn, s in (("no_exchange_floor", ex_local, sv), ("nccl", ex_nccl, sv), ("p2p", ex_p2p, sv_p2p)):
+            if name == collective:
+                exchange_ms[name + "_ms_per_step"] = r["ms_total"] / K
+                continue
+            if name == "p2p":
+                if not p2p_ok:
+                    exchange_ms["p2p"] = p2p_note or "not timed (--collective nccl)"
+                    continue
+            rr = time_mccfr(cx, s, fn, B, args.seed, it, 3, short)
+            it = rr["next_it"]
+            exchange_ms[name + "_ms_per_step"] = rr["ms_total"] / short
+            if name == "p2p":
+                err = s.peer_error()
+                bad = cx.max_over_ranks(float(err))
+                if bad:
+                    exchange_ms["p2p"] = f"peer exchange reported error word {int(bad)} (a rank timed out waiting for a peer)"
+                    exchange_ms.pop("p2p_ms_per_step", None)
+        exchange_ms["note"] = ("ms per iteration, max over ranks, same batch size; no_exchange_floor applies only the LOCAL delta "
+                               "(not a valid multi-GPU result): the gap to it is what the exchange costs")
 
-    # ------------------------------------------------------------------ textbook external sampling (opt-in estimator)
-    es_obj = None
-    if rank == 0:
-        es_sv = Solver(seed=42, device=dev)
-        Bes = 148 * 1024 * 2
-        for i in range(W):
-            es_sv.mccfr_batch(2, Bes, philox_seed=args.seed, first_trav=i * Bes, mode=1)
-            es_sv.mccfr_apply()
-        es_sv.counters(reset=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(K):
-            es_sv.mccfr_batch(2, Bes, philox_seed=args.seed, first_trav=(W + i) * Bes, mode=1)
-            es_sv.mccfr_apply()
-        e1.record()
-        torch.cuda.synchronize()
-        es_cnt = es_sv.counters()
-        es_s = e0.elapsed_time(e1) * 1e-3
-        es_obj = {"estimator": "external sampling (Lanctot et al. 2009), not in the reference", "kernel": "mccfr_es_tree_kernel",
-                  "traversals_per_sec": 2.0 * Bes * K / es_s, "regret_updates_per_sec": es_cnt["updates"] / es_s,
-                  "node_visits_per_sec": es_cnt["visits"] / es_s,
-                  "exploitability_after": {"traversals_per_player": (W + K) * Bes, "value": es_sv.exploitability(1)},
-                  "note": "the reference's own estimator plateaus near 0.49 exploitability on this deal"}
-        del es_sv
-        # BASELINE.json configs[2]: "10M traversals, exploitability vs iteration" -- both estimators from an empty table,
-        # 4096 traversals per player per iteration (frozen-sigma batches), exploitability by the device best response
-        curve = {}
-        for mode_id, name, kind in ((1, "external_sampling", 1), (0, "reference_estimator", 1)):
-            csv_ = Solver(seed=42, device=dev)
-            done, pts, Bc = 0, [], 4096
-            t0 = time.perf_counter()
-            for target in [t for t in (10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7) if t <= args.curve_max]:
-                while done < target:
-                    csv_.mccfr_batch(2, Bc, philox_seed=args.seed, first_trav=done, mode=mode_id)
-                    csv_.mccfr_apply()
-                    done += Bc
-                pts.append([done, csv_.exploitability(kind)])
-            curve[name] = {"traversals_per_player_vs_exploitability": pts, "wall_s": time.perf_counter() - t0}
-            del csv_
-        es_obj["exploitability_vs_traversals"] = curve
+    obj = {
+        "metric": "mccfr_infoset_node_updates_per_sec", "value": value, "unit": "infoset-node updates/s",
+        "ms_per_step": r["ms_total"] / K, "e2e": e2e, "gpu_launches": r["launches"],
+        "node_visits_per_sec": r["visits_all"] / (r["ms_total"] * 1e-3),
+        "tree_edges_per_sec_inside_mccfr": r["edges_all"] / (r["ms_total"] * 1e-3),
+        "roofline": mccfr_roofline(cx, upd_per_launch, r["ms_kernel"]),
+        "update_composition": {
+            "per_traversal_pair": {"updates": UPDATES_PER_PAIR, "node_visits": VISITS_PER_PAIR,
+                                   "updates_at_one_card_infosets": 120, "updates_with_regret_arithmetic": 52},
+            "note": "counted as the reference counts them (mc_cfr.py:83-84 runs at every traverser node): 120 of the 172 updates "
+                    "per traversal pair are one-card infosets whose regret delta is exactly 0 and whose update is one "
+                    "strategy-count increment; the deterministic last two plies are played once and accounted twice, as "
+                    "the reference's two recursive calls would visit them (node_visits_per_sec includes those visits)"},
+        "config": headline_config(args, world, collective),
+        "wall_s": r["wall"],
+    }
+    if exchange_ms is not None:
+        obj["exchange"] = exchange_ms
+    return obj, sv
 
-    # ------------------------------------------------------------------ env rollouts (config 2)
-    G = args.games
+
+def mccfr_roofline(cx, upd_per_launch, ms_kernel):
+    """The headline kernel keeps the table, the tree and every delta in shared memory: DRAM traffic is a few KB per
+    launch, so the bound is on chip.  `frac` = issue-slot utilisation = warp instructions per launch (from the committed
+    ncu capture of THIS kernel source, scaled by the traversals of the launch: the estimator's recursion shape is
+    data-independent) / (kernel time measured in this run x 148 SMs x 4 schedulers x the SM clock).  The HBM-equivalent
+    figure SURVEY 8(d) prescribes is kept as a side note."""
+    hbm_equiv = upd_per_launch * BYTES_PER_UPDATE_FP64 / (ms_kernel * 1e-3) / 1e9
+    cap = load_capture("mccfr_headline")
+    roof = {"bound": "issue", "kernel": cap["kernel"] if cap else "mccfr headline kernel", "kernel_ms": ms_kernel,
+            "hbm_equivalent": {"achieved_gbs": hbm_equiv, "peak_gbs": cx.hbm_gbs, "ratio": hbm_equiv / cx.hbm_gbs,
+                               "peak_source": cx.peak_src,
+                               "note": "203.7 algorithmic B/update x updates per launch / kernel time: what an HBM-resident "
+                                       "table would have to move; NOT a fraction of a binding resource (the table is "
+                                       "shared-memory resident)"}}
+    if cap is None:
+        roof.update({"achieved": None, "peak": None, "unit": "G warp-instructions/s", "frac": None, "traffic": None,
+                     "note": "no committed capture of this kernel (profiles/captures.json)"})
+        return roof
+    pairs = upd_per_launch / UPDATES_PER_PAIR
+    winst = cap["warp_inst_per_traversal_pair"] * pairs
+    sm_hz = cap["sm_clock_mhz_assumed"] * 1e6
+    peak = 148 * 4 * sm_hz
+    ach = winst / (ms_kernel * 1e-3)
+    roof.update({"achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s", "frac": ach / peak,
+                 "traffic": cap.get("dram_bytes_per_launch"),
+                 "capture": {k: cap.get(k) for k in ("file", "commit", "source_sha16", "stale", "issue_slots_active_pct",
+                                                      "smem_wavefronts_pct_of_peak", "alu_pipe_pct", "fp64_pipe_pct",
+                                                      "warp_inst_per_traversal_pair", "cas_stall_share_pct")},
+                 "note": "issue-slot roofline: achieved = warp instructions per launch (ncu smsp__inst_executed.sum of the "
+                         "committed capture per traversal pair x pairs in this launch) / kernel time measured in this run; "
+                         "peak = 148 SMs x 4 schedulers x 1 warp instruction per cycle at the assumed SM clock"})
+    return roof
+
+
+def section_env(cx):
+    """Config 2: 1 M concurrent random-policy games per GPU.  Collective-symmetric."""
+    torch, args = cx.torch, cx.args
+    from scopa_b200 import _lib
+    from scopa_b200.batch import BatchedMiniScopa, rollout_random_host
+    K, W, G, rank, world, dev = cx.K, cx.W, args.games, cx.rank, cx.world, cx.dev
     seeds_np = np.arange(1 + rank * G, 1 + (rank + 1) * G, dtype=np.int64)
     b = BatchedMiniScopa(dev).reset(seeds_np)
     actions = torch.empty((G, 8), dtype=torch.uint8, device=dev)
     rewards = torch.empty((G, 2), dtype=torch.float32, device=dev)
     for i in range(W):
         b.rollout_random(philox_seed=args.seed, game_offset=rank * G, actions=actions, rewards=rewards)
-    rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    launches1 = _lib.launch_count()
+    rev = cx.events(K)
+    cx.barrier()
+    l0 = _lib.launch_count()
     for i in range(K):
-        flush_l2()
+        cx.flush_l2(sync=True)
         rev[i][0].record()
         b.rollout_random(philox_seed=args.seed + i, game_offset=rank * G, actions=actions, rewards=rewards)
         rev[i][1].record()
-    barrier()
-    env_launches = _lib.launch_count() - launches1
-    clocks = sampler.stop()
-    env_ms_total = max_over_ranks(sum(a.elapsed_time(c) for a, c in rev))
-    env_value = 8.0 * G * world * K / (env_ms_total * 1e-3)
-    env_kernel_ms = sum(a.elapsed_time(c) for a, c in rev) / K
-    env_roof_ach = 8.0 * G * BYTES_PER_ENV_STEP / (env_kernel_ms * 1e-3) / 1e9
+    cx.barrier()
+    launches = _lib.launch_count() - l0
+    ms_total = cx.max_over_ranks(sum(a.elapsed_time(c) for a, c in rev))
+    value = 8.0 * G * world * K / (ms_total * 1e-3)
+    kernel_ms = sum(a.elapsed_time(c) for a, c in rev) / K
+    roof_ach = 8.0 * G * BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9
     # e2e: seeds in pinned host memory -> deal + rollout on device -> actions + rewards in pinned host memory
     h_seeds = torch.from_numpy(seeds_np).pin_memory()
     h_act = torch.empty((G, 8), dtype=torch.uint8).pin_memory()
     h_rew = torch.empty((G, 2), dtype=torch.float32).pin_memory()
     rollout_random_host(h_seeds, args.seed, rank * G, h_act, h_rew)
-    barrier()
+    e2e_steps = max(3, min(K, 10))
+    cx.barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         rollout_random_host(h_seeds, args.seed + i, rank * G, h_act, h_rew)
-    barrier()
-    env_e2e_s = max_over_ranks(time.perf_counter() - t0)
-    env_e2e = {"value": 8.0 * G * world * e2e_steps / env_e2e_s, "unit": "env steps/s",
-               "h2d_bytes_per_step": 8 * G, "d2h_bytes_per_step": 16 * G,
-               "what": "ms_rollout_random_host: reset(seed) + 8 steps per game, host buffers in and out"}
+    cx.barrier()
+    e2e_s = cx.max_over_ranks(time.perf_counter() - t0)
+    cap = load_capture("rollout_kernel")
+    return {
+        "metric": "env_steps_per_sec", "value": value, "unit": "env steps/s", "ms_per_step": ms_total / K,
+        "e2e": {"value": 8.0 * G * world * e2e_steps / e2e_s, "unit": "env steps/s",
+                "h2d_bytes_per_step": 8 * G, "d2h_bytes_per_step": 16 * G,
+                "what": "ms_rollout_random_host: reset(seed) + 8 steps per game, host buffers in and out"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": roof_ach, "peak": cx.hbm_gbs, "unit": "GB/s", "frac": roof_ach / cx.hbm_gbs,
+                     "traffic": (cap or {}).get("dram_bytes_per_launch"), "capture": cap,
+                     "kernel": "rollout_kernel", "kernel_ms": kernel_ms, "peak_source": cx.peak_src,
+                     "note": "against the step-granular 34 B/step figure (SURVEY 8(d)); the fused kernel itself moves "
+                             "36 B/game (4.5 B/step) and is integer-issue bound (ALU pipe 85 % in the committed capture), "
+                             "not HBM bound; env_step_api.step_kernel is the HBM-bound member of the family"},
+        "config": env_config(args, world),
+    }
 
-    # ------------------------------------------------------------------ step-granular env API (HBM-bound kernels)
-    # ms_step round-trips the 16-byte state through HBM: the one kernel family here whose real bound IS the HBM
-    # roofline (33 B/step + 8 B rewards + 1 B done = 42 B moved per step with all outputs requested)
+
+# =========================================================================================== single-GPU reporting
+def guarded(fn, *a, **kw):
+    """An auxiliary section must not take the headline line down with it."""
+    try:
+        return fn(*a, **kw)
+    except Exception as e:
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {"error": repr(e)}
+
+
+def section_restep(cx, sv):
+    """the same estimator re-stepping the env at every node (mode 3): step(), capture resolution, legal list, infoset
+    key and hash probe at every node instead of walking the enumerated tree -- kept as the comparison point"""
+    torch, args, K = cx.torch, cx.args, cx.K
+    Br = 148 * 768 * 3
+    for i in range(2):
+        sv.mccfr_batch(2, Br, philox_seed=args.seed, first_trav=i * Br, mode=3)
+        sv.mccfr_apply()
+    sv.counters(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        sv.mccfr_batch(2, Br, philox_seed=args.seed, first_trav=(2 + i) * Br, mode=3)
+        sv.mccfr_apply()
+    e1.record()
+    torch.cuda.synchronize()
+    rc = sv.counters(reset=True)
+    rms = e0.elapsed_time(e1)
+    return {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
+            "value": rc["updates"] / (rms * 1e-3), "ms_per_step": rms / K,
+            "env_steps_per_sec_inside_mccfr": rc["env_steps"] / (rms * 1e-3), "kernel": "mccfr_batch_kernel",
+            "config": {"workload": f"same estimator, mode 3 (env re-stepped at every node), {Br} traversals per player per step"}}
+
+
+def section_tree_walk(cx):
+    """the generic tree-walking kernel (mode 4: shared-memory frames, any root) beside the headline"""
+    torch, args, K = cx.torch, cx.args, cx.K
+    from scopa_b200.solver import Solver
+    sv = Solver(seed=42, device=cx.dev)
+    Bt = 148 * 1024 * 3
+    for i in range(2):
+        sv.mccfr_batch(2, Bt, philox_seed=args.seed, first_trav=i * Bt, mode=4)
+        sv.mccfr_apply()
+    sv.counters(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        sv.mccfr_batch(2, Bt, philox_seed=args.seed, first_trav=(2 + i) * Bt, mode=4)
+        sv.mccfr_apply()
+    e1.record()
+    torch.cuda.synchronize()
+    rc = sv.counters(reset=True)
+    rms = e0.elapsed_time(e1)
+    return {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
+            "value": rc["updates"] / (rms * 1e-3), "ms_per_step": rms / K, "kernel": "mccfr_tree_kernel",
+            "config": {"workload": f"same estimator, mode 4 (round 1's headline kernel: DFS frames in shared memory), {Bt} "
+                                   "traversals per player per step"}}
+
+
+def section_es(cx):
+    """textbook external sampling (opt-in estimator) + BASELINE.json configs[2] exploitability curves"""
+    torch, args, K, W = cx.torch, cx.args, cx.K, cx.W
+    from scopa_b200.solver import Solver
+    es_sv = Solver(seed=42, device=cx.dev)
+    Bes = 148 * 1024 * 2
+    for i in range(W):
+        es_sv.mccfr_batch(2, Bes, philox_seed=args.seed, first_trav=i * Bes, mode=1)
+        es_sv.mccfr_apply()
+    es_sv.counters(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        es_sv.mccfr_batch(2, Bes, philox_seed=args.seed, first_trav=(W + i) * Bes, mode=1)
+        es_sv.mccfr_apply()
+    e1.record()
+    torch.cuda.synchronize()
+    es_cnt = es_sv.counters()
+    es_s = e0.elapsed_time(e1) * 1e-3
+    return {"estimator": "external sampling (Lanctot et al. 2009), not in the reference", "kernel": "mccfr_es_tree_kernel",
+            "traversals_per_sec": 2.0 * Bes * K / es_s, "regret_updates_per_sec": es_cnt["updates"] / es_s,
+            "node_visits_per_sec": es_cnt["visits"] / es_s,
+            "exploitability_after": {"traversals_per_player": (W + K) * Bes, "value": es_sv.exploitability(1)},
+            "note": "the reference's own estimator plateaus near 0.49 exploitability on this deal"}
+
+
+def section_schedules(cx):
+    """BASELINE.json configs[2] ("10 M traversals, exploitability vs iteration") for the schedules the path offers:
+    B = 1 is the reference's own schedule (in-place kernel: every update visible to the next node visit), larger B are
+    frozen-sigma batches (the headline runs at B = --trav).  Same estimator, same deal, empty table at the start; reports
+    exploitability after 10^4..10^7 traversals per player, wall time, and the time to reach exploitability 0.3 (if it
+    does).  SURVEY H5: a batch of B traversals uses one strategy for all B, so the curve depends on B."""
+    torch, args = cx.torch, cx.args
+    from scopa_b200.solver import Solver
+    targets = [t for t in (10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7) if t <= args.curve_max]
+    out = {"estimator": "reference (mc_cfr.py:37-86)", "targets_traversals_per_player": targets, "schedules": {}}
+    if not targets:
+        return out
+    for B in (1, 4096, 65536, args.trav):
+        sv = Solver(seed=42, device=cx.dev)
+        done, pts, t_03 = 0, [], None
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for target in targets:
+            if B == 1:
+                sv.mccfr_inplace(target - done, philox_seed=args.seed, first_iter=done)
+                done = target
+            else:
+                while done < target:
+                    sv.mccfr_batch(2, B, philox_seed=args.seed, first_trav=done)
+                    sv.mccfr_apply()
+                    done += B
+            ex = sv.exploitability(1)       # synchronises
+            el = time.perf_counter() - t0
+            pts.append([done, ex, el])
+            if t_03 is None and ex <= 0.3:
+                t_03 = el
+        out["schedules"]["in_place_B1" if B == 1 else f"B{B}"] = {
+            "traversals_per_player_vs_exploitability_vs_wall_s": pts, "wall_s_to_exploitability_0.3_at_a_checkpoint": t_03}
+        del sv
+    # the textbook estimator at one batch size for reference
+    sv = Solver(seed=42, device=cx.dev)
+    done, pts = 0, []
+    t0 = time.perf_counter()
+    for target in targets:
+        while done < target:
+            sv.mccfr_batch(2, 4096, philox_seed=args.seed, first_trav=done, mode=1)
+            sv.mccfr_apply()
+            done += 4096
+        pts.append([done, sv.exploitability(1), time.perf_counter() - t0])
+    out["external_sampling_B4096"] = {"traversals_per_player_vs_exploitability_vs_wall_s": pts}
+    out["note"] = ("exploitability by the device best-response sweep (restated OpenSpiel definition, parity unpinned); wall time "
+                   "includes the best-response launches at the checkpoints; the reference at B = 1 plateaus near 0.49 "
+                   "(tests/golden/policies_eval.json), frozen-sigma batches of the same estimator plateau lower")
+    return out
+
+
+def section_inplace(cx):
+    """MCCFRTrainer.iteration() as the reference runs it (mc_cfr.py:88-92): one traversal per player, every update
+    visible to the next visit.  (a) one run: the one-thread in-place kernel; (b) the reference's experiment protocol
+    (run_mccfr_experiment.py:195-202: independent runs) as ONE launch: ms_mccfr_inplace_many, one warp per run."""
+    torch, args = cx.torch, cx.args
+    from scopa_b200.solver import Solver, mccfr_inplace_many
+    sv = Solver(seed=42, device=cx.dev)
+    sv.mccfr_inplace(50, philox_seed=1)
+    torch.cuda.synchronize()
+    iters = 2000
+    t0 = time.perf_counter()
+    sv.mccfr_inplace(iters, philox_seed=1, first_iter=50)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"single_run": {"iterations": iters, "us_per_iteration": dt / iters * 1e6, "iterations_per_sec": iters / dt,
+                          "updates_per_sec": iters * UPDATES_PER_PAIR / dt, "kernel": "mccfr_inplace_tree_kernel",
+                          "note": "the reference takes 62-67 ms per iteration on one CPU core (BASELINE.md section 2)"}}
+    for runs in (10, 148 * 32):
+        tabs = mccfr_inplace_many(sv, runs, 50, philox_seed0=100)
+        torch.cuda.synchronize()
+        it_m = 500
+        t0 = time.perf_counter()
+        tabs = mccfr_inplace_many(sv, runs, it_m, philox_seed0=100)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[f"many_runs_{runs}"] = {"runs": runs, "iterations_per_run": it_m, "ms": dt * 1e3,
+                                    "run_iterations_per_sec": runs * it_m / dt,
+                                    "updates_per_sec": runs * it_m * UPDATES_PER_PAIR / dt,
+                                    "kernel": "mccfr_inplace_many_kernel"}
+        del tabs
+    out["note"] = ("reference-semantics throughput: every run is bit-identical to a solo ms_mccfr_inplace run with the same "
+                   "Philox seed (tests/test_gpu_solver.py); 10 runs x 500 iterations is the reference's published protocol")
+    return out
+
+
+def section_step_api(cx):
+    """ms_step round-trips the 16-byte state through HBM: the one kernel family here whose real bound IS the HBM
+    roofline (33 B/step + 8 B rewards + 1 B done = 42 B moved per step with all outputs requested)"""
+    torch, args, K, W, dev = cx.torch, cx.args, cx.K, cx.W, cx.dev
+    from scopa_b200.batch import BatchedMiniScopa
     NS = args.step_states
     bs = BatchedMiniScopa(dev).reset(np.arange(1, NS + 1, dtype=np.int64))
     _, ordered0, _ = bs.legal_actions()
@@ -401,24 +698,28 @@ def run_ours(args):
     done_t = torch.empty((NS,), dtype=torch.uint8, device=dev)
     for i in range(W):
         bs.step(acts_u8, rewards=rew_s, done=done_t)
-    stev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
+    stev = cx.events(K)
+    torch.cuda.synchronize()
     for i in range(K):
         bs.states.copy_(st_backup)
-        flush_l2()
+        cx.flush_l2()
         stev[i][0].record()
         bs.step(acts_u8, rewards=rew_s, done=done_t)
         stev[i][1].record()
-    barrier()
+    torch.cuda.synchronize()
     step_ms = sum(a.elapsed_time(c) for a, c in stev) / K
-    step_obj = {"kernel": "step_kernel", "env_steps_per_sec": NS / (step_ms * 1e-3), "kernel_ms": step_ms,
-                "bytes_per_step": 42, "achieved_gbs": 42.0 * NS / (step_ms * 1e-3) / 1e9,
-                "frac_of_hbm_peak": 42.0 * NS / (step_ms * 1e-3) / 1e9 / hbm_gbs,
-                "note": f"{NS} states ({16 * NS >> 20} MiB, larger than L2), one ply per launch, state + action in, "
-                        "state + rewards + done out"}
-    del bs, st_backup, rew_s, done_t
+    gbs = 42.0 * NS / (step_ms * 1e-3) / 1e9
+    return {"kernel": "step_kernel", "env_steps_per_sec": NS / (step_ms * 1e-3), "kernel_ms": step_ms,
+            "bytes_per_step": 42, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / cx.hbm_gbs,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": cx.hbm_gbs, "unit": "GB/s", "frac": gbs / cx.hbm_gbs,
+                         "traffic": None, "peak_source": cx.peak_src},
+            "note": f"{NS} states ({16 * NS >> 20} MiB, larger than L2), one ply per launch, state + action in, "
+                    "state + rewards + done out"}
 
-    # ------------------------------------------------------------------ vanilla CFR (config 1)
+
+def section_cfr(cx):
+    torch, dev, rank = cx.torch, cx.dev, cx.rank
+    from scopa_b200.solver import Solver, cfr_iterate_many
     cfr_sv = Solver(seed=42, device=dev)
     cfr_sv.cfr_iterate(5)
     torch.cuda.synchronize()
@@ -427,13 +728,11 @@ def run_ours(args):
     cfr_sv.cfr_iterate(200)
     c1.record()
     torch.cuda.synchronize()
-    cfr_obj = {"kernel": "cfr_kernel", "us_per_iteration": c0.elapsed_time(c1) * 1e3 / 200,
-               "node_visits_per_sec": 2 * 2229 * 200 / (c0.elapsed_time(c1) * 1e-3),
-               "note": "BASELINE.json configs[0]: vanilla CFR on the seed-42 deal, 200 iterations in one launch, float64, "
-                       "bit-identical to the reference's tables; the reference takes 389 ms per iteration on one CPU core"}
-
+    obj = {"kernel": "cfr_kernel", "us_per_iteration": c0.elapsed_time(c1) * 1e3 / 200,
+           "node_visits_per_sec": 2 * 2229 * 200 / (c0.elapsed_time(c1) * 1e-3),
+           "note": "BASELINE.json configs[0]: vanilla CFR on the seed-42 deal, 200 iterations in one launch, float64, "
+                   "bit-identical to the reference's tables; the reference takes 389 ms per iteration on one CPU core"}
     # throughput mode: 148 independent deals, one CTA (= one SM) per deal, one launch
-    from scopa_b200.solver import cfr_iterate_many
     many = [Solver(seed=1000 + rank * 148 + i, device=dev) for i in range(148)]
     cfr_iterate_many(many, 3)
     torch.cuda.synchronize()
@@ -442,167 +741,178 @@ def run_ours(args):
     c1.record()
     torch.cuda.synchronize()
     nodes = sum(m_.n_nodes for m_ in many)
-    cfr_obj["many_deals"] = {"deals": 148, "iterations": 100, "ms": c0.elapsed_time(c1),
-                             "deal_iterations_per_sec": 148 * 100 / (c0.elapsed_time(c1) * 1e-3),
-                             "node_visits_per_sec": 2.0 * nodes * 100 / (c0.elapsed_time(c1) * 1e-3),
-                             "note": "ms_cfr_iterate_many: seeds 1000.., float64, each deal's tables identical to a solo run"}
-    del many
+    obj["many_deals"] = {"deals": 148, "iterations": 100, "ms": c0.elapsed_time(c1),
+                         "deal_iterations_per_sec": 148 * 100 / (c0.elapsed_time(c1) * 1e-3),
+                         "node_visits_per_sec": 2.0 * nodes * 100 / (c0.elapsed_time(c1) * 1e-3),
+                         "note": "ms_cfr_iterate_many: seeds 1000.., float64, each deal's tables identical to a solo run"}
+    return obj
 
-    # ------------------------------------------------------------------ atomic roofline
-    atom_obj = None
-    if rank == 0:
-        import ctypes
-        peaks = (ctypes.c_double * 3)()
-        _lib.check(_lib.load().ms_debug_atomic_peaks(peaks, _lib.stream_ptr()))
-        pairs_per_s = mccfr_value / world / 172.0          # traversal pairs per second on this GPU
-        # per traversal pair the batch kernel issues 118 shared-memory fp64 atomic adds (regret deltas of the
-        # traverser nodes with more than one action: (1*4 + 5*3 + 20*2) per player) and 172 u32 adds (visit counts)
-        atom_obj = {"measured_peaks_per_sec": {"smem_f64_atomic_add": peaks[0], "smem_u32_atomic_add": peaks[1],
-                                               "global_red_f64_l2_resident": peaks[2]},
-                    "mccfr_smem_f64_atomics_per_sec": 118.0 * pairs_per_s, "mccfr_smem_u32_atomics_per_sec": 172.0 * pairs_per_s,
-                    "frac_of_smem_f64_peak": 118.0 * pairs_per_s / peaks[0], "frac_of_smem_u32_peak": 172.0 * pairs_per_s / peaks[1],
-                    "note": "microbenchmark: 148 CTAs x 768 threads, pseudo-random addresses over a 738x4 table; shared-memory "
-                            "fp64 atomicAdd compiles to an ATOMS.CAST.SPIN.64 compare-and-swap loop, global fp64 to REDG.E.ADD.F64"}
 
-    # ------------------------------------------------------------------ multi-deal MCCFR
-    # The regime SURVEY 8(d) names as the one where the memory system is the bound: one infoset table for 65 536
-    # deals (5.1 M stored infosets, 0.66 GB of 128-byte lines, far beyond the 126 MB L2) in HBM.
-    md_obj = mdb_obj = None
-    if rank == 0 and args.md_deals > 0:
-        import ctypes
-        from scopa_b200 import multideal
-        lg = args.md_log2_capacity
-        md = multideal.MultiDealSolver(np.arange(1, args.md_deals + 1), log2_capacity=lg, device=dev)
-        nb = args.md_trav
-        for i in range(12):                                  # fill the table: inserts are rare afterwards
-            md.mccfr_batch(nb, philox_seed=args.seed, first_trav=i * nb)
-            md.apply()
-        md.counters(reset=True)
-        mev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
-        l0 = _lib.launch_count()
-        mev[0].record()
-        for i in range(K):
-            md.mccfr_batch(nb, philox_seed=args.seed, first_trav=(12 + i) * nb)
-            mev[2 * i + 1].record()
-            md.apply()
-            mev[2 * i + 2].record()
-        torch.cuda.synchronize()
-        md_launches = _lib.launch_count() - l0
-        mc = md.counters()
-        t_trav = sum(mev[2 * i].elapsed_time(mev[2 * i + 1]) for i in range(K)) / K
-        t_app = sum(mev[2 * i + 1].elapsed_time(mev[2 * i + 2]) for i in range(K)) / K
-        # ceiling: dependent 64-byte reads of random 128-byte lines over a buffer the size of the STORED infosets
-        lines_lg = max(10, int(np.ceil(np.log2(max(mc["infosets"], 1)))))
-        rp = (ctypes.c_double * 3)()
-        table_bytes = md.table_bytes
-        # the deal-blocked form on the same table: one deal per CTA visit, 3072 traversal pairs per visit staged on chip
-        VIS, PPV = 148, 3072
-        tb0 = time.perf_counter()
-        md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=0)     # first call builds the deal records
+def section_atomics(cx, mccfr_value):
+    """atomic roofline: measured on the box"""
+    import ctypes
+    from scopa_b200 import _lib
+    peaks = (ctypes.c_double * 3)()
+    _lib.check(_lib.load().ms_debug_atomic_peaks(peaks, _lib.stream_ptr()))
+    pairs_per_s = mccfr_value / float(UPDATES_PER_PAIR)          # traversal pairs per second on this GPU
+    # per traversal pair the batch kernel issues 118 shared-memory fp64 atomic adds (regret deltas of the
+    # traverser nodes with more than one action: (1*4 + 5*3 + 20*2) per player) and 172 u32 adds (visit counts)
+    return {"measured_peaks_per_sec": {"smem_f64_atomic_add": peaks[0], "smem_u32_atomic_add": peaks[1],
+                                       "global_red_f64_l2_resident": peaks[2]},
+            "mccfr_smem_f64_atomics_per_sec": 118.0 * pairs_per_s, "mccfr_smem_u32_atomics_per_sec": 172.0 * pairs_per_s,
+            "frac_of_smem_f64_peak": 118.0 * pairs_per_s / peaks[0], "frac_of_smem_u32_peak": 172.0 * pairs_per_s / peaks[1],
+            "note": "microbenchmark: 148 CTAs x 768 threads, pseudo-random addresses over a 738x4 table; shared-memory "
+                    "fp64 atomicAdd compiles to an ATOMS.CAST.SPIN.64 compare-and-swap loop, global fp64 to REDG.E.ADD.F64"}
+
+
+def section_multideal(cx):
+    """Multi-deal MCCFR: the regime SURVEY 8(d) names as the one where the memory system is the
+    bound: one infoset table for 65 536 deals (5.1 M stored infosets, 0.66 GB of 128-byte lines, far beyond L2) in HBM."""
+    import ctypes
+    torch, args, K, dev = cx.torch, cx.args, cx.K, cx.dev
+    from scopa_b200 import _lib, multideal
+    lg = args.md_log2_capacity
+    md = multideal.MultiDealSolver(np.arange(1, args.md_deals + 1), log2_capacity=lg, device=dev)
+    nb = args.md_trav
+    for i in range(12):                                  # fill the table: inserts are rare afterwards
+        md.mccfr_batch(nb, philox_seed=args.seed, first_trav=i * nb)
         md.apply()
-        torch.cuda.synchronize()
-        build_s = time.perf_counter() - tb0
-        for i in range(1, 4):
-            md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=i * VIS)
-            md.apply()
-        md.counters(reset=True)
-        bev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-        bev[0].record()
-        for i in range(K):
-            md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=(4 + i) * VIS)
-            md.apply()
-            bev[i + 1].record()
-        torch.cuda.synchronize()
-        bc = md.counters()
-        b_ms = bev[0].elapsed_time(bev[K]) / K
-        mdb_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
-                   "value": bc["updates"] / K / (b_ms * 1e-3), "ms_per_step": b_ms, "infosets": int(bc["infosets"]),
-                   "first_call_s_incl_describing_all_deals": build_s, "kernel": "md_blocked_kernel",
-                   "config": {"workload": f"same table and estimator, deal-blocked: {VIS} visits x {PPV} traversal pairs per step, one "
-                                          "deal per CTA visit staged in shared memory (tree, strategies, delta tables), table "
-                                          "read once and written once per visit"}}
-        del md
-        torch.cuda.empty_cache()
-        _lib.check(_lib.load().ms_debug_random_access_peaks(lines_lg, rp, _lib.stream_ptr()))
-        # per traversal pair (data-independent recursion shape of the estimator, 4+4-card deals): 163 lookups of
-        # stored infosets (player 0 traversal: 26 own + 85 opponent nodes with >1 card; player 1: 26 + 26) and 52
-        # update groups (regret-delta REDs + visit count on the line just read)
-        touches = (163.0 + 52.0) * nb / (t_trav * 1e-3)
-        md_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
-                  "value": mc["updates"] / K / ((t_trav + t_app) * 1e-3),
-                  "stored_infoset_updates_per_sec": 52.0 * nb / ((t_trav + t_app) * 1e-3),
-                  "node_visits_per_sec": mc["visits"] / K / ((t_trav + t_app) * 1e-3),
-                  "ms_traverse": t_trav, "ms_apply": t_app, "gpu_launches": int(md_launches),
-                  "infosets": int(mc["infosets"]), "load_factor": mc["infosets"] / float(1 << lg), "table_bytes": int(table_bytes),
-                  "roofline": {"bound": "hbm", "kind": "random 128-byte line transactions", "achieved": touches / 1e9,
-                               "peak": rp[0] / 1e9, "unit": "G lines/s", "frac": touches / rp[0],
-                               "peak_source": f"ms_debug_random_access_peaks over 2^{lines_lg} lines (the stored infosets' footprint), "
-                                              "148 x 768 threads, dependent 64-byte reads, measured in this run",
-                               "independent_reads_peak": rp[1] / 1e9, "red_x4_lines_peak": rp[2] / 1e9,
-                               "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get("md_mccfr_kernel"), "kernel": "md_mccfr_kernel",
-                               "note": "line touches = 163 lookups + 52 update groups per traversal pair; hot (shallow) "
-                                       "infosets hit in L2 (ncu: 75 % of sectors), so the DRAM-resident ceiling is not the "
-                                       "binding one yet: the kernel is latency-bound (profiles/README.md section 6)"},
-                  "config": {"workload": f"MCCFR (reference estimator) over {args.md_deals} deals (seeds 1..), chance-sampled root, "
-                                         f"{nb} traversal pairs per step, one fp64 infoset table of 2^{lg} x 128 B in HBM",
-                             "note": "updates are reference-equivalent (172 per traversal pair); infosets with one card in hand "
-                                     "(120 of the 172) are not stored -- their strategy is the constant [1.0]"}}
+    md.counters(reset=True)
+    mev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    l0 = _lib.launch_count()
+    mev[0].record()
+    for i in range(K):
+        md.mccfr_batch(nb, philox_seed=args.seed, first_trav=(12 + i) * nb)
+        mev[2 * i + 1].record()
+        md.apply()
+        mev[2 * i + 2].record()
+    torch.cuda.synchronize()
+    md_launches = _lib.launch_count() - l0
+    mc = md.counters()
+    t_trav = sum(mev[2 * i].elapsed_time(mev[2 * i + 1]) for i in range(K)) / K
+    t_app = sum(mev[2 * i + 1].elapsed_time(mev[2 * i + 2]) for i in range(K)) / K
+    # ceiling: dependent 64-byte reads of random 128-byte lines over a buffer the size of the STORED infosets
+    lines_lg = max(10, int(np.ceil(np.log2(max(mc["infosets"], 1)))))
+    rp = (ctypes.c_double * 3)()
+    table_bytes = md.table_bytes
+    # the deal-blocked form on the same table: one deal per CTA visit, 3072 traversal pairs per visit staged on chip
+    VIS, PPV = 148, 3072
+    tb0 = time.perf_counter()
+    md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=0)     # first call builds the deal records
+    md.apply()
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - tb0
+    for i in range(1, 4):
+        md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=i * VIS)
+        md.apply()
+    md.counters(reset=True)
+    bev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    bev[0].record()
+    for i in range(K):
+        md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=(4 + i) * VIS)
+        md.apply()
+        bev[i + 1].record()
+    torch.cuda.synchronize()
+    bc = md.counters()
+    b_ms = bev[0].elapsed_time(bev[K]) / K
+    n_info = int(bc["infosets"])
+    # deal-blocked traffic: per visit the deal's stored infosets are read once (64 B used of each 128 B line) and their
+    # deltas written once
+    mdb_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
+               "value": bc["updates"] / K / (b_ms * 1e-3), "ms_per_step": b_ms, "infosets": n_info,
+               "first_call_s_incl_describing_all_deals": build_s, "kernel": "md_blocked_kernel",
+               "config": {"workload": f"same table and estimator, deal-blocked: {VIS} visits x {PPV} traversal pairs per step, one "
+                                      "deal per CTA visit staged in shared memory (tree, strategies, delta tables), table "
+                                      "read once and written once per visit"}}
+    del md
+    torch.cuda.empty_cache()
+    _lib.check(_lib.load().ms_debug_random_access_peaks(lines_lg, rp, _lib.stream_ptr()))
+    # per traversal pair (data-independent recursion shape of the estimator, 4+4-card deals): 163 lookups of
+    # stored infosets (player 0 traversal: 26 own + 85 opponent nodes with >1 card; player 1: 26 + 26) and 52
+    # update groups (regret-delta REDs + visit count on the line just read)
+    touches = (163.0 + 52.0) * nb / (t_trav * 1e-3)
+    cap = load_capture("md_mccfr_kernel")
+    md_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
+              "value": mc["updates"] / K / ((t_trav + t_app) * 1e-3),
+              "stored_infoset_updates_per_sec": 52.0 * nb / ((t_trav + t_app) * 1e-3),
+              "node_visits_per_sec": mc["visits"] / K / ((t_trav + t_app) * 1e-3),
+              "ms_traverse": t_trav, "ms_apply": t_app, "gpu_launches": int(md_launches),
+              "infosets": int(mc["infosets"]), "load_factor": mc["infosets"] / float(1 << lg), "table_bytes": int(table_bytes),
+              "roofline": {"bound": "hbm", "kind": "random 128-byte line transactions", "achieved": touches / 1e9,
+                           "peak": rp[0] / 1e9, "unit": "G lines/s", "frac": touches / rp[0],
+                           "peak_source": f"ms_debug_random_access_peaks over 2^{lines_lg} lines (the stored infosets' footprint), "
+                                          "148 x 768 threads, dependent 64-byte reads, measured in this run",
+                           "independent_reads_peak": rp[1] / 1e9, "red_x4_lines_peak": rp[2] / 1e9,
+                           "traffic": (cap or {}).get("dram_bytes_per_launch"), "capture": cap, "kernel": "md_mccfr_kernel",
+                           "note": "line touches = 163 lookups + 52 update groups per traversal pair; hot (shallow) "
+                                   "infosets hit in L2 (ncu: 75 % of sectors), so the DRAM-resident ceiling is not the "
+                                   "binding one yet: the kernel is latency-bound (profiles/README.md section 6)"},
+              "config": {"workload": f"MCCFR (reference estimator) over {args.md_deals} deals (seeds 1..), chance-sampled root, "
+                                     f"{nb} traversal pairs per step, one fp64 infoset table of 2^{lg} x 128 B in HBM",
+                         "note": "updates are reference-equivalent (172 per traversal pair); infosets with one card in hand "
+                                 "(120 of the 172) are not stored -- their strategy is the constant [1.0]"}}
+    return {"traversal_per_thread": md_obj, "deal_blocked": mdb_obj}
 
-    # ------------------------------------------------------------------ 40-card Scopa rollouts
-    full_obj = None
-    if rank == 0 and args.full_games > 0:
-        from scopa_b200 import full as fs
-        FG = args.full_games
-        fb = fs.BatchedFullScopa(dev).reset(np.arange(1, FG + 1, dtype=np.int64))
-        for i in range(2):
-            fb.rollout_random(philox_seed=args.seed, game_offset=i * FG)
-        fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        for i in range(K):
-            flush_l2()
-            fev[i][0].record()
-            fb.rollout_random(philox_seed=args.seed, game_offset=(2 + i) * FG)
-            fev[i][1].record()
-        torch.cuda.synchronize()
-        f_ms = sum(a.elapsed_time(c) for a, c in fev) / K
-        h_seeds = np.arange(1, FG + 1, dtype=np.int64)
-        # e2e: seeds in pinned host memory -> deck + deal + 36-ply rollout on device -> actions + rewards in pinned host memory
-        p_seeds = torch.from_numpy(h_seeds).pin_memory()
-        p_act = torch.empty((FG, fs.PLIES), dtype=torch.uint8).pin_memory()
-        p_rew = torch.empty((FG, 2), dtype=torch.float32).pin_memory()
-        flib = _lib.load()
-        _lib.check(flib.ms_full_rollout_random_host(p_seeds.data_ptr(), FG, args.seed, 0, p_act.data_ptr(), p_rew.data_ptr()))
-        f_reps = max(3, min(K, 10))
+
+def section_full(cx):
+    """40-card Scopa rollouts"""
+    torch, args, K, dev = cx.torch, cx.args, cx.K, cx.dev
+    from scopa_b200 import _lib
+    from scopa_b200 import full as fs
+    FG = args.full_games
+    fb = fs.BatchedFullScopa(dev).reset(np.arange(1, FG + 1, dtype=np.int64))
+    for i in range(2):
+        fb.rollout_random(philox_seed=args.seed, game_offset=i * FG)
+    fev = cx.events(K)
+    for i in range(K):
+        cx.flush_l2()                     # local flush only: this section runs on one rank
+        fev[i][0].record()
+        fb.rollout_random(philox_seed=args.seed, game_offset=(2 + i) * FG)
+        fev[i][1].record()
+    torch.cuda.synchronize()
+    f_ms = sum(a.elapsed_time(c) for a, c in fev) / K
+    h_seeds = np.arange(1, FG + 1, dtype=np.int64)
+    # e2e: seeds in pinned host memory -> deck + deal + 36-ply rollout on device -> actions + rewards in pinned host memory
+    p_seeds = torch.from_numpy(h_seeds).pin_memory()
+    p_act = torch.empty((FG, fs.PLIES), dtype=torch.uint8).pin_memory()
+    p_rew = torch.empty((FG, 2), dtype=torch.float32).pin_memory()
+    flib = _lib.load()
+    _lib.check(flib.ms_full_rollout_random_host(p_seeds.data_ptr(), FG, args.seed, 0, p_act.data_ptr(), p_rew.data_ptr()))
+    f_reps = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for i in range(f_reps):
+        _lib.check(flib.ms_full_rollout_random_host(p_seeds.data_ptr(), FG, args.seed + i, 0, p_act.data_ptr(), p_rew.data_ptr()))
+    f_e2e = (time.perf_counter() - t0) / f_reps
+    cpu_full = None
+    if not args.no_cpu:
+        from oracle import ms_oracle as ora              # CPU leg: the checker timed as the baseline
+        ncpu = os.cpu_count() or 1
+        ora.full_rollout_random(h_seeds[:2000], args.seed)
         t0 = time.perf_counter()
-        for i in range(f_reps):
-            _lib.check(flib.ms_full_rollout_random_host(p_seeds.data_ptr(), FG, args.seed + i, 0, p_act.data_ptr(), p_rew.data_ptr()))
-        f_e2e = (time.perf_counter() - t0) / f_reps
-        cpu_full = None
-        if world == 1 and not args.no_cpu:
-            from oracle import ms_oracle as ora              # CPU leg: the checker timed as the baseline
-            ncpu = os.cpu_count() or 1
-            ora.full_rollout_random(h_seeds[:2000], args.seed)
-            t0 = time.perf_counter()
-            ora.full_rollout_random(h_seeds[:200_000], args.seed)
-            dt = time.perf_counter() - t0
-            cpu_full = {"value": 200_000 * fs.PLIES / dt, "unit": "env steps/s", "cores": ncpu, "kind": "port",
-                        "sample": "200 000 games x 36 plies, OpenMP over all host threads"}
-        full_obj = {"metric": "env_steps_per_sec", "unit": "env steps/s", "value": FG * fs.PLIES / (f_ms * 1e-3), "ms_per_step": f_ms,
-                    "e2e": {"value": FG * fs.PLIES / f_e2e, "unit": "env steps/s", "h2d_bytes_per_step": 8 * FG,
-                            "d2h_bytes_per_step": (fs.PLIES + 8) * FG,
-                            "what": "ms_full_rollout_random_host: FullDeck(seed) + deal + 36 plies per game, pinned host buffers in and out, "
-                                    "H2D / kernels / D2H pipelined over three streams"},
-                    "roofline": {"bound": "hbm", "achieved": FG * fs.PLIES * 65.0 / (f_ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
-                                 "frac": FG * fs.PLIES * 65.0 / (f_ms * 1e-3) / 1e9 / hbm_gbs, "traffic": None,
-                                 "kernel": "full_rollout_kernel", "peak_source": peak_src,
-                                 "note": "against the step-granular figure for this game, 65 B/step (32 B state load + 1 B action "
-                                         "+ 32 B state store); the fused kernel keeps the state in registers and moves "
-                                         "108 B/game = 3 B/step, so it is integer-issue bound like the Miniscopa rollout"},
-                    "cpu_baseline": cpu_full,
-                    "config": {"workload": f"{FG} concurrent random-policy games of 40-card Scopa (FullScopaEnv), 36 plies each, "
-                                           "deals resident in HBM", "l2": "256 MiB flush between timed steps"}}
-        del fb
+        ora.full_rollout_random(h_seeds[:200_000], args.seed)
+        dt = time.perf_counter() - t0
+        cpu_full = {"value": 200_000 * fs.PLIES / dt, "unit": "env steps/s", "cores": ncpu, "kind": "port",
+                    "sample": "200 000 games x 36 plies, OpenMP over all host threads"}
+    ach = FG * fs.PLIES * 65.0 / (f_ms * 1e-3) / 1e9
+    return {"metric": "env_steps_per_sec", "unit": "env steps/s", "value": FG * fs.PLIES / (f_ms * 1e-3), "ms_per_step": f_ms,
+            "e2e": {"value": FG * fs.PLIES / f_e2e, "unit": "env steps/s", "h2d_bytes_per_step": 8 * FG,
+                    "d2h_bytes_per_step": (fs.PLIES + 8) * FG,
+                    "what": "ms_full_rollout_random_host: FullDeck(seed) + deal + 36 plies per game, pinned host buffers in and out, "
+                            "H2D / kernels / D2H pipelined over three streams"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": cx.hbm_gbs, "unit": "GB/s", "frac": ach / cx.hbm_gbs, "traffic": None,
+                         "kernel": "full_rollout_kernel", "peak_source": cx.peak_src,
+                         "note": "against the step-granular figure for this game, 65 B/step (32 B state load + 1 B action "
+                                 "+ 32 B state store); the fused kernel keeps the state in registers and moves "
+                                 "108 B/game = 3 B/step, so it is integer-issue bound like the Miniscopa rollout"},
+            "cpu_baseline": cpu_full,
+            "config": {"workload": f"{FG} concurrent random-policy games of 40-card Scopa (FullScopaEnv), 36 plies each, "
+                                   "deals resident in HBM", "l2": "256 MiB flush between timed steps"}}
 
-    # ------------------------------------------------------------------ SDCFR traversal (config 4)
+
+def section_sdcfr(cx, sv):
+    """SDCFR traversal (config 4)"""
+    torch, args, K, dev = cx.torch, cx.args, cx.K, cx.dev
+    from scopa_b200 import _lib
     from scopa_b200 import sdcfr as sd
     T = args.sd_trav
     torch.manual_seed(1234)
@@ -611,21 +921,21 @@ def run_ours(args):
     sd_obj = None
     for prec, pname in ((sd.TENSOR_CORE, "bf16_tcgen05"), (sd.FP32, "fp32_cuda_cores")):
         for i in range(2):
-            trv.run(i & 1, blobs, T, philox_seed=args.seed, first_trav=rank * T, precision=prec)
-        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        barrier()
+            trv.run(i & 1, blobs, T, philox_seed=args.seed, first_trav=0, precision=prec)
+        sev = cx.events(K)
+        torch.cuda.synchronize()
         l0 = _lib.launch_count()
         for i in range(K):
-            flush_l2()
+            cx.flush_l2()
             sev[i][0].record()
-            trv.run(0, blobs, T, philox_seed=args.seed, first_trav=(i * world + rank) * T, precision=prec)
-            trv.run(1, blobs, T, philox_seed=args.seed, first_trav=(i * world + rank) * T, precision=prec)
+            trv.run(0, blobs, T, philox_seed=args.seed, first_trav=i * T, precision=prec)
+            trv.run(1, blobs, T, philox_seed=args.seed, first_trav=i * T, precision=prec)
             sev[i][1].record()
-        barrier()
+        torch.cuda.synchronize()
         sd_launches = _lib.launch_count() - l0
-        sd_ms = max_over_ranks(sum(a.elapsed_time(c) for a, c in sev))
-        inf = 187.0 * T * world * K                      # 105 + 82 advantage-net inferences per traversal pair
-        o = {"inferences_per_sec": inf / (sd_ms * 1e-3), "traversals_per_sec": 2.0 * T * world * K / (sd_ms * 1e-3),
+        sd_ms = sum(a.elapsed_time(c) for a, c in sev)
+        inf = 187.0 * T * K                      # 105 + 82 advantage-net inferences per traversal pair
+        o = {"inferences_per_sec": inf / (sd_ms * 1e-3), "traversals_per_sec": 2.0 * T * K / (sd_ms * 1e-3),
              "ms_per_step": sd_ms / K, "gpu_launches": int(sd_launches),
              "algorithmic_tflops": inf * 27136.0 / (sd_ms * 1e-3) / 1e12}
         if sd_obj is None:
@@ -648,93 +958,11 @@ def run_ours(args):
                           "note": "numerator = 27 136 FLOP x inferences of WHOLE traversals (env steps, sampling, backward levels "
                                   "and sample emission included in the time), so this is a floor on the tensor-pipe share; "
                                   "K = 34 / N = 16 layers pad to MMA tiles (profiles/README.md section 3)"}
-    if rank == 0:
-        try:
-            sd_obj["train"] = bench_sd_train(dev, _lib)
-        except Exception as e:      # an auxiliary section must not take the headline line down with it
-            sd_obj["train"] = {"error": repr(e)}
-        try:
-            sd_obj["drop_in_train"] = bench_sd_dropin(dev)
-        except Exception as e:
-            sd_obj["drop_in_train"] = {"error": repr(e)}
-
-    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
-    cpu_mccfr = cpu_env = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu_mccfr, cpu_env = cpu_baselines(args, sample_seconds=8.0)
-
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return None
-
-    mccfr_obj = {
-        "metric": "mccfr_infoset_node_updates_per_sec", "value": mccfr_value, "unit": "infoset-node updates/s",
-        "ms_per_step": ms_total / K, "e2e": mccfr_e2e, "gpu_launches": int(mccfr_launches),
-        "node_visits_per_sec": visits_all / (ms_total * 1e-3), "tree_edges_per_sec_inside_mccfr": steps_all / (ms_total * 1e-3),
-        "roofline": {"bound": "hbm", "achieved": mccfr_roof_ach, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": mccfr_roof_ach / hbm_gbs, "traffic": NCU_DRAM_BYTES_PER_LAUNCH["mccfr_tree_kernel"],
-                     "traffic_source": "ncu --set full, profiles/mccfr_r01h_raw.csv: dram__bytes_read.sum + "
-                                       "dram__bytes_write.sum per launch (table and tree staging only; independent of the batch size)",
-                     "kernel": "mccfr_tree_kernel",
-                     "kernel_ms": ms_kernel, "peak_source": peak_src,
-                     "on_chip": {"issue_slots_active_pct": 76.9, "shared_memory_wavefronts_pct_of_peak": 65.4,
-                                 "alu_pipe_pct": 53.6, "source": "ncu --set full, profiles/mccfr_r01h_raw.csv"},
-                     "note": "HBM-EQUIVALENT figure SURVEY 8(d) prescribes (203.7 algorithmic B/update: what an HBM-resident table "
-                             "would have to move); it exceeds 1 because the 53 KB table and the 9 KB tree of the one deal are "
-                             "shared-memory resident -- this is NOT an HBM result.  The binding resources are on chip: "
-                             "issue slots 77 % busy, shared-memory wavefronts at 65 % of peak (profiles/README.md section 1)"},
-        "cpu_baseline": cpu_mccfr,
-        "config": {"workload": "BASELINE.json configs[2]/[4]: MCCFR (reference estimator), seed-42 deal, "
-                               f"{B} traversals per player per GPU per iteration, fp64 table", "traversals_per_step": 2 * B * world,
-                   "parallelism": f"dp{world}: traversals sharded by id, one exchange of {5 * S} f64 per iteration via " +
-                                  ("ms_mccfr_apply_peers (NVLink peer-memory reads + rank-ordered sum + apply in one kernel)"
-                                   if collective == "p2p" else "NCCL all-reduce")
-                   if world > 1 else "single GPU",
-                   "l2": "256 MiB flush between timed steps (working set is on-chip anyway)", "philox_seed": args.seed},
-    }
-    env_obj = {
-        "metric": "env_steps_per_sec", "value": env_value, "unit": "env steps/s", "ms_per_step": env_ms_total / K,
-        "e2e": env_e2e, "gpu_launches": int(env_launches),
-        "roofline": {"bound": "hbm", "achieved": env_roof_ach, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": env_roof_ach / hbm_gbs, "traffic": NCU_DRAM_BYTES_PER_LAUNCH["rollout_kernel"] * (G / 1e6),
-                     "traffic_source": "ncu --set full, profiles/env_r01c_raw.csv: 20.05 MB read per 1 M games (writes "
-                                       "stayed in L2 under ncu)",
-                     "kernel": "rollout_kernel", "kernel_ms": env_kernel_ms,
-                     "peak_source": peak_src,
-                     "note": "against the step-granular 34 B/step figure (SURVEY 8(d)); the fused kernel itself moves "
-                             "36 B/game (4.5 B/step) and is integer-issue bound, not HBM bound"},
-        "cpu_baseline": cpu_env,
-        "config": {"workload": f"BASELINE.json configs[1]: {G} concurrent random-policy games per GPU, 8 plies each, "
-                               "deals resident in HBM", "l2": "256 MiB flush between timed steps", "games_per_gpu": G},
-    }
-    primary, secondary = (mccfr_obj, env_obj) if args.workload == "mccfr" else (env_obj, mccfr_obj)
-    line = {
-        "metric": primary["metric"], "value": primary["value"], "unit": primary["unit"], "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": primary["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64" if primary is mccfr_obj else "u32", "data": "synthetic",
-        "config": primary["config"], "e2e": primary["e2e"], "gpu_launches": primary["gpu_launches"],
-        "roofline": primary["roofline"], "cpu_baseline": primary["cpu_baseline"], "clocks": clocks,
-        "wall_s_mccfr_region": wall,
-        ("env" if primary is mccfr_obj else "mccfr"): secondary,
-        "sdcfr": sd_obj,
-        "env_step_api": step_obj,
-        "cfr": cfr_obj,
-        "mccfr_external_sampling": es_obj,
-        "atomics": atom_obj,
-        "mccfr_restep": restep_obj,
-        "mccfr_multi_deal": md_obj,
-        "mccfr_multi_deal_blocked": mdb_obj,
-        "full_scopa": full_obj,
-        "collective": collective,
-    }
-    if primary is mccfr_obj:
-        line["node_visits_per_sec"] = mccfr_obj["node_visits_per_sec"]
-    return line
+    sd_obj["train"] = guarded(bench_sd_train, dev, _lib)
+    sd_obj["drop_in_train"] = guarded(bench_sd_dropin, dev)
+    return sd_obj
 
 
-# ------------------------------------------------------------------------------------------- CPU side
 def bench_sd_train(dev, _lib, epochs=10, calls=20, rows=100_000):
     """AdvantageNetwork.train (deep_cfr.py:77-110), `epochs` optimiser steps per call on a full replay buffer:
     the fused kernel (one launch per call) beside the PyTorch step it replaces (about 40 launches and one
@@ -748,9 +976,7 @@ def bench_sd_train(dev, _lib, epochs=10, calls=20, rows=100_000):
     feat = (torch.rand((rows, 34), device=dev) < 0.25).float()
     mask = (torch.rand((rows, 16), device=dev) < 0.2).float()
     target = (torch.rand((rows, 16), device=dev) * 2 - 1) * mask
-    # the cluster form has not run on a GPU yet (written after the round's GPU budget was spent): opt-in here
-    variants = ("fused", "torch") + (("fused-cluster",) if os.environ.get("SCOPA_B200_BENCH_CLUSTER") == "1" else ())
-    for name in variants:
+    def one(name):
         adv = AdvantageNetwork(34, 16, device=dev, optimizer=name)
         adv.buffer.add_batch(feat, target, mask)
         for _ in range(3):
@@ -762,8 +988,8 @@ def bench_sd_train(dev, _lib, epochs=10, calls=20, rows=100_000):
             loss = adv.train(batch_size=128, epochs=epochs)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        out[name] = {"us_per_step": 1e6 * dt / (calls * epochs), "ms_per_call": 1e3 * dt / calls, "last_loss": loss,
-                     "our_launches_per_call": (_lib.launch_count() - l0) / calls}
+        o = {"us_per_step": 1e6 * dt / (calls * epochs), "ms_per_call": 1e3 * dt / calls, "last_loss": loss,
+             "our_launches_per_call": (_lib.launch_count() - l0) / calls}
         if name != "torch":     # the kernel alone (CUDA events around the launches, minibatch rows drawn beforehand)
             idx = adv._sample_rows(128, epochs)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -772,7 +998,11 @@ def bench_sd_train(dev, _lib, epochs=10, calls=20, rows=100_000):
                 adv._fused.step(adv.buffer.feat, adv.buffer.target, adv.buffer.mask, idx)
             e1.record()
             torch.cuda.synchronize()
-            out[name]["kernel_us_per_step"] = 1e3 * e0.elapsed_time(e1) / (calls * epochs)
+            o["kernel_us_per_step"] = 1e3 * e0.elapsed_time(e1) / (calls * epochs)
+        return o
+
+    for name in ("fused", "torch", "fused-cluster"):
+        out[name] = guarded(one, name)
     out["speedup_vs_torch_step"] = out["torch"]["us_per_step"] / out["fused"]["us_per_step"]
     out["note"] = ("sd_train_kernel: one CTA keeps the 13 776 weights, the minibatch and all activations in shared memory "
                    "for every epoch of the call; bit-identical to the host emulation of the same source "
@@ -805,11 +1035,115 @@ def bench_sd_dropin(dev, iterations=20):
         out[name] = {"ms_per_iteration": 1e3 * dt / iterations, "iterations_per_sec": iterations / dt,
                      "last_eval_reward_vs_random": d.training_history["eval_rewards"][-1]}
     out["speedup"] = out["default"]["ms_per_iteration"] / out["fused_optimizer_device_eval"]["ms_per_iteration"]
+    out["note"] = "the reference takes about 130 ms per iteration (traversal pair) on one CPU core (BASELINE.md section 2)"
     return out
 
 
+# =========================================================================================== ours
+def run_ours(args):
+    cx = Cx(args)
+    rank, world = cx.rank, cx.world
+    sampler = ClockSampler(cx.local)
+    mccfr_obj, sv = section_mccfr(cx, sampler)        # starts the sampler
+    env_obj = section_env(cx)
+    clocks = sampler.stop()
+    extras = {}
+    cpu_mccfr = cpu_env = None
+    if world == 1:
+        # single-GPU reporting: no collectives below this line
+        if not args.no_extras:
+            extras["mccfr_in_place"] = guarded(section_inplace, cx)
+            extras["mccfr_schedules"] = guarded(section_schedules, cx)
+            extras["mccfr_tree_walk"] = guarded(section_tree_walk, cx)
+            extras["mccfr_restep"] = guarded(section_restep, cx, sv)
+            extras["mccfr_external_sampling"] = guarded(section_es, cx)
+            extras["env_step_api"] = guarded(section_step_api, cx)
+            extras["cfr"] = guarded(section_cfr, cx)
+            extras["atomics"] = guarded(section_atomics, cx, mccfr_obj["value"])
+            if args.md_deals > 0:
+                extras["mccfr_multi_deal"] = guarded(section_multideal, cx)
+            if args.full_games > 0:
+                extras["full_scopa"] = guarded(section_full, cx)
+            extras["sdcfr"] = guarded(section_sdcfr, cx, sv)
+        if not args.no_cpu:
+            cpu = guarded(cpu_baselines, args, 8.0)
+            if isinstance(cpu, dict) and "error" in cpu:
+                cpu_mccfr = cpu_env = cpu
+            else:
+                cpu_mccfr, cpu_env = cpu
+    if world > 1:
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
+    if rank != 0:
+        return None
+    mccfr_obj["cpu_baseline"], env_obj["cpu_baseline"] = cpu_mccfr, cpu_env
+    primary, secondary = (mccfr_obj, env_obj) if args.workload == "mccfr" else (env_obj, mccfr_obj)
+    line = {
+        "metric": primary["metric"], "value": primary["value"], "unit": primary["unit"], "n_gpus": world, "steps": cx.K,
+        "warmup": cx.W, "ms_per_step": primary["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if primary is mccfr_obj else "u32", "data": "synthetic",
+        "config": primary["config"], "e2e": primary["e2e"], "gpu_launches": primary["gpu_launches"],
+        "roofline": primary["roofline"], "cpu_baseline": primary["cpu_baseline"], "clocks": clocks,
+        ("env" if primary is mccfr_obj else "mccfr"): secondary,
+        "collective": mccfr_obj["config"].get("collective"),
+    }
+    for k in ("node_visits_per_sec", "update_composition", "exchange"):
+        if primary is mccfr_obj and k in mccfr_obj:
+            line[k] = mccfr_obj[k]
+    line.update(extras)
+    return line
+
+
+# ------------------------------------------------------------------------------------------- CPU side
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def have_reference():
+    return os.path.exists(os.path.join(REF_DIR, "src", "algorithms", "mc_cfr.pyc"))
+
+
+class ReferencePool:
+    """`procs` persistent single-threaded Python processes, each with the UNMODIFIED reference imported (oracle/_ref:
+    byte-compiled from /root/reference/src by oracle/make_ref.py, behind the import shims of oracle/stubs).  The
+    reference has no multi-core path, so "all host cores" = one independent run per core.  Interpreter start-up, imports
+    and one warm-up iteration happen before `run` is first timed."""
+
+    def __init__(self, procs):
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "time_reference.py"), "serve"]
+        self.ps = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                    bufsize=1) for _ in range(procs)]
+        for p in self.ps:
+            line = p.stdout.readline()
+            if not line or not json.loads(line).get("ready"):
+                self.close()
+                raise RuntimeError("oracle/time_reference.py did not start (oracle/_ref unusable with this interpreter?)")
+
+    def run(self, what, n):
+        for p in self.ps:
+            p.stdin.write(f"{what} {n}\n")
+            p.stdin.flush()
+        return [json.loads(p.stdout.readline()) for p in self.ps]
+
+    def close(self):
+        for p in self.ps:
+            try:
+                p.stdin.write("quit\n"); p.stdin.flush(); p.stdin.close()
+                p.wait(timeout=5)
+            except Exception:
+                p.kill()
+
+
+def time_reference_python(what, n):
+    pool = ReferencePool(1)
+    try:
+        return pool.run(what, n)
+    finally:
+        pool.close()
+
+
 def cpu_baselines(args, sample_seconds, threads=None):
-    """Times the CPU restatement (oracle/, a C port of the reference's algorithm) on the host cores."""
+    """The CPU leg beside the GPU numbers (rank 0, N = 1): the C restatement (oracle/ms_oracle.c, "port") on all host
+    cores, and -- when oracle/_ref is there -- the unmodified Python reference on one core."""
     from oracle import ms_oracle as ora
     ora.build()
     cores = threads or (os.cpu_count() or 1)
@@ -840,51 +1174,111 @@ def cpu_baselines(args, sample_seconds, threads=None):
     dt = time.perf_counter() - t0
     cpu_env = {"value": 8 * n / dt, "unit": "env steps/s", "cores": cores, "kind": "port",
                "sample": f"{n} games (reset(seed) + 8 random-policy steps each, {dt:.2f} s); oracle/ms_oracle.c"}
+    if have_reference():
+        try:
+            m = time_reference_python("mccfr", 100)[0]
+            c = time_reference_python("cfr", 20)[0]
+            e = time_reference_python("env", 3000)[0]
+            cpu_mccfr["reference_python"] = {
+                "value": m["updates_per_sec"], "unit": "infoset-node updates/s", "cores": 1, "kind": "reference",
+                "sample": f"MCCFRTrainer.iteration() x {m['n']} (mc_cfr.py:88-92), {m['seconds']:.2f} s, one process",
+                "ms_per_iteration": m["ms_per_iteration"], "node_visits_per_sec": m["visits_per_sec"],
+                "vanilla_cfr": {"ms_per_iteration": c["ms_per_iteration"], "sample": f"CFRTrainer.train({c['n']}) (vanilla_cfr.py:105-120)"},
+                "host_cores": os.cpu_count()}
+            cpu_env["reference_python"] = {
+                "value": e["steps_per_sec"], "unit": "env steps/s", "cores": 1, "kind": "reference",
+                "sample": f"MiniScopaEnv.reset(seed=g) + 8 random legal steps x {e['n']} games (mini_scopa_game.py:131-167), "
+                          f"{e['seconds']:.2f} s, one process", "host_cores": os.cpu_count()}
+        except Exception as ex:
+            cpu_mccfr["reference_python"] = {"error": repr(ex)}
+    else:
+        cpu_mccfr["reference_python"] = {"unavailable": "oracle/_ref is absent (run oracle/make_ref.py where /root/reference exists)"}
     return cpu_mccfr, cpu_env
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores, same metric / config.
+    oracle/_ref (the unmodified Python reference, one single-threaded process per core) when present and not
+    --ref-kind port; else the C restatement on all cores."""
     rank, world, local = dist_env()
     if rank != 0:
         return None
     K, W = args.steps, args.warmup
+    cores = os.cpu_count() or 1
+    use_ref = have_reference() and args.ref_kind != "port"
     from oracle import ms_oracle as ora
     ora.build()
-    cores = os.cpu_count() or 1
-    # one "step" = a bounded sample of the same workload: traversal pairs on every core / games on every core
-    per_thread, games = args.ref_trav, args.ref_games
-    seeds = np.arange(1, games + 1, dtype=np.int64)
-    for _ in range(W):
-        ora.mccfr_bench(max(50, per_thread // 10), cores, args.seed)
-    t0 = time.perf_counter()
-    tot_u = tot_v = 0
-    for i in range(K):
-        u, v = ora.mccfr_bench(per_thread, cores, args.seed + i)
-        tot_u += u; tot_v += v
-    dt = time.perf_counter() - t0
-    t1 = time.perf_counter()
-    for i in range(K):
-        ora.rollout_random(seeds, args.seed + i, nthreads=cores)
-    dt_env = time.perf_counter() - t1
-    mccfr = {"metric": "mccfr_infoset_node_updates_per_sec", "value": tot_u / dt, "unit": "infoset-node updates/s",
-             "ms_per_step": dt / K * 1e3, "node_visits_per_sec": tot_v / dt}
-    env = {"metric": "env_steps_per_sec", "value": 8.0 * games * K / dt_env, "unit": "env steps/s",
-           "ms_per_step": dt_env / K * 1e3}
+    if use_ref:
+        # one "step" = every core runs `ref_iters` iterations of the unmodified MCCFRTrainer / `ref_py_games` env games
+        it, games = args.ref_iters, args.ref_py_games
+        pool = ReferencePool(cores)
+        try:
+            for _ in range(min(W, 2)):
+                pool.run("mccfr", max(1, it // 4))
+            tot_u = tot_v = 0.0
+            t0 = time.perf_counter()
+            for i in range(K):
+                for r in pool.run("mccfr", it):
+                    tot_u += r["updates"]; tot_v += r["visits"]
+            dt = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            tot_s = 0.0
+            for i in range(K):
+                for r in pool.run("env", games):
+                    tot_s += r["steps"]
+            dt_env = time.perf_counter() - t1
+        finally:
+            pool.close()
+        kind = "reference"
+        sample_m = (f"MCCFRTrainer.iteration() x {it} in each of {cores} independent single-threaded processes per step "
+                    "(unmodified reference, oracle/_ref; interpreter start-up, imports and warm-up outside the timed region)")
+        sample_e = f"{games} MiniScopaEnv games (reset + 8 random steps) in each of {cores} processes per step"
+        mccfr = {"metric": "mccfr_infoset_node_updates_per_sec", "value": tot_u / dt, "unit": "infoset-node updates/s",
+                 "ms_per_step": dt / K * 1e3, "node_visits_per_sec": tot_v / dt}
+        env = {"metric": "env_steps_per_sec", "value": tot_s / dt_env, "unit": "env steps/s", "ms_per_step": dt_env / K * 1e3}
+    else:
+        per_thread, games = args.ref_trav, args.ref_games
+        seeds = np.arange(1, games + 1, dtype=np.int64)
+        for _ in range(W):
+            ora.mccfr_bench(max(50, per_thread // 10), cores, args.seed)
+        t0 = time.perf_counter()
+        tot_u = tot_v = 0
+        for i in range(K):
+            u, v = ora.mccfr_bench(per_thread, cores, args.seed + i)
+            tot_u += u; tot_v += v
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        for i in range(K):
+            ora.rollout_random(seeds, args.seed + i, nthreads=cores)
+        dt_env = time.perf_counter() - t1
+        kind = "port"
+        sample_m = f"{per_thread} traversal pairs x {cores} workers per step (oracle/ms_oracle.c, C restatement of the reference)"
+        sample_e = f"{games} games per step (oracle/ms_oracle.c)"
+        mccfr = {"metric": "mccfr_infoset_node_updates_per_sec", "value": tot_u / dt, "unit": "infoset-node updates/s",
+                 "ms_per_step": dt / K * 1e3, "node_visits_per_sec": tot_v / dt}
+        env = {"metric": "env_steps_per_sec", "value": 8.0 * games * K / dt_env, "unit": "env steps/s",
+               "ms_per_step": dt_env / K * 1e3}
     primary, secondary = (mccfr, env) if args.workload == "mccfr" else (env, mccfr)
-    sample = (f"{per_thread} traversal pairs x {cores} workers per step" if primary is mccfr
-              else f"{games} games per step")
+    sample = sample_m if primary is mccfr else sample_e
+    port_line = None
+    if use_ref:        # the C port beside it, for scale (it is what cpu_baseline.kind "port" reports in the CUDA arm)
+        u, v = ora.mccfr_bench(200, cores, args.seed)
+        t0 = time.perf_counter()
+        u, v = ora.mccfr_bench(args.ref_trav, cores, args.seed)
+        port_line = {"value": u / (time.perf_counter() - t0), "unit": "infoset-node updates/s", "cores": cores, "kind": "port",
+                     "sample": f"{args.ref_trav} traversal pairs x {cores} workers, oracle/ms_oracle.c"}
     line = {
         "impl": "reference", "metric": primary["metric"], "value": primary["value"], "unit": primary["unit"],
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": primary["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64" if primary is mccfr else "u32", "data": "synthetic",
-        "config": {"workload": "same metric/config as the CUDA arm, CPU restatement of the reference (oracle/ms_oracle.c) "
-                               "on all host cores; each step is a bounded sample: " + sample},
-        "cpu_baseline": {"value": primary["value"], "unit": primary["unit"], "cores": cores, "kind": "port", "sample": sample},
+        "config": headline_config(args, world) if primary is mccfr else env_config(args, world),
+        "cpu_baseline": {"value": primary["value"], "unit": primary["unit"], "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": primary["value"], "unit": primary["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         ("env" if primary is mccfr else "mccfr"): secondary,
-        "note": "the reference itself is single-threaded pure Python (survey-measured 2.8 k updates/s, 106 k env steps/s "
-                "on one core); this C port is about 80x faster per core and uses every core",
+        "c_port_all_cores": port_line,
+        "note": "the reference is single-threaded pure Python with no multi-core path: all host cores = one independent "
+                "process per core (updates summed); each step is a bounded sample of the workload in `config`",
     }
     return line
 
@@ -909,10 +1303,15 @@ def main():
                     help="last point of the exploitability-vs-traversals curves (traversals per player; 0 = skip the curves)")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="multi-GPU delta exchange: peer-memory kernel (p2p), NCCL all-reduce, or p2p with NCCL fallback")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: only the two headline sections (and the CPU leg)")
+    ap.add_argument("--collective", default="both", choices=["both", "p2p", "nccl"],
+                    help="multi-GPU delta exchange of the headline number: NCCL all-reduce + apply (nccl, and both: which also "
+                         "times the peer-memory kernel beside it) or the peer-memory kernel (p2p)")
+    ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--ref-trav", type=int, default=1500)
     ap.add_argument("--ref-games", type=int, default=400_000)
+    ap.add_argument("--ref-iters", type=int, default=8, help="--impl reference (python): MCCFR iterations per process per step")
+    ap.add_argument("--ref-py-games", type=int, default=400, help="--impl reference (python): env games per process per step")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -127,7 +127,7 @@ typedef struct ms_solver ms_solver;
 
 int ms_solver_create(const ms_state* h_root, uint32_t hand_order, ms_solver** out);
 void ms_solver_destroy(ms_solver* s);
-int ms_solver_reset(ms_solver* s, void* stream);                 /* zero regrets / strategy sums */
+int ms_solver_reset(ms_solver* s, void* stream);                 /* zero regrets / strategy sums; MS_ERR_STATE while attached to peers */
 int ms_solver_counts(const ms_solver* s, int32_t* n_nodes, int32_t* n_slots, int32_t* n_levels);
 /* tree export (host buffers sized n_nodes): packed state, parent index (-1 root), level, slot
  * (-1 for terminals), first-child index, child count */
@@ -139,9 +139,11 @@ int ms_solver_export_table(const ms_solver* s, uint64_t* h_keys, uint8_t* h_nleg
                            double* h_regret, double* h_strategy, uint8_t* h_touched, void* stream);
 int ms_solver_import_table(ms_solver* s, const double* h_regret, const double* h_strategy, void* stream);
 /* device pointers to the slot-aligned arrays for collectives: regret / strategy are [n_slots][4] f64
- * (*n_table doubles each); delta is ONE contiguous buffer of *n_delta = 5 * n_slots doubles:
- * [n_slots][4] regret deltas followed by [n_slots] update counts (the strategy delta of a batch is
- * count * sigma because sigma is frozen for the batch) -> one all-reduce per iteration. */
+ * (*n_table doubles each); delta is ONE contiguous buffer of *n_delta = 6 * n_slots doubles:
+ * [n_slots][4] regret deltas, [n_slots] update counts (the strategy delta of a batch is count * sigma
+ * because sigma is frozen for the batch) and [n_slots] first-touch marks (non-zero = some traversal of the
+ * batch created the InfoNode, mc_cfr.py:52; summed like the rest, so every rank's `touched` flags agree)
+ * -> one all-reduce per iteration. */
 int ms_solver_device_ptrs(ms_solver* s, double** d_regret, double** d_strategy, double** d_delta, size_t* n_table,
                           size_t* n_delta);
 
@@ -158,18 +160,28 @@ int ms_cfr_iterate_many(ms_solver* const* solvers, int32_t n_solvers, int32_t it
 /* ms_mccfr_inplace: `iters` reference iterations of MCCFRTrainer.iteration()
  *   (src/algorithms/mc_cfr.py:37-92) with in-place table updates after every node, sampling from the
  *   Philox "MCCF" stream with traversal id first_iter + i (DESIGN.md "Random streams").
+ * ms_mccfr_inplace_many: the reference's experiment protocol (src/experiments/run_mccfr_experiment.py:195-202:
+ *   independent runs of MCCFRTrainer from an empty table) in ONE launch: n_runs tables, one warp per run, run r
+ *   advancing `iters` iterations on the stream of philox seed philox_seed0 + r -- bit-identical to a solo
+ *   ms_mccfr_inplace(s, iters, philox_seed0 + r, first_iter) on a table holding run r's rows.  The caller owns the
+ *   device buffers d_regret / d_strategy [n_runs][n_slots][4] f64 and d_touched [n_runs][n_slots] u8 (zero them for a
+ *   fresh start; call again to continue); the solver's own table is not touched.
  * ms_mccfr_batch: n_trav independent traversals for `player` (0, 1, or 2 = both) against the
  *   current (frozen) table, traversal ids first_trav..; regret / strategy deltas are accumulated
- *   into the delta arrays (not applied).
+ *   into the delta arrays (not applied).  On the tree of a fresh deal (every MiniScopaEnv.reset) this is the
+ *   static-shape kernel on the sequential Philox stream (DESIGN.md sections 5, 7); other roots use mode 4.
  * ms_mccfr_apply: table += delta; delta = 0 (call after the all-reduce of the delta arrays). */
 int ms_mccfr_inplace(ms_solver* s, int64_t iters, uint64_t philox_seed, uint64_t first_iter, void* stream);
+int ms_mccfr_inplace_many(ms_solver* s, int32_t n_runs, int64_t iters, uint64_t philox_seed0, uint64_t first_iter,
+                          double* d_regret, double* d_strategy, uint8_t* d_touched, void* stream);
 int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
                    void* stream);
 int ms_mccfr_apply(ms_solver* s, void* stream);
 /* ms_mccfr_batch_mode: like ms_mccfr_batch with a choice of estimator: mode 0 = the reference's estimator
  *   (mc_cfr.py:37-86), 1 = external sampling, 2 = outcome sampling (epsilon 0.6) -- the textbook estimators the
- *   reference does not implement (update rules as published by Lanctot et al. 2009).  Same table, same delta
- *   buffer, same apply step. */
+ *   reference does not implement (update rules as published by Lanctot et al. 2009); 3 = the reference's estimator
+ *   re-stepping the env at every node; 4 = the reference's estimator on the generic tree-walking kernel (any root;
+ *   call-indexed Philox stream).  Same table, same delta buffer, same apply step. */
 int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_trav, uint64_t philox_seed,
                         uint64_t first_trav, void* stream);
 /* Peer-memory exchange (one process per GPU, NVLink / NVSwitch): instead of a library all-reduce + ms_mccfr_apply,
@@ -179,10 +191,15 @@ int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_tr
  *     buffers and of its flag array; exchange them between ranks (any out-of-band all-gather of 88 bytes per rank);
  *   ms_solver_ipc_attach: `handles` = world x 64 bytes, `offsets` = world x 3 u64, in rank order (at most 8 ranks);
  *   ms_mccfr_apply_peers: replaces {all-reduce, ms_mccfr_apply} after ms_mccfr_batch; deltas are double buffered by
- *     iteration parity, so one cross-GPU barrier per iteration suffices.  Every rank must call it once per iteration. */
+ *     iteration parity, so one cross-GPU barrier per iteration suffices.  Every rank must call it once per iteration.
+ *     The barrier is bounded: a rank that has waited 2 s for a peer sets the solver's error word and leaves its table
+ *     unchanged from then on (no hang);
+ *   ms_solver_peer_error: synchronises the stream and reads that word: *h_err = 0 and MS_OK, or 1 + the rank that
+ *     did not arrive and MS_ERR_STATE. */
 int ms_solver_ipc_export(ms_solver* s, void* handle64, uint64_t offsets[3]);
 int ms_solver_ipc_attach(ms_solver* s, int32_t rank, int32_t world, const void* handles, const uint64_t* offsets);
 int ms_mccfr_apply_peers(ms_solver* s, void* stream);
+int ms_solver_peer_error(ms_solver* s, uint32_t* h_err, void* stream);
 /* counters accumulated by the MCCFR kernels since the last reset: [0] traverser-node updates,
  * [1] node visits (_sample calls), [2] env steps */
 int ms_solver_counters(ms_solver* s, uint64_t h_out[3], int reset, void* stream);

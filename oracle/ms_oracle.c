@@ -141,11 +141,12 @@ static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 
 /* ================================================================================ RNG facade */
 struct ora_rng {
-    int kind;            /* 0 numpy legacy MT19937, 1 Philox */
+    int kind;            /* 0 numpy legacy MT19937, 1 Philox addressed by call index, 2 Philox addressed by draw index */
     mt_t mt;
     uint64_t seed;
     /* Philox addressing, set by the traversal before each draw */
     uint32_t tag; uint64_t trav; uint32_t call;
+    uint32_t draw;       /* kind 2: number of uniforms this traversal has consumed so far */
 };
 
 ora_rng* ora_rng_new(int kind, uint64_t seed) {
@@ -166,9 +167,24 @@ static void rng_philox(const ora_rng* r, uint32_t out2[2]) {
     out2[0] = o[2 * (r->call & 1u)]; out2[1] = o[2 * (r->call & 1u) + 1];
 }
 
+/* kind 2 ("sequential" stream of the headline MCCFR kernel): the d-th uniform a traversal
+ * consumes is word d & 3 of the block with ctr = (traversal id lo, hi, d >> 2, tag), as a 31-bit fraction
+ * u = (word >> 1) / 2^31 (exactly representable, so `cdf <= u` below is the comparison numpy's searchsorted makes on
+ * this u; 31 bits so that ceil(cdf * 2^31), the integer the kernel compares with, fits 32 bits even for cdf = 1). */
+static double rng_seq32(ora_rng* r) {
+    uint32_t ctr[4] = {(uint32_t)r->trav, (uint32_t)(r->trav >> 32), r->draw >> 2, r->tag};
+    uint32_t key[2] = {(uint32_t)r->seed, (uint32_t)(r->seed >> 32)};
+    uint32_t o[4];
+    philox4x32_10(ctr, key, o);
+    double u = (double)(o[r->draw & 3u] >> 1) / 2147483648.0;
+    r->draw++;
+    return u;
+}
+
 /* uniform double in [0,1): numpy random_sample == (a>>5, b>>6) 53-bit; same formula on Philox words */
 static double rng_double(ora_rng* r) {
     uint32_t a, b;
+    if (r->kind == 2) return rng_seq32(r);
     if (r->kind == 0) { a = mt_next(&r->mt) >> 5; b = mt_next(&r->mt) >> 6; }
     else { uint32_t o[2]; rng_philox(r, o); a = o[0] >> 5; b = o[1] >> 6; }
     return (a * 67108864.0 + b) / 9007199254740992.0;
@@ -176,6 +192,7 @@ static double rng_double(ora_rng* r) {
 
 /* np.random.choice(n items, p): cdf = p.cumsum(); cdf /= cdf[-1]; idx = cdf.searchsorted(u, 'right') */
 static int rng_choice_p(ora_rng* r, const double* p, int n) {
+    if (r->kind == 2 && n == 1) return 0;   /* sequential stream: a forced move consumes no uniform */
     double cdf[16];
     double acc = 0.0;
     for (int i = 0; i < n; i++) { acc += p[i]; cdf[i] = acc; }
@@ -604,16 +621,17 @@ void ora_mccfr_populate(ora_table* t, int64_t seed) {
     populate_rec(t, &s);
 }
 
-void ora_mccfr_batch(ora_table* t, int64_t seed, int player, uint64_t philox_seed,
-                     uint64_t first_trav, int64_t ntrav, int64_t* n_updates, int64_t* n_visits) {
+#define TAG_MCCF_SEQ (TAG_MCCF + 64u)
+static void mccfr_batch_impl(ora_table* t, int64_t seed, int player, uint64_t philox_seed, uint64_t first_trav,
+                             int64_t ntrav, int64_t* n_updates, int64_t* n_visits, int rng_kind, uint32_t tag_base) {
     int n0 = t->n;
     double (*dreg)[4] = calloc((size_t)t->cap, sizeof(double[4]));
     double (*dstr)[4] = calloc((size_t)t->cap, sizeof(double[4]));
-    ora_rng* rng = ora_rng_new(1, philox_seed);
+    ora_rng* rng = ora_rng_new(rng_kind, philox_seed);
     mccfr_ctx c = {t, rng, player, dreg, dstr, 0, 0};
     for (int64_t k = 0; k < ntrav; k++) {
         ora_state s; ora_state_init(&s, seed);
-        rng->tag = TAG_MCCF + (uint32_t)player; rng->trav = first_trav + (uint64_t)k; rng->call = 0;
+        rng->tag = tag_base + (uint32_t)player; rng->trav = first_trav + (uint64_t)k; rng->call = 0; rng->draw = 0;
         double one[2] = {1.0, 1.0};
         mccfr_sample(&c, &s, one, one);
     }
@@ -623,6 +641,17 @@ void ora_mccfr_batch(ora_table* t, int64_t seed, int player, uint64_t philox_see
     if (n_updates) *n_updates = c.n_updates;
     if (n_visits) *n_visits = c.n_visits;
     ora_rng_free(rng); free(dreg); free(dstr);
+}
+
+void ora_mccfr_batch(ora_table* t, int64_t seed, int player, uint64_t philox_seed,
+                     uint64_t first_trav, int64_t ntrav, int64_t* n_updates, int64_t* n_visits) {
+    mccfr_batch_impl(t, seed, player, philox_seed, first_trav, ntrav, n_updates, n_visits, 1, TAG_MCCF);
+}
+
+/* the same frozen-sigma batch on the sequential 32-bit stream (what ms_mccfr_batch's static-shape kernel consumes) */
+void ora_mccfr_batch_seq(ora_table* t, int64_t seed, int player, uint64_t philox_seed,
+                         uint64_t first_trav, int64_t ntrav, int64_t* n_updates, int64_t* n_visits) {
+    mccfr_batch_impl(t, seed, player, philox_seed, first_trav, ntrav, n_updates, n_visits, 2, TAG_MCCF_SEQ);
 }
 
 /* ================================================================================ exploitability */

@@ -104,6 +104,7 @@ def lib():
     L.ora_mccfr_iterate.argtypes = [vp, i64, ci, vp, u64]
     L.ora_mccfr_populate.argtypes = [vp, i64]
     L.ora_mccfr_batch.argtypes = [vp, i64, ci, u64, u64, i64, P(i64), P(i64)]
+    L.ora_mccfr_batch_seq.argtypes = [vp, i64, ci, u64, u64, i64, P(i64), P(i64)]
     L.ora_exploitability.argtypes = [vp, ci, i64, P(dbl)]
     L.ora_exploitability.restype = dbl
     L.ora_features.argtypes = [P(OraState), ci, vp, vp]
@@ -302,6 +303,12 @@ class Table:
     def mccfr_batch(self, player, philox_seed, first_trav, ntrav, seed=42):
         nu, nv = C.c_int64(), C.c_int64()
         lib().ora_mccfr_batch(self.t, seed, player, philox_seed, first_trav, ntrav, C.byref(nu), C.byref(nv))
+        return nu.value, nv.value
+
+    def mccfr_batch_seq(self, player, philox_seed, first_trav, ntrav, seed=42):
+        """frozen-sigma batch on the sequential 32-bit Philox stream (the headline kernel's stream)"""
+        nu, nv = C.c_int64(), C.c_int64()
+        lib().ora_mccfr_batch_seq(self.t, seed, player, philox_seed, first_trav, ntrav, C.byref(nu), C.byref(nv))
         return nu.value, nv.value
 
     def mccfr_batch_mode(self, mode, player, philox_seed, first_trav, ntrav, seed=42):

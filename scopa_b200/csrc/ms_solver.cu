@@ -15,6 +15,7 @@
 #include "ms_common.cuh"
 #include "ms_state.cuh"
 #include "ms_tree_walk.cuh"
+#include "ms_static_walk.cuh"
 
 #ifndef MS_DYN_SMEM   // the host emulation of tests/emu/ms_solver_host.cpp supplies its own (one buffer per block)
 #define MS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
@@ -104,7 +105,7 @@ struct SolverDev {
     const unsigned long long* hkeys; const int16_t* hslots; int hcap;
     // table
     double* regret; double* strategy;   // [n_slots][4]
-    double* delta;                      // [n_slots][4] regret deltas, then [n_slots] update counts
+    double* delta;                      // [n_slots][4] regret deltas, then [n_slots] update counts, then [n_slots] first-touch marks
     uint8_t* touched;                   // [n_slots]
     unsigned long long* counters;       // [0] updates [1] visits [2] env steps
 };
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(MCCFR_THREADS, 1) mccfr_batch_kernel(SolverDev
     }
     for (int s = tid; s < S; s += T) {
         if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
-        if (touched[s]) d.touched[s] = 1;
+        if (touched[s] && !d.touched[s]) atomicAdd(&d.delta[5 * S + s], 1.0);   // first touch: travels with the delta
     }
     // counters: warp reduce, one atomic per warp
     for (int off = 16; off > 0; off >>= 1) {
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int
     }
     for (int s = tid; s < S; s += T) {
         if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
-        if (touched[s]) d.touched[s] = 1;
+        if (touched[s] && !d.touched[s]) atomicAdd(&d.delta[5 * S + s], 1.0);   // first touch: travels with the delta
     }
     for (int off = 16; off > 0; off >>= 1) {
         nu += __shfl_down_sync(0xffffffffu, nu, off);
@@ -762,6 +763,161 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int
         ns += __shfl_down_sync(0xffffffffu, ns, off);
     }
     if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3s  the headline kernel: the same estimator on a fresh deal's STATIC recursion shape (ms_static_walk.cuh).
+// One thread = one traversal at a time, recursion state in registers; the CTA's working set (node records with
+// integer cdf thresholds, sigma and 1/sigma, the private delta tables) is rebuilt in shared memory from the table at
+// the start of every launch -- the frozen strategy of the batch.
+struct StaticDims { int n6, n7, S2, s_hot, ncopy; };
+
+__global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
+                                                                         unsigned long long first_trav, StaticDims dm) {
+    MS_DYN_SMEM(smem_raw);
+    const int S = d.n_slots, T = STATIC_THREADS, tid = threadIdx.x, lane = tid & 31;
+    uint4* node = (uint4*)smem_raw;
+    double* sig = (double*)(node + dm.n6);
+    double* rsig = sig + 4 * S;
+    double* hot = rsig + 4 * S;
+    double* dreg = hot + 128 * (size_t)dm.s_hot;
+    uint32_t* endrec = (uint32_t*)(dreg + (size_t)dm.ncopy * 4 * dm.S2);
+    uint32_t* dcnt = endrec + (dm.n7 - dm.n6);
+    uint8_t* touched = (uint8_t*)(dcnt + S);
+    int* s_need = (int*)(((uintptr_t)(touched + S) + 15) & ~(uintptr_t)15);
+    uint32_t* thr = (uint32_t*)dreg;        // [S2][3] staging of the per-slot thresholds (the delta tables are zeroed afterwards)
+
+    if (tid == 0) *s_need = 0;
+    __syncthreads();
+    for (int s = tid; s < S; s += T) {
+        double reg[4], sg[4], cd[4];
+        const int n = d.slot_nlegal[s];
+        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+        regret_match(reg, n, sg);
+        strategy_cdf(sg, n, cd);
+        for (int i = 0; i < 4; i++) {
+            sig[4 * s + i] = sg[i];
+            rsig[4 * s + i] = sg[i] > 0.0 ? __ddiv_rn(1.0, sg[i]) : 0.0;
+        }
+        if (s < dm.S2)      // T_i = ceil(cdf_i * 2^31) (exact scaling; cdf_i in [0, 1]); the last entry of a row is never read
+            for (int i = 0; i < 3; i++) thr[3 * s + i] = (i + 1 < n) ? (uint32_t)ceil(cd[i] * 2147483648.0) : 0x80000000u;
+        dcnt[s] = 0u; touched[s] = 0;
+        if (!d.touched[s]) *s_need = 1;
+    }
+    __syncthreads();
+    for (int v = tid; v < dm.n7; v += T) {
+        const int sl = d.node_slot[v];
+        if (v < dm.n6) node[v] = make_uint4(thr[3 * sl], thr[3 * sl + 1], thr[3 * sl + 2], (uint32_t)d.child_begin[v] | ((uint32_t)sl << 12));
+        else {              // ply 6: its forced child (ply 7), whose forced child is the leaf
+            const int c7 = d.child_begin[v], leaf = d.child_begin[c7];
+            endrec[v - dm.n6] = (uint32_t)sl | ((uint32_t)d.node_slot[c7] << 11) | ((uint32_t)((int)d.rx2[leaf] + 16) << 22);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < dm.ncopy * 4 * dm.S2; i += T) dreg[i] = 0.0;
+    for (int i = tid; i < 128 * dm.s_hot; i += T) hot[i] = 0.0;
+    __syncthreads();
+
+    StaticShared c;
+    c.node = node; c.endrec = endrec - dm.n6; c.sig = sig; c.rsig = rsig;
+    c.hot = hot + lane; c.dreg = dreg + (size_t)(lane & (dm.ncopy - 1)) * 4 * dm.S2;
+    c.dcnt = dcnt; c.touched = touched; c.need_touch = *s_need != 0;
+    c.key = pkey; c.blk = make_uint4(0u, 0u, 0u, 0u);
+    unsigned long long v0, u0, e0, v1, u1, e1;
+    static_shape_counts(0, v0, u0, e0);
+    static_shape_counts(1, v1, u1, e1);
+    unsigned long long nu = 0, nv = 0, ns = 0;
+    const long long gstride = (long long)gridDim.x * T;
+    const int flip = (tid >> 5) & 1;      // odd warps run player 1 first: the halves of the CTA update disjoint infosets
+    for (long long k = blockIdx.x * (long long)T + tid; k < n_trav; k += gstride) {
+        const unsigned long long trav = first_trav + (unsigned long long)k;
+        c.t_lo = (uint32_t)trav; c.t_hi = (uint32_t)(trav >> 32);
+        for (int j = 0; j < 2; j++) {
+            const int tp = j ^ flip;
+            if (player < 2 && tp != player) continue;
+            c.nd = 0u; c.tag = MS_TAG_MCCF_SEQ + (uint32_t)tp;
+            if (tp == 0) { StaticWalk<0, 0>::run(0u, 1.0, c); nu += u0; nv += v0; ns += e0; }
+            else { StaticWalk<0, 1>::run(0u, 1.0, c); nu += u1; nv += v1; ns += e1; }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 4 * dm.S2; i += T) {
+        double v = 0.0;
+        if (i < 4 * dm.s_hot) { for (int l = 0; l < 32; l++) v = __dadd_rn(v, hot[(size_t)i * 32 + l]); }
+        else for (int cpy = 0; cpy < dm.ncopy; cpy++) v = __dadd_rn(v, dreg[(size_t)cpy * 4 * dm.S2 + i]);
+        if (v != 0.0) atomicAdd(&d.delta[i], v);
+    }
+    for (int s = tid; s < S; s += T) {
+        if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
+        if (touched[s] && !d.touched[s]) atomicAdd(&d.delta[5 * S + s], 1.0);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        nu += __shfl_down_sync(0xffffffffu, nu, off);
+        nv += __shfl_down_sync(0xffffffffu, nv, off);
+        ns += __shfl_down_sync(0xffffffffu, ns, off);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3m  many INDEPENDENT reference-semantics runs in one launch (the reference's experiment protocol,
+// run_mccfr_experiment.py:195-202: R runs from an empty table, each its own random stream).  One warp per run: lane 0
+// walks (mccfr_tree_traverse<true>, exactly what mccfr_inplace_tree_kernel does for one run), the warp stages and
+// writes back the run's table.  Shared memory holds the tree once per CTA and one (regret, strategy, touched, frames)
+// set per warp; run r of the launch is bit-identical to a solo ms_mccfr_inplace with philox seed `seed0 + r`.
+struct ManyRuns { double* regret; double* strategy; uint8_t* touched; int n_runs; };   // [n_runs][4S], [n_runs][4S], [n_runs][S]
+
+__host__ __device__ inline size_t inplace_many_warp_bytes(int S, int nframes) {
+    return (64 * (size_t)S + (size_t)nframes * 26 + (size_t)S + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(256, 1) mccfr_inplace_many_kernel(SolverDev d, ManyRuns m, long long iters, unsigned long long seed0,
+                                                                    unsigned long long first_iter, int nframes, int warps) {
+    MS_DYN_SMEM(smem_raw);
+    const int S = d.n_slots, N = d.n_nodes, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t* tree = (uint32_t*)smem_raw;
+    unsigned char* wbase = smem_raw + ((4 * (size_t)N + 15) & ~(size_t)15) + (size_t)wid * inplace_many_warp_bytes(S, nframes);
+    for (int v = tid; v < N; v += blockDim.x) {
+        const int sl = d.node_slot[v];
+        uint32_t rec;
+        if (sl < 0) rec = ((uint32_t)((int)d.rx2[v] + 2048) & 0xFFFu) | (TREE_TERMINAL << 12);
+        else rec = (uint32_t)d.child_begin[v] | ((uint32_t)sl << 12) | ((uint32_t)d.nchild[v] << 23) | ((uint32_t)d.slot_player[sl] << 26);
+        tree[v] = rec;
+    }
+    __syncthreads();
+    const int run = blockIdx.x * warps + wid;
+    const bool active = wid < warps && run < m.n_runs;      // (block-wide barriers below: no early exit)
+    double* reg = (double*)wbase;
+    double* str = reg + 4 * S;
+    TreeFrames f;
+    f.ro = str + 4 * S;
+    f.sp = f.ro + nframes;
+    f.meta = (uint32_t*)(f.sp + nframes);
+    f.cfv = f.meta + nframes;
+    f.cb = (uint16_t*)(f.cfv + nframes);
+    uint8_t* touched = (uint8_t*)(f.cb + nframes);
+    double* greg = m.regret + (size_t)run * 4 * S;
+    double* gstr = m.strategy + (size_t)run * 4 * S;
+    uint8_t* gtch = m.touched + (size_t)run * S;
+    if (active) {
+        for (int i = lane; i < 4 * S; i += 32) { reg[i] = greg[i]; str[i] = gstr[i]; }
+        for (int i = lane; i < S; i += 32) touched[i] = gtch[i];
+    }
+    __syncthreads();
+    if (active && lane == 0) {
+        MccfrShared sh{nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, touched, reg, str};
+        const unsigned long long seed = seed0 + (unsigned long long)run;
+        const uint2 pkey = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        unsigned long long nu = 0, nv = 0, ns = 0;
+        for (long long it = 0; it < iters; it++)
+            for (int tp = 0; tp < 2; tp++)
+                mccfr_tree_traverse<true>(tree, sh, tp, first_iter + (unsigned long long)it, pkey, f, 1, nu, nv, ns);
+        atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns);
+    }
+    __syncthreads();
+    if (!active) return;
+    for (int i = lane; i < 4 * S; i += 32) { greg[i] = reg[i]; gstr[i] = str[i]; }
+    for (int i = lane; i < S; i += 32) gtch[i] = touched[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -901,7 +1057,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1) mccfr_es_kernel(SolverDev d, in
     for (int i = tid; i < 4 * S; i += T) { const double v = dreg[i]; if (v != 0.0) atomicAdd(&d.delta[i], v); }
     for (int s = tid; s < S; s += T) {
         if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
-        if (touched[s]) d.touched[s] = 1;
+        if (touched[s] && !d.touched[s]) atomicAdd(&d.delta[5 * S + s], 1.0);   // first touch: travels with the delta
     }
     for (int off = 16; off > 0; off >>= 1) {
         nu += __shfl_down_sync(0xffffffffu, nu, off);
@@ -1117,7 +1273,7 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_es_tree_kernel(SolverDev d, 
     }
     for (int s = tid; s < S; s += T) {
         if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
-        if (touched[s]) d.touched[s] = 1;
+        if (touched[s] && !d.touched[s]) atomicAdd(&d.delta[5 * S + s], 1.0);   // first touch: travels with the delta
     }
     for (int off = 16; off > 0; off >>= 1) {
         nu += __shfl_down_sync(0xffffffffu, nu, off);
@@ -1157,7 +1313,7 @@ __global__ void __launch_bounds__(256) mccfr_os_kernel(SolverDev d, int player, 
     for (int i = tid; i < 4 * S; i += T) { const double v = dreg[i]; if (v != 0.0) atomicAdd(&d.delta[i], v); }
     for (int s = tid; s < S; s += T) {
         if (dwt[s] != 0.0) atomicAdd(&d.delta[4 * S + s], dwt[s]);
-        if (touched[s]) d.touched[s] = 1;
+        if (touched[s] && !d.touched[s]) atomicAdd(&d.delta[5 * S + s], 1.0);   // first touch: travels with the delta
     }
     for (int off = 16; off > 0; off >>= 1) {
         nu += __shfl_down_sync(0xffffffffu, nu, off);
@@ -1186,6 +1342,9 @@ __global__ void __launch_bounds__(256) mccfr_apply_kernel(SolverDev d) {
             d.delta[4 * s + i] = 0.0;
         }
         d.delta[4 * S + s] = 0.0;
+        // first touch of the infoset by ANY rank's traversals (the mark is summed with the rest of the delta): the
+        // reference creates the InfoNode on first touch (mc_cfr.py:52), and every replica must agree on which exist
+        if (d.delta[5 * S + s] != 0.0) { d.touched[s] = 1; d.delta[5 * S + s] = 0.0; }
     }
 }
 
@@ -1207,25 +1366,56 @@ struct PeerView {
     int rank, world;
 };
 
-#ifndef MS_HOST_RULES_ONLY   // PTX in the body: not part of the host build of tests/emu/ms_solver_host.cpp
-__global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d, PeerView pv, unsigned long long epoch) {
+// The barrier's two memory operations, behind inline functions so that tests/emu can run the kernel with two emulated
+// "ranks" in one process (host build: C++ atomics with the same ordering).
+#ifndef MS_CTA_EMU
+__device__ __forceinline__ void peer_signal(unsigned long long* flag, unsigned long long epoch) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(epoch) : "memory");
+}
+__device__ __forceinline__ unsigned long long peer_poll(const unsigned long long* flag) {
+    unsigned long long seen;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+    return seen;
+}
+__device__ __forceinline__ unsigned long long peer_clock_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ double peer_load(const double* p) { return __ldcv(p); }
+__device__ __forceinline__ void peer_fence() { __threadfence_system(); }
+#endif
+
+constexpr unsigned long long MS_PEER_TIMEOUT_NS = 2000000000ull;     // a peer that has not arrived after 2 s is given up on
+
+// err[0]: 0 = fine; otherwise (1 + the first peer that did not arrive) of the first failed exchange.  Once set, every
+// later exchange returns at once without touching the table (ms_mccfr_apply_peers reports MS_ERR_STATE).
+__global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d, PeerView pv, unsigned long long epoch,
+                                                                    unsigned int* err) {
+    MS_DYN_SMEM(smem_raw);                  // one int: dynamic, so that emulated ranks (blocks) do not share it
+    volatile int& s_bad = *(volatile int*)smem_raw;
     const int tid = threadIdx.x, S = d.n_slots;
+    if (tid == 0) s_bad = (*(volatile unsigned int*)err != 0u) ? 1 : 0;
+    __syncthreads();
+    if (s_bad) return;
     if (tid < pv.world) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(pv.flags[tid] + pv.rank), "l"(epoch) : "memory");
-        unsigned long long seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(pv.my_flags + tid) : "memory");
-        } while (seen < epoch);
+        peer_fence();
+        peer_signal(pv.flags[tid] + pv.rank, epoch);
+        const unsigned long long t0 = peer_clock_ns();
+        while (peer_poll(pv.my_flags + tid) < epoch) {
+            if (peer_clock_ns() - t0 > MS_PEER_TIMEOUT_NS) { atomicCAS(err, 0u, 1u + (unsigned)tid); s_bad = 1; break; }
+        }
     }
     __syncthreads();
+    if (s_bad) return;
     for (int s = tid; s < S; s += blockDim.x) {
-        double dv[4] = {0.0, 0.0, 0.0, 0.0}, cnt = 0.0;
+        double dv[4] = {0.0, 0.0, 0.0, 0.0}, cnt = 0.0, tch = 0.0;
         for (int r = 0; r < pv.world; r++) {
             const double* pd = pv.delta[r];
-            cnt = __dadd_rn(cnt, __ldcv(pd + 4 * S + s));
+            cnt = __dadd_rn(cnt, peer_load(pd + 4 * S + s));
+            tch = __dadd_rn(tch, peer_load(pd + 5 * S + s));
 #pragma unroll
-            for (int i = 0; i < 4; i++) dv[i] = __dadd_rn(dv[i], __ldcv(pd + 4 * s + i));
+            for (int i = 0; i < 4; i++) dv[i] = __dadd_rn(dv[i], peer_load(pd + 4 * s + i));
         }
         double reg[4], sg[4];
         for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
@@ -1236,10 +1426,10 @@ __global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d,
         }
         for (int i = 0; i < 4; i++)
             if (dv[i] != 0.0) d.regret[4 * s + i] = __dadd_rn(reg[i], dv[i]);
+        if (tch != 0.0) d.touched[s] = 1;
     }
-    for (int i = tid; i < 5 * S; i += blockDim.x) pv.zero_me[i] = 0.0;
+    for (int i = tid; i < 6 * S; i += blockDim.x) pv.zero_me[i] = 0.0;
 }
-#endif  // MS_HOST_RULES_ONLY
 
 // ------------------------------------------------------------------------------------------------
 // Best response against the table's average policy (restated open_spiel BestResponsePolicy, see
@@ -1389,6 +1579,8 @@ struct ms_solver {
     ms_state root{};
     uint32_t hand_order = 0;
     int n_nodes = 0, n_levels = 0, n_slots = 0, n_dec = 0, hcap = 0, nframes = 4, nframes_tree = 4, nframes_es = 4;
+    bool static_shape = false;                 // the tree of a fresh 4+4-card deal (ms_static_walk.cuh)
+    StaticDims sdm{};
     std::vector<int> level_begin, slot_level_begin;
     // host copies for export
     std::vector<ms_state> h_state; std::vector<int> h_parent, h_child_begin, h_slot; std::vector<uint8_t> h_nchild, h_level;
@@ -1399,6 +1591,7 @@ struct ms_solver {
     // peer-memory exchange (ms_solver_ipc_export / _attach / ms_mccfr_apply_peers)
     double* delta_buf[2] = {nullptr, nullptr};
     unsigned long long* flags = nullptr;
+    unsigned int* peer_err = nullptr;          // device word set by the peer exchange when a peer did not arrive
     int rank = 0, world = 1, parity = 0;
     unsigned long long epoch = 0;
     bool attached = false;
@@ -1553,11 +1746,28 @@ int solver_build(ms_solver* sv) {
         sv->nframes_es = std::max(1, std::max(need0[0], need1[0]));
     }
 
+    // Does the tree have the shape of a fresh deal?  9 levels; at ply d < 8 every node has 4 - d/2 children and player d & 1
+    // moves; ply 8 is all leaves; the infosets of a ply are a contiguous slot range (they are: breadth-first numbering).
+    {
+        bool ok = (L == STATIC_PLIES + 1) && root_cur == 0 && S < 2048 && N <= 4096;
+        for (int l = 0; ok && l < L; l++)
+            for (int v = sv->level_begin[l]; ok && v < sv->level_begin[l + 1]; v++) {
+                const int want = l < STATIC_PLIES ? 4 - l / 2 : 0;
+                ok = sv->h_nchild[v] == want && (want == 0 || (int)((sv->h_state[v].meta >> 17) & 1u) == (l & 1));
+            }
+        sv->static_shape = ok;
+        if (ok) {
+            sv->sdm.n6 = sv->level_begin[6]; sv->sdm.n7 = sv->level_begin[7];
+            sv->sdm.S2 = sv->slot_level_begin[6]; sv->sdm.s_hot = sv->slot_level_begin[STATIC_HOT_PLIES];
+            sv->sdm.ncopy = 1;
+        }
+    }
+
     // ---- 3. upload
     size_t total = 0;
     auto sz = [&](size_t n) { size_t b = (n + 255) & ~(size_t)255; total += b; return b; };
     sz(4 * (L + 1)); sz(2 * N); sz(N); sz(2 * N); sz(N); sz(2 * (S + 1)); sz(2 * sv->n_dec); sz(4 * (L + 1)); sz(S); sz(S);
-    sz(8 * hcap); sz(2 * hcap); sz(32 * S); sz(32 * S); sz(8 * (5 * S)); sz(8 * (5 * S)); sz(8 * MS_MAX_PEERS); sz(S); sz(8 * 4); sz(16);
+    sz(8 * hcap); sz(2 * hcap); sz(32 * S); sz(32 * S); sz(8 * (6 * S)); sz(8 * (6 * S)); sz(8 * MS_MAX_PEERS); sz(16); sz(S); sz(8 * 4); sz(16);
     MS_CUDA(cudaMalloc(&sv->d_block, total + 4096));
     MS_CUDA(cudaMemset(sv->d_block, 0, total + 4096));
     p = sv->d_block;
@@ -1583,10 +1793,11 @@ int solver_build(ms_solver* sv) {
 #undef UP
     d.regret = carve<double>(p, 4 * (size_t)S);
     d.strategy = carve<double>(p, 4 * (size_t)S);
-    d.delta = carve<double>(p, 5 * (size_t)S);
+    d.delta = carve<double>(p, 6 * (size_t)S);
     sv->delta_buf[0] = d.delta;
-    sv->delta_buf[1] = carve<double>(p, 5 * (size_t)S);
+    sv->delta_buf[1] = carve<double>(p, 6 * (size_t)S);
     sv->flags = carve<unsigned long long>(p, MS_MAX_PEERS);
+    sv->peer_err = carve<unsigned int>(p, 4);
     d.touched = carve<uint8_t>(p, (size_t)S);
     d.counters = carve<unsigned long long>(p, 4);
     sv->d_value = carve<double>(p, 2);
@@ -1628,12 +1839,14 @@ void ms_solver_destroy(ms_solver* s) {
 
 int ms_solver_reset(ms_solver* s, void* stream) {
     int rc = check_dev(s); if (rc) return rc;
+    // attached peers read this solver's delta buffers at their own pace: clearing them here would race with those reads
+    if (s->attached) return fail(MS_ERR_STATE, "ms_solver_reset: the solver is attached to peers (create a new solver instead)");
     const size_t S = s->n_slots;
     cudaStream_t st = (cudaStream_t)stream;
     MS_CUDA(cudaMemsetAsync(s->dev.regret, 0, 32 * S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.strategy, 0, 32 * S, st));
-    MS_CUDA(cudaMemsetAsync(s->delta_buf[0], 0, 40 * S, st));
-    MS_CUDA(cudaMemsetAsync(s->delta_buf[1], 0, 40 * S, st));
+    MS_CUDA(cudaMemsetAsync(s->delta_buf[0], 0, 48 * S, st));
+    MS_CUDA(cudaMemsetAsync(s->delta_buf[1], 0, 48 * S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.touched, 0, S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.counters, 0, 32, st));
     return MS_OK;
@@ -1692,7 +1905,7 @@ int ms_solver_device_ptrs(ms_solver* s, double** d_regret, double** d_strategy, 
     if (d_strategy) *d_strategy = s->dev.strategy;
     if (d_delta) *d_delta = s->dev.delta;
     if (n_table) *n_table = 4 * (size_t)s->n_slots;
-    if (n_delta) *n_delta = 5 * (size_t)s->n_slots;
+    if (n_delta) *n_delta = 6 * (size_t)s->n_slots;
     return MS_OK;
 }
 
@@ -1806,10 +2019,24 @@ static int launch_mccfr_tree(ms_solver* s, int threads, int ncopy, int32_t playe
     return MS_OK;
 }
 
-int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
-    int rc = check_dev(s); if (rc) return rc;
-    if (player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch: bad argument");
-    if (n_trav == 0) return MS_OK;
+static int launch_mccfr_static(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
+    StaticDims dm = s->sdm;
+    for (int ncopy : {8, 4, 2, 1}) {
+        dm.ncopy = ncopy;
+        const size_t smem = mccfr_static_smem(s->n_slots, dm.S2, dm.s_hot, dm.n6, dm.n7, ncopy) + 16;
+        if (smem > 227 * 1024) continue;
+        MS_CUDA(cudaFuncSetAttribute(mccfr_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mccfr_static_kernel<<<grid_for(n_trav, STATIC_THREADS, 1), STATIC_THREADS, smem, (cudaStream_t)stream>>>(
+            s->dev, player, (long long)n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
+            (unsigned long long)first_trav, dm);
+        MS_LAUNCH_CHECK();
+        return MS_OK;
+    }
+    return fail(MS_ERR_CAPACITY, "MCCFR static-shape working set exceeds shared memory");
+}
+
+// the generic tree-walking kernel (any root whose tree fits): mode 4, and mode 0 on trees without the fresh-deal shape
+static int launch_mccfr_generic(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
     if (s->n_slots >= (int)TREE_TERMINAL || s->n_nodes > 4096) return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
     for (int threads : {TREE_THREADS, 512})
         for (int ncopy : {4, 2, 1})
@@ -1818,13 +2045,22 @@ int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox
     return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
 }
 
+int ms_mccfr_batch(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch: bad argument");
+    if (n_trav == 0) return MS_OK;
+    if (s->static_shape) return launch_mccfr_static(s, player, n_trav, philox_seed, first_trav, stream);
+    return launch_mccfr_generic(s, player, n_trav, philox_seed, first_trav, stream);
+}
+
 int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_trav, uint64_t philox_seed,
                         uint64_t first_trav, void* stream) {
     if (mode == 0) return ms_mccfr_batch(s, player, n_trav, philox_seed, first_trav, stream);
     int rc = check_dev(s); if (rc) return rc;
-    if (mode < 0 || mode > 3 || player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch_mode: bad argument");
+    if (mode < 0 || mode > 4 || player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch_mode: bad argument");
     if (n_trav == 0) return MS_OK;
     if (mode == 3) return launch_mccfr_restep(s, player, n_trav, philox_seed, first_trav, stream);
+    if (mode == 4) return launch_mccfr_generic(s, player, n_trav, philox_seed, first_trav, stream);
     const uint2 key = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
     if (mode == 1 && s->n_slots < (int)TREE_TERMINAL && s->n_nodes <= 4096) {
         for (int ncopy : {4, 2, 1}) {
@@ -1903,10 +2139,41 @@ int ms_mccfr_apply_peers(ms_solver* s, void* stream) {
     pv.zero_me = s->delta_buf[s->parity ^ 1];
     pv.rank = s->rank; pv.world = s->world;
     s->epoch += 1;
-    mccfr_apply_peers_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(s->dev, pv, s->epoch);
+    mccfr_apply_peers_kernel<<<1, 1024, 16, (cudaStream_t)stream>>>(s->dev, pv, s->epoch, s->peer_err);
     MS_LAUNCH_CHECK();
     s->parity ^= 1;                       // the next batch accumulates into the other buffer
     s->dev.delta = s->delta_buf[s->parity];
+    return MS_OK;
+}
+
+int ms_solver_peer_error(ms_solver* s, uint32_t* h_err, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (!h_err) return fail(MS_ERR_ARG, "ms_solver_peer_error: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MS_CUDA(cudaMemcpyAsync(h_err, s->peer_err, 4, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    if (*h_err) return fail(MS_ERR_STATE, "peer exchange: rank %u did not arrive within %llu ms; the table was left unchanged from "
+                            "that iteration on", *h_err - 1u, (unsigned long long)(MS_PEER_TIMEOUT_NS / 1000000ull));
+    return MS_OK;
+}
+
+int ms_mccfr_inplace_many(ms_solver* s, int32_t n_runs, int64_t iters, uint64_t philox_seed0, uint64_t first_iter,
+                          double* d_regret, double* d_strategy, uint8_t* d_touched, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (n_runs < 0 || iters < 0 || !d_regret || !d_strategy || !d_touched) return fail(MS_ERR_ARG, "ms_mccfr_inplace_many: bad argument");
+    if (n_runs == 0 || iters == 0) return MS_OK;
+    if (s->n_slots >= (int)TREE_TERMINAL || s->n_nodes > 4096) return fail(MS_ERR_CAPACITY, "ms_mccfr_inplace_many: tree too large");
+    const size_t tree_b = (4 * (size_t)s->n_nodes + 15) & ~(size_t)15, per_warp = inplace_many_warp_bytes(s->n_slots, s->nframes_tree);
+    int warps = (int)((227 * 1024 - tree_b) / per_warp);
+    if (warps > 8) warps = 8;
+    if (warps < 1) return fail(MS_ERR_CAPACITY, "ms_mccfr_inplace_many: one run's table exceeds shared memory");
+    if (warps > n_runs) warps = n_runs;
+    const size_t smem = tree_b + (size_t)warps * per_warp;
+    ManyRuns m{d_regret, d_strategy, d_touched, n_runs};
+    MS_CUDA(cudaFuncSetAttribute(mccfr_inplace_many_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mccfr_inplace_many_kernel<<<(n_runs + warps - 1) / warps, 256, smem, (cudaStream_t)stream>>>(
+        s->dev, m, (long long)iters, (unsigned long long)philox_seed0, (unsigned long long)first_iter, s->nframes_tree, warps);
+    MS_LAUNCH_CHECK();
     return MS_OK;
 }
 

@@ -1,0 +1,158 @@
+// scopa_b200/csrc/ms_static_walk.cuh -- the headline MCCFR kernel: the reference's sampled-CFR estimator (mc_cfr.py:37-86)
+// with frozen-sigma batch semantics, specialised for the shape EVERY fresh Miniscopa deal has.
+//
+// A fresh 4+4-card deal is 8 plies, player 0 first, players alternating, and the mover at ply d always holds
+// 4 - d/2 cards: the number of legal actions, the player to move and the depth of the end are functions of the ply
+// alone (solver_build checks this on the enumerated tree: `static_shape`).  The recursion of the reference's estimator
+// -- at a traverser node: the sampled action, then every action, each with a fresh sampled continuation; at an opponent
+// node: one sampled action -- therefore has a data-INDEPENDENT shape: 411 (player 0) / 292 (player 1) node visits per
+// traversal, always in the same order.  Only WHICH node sits at each position depends on the random draws.
+//
+// mccfr_tree_kernel (the generic form, any root) runs that recursion as an explicit DFS with 26-byte frames in shared
+// memory and a run-time state machine: 52 k thread-instructions per traversal pair, 77 % of the issue slots
+// (profiles/README.md section 1).  Here the recursion is written out as nested loops, one template instantiation per
+// ply:
+//   * the DFS frames are registers (per traverser level: the path weight, the node record, the packed child values);
+//   * reach_opp / sample_own is ONE running product w (opponent sigma and traverser 1/sigma factors from two shared
+//     tables), so an update needs no division;
+//   * an opponent visit is one 16-byte node record (first child | slot, and the strategy's cdf as three 31-bit integer
+//     thresholds), an integer compare per action, and one fp64 multiply;
+//   * the last two plies are forced: a ply-6 node's record carries both infoset slots and the leaf's reward;
+//   * random numbers: Philox4x32-10 keyed by (traversal id, draw index / 4), four 31-bit uniforms per block, consumed
+//     in visiting order ("sequential stream"; oracle: ora_mccfr_batch_seq);
+//   * regret deltas go to shared-memory tables private to the CTA: lane-private rows for the infosets of the first
+//     HOT_LEVELS plies (every lane of a warp sits on those at the same instant: a shared fp64 atomicAdd is a
+//     compare-and-swap loop and the lanes would retry against each other), NC lane-interleaved copies for the rest;
+//   * visit counters are arithmetic (the shape is static), not per-visit increments.
+// Semantics are those of mccfr_tree_kernel<false> (same estimator, same frozen-sigma batch, same delta layout); the
+// random stream differs, so the two agree statistically, and each agrees with its own oracle function to 1e-9.
+#pragma once
+#include <cstdint>
+
+#include "ms_state.cuh"
+#include "ms_tree_walk.cuh"
+
+namespace ms {
+
+constexpr uint32_t MS_TAG_MCCF_SEQ = MS_TAG_MCCF + 64u;
+constexpr int STATIC_THREADS = 1024;
+constexpr int STATIC_PLIES = 8;          // plies of a fresh deal
+constexpr int STATIC_DECIDED = 6;        // plies with more than one legal action
+
+constexpr int STATIC_HOT_PLIES = 3;      // infosets of plies 0..2 (at most 1 + 4 + 16) get lane-private delta rows
+
+// visits / updates / tree edges of ONE traversal by traverser `tp`, counted as the generic kernels count them (and as the
+// reference's recursion visits them): a traverser node with nl actions makes nl + 1 recursive calls; the forced last
+// plies are visited by both calls of the forced traverser node but their edges are played once.
+__host__ __device__ inline void static_shape_counts(int tp, unsigned long long& visits, unsigned long long& updates,
+                                                    unsigned long long& edges) {
+    unsigned long long V = 1, U = 0, E = 0;           // a terminal node
+    for (int ply = STATIC_PLIES - 1; ply >= 0; ply--) {
+        const unsigned long long nl = 4 - ply / 2;
+        if ((ply & 1) == tp) { V = 1 + (nl + 1) * V; U = 1 + (nl + 1) * U; E = (nl == 1 ? 1 : nl + 1) * (1 + E); }
+        else { V = 1 + V; E = 1 + E; }
+    }
+    visits = V; updates = U; edges = E;
+}
+
+struct StaticShared {
+    const uint4* node;        // [n6] plies 0..5: {thr0, thr1, thr2, first child | slot << 12}, thr_i = ceil(cdf_i * 2^31)
+    const uint32_t* endrec;   // ply-6 nodes, indexed by NODE id (pointer pre-offset): slot6 | slot7 << 11 | (2 * reward0 + 16) << 22
+    const double* sig;        // [S][4] frozen strategies
+    const double* rsig;       // [S][4] 1 / sigma (0 where sigma == 0: the reference's weight is 0 when the sampling prob is 0)
+    double* hot;              // [s_hot][4][32] regret deltas of the infosets of plies < STATIC_HOT_PLIES, pre-offset by lane
+    double* dreg;             // [S2][4] regret deltas of the other infosets with more than one action: this lane's copy
+    uint32_t* dcnt;           // [S] update counts (strategy delta = count * sigma)
+    uint8_t* touched;         // [S]
+    bool need_touch;
+    // per-thread random stream
+    uint4 blk; uint32_t nd; uint32_t t_lo, t_hi, tag; uint2 key;
+};
+
+// One copy of the ten Philox rounds for the twelve draw sites of the two walks (they are nested loops, not unrolled:
+// inlining it twelve times makes the kernel 48 KB of SASS against a 32 KB instruction cache).
+__device__ __noinline__ uint4 static_philox(uint32_t t_lo, uint32_t t_hi, uint32_t blk, uint32_t tag, uint2 key) {
+    return philox4x32_10(make_uint4(t_lo, t_hi, blk, tag), key);
+}
+
+__device__ __forceinline__ uint32_t static_draw(StaticShared& c) {
+    if ((c.nd & 3u) == 0u) c.blk = static_philox(c.t_lo, c.t_hi, c.nd >> 2, c.tag, c.key);
+    const uint32_t k = c.nd & 3u;
+    c.nd++;
+    const uint32_t w = (k & 2u) ? ((k & 1u) ? c.blk.w : c.blk.z) : ((k & 1u) ? c.blk.y : c.blk.x);
+    return w >> 1;                                   // 31-bit uniform: u = (w >> 1) / 2^31
+}
+
+// searchsorted(cdf, u, 'right') on the integer thresholds T_i = ceil(cdf_i * 2^31): cdf_i <= u/2^31  <=>  T_i <= u
+template <int NL>
+__device__ __forceinline__ int static_pick(const uint4& rec, uint32_t u) {
+    int ai = (rec.x <= u) ? 1 : 0;
+    if (NL > 2) ai += (rec.y <= u) ? 1 : 0;
+    if (NL > 3) ai += (rec.z <= u) ? 1 : 0;
+    return ai;
+}
+
+template <int PLY, int TP>
+struct StaticWalk {
+    static constexpr int NL = 4 - PLY / 2;
+    static constexpr bool MINE = (PLY & 1) == TP;
+
+    // -> 2 * (reward of the traverser) of the sampled line below `node`
+    static __device__ __forceinline__ int run(uint32_t node, double w, StaticShared& c) {
+        const uint4 rec = c.node[node];
+        const uint32_t slot = rec.w >> 12, cb = rec.w & 0xFFFu;
+        if (c.need_touch) c.touched[slot] = 1;       // node created on first touch, for both players (mc_cfr.py:52)
+        const int ai = static_pick<NL>(rec, static_draw(c));
+        if (!MINE) {                                 // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
+            return StaticWalk<PLY + 1, TP>::run(cb + (uint32_t)ai, __dmul_rn(w, c.sig[4 * slot + ai]), c);
+        }
+        // traverser: the sampled action first (:58-67), then every action with a fresh sampled continuation (:71-78)
+        uint32_t cfvb = 0u;
+        int util = 0;
+#pragma unroll 1
+        for (int j = -1; j < NL; j++) {
+            const int a = j < 0 ? ai : j;
+            const int r = StaticWalk<PLY + 1, TP>::run(cb + (uint32_t)a, __dmul_rn(w, c.rsig[4 * slot + a]), c);
+            if (j < 0) util = r;
+            else cfvb |= ((uint32_t)r & 0xFFu) << (8 * j);
+        }
+        // regret / strategy deltas (:79-84): weight = reach_opp / sample_own = w; strategy delta = count * sigma
+        double cfv[NL], v = 0.0;
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            cfv[i] = 0.5 * (double)(int)(int8_t)((cfvb >> (8 * i)) & 0xFFu);
+            v = __dadd_rn(v, __dmul_rn(c.sig[4 * slot + i], cfv[i]));
+        }
+        constexpr bool HOT = PLY < STATIC_HOT_PLIES;
+        double* row = HOT ? c.hot + 128 * slot : c.dreg + 4 * slot;
+        constexpr int stride = HOT ? 32 : 1;
+#pragma unroll
+        for (int i = 0; i < NL; i++) atomicAdd(row + i * stride, __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+        atomicAdd(&c.dcnt[slot], 1u);
+        return util;
+    }
+};
+
+// plies 6 and 7: one card each, both moves forced, then the end.  The reference's traverser node samples its only
+// action and then evaluates it again: both calls walk this same line, so it is played once (and counted twice by the
+// arithmetic visit counters).  Regret delta = w * (cfv - v) = 0 exactly; strategy delta = 1 * [1.0].
+template <int TP>
+struct StaticWalk<6, TP> {
+    static __device__ __forceinline__ int run(uint32_t node, double, StaticShared& c) {
+        const uint32_t e = c.endrec[node];
+        const uint32_t slot6 = e & 0x7FFu, slot7 = (e >> 11) & 0x7FFu;
+        if (c.need_touch) { c.touched[slot6] = 1; c.touched[slot7] = 1; }
+        atomicAdd(&c.dcnt[TP == 0 ? slot6 : slot7], 1u);
+        const int r = (int)((e >> 22) & 0x3Fu) - 16;
+        return TP == 0 ? r : -r;
+    }
+};
+
+// n6 / n7: first node id of ply 6 / ply 7 (nodes are numbered ply by ply); S2: infosets of plies 0..5 (the slots are
+// numbered ply by ply too, so these are slots [0, S2)); s_hot: infosets of plies < STATIC_HOT_PLIES
+__host__ __device__ inline size_t mccfr_static_smem(int S, int S2, int s_hot, int n6, int n7, int ncopy) {
+    return 16 * (size_t)n6 + sizeof(double) * 8 * (size_t)S + sizeof(double) * 128 * (size_t)s_hot +
+           sizeof(double) * 4 * (size_t)S2 * ncopy + 4 * (size_t)(n7 - n6) + 4 * (size_t)S + (size_t)S + 64;
+}
+
+}  // namespace ms

@@ -129,7 +129,7 @@ class Solver:
                                                        None if s is None else s.ctypes.data, self._stream()))
 
     def delta_tensor(self):
-        """torch float64 view [5*S] of the device delta buffer (regret deltas then update counts):
+        """torch float64 view [6*S] of the device delta buffer (regret deltas, update counts, first-touch marks):
         the thing a multi-GPU run all-reduces once per iteration."""
         if self._delta_t is None:
             pr, ps, pd = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -162,8 +162,9 @@ class Solver:
             _lib.check(self.lib.ms_mccfr_inplace(self.h, int(iters), int(philox_seed), int(first_iter), self._stream()))
 
     def mccfr_batch(self, player, n_trav, philox_seed=0, first_trav=0, mode=0):
-        """mode 0 = the reference's estimator (walks the deal's enumerated tree), 1 = external sampling, 2 = outcome
-        sampling (textbook, opt-in), 3 = the reference's estimator re-stepping the env at every node (same tables as 0)."""
+        """mode 0 = the reference's estimator (static-shape kernel on a fresh deal's tree), 1 = external sampling,
+        2 = outcome sampling (textbook, opt-in), 3 = the reference's estimator re-stepping the env at every node,
+        4 = the reference's estimator on the generic tree-walking kernel (3 and 4 produce the same tables)."""
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_mccfr_batch_mode(self.h, int(mode), int(player), int(n_trav), int(philox_seed),
                                                     int(first_trav), self._stream()))
@@ -197,6 +198,13 @@ class Solver:
         """barrier + sum of all ranks' deltas (rank order) + table update, one kernel per rank."""
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_mccfr_apply_peers(self.h, self._stream()))
+
+    def peer_error(self):
+        """0, or 1 + the rank that did not arrive at a peer exchange within its time limit (synchronises)."""
+        err = C.c_uint32(0)
+        with torch.cuda.device(self.device):
+            self.lib.ms_solver_peer_error(self.h, C.byref(err), self._stream())
+        return int(err.value)
 
     def counters(self, reset=False):
         out = (C.c_uint64 * 3)()
@@ -257,6 +265,30 @@ def cfr_iterate_many(solvers, iters):
         _lib.check(solvers[0].lib.ms_cfr_iterate_many(arr, len(solvers), int(iters), solvers[0]._stream()))
 
 
+class ManyRuns:
+    """Tables of n independent reference-semantics MCCFR runs on one deal (device tensors [n, S, 4] / [n, S])."""
+
+    def __init__(self, solver, n_runs):
+        self.solver, self.n = solver, int(n_runs)
+        S = solver.n_slots
+        self.regret = torch.zeros((self.n, S, 4), dtype=torch.float64, device=solver.device)
+        self.strategy = torch.zeros((self.n, S, 4), dtype=torch.float64, device=solver.device)
+        self.touched = torch.zeros((self.n, S), dtype=torch.uint8, device=solver.device)
+        self.iterations = 0
+
+
+def mccfr_inplace_many(solver, runs, iters, philox_seed0=0):
+    """MCCFRTrainer.iteration() x iters for every one of `runs` independent runs (an int = that many fresh tables, or a
+    ManyRuns to continue), one launch, one warp per run; run r uses philox seed philox_seed0 + r.  -> ManyRuns"""
+    m = runs if isinstance(runs, ManyRuns) else ManyRuns(solver, runs)
+    with torch.cuda.device(solver.device):
+        _lib.check(solver.lib.ms_mccfr_inplace_many(solver.h, m.n, int(iters), int(philox_seed0), m.iterations,
+                                                    m.regret.data_ptr(), m.strategy.data_ptr(), m.touched.data_ptr(),
+                                                    solver._stream()))
+    m.iterations += int(iters)
+    return m
+
+
 def smoke_check(ora):
     """Used by __graft_entry__.smoke(): a few CFR iterations and an MCCFR batch against the oracle."""
     sv = Solver(seed=42, device="cuda:0")
@@ -275,7 +307,7 @@ def smoke_check(ora):
     reg, strat, _ = sv.export()
     t = ora.Table()
     t.mccfr_populate()
-    t.mccfr_batch(0, 5, 0, 256)
+    t.mccfr_batch_seq(0, 5, 0, 256)      # the static-shape kernel consumes the sequential Philox stream
     keys, oreg, ostrat, _, _ = t.arrays()
     perm = np.array([idx[k.split("|", 1)[1]] for k in keys])
     assert np.allclose(reg[perm], oreg, rtol=1e-9, atol=1e-9), "MCCFR regret deltas differ from the oracle"

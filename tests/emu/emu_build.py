@@ -103,7 +103,7 @@ def build_solver_host():
     src = os.path.join(HERE, "ms_solver_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
     deps = [src, HOST_H, os.path.join(HERE, "cta_emu.h"), os.path.join(HERE, "cta_emu_warp.h")] + [os.path.join(csrc, f) for f in ("ms_solver.cu", "ms_tree_walk.cuh",
-                                                                                     "ms_state.cuh", "ms_common.cuh")]
+                                                                                     "ms_static_walk.cuh", "ms_state.cuh", "ms_common.cuh")]
     if _newer(SOLVER_LIB, deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
                         f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", SOLVER_LIB, src], check=True)

@@ -19,6 +19,21 @@
 static inline void __syncwarp() { __syncthreads(); }   // only used by the one-warp kernels (<<<1, 32>>>): the warp is the block
 #include "cta_emu_warp.h"
 
+// the peer exchange's two memory operations + clock + load (device: PTX in ms_solver.cu), for two emulated ranks in one process
+#include <atomic>
+#include <chrono>
+static inline void peer_signal(unsigned long long* flag, unsigned long long epoch) { __atomic_store_n(flag, epoch, __ATOMIC_RELEASE); }
+static inline unsigned long long peer_poll(const unsigned long long* flag) { return __atomic_load_n(flag, __ATOMIC_ACQUIRE); }
+static inline unsigned long long peer_clock_ns() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static inline double peer_load(const double* p) { return *(const volatile double*)p; }
+static inline void peer_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned val) {
+    __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+    return cmp;
+}
+
 #define MS_HOST_RULES_ONLY
 #include "../../scopa_b200/csrc/ms_solver.cu"
 
@@ -38,6 +53,12 @@ struct InplaceArgs { SolverDev d; long long iters; uint2 key; unsigned long long
 void inplace_entry(InplaceArgs a) { mccfr_inplace_kernel(a.d, a.iters, a.key, a.first_iter, a.nframes); }
 void inplace_tree_entry(InplaceArgs a) { mccfr_inplace_tree_kernel(a.d, a.iters, a.key, a.first_iter, a.nframes); }
 struct BatchArgs { SolverDev d; int player; long long n_trav; uint2 key; unsigned long long first_trav; int nframes, ncopy; };
+struct StaticArgs { SolverDev d; int player; long long n_trav; uint2 key; unsigned long long first_trav; StaticDims dm; };
+void static_entry(StaticArgs a) { mccfr_static_kernel(a.d, a.player, a.n_trav, a.key, a.first_trav, a.dm); }
+struct ManyRunArgs { SolverDev d; ManyRuns m; long long iters; unsigned long long seed0, first_iter; int nframes, warps; };
+void inplace_many_entry(ManyRunArgs a) { mccfr_inplace_many_kernel(a.d, a.m, a.iters, a.seed0, a.first_iter, a.nframes, a.warps); }
+struct PeersArgs { SolverDev d[2]; PeerView pv[2]; unsigned long long epoch; unsigned int* err[2]; };
+void peers_entry(PeersArgs a) { const unsigned r = emu_block_slot; mccfr_apply_peers_kernel(a.d[r], a.pv[r], a.epoch, a.err[r]); }
 void tree_entry(BatchArgs a) { mccfr_tree_kernel<TREE_THREADS>(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes, a.ncopy); }
 void restep_entry(BatchArgs a) { mccfr_batch_kernel(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes); }
 void es_tree_entry(BatchArgs a) { mccfr_es_tree_kernel<TREE_THREADS>(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes, a.ncopy); }
@@ -124,7 +145,7 @@ int host_solver_build(const uint32_t* root4, uint32_t hand_order, int* n_nodes, 
     H.n_dec = (int)H.chain_nodes.size();
     H.child_begin.resize(N);
     for (int v = 0; v < N; v++) H.child_begin[v] = (uint16_t)H.child_begin32[v];
-    H.regret.assign(4 * (size_t)S, 0.0); H.strategy.assign(4 * (size_t)S, 0.0); H.delta.assign(5 * (size_t)S, 0.0);
+    H.regret.assign(4 * (size_t)S, 0.0); H.strategy.assign(4 * (size_t)S, 0.0); H.delta.assign(6 * (size_t)S, 0.0);
     H.touched.assign(S, 0); H.counters.assign(4, 0);
     SolverDev& d = H.dev;
     d.n_nodes = N; d.n_levels = L; d.n_slots = S; d.root_cur = (int)((root4[3] >> 17) & 1u);
@@ -226,19 +247,43 @@ int host_mccfr_inplace_tree(long long iters, unsigned long long philox_seed, uns
     return emu_launch_cta(inplace_tree_entry, a, 32);
 }
 
-// ms_mccfr_batch_mode: 0 = mccfr_tree_kernel (the headline kernel), 3 = mccfr_batch_kernel (re-stepping), 1 = external
-// sampling on the tree, 2 = outcome sampling; grids as grid_for(n_trav, threads, 1), blocks one after another
+// does the enumerated tree have the shape of a fresh deal (solver_build's static_shape test, restated)?
+static bool host_static_dims(StaticDims& dm) {
+    if (H.L != STATIC_PLIES + 1 || H.dev.root_cur != 0) return false;
+    for (int l = 0; l < H.L; l++)
+        for (int v = H.level_begin[l]; v < H.level_begin[l + 1]; v++) {
+            const int want = l < STATIC_PLIES ? 4 - l / 2 : 0;
+            if (H.nchild[v] != want || (want && (int)((H.state[v].w >> 17) & 1u) != (l & 1))) return false;
+        }
+    dm.n6 = H.level_begin[6]; dm.n7 = H.level_begin[7]; dm.S2 = H.slot_level_begin[6]; dm.s_hot = H.slot_level_begin[STATIC_HOT_PLIES];
+    dm.ncopy = 1;
+    return true;
+}
+
+// ms_mccfr_batch_mode: 0 = mccfr_static_kernel on a fresh deal's tree (the headline kernel; mccfr_tree_kernel otherwise),
+// 4 = mccfr_tree_kernel, 3 = mccfr_batch_kernel (re-stepping), 1 = external sampling on the tree, 2 = outcome sampling;
+// grids as grid_for(n_trav, threads, 1), blocks one after another
 int host_mccfr_batch(int mode, int player, long long n_trav, unsigned long long philox_seed, unsigned long long first_trav) {
     BatchArgs a{H.dev, player, n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)), first_trav, 0, 1};
     auto grid = [&](int threads) { long long g = (n_trav + threads - 1) / threads; return (unsigned)(g < 1 ? 1 : (g > 148 ? 148 : g)); };
-    if (mode == 0 || mode == 1) {
-        a.nframes = mode == 0 ? H.nframes_tree : H.nframes_es;
+    StaticDims dm{};
+    if (mode == 0 && host_static_dims(dm)) {
+        StaticArgs sa{H.dev, player, n_trav, a.key, first_trav, dm};
+        for (int ncopy : {8, 4, 2, 1}) {
+            if (mccfr_static_smem(H.S, dm.S2, dm.s_hot, dm.n6, dm.n7, ncopy) + 16 > 227 * 1024) continue;
+            sa.dm.ncopy = ncopy;
+            return emu_launch_grid(static_entry, sa, grid(STATIC_THREADS), STATIC_THREADS);
+        }
+        return -4;
+    }
+    if (mode == 0 || mode == 4 || mode == 1) {
+        a.nframes = mode != 1 ? H.nframes_tree : H.nframes_es;
         for (int ncopy : {4, 2, 1}) {
-            const size_t smem = mode == 0 ? mccfr_tree_smem(H.S, H.N, a.nframes, TREE_THREADS, ncopy)
+            const size_t smem = mode != 1 ? mccfr_tree_smem(H.S, H.N, a.nframes, TREE_THREADS, ncopy)
                                           : es_tree_smem(H.S, H.N, a.nframes, TREE_THREADS, ncopy);
             if (smem > 227 * 1024) continue;
             a.ncopy = ncopy;
-            return emu_launch_grid(mode == 0 ? tree_entry : es_tree_entry, a, grid(TREE_THREADS), TREE_THREADS);
+            return emu_launch_grid(mode != 1 ? tree_entry : es_tree_entry, a, grid(TREE_THREADS), TREE_THREADS);
         }
         return -4;
     }
@@ -253,6 +298,52 @@ int host_mccfr_batch(int mode, int player, long long n_trav, unsigned long long 
 }
 
 int host_mccfr_apply() { return emu_launch_grid(apply_entry, H.dev, (unsigned)((H.S + 255) / 256), 256); }
+
+// ms_mccfr_inplace_many: mccfr_inplace_many_kernel<<<ceil(n_runs / warps), 256, smem>>>, one warp per run
+int host_mccfr_inplace_many(int n_runs, long long iters, unsigned long long seed0, unsigned long long first_iter,
+                            double* regret, double* strategy, uint8_t* touched) {
+    const size_t tree_b = (4 * (size_t)H.N + 15) & ~(size_t)15, per_warp = inplace_many_warp_bytes(H.S, H.nframes_tree);
+    int warps = (int)((227 * 1024 - tree_b) / per_warp);
+    if (warps > 8) warps = 8;
+    if (warps < 1) return -4;
+    if (warps > n_runs) warps = n_runs;
+    ManyRunArgs a{H.dev, ManyRuns{regret, strategy, touched, n_runs}, iters, seed0, first_iter, H.nframes_tree, warps};
+    return emu_launch_grid(inplace_many_entry, a, (unsigned)((n_runs + warps - 1) / warps), 256);
+}
+
+// ms_mccfr_apply_peers with TWO emulated ranks in this process: rank 0 is the solver H, rank 1 a second replica of its
+// table (`regret1` / `strategy1` / `touched1`, caller-owned) with its own delta buffer `delta1` [6S]; both ranks' kernels
+// (one block each) run CONCURRENTLY as an emulated cluster launch, meet at the flag barrier, sum the two delta buffers
+// in rank order and update their replicas.  `absent` = 1: rank 1 never arrives (its kernel is not launched), so rank 0
+// must time out, set its error word and leave its table alone.  -> rank 0's error word (0 = fine), or < 0.
+static std::vector<double> g_zero[2];
+static unsigned long long g_flags[2][MS_MAX_PEERS];
+static unsigned int g_err[2][4];
+static unsigned long long g_epoch = 0;
+int host_apply_peers(double* regret1, double* strategy1, uint8_t* touched1, double* delta1, int absent) {
+    const size_t n = 6 * (size_t)H.S;
+    for (int r = 0; r < 2; r++) if (g_zero[r].size() != n) g_zero[r].assign(n, 0.0);
+    PeersArgs a{};
+    a.d[0] = H.dev;
+    a.d[1] = H.dev; a.d[1].regret = regret1; a.d[1].strategy = strategy1; a.d[1].touched = touched1; a.d[1].delta = delta1;
+    for (int r = 0; r < 2; r++) {
+        PeerView& pv = a.pv[r];
+        pv.delta[0] = H.delta.data(); pv.delta[1] = delta1;
+        pv.flags[0] = g_flags[0]; pv.flags[1] = g_flags[1];
+        pv.my_flags = g_flags[r]; pv.zero_me = g_zero[r].data(); pv.rank = r; pv.world = 2;
+        a.err[r] = g_err[r];
+    }
+    a.epoch = ++g_epoch;
+    int rc;
+    if (absent) rc = emu_launch_cluster(peers_entry, a, 1, 1024);     // only block 0 = rank 0 runs
+    else rc = emu_launch_cluster(peers_entry, a, 2, 1024);
+    if (rc) return -1;
+    // the exchange consumed both delta buffers: the next batch accumulates into fresh ones (the library alternates two
+    // buffers per rank and zeroes the idle one in the kernel; here one buffer per rank is simply cleared)
+    if (!g_err[0][0]) { std::fill(H.delta.begin(), H.delta.end(), 0.0); if (!absent) std::fill(delta1, delta1 + n, 0.0); }
+    return (int)g_err[0][0];
+}
+void host_peers_reset() { g_epoch = 0; for (int r = 0; r < 2; r++) { for (auto& f : g_flags[r]) f = 0; for (auto& e : g_err[r]) e = 0; } }
 
 // ms_cfr_iterate_many: cfr_many_kernel<<<n_jobs, 512, smem>>>, one CTA per job.  The shim holds one solver, so the jobs
 // are `n_jobs` references to it and the emulator runs the CTAs one after another: n_jobs x iters iterations in all.
@@ -280,10 +371,10 @@ int host_eval(const double* pol0, const double* pol1, long long n, unsigned long
     return emu_launch_grid(eval_entry, a, 4, 256);
 }
 
-// the slot-aligned delta buffer the multi-GPU exchange sums over ranks: [S][4] regret deltas, then [S] update counts
-void host_solver_delta(double* out5S) { for (size_t i = 0; i < H.delta.size(); i++) out5S[i] = H.delta[i]; }
+// the slot-aligned delta buffer the multi-GPU exchange sums over ranks: [S][4] regret deltas, [S] update counts, [S] first-touch marks
+void host_solver_delta(double* out6S) { for (size_t i = 0; i < H.delta.size(); i++) out6S[i] = H.delta[i]; }
 
-void host_solver_set_delta(const double* in5S) { for (size_t i = 0; i < H.delta.size(); i++) H.delta[i] = in5S[i]; }
+void host_solver_set_delta(const double* in6S) { for (size_t i = 0; i < H.delta.size(); i++) H.delta[i] = in6S[i]; }
 
 double host_solver_delta_abs_sum() {
     double t = 0.0;

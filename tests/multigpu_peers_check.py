@@ -1,4 +1,5 @@
-"""Multi-GPU check of the peer-memory exchange (run under torchrun, one process per GPU; not collected by pytest):
+"""Multi-GPU check of the peer-memory exchange (run under torchrun, one process per GPU; tests/test_gpu_multigpu.py
+launches it with 2 ranks when the box has 2 GPUs):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu_peers_check.py
 
@@ -21,7 +22,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     a, b = Solver(seed=42, device=dev), Solver(seed=42, device=dev)
     a.attach_peers()
     B = 4096
@@ -33,12 +35,25 @@ def main():
         dist.all_reduce(b.delta_tensor())
         b.mccfr_apply()
     torch.cuda.synchronize()
-    ra, sa, _ = a.export()
-    rb, sb, _ = b.export()
+    assert a.peer_error() == 0
+    ra, sa, ta = a.export()
+    rb, sb, tb = b.export()
     np.testing.assert_allclose(ra, rb, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(sa, sb, rtol=1e-9, atol=1e-9)
-    # replicas are bit-identical on the peer path
-    t = torch.from_numpy(np.concatenate([ra.ravel(), sa.ravel()])).to(dev)
+    assert np.array_equal(ta, tb) and ta.sum() > 700        # which InfoNodes exist: same on both paths
+    # ... and equal to ONE GPU running every rank's traversal ids (the result does not depend on the number of ranks)
+    if rank == 0:
+        one = Solver(seed=42, device=dev)
+        for it in range(6):
+            for r in range(world):
+                one.mccfr_batch(2, B, philox_seed=5, first_trav=(it * world + r) * B)
+            one.mccfr_apply()
+        r1, s1, t1 = one.export()
+        np.testing.assert_allclose(ra, r1, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(sa, s1, rtol=1e-9, atol=1e-9)
+        assert np.array_equal(ta, t1)
+    # replicas are bit-identical on the peer path (tables and touched flags)
+    t = torch.from_numpy(np.concatenate([ra.ravel(), sa.ravel(), ta.astype(np.float64)])).to(dev)
     lo, hi = t.clone(), t.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -72,7 +87,7 @@ def main():
         b.mccfr_apply()
 
     out = {}
-    for batch in (768, 8192, 113664):
+    for batch in ((768, 113664) if os.environ.get("PEERS_CHECK_TIMING", "1") == "1" else ()):
         out[batch] = {"peers_ms": timed(step_peers, batch), "nccl_ms": timed(step_nccl, batch), "no_exchange_ms": timed(step_none, batch)}
     if rank == 0:
         print("PEERS_CHECK_OK world=%d" % world, out, flush=True)

@@ -113,9 +113,15 @@ def test_mccfr_inplace_matches_oracle_stream():
     assert c["visits"] == 703 * 25 and c["updates"] == 172 * 25
 
 
-@pytest.mark.parametrize("player,ntrav", [(0, 1), (1, 1), (0, 700), (1, 700), (2, 1500)])
-def test_mccfr_batch_matches_oracle_frozen_sigma(player, ntrav):
+@pytest.mark.parametrize("mode,player,ntrav", [(0, 0, 1), (0, 1, 1), (0, 0, 700), (0, 1, 700), (0, 2, 1500), (0, 2, 20000),
+                                               (4, 0, 1), (4, 1, 700), (4, 2, 1500)])
+def test_mccfr_batch_matches_oracle_frozen_sigma(mode, player, ntrav):
+    """mode 0 = mccfr_static_kernel (the headline kernel; sequential Philox stream, oracle: mccfr_batch_seq), mode 4 =
+    mccfr_tree_kernel (call-indexed stream, oracle: mccfr_batch): same estimator, same frozen table, same traversal ids
+    -> tables to 1e-9 (fp64 sums in another order; the static kernel multiplies by 1/sigma where the reference divides),
+    update / visit / edge counts exactly."""
     sv = Solver(seed=42)
+    obatch = (lambda t, *a: t.mccfr_batch_seq(*a)) if mode == 0 else (lambda t, *a: t.mccfr_batch(*a))
     t = ora.Table()
     t.mccfr_populate()
     keys0, _, _, _, _ = t.arrays()
@@ -125,7 +131,7 @@ def test_mccfr_batch_matches_oracle_frozen_sigma(player, ntrav):
     rng = ora.Rng(1, 9)
     t.mccfr_iterate(6, rng)
     sv.counters(reset=True)
-    sv.mccfr_batch(player, ntrav, philox_seed=31337, first_trav=1000)
+    sv.mccfr_batch(player, ntrav, philox_seed=31337, first_trav=1000, mode=mode)
     # deltas are not applied yet
     reg0, strat0, _ = sv.export()
     _, oreg0, ostrat0, _, _ = t.arrays()
@@ -134,16 +140,16 @@ def test_mccfr_batch_matches_oracle_frozen_sigma(player, ntrav):
     # oracle: both players against the SAME frozen table when player == 2
     if player == 2:
         snap_reg, snap_strat = oreg0.copy(), ostrat0.copy()
-        u0, v0 = t.mccfr_batch(0, 31337, 1000, ntrav)
+        u0, v0 = obatch(t, 0, 31337, 1000, ntrav)
         _, r_a, s_a, _, _ = t.arrays()
         t.set_arrays(snap_reg, snap_strat)
-        u1, v1 = t.mccfr_batch(1, 31337, 1000, ntrav)
+        u1, v1 = obatch(t, 1, 31337, 1000, ntrav)
         _, r_b, s_b, _, _ = t.arrays()
         oreg = r_a + r_b - snap_reg
         ostrat = s_a + s_b - snap_strat
         nu, nv = u0 + u1, v0 + v1
     else:
-        nu, nv = t.mccfr_batch(player, 31337, 1000, ntrav)
+        nu, nv = obatch(t, player, 31337, 1000, ntrav)
         _, oreg, ostrat, _, _ = t.arrays()
     reg, strat, _ = sv.export()
     np.testing.assert_allclose(reg[perm], oreg, rtol=1e-9, atol=1e-9)
@@ -167,14 +173,15 @@ def test_mccfr_batch_shards_sum_to_whole():
     a.mccfr_batch(2, 2048, philox_seed=5, first_trav=0)
     b.mccfr_batch(2, 2048, philox_seed=5, first_trav=2048)
     dsum = a.delta_tensor() + b.delta_tensor()
-    torch.testing.assert_close(dsum, whole.delta_tensor(), rtol=1e-9, atol=1e-9)
     S = whole.n_slots
-    assert torch.equal(dsum[4 * S:], whole.delta_tensor()[4 * S:])    # update counts are exact integers
+    torch.testing.assert_close(dsum[:5 * S], whole.delta_tensor()[:5 * S], rtol=1e-9, atol=1e-9)
+    assert torch.equal(dsum[4 * S:5 * S], whole.delta_tensor()[4 * S:5 * S])    # update counts are exact integers
+    assert torch.equal(dsum[5 * S:] != 0, whole.delta_tensor()[5 * S:] != 0)    # first-touch marks: the same set of infosets
 
 
 @pytest.mark.parametrize("seed", [42, 1, 2 ** 33 + 7])
 def test_tree_walk_and_restep_kernels_agree(seed):
-    """mode 0 (the estimator walking the enumerated tree, the default) and mode 3 (the env re-stepped at every node):
+    """mode 4 (the estimator walking the enumerated tree, generic kernel) and mode 3 (the env re-stepped at every node):
     same traversals, same Philox draws -> same deltas (fp64 sums differ only by addition order), identical update
     counts, touched flags and counters."""
     a, b = Solver(seed=seed), Solver(seed=seed)
@@ -183,11 +190,12 @@ def test_tree_walk_and_restep_kernels_agree(seed):
         s.counters(reset=True)
     n = 3 * 1024 + 17
     for player in (0, 1, 2):
-        a.mccfr_batch(player, n, philox_seed=8, first_trav=100, mode=0)
+        a.mccfr_batch(player, n, philox_seed=8, first_trav=100, mode=4)
         b.mccfr_batch(player, n, philox_seed=8, first_trav=100, mode=3)
         S = a.n_slots
         torch.testing.assert_close(a.delta_tensor()[:4 * S], b.delta_tensor()[:4 * S], rtol=1e-10, atol=1e-10)
-        assert torch.equal(a.delta_tensor()[4 * S:], b.delta_tensor()[4 * S:])
+        assert torch.equal(a.delta_tensor()[4 * S:5 * S], b.delta_tensor()[4 * S:5 * S])
+        assert torch.equal(a.delta_tensor()[5 * S:] != 0, b.delta_tensor()[5 * S:] != 0)
         a.mccfr_apply()
         b.mccfr_apply()
     assert a.counters() == b.counters()
@@ -218,7 +226,8 @@ def test_tree_walk_and_restep_kernels_agree_on_mid_game_roots(seed, plies):
         c.mccfr_batch(2, n, philox_seed=4, first_trav=7, mode=mode_c)
         S = a.n_slots
         torch.testing.assert_close(a.delta_tensor()[:4 * S], c.delta_tensor()[:4 * S], rtol=1e-10, atol=1e-10)
-        assert torch.equal(a.delta_tensor()[4 * S:], c.delta_tensor()[4 * S:])
+        assert torch.equal(a.delta_tensor()[4 * S:5 * S], c.delta_tensor()[4 * S:5 * S])
+        assert torch.equal(a.delta_tensor()[5 * S:] != 0, c.delta_tensor()[5 * S:] != 0)
         a.mccfr_apply()
         c.mccfr_apply()
     assert a.counters() == c.counters()
@@ -389,3 +398,81 @@ def test_cfr_many_deals_in_one_launch():
         ra, sa, _ = sv.export()
         rb, sb, _ = one.export()
         assert np.array_equal(ra, rb) and np.array_equal(sa, sb), s
+
+
+def test_static_and_generic_kernels_agree_statistically():
+    """mccfr_static_kernel (mode 0) and mccfr_tree_kernel (mode 4) run the same estimator on different random streams:
+    from the same frozen table the mean regret delta per traversal agrees within sampling error, and the deterministic
+    parts (root update count, total updates / visits) are equal."""
+    a, b = Solver(seed=42), Solver(seed=42)
+    for s in (a, b):
+        s.mccfr_inplace(30, philox_seed=3)
+        s.counters(reset=True)
+    n = 200_000
+    a.mccfr_batch(2, n, philox_seed=8, first_trav=0, mode=0)
+    b.mccfr_batch(2, n, philox_seed=8, first_trav=0, mode=4)
+    S = a.n_slots
+    da, db = a.delta_tensor().cpu().numpy(), b.delta_tensor().cpu().numpy()
+    assert a.counters() == b.counters()
+    assert da[4 * S] == db[4 * S] == n                                   # the root is updated once per player-0 traversal
+    assert da[4 * S:5 * S].sum() == db[4 * S:5 * S].sum() == 172 * n
+    # visit counts of the first plies: binomial noise only
+    lvl1 = slice(4 * S + 1, 4 * S + 5)
+    assert np.all(np.abs(da[lvl1] - db[lvl1]) < 6 * np.sqrt(n))
+    # root regret deltas: mean over n traversals, |cfv - v| <= 9 and w = 1 at the root
+    assert np.all(np.abs(da[:4] - db[:4]) / n < 6 * 9 / np.sqrt(n))
+
+
+def test_static_kernel_is_used_for_fresh_deals_and_shards_by_traversal_id():
+    """ms_mccfr_batch on a fresh deal = mccfr_static_kernel; its result depends on the traversal ids only, not on how
+    they are split into launches, CTAs or ranks (the premise of the multi-GPU exchange), for several deals."""
+    for seed in (42, 7, 2 ** 33 + 7):
+        whole, parts = Solver(seed=seed), Solver(seed=seed)
+        for s in (whole, parts):
+            s.mccfr_inplace(4, philox_seed=2)
+        whole.mccfr_batch(2, 5000, philox_seed=5, first_trav=100)
+        for lo, n in ((100, 1), (101, 1023), (1124, 2048), (3172, 1928)):
+            parts.mccfr_batch(2, n, philox_seed=5, first_trav=lo)
+        S = whole.n_slots
+        dw, dp = whole.delta_tensor(), parts.delta_tensor()
+        torch.testing.assert_close(dp[:4 * S], dw[:4 * S], rtol=1e-9, atol=1e-9)
+        assert torch.equal(dp[4 * S:5 * S], dw[4 * S:5 * S])
+        assert whole.counters() == parts.counters()
+
+
+def test_mccfr_inplace_many_runs_equal_solo_runs():
+    """ms_mccfr_inplace_many (the reference's independent-runs protocol, run_mccfr_experiment.py:195-202, in one launch):
+    run r == a solo ms_mccfr_inplace on philox seed seed0 + r, bit for bit, incl. continuation and first-touch sets."""
+    from scopa_b200.solver import mccfr_inplace_many
+    sv = Solver(seed=42)
+    runs, seed0 = 37, 9000                      # more runs than one wave of CTAs holds per SM, not a multiple of 4
+    m = mccfr_inplace_many(sv, runs, 20, philox_seed0=seed0)
+    m = mccfr_inplace_many(sv, m, 30, philox_seed0=seed0)
+    torch.cuda.synchronize()
+    assert m.iterations == 50
+    c = sv.counters()
+    assert c["updates"] == 172 * 50 * runs and c["visits"] == 703 * 50 * runs
+    reg, strat, tch = m.regret.cpu().numpy(), m.strategy.cpu().numpy(), m.touched.cpu().numpy()
+    for r in (0, 1, 17, 36):
+        solo = Solver(seed=42)
+        solo.mccfr_inplace(50, philox_seed=seed0 + r)
+        r1, s1, t1 = solo.export()
+        assert np.array_equal(reg[r], r1) and np.array_equal(strat[r], s1) and np.array_equal(tch[r], t1)
+    assert not np.array_equal(reg[0], reg[1])
+    r0, s0, _ = sv.export()
+    assert not r0.any() and not s0.any()        # the solver's own table is untouched
+
+
+def test_reset_refused_while_attached_and_touched_travels_with_delta():
+    """touched flags are set by the apply step from the delta buffer's first-touch marks (so that every rank of a
+    multi-GPU run agrees on which InfoNodes exist), not by the traversal kernels directly."""
+    sv = Solver(seed=42)
+    sv.mccfr_batch(2, 2048, philox_seed=1)
+    _, _, t0 = sv.export()
+    assert not t0.any()                          # nothing is marked before the apply step
+    S = sv.n_slots
+    marks = sv.delta_tensor()[5 * S:].cpu().numpy()
+    sv.mccfr_apply()
+    _, _, t1 = sv.export()
+    assert np.array_equal(t1.astype(bool), marks != 0) and t1.sum() > 0.9 * S
+    assert float(sv.delta_tensor().abs().sum().item()) == 0.0

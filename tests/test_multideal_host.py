@@ -77,7 +77,7 @@ def test_one_deal_reproduces_batch_solver(md, solver_lib):  # noqa: F811
     n = 2048
     for b in range(3):
         for p in (0, 1):
-            assert solver_lib.host_mccfr_batch(0, p, n, 5, b * n) == 0 and solver_lib.host_mccfr_apply() == 0
+            assert solver_lib.host_mccfr_batch(4, p, n, 5, b * n) == 0 and solver_lib.host_mccfr_apply() == 0
             assert md.host_md_batch(p, n, 5, b * n) == 0 and md.host_md_apply() == 0
     tab = sv.table()
     c1, touched = _counters(sv)
@@ -140,7 +140,7 @@ def test_blocked_one_deal_reproduces_batch_solver(md, solver_lib):  # noqa: F811
     n = 2048
     for b in range(3):
         for p in (0, 1):
-            assert solver_lib.host_mccfr_batch(0, p, n, 5, b * n) == 0 and solver_lib.host_mccfr_apply() == 0
+            assert solver_lib.host_mccfr_batch(4, p, n, 5, b * n) == 0 and solver_lib.host_mccfr_apply() == 0
             assert md.host_md_blocked(p, b, 1, n, 5) == 0 and md.host_md_apply() == 0
     tab = sv.table()
     c1, _ = _counters(sv)

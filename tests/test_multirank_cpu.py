@@ -103,6 +103,7 @@ def _emu_solver():
     L.host_mccfr_batch.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_ulonglong, C.c_ulonglong]
     L.host_solver_delta.argtypes = [vp]
     L.host_solver_set_delta.argtypes = [vp]
+    L.host_solver_counters.argtypes = [vp, vp, C.c_int]
     sv = HostSolver(L, 42)
     assert L.host_mccfr_inplace_tree(3, 5, 0) == 0        # same non-trivial starting table on every rank
     return L, sv
@@ -117,13 +118,16 @@ def _emu_worker(rank, world, port, total, q):
     L, sv = _emu_solver()
     lo, n = shard_bounds(total, rank, world)
     assert L.host_mccfr_batch(0, 2, n, 99, lo) == 0       # both players, traversal ids [lo, lo + n)
-    buf = torch.zeros(5 * sv.n_slots, dtype=torch.float64)
+    buf = torch.zeros(6 * sv.n_slots, dtype=torch.float64)
     L.host_solver_delta(buf.data_ptr())
     allreduce_delta(buf)
     L.host_solver_set_delta(buf.data_ptr())
     assert L.host_mccfr_apply() == 0
     tab = sv.table()
-    q.put((rank, tab["regret"], tab["strategy"], buf.numpy()[4 * sv.n_slots:].copy()))
+    cnt = np.zeros(3, np.uint64)
+    touched = np.zeros(sv.n_slots, np.uint8)
+    L.host_solver_counters(cnt.ctypes.data, touched.ctypes.data, 0)
+    q.put((rank, tab["regret"], tab["strategy"], buf.numpy()[4 * sv.n_slots:5 * sv.n_slots].copy(), touched))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -136,18 +140,24 @@ def test_two_ranks_of_the_product_kernel_equal_single_rank():
     procs = [ctx.Process(target=_emu_worker, args=(r, world, port, total, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict((r, (reg, strat, cnt)) for r, reg, strat, cnt in (q.get(timeout=180) for _ in range(world)))
+    got = dict((r, (reg, strat, cnt, tch)) for r, reg, strat, cnt, tch in (q.get(timeout=180) for _ in range(world)))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     # replicas stay identical: every rank applied the same summed delta
     assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    assert np.array_equal(got[0][3], got[1][3])         # ... including WHICH infosets exist (touched travels with the delta)
     L, sv = _emu_solver()
     assert L.host_mccfr_batch(0, 2, total, 99, 0) == 0
-    whole = np.zeros(5 * sv.n_slots)
+    whole = np.zeros(6 * sv.n_slots)
     L.host_solver_delta(whole.ctypes.data)
     assert L.host_mccfr_apply() == 0
     tab = sv.table()
-    assert np.array_equal(got[0][2], whole[4 * sv.n_slots:])              # update counts: exact integers
+    S = sv.n_slots
+    assert np.array_equal(got[0][2], whole[4 * S:5 * S])                  # update counts: exact integers
+    cnt = np.zeros(3, np.uint64)
+    touched = np.zeros(S, np.uint8)
+    L.host_solver_counters(cnt.ctypes.data, touched.ctypes.data, 0)
+    assert np.array_equal(got[0][3], touched) and touched.sum() > 0.9 * S   # same infosets as the single-rank run
     np.testing.assert_allclose(got[0][0], tab["regret"], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(got[0][1], tab["strategy"], rtol=1e-9, atol=1e-9)

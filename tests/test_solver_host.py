@@ -70,6 +70,10 @@ def lib():
     L.host_best_response.argtypes = [C.c_int, vp]
     L.host_policy.argtypes = [C.c_int, vp]
     L.host_eval.argtypes = [vp, vp, C.c_longlong, C.c_ulonglong, C.c_ulonglong, vp, vp]
+    L.host_mccfr_inplace_many.argtypes = [C.c_int, C.c_longlong, C.c_ulonglong, C.c_ulonglong, vp, vp, vp]
+    L.host_apply_peers.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.host_solver_delta.argtypes = [vp]
+    L.host_solver_set_delta.argtypes = [vp]
     return L
 
 
@@ -189,11 +193,13 @@ def test_mccfr_inplace_matches_oracle_stream(lib, kernel):
     assert cnt["visits"] == 703 * 25 and cnt["updates"] == 172 * 25
 
 
-@pytest.mark.parametrize("mode,player,ntrav", [(0, 0, 1), (0, 1, 700), (0, 2, 1500), (3, 0, 700), (3, 2, 900)])
+@pytest.mark.parametrize("mode,player,ntrav", [(0, 0, 1), (0, 1, 1), (0, 0, 700), (0, 1, 700), (0, 2, 1500), (4, 0, 1), (4, 1, 700),
+                                               (4, 2, 1200), (3, 0, 700), (3, 2, 900)])
 def test_mccfr_batch_matches_oracle_frozen_sigma(lib, mode, player, ntrav):
-    """mccfr_tree_kernel<1024> (mode 0: the headline kernel of bench.py) and mccfr_batch_kernel (mode 3), then
-    mccfr_apply_kernel, against the oracle's frozen-sigma batch on the same Philox ids: tables to 1e-9 (fp64 sums in
-    another order), update / visit / step counts exactly."""
+    """mccfr_static_kernel (mode 0: the headline kernel of bench.py, sequential Philox stream), mccfr_tree_kernel<1024>
+    (mode 4) and mccfr_batch_kernel (mode 3) (both: call-indexed stream), then mccfr_apply_kernel, against the oracle's
+    frozen-sigma batch on the same stream and traversal ids: tables to 1e-9 (fp64 sums in another order; the static
+    kernel multiplies by 1/sigma where the reference divides), update / visit / step counts exactly."""
     sv = HostSolver(lib, 42)
     strings = sv.table()["strings"]
     t = ora.Table()
@@ -211,7 +217,7 @@ def test_mccfr_batch_matches_oracle_frozen_sigma(lib, mode, player, ntrav):
     oreg, ostrat, nu, nv = oreg0.copy(), ostrat0.copy(), 0, 0
     for p in ((0, 1) if player == 2 else (player,)):            # both players against the SAME frozen table
         t.set_arrays(oreg0, ostrat0)
-        u, v = t.mccfr_batch(p, 31337, 1000, ntrav)
+        u, v = (t.mccfr_batch_seq if mode == 0 else t.mccfr_batch)(p, 31337, 1000, ntrav)
         _, r1, s1, _, _ = t.arrays()
         oreg += r1 - oreg0
         ostrat += s1 - ostrat0
@@ -327,12 +333,105 @@ def test_mccfr_batch_shards_sum_to_whole(lib):
         sv = HostSolver(lib, 42)
         assert lib.host_mccfr_inplace_tree(4, 2, 0) == 0          # the same starting table on every "rank"
         assert lib.host_mccfr_batch(0, 2, n, 5, first) == 0
-        out = np.zeros(5 * sv.n_slots)
+        out = np.zeros(6 * sv.n_slots)
         lib.host_solver_delta(out.ctypes.data)
         return out, sv.n_slots
 
     whole, S = deltas(0, 3000)
     a, _ = deltas(0, 1500)
     b, _ = deltas(1500, 1500)
-    np.testing.assert_allclose(a + b, whole, rtol=1e-9, atol=1e-9)
-    assert np.array_equal((a + b)[4 * S:], whole[4 * S:]) and whole[4 * S:].sum() > 0
+    np.testing.assert_allclose((a + b)[:5 * S], whole[:5 * S], rtol=1e-9, atol=1e-9)
+    assert np.array_equal((a + b)[4 * S:5 * S], whole[4 * S:5 * S]) and whole[4 * S:5 * S].sum() > 0
+    assert np.array_equal((a + b)[5 * S:] != 0, whole[5 * S:] != 0)       # first-touch marks: the same SET of infosets
+
+
+def test_mccfr_inplace_many_runs_equal_solo_runs(lib):
+    """mccfr_inplace_many_kernel (the reference's 10-independent-runs protocol, run_mccfr_experiment.py:195-202, as one
+    launch, one warp per run): run r of the launch holds the same float64 bits and first-touch set as a solo
+    mccfr_inplace_tree_kernel run on philox seed seed0 + r -- also when the launch is continued, and with more runs than
+    one CTA holds (4 per CTA for this deal)."""
+    sv = HostSolver(lib, 42)
+    S, runs, seed0 = sv.n_slots, 6, 4000
+    reg, strat, tch = np.zeros((runs, S, 4)), np.zeros((runs, S, 4)), np.zeros((runs, S), np.uint8)
+    assert lib.host_mccfr_inplace_many(runs, 3, seed0, 0, reg.ctypes.data, strat.ctypes.data, tch.ctypes.data) == 0
+    assert lib.host_mccfr_inplace_many(runs, 4, seed0, 3, reg.ctypes.data, strat.ctypes.data, tch.ctypes.data) == 0
+    cnt, _ = _counters(sv)
+    assert cnt["updates"] == 172 * 7 * runs and cnt["visits"] == 703 * 7 * runs
+    assert np.array_equal(sv.table()["regret"], np.zeros((S, 4)))          # the solver's own table is not touched
+    for r in range(runs):
+        solo = HostSolver(lib, 42)
+        assert lib.host_mccfr_inplace_tree(7, seed0 + r, 0) == 0
+        tab = solo.table()
+        _, touched = _counters(solo)
+        assert np.array_equal(reg[r], tab["regret"]) and np.array_equal(strat[r], tab["strategy"])
+        assert np.array_equal(tch[r], touched)
+    assert not np.array_equal(reg[0], reg[1])                              # the runs are independent streams
+
+
+def _shares(lib, S, first, n0, n1):
+    """one batch split over two ranks on the emulated solver's CURRENT table: rank 1's share [first + n0, first + n0 + n1)
+    is run first and moved out of the solver's delta buffer, then rank 0's share [first, first + n0) is run into it
+    -> (delta0 copy, delta1)"""
+    delta0, delta1 = np.zeros(6 * S), np.zeros(6 * S)
+    assert lib.host_mccfr_batch(0, 2, n1, 99, first + n0) == 0
+    lib.host_solver_delta(delta1.ctypes.data)
+    lib.host_solver_set_delta(np.zeros(6 * S).ctypes.data)
+    assert lib.host_mccfr_batch(0, 2, n0, 99, first) == 0
+    lib.host_solver_delta(delta0.ctypes.data)
+    return delta0, delta1
+
+
+def test_apply_peers_two_emulated_ranks_equal_sum_and_apply(lib):
+    """mccfr_apply_peers_kernel with two ranks running CONCURRENTLY in this process (flag barrier with release / acquire
+    semantics, both ranks reading both delta buffers, rank-ordered sum, table update, first-touch marks): after every
+    exchange the two replicas hold the same bits, and they equal {delta0 + delta1, mccfr_apply_kernel} -- two exchanges in
+    a row (the epoch advances, the buffers are cleared)."""
+    lib.host_peers_reset()
+    sv = HostSolver(lib, 42)
+    S = sv.n_slots
+    assert lib.host_mccfr_inplace_tree(1, 5, 0) == 0           # one iteration: most infosets are still untouched
+    start = sv.table()
+    _, tch_start = _counters(sv)
+    reg1, strat1, tch1 = start["regret"].copy(), start["strategy"].copy(), tch_start.copy()
+    sums = []
+    for first, n0, n1 in ((0, 700, 500), (1200, 300, 900)):
+        delta0, delta1 = _shares(lib, S, first, n0, n1)
+        sums.append(delta0 + delta1)
+        assert lib.host_apply_peers(reg1.ctypes.data, strat1.ctypes.data, tch1.ctypes.data, delta1.ctypes.data, 0) == 0
+        tab0 = sv.table()
+        _, tch0 = _counters(sv)
+        assert np.array_equal(tab0["regret"], reg1) and np.array_equal(tab0["strategy"], strat1)
+        assert np.array_equal(tch0, tch1) and tch0.sum() > tch_start.sum()
+        assert lib.host_solver_delta_abs_sum() == 0.0 and not delta1.any()
+    ref = HostSolver(lib, 42)                                   # (the emulator holds ONE solver: this replaces `sv`)
+    assert lib.host_mccfr_inplace_tree(1, 5, 0) == 0
+    for d in sums:
+        lib.host_solver_set_delta(d.ctypes.data)
+        assert lib.host_mccfr_apply() == 0
+    want = ref.table()
+    _, tch_want = _counters(ref)
+    assert np.array_equal(tab0["regret"], want["regret"]) and np.array_equal(tab0["strategy"], want["strategy"])
+    assert np.array_equal(tch0, tch_want)
+
+
+def test_apply_peers_gives_up_on_an_absent_rank(lib):
+    """The barrier is bounded: when rank 1 never arrives, rank 0 stops waiting after MS_PEER_TIMEOUT_NS, reports
+    1 + the missing rank in its error word and leaves its table untouched; later exchanges return at once."""
+    import time
+    lib.host_peers_reset()
+    sv = HostSolver(lib, 42)
+    S = sv.n_slots
+    assert lib.host_mccfr_inplace_tree(2, 5, 0) == 0
+    before = sv.table()
+    _shares(lib, S, 0, 200, 100)
+    junk = [np.zeros((S, 4)), np.zeros((S, 4)), np.zeros(S, np.uint8), np.zeros(6 * S)]
+    t0 = time.perf_counter()
+    assert lib.host_apply_peers(*[j.ctypes.data for j in junk], 1) == 2          # 1 + rank 1
+    waited = time.perf_counter() - t0
+    assert 1.5 < waited < 30.0
+    after = sv.table()
+    assert np.array_equal(before["regret"], after["regret"]) and np.array_equal(before["strategy"], after["strategy"])
+    t0 = time.perf_counter()
+    assert lib.host_apply_peers(*[j.ctypes.data for j in junk], 1) == 2          # sticky, and immediate
+    assert time.perf_counter() - t0 < 1.0
+    lib.host_peers_reset()
