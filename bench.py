@@ -278,12 +278,23 @@ def attach_peers_all_ranks(cx, sv):
 
 def time_mccfr(cx, sv, exchange, B, seed, it0, warm, steps):
     """`warm` untimed + `steps` timed iterations of {batch kernel, exchange, apply}; -> dict of device times (ms) and
-    counters, max over ranks for the step time.  `exchange(sv)` is one of the three forms below."""
+    counters, max over ranks for the step time.  `exchange(sv)` is one of the forms in section_mccfr; the string "fused"
+    selects ms_mccfr_batch_peers (traversals + peer exchange + apply in ONE launch)."""
     torch = cx.torch
     from scopa_b200 import _lib
     rank, world = cx.rank, cx.world
+    fused = exchange == "fused"
+
+    def batch(s, first):
+        if fused:
+            s.mccfr_batch_peers(2, B, philox_seed=seed, first_trav=first)
+        else:
+            s.mccfr_batch(2, B, philox_seed=seed, first_trav=first)
+
+    if fused:
+        exchange = lambda s: None
     for i in range(warm):
-        sv.mccfr_batch(2, B, philox_seed=seed, first_trav=((it0 + i) * world + rank) * B)
+        batch(sv, ((it0 + i) * world + rank) * B)
         exchange(sv)
     sv.counters(reset=True)
     ev, kev = cx.events(steps), cx.events(steps)
@@ -294,7 +305,7 @@ def time_mccfr(cx, sv, exchange, B, seed, it0, warm, steps):
         cx.flush_l2(sync=True)
         ev[i][0].record()
         kev[i][0].record()
-        sv.mccfr_batch(2, B, philox_seed=seed, first_trav=((it0 + warm + i) * world + rank) * B)
+        batch(sv, ((it0 + warm + i) * world + rank) * B)
         kev[i][1].record()
         exchange(sv)
         ev[i][1].record()
@@ -341,7 +352,7 @@ def section_mccfr(cx, sampler):
     if world == 1:
         collective, exchange, hsv = "none", ex_local, sv
     elif args.collective == "p2p":
-        collective, exchange, hsv = "p2p", ex_p2p, sv_p2p
+        collective, exchange, hsv = "p2p_fused", "fused", sv_p2p
     else:
         collective, exchange, hsv = "nccl", ex_nccl, sv
 
@@ -362,8 +373,11 @@ def section_mccfr(cx, sampler):
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         _lib.check(lib.ms_solver_import_table(hsv.h, h_reg.data_ptr(), h_str.data_ptr(), hsv._stream()))
-        hsv.mccfr_batch(2, B, philox_seed=args.seed, first_trav=((r["next_it"] + i) * world + rank) * B)
-        exchange(hsv)
+        if exchange == "fused":
+            hsv.mccfr_batch_peers(2, B, philox_seed=args.seed, first_trav=((r["next_it"] + i) * world + rank) * B)
+        else:
+            hsv.mccfr_batch(2, B, philox_seed=args.seed, first_trav=((r["next_it"] + i) * world + rank) * B)
+            exchange(hsv)
         _lib.check(lib.ms_solver_export_table(hsv.h, None, None, None, h_reg.data_ptr(), h_str.data_ptr(), None,
                                               hsv._stream()))
     cx.barrier()
@@ -379,25 +393,29 @@ def section_mccfr(cx, sampler):
         exchange_ms = {"headline": collective}
         it = r["next_it"] + e2e_steps
         short = max(5, min(K, 10))
-        for name, fn, s in (("no_exchange_floor", ex_local, sv), ("nccl", ex_nccl, sv), ("p2p", ex_p2p, sv_p2p)):
+        for name, fn, s in (("no_exchange_floor", ex_local, sv), ("nccl", ex_nccl, sv), ("p2p", ex_p2p, sv_p2p),
+                            ("p2p_fused", "fused", sv_p2p)):
             if name == collective:
                 exchange_ms[name + "_ms_per_step"] = r["ms_total"] / K
                 continue
-            if name == "p2p":
+            if name.startswith("p2p"):
                 if not p2p_ok:
-                    exchange_ms["p2p"] = p2p_note or "not timed (--collective nccl)"
+                    exchange_ms[name] = p2p_note or "not timed (--collective nccl)"
                     continue
             rr = time_mccfr(cx, s, fn, B, args.seed, it, 3, short)
             it = rr["next_it"]
             exchange_ms[name + "_ms_per_step"] = rr["ms_total"] / short
-            if name == "p2p":
+            if name.startswith("p2p"):
                 err = s.peer_error()
                 bad = cx.max_over_ranks(float(err))
                 if bad:
-                    exchange_ms["p2p"] = f"peer exchange reported error word {int(bad)} (a rank timed out waiting for a peer)"
-                    exchange_ms.pop("p2p_ms_per_step", None)
-        exchange_ms["note"] = ("ms per iteration, max over ranks, same batch size; no_exchange_floor applies only the LOCAL delta "
-                               "(not a valid multi-GPU result): the gap to it is what the exchange costs")
+                    exchange_ms[name] = f"peer exchange reported error word {int(bad)} (a rank timed out waiting for a peer)"
+                    exchange_ms.pop(name + "_ms_per_step", None)
+        exchange_ms["note"] = ("ms per iteration, max over ranks, same batch size; nccl = batch kernel + NCCL all-reduce + apply "
+                               "kernel; p2p = batch kernel + ms_mccfr_apply_peers (peer-memory reads, rank-ordered sum, apply in "
+                               "one kernel); p2p_fused = ms_mccfr_batch_peers, ONE launch: the last CTA to finish its traversals "
+                               "does the exchange; no_exchange_floor applies only the LOCAL delta (not a valid multi-GPU "
+                               "result): the gap to it is what the exchange costs")
 
     obj = {
         "metric": "mccfr_infoset_node_updates_per_sec", "value": value, "unit": "infoset-node updates/s",
@@ -613,9 +631,19 @@ def section_schedules(cx):
     for B in (1, 4096, 65536, args.trav):
         sv = Solver(seed=42, device=cx.dev)
         done, pts, t_03 = 0, [], None
+        my_targets = targets
+        if B == 1:
+            # one device thread runs the reference's schedule: time 1000 iterations, keep the targets that fit ~12 s
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sv.mccfr_inplace(1000, philox_seed=args.seed, first_iter=0)
+            torch.cuda.synchronize()
+            per_it = (time.perf_counter() - t0) / 1000
+            sv = Solver(seed=42, device=cx.dev)
+            my_targets = [t for t in targets if t * per_it <= 12.0] or [min(targets[0], max(1000, int(12.0 / per_it)))]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for target in targets:
+        for target in my_targets:
             if B == 1:
                 sv.mccfr_inplace(target - done, philox_seed=args.seed, first_iter=done)
                 done = target
@@ -631,6 +659,10 @@ def section_schedules(cx):
                 t_03 = el
         out["schedules"]["in_place_B1" if B == 1 else f"B{B}"] = {
             "traversals_per_player_vs_exploitability_vs_wall_s": pts, "wall_s_to_exploitability_0.3_at_a_checkpoint": t_03}
+        if B == 1:
+            out["schedules"]["in_place_B1"]["us_per_iteration"] = per_it * 1e6
+            out["schedules"]["in_place_B1"]["note"] = ("one device thread; targets beyond ~12 s of run time are left out "
+                                                       "(the reference itself takes 62-67 ms per iteration)")
         del sv
     # the textbook estimator at one batch size for reference
     sv = Solver(seed=42, device=cx.dev)
@@ -658,7 +690,7 @@ def section_inplace(cx):
     sv = Solver(seed=42, device=cx.dev)
     sv.mccfr_inplace(50, philox_seed=1)
     torch.cuda.synchronize()
-    iters = 2000
+    iters = 1000
     t0 = time.perf_counter()
     sv.mccfr_inplace(iters, philox_seed=1, first_iter=50)
     torch.cuda.synchronize()
@@ -666,10 +698,9 @@ def section_inplace(cx):
     out = {"single_run": {"iterations": iters, "us_per_iteration": dt / iters * 1e6, "iterations_per_sec": iters / dt,
                           "updates_per_sec": iters * UPDATES_PER_PAIR / dt, "kernel": "mccfr_inplace_tree_kernel",
                           "note": "the reference takes 62-67 ms per iteration on one CPU core (BASELINE.md section 2)"}}
-    for runs in (10, 148 * 32):
-        tabs = mccfr_inplace_many(sv, runs, 50, philox_seed0=100)
+    for runs, it_m in ((10, 500), (148 * 4, 500), (148 * 32, 100)):
+        tabs = mccfr_inplace_many(sv, runs, 20, philox_seed0=100)
         torch.cuda.synchronize()
-        it_m = 500
         t0 = time.perf_counter()
         tabs = mccfr_inplace_many(sv, runs, it_m, philox_seed0=100)
         torch.cuda.synchronize()
@@ -1052,19 +1083,31 @@ def run_ours(args):
     if world == 1:
         # single-GPU reporting: no collectives below this line
         if not args.no_extras:
-            extras["mccfr_in_place"] = guarded(section_inplace, cx)
-            extras["mccfr_schedules"] = guarded(section_schedules, cx)
-            extras["mccfr_tree_walk"] = guarded(section_tree_walk, cx)
-            extras["mccfr_restep"] = guarded(section_restep, cx, sv)
-            extras["mccfr_external_sampling"] = guarded(section_es, cx)
-            extras["env_step_api"] = guarded(section_step_api, cx)
-            extras["cfr"] = guarded(section_cfr, cx)
-            extras["atomics"] = guarded(section_atomics, cx, mccfr_obj["value"])
+            t_ex = time.perf_counter()
+
+            def extra(name, fn, *a):
+                # the default run must end within minutes whatever a section does: past the budget the rest is skipped
+                if time.perf_counter() - t_ex > args.extras_budget_s:
+                    extras[name] = {"skipped": f"extras wall budget of {args.extras_budget_s:.0f} s used up"}
+                    return
+                t0 = time.perf_counter()
+                extras[name] = guarded(fn, *a)
+                if isinstance(extras[name], dict):
+                    extras[name]["section_wall_s"] = time.perf_counter() - t0
+
+            extra("mccfr_in_place", section_inplace, cx)
+            extra("mccfr_schedules", section_schedules, cx)
+            extra("mccfr_tree_walk", section_tree_walk, cx)
+            extra("mccfr_restep", section_restep, cx, sv)
+            extra("mccfr_external_sampling", section_es, cx)
+            extra("env_step_api", section_step_api, cx)
+            extra("cfr", section_cfr, cx)
+            extra("atomics", section_atomics, cx, mccfr_obj["value"])
             if args.md_deals > 0:
-                extras["mccfr_multi_deal"] = guarded(section_multideal, cx)
+                extra("mccfr_multi_deal", section_multideal, cx)
             if args.full_games > 0:
-                extras["full_scopa"] = guarded(section_full, cx)
-            extras["sdcfr"] = guarded(section_sdcfr, cx, sv)
+                extra("full_scopa", section_full, cx)
+            extra("sdcfr", section_sdcfr, cx, sv)
         if not args.no_cpu:
             cpu = guarded(cpu_baselines, args, 8.0)
             if isinstance(cpu, dict) and "error" in cpu:
@@ -1304,9 +1347,11 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="N = 1: only the two headline sections (and the CPU leg)")
+    ap.add_argument("--extras-budget-s", type=float, default=240.0,
+                    help="N = 1: no further single-GPU reporting section is started after this many seconds of them")
     ap.add_argument("--collective", default="both", choices=["both", "p2p", "nccl"],
                     help="multi-GPU delta exchange of the headline number: NCCL all-reduce + apply (nccl, and both: which also "
-                         "times the peer-memory kernel beside it) or the peer-memory kernel (p2p)")
+                         "times the peer-memory kernels beside it) or the fused traversal + peer-exchange kernel (p2p)")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--ref-trav", type=int, default=1500)
     ap.add_argument("--ref-games", type=int, default=400_000)

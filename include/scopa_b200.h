@@ -195,10 +195,15 @@ int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_tr
  *     The barrier is bounded: a rank that has waited 2 s for a peer sets the solver's error word and leaves its table
  *     unchanged from then on (no hang);
  *   ms_solver_peer_error: synchronises the stream and reads that word: *h_err = 0 and MS_OK, or 1 + the rank that
- *     did not arrive and MS_ERR_STATE. */
+ *     did not arrive and MS_ERR_STATE;
+ *   ms_mccfr_batch_peers: ms_mccfr_batch + ms_mccfr_apply_peers as ONE launch per iteration: the last CTA to finish its
+ *     traversals performs the exchange and the table update (fused compute + exchange; fresh-deal roots, otherwise it
+ *     falls back to the two launches). */
 int ms_solver_ipc_export(ms_solver* s, void* handle64, uint64_t offsets[3]);
 int ms_solver_ipc_attach(ms_solver* s, int32_t rank, int32_t world, const void* handles, const uint64_t* offsets);
 int ms_mccfr_apply_peers(ms_solver* s, void* stream);
+int ms_mccfr_batch_peers(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav,
+                         void* stream);
 int ms_solver_peer_error(ms_solver* s, uint32_t* h_err, void* stream);
 /* counters accumulated by the MCCFR kernels since the last reset: [0] traverser-node updates,
  * [1] node visits (_sample calls), [2] env steps */

@@ -56,6 +56,7 @@ _SIGS = {
     "ms_solver_ipc_export": ([vp, vp, C.POINTER(u64)], C.c_int),
     "ms_solver_ipc_attach": ([vp, i32, i32, vp, C.POINTER(u64)], C.c_int),
     "ms_mccfr_apply_peers": ([vp, vp], C.c_int),
+    "ms_mccfr_batch_peers": ([vp, i32, i64, u64, u64, vp], C.c_int),
     "ms_solver_peer_error": ([vp, C.POINTER(C.c_uint32), vp], C.c_int),
     "ms_mccfr_inplace_many": ([vp, i32, i64, u64, u64, vp, vp, vp, vp], C.c_int),
     "ms_solver_counters": ([vp, C.POINTER(u64), C.c_int, vp], C.c_int),

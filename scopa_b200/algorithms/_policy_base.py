@@ -12,3 +12,15 @@ def root_of(game):
     """(packed root words, hand_order) of game.new_initial_state() for the device solver."""
     state = game.new_initial_state()
     return state.env.packed()
+
+
+_MAX_STEPS_FIELD = 0x1F << 19      # codec.pack_state: bits 19-23 of the meta word hold the env's max_steps
+
+
+def root_id(words, order):
+    """Identity of a packed state for "is this the solver's root?" checks.  The step limit is not part of it: a
+    `clone()` of a fresh root carries max_steps = 16 where the original has 8 (the reference's clone quirk,
+    openspiel_mini_scopa.py:108), and both are the same root to _cfr_recursive / _external_sampling_cfr."""
+    w = [int(x) & 0xFFFFFFFF for x in words]
+    w[3] &= ~_MAX_STEPS_FIELD
+    return tuple(w), int(order)

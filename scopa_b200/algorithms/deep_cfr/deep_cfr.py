@@ -21,7 +21,7 @@ import torch.nn.functional as F
 import torch.optim as optim
 
 from ... import codec, sdcfr
-from .._policy_base import root_of
+from .._policy_base import root_id, root_of
 from .nets import FlexibleNet, positive_regret_policy
 
 HIDDEN = [128, 64]
@@ -307,7 +307,8 @@ class DeepCFR:
             "eval_scopas": [],
         }
         words, order = root_of(game)
-        self._root = (tuple(int(w) for w in words), int(order))
+        self._root = root_id(words, order)
+        self._root_state = (tuple(int(w) for w in words), int(order))
         self._traverser = sdcfr.Traverser(words, order, device=device)
         self._root_state = None
 
@@ -340,7 +341,7 @@ class DeepCFR:
         if state.is_terminal():
             return float(state.rewards()[player])
         words, order = state.env.packed()
-        if (tuple(int(w) for w in words), int(order)) != self._root:
+        if root_id(words, order) != self._root:
             raise NotImplementedError("_external_sampling_cfr on a non-root state")
         n = self.traversals_per_iteration
         blobs = [a.blob() for a in self.advantage_nets]
@@ -441,7 +442,7 @@ class DeepCFR:
             return self._pol_in
         from ...solver import Solver
         if getattr(self, "_solver", None) is None:
-            self._solver = Solver(self._root[0], self._root[1], device=self.device)
+            self._solver = Solver(self._root_state[0], self._root_state[1], device=self.device)
         sv = self._solver
         st = sv.static_table()
         S = sv.n_slots

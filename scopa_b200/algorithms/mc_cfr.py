@@ -70,6 +70,8 @@ class MCCFRTrainer:
         return self._map
 
     def _refresh(self):
+        if self.peer_memory and self.solver.peer_error():
+            raise RuntimeError("peer-memory exchange failed: a rank did not arrive (see ms_solver_peer_error)")
         st = self.solver.static_table()
         reg, strat, touched = self.solver.export()
         m = {}
@@ -100,6 +102,10 @@ class MCCFRTrainer:
             B = int(self.batch)
             lo, n = shard_bounds(B, rank, world)
             for _ in range(iterations):
+                if self.peer_memory and self.mode == 0:     # traversals + exchange + apply: one launch per iteration
+                    self.solver.mccfr_batch_peers(2, n, philox_seed=self.seed, first_trav=self._iter * B + lo)
+                    self._iter += 1
+                    continue
                 self.solver.mccfr_batch(2, n, philox_seed=self.seed, first_trav=self._iter * B + lo, mode=self.mode)
                 if self.peer_memory:
                     self.solver.apply_peers()

@@ -12,7 +12,7 @@ import numpy as np
 
 from ..solver import Solver
 from ._evaluate import evaluate_agent  # noqa: F401  (re-exported, as in the reference module)
-from ._policy_base import Policy, root_of
+from ._policy_base import Policy, root_id, root_of
 
 
 def _uniform(n):
@@ -55,7 +55,7 @@ class CFRTrainer:
     def __init__(self, game, device="cuda"):
         self.game = game
         words, order = root_of(game)
-        self._root = (tuple(int(w) for w in words), int(order))
+        self._root = root_id(words, order)
         self.solver = Solver(words, order, device=device)
         self._view, self._stale = {}, False
 
@@ -84,7 +84,7 @@ class CFRTrainer:
         if state.is_terminal():
             return state.rewards()[traversing_player]
         words, order = state.env.packed()
-        if (tuple(int(w) for w in words), int(order)) != self._root:
+        if root_id(words, order) != self._root:
             raise NotImplementedError("_cfr_recursive on a non-root state: build a CFRTrainer for a game rooted there")
         self._stale = True
         return self.solver.cfr_traverse(traversing_player, reach_p0, reach_p1)

@@ -770,37 +770,35 @@ __global__ void __launch_bounds__(THREADS, 1) mccfr_tree_kernel(SolverDev d, int
 // One thread = one traversal at a time, recursion state in registers; the CTA's working set (node records with
 // integer cdf thresholds, sigma and 1/sigma, the private delta tables) is rebuilt in shared memory from the table at
 // the start of every launch -- the frozen strategy of the batch.
-struct StaticDims { int n6, n7, S2, s_hot, ncopy; };
-
-__global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
-                                                                         unsigned long long first_trav, StaticDims dm) {
-    MS_DYN_SMEM(smem_raw);
+__device__ __forceinline__ void mccfr_static_body(const SolverDev& d, int player, long long n_trav, uint2 pkey,
+                                                  unsigned long long first_trav, const StaticDims& dm, unsigned char* smem_raw) {
     const int S = d.n_slots, T = STATIC_THREADS, tid = threadIdx.x, lane = tid & 31;
     uint4* node = (uint4*)smem_raw;
     double* sig = (double*)(node + dm.n6);
-    double* rsig = sig + 4 * S;
-    double* hot = rsig + 4 * S;
-    double* dreg = hot + 128 * (size_t)dm.s_hot;
-    uint32_t* endrec = (uint32_t*)(dreg + (size_t)dm.ncopy * 4 * dm.S2);
+    double* rsig = sig + 4 * dm.S2;
+    double* acc = rsig + 4 * dm.S2;
+    uint32_t* endrec = (uint32_t*)(acc + 32 * (size_t)dm.n_acc);
     uint32_t* dcnt = endrec + (dm.n7 - dm.n6);
     uint8_t* touched = (uint8_t*)(dcnt + S);
     int* s_need = (int*)(((uintptr_t)(touched + S) + 15) & ~(uintptr_t)15);
-    uint32_t* thr = (uint32_t*)dreg;        // [S2][3] staging of the per-slot thresholds (the delta tables are zeroed afterwards)
+    uint32_t* thr = (uint32_t*)acc;         // [S2][3] staging of the per-slot thresholds (the accumulators are zeroed afterwards)
 
     if (tid == 0) *s_need = 0;
     __syncthreads();
     for (int s = tid; s < S; s += T) {
-        double reg[4], sg[4], cd[4];
-        const int n = d.slot_nlegal[s];
-        for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
-        regret_match(reg, n, sg);
-        strategy_cdf(sg, n, cd);
-        for (int i = 0; i < 4; i++) {
-            sig[4 * s + i] = sg[i];
-            rsig[4 * s + i] = sg[i] > 0.0 ? __ddiv_rn(1.0, sg[i]) : 0.0;
-        }
-        if (s < dm.S2)      // T_i = ceil(cdf_i * 2^31) (exact scaling; cdf_i in [0, 1]); the last entry of a row is never read
+        if (s < dm.S2) {
+            double reg[4], sg[4], cd[4];
+            const int n = d.slot_nlegal[s];
+            for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
+            regret_match(reg, n, sg);
+            strategy_cdf(sg, n, cd);
+            for (int i = 0; i < 4; i++) {
+                sig[4 * s + i] = sg[i];
+                rsig[4 * s + i] = sg[i] > 0.0 ? __ddiv_rn(1.0, sg[i]) : 0.0;
+            }
+            // T_i = ceil(cdf_i * 2^31) (exact scaling; cdf_i in [0, 1]); the last entry of a row is never read
             for (int i = 0; i < 3; i++) thr[3 * s + i] = (i + 1 < n) ? (uint32_t)ceil(cd[i] * 2147483648.0) : 0x80000000u;
+        }
         dcnt[s] = 0u; touched[s] = 0;
         if (!d.touched[s]) *s_need = 1;
     }
@@ -814,13 +812,12 @@ __global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_kernel(SolverD
         }
     }
     __syncthreads();
-    for (int i = tid; i < dm.ncopy * 4 * dm.S2; i += T) dreg[i] = 0.0;
-    for (int i = tid; i < 128 * dm.s_hot; i += T) hot[i] = 0.0;
+    for (int i = tid; i < 32 * dm.n_acc; i += T) acc[i] = 0.0;
     __syncthreads();
 
     StaticShared c;
     c.node = node; c.endrec = endrec - dm.n6; c.sig = sig; c.rsig = rsig;
-    c.hot = hot + lane; c.dreg = dreg + (size_t)(lane & (dm.ncopy - 1)) * 4 * dm.S2;
+    c.acc = acc + lane;
     c.dcnt = dcnt; c.touched = touched; c.need_touch = *s_need != 0;
     c.key = pkey; c.blk = make_uint4(0u, 0u, 0u, 0u);
     unsigned long long v0, u0, e0, v1, u1, e1;
@@ -836,16 +833,31 @@ __global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_kernel(SolverD
             const int tp = j ^ flip;
             if (player < 2 && tp != player) continue;
             c.nd = 0u; c.tag = MS_TAG_MCCF_SEQ + (uint32_t)tp;
-            if (tp == 0) { StaticWalk<0, 0>::run(0u, 1.0, c); nu += u0; nv += v0; ns += e0; }
-            else { StaticWalk<0, 1>::run(0u, 1.0, c); nu += u1; nv += v1; ns += e1; }
+            if (tp == 0) { StaticWalk<0, 0>::run(0u, 1.0, c, dm); nu += u0; nv += v0; ns += e0; }
+            else { StaticWalk<0, 1>::run(0u, 1.0, c, dm); nu += u1; nv += v1; ns += e1; }
         }
     }
     __syncthreads();
-    for (int i = tid; i < 4 * dm.S2; i += T) {
-        double v = 0.0;
-        if (i < 4 * dm.s_hot) { for (int l = 0; l < 32; l++) v = __dadd_rn(v, hot[(size_t)i * 32 + l]); }
-        else for (int cpy = 0; cpy < dm.ncopy; cpy++) v = __dadd_rn(v, dreg[(size_t)cpy * 4 * dm.S2 + i]);
-        if (v != 0.0) atomicAdd(&d.delta[i], v);
+    // flush: per infoset, D_i = sum of its lane columns; delta_a = D_a - sum_j sigma_j D_j (D_last = 0)
+    for (int s = tid; s < dm.S2; s += T) {
+        int p = 0, sb0 = 0, cnt = 1, ab = 0;
+#pragma unroll
+        for (int q = 0; q < 6; q++)         // (compile-time indices only: dm stays in the constant bank)
+            if (s >= dm.sb[q] && s < dm.sb[q + 1]) { p = q; sb0 = dm.sb[q]; cnt = dm.sb[q + 1] - dm.sb[q]; ab = dm.accbase[q]; }
+        const int nl = 4 - p / 2;
+        double D0 = 0.0, D1 = 0.0, D2 = 0.0, sum = 0.0;
+        for (int i = 0; i < nl - 1; i++) {
+            const double* col = acc + 32 * (size_t)(ab + i * cnt + s - sb0);
+            double t = 0.0;
+            for (int l = 0; l < 32; l++) t = __dadd_rn(t, col[l]);
+            if (i == 0) D0 = t; else if (i == 1) D1 = t; else D2 = t;
+            sum = __dadd_rn(sum, __dmul_rn(sig[4 * s + i], t));
+        }
+        for (int a = 0; a < nl; a++) {
+            const double Da = a == 0 ? D0 : (a == 1 ? D1 : D2);
+            const double v = a < nl - 1 ? __dadd_rn(Da, -sum) : -sum;
+            if (v != 0.0) atomicAdd(&d.delta[4 * s + a], v);
+        }
     }
     for (int s = tid; s < S; s += T) {
         if (dcnt[s]) atomicAdd(&d.delta[4 * S + s], (double)dcnt[s]);
@@ -857,6 +869,12 @@ __global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_kernel(SolverD
         ns += __shfl_down_sync(0xffffffffu, ns, off);
     }
     if ((tid & 31) == 0) { atomicAdd(&d.counters[0], nu); atomicAdd(&d.counters[1], nv); atomicAdd(&d.counters[2], ns); }
+}
+
+__global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
+                                                                         unsigned long long first_trav, StaticDims dm) {
+    MS_DYN_SMEM(smem_raw);
+    mccfr_static_body(d, player, n_trav, pkey, first_trav, dm, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1389,25 +1407,25 @@ __device__ __forceinline__ void peer_fence() { __threadfence_system(); }
 constexpr unsigned long long MS_PEER_TIMEOUT_NS = 2000000000ull;     // a peer that has not arrived after 2 s is given up on
 
 // err[0]: 0 = fine; otherwise (1 + the first peer that did not arrive) of the first failed exchange.  Once set, every
-// later exchange returns at once without touching the table (ms_mccfr_apply_peers reports MS_ERR_STATE).
-__global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d, PeerView pv, unsigned long long epoch,
-                                                                    unsigned int* err) {
-    MS_DYN_SMEM(smem_raw);                  // one int: dynamic, so that emulated ranks (blocks) do not share it
-    volatile int& s_bad = *(volatile int*)smem_raw;
+// later exchange returns at once without touching the table (ms_solver_peer_error reports MS_ERR_STATE).
+// One CTA (all its threads) runs this: as the whole of mccfr_apply_peers_kernel, or as the tail of the fused
+// mccfr_static_peers_kernel in the last CTA to finish its traversals.  `s_bad` is one int of shared memory.
+__device__ __forceinline__ void peers_exchange_cta(const SolverDev& d, const PeerView& pv, unsigned long long epoch, unsigned int* err,
+                                                   volatile int* s_bad) {
     const int tid = threadIdx.x, S = d.n_slots;
-    if (tid == 0) s_bad = (*(volatile unsigned int*)err != 0u) ? 1 : 0;
+    if (tid == 0) *s_bad = (*(volatile unsigned int*)err != 0u) ? 1 : 0;
     __syncthreads();
-    if (s_bad) return;
+    if (*s_bad) return;
     if (tid < pv.world) {
         peer_fence();
         peer_signal(pv.flags[tid] + pv.rank, epoch);
         const unsigned long long t0 = peer_clock_ns();
         while (peer_poll(pv.my_flags + tid) < epoch) {
-            if (peer_clock_ns() - t0 > MS_PEER_TIMEOUT_NS) { atomicCAS(err, 0u, 1u + (unsigned)tid); s_bad = 1; break; }
+            if (peer_clock_ns() - t0 > MS_PEER_TIMEOUT_NS) { atomicCAS(err, 0u, 1u + (unsigned)tid); *s_bad = 1; break; }
         }
     }
     __syncthreads();
-    if (s_bad) return;
+    if (*s_bad) return;
     for (int s = tid; s < S; s += blockDim.x) {
         double dv[4] = {0.0, 0.0, 0.0, 0.0}, cnt = 0.0, tch = 0.0;
         for (int r = 0; r < pv.world; r++) {
@@ -1429,6 +1447,38 @@ __global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d,
         if (tch != 0.0) d.touched[s] = 1;
     }
     for (int i = tid; i < 6 * S; i += blockDim.x) pv.zero_me[i] = 0.0;
+}
+
+__global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d, PeerView pv, unsigned long long epoch,
+                                                                    unsigned int* err) {
+    MS_DYN_SMEM(smem_raw);                  // one int: dynamic, so that emulated ranks (blocks) do not share it
+    peers_exchange_cta(d, pv, epoch, err, (volatile int*)smem_raw);
+}
+
+// The fused form (one launch per MCCFR iteration per GPU): the traversals of mccfr_static_kernel, and in the LAST CTA to
+// finish them (a ticket counter in global memory) the cross-GPU exchange + table update of peers_exchange_cta.  The
+// deltas of a batch are complete only when its last traversal is, so the exchange cannot start earlier; what the fusion
+// removes is the launch gap and the second kernel's ramp between the two.  Each CTA's delta flush is a set of device-scope
+// atomics followed by __threadfence() and the ticket increment; the last CTA observes every ticket, fences at system
+// scope (peers_exchange_cta) and only then signals its peers, so a peer that sees the flag sees the deltas.
+__global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_peers_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
+                                                                               unsigned long long first_trav, StaticDims dm, PeerView pv,
+                                                                               unsigned long long epoch, unsigned int* err,
+                                                                               unsigned int* ticket) {
+    MS_DYN_SMEM(smem_raw);
+    mccfr_static_body(d, player, n_trav, pkey, first_trav, dm, smem_raw);
+    volatile int* s_flag = (volatile int*)smem_raw;          // the traversal working set is dead from here on
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_flag[1] = (t == gridDim.x - 1u) ? 1 : 0;
+        if (s_flag[1]) *ticket = 0u;                         // ready for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (!s_flag[1]) return;
+    __threadfence();
+    peers_exchange_cta(d, pv, epoch, err, s_flag);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1757,9 +1807,8 @@ int solver_build(ms_solver* sv) {
             }
         sv->static_shape = ok;
         if (ok) {
-            sv->sdm.n6 = sv->level_begin[6]; sv->sdm.n7 = sv->level_begin[7];
-            sv->sdm.S2 = sv->slot_level_begin[6]; sv->sdm.s_hot = sv->slot_level_begin[STATIC_HOT_PLIES];
-            sv->sdm.ncopy = 1;
+            sv->sdm = static_dims_from(sv->level_begin.data(), sv->slot_level_begin.data());
+            if (mccfr_static_smem(S, sv->sdm) + 16 > 227 * 1024) sv->static_shape = false;
         }
     }
 
@@ -2020,19 +2069,13 @@ static int launch_mccfr_tree(ms_solver* s, int threads, int ncopy, int32_t playe
 }
 
 static int launch_mccfr_static(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
-    StaticDims dm = s->sdm;
-    for (int ncopy : {8, 4, 2, 1}) {
-        dm.ncopy = ncopy;
-        const size_t smem = mccfr_static_smem(s->n_slots, dm.S2, dm.s_hot, dm.n6, dm.n7, ncopy) + 16;
-        if (smem > 227 * 1024) continue;
-        MS_CUDA(cudaFuncSetAttribute(mccfr_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mccfr_static_kernel<<<grid_for(n_trav, STATIC_THREADS, 1), STATIC_THREADS, smem, (cudaStream_t)stream>>>(
-            s->dev, player, (long long)n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
-            (unsigned long long)first_trav, dm);
-        MS_LAUNCH_CHECK();
-        return MS_OK;
-    }
-    return fail(MS_ERR_CAPACITY, "MCCFR static-shape working set exceeds shared memory");
+    const size_t smem = mccfr_static_smem(s->n_slots, s->sdm) + 16;
+    MS_CUDA(cudaFuncSetAttribute(mccfr_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mccfr_static_kernel<<<grid_for(n_trav, STATIC_THREADS, 1), STATIC_THREADS, smem, (cudaStream_t)stream>>>(
+        s->dev, player, (long long)n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
+        (unsigned long long)first_trav, s->sdm);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
 }
 
 // the generic tree-walking kernel (any root whose tree fits): mode 4, and mode 0 on trees without the fresh-deal shape
@@ -2127,9 +2170,7 @@ int ms_solver_ipc_attach(ms_solver* s, int32_t rank, int32_t world, const void* 
     return MS_OK;
 }
 
-int ms_mccfr_apply_peers(ms_solver* s, void* stream) {
-    int rc = check_dev(s); if (rc) return rc;
-    if (!s->attached) return fail(MS_ERR_STATE, "ms_mccfr_apply_peers: call ms_solver_ipc_attach first");
+static PeerView peer_view(ms_solver* s) {
     PeerView pv{};
     for (int r = 0; r < s->world; r++) {
         pv.delta[r] = (const double*)((char*)s->peer_base[r] + s->peer_off[r][s->parity]);
@@ -2138,11 +2179,42 @@ int ms_mccfr_apply_peers(ms_solver* s, void* stream) {
     pv.my_flags = s->flags;
     pv.zero_me = s->delta_buf[s->parity ^ 1];
     pv.rank = s->rank; pv.world = s->world;
+    return pv;
+}
+
+static void peer_advance(ms_solver* s) {
+    s->parity ^= 1;                       // the next batch accumulates into the other buffer
+    s->dev.delta = s->delta_buf[s->parity];
+}
+
+int ms_mccfr_apply_peers(ms_solver* s, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (!s->attached) return fail(MS_ERR_STATE, "ms_mccfr_apply_peers: call ms_solver_ipc_attach first");
+    const PeerView pv = peer_view(s);
     s->epoch += 1;
     mccfr_apply_peers_kernel<<<1, 1024, 16, (cudaStream_t)stream>>>(s->dev, pv, s->epoch, s->peer_err);
     MS_LAUNCH_CHECK();
-    s->parity ^= 1;                       // the next batch accumulates into the other buffer
-    s->dev.delta = s->delta_buf[s->parity];
+    peer_advance(s);
+    return MS_OK;
+}
+
+int ms_mccfr_batch_peers(ms_solver* s, int32_t player, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* stream) {
+    int rc = check_dev(s); if (rc) return rc;
+    if (!s->attached) return fail(MS_ERR_STATE, "ms_mccfr_batch_peers: call ms_solver_ipc_attach first");
+    if (player < 0 || player > 2 || n_trav < 0) return fail(MS_ERR_ARG, "ms_mccfr_batch_peers: bad argument");
+    if (!s->static_shape) {               // other roots: the generic traversal kernel, then the exchange kernel
+        if (n_trav > 0) { rc = launch_mccfr_generic(s, player, n_trav, philox_seed, first_trav, stream); if (rc) return rc; }
+        return ms_mccfr_apply_peers(s, stream);
+    }
+    const size_t smem = mccfr_static_smem(s->n_slots, s->sdm) + 16;
+    const PeerView pv = peer_view(s);
+    s->epoch += 1;
+    MS_CUDA(cudaFuncSetAttribute(mccfr_static_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mccfr_static_peers_kernel<<<grid_for(n_trav > 0 ? n_trav : 1, STATIC_THREADS, 1), STATIC_THREADS, smem, (cudaStream_t)stream>>>(
+        s->dev, player, (long long)n_trav, make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)),
+        (unsigned long long)first_trav, s->sdm, pv, s->epoch, s->peer_err, s->peer_err + 1);
+    MS_LAUNCH_CHECK();
+    peer_advance(s);
     return MS_OK;
 }
 

@@ -20,9 +20,7 @@
 //   * the last two plies are forced: a ply-6 node's record carries both infoset slots and the leaf's reward;
 //   * random numbers: Philox4x32-10 keyed by (traversal id, draw index / 4), four 31-bit uniforms per block, consumed
 //     in visiting order ("sequential stream"; oracle: ora_mccfr_batch_seq);
-//   * regret deltas go to shared-memory tables private to the CTA: lane-private rows for the infosets of the first
-//     HOT_LEVELS plies (every lane of a warp sits on those at the same instant: a shared fp64 atomicAdd is a
-//     compare-and-swap loop and the lanes would retry against each other), NC lane-interleaved copies for the rest;
+//   * regret deltas go to lane-private accumulator columns in shared memory, nl - 1 per infoset (see StaticShared);
 //   * visit counters are arithmetic (the shape is static), not per-visit increments.
 // Semantics are those of mccfr_tree_kernel<false> (same estimator, same frozen-sigma batch, same delta layout); the
 // random stream differs, so the two agree statistically, and each agrees with its own oracle function to 1e-9.
@@ -39,8 +37,6 @@ constexpr int STATIC_THREADS = 1024;
 constexpr int STATIC_PLIES = 8;          // plies of a fresh deal
 constexpr int STATIC_DECIDED = 6;        // plies with more than one legal action
 
-constexpr int STATIC_HOT_PLIES = 3;      // infosets of plies 0..2 (at most 1 + 4 + 16) get lane-private delta rows
-
 // visits / updates / tree edges of ONE traversal by traverser `tp`, counted as the generic kernels count them (and as the
 // reference's recursion visits them): a traverser node with nl actions makes nl + 1 recursive calls; the forced last
 // plies are visited by both calls of the forced traverser node but their edges are played once.
@@ -55,13 +51,40 @@ __host__ __device__ inline void static_shape_counts(int tp, unsigned long long& 
     visits = V; updates = U; edges = E;
 }
 
+// Sizes and offsets of one deal's static layout (host: static_dims_from; passed to the kernel by value).
+//   n6 / n7: first node id of ply 6 / ply 7 (nodes are numbered ply by ply); sb[p]: first infoset slot of ply p (slots
+//   are numbered ply by ply too: breadth-first first occurrence), sb[6] = S2 = number of infosets with more than one
+//   action; accbase[p]: first accumulator row of ply p; n_acc rows in all.
+struct StaticDims { int n6, n7, S2, n_acc; int sb[7]; int accbase[6]; };
+
+__host__ __device__ inline StaticDims static_dims_from(const int* level_begin, const int* slot_level_begin) {
+    StaticDims dm{};
+    dm.n6 = level_begin[6]; dm.n7 = level_begin[7];
+    for (int p = 0; p <= 6; p++) dm.sb[p] = slot_level_begin[p];
+    dm.S2 = dm.sb[6];
+    int a = 0;
+    for (int p = 0; p < 6; p++) { dm.accbase[p] = a; a += (3 - p / 2) * (dm.sb[p + 1] - dm.sb[p]); }   // nl - 1 rows per infoset
+    dm.n_acc = a;
+    return dm;
+}
+
+// Regret deltas without intra-warp collisions and with nl - 1 accumulators per infoset.
+//   * The regret delta of a visit is w * (cfv_a - v) with v = sum_j sigma_j cfv_j, and sigma is FROZEN for the batch.
+//     With e_i = cfv_i - cfv_last (small exact half-integers) the batch total is  delta_a = D_a - sum_j sigma_j D_j,
+//     D_i = sum over visits of w * e_i  (D_last = 0): a visit adds nl - 1 numbers and needs no sigma at all; the
+//     sigma-weighted part is applied once per infoset when the CTA flushes (mccfr_static_body).
+//   * A shared-memory fp64 atomicAdd is a compare-and-swap loop, and ncu (profiles/README.md, r02b) measured 27 shared
+//     wavefronts per executed CAS and 2.7 executions per add when the lanes of a warp -- which walk in lock-step and sit
+//     on a handful of infosets -- share accumulator copies: 71 % of the kernel's shared-memory traffic.  Here every
+//     accumulator row is [32 lanes] wide and a lane only ever touches its own column: no two lanes of a warp can
+//     collide, the access is conflict-free (consecutive doubles), and the CAS only arbitrates between the warps of the
+//     CTA (rare).  575 rows x 256 B at most (a deal has at most 1 + 4 + 16 + 48 + 144 + 288 such infosets).
 struct StaticShared {
     const uint4* node;        // [n6] plies 0..5: {thr0, thr1, thr2, first child | slot << 12}, thr_i = ceil(cdf_i * 2^31)
     const uint32_t* endrec;   // ply-6 nodes, indexed by NODE id (pointer pre-offset): slot6 | slot7 << 11 | (2 * reward0 + 16) << 22
-    const double* sig;        // [S][4] frozen strategies
-    const double* rsig;       // [S][4] 1 / sigma (0 where sigma == 0: the reference's weight is 0 when the sampling prob is 0)
-    double* hot;              // [s_hot][4][32] regret deltas of the infosets of plies < STATIC_HOT_PLIES, pre-offset by lane
-    double* dreg;             // [S2][4] regret deltas of the other infosets with more than one action: this lane's copy
+    const double* sig;        // [S2][4] frozen strategies
+    const double* rsig;       // [S2][4] 1 / sigma (0 where sigma == 0: the reference's weight is 0 when the sampling prob is 0)
+    double* acc;              // [n_acc][32] D accumulators, pre-offset by lane
     uint32_t* dcnt;           // [S] update counts (strategy delta = count * sigma)
     uint8_t* touched;         // [S]
     bool need_touch;
@@ -98,13 +121,13 @@ struct StaticWalk {
     static constexpr bool MINE = (PLY & 1) == TP;
 
     // -> 2 * (reward of the traverser) of the sampled line below `node`
-    static __device__ __forceinline__ int run(uint32_t node, double w, StaticShared& c) {
+    static __device__ __forceinline__ int run(uint32_t node, double w, StaticShared& c, const StaticDims& dm) {
         const uint4 rec = c.node[node];
         const uint32_t slot = rec.w >> 12, cb = rec.w & 0xFFFu;
         if (c.need_touch) c.touched[slot] = 1;       // node created on first touch, for both players (mc_cfr.py:52)
         const int ai = static_pick<NL>(rec, static_draw(c));
         if (!MINE) {                                 // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
-            return StaticWalk<PLY + 1, TP>::run(cb + (uint32_t)ai, __dmul_rn(w, c.sig[4 * slot + ai]), c);
+            return StaticWalk<PLY + 1, TP>::run(cb + (uint32_t)ai, __dmul_rn(w, c.sig[4 * slot + ai]), c, dm);
         }
         // traverser: the sampled action first (:58-67), then every action with a fresh sampled continuation (:71-78)
         uint32_t cfvb = 0u;
@@ -112,22 +135,21 @@ struct StaticWalk {
 #pragma unroll 1
         for (int j = -1; j < NL; j++) {
             const int a = j < 0 ? ai : j;
-            const int r = StaticWalk<PLY + 1, TP>::run(cb + (uint32_t)a, __dmul_rn(w, c.rsig[4 * slot + a]), c);
+            const int r = StaticWalk<PLY + 1, TP>::run(cb + (uint32_t)a, __dmul_rn(w, c.rsig[4 * slot + a]), c, dm);
             if (j < 0) util = r;
             else cfvb |= ((uint32_t)r & 0xFFu) << (8 * j);
         }
-        // regret / strategy deltas (:79-84): weight = reach_opp / sample_own = w; strategy delta = count * sigma
-        double cfv[NL], v = 0.0;
+        // regret deltas (:79-84), weight = reach_opp / sample_own = w: D_i += w * (cfv_i - cfv_last), see StaticShared;
+        // strategy delta = count * sigma
+        const int last = (int)(int8_t)((cfvb >> (8 * (NL - 1))) & 0xFFu);
+        double* row = c.acc + 32 * (dm.accbase[PLY] + (int)slot - dm.sb[PLY]);
+        const int plane = 32 * (dm.sb[PLY + 1] - dm.sb[PLY]);
 #pragma unroll
-        for (int i = 0; i < NL; i++) {
-            cfv[i] = 0.5 * (double)(int)(int8_t)((cfvb >> (8 * i)) & 0xFFu);
-            v = __dadd_rn(v, __dmul_rn(c.sig[4 * slot + i], cfv[i]));
+        for (int i = 0; i < NL - 1; i++) {
+            const int e2 = (int)(int8_t)((cfvb >> (8 * i)) & 0xFFu) - last;          // 2 * (cfv_i - cfv_last)
+            const double val = __dmul_rn(w, 0.5 * (double)e2);
+            if (val != 0.0) atomicAdd(row + i * plane, val);
         }
-        constexpr bool HOT = PLY < STATIC_HOT_PLIES;
-        double* row = HOT ? c.hot + 128 * slot : c.dreg + 4 * slot;
-        constexpr int stride = HOT ? 32 : 1;
-#pragma unroll
-        for (int i = 0; i < NL; i++) atomicAdd(row + i * stride, __dmul_rn(w, __dadd_rn(cfv[i], -v)));
         atomicAdd(&c.dcnt[slot], 1u);
         return util;
     }
@@ -138,7 +160,7 @@ struct StaticWalk {
 // arithmetic visit counters).  Regret delta = w * (cfv - v) = 0 exactly; strategy delta = 1 * [1.0].
 template <int TP>
 struct StaticWalk<6, TP> {
-    static __device__ __forceinline__ int run(uint32_t node, double, StaticShared& c) {
+    static __device__ __forceinline__ int run(uint32_t node, double, StaticShared& c, const StaticDims&) {
         const uint32_t e = c.endrec[node];
         const uint32_t slot6 = e & 0x7FFu, slot7 = (e >> 11) & 0x7FFu;
         if (c.need_touch) { c.touched[slot6] = 1; c.touched[slot7] = 1; }
@@ -148,11 +170,9 @@ struct StaticWalk<6, TP> {
     }
 };
 
-// n6 / n7: first node id of ply 6 / ply 7 (nodes are numbered ply by ply); S2: infosets of plies 0..5 (the slots are
-// numbered ply by ply too, so these are slots [0, S2)); s_hot: infosets of plies < STATIC_HOT_PLIES
-__host__ __device__ inline size_t mccfr_static_smem(int S, int S2, int s_hot, int n6, int n7, int ncopy) {
-    return 16 * (size_t)n6 + sizeof(double) * 8 * (size_t)S + sizeof(double) * 128 * (size_t)s_hot +
-           sizeof(double) * 4 * (size_t)S2 * ncopy + 4 * (size_t)(n7 - n6) + 4 * (size_t)S + (size_t)S + 64;
+__host__ __device__ inline size_t mccfr_static_smem(int S, const StaticDims& dm) {
+    return 16 * (size_t)dm.n6 + sizeof(double) * 8 * (size_t)dm.S2 + sizeof(double) * 32 * (size_t)dm.n_acc +
+           4 * (size_t)(dm.n7 - dm.n6) + 4 * (size_t)S + (size_t)S + 64;
 }
 
 }  // namespace ms

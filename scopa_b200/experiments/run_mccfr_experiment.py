@@ -19,9 +19,9 @@ from ..envs import openspiel_mini_scopa  # noqa: F401  (registers the game)
 from ..algorithms.mc_cfr import MCCFRTrainer
 
 
-def _evaluate(solver, n, seed):
+def _evaluate(solver, n, seed, policy_kind=1):
     """avg reward of the trained seat, avg scopas trained / random (evaluate_policy_quick, :24-61)."""
-    tab, uni = solver.average_policy(1), solver.uniform_policy()
+    tab, uni = solver.average_policy(policy_kind), solver.uniform_policy()
     n0 = int(np.ceil(n / 2))
     r_a, s_a = solver.evaluate(tab, uni, n0, philox_seed=seed, first_game=0)
     r_b, s_b = solver.evaluate(uni, tab, n - n0, philox_seed=seed, first_game=n0)
@@ -86,10 +86,15 @@ def main():
     ap.add_argument("--final-episodes", type=int, default=5000)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default="MiniScopa_MCCFR_data.json")
+    ap.add_argument("--out-dir", default=None,
+                    help="also write every file ExperimentTracker.save writes (pickle, JSON, per-run and statistics CSVs) here")
     a = ap.parse_args()
     data = run_experiments(a.runs, a.iterations, a.eval_interval, a.final_episodes, a.seed)
     with open(a.out, "w") as f:
         json.dump(data, f, indent=2)
+    if a.out_dir:
+        from . import tracker_output
+        tracker_output.save("MiniScopa_MCCFR", "MC-CFR", data["runs"], a.out_dir)
     fm = data["statistics"]["final_metrics"]
     print(f"final reward vs random: {fm['reward_mean']:.4f} +- {fm['reward_std']:.4f}  "
           f"(reference's shipped file: 1.1545 +- 0.1163)")

@@ -199,6 +199,12 @@ class Solver:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_mccfr_apply_peers(self.h, self._stream()))
 
+    def mccfr_batch_peers(self, player, n_trav, philox_seed=0, first_trav=0):
+        """mccfr_batch + apply_peers as ONE launch (the last CTA to finish its traversals does the exchange)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_mccfr_batch_peers(self.h, int(player), int(n_trav), int(philox_seed), int(first_trav),
+                                                     self._stream()))
+
     def peer_error(self):
         """0, or 1 + the rank that did not arrive at a peer exchange within its time limit (synchronises)."""
         err = C.c_uint32(0)

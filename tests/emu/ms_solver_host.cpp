@@ -29,6 +29,7 @@ static inline unsigned long long peer_clock_ns() {
 }
 static inline double peer_load(const double* p) { return *(const volatile double*)p; }
 static inline void peer_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned val) {
     __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
     return cmp;
@@ -59,6 +60,12 @@ struct ManyRunArgs { SolverDev d; ManyRuns m; long long iters; unsigned long lon
 void inplace_many_entry(ManyRunArgs a) { mccfr_inplace_many_kernel(a.d, a.m, a.iters, a.seed0, a.first_iter, a.nframes, a.warps); }
 struct PeersArgs { SolverDev d[2]; PeerView pv[2]; unsigned long long epoch; unsigned int* err[2]; };
 void peers_entry(PeersArgs a) { const unsigned r = emu_block_slot; mccfr_apply_peers_kernel(a.d[r], a.pv[r], a.epoch, a.err[r]); }
+struct FusedArgs { SolverDev d[2]; PeerView pv[2]; unsigned int* err[2]; unsigned int* ticket[2]; unsigned long long epoch, first_trav[2];
+                   long long n_trav; uint2 key; StaticDims dm; int force_rank; };
+void fused_entry(FusedArgs a) {
+    const unsigned r = a.force_rank >= 0 ? (unsigned)a.force_rank : emu_block_slot;
+    mccfr_static_peers_kernel(a.d[r], 2, a.n_trav, a.key, a.first_trav[r], a.dm, a.pv[r], a.epoch, a.err[r], a.ticket[r]);
+}
 void tree_entry(BatchArgs a) { mccfr_tree_kernel<TREE_THREADS>(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes, a.ncopy); }
 void restep_entry(BatchArgs a) { mccfr_batch_kernel(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes); }
 void es_tree_entry(BatchArgs a) { mccfr_es_tree_kernel<TREE_THREADS>(a.d, a.player, a.n_trav, a.key, a.first_trav, a.nframes, a.ncopy); }
@@ -255,9 +262,8 @@ static bool host_static_dims(StaticDims& dm) {
             const int want = l < STATIC_PLIES ? 4 - l / 2 : 0;
             if (H.nchild[v] != want || (want && (int)((H.state[v].w >> 17) & 1u) != (l & 1))) return false;
         }
-    dm.n6 = H.level_begin[6]; dm.n7 = H.level_begin[7]; dm.S2 = H.slot_level_begin[6]; dm.s_hot = H.slot_level_begin[STATIC_HOT_PLIES];
-    dm.ncopy = 1;
-    return true;
+    dm = static_dims_from(H.level_begin.data(), H.slot_level_begin.data());
+    return mccfr_static_smem(H.S, dm) + 16 <= 227 * 1024;
 }
 
 // ms_mccfr_batch_mode: 0 = mccfr_static_kernel on a fresh deal's tree (the headline kernel; mccfr_tree_kernel otherwise),
@@ -269,12 +275,7 @@ int host_mccfr_batch(int mode, int player, long long n_trav, unsigned long long 
     StaticDims dm{};
     if (mode == 0 && host_static_dims(dm)) {
         StaticArgs sa{H.dev, player, n_trav, a.key, first_trav, dm};
-        for (int ncopy : {8, 4, 2, 1}) {
-            if (mccfr_static_smem(H.S, dm.S2, dm.s_hot, dm.n6, dm.n7, ncopy) + 16 > 227 * 1024) continue;
-            sa.dm.ncopy = ncopy;
-            return emu_launch_grid(static_entry, sa, grid(STATIC_THREADS), STATIC_THREADS);
-        }
-        return -4;
+        return emu_launch_grid(static_entry, sa, grid(STATIC_THREADS), STATIC_THREADS);
     }
     if (mode == 0 || mode == 4 || mode == 1) {
         a.nframes = mode != 1 ? H.nframes_tree : H.nframes_es;
@@ -343,6 +344,46 @@ int host_apply_peers(double* regret1, double* strategy1, uint8_t* touched1, doub
     if (!g_err[0][0]) { std::fill(H.delta.begin(), H.delta.end(), 0.0); if (!absent) std::fill(delta1, delta1 + n, 0.0); }
     return (int)g_err[0][0];
 }
+// ms_mccfr_batch_peers (mccfr_static_peers_kernel: traversals + exchange in one launch) with two emulated ranks, G CTAs
+// each.  Rank r runs traversal ids [first_r, first_r + n_trav) with n_trav <= (G - 1) * 1024, so that CTAs 0 .. G-2 do all
+// the traversal work and can run one after another; the LAST CTA of each rank (no traversals left for it: it only takes
+// the final ticket and performs the exchange) runs concurrently with the other rank's last CTA.
+static unsigned int g_ticket[2][4];
+int host_batch_peers(double* regret1, double* strategy1, uint8_t* touched1, double* delta1, unsigned long long* counters1,
+                     long long n_trav, unsigned long long philox_seed, unsigned long long first0, unsigned long long first1, int G) {
+    StaticDims dm{};
+    if (!host_static_dims(dm) || G < 2 || n_trav > (long long)(G - 1) * STATIC_THREADS) return -5;
+    const size_t n = 6 * (size_t)H.S;
+    for (int r = 0; r < 2; r++) if (g_zero[r].size() != n) g_zero[r].assign(n, 0.0);
+    FusedArgs a{};
+    a.d[0] = H.dev;
+    a.d[1] = H.dev; a.d[1].regret = regret1; a.d[1].strategy = strategy1; a.d[1].touched = touched1; a.d[1].delta = delta1;
+    a.d[1].counters = counters1;
+    for (int r = 0; r < 2; r++) {
+        PeerView& pv = a.pv[r];
+        pv.delta[0] = H.delta.data(); pv.delta[1] = delta1;
+        pv.flags[0] = g_flags[0]; pv.flags[1] = g_flags[1];
+        pv.my_flags = g_flags[r]; pv.zero_me = g_zero[r].data(); pv.rank = r; pv.world = 2;
+        a.err[r] = g_err[r]; a.ticket[r] = g_ticket[r]; g_ticket[r][0] = 0;
+    }
+    a.first_trav[0] = first0; a.first_trav[1] = first1;
+    a.n_trav = n_trav; a.key = make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32));
+    a.epoch = ++g_epoch;
+    a.dm = dm;
+    gridDim = {(unsigned)G, 1, 1};
+    for (int r = 0; r < 2; r++) {
+        a.force_rank = r;
+        for (int b = 0; b + 1 < G; b++)
+            if (emu_run_blocks(fused_entry, a, (unsigned)b, 1, STATIC_THREADS)) return -1;
+    }
+    a.force_rank = -1;                    // the two last CTAs, one per rank (slot = rank), side by side
+    if (emu_run_blocks(fused_entry, a, (unsigned)(G - 1), 2, STATIC_THREADS)) return -1;
+    gridDim = {1, 1, 1};
+    if (g_ticket[0][0] != 0 || g_ticket[1][0] != 0) return -6;       // the last CTA re-arms the ticket
+    if (!g_err[0][0]) { std::fill(H.delta.begin(), H.delta.end(), 0.0); std::fill(delta1, delta1 + n, 0.0); }
+    return (int)g_err[0][0];
+}
+
 void host_peers_reset() { g_epoch = 0; for (int r = 0; r < 2; r++) { for (auto& f : g_flags[r]) f = 0; for (auto& e : g_err[r]) e = 0; } }
 
 // ms_cfr_iterate_many: cfr_many_kernel<<<n_jobs, 512, smem>>>, one CTA per job.  The shim holds one solver, so the jobs

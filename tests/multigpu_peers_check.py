@@ -24,19 +24,30 @@ def main():
     dev = torch.device("cuda", local)
     import datetime
     dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
-    a, b = Solver(seed=42, device=dev), Solver(seed=42, device=dev)
+    a, b, f = Solver(seed=42, device=dev), Solver(seed=42, device=dev), Solver(seed=42, device=dev)
     a.attach_peers()
+    f.attach_peers()
     B = 4096
     for it in range(6):
         first = (it * world + rank) * B
         a.mccfr_batch(2, B, philox_seed=5, first_trav=first)
         a.apply_peers()
+        f.mccfr_batch_peers(2, B, philox_seed=5, first_trav=first)      # the fused form: one launch
         b.mccfr_batch(2, B, philox_seed=5, first_trav=first)
         dist.all_reduce(b.delta_tensor())
         b.mccfr_apply()
     torch.cuda.synchronize()
-    assert a.peer_error() == 0
+    assert a.peer_error() == 0 and f.peer_error() == 0
+    rf, sf, tf = f.export()
     ra, sa, ta = a.export()
+    np.testing.assert_allclose(rf, ra, rtol=1e-9, atol=1e-9)      # (CTAs flush their deltas in a different order)
+    np.testing.assert_allclose(sf, sa, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(tf, ta)
+    tt = torch.from_numpy(np.concatenate([rf.ravel(), sf.ravel()])).to(dev)          # fused path: replicas bit-identical too
+    lo_, hi_ = tt.clone(), tt.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo_, hi_), "replicas diverged on the fused path"
     rb, sb, tb = b.export()
     np.testing.assert_allclose(ra, rb, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(sa, sb, rtol=1e-9, atol=1e-9)
@@ -77,6 +88,9 @@ def main():
         a.mccfr_batch(2, batch, philox_seed=6, first_trav=(i * world + rank) * batch)
         a.apply_peers()
 
+    def step_fused(batch, i):
+        f.mccfr_batch_peers(2, batch, philox_seed=6, first_trav=(i * world + rank) * batch)
+
     def step_nccl(batch, i):
         b.mccfr_batch(2, batch, philox_seed=6, first_trav=(i * world + rank) * batch)
         dist.all_reduce(b.delta_tensor())
@@ -88,7 +102,7 @@ def main():
 
     out = {}
     for batch in ((768, 113664) if os.environ.get("PEERS_CHECK_TIMING", "1") == "1" else ()):
-        out[batch] = {"peers_ms": timed(step_peers, batch), "nccl_ms": timed(step_nccl, batch), "no_exchange_ms": timed(step_none, batch)}
+        out[batch] = {"peers_ms": timed(step_peers, batch), "fused_ms": timed(step_fused, batch), "nccl_ms": timed(step_nccl, batch), "no_exchange_ms": timed(step_none, batch)}
     if rank == 0:
         print("PEERS_CHECK_OK world=%d" % world, out, flush=True)
     dist.barrier()

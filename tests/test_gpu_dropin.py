@@ -130,6 +130,16 @@ def test_cfr_trainer_drop_in():
         for i in range(game.num_players()):
             t2._cfr_recursive(game.new_initial_state(), i, 1.0, 1.0)
     assert np.array_equal(t2.info_set_map[g["keys"][0]].regret_sum, g["reg_2"][0, :4])
+    # a clone() of the fresh root is the same root (its step limit differs: the reference's clone hard-codes 16)
+    t3 = CFRTrainer(game=game)
+    for _ in range(2):
+        for i in range(game.num_players()):
+            t3._cfr_recursive(game.new_initial_state().clone(), i, 1.0, 1.0)
+    assert np.array_equal(t3.info_set_map[g["keys"][0]].regret_sum, g["reg_2"][0, :4])
+    child = game.new_initial_state()
+    child.apply_action(child.legal_actions()[0])
+    with pytest.raises(NotImplementedError):
+        t3._cfr_recursive(child, 0, 1.0, 1.0)
     np.random.seed(3)
     avg, hist, stats = evaluate_agent(game, trainer.get_openspiel_policy(), RandomPolicy(game), num_episodes=60)
     assert len(hist) == 60 and stats["data_collected"] and -5 < avg < 5

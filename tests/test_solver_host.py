@@ -72,6 +72,7 @@ def lib():
     L.host_eval.argtypes = [vp, vp, C.c_longlong, C.c_ulonglong, C.c_ulonglong, vp, vp]
     L.host_mccfr_inplace_many.argtypes = [C.c_int, C.c_longlong, C.c_ulonglong, C.c_ulonglong, vp, vp, vp]
     L.host_apply_peers.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.host_batch_peers.argtypes = [vp, vp, vp, vp, vp, C.c_longlong, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, C.c_int]
     L.host_solver_delta.argtypes = [vp]
     L.host_solver_set_delta.argtypes = [vp]
     return L
@@ -411,6 +412,43 @@ def test_apply_peers_two_emulated_ranks_equal_sum_and_apply(lib):
     want = ref.table()
     _, tch_want = _counters(ref)
     assert np.array_equal(tab0["regret"], want["regret"]) and np.array_equal(tab0["strategy"], want["strategy"])
+    assert np.array_equal(tch0, tch_want)
+
+
+def test_fused_batch_and_exchange_kernel_two_emulated_ranks(lib):
+    """mccfr_static_peers_kernel (ms_mccfr_batch_peers: the traversals and, in the last CTA to finish, the cross-rank
+    exchange + table update -- ONE launch per iteration per GPU) with two emulated ranks of 3 CTAs each: both replicas end
+    up with the same bits, equal to {each rank's batch, delta0 + delta1, mccfr_apply_kernel}; counters and first-touch
+    flags included; two iterations in a row."""
+    lib.host_peers_reset()
+    sv = HostSolver(lib, 42)
+    S = sv.n_slots
+    assert lib.host_mccfr_inplace_tree(1, 5, 0) == 0
+    start = sv.table()
+    _, tch_start = _counters(sv, reset=True)
+    reg1, strat1, tch1 = start["regret"].copy(), start["strategy"].copy(), tch_start.copy()
+    delta1, cnt1 = np.zeros(6 * S), np.zeros(4, np.uint64)
+    n = 1500
+    for it in range(2):
+        rc = lib.host_batch_peers(reg1.ctypes.data, strat1.ctypes.data, tch1.ctypes.data, delta1.ctypes.data, cnt1.ctypes.data,
+                                  n, 99, (2 * it) * n, (2 * it + 1) * n, 3)
+        assert rc == 0
+        tab0 = sv.table()
+        c0, tch0 = _counters(sv)
+        assert np.array_equal(tab0["regret"], reg1) and np.array_equal(tab0["strategy"], strat1) and np.array_equal(tch0, tch1)
+        assert lib.host_solver_delta_abs_sum() == 0.0 and not delta1.any()
+    assert c0["updates"] == int(cnt1[0]) == 172 * n * 2 and c0["visits"] == int(cnt1[1]) == 703 * n * 2
+    # the same two iterations as {batch of rank 0's ids, batch of rank 1's ids, apply} on one solver
+    ref = HostSolver(lib, 42)
+    assert lib.host_mccfr_inplace_tree(1, 5, 0) == 0
+    for it in range(2):
+        assert lib.host_mccfr_batch(0, 2, n, 99, (2 * it) * n) == 0
+        assert lib.host_mccfr_batch(0, 2, n, 99, (2 * it + 1) * n) == 0
+        assert lib.host_mccfr_apply() == 0
+    want = ref.table()
+    _, tch_want = _counters(ref)
+    np.testing.assert_allclose(tab0["regret"], want["regret"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(tab0["strategy"], want["strategy"], rtol=1e-9, atol=1e-9)
     assert np.array_equal(tch0, tch_want)
 
 
