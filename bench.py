@@ -340,9 +340,11 @@ def section_mccfr(cx, sampler):
     def ex_p2p(s):
         s.apply_peers()
 
-    # the exchange of the headline number: NCCL unless --collective p2p; the peer-memory kernel is timed beside it
+    # the exchange of the headline number: the fused traversal + peer-exchange kernel (auto / p2p; verified on hardware
+    # by tests/test_gpu_multigpu.py), NCCL all-reduce + apply when the peer mapping is unavailable or --collective nccl;
+    # every other form is timed beside it
     sv_p2p, p2p_ok, p2p_note = None, False, None
-    if world > 1 and args.collective in ("p2p", "both"):
+    if world > 1:
         sv_p2p = Solver(seed=42, device=cx.dev)
         p2p_ok = attach_peers_all_ranks(cx, sv_p2p)
         if not p2p_ok:
@@ -351,13 +353,19 @@ def section_mccfr(cx, sampler):
                 raise SystemExit("--collective p2p requested but peer memory is unavailable")
     if world == 1:
         collective, exchange, hsv = "none", ex_local, sv
-    elif args.collective == "p2p":
+    elif args.collective in ("auto", "p2p") and p2p_ok:
         collective, exchange, hsv = "p2p_fused", "fused", sv_p2p
     else:
         collective, exchange, hsv = "nccl", ex_nccl, sv
 
     sampler.start()
     r = time_mccfr(cx, hsv, exchange, B, args.seed, 0, W, K)
+    if collective == "p2p_fused" and cx.max_over_ranks(float(hsv.peer_error())):
+        # a rank gave up on a peer (bounded wait): the tables are not those of a multi-GPU run -- redo with NCCL
+        print(f"[rank {rank}] peer exchange reported an error word; falling back to NCCL", file=sys.stderr)
+        collective, exchange, hsv, p2p_ok = "nccl", ex_nccl, sv, False
+        p2p_note = "peer exchange timed out during the headline run (a rank waited 2 s for a peer)"
+        r = time_mccfr(cx, hsv, exchange, B, args.seed, 0, W, K)
     value = r["updates_all"] / (r["ms_total"] * 1e-3)
     upd_per_launch = r["cnt"]["updates"] / K
 
@@ -400,7 +408,7 @@ def section_mccfr(cx, sampler):
                 continue
             if name.startswith("p2p"):
                 if not p2p_ok:
-                    exchange_ms[name] = p2p_note or "not timed (--collective nccl)"
+                    exchange_ms[name] = p2p_note
                     continue
             rr = time_mccfr(cx, s, fn, B, args.seed, it, 3, short)
             it = rr["next_it"]
@@ -1142,7 +1150,7 @@ REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
 def have_reference():
-    return os.path.exists(os.path.join(REF_DIR, "src", "algorithms", "mc_cfr.pyc"))
+    return os.path.exists(os.path.join(REF_DIR, "src", "algorithms", "mc_cfr.refc"))
 
 
 class ReferencePool:
@@ -1333,8 +1341,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mccfr", choices=["mccfr", "rollout"])
-    ap.add_argument("--trav", type=int, default=454656,
-                    help="traversals per player per GPU per step (default: 3 full waves of 148 CTAs x 1024 threads)")
+    ap.add_argument("--trav", type=int, default=909312,
+                    help="traversals per player per GPU per step (default: 6 full waves of 148 CTAs x 1024 threads)")
     ap.add_argument("--games", type=int, default=1_000_000, help="concurrent games per GPU")
     ap.add_argument("--sd-trav", type=int, default=65536, help="SDCFR traversals per player per GPU per step")
     ap.add_argument("--step-states", type=int, default=16_000_000, help="states in the step-granular API measurement")
@@ -1349,9 +1357,10 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="N = 1: only the two headline sections (and the CPU leg)")
     ap.add_argument("--extras-budget-s", type=float, default=240.0,
                     help="N = 1: no further single-GPU reporting section is started after this many seconds of them")
-    ap.add_argument("--collective", default="both", choices=["both", "p2p", "nccl"],
-                    help="multi-GPU delta exchange of the headline number: NCCL all-reduce + apply (nccl, and both: which also "
-                         "times the peer-memory kernels beside it) or the fused traversal + peer-exchange kernel (p2p)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU delta exchange of the headline number: the fused traversal + peer-exchange kernel (p2p; auto = "
+                         "the same with an NCCL fallback when the peer mapping fails) or NCCL all-reduce + apply (nccl); the "
+                         "other forms are timed beside it")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--ref-trav", type=int, default=1500)
     ap.add_argument("--ref-games", type=int, default=400_000)

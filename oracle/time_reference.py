@@ -19,11 +19,19 @@ import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
-if not os.path.isdir(os.path.join(REF, "src")):
-    REF = "/root/reference"          # authoring container: the sources themselves
 os.environ.setdefault("OMP_NUM_THREADS", "1")
 os.environ.setdefault("MKL_NUM_THREADS", "1")
-sys.path[:0] = [os.path.join(HERE, "stubs"), os.path.join(REF, "src"), REF]
+sys.path.insert(0, os.path.join(HERE, "stubs"))
+if os.path.isfile(os.path.join(REF, "src", "algorithms", "mc_cfr.refc")):
+    sys.path.insert(0, HERE)
+    import ref_import
+    ref_import.install([os.path.join(REF, "src"), REF])
+    REF_KIND = "oracle/_ref (byte-compiled reference)"
+elif os.path.isdir("/root/reference/src"):
+    sys.path[1:1] = ["/root/reference/src", "/root/reference"]       # authoring container: the sources themselves
+    REF_KIND = "/root/reference"
+else:
+    raise SystemExit("time_reference.py: neither oracle/_ref nor /root/reference is present")
 
 import numpy as np  # noqa: E402
 import pyspiel  # noqa: E402  (shim unless the real package is installed)
@@ -80,7 +88,7 @@ def main():
     if len(sys.argv) >= 2 and sys.argv[1] == "serve":
         run("mccfr", 1)
         run("env", 20)
-        print(json.dumps({"ready": True, "pid": os.getpid()}), flush=True)
+        print(json.dumps({"ready": True, "pid": os.getpid(), "reference": REF_KIND, "module_file": ref_mccfr.__file__}), flush=True)
         for line in sys.stdin:
             parts = line.split()
             if not parts or parts[0] == "quit":

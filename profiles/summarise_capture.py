@@ -33,14 +33,21 @@ def sha16(files):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("name")
-    ap.add_argument("raw_csv")
+    ap.add_argument("raw_csv", nargs="?")
     ap.add_argument("--row", type=int, default=0, help="which captured launch of the file")
     ap.add_argument("--pairs", type=float, default=None, help="traversal pairs the captured launch processed")
     ap.add_argument("--sources", nargs="+", required=True)
     ap.add_argument("--sm-clock-mhz", type=float, default=None, help="SM clock assumed by bench.py's issue-slot peak (default: measured in the capture)")
     ap.add_argument("--cas-stall-share-pct", type=float, default=None, help="share of stall samples on the fp64 atomicAdd lines (source page)")
     ap.add_argument("--note", default=None)
+    ap.add_argument("--source-sha16", default=None,
+                    help="hash of --sources recorded ON THE GPU BOX when the capture was taken (profiles/prof_*.sh write it with "
+                         "--hash-only); default: the hash of the files as they are now")
+    ap.add_argument("--hash-only", action="store_true", help="print the hash of --sources and exit")
     a = ap.parse_args()
+    if a.hash_only:
+        print(sha16(a.sources))
+        return
     rows = list(csv.reader(open(a.raw_csv)))
     hdr, units, row = rows[0], rows[1], rows[2 + a.row]
 
@@ -61,7 +68,7 @@ def main():
         commit = None
     e = {
         "kernel": get("Kernel Name"), "file": os.path.relpath(os.path.abspath(a.raw_csv), ROOT), "commit": commit,
-        "source_files": a.sources, "source_sha16": sha16(a.sources),
+        "source_files": a.sources, "source_sha16": a.source_sha16 or sha16(a.sources),
         "duration_us_under_ncu": (get("gpu__time_duration.sum") or 0) * 1e6,
         "warp_inst_per_launch": inst, "sm_clock_mhz_in_capture": clock / 1e6 if clock else None,
         "sm_clock_mhz_assumed": a.sm_clock_mhz or (clock / 1e6 if clock else 1965.0),

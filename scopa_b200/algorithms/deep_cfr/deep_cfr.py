@@ -308,7 +308,7 @@ class DeepCFR:
         }
         words, order = root_of(game)
         self._root = root_id(words, order)
-        self._root_state = (tuple(int(w) for w in words), int(order))
+        self._root_words = (tuple(int(w) for w in words), int(order))
         self._traverser = sdcfr.Traverser(words, order, device=device)
         self._root_state = None
 
@@ -442,7 +442,7 @@ class DeepCFR:
             return self._pol_in
         from ...solver import Solver
         if getattr(self, "_solver", None) is None:
-            self._solver = Solver(self._root_state[0], self._root_state[1], device=self.device)
+            self._solver = Solver(self._root_words[0], self._root_words[1], device=self.device)
         sv = self._solver
         st = sv.static_table()
         S = sv.n_slots

@@ -818,7 +818,8 @@ __device__ __forceinline__ void mccfr_static_body(const SolverDev& d, int player
     StaticShared c;
     c.node = node; c.endrec = endrec - dm.n6; c.sig = sig; c.rsig = rsig;
     c.acc = acc + lane;
-    c.dcnt = dcnt; c.touched = touched; c.need_touch = *s_need != 0;
+    c.dcnt = dcnt; c.touched = touched;
+    const bool need_touch = *s_need != 0;
     c.key = pkey; c.blk = make_uint4(0u, 0u, 0u, 0u);
     unsigned long long v0, u0, e0, v1, u1, e1;
     static_shape_counts(0, v0, u0, e0);
@@ -833,8 +834,13 @@ __device__ __forceinline__ void mccfr_static_body(const SolverDev& d, int player
             const int tp = j ^ flip;
             if (player < 2 && tp != player) continue;
             c.nd = 0u; c.tag = MS_TAG_MCCF_SEQ + (uint32_t)tp;
-            if (tp == 0) { StaticWalk<0, 0>::run(0u, 1.0, c, dm); nu += u0; nv += v0; ns += e0; }
-            else { StaticWalk<0, 1>::run(0u, 1.0, c, dm); nu += u1; nv += v1; ns += e1; }
+            if (tp == 0) {
+                if (need_touch) StaticWalk<0, 0, true>::run(0u, 1.0, c, dm); else StaticWalk<0, 0, false>::run(0u, 1.0, c, dm);
+                nu += u0; nv += v0; ns += e0;
+            } else {
+                if (need_touch) StaticWalk<0, 1, true>::run(0u, 1.0, c, dm); else StaticWalk<0, 1, false>::run(0u, 1.0, c, dm);
+                nu += u1; nv += v1; ns += e1;
+            }
         }
     }
     __syncthreads();

@@ -87,7 +87,6 @@ struct StaticShared {
     double* acc;              // [n_acc][32] D accumulators, pre-offset by lane
     uint32_t* dcnt;           // [S] update counts (strategy delta = count * sigma)
     uint8_t* touched;         // [S]
-    bool need_touch;
     // per-thread random stream
     uint4 blk; uint32_t nd; uint32_t t_lo, t_hi, tag; uint2 key;
 };
@@ -98,11 +97,13 @@ __device__ __noinline__ uint4 static_philox(uint32_t t_lo, uint32_t t_hi, uint32
     return philox4x32_10(make_uint4(t_lo, t_hi, blk, tag), key);
 }
 
+// The d-th uniform of a traversal is word d & 3 of block d >> 2: the four words of the current block sit in a shift
+// register (c.blk.x is the next one), refilled every fourth draw -- no word-select logic per draw.
 __device__ __forceinline__ uint32_t static_draw(StaticShared& c) {
     if ((c.nd & 3u) == 0u) c.blk = static_philox(c.t_lo, c.t_hi, c.nd >> 2, c.tag, c.key);
-    const uint32_t k = c.nd & 3u;
     c.nd++;
-    const uint32_t w = (k & 2u) ? ((k & 1u) ? c.blk.w : c.blk.z) : ((k & 1u) ? c.blk.y : c.blk.x);
+    const uint32_t w = c.blk.x;
+    c.blk.x = c.blk.y; c.blk.y = c.blk.z; c.blk.z = c.blk.w;
     return w >> 1;                                   // 31-bit uniform: u = (w >> 1) / 2^31
 }
 
@@ -115,7 +116,8 @@ __device__ __forceinline__ int static_pick(const uint4& rec, uint32_t u) {
     return ai;
 }
 
-template <int PLY, int TP>
+// TOUCH: record first touches (only while some infoset of the deal has never been visited: the first batches)
+template <int PLY, int TP, bool TOUCH>
 struct StaticWalk {
     static constexpr int NL = 4 - PLY / 2;
     static constexpr bool MINE = (PLY & 1) == TP;
@@ -124,18 +126,18 @@ struct StaticWalk {
     static __device__ __forceinline__ int run(uint32_t node, double w, StaticShared& c, const StaticDims& dm) {
         const uint4 rec = c.node[node];
         const uint32_t slot = rec.w >> 12, cb = rec.w & 0xFFFu;
-        if (c.need_touch) c.touched[slot] = 1;       // node created on first touch, for both players (mc_cfr.py:52)
+        if (TOUCH) c.touched[slot] = 1;              // node created on first touch, for both players (mc_cfr.py:52)
         const int ai = static_pick<NL>(rec, static_draw(c));
         if (!MINE) {                                 // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
-            return StaticWalk<PLY + 1, TP>::run(cb + (uint32_t)ai, __dmul_rn(w, c.sig[4 * slot + ai]), c, dm);
+            return StaticWalk<PLY + 1, TP, TOUCH>::run(cb + (uint32_t)ai, __dmul_rn(w, c.sig[4 * slot + ai]), c, dm);
         }
         // traverser: the sampled action first (:58-67), then every action with a fresh sampled continuation (:71-78)
         uint32_t cfvb = 0u;
         int util = 0;
-#pragma unroll 1
+#pragma unroll(PLY >= 4 ? NL + 1 : 1)           // the innermost child loops (3 short iterations) are written out
         for (int j = -1; j < NL; j++) {
             const int a = j < 0 ? ai : j;
-            const int r = StaticWalk<PLY + 1, TP>::run(cb + (uint32_t)a, __dmul_rn(w, c.rsig[4 * slot + a]), c, dm);
+            const int r = StaticWalk<PLY + 1, TP, TOUCH>::run(cb + (uint32_t)a, __dmul_rn(w, c.rsig[4 * slot + a]), c, dm);
             if (j < 0) util = r;
             else cfvb |= ((uint32_t)r & 0xFFu) << (8 * j);
         }
@@ -158,12 +160,12 @@ struct StaticWalk {
 // plies 6 and 7: one card each, both moves forced, then the end.  The reference's traverser node samples its only
 // action and then evaluates it again: both calls walk this same line, so it is played once (and counted twice by the
 // arithmetic visit counters).  Regret delta = w * (cfv - v) = 0 exactly; strategy delta = 1 * [1.0].
-template <int TP>
-struct StaticWalk<6, TP> {
+template <int TP, bool TOUCH>
+struct StaticWalk<6, TP, TOUCH> {
     static __device__ __forceinline__ int run(uint32_t node, double, StaticShared& c, const StaticDims&) {
         const uint32_t e = c.endrec[node];
         const uint32_t slot6 = e & 0x7FFu, slot7 = (e >> 11) & 0x7FFu;
-        if (c.need_touch) { c.touched[slot6] = 1; c.touched[slot7] = 1; }
+        if (TOUCH) { c.touched[slot6] = 1; c.touched[slot7] = 1; }
         atomicAdd(&c.dcnt[TP == 0 ? slot6 : slot7], 1u);
         const int r = (int)((e >> 22) & 0x3Fu) - 16;
         return TP == 0 ? r : -r;
