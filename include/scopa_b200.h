@@ -185,12 +185,13 @@ int ms_mccfr_apply(ms_solver* s, void* stream);
 int ms_mccfr_batch_mode(ms_solver* s, int32_t mode, int32_t player, int64_t n_trav, uint64_t philox_seed,
                         uint64_t first_trav, void* stream);
 /* Peer-memory exchange (one process per GPU, NVLink / NVSwitch): instead of a library all-reduce + ms_mccfr_apply,
- * every rank maps the other ranks' delta buffers (CUDA IPC) and ONE kernel per rank does barrier + sum over all
- * ranks (in rank order: replicas stay bit-identical) + table update.
- *   ms_solver_ipc_export: 64-byte cudaIpcMemHandle_t of this solver's device block + byte offsets of its two delta
- *     buffers and of its flag array; exchange them between ranks (any out-of-band all-gather of 88 bytes per rank);
+ * every rank maps the other ranks' inboxes (CUDA IPC) and ONE kernel per rank pushes its deltas into every inbox,
+ * meets the others at a flag barrier, sums its own inbox (in rank order: replicas stay bit-identical) and updates its table.
+ *   ms_solver_ipc_export: 64-byte cudaIpcMemHandle_t of this solver's device block + byte offsets of its two inboxes
+ *     (one per iteration parity) and of its flag array; exchange them between ranks (any out-of-band all-gather of 88
+ *     bytes per rank);
  *   ms_solver_ipc_attach: `handles` = world x 64 bytes, `offsets` = world x 3 u64, in rank order (at most 8 ranks);
- *   ms_mccfr_apply_peers: replaces {all-reduce, ms_mccfr_apply} after ms_mccfr_batch; deltas are double buffered by
+ *   ms_mccfr_apply_peers: replaces {all-reduce, ms_mccfr_apply} after ms_mccfr_batch; inboxes are double buffered by
  *     iteration parity, so one cross-GPU barrier per iteration suffices.  Every rank must call it once per iteration.
  *     The barrier is bounded: a rank that has waited 2 s for a peer sets the solver's error word and leaves its table
  *     unchanged from then on (no hang);

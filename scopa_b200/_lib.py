@@ -115,8 +115,8 @@ def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if build_if_missing and _build.stale():
+    path = os.environ.get("SCOPA_B200_LIB") or _build.LIB      # (override: kernel-variant experiments under profiles/)
+    if path == _build.LIB and build_if_missing and _build.stale():
         try:
             _build.build_library()
         except Exception as e:  # on the GPU box nvcc exists too; if not, a prebuilt .so must be there

@@ -1372,21 +1372,23 @@ __global__ void __launch_bounds__(256) mccfr_apply_kernel(SolverDev d) {
     }
 }
 
-// Multi-GPU exchange without a library collective: every rank reads every rank's delta buffer directly over
-// NVLink / NVSwitch peer memory (CUDA IPC mappings), sums them in rank order -- so all replicas compute the same
-// bits -- and applies the sum to its own table, all in this one kernel.
-//   * barrier: each rank stores the iteration number into its slot of every peer's flag array
-//     (st.release.sys after a system-scope fence) and spins until all slots of its own array have reached it;
-//   * the deltas are double buffered by iteration parity: by the time a rank passes the barrier of iteration i,
-//     every peer has finished reading buffer (i-1)&1 (its apply(i-1) precedes its signal(i) in stream order), so
-//     that buffer is zeroed here for iteration i+1;
-//   * peer loads use ld.global.cv: peer lines may sit stale in the local L1.
+// Multi-GPU exchange without a library collective, PUSH form.  Every rank owns an inbox of [world][6 S] doubles per
+// iteration parity, mapped into every peer (CUDA IPC over NVLink / NVSwitch).  One CTA per rank:
+//   1. push: copies this rank's delta buffer into slot `rank` of EVERY rank's inbox (plain stores over peer memory:
+//      fire-and-forget, bandwidth-bound -- a pull would pay one NVLink round trip per dependent load) and zeroes it;
+//   2. barrier: system-scope fence, then the iteration number into its slot of every peer's flag array
+//      (st.release.sys), and spins (bounded) until all slots of its own array have reached it (ld.acquire.sys):
+//      a rank that sees peer r's flag sees r's pushed deltas;
+//   3. sums its own inbox in rank order -- so all replicas compute the same bits -- and applies the sum to its table.
+// Inboxes are double buffered by iteration parity: a peer can be at most one iteration ahead (it cannot pass the
+// barrier of iteration i + 1 before this rank has signalled it, which this rank does after reading inbox i).
+// Measured at 8 GPUs (profiles/README.md): the pull form cost 23 us per iteration (8 dependent rounds of remote loads),
+// NCCL all-reduce + apply 36 us.
 constexpr int MS_MAX_PEERS = 8;
 struct PeerView {
-    const double* delta[MS_MAX_PEERS];          // peers' delta buffer of the current parity
+    double* inbox[MS_MAX_PEERS];                // rank r's inbox of the current parity, [world][6 S] (inbox[rank] is local)
     unsigned long long* flags[MS_MAX_PEERS];    // peers' flag arrays ([world] u64 each)
     unsigned long long* my_flags;
-    double* zero_me;                            // own delta buffer of the other parity
     int rank, world;
 };
 
@@ -1406,7 +1408,8 @@ __device__ __forceinline__ unsigned long long peer_clock_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ double peer_load(const double* p) { return __ldcv(p); }
+__device__ __forceinline__ double peer_load(const double* p) { return __ldcv(p); }      // written by a peer: not from L1
+__device__ __forceinline__ void peer_store(double* p, double v) { __stcg(p, v); }
 __device__ __forceinline__ void peer_fence() { __threadfence_system(); }
 #endif
 
@@ -1422,8 +1425,17 @@ __device__ __forceinline__ void peers_exchange_cta(const SolverDev& d, const Pee
     if (tid == 0) *s_bad = (*(volatile unsigned int*)err != 0u) ? 1 : 0;
     __syncthreads();
     if (*s_bad) return;
+    // 1. push this rank's deltas into every rank's inbox (its own included), and clear them for the next batch
+    const int n6 = 6 * S;
+    for (int i = tid; i < n6; i += blockDim.x) {
+        const double v = __ldcg(d.delta + i);               // accumulated by other CTAs' atomics: read at L2
+        d.delta[i] = 0.0;
+        for (int r = 0; r < pv.world; r++) peer_store(pv.inbox[r] + (size_t)pv.rank * n6 + i, v);
+    }
+    peer_fence();                                           // every pushing thread: its stores before the flags below
+    __syncthreads();
+    // 2. barrier
     if (tid < pv.world) {
-        peer_fence();
         peer_signal(pv.flags[tid] + pv.rank, epoch);
         const unsigned long long t0 = peer_clock_ns();
         while (peer_poll(pv.my_flags + tid) < epoch) {
@@ -1432,10 +1444,12 @@ __device__ __forceinline__ void peers_exchange_cta(const SolverDev& d, const Pee
     }
     __syncthreads();
     if (*s_bad) return;
+    // 3. rank-ordered sum of the own inbox, table update
+    const double* in = pv.inbox[pv.rank];
     for (int s = tid; s < S; s += blockDim.x) {
         double dv[4] = {0.0, 0.0, 0.0, 0.0}, cnt = 0.0, tch = 0.0;
         for (int r = 0; r < pv.world; r++) {
-            const double* pd = pv.delta[r];
+            const double* pd = in + (size_t)r * n6;
             cnt = __dadd_rn(cnt, peer_load(pd + 4 * S + s));
             tch = __dadd_rn(tch, peer_load(pd + 5 * S + s));
 #pragma unroll
@@ -1452,7 +1466,6 @@ __device__ __forceinline__ void peers_exchange_cta(const SolverDev& d, const Pee
             if (dv[i] != 0.0) d.regret[4 * s + i] = __dadd_rn(reg[i], dv[i]);
         if (tch != 0.0) d.touched[s] = 1;
     }
-    for (int i = tid; i < 6 * S; i += blockDim.x) pv.zero_me[i] = 0.0;
 }
 
 __global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d, PeerView pv, unsigned long long epoch,
@@ -1645,7 +1658,7 @@ struct ms_solver {
     SolverDev dev{};
     double* d_value = nullptr; // [2] scratch for returned values
     // peer-memory exchange (ms_solver_ipc_export / _attach / ms_mccfr_apply_peers)
-    double* delta_buf[2] = {nullptr, nullptr};
+    double* inbox[2] = {nullptr, nullptr};     // [MS_MAX_PEERS][6 S] per iteration parity: where the peers push their deltas
     unsigned long long* flags = nullptr;
     unsigned int* peer_err = nullptr;          // device word set by the peer exchange when a peer did not arrive
     int rank = 0, world = 1, parity = 0;
@@ -1822,7 +1835,7 @@ int solver_build(ms_solver* sv) {
     size_t total = 0;
     auto sz = [&](size_t n) { size_t b = (n + 255) & ~(size_t)255; total += b; return b; };
     sz(4 * (L + 1)); sz(2 * N); sz(N); sz(2 * N); sz(N); sz(2 * (S + 1)); sz(2 * sv->n_dec); sz(4 * (L + 1)); sz(S); sz(S);
-    sz(8 * hcap); sz(2 * hcap); sz(32 * S); sz(32 * S); sz(8 * (6 * S)); sz(8 * (6 * S)); sz(8 * MS_MAX_PEERS); sz(16); sz(S); sz(8 * 4); sz(16);
+    sz(8 * hcap); sz(2 * hcap); sz(32 * S); sz(32 * S); sz(8 * (6 * S)); sz(8 * (size_t)MS_MAX_PEERS * 6 * S); sz(8 * (size_t)MS_MAX_PEERS * 6 * S); sz(8 * MS_MAX_PEERS); sz(16); sz(S); sz(8 * 4); sz(16);
     MS_CUDA(cudaMalloc(&sv->d_block, total + 4096));
     MS_CUDA(cudaMemset(sv->d_block, 0, total + 4096));
     p = sv->d_block;
@@ -1849,8 +1862,8 @@ int solver_build(ms_solver* sv) {
     d.regret = carve<double>(p, 4 * (size_t)S);
     d.strategy = carve<double>(p, 4 * (size_t)S);
     d.delta = carve<double>(p, 6 * (size_t)S);
-    sv->delta_buf[0] = d.delta;
-    sv->delta_buf[1] = carve<double>(p, 6 * (size_t)S);
+    sv->inbox[0] = carve<double>(p, (size_t)MS_MAX_PEERS * 6 * S);
+    sv->inbox[1] = carve<double>(p, (size_t)MS_MAX_PEERS * 6 * S);
     sv->flags = carve<unsigned long long>(p, MS_MAX_PEERS);
     sv->peer_err = carve<unsigned int>(p, 4);
     d.touched = carve<uint8_t>(p, (size_t)S);
@@ -1900,8 +1913,7 @@ int ms_solver_reset(ms_solver* s, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MS_CUDA(cudaMemsetAsync(s->dev.regret, 0, 32 * S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.strategy, 0, 32 * S, st));
-    MS_CUDA(cudaMemsetAsync(s->delta_buf[0], 0, 48 * S, st));
-    MS_CUDA(cudaMemsetAsync(s->delta_buf[1], 0, 48 * S, st));
+    MS_CUDA(cudaMemsetAsync(s->dev.delta, 0, 48 * S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.touched, 0, S, st));
     MS_CUDA(cudaMemsetAsync(s->dev.counters, 0, 32, st));
     return MS_OK;
@@ -2154,8 +2166,8 @@ int ms_solver_ipc_export(ms_solver* s, void* handle64, uint64_t offsets[3]) {
     if (!handle64 || !offsets) return fail(MS_ERR_ARG, "ms_solver_ipc_export: bad argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     MS_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, s->d_block));
-    offsets[0] = (uint64_t)((char*)s->delta_buf[0] - s->d_block);
-    offsets[1] = (uint64_t)((char*)s->delta_buf[1] - s->d_block);
+    offsets[0] = (uint64_t)((char*)s->inbox[0] - s->d_block);
+    offsets[1] = (uint64_t)((char*)s->inbox[1] - s->d_block);
     offsets[2] = (uint64_t)((char*)s->flags - s->d_block);
     return MS_OK;
 }
@@ -2179,19 +2191,15 @@ int ms_solver_ipc_attach(ms_solver* s, int32_t rank, int32_t world, const void* 
 static PeerView peer_view(ms_solver* s) {
     PeerView pv{};
     for (int r = 0; r < s->world; r++) {
-        pv.delta[r] = (const double*)((char*)s->peer_base[r] + s->peer_off[r][s->parity]);
+        pv.inbox[r] = (double*)((char*)s->peer_base[r] + s->peer_off[r][s->parity]);
         pv.flags[r] = (unsigned long long*)((char*)s->peer_base[r] + s->peer_off[r][2]);
     }
     pv.my_flags = s->flags;
-    pv.zero_me = s->delta_buf[s->parity ^ 1];
     pv.rank = s->rank; pv.world = s->world;
     return pv;
 }
 
-static void peer_advance(ms_solver* s) {
-    s->parity ^= 1;                       // the next batch accumulates into the other buffer
-    s->dev.delta = s->delta_buf[s->parity];
-}
+static void peer_advance(ms_solver* s) { s->parity ^= 1; }     // the next iteration's pushes go to the other inbox
 
 int ms_mccfr_apply_peers(ms_solver* s, void* stream) {
     int rc = check_dev(s); if (rc) return rc;

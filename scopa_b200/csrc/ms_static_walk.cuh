@@ -93,7 +93,10 @@ struct StaticShared {
 
 // One copy of the ten Philox rounds for the twelve draw sites of the two walks (they are nested loops, not unrolled:
 // inlining it twelve times makes the kernel 48 KB of SASS against a 32 KB instruction cache).
-__device__ __noinline__ uint4 static_philox(uint32_t t_lo, uint32_t t_hi, uint32_t blk, uint32_t tag, uint2 key) {
+#ifndef MS_STATIC_PHILOX_ATTR
+#define MS_STATIC_PHILOX_ATTR __noinline__
+#endif
+__device__ MS_STATIC_PHILOX_ATTR uint4 static_philox(uint32_t t_lo, uint32_t t_hi, uint32_t blk, uint32_t tag, uint2 key) {
     return philox4x32_10(make_uint4(t_lo, t_hi, blk, tag), key);
 }
 

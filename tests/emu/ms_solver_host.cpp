@@ -28,8 +28,10 @@ static inline unsigned long long peer_clock_ns() {
     return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 static inline double peer_load(const double* p) { return *(const volatile double*)p; }
+static inline void peer_store(double* p, double v) { *(volatile double*)p = v; }
 static inline void peer_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T> static inline T __ldcg_host(const T* p) { return *p; }
 static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned val) {
     __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
     return cmp;
@@ -317,21 +319,21 @@ int host_mccfr_inplace_many(int n_runs, long long iters, unsigned long long seed
 // (one block each) run CONCURRENTLY as an emulated cluster launch, meet at the flag barrier, sum the two delta buffers
 // in rank order and update their replicas.  `absent` = 1: rank 1 never arrives (its kernel is not launched), so rank 0
 // must time out, set its error word and leave its table alone.  -> rank 0's error word (0 = fine), or < 0.
-static std::vector<double> g_zero[2];
+static std::vector<double> g_inbox[2];                // one inbox per emulated rank: [2 ranks][6 S]
 static unsigned long long g_flags[2][MS_MAX_PEERS];
 static unsigned int g_err[2][4];
 static unsigned long long g_epoch = 0;
 int host_apply_peers(double* regret1, double* strategy1, uint8_t* touched1, double* delta1, int absent) {
     const size_t n = 6 * (size_t)H.S;
-    for (int r = 0; r < 2; r++) if (g_zero[r].size() != n) g_zero[r].assign(n, 0.0);
+    for (int r = 0; r < 2; r++) g_inbox[r].assign(2 * n, 0.0);
     PeersArgs a{};
     a.d[0] = H.dev;
     a.d[1] = H.dev; a.d[1].regret = regret1; a.d[1].strategy = strategy1; a.d[1].touched = touched1; a.d[1].delta = delta1;
     for (int r = 0; r < 2; r++) {
         PeerView& pv = a.pv[r];
-        pv.delta[0] = H.delta.data(); pv.delta[1] = delta1;
+        pv.inbox[0] = g_inbox[0].data(); pv.inbox[1] = g_inbox[1].data();
         pv.flags[0] = g_flags[0]; pv.flags[1] = g_flags[1];
-        pv.my_flags = g_flags[r]; pv.zero_me = g_zero[r].data(); pv.rank = r; pv.world = 2;
+        pv.my_flags = g_flags[r]; pv.rank = r; pv.world = 2;
         a.err[r] = g_err[r];
     }
     a.epoch = ++g_epoch;
@@ -339,10 +341,7 @@ int host_apply_peers(double* regret1, double* strategy1, uint8_t* touched1, doub
     if (absent) rc = emu_launch_cluster(peers_entry, a, 1, 1024);     // only block 0 = rank 0 runs
     else rc = emu_launch_cluster(peers_entry, a, 2, 1024);
     if (rc) return -1;
-    // the exchange consumed both delta buffers: the next batch accumulates into fresh ones (the library alternates two
-    // buffers per rank and zeroes the idle one in the kernel; here one buffer per rank is simply cleared)
-    if (!g_err[0][0]) { std::fill(H.delta.begin(), H.delta.end(), 0.0); if (!absent) std::fill(delta1, delta1 + n, 0.0); }
-    return (int)g_err[0][0];
+    return (int)g_err[0][0];          // (the kernel itself clears each rank's delta buffer after pushing it)
 }
 // ms_mccfr_batch_peers (mccfr_static_peers_kernel: traversals + exchange in one launch) with two emulated ranks, G CTAs
 // each.  Rank r runs traversal ids [first_r, first_r + n_trav) with n_trav <= (G - 1) * 1024, so that CTAs 0 .. G-2 do all
@@ -354,16 +353,16 @@ int host_batch_peers(double* regret1, double* strategy1, uint8_t* touched1, doub
     StaticDims dm{};
     if (!host_static_dims(dm) || G < 2 || n_trav > (long long)(G - 1) * STATIC_THREADS) return -5;
     const size_t n = 6 * (size_t)H.S;
-    for (int r = 0; r < 2; r++) if (g_zero[r].size() != n) g_zero[r].assign(n, 0.0);
+    for (int r = 0; r < 2; r++) g_inbox[r].assign(2 * n, 0.0);
     FusedArgs a{};
     a.d[0] = H.dev;
     a.d[1] = H.dev; a.d[1].regret = regret1; a.d[1].strategy = strategy1; a.d[1].touched = touched1; a.d[1].delta = delta1;
     a.d[1].counters = counters1;
     for (int r = 0; r < 2; r++) {
         PeerView& pv = a.pv[r];
-        pv.delta[0] = H.delta.data(); pv.delta[1] = delta1;
+        pv.inbox[0] = g_inbox[0].data(); pv.inbox[1] = g_inbox[1].data();
         pv.flags[0] = g_flags[0]; pv.flags[1] = g_flags[1];
-        pv.my_flags = g_flags[r]; pv.zero_me = g_zero[r].data(); pv.rank = r; pv.world = 2;
+        pv.my_flags = g_flags[r]; pv.rank = r; pv.world = 2;
         a.err[r] = g_err[r]; a.ticket[r] = g_ticket[r]; g_ticket[r][0] = 0;
     }
     a.first_trav[0] = first0; a.first_trav[1] = first1;
@@ -380,7 +379,6 @@ int host_batch_peers(double* regret1, double* strategy1, uint8_t* touched1, doub
     if (emu_run_blocks(fused_entry, a, (unsigned)(G - 1), 2, STATIC_THREADS)) return -1;
     gridDim = {1, 1, 1};
     if (g_ticket[0][0] != 0 || g_ticket[1][0] != 0) return -6;       // the last CTA re-arms the ticket
-    if (!g_err[0][0]) { std::fill(H.delta.begin(), H.delta.end(), 0.0); std::fill(delta1, delta1 + n, 0.0); }
     return (int)g_err[0][0];
 }
 
