@@ -340,27 +340,29 @@ def section_mccfr(cx, sampler):
     def ex_p2p(s):
         s.apply_peers()
 
-    # the exchange of the headline number: the fused traversal + peer-exchange kernel (auto / p2p; verified on hardware
-    # by tests/test_gpu_multigpu.py), NCCL all-reduce + apply when the peer mapping is unavailable or --collective nccl;
-    # every other form is timed beside it
+    # the exchange of the headline number: the peer-memory exchange kernel (auto / p2p; verified on hardware by
+    # tests/test_gpu_multigpu.py; the fastest of the forms at N = 2 / 4 / 8, profiles/README.md r02g), NCCL all-reduce +
+    # apply when the peer mapping is unavailable or --collective nccl; every other form is timed beside it
     sv_p2p, p2p_ok, p2p_note = None, False, None
     if world > 1:
         sv_p2p = Solver(seed=42, device=cx.dev)
         p2p_ok = attach_peers_all_ranks(cx, sv_p2p)
         if not p2p_ok:
             p2p_note = "peer attach failed on at least one rank (stderr has the reason)"
-            if args.collective == "p2p":
+            if args.collective in ("p2p", "p2p_fused"):
                 raise SystemExit("--collective p2p requested but peer memory is unavailable")
     if world == 1:
         collective, exchange, hsv = "none", ex_local, sv
-    elif args.collective in ("auto", "p2p") and p2p_ok:
+    elif args.collective == "p2p_fused" and p2p_ok:
         collective, exchange, hsv = "p2p_fused", "fused", sv_p2p
+    elif args.collective in ("auto", "p2p") and p2p_ok:
+        collective, exchange, hsv = "p2p", ex_p2p, sv_p2p
     else:
         collective, exchange, hsv = "nccl", ex_nccl, sv
 
     sampler.start()
     r = time_mccfr(cx, hsv, exchange, B, args.seed, 0, W, K)
-    if collective == "p2p_fused" and cx.max_over_ranks(float(hsv.peer_error())):
+    if collective.startswith("p2p") and cx.max_over_ranks(float(hsv.peer_error())):
         # a rank gave up on a peer (bounded wait): the tables are not those of a multi-GPU run -- redo with NCCL
         print(f"[rank {rank}] peer exchange reported an error word; falling back to NCCL", file=sys.stderr)
         collective, exchange, hsv, p2p_ok = "nccl", ex_nccl, sv, False
@@ -464,6 +466,14 @@ def mccfr_roofline(cx, upd_per_launch, ms_kernel):
         roof.update({"achieved": None, "peak": None, "unit": "G warp-instructions/s", "frac": None, "traffic": None,
                      "note": "no committed capture of this kernel (profiles/captures.json)"})
         return roof
+    cap_keys = ("file", "commit", "source_sha16", "stale", "issue_slots_active_pct", "smem_wavefronts_pct_of_peak", "alu_pipe_pct",
+                "fp64_pipe_pct", "warp_inst_per_traversal_pair", "cas_stall_share_pct")
+    if cap["stale"]:
+        roof.update({"achieved": None, "peak": None, "unit": "G warp-instructions/s", "frac": None, "traffic": None,
+                     "capture": {k: cap.get(k) for k in cap_keys},
+                     "note": "the committed capture describes an OLDER version of the kernel sources (hash mismatch): no "
+                             "instruction count is quoted for the running kernel; re-capture with profiles/prof_*.sh"})
+        return roof
     pairs = upd_per_launch / UPDATES_PER_PAIR
     winst = cap["warp_inst_per_traversal_pair"] * pairs
     sm_hz = cap["sm_clock_mhz_assumed"] * 1e6
@@ -471,12 +481,11 @@ def mccfr_roofline(cx, upd_per_launch, ms_kernel):
     ach = winst / (ms_kernel * 1e-3)
     roof.update({"achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s", "frac": ach / peak,
                  "traffic": cap.get("dram_bytes_per_launch"),
-                 "capture": {k: cap.get(k) for k in ("file", "commit", "source_sha16", "stale", "issue_slots_active_pct",
-                                                      "smem_wavefronts_pct_of_peak", "alu_pipe_pct", "fp64_pipe_pct",
-                                                      "warp_inst_per_traversal_pair", "cas_stall_share_pct")},
+                 "capture": {k: cap.get(k) for k in cap_keys},
                  "note": "issue-slot roofline: achieved = warp instructions per launch (ncu smsp__inst_executed.sum of the "
-                         "committed capture per traversal pair x pairs in this launch) / kernel time measured in this run; "
-                         "peak = 148 SMs x 4 schedulers x 1 warp instruction per cycle at the assumed SM clock"})
+                         "committed capture per traversal pair x pairs in this launch; the recursion shape is data-independent) / "
+                         "kernel time measured in this run; peak = 148 SMs x 4 schedulers x 1 warp instruction per cycle at "
+                         "the maximum SM clock; traffic = DRAM bytes per launch in the capture (table and tree staging only)"})
     return roof
 
 
@@ -794,14 +803,17 @@ def section_atomics(cx, mccfr_value):
     peaks = (ctypes.c_double * 3)()
     _lib.check(_lib.load().ms_debug_atomic_peaks(peaks, _lib.stream_ptr()))
     pairs_per_s = mccfr_value / float(UPDATES_PER_PAIR)          # traversal pairs per second on this GPU
-    # per traversal pair the batch kernel issues 118 shared-memory fp64 atomic adds (regret deltas of the
-    # traverser nodes with more than one action: (1*4 + 5*3 + 20*2) per player) and 172 u32 adds (visit counts)
+    # per traversal pair the headline kernel issues at most 66 shared-memory fp64 atomic adds (nl - 1 difference
+    # accumulators per traverser node with more than one action: (3 + 5*2 + 20*1) per player; zero addends are skipped)
+    # into lane-private columns, and 172 u32 increments (update counts)
     return {"measured_peaks_per_sec": {"smem_f64_atomic_add": peaks[0], "smem_u32_atomic_add": peaks[1],
                                        "global_red_f64_l2_resident": peaks[2]},
-            "mccfr_smem_f64_atomics_per_sec": 118.0 * pairs_per_s, "mccfr_smem_u32_atomics_per_sec": 172.0 * pairs_per_s,
-            "frac_of_smem_f64_peak": 118.0 * pairs_per_s / peaks[0], "frac_of_smem_u32_peak": 172.0 * pairs_per_s / peaks[1],
+            "mccfr_smem_f64_atomics_per_sec_upper_bound": 66.0 * pairs_per_s, "mccfr_smem_u32_atomics_per_sec": 172.0 * pairs_per_s,
+            "frac_of_smem_f64_peak": 66.0 * pairs_per_s / peaks[0], "frac_of_smem_u32_peak": 172.0 * pairs_per_s / peaks[1],
             "note": "microbenchmark: 148 CTAs x 768 threads, pseudo-random addresses over a 738x4 table; shared-memory "
-                    "fp64 atomicAdd compiles to an ATOMS.CAST.SPIN.64 compare-and-swap loop, global fp64 to REDG.E.ADD.F64"}
+                    "fp64 atomicAdd compiles to an ATOMS.CAST.SPIN.64 compare-and-swap loop, global fp64 to REDG.E.ADD.F64.  "
+                    "The microbenchmark's random addresses collide inside a warp; the kernel's lane-private columns do not, "
+                    "so its adds are cheaper than the benchmark's (profiles/README.md, r02)"}
 
 
 def section_multideal(cx):
@@ -1341,8 +1353,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mccfr", choices=["mccfr", "rollout"])
-    ap.add_argument("--trav", type=int, default=909312,
-                    help="traversals per player per GPU per step (default: 6 full waves of 148 CTAs x 1024 threads)")
+    ap.add_argument("--trav", type=int, default=1818624,
+                    help="traversals per player per GPU per step (default: 12 full waves of 148 CTAs x 1024 threads, about half a "
+                         "millisecond of traversal per step)")
     ap.add_argument("--games", type=int, default=1_000_000, help="concurrent games per GPU")
     ap.add_argument("--sd-trav", type=int, default=65536, help="SDCFR traversals per player per GPU per step")
     ap.add_argument("--step-states", type=int, default=16_000_000, help="states in the step-granular API measurement")
@@ -1357,10 +1370,10 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="N = 1: only the two headline sections (and the CPU leg)")
     ap.add_argument("--extras-budget-s", type=float, default=240.0,
                     help="N = 1: no further single-GPU reporting section is started after this many seconds of them")
-    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"],
-                    help="multi-GPU delta exchange of the headline number: the fused traversal + peer-exchange kernel (p2p; auto = "
-                         "the same with an NCCL fallback when the peer mapping fails) or NCCL all-reduce + apply (nccl); the "
-                         "other forms are timed beside it")
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "p2p_fused", "nccl"],
+                    help="multi-GPU delta exchange of the headline number: the peer-memory exchange kernel after the traversal kernel "
+                         "(p2p; auto = the same with an NCCL fallback when the peer mapping fails), the two fused into one launch "
+                         "(p2p_fused), or NCCL all-reduce + apply (nccl); the other forms are timed beside it")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--ref-trav", type=int, default=1500)
     ap.add_argument("--ref-games", type=int, default=400_000)

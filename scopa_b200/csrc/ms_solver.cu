@@ -777,8 +777,7 @@ __device__ __forceinline__ void mccfr_static_body(const SolverDev& d, int player
     double* sig = (double*)(node + dm.n6);
     double* rsig = sig + 4 * dm.S2;
     double* acc = rsig + 4 * dm.S2;
-    uint32_t* endrec = (uint32_t*)(acc + 32 * (size_t)dm.n_acc);
-    uint32_t* dcnt = endrec + (dm.n7 - dm.n6);
+    uint32_t* dcnt = (uint32_t*)(acc + 32 * (size_t)dm.n_acc);
     uint8_t* touched = (uint8_t*)(dcnt + S);
     int* s_need = (int*)(((uintptr_t)(touched + S) + 15) & ~(uintptr_t)15);
     uint32_t* thr = (uint32_t*)acc;         // [S2][3] staging of the per-slot thresholds (the accumulators are zeroed afterwards)
@@ -803,12 +802,17 @@ __device__ __forceinline__ void mccfr_static_body(const SolverDev& d, int player
         if (!d.touched[s]) *s_need = 1;
     }
     __syncthreads();
-    for (int v = tid; v < dm.n7; v += T) {
+    for (int v = tid; v < dm.n6; v += T) {
         const int sl = d.node_slot[v];
-        if (v < dm.n6) node[v] = make_uint4(thr[3 * sl], thr[3 * sl + 1], thr[3 * sl + 2], (uint32_t)d.child_begin[v] | ((uint32_t)sl << 12));
-        else {              // ply 6: its forced child (ply 7), whose forced child is the leaf
-            const int c7 = d.child_begin[v], leaf = d.child_begin[c7];
-            endrec[v - dm.n6] = (uint32_t)sl | ((uint32_t)d.node_slot[c7] << 11) | ((uint32_t)((int)d.rx2[leaf] + 16) << 22);
+        const uint32_t link = (uint32_t)d.child_begin[v] | ((uint32_t)sl << 12);
+        if (v < dm.n5) node[v] = make_uint4(thr[3 * sl], thr[3 * sl + 1], thr[3 * sl + 2], link);
+        else {              // ply 5: both children are ply-6 nodes, whose forced child (ply 7) has the leaf as its forced child
+            uint32_t e[2];
+            for (int k = 0; k < 2; k++) {
+                const int c6 = d.child_begin[v] + k, c7 = d.child_begin[c6], leaf = d.child_begin[c7];
+                e[k] = (uint32_t)d.node_slot[c6] | ((uint32_t)d.node_slot[c7] << 11) | ((uint32_t)((int)d.rx2[leaf] + 16) << 22);
+            }
+            node[v] = make_uint4(thr[3 * sl], link, e[0], e[1]);
         }
     }
     __syncthreads();
@@ -816,7 +820,7 @@ __device__ __forceinline__ void mccfr_static_body(const SolverDev& d, int player
     __syncthreads();
 
     StaticShared c;
-    c.node = node; c.endrec = endrec - dm.n6; c.sig = sig; c.rsig = rsig;
+    c.node = node; c.sig = sig; c.rsig = rsig;
     c.acc = acc + lane;
     c.dcnt = dcnt; c.touched = touched;
     const bool need_touch = *s_need != 0;
@@ -1418,9 +1422,10 @@ constexpr unsigned long long MS_PEER_TIMEOUT_NS = 2000000000ull;     // a peer t
 // err[0]: 0 = fine; otherwise (1 + the first peer that did not arrive) of the first failed exchange.  Once set, every
 // later exchange returns at once without touching the table (ms_solver_peer_error reports MS_ERR_STATE).
 // One CTA (all its threads) runs this: as the whole of mccfr_apply_peers_kernel, or as the tail of the fused
-// mccfr_static_peers_kernel in the last CTA to finish its traversals.  `s_bad` is one int of shared memory.
+// mccfr_static_peers_kernel in the last CTA to finish its traversals.  `s_bad` is one int of shared memory, `s_sum`
+// [6 S] doubles of it.
 __device__ __forceinline__ void peers_exchange_cta(const SolverDev& d, const PeerView& pv, unsigned long long epoch, unsigned int* err,
-                                                   volatile int* s_bad) {
+                                                   volatile int* s_bad, double* s_sum) {
     const int tid = threadIdx.x, S = d.n_slots;
     if (tid == 0) *s_bad = (*(volatile unsigned int*)err != 0u) ? 1 : 0;
     __syncthreads();
@@ -1444,17 +1449,21 @@ __device__ __forceinline__ void peers_exchange_cta(const SolverDev& d, const Pee
     }
     __syncthreads();
     if (*s_bad) return;
-    // 3. rank-ordered sum of the own inbox, table update
+    // 3. rank-ordered sum of the own inbox into shared memory (per element the loads of all ranks are independent and
+    //    issued together: one L2 round trip per element instead of one per rank), then the table update
     const double* in = pv.inbox[pv.rank];
-    for (int s = tid; s < S; s += blockDim.x) {
-        double dv[4] = {0.0, 0.0, 0.0, 0.0}, cnt = 0.0, tch = 0.0;
-        for (int r = 0; r < pv.world; r++) {
-            const double* pd = in + (size_t)r * n6;
-            cnt = __dadd_rn(cnt, peer_load(pd + 4 * S + s));
-            tch = __dadd_rn(tch, peer_load(pd + 5 * S + s));
+    for (int i = tid; i < n6; i += blockDim.x) {
+        double v[MS_MAX_PEERS];
 #pragma unroll
-            for (int i = 0; i < 4; i++) dv[i] = __dadd_rn(dv[i], peer_load(pd + 4 * s + i));
-        }
+        for (int r = 0; r < MS_MAX_PEERS; r++) v[r] = r < pv.world ? peer_load(in + (size_t)r * n6 + i) : 0.0;
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < MS_MAX_PEERS; r++) if (r < pv.world) t = __dadd_rn(t, v[r]);
+        s_sum[i] = t;
+    }
+    __syncthreads();
+    for (int s = tid; s < S; s += blockDim.x) {
+        const double cnt = s_sum[4 * S + s], tch = s_sum[5 * S + s];
         double reg[4], sg[4];
         for (int i = 0; i < 4; i++) reg[i] = d.regret[4 * s + i];
         const int n = d.slot_nlegal[s];
@@ -1462,16 +1471,18 @@ __device__ __forceinline__ void peers_exchange_cta(const SolverDev& d, const Pee
             regret_match(reg, n, sg);
             for (int i = 0; i < n; i++) d.strategy[4 * s + i] = __dadd_rn(d.strategy[4 * s + i], __dmul_rn(cnt, sg[i]));
         }
-        for (int i = 0; i < 4; i++)
-            if (dv[i] != 0.0) d.regret[4 * s + i] = __dadd_rn(reg[i], dv[i]);
+        for (int i = 0; i < 4; i++) {
+            const double dv = s_sum[4 * s + i];
+            if (dv != 0.0) d.regret[4 * s + i] = __dadd_rn(reg[i], dv);
+        }
         if (tch != 0.0) d.touched[s] = 1;
     }
 }
 
 __global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d, PeerView pv, unsigned long long epoch,
                                                                     unsigned int* err) {
-    MS_DYN_SMEM(smem_raw);                  // one int: dynamic, so that emulated ranks (blocks) do not share it
-    peers_exchange_cta(d, pv, epoch, err, (volatile int*)smem_raw);
+    MS_DYN_SMEM(smem_raw);                  // 16 bytes of flags + [6 S] doubles (dynamic: emulated ranks = blocks must not share it)
+    peers_exchange_cta(d, pv, epoch, err, (volatile int*)smem_raw, (double*)(smem_raw + 16));
 }
 
 // The fused form (one launch per MCCFR iteration per GPU): the traversals of mccfr_static_kernel, and in the LAST CTA to
@@ -1497,7 +1508,7 @@ __global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_peers_kernel(S
     __syncthreads();
     if (!s_flag[1]) return;
     __threadfence();
-    peers_exchange_cta(d, pv, epoch, err, s_flag);
+    peers_exchange_cta(d, pv, epoch, err, s_flag, (double*)(smem_raw + 16));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2206,7 +2217,9 @@ int ms_mccfr_apply_peers(ms_solver* s, void* stream) {
     if (!s->attached) return fail(MS_ERR_STATE, "ms_mccfr_apply_peers: call ms_solver_ipc_attach first");
     const PeerView pv = peer_view(s);
     s->epoch += 1;
-    mccfr_apply_peers_kernel<<<1, 1024, 16, (cudaStream_t)stream>>>(s->dev, pv, s->epoch, s->peer_err);
+    const size_t smem = 16 + 48 * (size_t)s->n_slots;
+    MS_CUDA(cudaFuncSetAttribute(mccfr_apply_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mccfr_apply_peers_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(s->dev, pv, s->epoch, s->peer_err);
     MS_LAUNCH_CHECK();
     peer_advance(s);
     return MS_OK;

@@ -52,14 +52,14 @@ __host__ __device__ inline void static_shape_counts(int tp, unsigned long long& 
 }
 
 // Sizes and offsets of one deal's static layout (host: static_dims_from; passed to the kernel by value).
-//   n6 / n7: first node id of ply 6 / ply 7 (nodes are numbered ply by ply); sb[p]: first infoset slot of ply p (slots
+//   n5 / n6 / n7: first node id of ply 5 / 6 / 7 (nodes are numbered ply by ply); sb[p]: first infoset slot of ply p (slots
 //   are numbered ply by ply too: breadth-first first occurrence), sb[6] = S2 = number of infosets with more than one
 //   action; accbase[p]: first accumulator row of ply p; n_acc rows in all.
-struct StaticDims { int n6, n7, S2, n_acc; int sb[7]; int accbase[6]; };
+struct StaticDims { int n5, n6, n7, S2, n_acc; int sb[7]; int accbase[6]; };
 
 __host__ __device__ inline StaticDims static_dims_from(const int* level_begin, const int* slot_level_begin) {
     StaticDims dm{};
-    dm.n6 = level_begin[6]; dm.n7 = level_begin[7];
+    dm.n5 = level_begin[5]; dm.n6 = level_begin[6]; dm.n7 = level_begin[7];
     for (int p = 0; p <= 6; p++) dm.sb[p] = slot_level_begin[p];
     dm.S2 = dm.sb[6];
     int a = 0;
@@ -80,8 +80,8 @@ __host__ __device__ inline StaticDims static_dims_from(const int* level_begin, c
 //     collide, the access is conflict-free (consecutive doubles), and the CAS only arbitrates between the warps of the
 //     CTA (rare).  575 rows x 256 B at most (a deal has at most 1 + 4 + 16 + 48 + 144 + 288 such infosets).
 struct StaticShared {
-    const uint4* node;        // [n6] plies 0..5: {thr0, thr1, thr2, first child | slot << 12}, thr_i = ceil(cdf_i * 2^31)
-    const uint32_t* endrec;   // ply-6 nodes, indexed by NODE id (pointer pre-offset): slot6 | slot7 << 11 | (2 * reward0 + 16) << 22
+    const uint4* node;        // [n6] plies 0..4: {thr0, thr1, thr2, first child | slot << 12}, thr_i = ceil(cdf_i * 2^31);
+                              //      ply 5: {thr0, first child | slot << 12, endgame of child 0, endgame of child 1}
     const double* sig;        // [S2][4] frozen strategies
     const double* rsig;       // [S2][4] 1 / sigma (0 where sigma == 0: the reference's weight is 0 when the sampling prob is 0)
     double* acc;              // [n_acc][32] D accumulators, pre-offset by lane
@@ -91,10 +91,12 @@ struct StaticShared {
     uint4 blk; uint32_t nd; uint32_t t_lo, t_hi, tag; uint2 key;
 };
 
-// One copy of the ten Philox rounds for the twelve draw sites of the two walks (they are nested loops, not unrolled:
-// inlining it twelve times makes the kernel 48 KB of SASS against a 32 KB instruction cache).
+// The ten Philox rounds are inlined at each of the twelve draw sites of the two walks: the key is a kernel parameter, so
+// the round-key schedule runs on the uniform datapath and the call / argument marshalling of an out-of-line copy
+// disappears (measured: 486 -> 560 G updates/s; the out-of-line form had been chosen for code size, which costs less
+// than it saves here: the instruction cache misses of a 60 KB kernel are not what binds it).
 #ifndef MS_STATIC_PHILOX_ATTR
-#define MS_STATIC_PHILOX_ATTR __noinline__
+#define MS_STATIC_PHILOX_ATTR __forceinline__
 #endif
 __device__ MS_STATIC_PHILOX_ATTR uint4 static_philox(uint32_t t_lo, uint32_t t_hi, uint32_t blk, uint32_t tag, uint2 key) {
     return philox4x32_10(make_uint4(t_lo, t_hi, blk, tag), key);
@@ -163,21 +165,40 @@ struct StaticWalk {
 // plies 6 and 7: one card each, both moves forced, then the end.  The reference's traverser node samples its only
 // action and then evaluates it again: both calls walk this same line, so it is played once (and counted twice by the
 // arithmetic visit counters).  Regret delta = w * (cfv - v) = 0 exactly; strategy delta = 1 * [1.0].
+// e = slot of the ply-6 infoset | slot of the ply-7 infoset << 11 | (2 * reward of player 0 + 16) << 22
 template <int TP, bool TOUCH>
-struct StaticWalk<6, TP, TOUCH> {
-    static __device__ __forceinline__ int run(uint32_t node, double, StaticShared& c, const StaticDims&) {
-        const uint32_t e = c.endrec[node];
-        const uint32_t slot6 = e & 0x7FFu, slot7 = (e >> 11) & 0x7FFu;
-        if (TOUCH) { c.touched[slot6] = 1; c.touched[slot7] = 1; }
-        atomicAdd(&c.dcnt[TP == 0 ? slot6 : slot7], 1u);
-        const int r = (int)((e >> 22) & 0x3Fu) - 16;
-        return TP == 0 ? r : -r;
+__device__ __forceinline__ int static_endgame(uint32_t e, StaticShared& c) {
+    const uint32_t slot6 = e & 0x7FFu, slot7 = (e >> 11) & 0x7FFu;
+    if (TOUCH) { c.touched[slot6] = 1; c.touched[slot7] = 1; }
+    atomicAdd(&c.dcnt[TP == 0 ? slot6 : slot7], 1u);
+    const int r = (int)((e >> 22) & 0x3Fu) - 16;
+    return TP == 0 ? r : -r;
+}
+
+// ply 5 (two cards in hand): the node record carries the forced endgames of BOTH children, {thr0, first child | slot << 12,
+// endgame of child 0, endgame of child 1}, so the 60 endgames of a traversal cost no further (dependent) load.
+template <int TP, bool TOUCH>
+struct StaticWalk<5, TP, TOUCH> {
+    static __device__ __forceinline__ int run(uint32_t node, double w, StaticShared& c, const StaticDims& dm) {
+        const uint4 rec = c.node[node];
+        const uint32_t slot = rec.y >> 12;
+        if (TOUCH) c.touched[slot] = 1;
+        const uint32_t u = static_draw(c);
+        const uint32_t e_s = (rec.x <= u) ? rec.w : rec.z;           // the sampled child's endgame
+        if (TP == 0) return static_endgame<TP, TOUCH>(e_s, c);      // opponent node: tail call; the weight is dead below
+        const int util = static_endgame<TP, TOUCH>(e_s, c);         // traverser: sampled action, then both actions
+        const int r0 = static_endgame<TP, TOUCH>(rec.z, c);
+        const int r1 = static_endgame<TP, TOUCH>(rec.w, c);
+        const double val = __dmul_rn(w, 0.5 * (double)(r0 - r1));   // D_0 += w * (cfv_0 - cfv_1)
+        if (val != 0.0) atomicAdd(c.acc + 32 * (dm.accbase[5] + (int)slot - dm.sb[5]), val);
+        atomicAdd(&c.dcnt[slot], 1u);
+        return util;
     }
 };
 
 __host__ __device__ inline size_t mccfr_static_smem(int S, const StaticDims& dm) {
     return 16 * (size_t)dm.n6 + sizeof(double) * 8 * (size_t)dm.S2 + sizeof(double) * 32 * (size_t)dm.n_acc +
-           4 * (size_t)(dm.n7 - dm.n6) + 4 * (size_t)S + (size_t)S + 64;
+           4 * (size_t)S + (size_t)S + 64;
 }
 
 }  // namespace ms

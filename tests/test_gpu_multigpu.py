@@ -51,5 +51,5 @@ def test_bench_default_command_line_on_two_gpus():
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["n_gpus"] == 2 and d["value"] > 0 and d["collective"] in ("nccl", "p2p_fused")
+    assert d["n_gpus"] == 2 and d["value"] > 0 and d["collective"] in ("nccl", "p2p")
     assert d["exchange"]["nccl_ms_per_step"] > 0 and d["exchange"]["p2p_fused_ms_per_step"] > 0
