@@ -210,46 +210,50 @@ def test_deep_cfr_drop_in():
     assert d2.training_history["buffer_sizes"][1][-1] == 3 * 512 * 41
 
 
-def test_sdcfr_exploitability_curve_vs_reference():
-    """Statistical parity for SDCFR.  tests/golden/sdcfr_curve.json holds the exploitability (restated BR) of the
-    UNMODIFIED reference's average policy after 5/10/20/30 iterations for 3 trials (seeds trial*42, as the
-    reference's run_experiments.py): it is very noisy (30 iterations: 1.43 / 0.68 / 1.73; uniform play = 2.26).
-    Stated tolerance: the mean over 6 of our seeds, same hyper-parameters (1 traversal per player per iteration,
-    5 advantage epochs, fp32 inference), is within 0.6 of the reference's trial mean at 20 and 30 iterations and
-    the table-wide policy agrees with get_policy() node by node."""
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sdcfr_exploitability_curve_vs_reference(precision):
+    """Statistical parity for SDCFR, for BOTH inference paths (fp32 on CUDA cores = the reference's precision; bf16 operands
+    on the tcgen05 tensor cores = narrower than the reference).  tests/golden/sdcfr_curve12.json holds the exploitability
+    (restated BR) of the UNMODIFIED reference's average policy after 20 / 30 iterations for 12 trials (seeds trial*42, as
+    the reference's run_experiments.py:33-34; oracle/gen_golden.py sdcfr_curve with SDCFR_CURVE_TRIALS=12): mean 1.753 /
+    1.551, standard deviation 0.49 per trial (uniform play = 2.26) -- SDCFR at 30 iterations of ONE traversal is noisy.
+    Stated tolerance: |mean of 16 of our seeds - mean of the 12 reference trials| < 3 standard errors of that difference
+    (sqrt(se_ref^2 + se_ours^2), both from the sample spreads: about 0.55), same hyper-parameters (1 traversal per player
+    per iteration, 5 advantage epochs); and the curve must fall from 20 to 30 iterations like the reference's."""
     import torch
     from scopa_b200 import pyspiel_compat as pyspiel
     from scopa_b200.envs import openspiel_mini_scopa  # noqa: F401
     from scopa_b200.algorithms.deep_cfr import DeepCFR
-    ref = load_golden_json("sdcfr_curve.json")
-    ref_mean = np.mean(np.array(ref["trials"]), axis=0)
+    ref = load_golden_json("sdcfr_curve12.json")
+    assert ref["iterations"] == [20, 30]
+    ref_t = np.array(ref["trials"])
     game = pyspiel.load_game("mini_scopa")
+    n_seeds = 16
     ours = {20: [], 30: []}
-    for seed in range(6):
-        torch.manual_seed(seed * 42)
-        np.random.seed(seed * 42)
-        d = DeepCFR(game, 2, "cuda", seed=seed)
-        d.train(iterations=20, advantage_epochs=5, eval_freq=10 ** 9, eval_episodes=0)
-        ours[20].append(d.exploitability())
-        if seed == 0:       # the batched table equals the reference-shaped per-state get_policy()
-            tab = d.average_policy_table().cpu().numpy()
-            st = d._solver.static_table()
-            s = game.new_initial_state()
-            for _ in range(3):
-                cp = s.current_player()
-                p16 = d.get_policy(s, cp)
-                slot = st["strings"].index(s.information_state_string(cp))
-                legal = s.legal_actions(cp)
-                want = p16[legal] / p16[legal].sum() if p16[legal].sum() > 0 else np.ones(len(legal)) / len(legal)
-                np.testing.assert_allclose(tab[slot, :len(legal)], want, rtol=1e-4, atol=1e-5)
-                s.apply_action(legal[0])
-    for seed in range(6):
-        torch.manual_seed(seed * 42 + 1)
-        np.random.seed(seed * 42 + 1)
-        d = DeepCFR(game, 2, "cuda", seed=100 + seed)
-        d.train(iterations=30, advantage_epochs=5, eval_freq=10 ** 9, eval_episodes=0)
-        ours[30].append(d.exploitability())
-    for k, idx in ((20, 2), (30, 3)):
-        m = float(np.mean(ours[k]))
-        assert abs(m - ref_mean[idx]) < 0.6, (k, m, ref_mean[idx], ours[k])
-        assert m < 2.26
+    for iters, offset in ((20, 0), (30, 1)):
+        for seed in range(n_seeds):
+            torch.manual_seed(seed * 42 + offset)
+            np.random.seed(seed * 42 + offset)
+            d = DeepCFR(game, 2, "cuda", seed=100 * offset + seed, precision=precision)
+            d.train(iterations=iters, advantage_epochs=5, eval_freq=10 ** 9, eval_episodes=0)
+            ours[iters].append(d.exploitability())
+            if seed == 0 and iters == 20 and precision == "fp32":   # the batched table equals the per-state get_policy()
+                tab = d.average_policy_table().cpu().numpy()
+                st = d._solver.static_table()
+                s = game.new_initial_state()
+                for _ in range(3):
+                    cp = s.current_player()
+                    p16 = d.get_policy(s, cp)
+                    slot = st["strings"].index(s.information_state_string(cp))
+                    legal = s.legal_actions(cp)
+                    want = p16[legal] / p16[legal].sum() if p16[legal].sum() > 0 else np.ones(len(legal)) / len(legal)
+                    np.testing.assert_allclose(tab[slot, :len(legal)], want, rtol=1e-4, atol=1e-5)
+                    s.apply_action(legal[0])
+    means = {}
+    for k, idx in ((20, 0), (30, 1)):
+        o = np.array(ours[k])
+        se = float(np.sqrt(ref_t[:, idx].var(ddof=1) / len(ref_t) + o.var(ddof=1) / len(o)))
+        means[k] = float(o.mean())
+        assert abs(means[k] - ref_t[:, idx].mean()) < 3.0 * se, (precision, k, means[k], float(ref_t[:, idx].mean()), se, ours[k])
+        assert means[k] < 2.26
+    assert means[30] < means[20] + 0.15, means          # learning continues (reference: 1.753 -> 1.551)
