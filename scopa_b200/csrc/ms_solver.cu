@@ -1437,10 +1437,10 @@ __device__ __forceinline__ void peers_exchange_cta(const SolverDev& d, const Pee
         d.delta[i] = 0.0;
         for (int r = 0; r < pv.world; r++) peer_store(pv.inbox[r] + (size_t)pv.rank * n6 + i, v);
     }
-    peer_fence();                                           // every pushing thread: its stores before the flags below
-    __syncthreads();
+    __syncthreads();                                        // all pushes of the CTA happen-before the signalling threads ...
     // 2. barrier
     if (tid < pv.world) {
+        peer_fence();                                       // ... whose system-scope fence + release store publish them (cumulativity)
         peer_signal(pv.flags[tid] + pv.rank, epoch);
         const unsigned long long t0 = peer_clock_ns();
         while (peer_poll(pv.my_flags + tid) < epoch) {
@@ -1491,6 +1491,10 @@ __global__ void __launch_bounds__(1024, 1) mccfr_apply_peers_kernel(SolverDev d,
 // removes is the launch gap and the second kernel's ramp between the two.  Each CTA's delta flush is a set of device-scope
 // atomics followed by __threadfence() and the ticket increment; the last CTA observes every ticket, fences at system
 // scope (peers_exchange_cta) and only then signals its peers, so a peer that sees the flag sees the deltas.
+// Measured (profiles/fused_probe.py, one GPU, world = 1, 12 waves): {batch, apply} 469 us, {batch, apply_peers} 477 us,
+// this kernel 502 us -- with the exchange code inlined behind them the traversal loops themselves run 5 % slower (ptxas
+// allocates the same 64 registers differently); an out-of-line tail was worse (the parameter structs then live in local
+// memory: 512 us).  The headline therefore uses two launches; this form is kept, tested and reported beside it.
 __global__ void __launch_bounds__(STATIC_THREADS, 1) mccfr_static_peers_kernel(SolverDev d, int player, long long n_trav, uint2 pkey,
                                                                                unsigned long long first_trav, StaticDims dm, PeerView pv,
                                                                                unsigned long long epoch, unsigned int* err,

@@ -175,24 +175,35 @@ class Solver:
 
     # ------------------------------------------------------------------------------- peer-memory exchange
     def attach_peers(self, group=None):
-        """Map every rank's delta buffers into this process (CUDA IPC over NVLink / NVSwitch).  Collective: all
-        ranks of `group` must call it.  Afterwards use apply_peers() instead of {all_reduce, mccfr_apply}."""
+        """Map every rank's inboxes into this process (CUDA IPC over NVLink / NVSwitch).  Collective: all ranks of
+        `group` must call it.  Afterwards use apply_peers() / mccfr_batch_peers() instead of {all_reduce, mccfr_apply}.
+        A failure on ANY rank (no peer access, IPC refused) raises MsError on EVERY rank: the outcome is agreed on with
+        an all-reduce, so no rank is left waiting in a collective the failing rank never joins."""
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         handle = (C.c_ubyte * 64)()
         offs = (C.c_uint64 * 3)()
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.ms_solver_ipc_export(self.h, handle, offs))
-        mine = (bytes(handle), [int(o) for o in offs])
+        err = None
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.ms_solver_ipc_export(self.h, handle, offs))
+        except _lib.MsError as e:
+            err = e
         everyone = [None] * world
-        dist.all_gather_object(everyone, mine, group=group)
-        handles = b"".join(h for h, _ in everyone)
-        flat = (C.c_uint64 * (3 * world))(*[o for _, oo in everyone for o in oo])
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.ms_solver_ipc_attach(self.h, rank, world, handles, flat))
-        self._delta_t = None        # the active delta buffer now alternates: delta_tensor() is no longer meaningful
+        dist.all_gather_object(everyone, None if err else (bytes(handle), [int(o) for o in offs]), group=group)
+        if err is None and all(x is not None for x in everyone):
+            try:
+                handles = b"".join(h for h, _ in everyone)
+                flat = (C.c_uint64 * (3 * world))(*[o for _, oo in everyone for o in oo])
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.ms_solver_ipc_attach(self.h, rank, world, handles, flat))
+            except _lib.MsError as e:
+                err = e
+        ok = torch.tensor([0.0 if (err is not None or any(x is None for x in everyone)) else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() < 1.0:
+            raise _lib.MsError(f"attach_peers failed on at least one rank (this rank: {err or 'ok'})")
         self._peers = True
-        dist.barrier(group)
 
     def apply_peers(self):
         """barrier + sum of all ranks' deltas (rank order) + table update, one kernel per rank."""
