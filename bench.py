@@ -448,15 +448,15 @@ def section_mccfr(cx, sampler):
     return obj, sv
 
 
-def mccfr_roofline(cx, upd_per_launch, ms_kernel):
+def mccfr_roofline(cx, upd_per_launch, ms_kernel, capture_name="mccfr_headline"):
     """The headline kernel keeps the table, the tree and every delta in shared memory: DRAM traffic is a few KB per
     launch, so the bound is on chip.  `frac` = issue-slot utilisation = warp instructions per launch (from the committed
     ncu capture of THIS kernel source, scaled by the traversals of the launch: the estimator's recursion shape is
     data-independent) / (kernel time measured in this run x 148 SMs x 4 schedulers x the SM clock).  The HBM-equivalent
     figure SURVEY 8(d) prescribes is kept as a side note."""
     hbm_equiv = upd_per_launch * BYTES_PER_UPDATE_FP64 / (ms_kernel * 1e-3) / 1e9
-    cap = load_capture("mccfr_headline")
-    roof = {"bound": "issue", "kernel": cap["kernel"] if cap else "mccfr headline kernel", "kernel_ms": ms_kernel,
+    cap = load_capture(capture_name)
+    roof = {"bound": "issue", "kernel": cap["kernel"] if cap else capture_name, "kernel_ms": ms_kernel,
             "hbm_equivalent": {"achieved_gbs": hbm_equiv, "peak_gbs": cx.hbm_gbs, "ratio": hbm_equiv / cx.hbm_gbs,
                                "peak_source": cx.peak_src,
                                "note": "203.7 algorithmic B/update x updates per launch / kernel time: what an HBM-resident "
@@ -847,7 +847,7 @@ def section_multideal(cx):
     rp = (ctypes.c_double * 3)()
     table_bytes = md.table_bytes
     # the deal-blocked form on the same table: one deal per CTA visit, 3072 traversal pairs per visit staged on chip
-    VIS, PPV = 148, 3072
+    VIS, PPV = 148, 12288
     tb0 = time.perf_counter()
     md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=0)     # first call builds the deal records
     md.apply()
@@ -857,24 +857,27 @@ def section_multideal(cx):
         md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=i * VIS)
         md.apply()
     md.counters(reset=True)
-    bev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    bev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
     bev[0].record()
     for i in range(K):
         md.mccfr_blocked(VIS, pairs_per_visit=PPV, philox_seed=args.seed, first_visit=(4 + i) * VIS)
+        bev[2 * i + 1].record()
         md.apply()
-        bev[i + 1].record()
+        bev[2 * i + 2].record()
     torch.cuda.synchronize()
     bc = md.counters()
-    b_ms = bev[0].elapsed_time(bev[K]) / K
+    b_ms = bev[0].elapsed_time(bev[2 * K]) / K
+    bk_ms = sum(bev[2 * i].elapsed_time(bev[2 * i + 1]) for i in range(K)) / K
     n_info = int(bc["infosets"])
-    # deal-blocked traffic: per visit the deal's stored infosets are read once (64 B used of each 128 B line) and their
-    # deltas written once
+    # deal-blocked traffic: per visit the deal's stored infosets are read once and their deltas written once (a few tens of
+    # KB per visit of thousands of traversals): like the one-deal kernel it is bound by issue slots, not by the table
     mdb_obj = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s",
-               "value": bc["updates"] / K / (b_ms * 1e-3), "ms_per_step": b_ms, "infosets": n_info,
+               "value": bc["updates"] / K / (b_ms * 1e-3), "ms_per_step": b_ms, "ms_traverse": bk_ms, "infosets": n_info,
                "first_call_s_incl_describing_all_deals": build_s, "kernel": "md_blocked_kernel",
+               "roofline": mccfr_roofline(cx, bc["updates"] / K, bk_ms, "md_blocked_kernel"),
                "config": {"workload": f"same table and estimator, deal-blocked: {VIS} visits x {PPV} traversal pairs per step, one "
-                                      "deal per CTA visit staged in shared memory (tree, strategies, delta tables), table "
-                                      "read once and written once per visit"}}
+                                      "deal per CTA visit staged in shared memory (node records, strategies, lane-private "
+                                      "accumulators: the one-deal solver's static walk), table read once and written once per visit"}}
     del md
     torch.cuda.empty_cache()
     _lib.check(_lib.load().ms_debug_random_access_peaks(lines_lg, rp, _lib.stream_ptr()))

@@ -137,6 +137,7 @@ static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 
 #define TAG_ROLL 0x4C4C4F52u /* "ROLL" */
 #define TAG_MCCF 0x4643434Du /* "MCCF" */
+#define TAG_MCCF_SEQ (TAG_MCCF + 64u) /* the sequential stream of the static-shape kernels */
 #define TAG_SDCF 0x46434453u /* "SDCF" */
 
 /* ================================================================================ RNG facade */
@@ -621,7 +622,6 @@ void ora_mccfr_populate(ora_table* t, int64_t seed) {
     populate_rec(t, &s);
 }
 
-#define TAG_MCCF_SEQ (TAG_MCCF + 64u)
 static void mccfr_batch_impl(ora_table* t, int64_t seed, int player, uint64_t philox_seed, uint64_t first_trav,
                              int64_t ntrav, int64_t* n_updates, int64_t* n_visits, int rng_kind, uint32_t tag_base) {
     int n0 = t->n;
@@ -1476,7 +1476,7 @@ void ora_md_populate(ora_mdtable* t, const int64_t* seeds, int64_t n_deals) {
 
 void ora_md_batch_blocked(ora_mdtable* t, const int64_t* seeds, int64_t n_deals, int player, uint64_t philox_seed,
                           uint64_t first_visit, int64_t n_visits, int64_t pairs, int64_t* n_updates, int64_t* n_visits_out) {
-    ora_rng* rng = ora_rng_new(1, philox_seed);
+    ora_rng* rng = ora_rng_new(2, philox_seed);               /* the sequential stream, like ora_mccfr_batch_seq */
     md_ctx c = {t, rng, 0, 0, 0};
     const uint32_t key[2] = {(uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)};
     for (int64_t v = 0; v < n_visits; v++) {
@@ -1490,7 +1490,7 @@ void ora_md_batch_blocked(ora_mdtable* t, const int64_t* seeds, int64_t n_deals,
                 if (player < 2 && tp != player) continue;
                 ora_state s; ora_state_init(&s, seeds[deal]);
                 c.tp = tp;
-                rng->tag = TAG_MCCF + (uint32_t)tp; rng->trav = trav; rng->call = 0;
+                rng->tag = TAG_MCCF_SEQ + (uint32_t)tp; rng->trav = trav; rng->call = 0; rng->draw = 0;
                 double one[2] = {1.0, 1.0};
                 md_sample(&c, &s, one, one);
             }

@@ -24,6 +24,7 @@
 #include "ms_common.cuh"
 #include "ms_state.cuh"
 #include "ms_tree_walk.cuh"
+#include "ms_static_walk.cuh"
 
 #ifndef MS_DYN_SMEM   // the host emulation (tests/emu) supplies its own: one buffer per emulated block
 #define MS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
@@ -485,12 +486,12 @@ __global__ void __launch_bounds__(768, 1) rnd_red_kernel(MdSlot* tab, unsigned l
 // line transaction, and the dependent chain of a depth-first traversal keeps it latency-bound (section 11 of
 // DESIGN.md).  Here a CTA takes one deal at a time and runs a whole block of traversals on it (`pairs_per_visit`,
 // thousands), exactly like the one-deal solver: the deal's enumerated tree, the frozen strategies of its infosets,
-// their cdfs and the private delta tables live in shared memory (mccfr_tree_traverse of ms_tree_walk.cuh does the
-// walking), and the HBM table is read once when the visit starts (one gather of the deal's <= 501 infoset lines) and
+// their cdfs and the private delta tables live in shared memory (the walk is StaticWalk<.., MODE 1> of
+// ms_static_walk.cuh), and the HBM table is read once when the visit starts (one gather of the deal's <= 501 infoset lines) and
 // written once when it ends (REDs of the non-zero deltas and visit counts).  Random-line traffic per traversal drops
 // by three orders of magnitude.  Chance sampling is per visit: visit v plays deal
 // mulhi32(x0, D), x = Philox4x32-10(key = seed, ctr = (v lo, v hi, 1, "DEAL")); its traversals have the global
-// ids v * pairs_per_visit + i and use the same "MCCF" streams as everywhere else.
+// ids v * pairs_per_visit + i and use the sequential "MCCF"+64 streams of the one-deal solver's headline kernel.
 //
 // Fresh 4+4-card deals all have the same tree SHAPE (levels of 1, 4, 16, 48, 144, 288, 576, 576, 576 nodes with 4, 4,
 // 3, 3, 2, 2, 1, 1 legal actions; node i of a level has children begin[L+1] + i * n_legal + a, a in legal_actions()
@@ -507,8 +508,10 @@ struct MdDealInfo {
     uint16_t node_local[MDB_LOCAL];     // nodes 0..500 -> local infoset index
     uint8_t local_perm[MDB_LOCAL];      // 2 bits per legal action: its column (rank of the card id in the hand)
     int8_t rx2[MDB_LEAVES];             // 2 * reward of player 0 at the 576 leaves
+    uint16_t acc_row[MDB_LOCAL];        // first regret-accumulator row of each local infoset (it owns nl - 1 consecutive rows)
     uint32_t n_local;
-    uint32_t pad[3];
+    uint32_t n_acc;                     // accumulator rows of the deal (<= 575)
+    uint32_t pad[2];
 };
 static_assert(sizeof(MdDealInfo) % 16 == 0, "deal records are copied with 128-bit accesses");
 
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(256) md_build_kernel(MdDev t, MdDealInfo* __re
     __shared__ uint16_t hloc[1024];
     __shared__ uint8_t hmeta[1024];          // perm of the infoset claimed at this hash position
     __shared__ uint8_t hnl[1024];
-    __shared__ int part[257];
+    __shared__ int part[257], part2[257];
     const int tid = threadIdx.x;
     for (unsigned int deal = blockIdx.x; deal < t.n_deals; deal += gridDim.x) {
         MdDealInfo* out = info + deal;
@@ -557,14 +560,15 @@ __global__ void __launch_bounds__(256) md_build_kernel(MdDev t, MdDealInfo* __re
             __syncthreads();
         }
         // hash positions -> dense local indices, in position order
-        int mine = 0;
-        for (int j = 0; j < 4; j++) mine += hkey[4 * tid + j] != 0ull;
-        part[tid + 1] = mine;
-        if (tid == 0) part[0] = 0;
+        int mine = 0, mine2 = 0;
+        for (int j = 0; j < 4; j++)
+            if (hkey[4 * tid + j] != 0ull) { mine++; mine2 += (int)hnl[4 * tid + j] - 1; }
+        part[tid + 1] = mine; part2[tid + 1] = mine2;
+        if (tid == 0) { part[0] = 0; part2[0] = 0; }
         __syncthreads();
-        if (tid == 0) for (int j = 1; j <= 256; j++) part[j] += part[j - 1];
+        if (tid == 0) for (int j = 1; j <= 256; j++) { part[j] += part[j - 1]; part2[j] += part2[j - 1]; }
         __syncthreads();
-        int idx = part[tid];
+        int idx = part[tid], row = part2[tid];
         uint32_t ins = 0u;
         for (int j = 0; j < 4; j++) {
             const int h = 4 * tid + j;
@@ -574,57 +578,53 @@ __global__ void __launch_bounds__(256) md_build_kernel(MdDev t, MdDealInfo* __re
                 const long long slot = md_find_regrets(t, hkey[h], unused, ins);     // claims the slot on first sight
                 out->local_slot[idx] = ((uint32_t)(slot < 0 ? 0 : slot) & 0x3FFFFFFFu) | ((uint32_t)(hnl[h] - 2) << 30);
                 out->local_perm[idx] = hmeta[h];
+                out->acc_row[idx] = (uint16_t)row;
+                row += (int)hnl[h] - 1;
                 idx++;
             }
         }
         if (ins) atomicAdd(&t.counters[3], (unsigned long long)ins);
-        if (tid == 0) out->n_local = (uint32_t)part[256];
+        if (tid == 0) { out->n_local = (uint32_t)part[256]; out->n_acc = (uint32_t)part2[256]; }
         __syncthreads();
         for (int n = tid; n < MDB_MULTI; n += 256) out->node_local[n] = hloc[out->node_local[n]];
         __syncthreads();
     }
 }
 
-constexpr int MDB_THREADS = 1024, MDB_COPIES = 4, MDB_FRAMES = 3;
+constexpr int MDB_THREADS = 1024;
+constexpr int MDB_ACC_MAX = 3 * (1 + 4) + 2 * (16 + 48) + (144 + 288);      // nl - 1 rows per infoset, every node its own infoset
 
 __host__ __device__ inline size_t mdb_smem_bytes() {
-    return sizeof(double) * (7 + 4 * MDB_COPIES) * MDB_LOCAL + 4 * MDB_NODES + 4 * MDB_SLOTS + MDB_SLOTS +
-           sizeof(MdDealInfo) + (size_t)MDB_THREADS * MDB_FRAMES * (8 + 8 + 4 + 4 + 2) + 64;
+    return 16 * (size_t)MDB_LOCAL + sizeof(double) * 8 * MDB_LOCAL + sizeof(double) * 32 * MDB_ACC_MAX + 4 * MDB_LOCAL +
+           sizeof(MdDealInfo) + 64;
 }
 
+// Round 2: the walk is ms_static_walk.cuh's (MODE 1) -- the estimator's recursion written out as nested loops with its
+// state in registers, integer cdf thresholds, the sequential Philox stream, lane-private nl - 1 regret accumulators --
+// instead of the generic DFS with frames in shared memory: the same change that took the one-deal solver from 95 to 650 G
+// updates/s.  One-card infosets are not stored in this table, so the forced endgames count nothing and a ply-5 record
+// carries just the two leaf rewards.
 __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, const MdDealInfo* __restrict__ info, int player,
                                                                   unsigned long long first_visit, long long n_visits,
                                                                   int pairs_per_visit, uint2 pkey) {
     MS_DYN_SMEM(smem_raw);
     constexpr int T = MDB_THREADS, SL = MDB_LOCAL;
-    const int tid = threadIdx.x;
-    double* sig = (double*)smem_raw;                       // [SL][4] frozen strategies, legal (= deal) order
-    double* cdf = sig + 4 * SL;                            // [SL][3]
-    double* dreg = cdf + 3 * SL;                           // MDB_COPIES x [SL][4], chosen by lane id
-    TreeFrames f;
-    f.ro = dreg + MDB_COPIES * 4 * SL;
-    f.sp = f.ro + T * MDB_FRAMES;
-    MdDealInfo* di = (MdDealInfo*)(f.sp + T * MDB_FRAMES);
-    f.meta = (uint32_t*)(di + 1);
-    f.cfv = f.meta + T * MDB_FRAMES;
-    uint32_t* tree = f.cfv + T * MDB_FRAMES;
-    uint32_t* dcnt = tree + MDB_NODES;
-    f.cb = (uint16_t*)(dcnt + MDB_SLOTS);
-    uint8_t* touched = (uint8_t*)(f.cb + T * MDB_FRAMES);
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint4* node = (uint4*)smem_raw;                        // [SL] records of the 501 multi-action nodes
+    double* sig = (double*)(node + SL);                    // [SL][4] frozen strategies, legal (= deal) order
+    double* rsig = sig + 4 * SL;                           // [SL][4] 1 / sigma (0 where sigma == 0)
+    double* acc = rsig + 4 * SL;                           // [MDB_ACC_MAX][32] lane-private D accumulators
+    uint32_t* dcnt = (uint32_t*)(acc + 32 * MDB_ACC_MAX);  // [SL] update counts per local infoset
+    MdDealInfo* di = (MdDealInfo*)(dcnt + SL);
+    uint32_t* thr = (uint32_t*)acc;                        // [SL][3] staging of the thresholds (acc is zeroed afterwards)
 
-    // the deal-independent part of the node records
-    for (int n = tid; n < MDB_NODES; n += T) {
-        int L = 0;
-        while (n >= c_mdb_begin[L + 1]) L++;
-        const int i = n - c_mdb_begin[L], nl = c_mdb_nl[L];
-        uint32_t rec;
-        if (L == 8) rec = TREE_TERMINAL << 12;
-        else rec = (uint32_t)(c_mdb_begin[L + 1] + i * nl) | ((uint32_t)nl << 23) | ((uint32_t)(L & 1) << 26) |
-                   ((uint32_t)(L >= 6 ? MDB_LOCAL + (n - MDB_MULTI) : 0) << 12);
-        tree[n] = rec;
-    }
-    MccfrShared sh{nullptr, nullptr, 0, sig, cdf, dreg + (size_t)(tid & (MDB_COPIES - 1)) * 4 * SL, dcnt, touched, nullptr, nullptr};
-    f.ro += tid; f.sp += tid; f.meta += tid; f.cfv += tid; f.cb += tid;
+    StaticShared c;
+    c.node = node; c.sig = sig; c.rsig = rsig; c.acc = acc + lane; c.accrow = di->acc_row; c.dcnt = dcnt; c.touched = nullptr;
+    c.key = pkey; c.blk = make_uint4(0u, 0u, 0u, 0u);
+    const StaticDims dm{};                                 // (MODE 1 takes its rows from c.accrow)
+    unsigned long long v0, u0, e0, v1, u1, e1;
+    static_shape_counts(0, v0, u0, e0);
+    static_shape_counts(1, v1, u1, e1);
     unsigned long long nu = 0, nv = 0, ns = 0;
     const int flip = (tid >> 5) & 1;
 
@@ -638,13 +638,9 @@ __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, con
             uint4* dst = (uint4*)di;
             for (int i = tid; i < (int)(sizeof(MdDealInfo) / 16); i += T) dst[i] = src[i];
         }
-        for (int i = tid; i < MDB_COPIES * 4 * SL; i += T) dreg[i] = 0.0;
-        for (int i = tid; i < MDB_SLOTS; i += T) dcnt[i] = 0u;
+        for (int i = tid; i < SL; i += T) dcnt[i] = 0u;
         __syncthreads();
-        const int n_local = (int)di->n_local;
-        for (int n = tid; n < MDB_MULTI; n += T) tree[n] = (tree[n] & ~(0x7FFu << 12)) | ((uint32_t)di->node_local[n] << 12);
-        for (int n = tid; n < MDB_LEAVES; n += T)
-            tree[MDB_FIRST_LEAF + n] = ((uint32_t)((int)di->rx2[n] + 2048) & 0xFFFu) | (TREE_TERMINAL << 12);
+        const int n_local = (int)di->n_local, n_acc = (int)di->n_acc;
         for (int j = tid; j < n_local; j += T) {           // gather: one table line per infoset of the deal
             const uint32_t ls = di->local_slot[j];
             const MdSlot* sl = t.slots + (ls & 0x3FFFFFFFu);
@@ -658,17 +654,34 @@ __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, con
             for (int k = 0; k < 4; k++) sg[k] = (k < nl) ? md_pick(sc, (int)((perm >> (2 * k)) & 3u)) : 0.0;
             strategy_cdf(sg, nl, cd);
 #pragma unroll
-            for (int k = 0; k < 4; k++) sig[4 * j + k] = sg[k];
+            for (int k = 0; k < 4; k++) { sig[4 * j + k] = sg[k]; rsig[4 * j + k] = sg[k] > 0.0 ? __ddiv_rn(1.0, sg[k]) : 0.0; }
 #pragma unroll
-            for (int k = 0; k < 3; k++) cdf[3 * j + k] = cd[k];
+            for (int k = 0; k < 3; k++) thr[3 * j + k] = (k + 1 < nl) ? (uint32_t)ceil(cd[k] * 2147483648.0) : 0x80000000u;
         }
+        __syncthreads();
+        for (int n = tid; n < MDB_MULTI; n += T) {         // node records (ms_static_walk.cuh)
+            int L = 0;
+            while (n >= c_mdb_begin[L + 1]) L++;
+            const int i = n - c_mdb_begin[L], nl = c_mdb_nl[L], j = (int)di->node_local[n];
+            const uint32_t link = (uint32_t)(c_mdb_begin[L + 1] + i * nl) | ((uint32_t)j << 12);
+            if (L < 5) node[n] = make_uint4(thr[3 * j], thr[3 * j + 1], thr[3 * j + 2], link);
+            else {          // ply 5: child k is ply-6 node 2 i + k of its level, whose forced line ends at leaf 2 i + k
+                const uint32_t e0r = (uint32_t)((int)di->rx2[2 * i] + 16) << 22, e1r = (uint32_t)((int)di->rx2[2 * i + 1] + 16) << 22;
+                node[n] = make_uint4(thr[3 * j], link, e0r, e1r);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 32 * n_acc; i += T) acc[i] = 0.0;
         __syncthreads();
         for (int k = tid; k < pairs_per_visit; k += T) {
             const unsigned long long trav = visit * (unsigned long long)pairs_per_visit + (unsigned long long)k;
+            c.t_lo = (uint32_t)trav; c.t_hi = (uint32_t)(trav >> 32);
             for (int j = 0; j < 2; j++) {
                 const int tp = j ^ flip;
                 if (player < 2 && tp != player) continue;
-                mccfr_tree_traverse<false>(tree, sh, tp, trav, pkey, f, T, nu, nv, ns);
+                c.nd = 0u; c.tag = MS_TAG_MCCF_SEQ + (uint32_t)tp;
+                if (tp == 0) { StaticWalk<0, 0, false, 1>::run(0u, 1.0, c, dm); nu += u0; nv += v0; ns += e0; }
+                else { StaticWalk<0, 1, false, 1>::run(0u, 1.0, c, dm); nu += u1; nv += v1; ns += e1; }
             }
         }
         __syncthreads();
@@ -679,9 +692,18 @@ __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, con
             const long long slot = (long long)(ls & 0x3FFFFFFFu);
             const int nl = (int)(ls >> 30) + 2;
             const uint32_t perm = di->local_perm[j];
+            // delta_a = D_a - sum_i sigma_i D_i with D_last = 0 (ms_static_walk.cuh)
+            double D0 = 0.0, D1 = 0.0, D2 = 0.0, sum = 0.0;
+            for (int i = 0; i < nl - 1; i++) {
+                const double* col = acc + 32 * (size_t)((int)di->acc_row[j] + i);
+                double tt = 0.0;
+                for (int l = 0; l < 32; l++) tt = __dadd_rn(tt, col[l]);
+                if (i == 0) D0 = tt; else if (i == 1) D1 = tt; else D2 = tt;
+                sum = __dadd_rn(sum, __dmul_rn(sig[4 * j + i], tt));
+            }
             for (int k = 0; k < nl; k++) {
-                double v = dreg[4 * j + k];
-                for (int c = 1; c < MDB_COPIES; c++) v = __dadd_rn(v, dreg[(size_t)c * 4 * SL + 4 * j + k]);
+                const double Dk = k == 0 ? D0 : (k == 1 ? D1 : D2);
+                const double v = k < nl - 1 ? __dadd_rn(Dk, -sum) : -sum;
                 if (v != 0.0) atomicAdd(&t.slots[slot].delta[(perm >> (2 * k)) & 3u], v);
             }
             atomicAdd(&t.slots[slot].cnt, cnt);

@@ -85,6 +85,7 @@ struct StaticShared {
     const double* sig;        // [S2][4] frozen strategies
     const double* rsig;       // [S2][4] 1 / sigma (0 where sigma == 0: the reference's weight is 0 when the sampling prob is 0)
     double* acc;              // [n_acc][32] D accumulators, pre-offset by lane
+    const uint16_t* accrow;   // MODE 1 only: first accumulator row of each (local) infoset
     uint32_t* dcnt;           // [S] update counts (strategy delta = count * sigma)
     uint8_t* touched;         // [S]
     // per-thread random stream
@@ -121,8 +122,13 @@ __device__ __forceinline__ int static_pick(const uint4& rec, uint32_t u) {
     return ai;
 }
 
-// TOUCH: record first touches (only while some infoset of the deal has never been visited: the first batches)
-template <int PLY, int TP, bool TOUCH>
+// TOUCH: record first touches (only while some infoset of the deal has never been visited: the first batches).
+// MODE 0: the one-deal solver -- infoset slots are numbered ply by ply, so an infoset's accumulator rows follow from its
+//   slot by arithmetic (plane layout: row = accbase[ply] + i * (infosets of the ply) + slot - sb[ply]), and the one-card
+//   infosets of the last two plies are counted.  MODE 1: the deal-blocked multi-deal solver (ms_multideal.cu) -- local
+//   infoset indices in no particular order, so the first row of an infoset comes from a table (rows i = 0 .. nl - 2 are
+//   consecutive); one-card infosets are not stored there, so the forced endgame is just the leaf's reward.
+template <int PLY, int TP, bool TOUCH, int MODE = 0>
 struct StaticWalk {
     static constexpr int NL = 4 - PLY / 2;
     static constexpr bool MINE = (PLY & 1) == TP;
@@ -134,7 +140,7 @@ struct StaticWalk {
         if (TOUCH) c.touched[slot] = 1;              // node created on first touch, for both players (mc_cfr.py:52)
         const int ai = static_pick<NL>(rec, static_draw(c));
         if (!MINE) {                                 // opponent: reach *= sigma[a]; tail call (mc_cfr.py:63-65)
-            return StaticWalk<PLY + 1, TP, TOUCH>::run(cb + (uint32_t)ai, __dmul_rn(w, c.sig[4 * slot + ai]), c, dm);
+            return StaticWalk<PLY + 1, TP, TOUCH, MODE>::run(cb + (uint32_t)ai, __dmul_rn(w, c.sig[4 * slot + ai]), c, dm);
         }
         // traverser: the sampled action first (:58-67), then every action with a fresh sampled continuation (:71-78)
         uint32_t cfvb = 0u;
@@ -142,15 +148,15 @@ struct StaticWalk {
 #pragma unroll(PLY >= 4 ? NL + 1 : 1)           // the innermost child loops (3 short iterations) are written out
         for (int j = -1; j < NL; j++) {
             const int a = j < 0 ? ai : j;
-            const int r = StaticWalk<PLY + 1, TP, TOUCH>::run(cb + (uint32_t)a, __dmul_rn(w, c.rsig[4 * slot + a]), c, dm);
+            const int r = StaticWalk<PLY + 1, TP, TOUCH, MODE>::run(cb + (uint32_t)a, __dmul_rn(w, c.rsig[4 * slot + a]), c, dm);
             if (j < 0) util = r;
             else cfvb |= ((uint32_t)r & 0xFFu) << (8 * j);
         }
         // regret deltas (:79-84), weight = reach_opp / sample_own = w: D_i += w * (cfv_i - cfv_last), see StaticShared;
         // strategy delta = count * sigma
         const int last = (int)(int8_t)((cfvb >> (8 * (NL - 1))) & 0xFFu);
-        double* row = c.acc + 32 * (dm.accbase[PLY] + (int)slot - dm.sb[PLY]);
-        const int plane = 32 * (dm.sb[PLY + 1] - dm.sb[PLY]);
+        double* row = MODE == 0 ? c.acc + 32 * (dm.accbase[PLY] + (int)slot - dm.sb[PLY]) : c.acc + 32 * (int)c.accrow[slot];
+        const int plane = MODE == 0 ? 32 * (dm.sb[PLY + 1] - dm.sb[PLY]) : 32;
 #pragma unroll
         for (int i = 0; i < NL - 1; i++) {
             const int e2 = (int)(int8_t)((cfvb >> (8 * i)) & 0xFFu) - last;          // 2 * (cfv_i - cfv_last)
@@ -166,31 +172,33 @@ struct StaticWalk {
 // action and then evaluates it again: both calls walk this same line, so it is played once (and counted twice by the
 // arithmetic visit counters).  Regret delta = w * (cfv - v) = 0 exactly; strategy delta = 1 * [1.0].
 // e = slot of the ply-6 infoset | slot of the ply-7 infoset << 11 | (2 * reward of player 0 + 16) << 22
-template <int TP, bool TOUCH>
+template <int TP, bool TOUCH, int MODE>
 __device__ __forceinline__ int static_endgame(uint32_t e, StaticShared& c) {
-    const uint32_t slot6 = e & 0x7FFu, slot7 = (e >> 11) & 0x7FFu;
-    if (TOUCH) { c.touched[slot6] = 1; c.touched[slot7] = 1; }
-    atomicAdd(&c.dcnt[TP == 0 ? slot6 : slot7], 1u);
+    if (MODE == 0) {
+        const uint32_t slot6 = e & 0x7FFu, slot7 = (e >> 11) & 0x7FFu;
+        if (TOUCH) { c.touched[slot6] = 1; c.touched[slot7] = 1; }
+        atomicAdd(&c.dcnt[TP == 0 ? slot6 : slot7], 1u);
+    }
     const int r = (int)((e >> 22) & 0x3Fu) - 16;
     return TP == 0 ? r : -r;
 }
 
 // ply 5 (two cards in hand): the node record carries the forced endgames of BOTH children, {thr0, first child | slot << 12,
 // endgame of child 0, endgame of child 1}, so the 60 endgames of a traversal cost no further (dependent) load.
-template <int TP, bool TOUCH>
-struct StaticWalk<5, TP, TOUCH> {
+template <int TP, bool TOUCH, int MODE>
+struct StaticWalk<5, TP, TOUCH, MODE> {
     static __device__ __forceinline__ int run(uint32_t node, double w, StaticShared& c, const StaticDims& dm) {
         const uint4 rec = c.node[node];
         const uint32_t slot = rec.y >> 12;
         if (TOUCH) c.touched[slot] = 1;
         const uint32_t u = static_draw(c);
         const uint32_t e_s = (rec.x <= u) ? rec.w : rec.z;           // the sampled child's endgame
-        if (TP == 0) return static_endgame<TP, TOUCH>(e_s, c);      // opponent node: tail call; the weight is dead below
-        const int util = static_endgame<TP, TOUCH>(e_s, c);         // traverser: sampled action, then both actions
-        const int r0 = static_endgame<TP, TOUCH>(rec.z, c);
-        const int r1 = static_endgame<TP, TOUCH>(rec.w, c);
+        if (TP == 0) return static_endgame<TP, TOUCH, MODE>(e_s, c);      // opponent node: tail call; the weight is dead below
+        const int util = static_endgame<TP, TOUCH, MODE>(e_s, c);         // traverser: sampled action, then both actions
+        const int r0 = static_endgame<TP, TOUCH, MODE>(rec.z, c);
+        const int r1 = static_endgame<TP, TOUCH, MODE>(rec.w, c);
         const double val = __dmul_rn(w, 0.5 * (double)(r0 - r1));   // D_0 += w * (cfv_0 - cfv_1)
-        if (val != 0.0) atomicAdd(c.acc + 32 * (dm.accbase[5] + (int)slot - dm.sb[5]), val);
+        if (val != 0.0) atomicAdd(MODE == 0 ? c.acc + 32 * (dm.accbase[5] + (int)slot - dm.sb[5]) : c.acc + 32 * (int)c.accrow[slot], val);
         atomicAdd(&c.dcnt[slot], 1u);
         return util;
     }

@@ -27,7 +27,7 @@ def test_one_deal_reproduces_batch_solver():
     n = 4096
     for b in range(3):
         for p in (0, 1):
-            sv.mccfr_batch(p, n, philox_seed=5, first_trav=b * n, mode=4)     # the multi-deal kernels share the call-indexed stream
+            sv.mccfr_batch(p, n, philox_seed=5, first_trav=b * n, mode=4)     # md_mccfr_kernel shares the call-indexed stream of mode 4
             sv.mccfr_apply()
             md.mccfr_batch(n, philox_seed=5, first_trav=b * n, player=p)
             md.apply()
@@ -87,7 +87,7 @@ def test_blocked_one_deal_reproduces_batch_solver():
     n = 4096
     for b in range(3):
         for p in (0, 1):
-            sv.mccfr_batch(p, n, philox_seed=5, first_trav=b * n, mode=4)     # the multi-deal kernels share the call-indexed stream
+            sv.mccfr_batch(p, n, philox_seed=5, first_trav=b * n)     # mode 0: the same walk and sequential stream as md_blocked_kernel
             sv.mccfr_apply()
             md.mccfr_blocked(1, pairs_per_visit=n, philox_seed=5, first_visit=b, player=p)
             md.apply()

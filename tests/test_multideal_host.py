@@ -134,13 +134,14 @@ def test_many_deals_match_oracle(md, player):
 
 def test_blocked_one_deal_reproduces_batch_solver(md, solver_lib):  # noqa: F811
     """Deal-blocked form (md_build_kernel + md_blocked_kernel), one deal: visit b with n traversal pairs ==
-    mccfr_tree_kernel on ids [n b, n (b + 1))."""
+    mccfr_static_kernel (the one-deal solver's headline kernel: same walk, same sequential Philox stream) on ids
+    [n b, n (b + 1))."""
     sv = HostSolver(solver_lib, 42)
     create(md, [42], 12)
     n = 2048
     for b in range(3):
         for p in (0, 1):
-            assert solver_lib.host_mccfr_batch(4, p, n, 5, b * n) == 0 and solver_lib.host_mccfr_apply() == 0
+            assert solver_lib.host_mccfr_batch(0, p, n, 5, b * n) == 0 and solver_lib.host_mccfr_apply() == 0
             assert md.host_md_blocked(p, b, 1, n, 5) == 0 and md.host_md_apply() == 0
     tab = sv.table()
     c1, _ = _counters(sv)
