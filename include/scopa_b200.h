@@ -395,6 +395,26 @@ int ms_md_export(ms_mdsolver* s, uint64_t* d_keys, double* d_regret, double* d_s
                  void* stream);
 int ms_md_lookup(ms_mdsolver* s, const uint64_t* d_keys, int64_t n, double* d_regret, double* d_strategy,
                  uint8_t* d_found, void* stream);
+/* Table sharded over the GPUs of one box (last sentence: "infosets are shared across deals ... shard by
+ * hash(key) % G with an all-to-all of deltas").  One process per GPU creates its own ms_mdsolver with the SAME seeds;
+ * 2^log2_capacity is then the capacity of one SHARD.  Infoset `key` lives on rank mulhi32(hi32(key * 0xD6E8FEB86659FD93), G),
+ * in that rank's shard; every rank maps every shard (CUDA IPC over NVLink / NVSwitch).  The "all-to-all" is not a
+ * separate collective: ms_md_mccfr_blocked gathers the frozen regrets of a deal's infosets straight from the owners'
+ * shards and sends its deltas to them as fp64 RED.ADDs through peer memory, inside the traversal kernel.  One iteration:
+ *     ms_md_mccfr_blocked(this rank's visits) ; ms_md_peer_barrier ; ms_md_apply (own shard) ; ms_md_peer_barrier.
+ * Visit ids are global, so the union of all ranks' visits -- and the table -- does not depend on G (up to the order
+ * of the fp64 additions).
+ * ms_md_ipc_export: two 64-byte IPC handles (table shard, dirty bitmap + barrier flags) into handles128.
+ * ms_md_ipc_attach: handles = world x 128 bytes in rank order; before the first traversal, on a fresh table.  Afterwards
+ *   ms_md_reset is refused (MS_ERR_STATE), ms_md_export lists THIS rank's shard (max_n = 0: count only, pointers may be
+ *   NULL), ms_md_lookup reads any rank's shard, ms_md_counters[3] counts the infosets this rank created.
+ * ms_md_peer_barrier: stream-ordered barrier across the attached ranks (a no-op when not attached); a peer that does
+ *   not arrive within 2 s sets a sticky error word instead of hanging the GPU: ms_md_peer_error returns MS_ERR_STATE
+ *   and *h_err = 1 + that rank (synchronises). */
+int ms_md_ipc_export(ms_mdsolver* s, void* handles128);
+int ms_md_ipc_attach(ms_mdsolver* s, int32_t rank, int32_t world, const void* handles);
+int ms_md_peer_barrier(ms_mdsolver* s, void* stream);
+int ms_md_peer_error(ms_mdsolver* s, uint32_t* h_err, void* stream);
 /* measurement hook: random-access ceilings of the table's pattern over a zeroed buffer of 2^log2_lines 128-byte
  * lines, 148 x 768 threads: h_out[0] dependent 64-byte reads/s (one in flight per thread), [1] independent 64-byte
  * reads/s (8 in flight per thread), [2] random lines/s receiving four fp64 RED.ADDs */

@@ -101,6 +101,10 @@ _SIGS = {
     "ms_md_counters": ([vp, C.POINTER(u64), C.c_int, vp], C.c_int),
     "ms_md_export": ([vp, vp, vp, vp, i64, C.POINTER(i64), vp], C.c_int),
     "ms_md_lookup": ([vp, vp, i64, vp, vp, vp, vp], C.c_int),
+    "ms_md_ipc_export": ([vp, vp], C.c_int),
+    "ms_md_ipc_attach": ([vp, i32, i32, vp], C.c_int),
+    "ms_md_peer_barrier": ([vp, vp], C.c_int),
+    "ms_md_peer_error": ([vp, C.POINTER(C.c_uint32), vp], C.c_int),
     "ms_debug_random_access_peaks": ([i32, C.POINTER(dbl), vp], C.c_int),
 }
 

@@ -43,17 +43,50 @@ struct __align__(128) MdSlot {
 };
 static_assert(sizeof(MdSlot) == 128, "one cache line per infoset");
 
+constexpr int MD_MAX_PEERS = 8;
+
 struct MdDev {
-    MdSlot* slots;
-    unsigned long long mask;     // capacity - 1
-    int shift;                   // 64 - log2(capacity)
+    MdSlot* slots;               // this rank's shard of the table (the whole table on one GPU)
+    unsigned long long mask;     // capacity of a shard - 1
+    int shift;                   // 64 - log2(capacity of a shard)
     unsigned int max_probe;
     const uint4* roots;          // [n_deals] dealt states
     const uint32_t* hand_order;  // [n_deals]
     unsigned int n_deals;
     unsigned int* dirty;         // one bit per slot: touched by an update of the running batch (L2-resident: 16 MB at 2^27)
     unsigned long long* counters;   // [0] updates [1] visits [2] env steps [3] infosets [4] overflow / invariant flag
+    // Table sharded over the GPUs of one box ("shard by hash(key) % G"; ms_md_ipc_attach): infoset `key`
+    // lives on rank md_owner(key), in that rank's shard, which every rank has mapped (CUDA IPC over NVLink / NVSwitch).
+    // A global slot id is owner << lshift | slot inside the shard.  One GPU: world = 1, peer_slots[0] = slots.
+    int world, rank, lshift;
+    MdSlot* peer_slots[MD_MAX_PEERS];
+    unsigned int* peer_dirty[MD_MAX_PEERS];
 };
+
+// Which rank's shard holds `key`: a second multiplicative hash, independent of the probe position inside the shard.
+__device__ __forceinline__ int md_owner(const MdDev& t, unsigned long long key) {
+    if (t.world <= 1) return 0;
+    return (int)__umulhi((uint32_t)((key * 0xD6E8FEB86659FD93ull) >> 32), (uint32_t)t.world);
+}
+__device__ __forceinline__ MdSlot* md_slot(const MdDev& t, long long g) {
+    return t.peer_slots[(int)(g >> t.lshift)] + (g & (long long)t.mask);
+}
+// Table words another GPU may have written (peers' REDs, the owner's apply step) are read past L1 and, on a sharded
+// table, as system-scope volatile loads: a peer's line is never served from a cache on this side of the link.
+template <class T>
+__device__ __forceinline__ T md_ld(const MdDev& t, const T* p) { return t.world > 1 ? __ldcv(p) : __ldcg(p); }
+// Updates: RED.ADDs performed at the owner's L2; system scope when the owner is (or may be) another GPU.
+__device__ __forceinline__ void md_add(const MdDev& t, double* p, double v) {
+    if (t.world > 1) atomicAdd_system(p, v); else atomicAdd(p, v);
+}
+__device__ __forceinline__ void md_add(const MdDev& t, unsigned int* p, unsigned int v) {
+    if (t.world > 1) atomicAdd_system(p, v); else atomicAdd(p, v);
+}
+__device__ __forceinline__ void md_mark_dirty(const MdDev& t, long long g) {
+    const long long l = g & (long long)t.mask;
+    unsigned int* w = t.peer_dirty[(int)(g >> t.lshift)] + (l >> 5);
+    if (t.world > 1) atomicOr_system(w, 1u << (l & 31)); else atomicOr(w, 1u << (l & 31));
+}
 
 constexpr uint32_t MS_TAG_DEAL = 0x4C414544u;   // "DEAL"
 constexpr int MD_THREADS = 768;
@@ -72,19 +105,22 @@ __device__ __forceinline__ unsigned long long md_hash(unsigned long long key, in
 // measured and doubled the traversal time there -- and the table is sized for a low load factor instead, because a
 // warp waits for the slowest of its 32 lookups.
 // Returns -1 (and raises the overflow flag) when the probe limit is reached.
+// Returns the GLOBAL slot id (= the slot on one GPU).
 __device__ __forceinline__ long long md_find_regrets(const MdDev& t, unsigned long long key, double* reg, uint32_t& n_ins) {
     unsigned long long h = md_hash(key, t.shift);
+    const int owner = md_owner(t, key);
+    MdSlot* base = t.peer_slots[owner];
     for (unsigned int probe = 0; probe < t.max_probe; probe++) {
-        MdSlot* a = t.slots + h;
-        unsigned long long ka = __ldcg(&a->key);
-        const double2 a01 = __ldcg((const double2*)&a->regret[0]), a23 = __ldcg((const double2*)&a->regret[2]);
+        MdSlot* a = base + h;
+        unsigned long long ka = md_ld(t, &a->key);
+        const double2 a01 = md_ld(t, (const double2*)&a->regret[0]), a23 = md_ld(t, (const double2*)&a->regret[2]);
         bool fresh = false;
-        if (ka == 0ull) { ka = atomicCAS(&a->key, 0ull, key); fresh = ka == 0ull; }
+        if (ka == 0ull) { ka = t.world > 1 ? atomicCAS_system(&a->key, 0ull, key) : atomicCAS(&a->key, 0ull, key); fresh = ka == 0ull; }
         if (fresh || ka == key) {
             n_ins += fresh ? 1u : 0u;
             reg[0] = fresh ? 0.0 : a01.x; reg[1] = fresh ? 0.0 : a01.y;
             reg[2] = fresh ? 0.0 : a23.x; reg[3] = fresh ? 0.0 : a23.y;
-            return (long long)h;
+            return ((long long)owner << t.lshift) | (long long)h;
         }
         h = (h + 1ull) & t.mask;
     }
@@ -310,11 +346,11 @@ __device__ void md_traverse(const MdDev& t, const MsState root, int tp,
             const uint32_t list = meta.y & 0xFFFFu;
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (i < nl) atomicAdd(&t.slots[slot].delta[md_col(hand, list, i)], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
+                if (i < nl) md_add(t, &md_slot(t, slot)->delta[md_col(hand, list, i)], __dmul_rn(w, __dadd_rn(cfv[i], -v)));
         }
         if (slot >= 0) {
-            atomicAdd(&t.slots[slot].cnt, 1u);
-            atomicOr(&t.dirty[slot >> 5], 1u << (slot & 31));
+            md_add(t, &md_slot(t, slot)->cnt, 1u);
+            md_mark_dirty(t, slot);
         }
         c.upd++;
         ret_x2 = (int)(int8_t)((meta.y >> 16) & 0xFFu);
@@ -413,9 +449,10 @@ __global__ void __launch_bounds__(256) md_lookup_kernel(MdDev t, const unsigned 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
         const unsigned long long key = keys[i];
         unsigned long long h = md_hash(key, t.shift);
+        const MdSlot* base = t.peer_slots[md_owner(t, key)];      // any rank can look any infoset up
         long long slot = -1;
         for (unsigned int probe = 0; probe < t.max_probe; probe++) {
-            const unsigned long long k = t.slots[h].key;
+            const unsigned long long k = md_ld(t, &base[h].key);
             if (k == key) { slot = (long long)h; break; }
             if (k == 0ull) break;
             h = (h + 1ull) & t.mask;
@@ -424,8 +461,8 @@ __global__ void __launch_bounds__(256) md_lookup_kernel(MdDev t, const unsigned 
         if (found) found[i] = slot >= 0;
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-            if (regret) regret[4 * i + a] = slot >= 0 ? t.slots[slot].regret[a] : 0.0;
-            if (strategy) strategy[4 * i + a] = slot >= 0 ? t.slots[slot].strategy[a] : 0.0;
+            if (regret) regret[4 * i + a] = slot >= 0 ? md_ld(t, &base[slot].regret[a]) : 0.0;
+            if (strategy) strategy[4 * i + a] = slot >= 0 ? md_ld(t, &base[slot].strategy[a]) : 0.0;
         }
     }
 }
@@ -643,9 +680,9 @@ __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, con
         const int n_local = (int)di->n_local, n_acc = (int)di->n_acc;
         for (int j = tid; j < n_local; j += T) {           // gather: one table line per infoset of the deal
             const uint32_t ls = di->local_slot[j];
-            const MdSlot* sl = t.slots + (ls & 0x3FFFFFFFu);
+            const MdSlot* sl = md_slot(t, (long long)(ls & 0x3FFFFFFFu));     // on a sharded table: 7 of 8 lines over NVLink
             const int nl = (int)(ls >> 30) + 2;
-            const double2 r01 = __ldcg((const double2*)&sl->regret[0]), r23 = __ldcg((const double2*)&sl->regret[2]);
+            const double2 r01 = md_ld(t, (const double2*)&sl->regret[0]), r23 = md_ld(t, (const double2*)&sl->regret[2]);
             const double reg[4] = {r01.x, r01.y, r23.x, r23.y};
             double sc[4], sg[4], cd[4];
             md_regret_match(reg, nl, sc);                  // over the table's columns, like the apply step
@@ -704,10 +741,10 @@ __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, con
             for (int k = 0; k < nl; k++) {
                 const double Dk = k == 0 ? D0 : (k == 1 ? D1 : D2);
                 const double v = k < nl - 1 ? __dadd_rn(Dk, -sum) : -sum;
-                if (v != 0.0) atomicAdd(&t.slots[slot].delta[(perm >> (2 * k)) & 3u], v);
+                if (v != 0.0) md_add(t, &md_slot(t, slot)->delta[(perm >> (2 * k)) & 3u], v);
             }
-            atomicAdd(&t.slots[slot].cnt, cnt);
-            atomicOr(&t.dirty[slot >> 5], 1u << (slot & 31));
+            md_add(t, &md_slot(t, slot)->cnt, cnt);
+            md_mark_dirty(t, slot);
         }
     }
     for (int off = 16; off > 0; off >>= 1) {
@@ -716,6 +753,50 @@ __global__ void __launch_bounds__(MDB_THREADS, 1) md_blocked_kernel(MdDev t, con
         ns += __shfl_down_sync(0xffffffffu, ns, off);
     }
     if ((tid & 31) == 0) { atomicAdd(&t.counters[0], nu); atomicAdd(&t.counters[1], nv); atomicAdd(&t.counters[2], ns); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Barrier between the GPUs that share a sharded table.  One iteration is
+//     md_blocked_kernel (gather of frozen regrets and REDs of deltas, both through peer memory)
+//     -> barrier -> md_apply_kernel (every rank folds the deltas of ITS shard in) -> barrier -> next iteration,
+// and the barrier is this kernel, stream-ordered between them: one thread per peer fences at system scope, writes the
+// epoch into its slot of that peer's flag array (st.release.sys) and waits (bounded) until its own array shows the
+// epoch from every peer (ld.acquire.sys).  The kernel before it on the stream has completed, so its peer stores and
+// REDs are performed before the flags are written; a rank that passes the barrier therefore sees every rank's updates.
+// err[0]: 0 = fine, else 1 + the first peer that did not arrive in time; sticky (ms_md_peer_error).
+struct MdPeerSync {
+    unsigned long long* flags[MD_MAX_PEERS];    // rank r's flag array ([MD_MAX_PEERS] u64), mapped here
+    unsigned long long* my_flags;
+    int rank, world;
+};
+#ifndef MS_CTA_EMU
+__device__ __forceinline__ void md_peer_signal(unsigned long long* flag, unsigned long long epoch) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(epoch) : "memory");
+}
+__device__ __forceinline__ unsigned long long md_peer_poll(const unsigned long long* flag) {
+    unsigned long long seen;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+    return seen;
+}
+__device__ __forceinline__ unsigned long long md_peer_clock_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void md_peer_fence() { __threadfence_system(); }
+#endif
+constexpr unsigned long long MD_PEER_TIMEOUT_NS = 2000000000ull;
+
+__global__ void __launch_bounds__(32) md_peer_barrier_kernel(MdPeerSync ps, unsigned long long epoch, unsigned int* err) {
+    const int tid = threadIdx.x;
+    if (tid >= ps.world) return;
+    if (*(volatile unsigned int*)err != 0u) return;
+    md_peer_fence();
+    md_peer_signal(ps.flags[tid] + ps.rank, epoch);
+    const unsigned long long t0 = md_peer_clock_ns();
+    while (md_peer_poll(ps.my_flags + tid) < epoch) {
+        if (md_peer_clock_ns() - t0 > MD_PEER_TIMEOUT_NS) { atomicCAS(err, 0u, 1u + (unsigned)tid); break; }
+    }
 }
 
 }  // namespace ms
@@ -731,7 +812,18 @@ struct ms_mdsolver {
     uint4* d_roots; uint32_t* d_hand_order;
     unsigned long long* d_counters;    // 5 counters + 1 export cursor
     MdDealInfo* d_info;                // per-deal tree descriptions of the deal-blocked form (built on first use)
+    // sharded table (ms_md_ipc_export / ms_md_ipc_attach / ms_md_peer_barrier)
+    unsigned long long* d_flags;       // [MD_MAX_PEERS] barrier flags, inside the dirty bitmap's allocation (one IPC handle)
+    unsigned int* d_peer_err;          // device word set by the barrier when a peer did not arrive
+    int attached, rank, world;
+    unsigned long long epoch;
+    void* peer_slots_base[MD_MAX_PEERS];
+    void* peer_aux_base[MD_MAX_PEERS];
 };
+
+// the dirty bitmap's allocation: [capacity / 32 words] then, 256-byte aligned, [MD_MAX_PEERS] u64 flags and the error word
+static size_t md_aux_flags_off(int log2cap) { return ((((size_t)1 << log2cap) >> 5) * sizeof(unsigned int) + 255) & ~(size_t)255; }
+static size_t md_aux_bytes(int log2cap) { return md_aux_flags_off(log2cap) + 256; }
 
 extern "C" {
 
@@ -750,7 +842,7 @@ int ms_md_create(const int64_t* d_seeds, int64_t n_deals, int32_t log2_capacity,
     if (e == cudaSuccess) e = cudaMalloc(&s->d_roots, (size_t)n_deals * sizeof(uint4));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_hand_order, (size_t)n_deals * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, 8 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&s->dev.dirty, (cap >> 5) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&s->dev.dirty, md_aux_bytes(log2_capacity));
     if (e != cudaSuccess) {
         cudaFree(s->dev.slots); cudaFree(s->dev.dirty); cudaFree(s->d_roots); cudaFree(s->d_hand_order); cudaFree(s->d_counters);
         delete s;
@@ -763,6 +855,11 @@ int ms_md_create(const int64_t* d_seeds, int64_t n_deals, int32_t log2_capacity,
     s->dev.roots = s->d_roots; s->dev.hand_order = s->d_hand_order;
     s->dev.n_deals = (unsigned int)n_deals;
     s->dev.counters = s->d_counters;
+    s->dev.world = 1; s->dev.rank = 0; s->dev.lshift = log2_capacity;
+    s->dev.peer_slots[0] = s->dev.slots; s->dev.peer_dirty[0] = s->dev.dirty;
+    s->world = 1;
+    s->d_flags = (unsigned long long*)((char*)s->dev.dirty + md_aux_flags_off(log2_capacity));
+    s->d_peer_err = (unsigned int*)(s->d_flags + MD_MAX_PEERS);
     int rc = ms_deal_from_seeds(d_seeds, n_deals, (ms_state*)s->d_roots, s->d_hand_order, stream);
     if (rc == MS_OK) rc = ms_md_reset(s, stream);
     if (rc != MS_OK) { ms_md_destroy(s); return rc; }
@@ -772,6 +869,12 @@ int ms_md_create(const int64_t* d_seeds, int64_t n_deals, int32_t log2_capacity,
 
 void ms_md_destroy(ms_mdsolver* s) {
     if (!s) return;
+    if (s->attached)
+        for (int r = 0; r < s->world; r++) {
+            if (r == s->rank) continue;
+            if (s->peer_slots_base[r]) cudaIpcCloseMemHandle(s->peer_slots_base[r]);
+            if (s->peer_aux_base[r]) cudaIpcCloseMemHandle(s->peer_aux_base[r]);
+        }
     cudaFree(s->dev.slots); cudaFree(s->dev.dirty); cudaFree(s->d_roots); cudaFree(s->d_hand_order); cudaFree(s->d_counters);
     cudaFree(s->d_info);
     delete s;
@@ -779,8 +882,10 @@ void ms_md_destroy(ms_mdsolver* s) {
 
 int ms_md_reset(ms_mdsolver* s, void* stream) {
     if (!s) return fail(MS_ERR_ARG, "ms_md_reset: NULL handle");
+    // peers read and update this shard at their own pace: clearing it under them would race
+    if (s->attached) return fail(MS_ERR_STATE, "ms_md_reset: the table is shared with peers (create a new solver instead)");
     MS_CUDA(cudaMemsetAsync(s->dev.slots, 0, ((size_t)1 << s->log2cap) * sizeof(MdSlot), (cudaStream_t)stream));
-    MS_CUDA(cudaMemsetAsync(s->dev.dirty, 0, (((size_t)1 << s->log2cap) >> 5) * sizeof(unsigned int), (cudaStream_t)stream));
+    MS_CUDA(cudaMemsetAsync(s->dev.dirty, 0, md_aux_bytes(s->log2cap), (cudaStream_t)stream));
     MS_CUDA(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
     if (s->d_info) {            // the deal descriptions name table slots: they die with the table's keys
         MS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -830,7 +935,8 @@ int ms_md_counters(ms_mdsolver* s, uint64_t h_out[5], int reset, void* stream) {
 
 int ms_md_export(ms_mdsolver* s, uint64_t* d_keys, double* d_regret, double* d_strategy, int64_t max_n, int64_t* h_n,
                  void* stream) {
-    if (!s || !d_keys || !d_regret || !d_strategy || !h_n || max_n < 0) return fail(MS_ERR_ARG, "ms_md_export: bad argument");
+    if (!s || !h_n || max_n < 0 || (max_n > 0 && (!d_keys || !d_regret || !d_strategy)))      // max_n = 0: count only
+        return fail(MS_ERR_ARG, "ms_md_export: bad argument");
     MS_CUDA(cudaMemsetAsync(s->d_counters + 5, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     const int64_t cap = (int64_t)1 << s->log2cap;
     md_export_kernel<<<grid_for(cap, 256, 8), 256, 0, (cudaStream_t)stream>>>(
@@ -840,7 +946,7 @@ int ms_md_export(ms_mdsolver* s, uint64_t* d_keys, double* d_regret, double* d_s
     MS_CUDA(cudaMemcpyAsync(&n, s->d_counters + 5, sizeof(n), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     *h_n = (int64_t)n;
-    if ((int64_t)n > max_n) return fail(MS_ERR_CAPACITY, "ms_md_export: %llu infosets, buffers hold %lld", n, (long long)max_n);
+    if ((int64_t)n > max_n && max_n > 0) return fail(MS_ERR_CAPACITY, "ms_md_export: %llu infosets, buffers hold %lld", n, (long long)max_n);
     return MS_OK;
 }
 
@@ -860,7 +966,9 @@ int ms_md_mccfr_blocked(ms_mdsolver* s, int32_t player, int64_t first_visit, int
     if (player < 0 || player > 2 || first_visit < 0 || n_visits < 0 || pairs_per_visit < 1 || pairs_per_visit > (1 << 24))
         return fail(MS_ERR_ARG, "ms_md_mccfr_blocked: bad argument");
     if (n_visits == 0) return MS_OK;
-    if (s->log2cap > 30) return fail(MS_ERR_ARG, "ms_md_mccfr_blocked: table slots must fit 30 bits");
+    int owner_bits = 0;
+    while ((1 << owner_bits) < s->world) owner_bits++;
+    if (s->log2cap + owner_bits > 30) return fail(MS_ERR_ARG, "ms_md_mccfr_blocked: global table slots must fit 30 bits");
     if (!s->d_info) {                                      // describe every deal's tree once; claims the table slots
         MS_CUDA(cudaMalloc(&s->d_info, (size_t)s->n_deals * sizeof(MdDealInfo)));
         md_build_kernel<<<grid_for(s->n_deals * 256, 256, 4), 256, 0, (cudaStream_t)stream>>>(s->dev, s->d_info);
@@ -873,6 +981,63 @@ int ms_md_mccfr_blocked(ms_mdsolver* s, int32_t player, int64_t first_visit, int
         s->dev, s->d_info, player, (unsigned long long)first_visit, (long long)n_visits, pairs_per_visit,
         make_uint2((uint32_t)philox_seed, (uint32_t)(philox_seed >> 32)));
     MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+/* ---- table sharded over the GPUs of one box ---- */
+
+int ms_md_ipc_export(ms_mdsolver* s, void* handles128) {
+    if (!s || !handles128) return fail(MS_ERR_ARG, "ms_md_ipc_export: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    MS_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handles128, s->dev.slots));
+    MS_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)((char*)handles128 + 64), s->dev.dirty));
+    return MS_OK;
+}
+
+int ms_md_ipc_attach(ms_mdsolver* s, int32_t rank, int32_t world, const void* handles) {
+    if (!s || !handles || world < 1 || world > MD_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(MS_ERR_ARG, "ms_md_ipc_attach: bad argument (at most %d ranks)", MD_MAX_PEERS);
+    if (s->attached) return fail(MS_ERR_STATE, "the table is already attached to its peers");
+    if (s->d_info) return fail(MS_ERR_STATE, "ms_md_ipc_attach: attach before the first traversal (the deal descriptions name table slots)");
+    int owner_bits = 0;
+    while ((1 << owner_bits) < world) owner_bits++;
+    if (s->log2cap + owner_bits > 30) return fail(MS_ERR_ARG, "ms_md_ipc_attach: 2^%d slots x %d ranks exceed the 30-bit global slot id", s->log2cap, world);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { s->peer_slots_base[r] = s->dev.slots; s->peer_aux_base[r] = s->dev.dirty; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + 128 * (size_t)r, 64);
+        MS_CUDA(cudaIpcOpenMemHandle(&s->peer_slots_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+        std::memcpy(&h, (const char*)handles + 128 * (size_t)r + 64, 64);
+        MS_CUDA(cudaIpcOpenMemHandle(&s->peer_aux_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    for (int r = 0; r < world; r++) {
+        s->dev.peer_slots[r] = (MdSlot*)s->peer_slots_base[r];
+        s->dev.peer_dirty[r] = (unsigned int*)s->peer_aux_base[r];
+    }
+    s->dev.world = world; s->dev.rank = rank;
+    s->rank = rank; s->world = world; s->attached = 1; s->epoch = 0;
+    return MS_OK;
+}
+
+int ms_md_peer_barrier(ms_mdsolver* s, void* stream) {
+    if (!s) return fail(MS_ERR_ARG, "ms_md_peer_barrier: NULL handle");
+    if (!s->attached) return MS_OK;                        // one GPU: stream order is the barrier
+    MdPeerSync ps{};
+    const size_t flags_off = md_aux_flags_off(s->log2cap);
+    for (int r = 0; r < s->world; r++) ps.flags[r] = (unsigned long long*)((char*)s->peer_aux_base[r] + flags_off);
+    ps.my_flags = s->d_flags; ps.rank = s->rank; ps.world = s->world;
+    s->epoch++;
+    md_peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ps, s->epoch, s->d_peer_err);
+    MS_LAUNCH_CHECK();
+    return MS_OK;
+}
+
+int ms_md_peer_error(ms_mdsolver* s, uint32_t* h_err, void* stream) {
+    if (!s || !h_err) return fail(MS_ERR_ARG, "ms_md_peer_error: bad argument");
+    MS_CUDA(cudaMemcpyAsync(h_err, s->d_peer_err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (*h_err) return fail(MS_ERR_STATE, "multi-deal peer barrier: rank %u did not arrive within %llu ms", *h_err - 1u,
+                            (unsigned long long)(MD_PEER_TIMEOUT_NS / 1000000ull));
     return MS_OK;
 }
 

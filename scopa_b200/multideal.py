@@ -84,6 +84,72 @@ class MultiDealSolver:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ms_md_reset(self.h, self._stream()))
 
+    # ---- the table sharded over the GPUs of one box (one process per GPU; SURVEY.md 8(e), last sentence) ----
+
+    def attach_peers(self, group=None):
+        """Shard the infoset table over the ranks of `group`: infoset `key` then lives on rank owner(key) (a hash of
+        the key), in that rank's table, and every rank maps every rank's table (CUDA IPC over NVLink / NVSwitch).
+        Collective; every rank must have created its solver with the same seeds and capacity (= the capacity of ONE
+        shard), and must call this before its first traversal.  A failure on any rank raises MsError on every rank."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handles = (C.c_ubyte * 128)()
+        err = None
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.ms_md_ipc_export(self.h, handles))
+        except _lib.MsError as e:
+            err = e
+        everyone = [None] * world
+        dist.all_gather_object(everyone, None if err else bytes(handles), group=group)
+        if err is None and all(x is not None for x in everyone):
+            try:
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.ms_md_ipc_attach(self.h, rank, world, b"".join(everyone)))
+            except _lib.MsError as e:
+                err = e
+        ok = torch.tensor([0.0 if (err is not None or any(x is None for x in everyone)) else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() < 1.0:
+            raise _lib.MsError(f"MultiDealSolver.attach_peers failed on at least one rank (this rank: {err or 'ok'})")
+        self.group, self.rank, self.world = group, rank, world
+
+    def barrier(self):
+        """Stream-ordered barrier across the attached ranks (bounded: see peer_error); a no-op on one GPU."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_md_peer_barrier(self.h, self._stream()))
+
+    def peer_error(self):
+        """0, or 1 + the rank that did not arrive at a barrier within its time limit (synchronises)."""
+        err = C.c_uint32(0)
+        with torch.cuda.device(self.device):
+            self.lib.ms_md_peer_error(self.h, C.byref(err), self._stream())
+        return int(err.value)
+
+    def iterate_blocked(self, n_visits, pairs_per_visit=3072, philox_seed=0, first_visit=0, player=2):
+        """One iteration of the deal-blocked solver over ALL ranks: this rank runs its share of the visits
+        [first_visit, first_visit + n_visits) -- regrets gathered from, deltas sent to the owners' shards inside the
+        kernel --, then every rank folds the deltas of its own shard in.  Same table as one GPU running all the visits."""
+        from .sharding import shard_bounds
+        lo, n = shard_bounds(int(n_visits), getattr(self, "rank", 0), getattr(self, "world", 1))
+        self.mccfr_blocked(n, pairs_per_visit, philox_seed, first_visit + lo, player)
+        self.barrier()
+        self.apply()
+        self.barrier()
+
+    def export_shard(self):
+        """-> keys, regret, strategy of the infosets in THIS rank's shard (unsorted numpy arrays)."""
+        got = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ms_md_export(self.h, None, None, None, 0, C.byref(got), self._stream()))
+            n = got.value
+            keys = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+            reg = torch.empty((max(n, 1), 4), dtype=torch.float64, device=self.device)
+            strat = torch.empty((max(n, 1), 4), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.ms_md_export(self.h, keys.data_ptr(), reg.data_ptr(), strat.data_ptr(), n, C.byref(got),
+                                             self._stream()))
+        return keys[:n].cpu().numpy().view(np.uint64), reg[:n].cpu().numpy(), strat[:n].cpu().numpy()
+
     def mccfr_batch(self, n_trav, philox_seed=0, first_trav=0, player=2):
         """Launch n_trav traversals (each: one sampled deal, traverser = player, or both when player == 2) against
         the strategies frozen at launch; deltas stay in the table until apply()."""
@@ -111,7 +177,15 @@ class MultiDealSolver:
         return {"updates": out[0], "visits": out[1], "env_steps": out[2], "infosets": out[3]}
 
     def export(self):
-        """-> keys [n] uint64 (numpy, sorted), regret [n,4], strategy [n,4] float64 of every infoset in the table"""
+        """-> keys [n] uint64 (numpy, sorted), regret [n,4], strategy [n,4] float64 of every infoset in the table
+        (on a sharded table: of all shards, gathered from every rank -- a collective)"""
+        if getattr(self, "world", 1) > 1:
+            import torch.distributed as dist
+            parts = [None] * self.world
+            dist.all_gather_object(parts, self.export_shard(), group=self.group)
+            k = np.concatenate([p[0] for p in parts])
+            order = np.argsort(k, kind="stable")
+            return k[order], np.concatenate([p[1] for p in parts])[order], np.concatenate([p[2] for p in parts])[order]
         n = int(self.counters()["infosets"])
         keys = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
         reg = torch.empty((max(n, 1), 4), dtype=torch.float64, device=self.device)

@@ -23,6 +23,7 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
+template <class T> static inline T __ldcv(const T* p) { return *p; }
 static inline size_t __cvta_generic_to_shared(const void*) { return 0; }   // feeds the tcgen05 / mbarrier PTX only, never run
 
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
@@ -45,6 +46,12 @@ static inline double atomicAdd(double* p, double v) {
     std::memcpy(&cur, &old, 8);
     return cur;
 }
+
+// system-scope forms (peer memory over NVLink on the device): the same host atomics
+static inline unsigned atomicAdd_system(unsigned* p, unsigned v) { return atomicAdd(p, v); }
+static inline double atomicAdd_system(double* p, double v) { return atomicAdd(p, v); }
+static inline unsigned atomicOr_system(unsigned* p, unsigned v) { return atomicOr(p, v); }
+static inline unsigned long long atomicCAS_system(unsigned long long* p, unsigned long long cmp, unsigned long long val) { return atomicCAS(p, cmp, val); }
 
 // CUDA's function / variable qualifiers (cuda_runtime.h defines some of them for the host compiler): cleared here; the
 // one-thread builds then define the few they need, the CTA-emulator builds include cta_emu.h

@@ -17,6 +17,19 @@
 static inline void __syncwarp() { __syncthreads(); }
 #include "cta_emu_warp.h"
 
+// the barrier's memory operations (ms_multideal.cu defines the PTX forms for the device)
+#include <chrono>
+static inline void md_peer_signal(unsigned long long* flag, unsigned long long epoch) { __atomic_store_n(flag, epoch, __ATOMIC_RELEASE); }
+static inline unsigned long long md_peer_poll(const unsigned long long* flag) { return __atomic_load_n(flag, __ATOMIC_ACQUIRE); }
+static inline unsigned long long md_peer_clock_ns() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static inline void md_peer_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned val) {
+    __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+    return cmp;
+}
+
 #define MS_HOST_RULES_ONLY
 #include "../../scopa_b200/csrc/ms_multideal.cu"
 
@@ -35,7 +48,16 @@ struct HostMd {
     std::vector<unsigned int> dirty;
     MdSlot* slots = nullptr;
     std::vector<MdDealInfo> info; bool have_info = false;
-} M;
+    std::vector<unsigned long long> flags;      // barrier flags of this "rank"
+    unsigned int peer_err = 0;
+};
+// Several emulated RANKS in one process (host_md_world_create): each owns a shard of the table, a dirty bitmap, counters
+// and deal descriptions, and sees the others' shards through MdDev::peer_slots / peer_dirty -- exactly what CUDA IPC
+// gives the device build.  host_md_select picks the rank the calls below act on.
+HostMd RANKS[MD_MAX_PEERS];
+int CUR = 0, WORLD = 1;
+unsigned long long EPOCH = 0;
+#define M RANKS[CUR]
 
 unsigned grid_of(long long n, int block, int per_sm) {
     long long need = (n + block - 1) / block, cap = 148LL * per_sm;
@@ -59,9 +81,31 @@ void lookup_entry(LookupArgs a) { md_lookup_kernel(a.t, a.keys, a.n, a.reg, a.st
 extern "C" {
 
 // ms_md_create + ms_md_reset with the roots already dealt (states [n][4] u32, hand_order [n])
+static int create_rank(const uint32_t* roots4, const uint32_t* hand_order, long long n_deals, int log2_capacity);
+
 int host_md_create(const uint32_t* roots4, const uint32_t* hand_order, long long n_deals, int log2_capacity) {
-    if (M.slots) std::free(M.slots);
-    M = HostMd();
+    for (int r = 0; r < MD_MAX_PEERS; r++) { if (RANKS[r].slots) std::free(RANKS[r].slots); RANKS[r] = HostMd(); }
+    CUR = 0; WORLD = 1; EPOCH = 0;
+    return create_rank(roots4, hand_order, n_deals, log2_capacity);
+}
+
+// `world` ranks with the same deals, every shard 2^log2_capacity slots, wired to each other like ms_md_ipc_attach does
+int host_md_world_create(const uint32_t* roots4, const uint32_t* hand_order, long long n_deals, int log2_capacity, int world) {
+    if (world < 1 || world > MD_MAX_PEERS) return -2;
+    for (int r = 0; r < MD_MAX_PEERS; r++) { if (RANKS[r].slots) std::free(RANKS[r].slots); RANKS[r] = HostMd(); }
+    WORLD = world; EPOCH = 0;
+    for (int r = 0; r < world; r++) { CUR = r; if (create_rank(roots4, hand_order, n_deals, log2_capacity)) return -1; }
+    for (int r = 0; r < world; r++) {
+        RANKS[r].dev.world = world; RANKS[r].dev.rank = r;
+        for (int q = 0; q < world; q++) { RANKS[r].dev.peer_slots[q] = RANKS[q].slots; RANKS[r].dev.peer_dirty[q] = RANKS[q].dirty.data(); }
+    }
+    CUR = 0;
+    return 0;
+}
+
+int host_md_select(int rank) { if (rank < 0 || rank >= WORLD) return -1; CUR = rank; return 0; }
+
+static int create_rank(const uint32_t* roots4, const uint32_t* hand_order, long long n_deals, int log2_capacity) {
     M.log2cap = log2_capacity;
     const size_t cap = (size_t)1 << log2_capacity;
     M.slots = (MdSlot*)std::aligned_alloc(128, cap * sizeof(MdSlot));
@@ -77,6 +121,9 @@ int host_md_create(const uint32_t* roots4, const uint32_t* hand_order, long long
     M.dev.max_probe = cap < 8192 ? (unsigned int)cap : 8192u;
     M.dev.roots = M.roots.data(); M.dev.hand_order = M.hand_order.data(); M.dev.n_deals = (unsigned int)n_deals;
     M.dev.dirty = M.dirty.data(); M.dev.counters = M.counters.data();
+    M.dev.world = 1; M.dev.rank = 0; M.dev.lshift = log2_capacity;
+    M.dev.peer_slots[0] = M.slots; M.dev.peer_dirty[0] = M.dirty.data();
+    M.flags.assign(MD_MAX_PEERS, 0ull);
     return 0;
 }
 
@@ -108,6 +155,25 @@ void host_md_counters(unsigned long long* out5, int reset) {
     for (int i = 0; i < 5; i++) out5[i] = M.counters[i];
     if (reset) for (int i = 0; i < 3; i++) M.counters[i] = 0;
 }
+
+// ms_md_peer_barrier on every rank at once: md_peer_barrier_kernel, one block per emulated rank, running concurrently.
+// `absent` >= 0: that rank does not show up (its block returns at once) -- the others must time out and report it.
+struct BarrierArgs { MdPeerSync ps[MD_MAX_PEERS]; unsigned long long epoch; unsigned int* err[MD_MAX_PEERS]; int absent; };
+static void barrier_entry(BarrierArgs a) {
+    if ((int)blockIdx.x == a.absent) return;
+    md_peer_barrier_kernel(a.ps[blockIdx.x], a.epoch, a.err[blockIdx.x]);
+}
+int host_md_barrier_all(int absent) {
+    BarrierArgs a{};
+    a.epoch = ++EPOCH; a.absent = absent;
+    for (int r = 0; r < WORLD; r++) {
+        for (int q = 0; q < WORLD; q++) a.ps[r].flags[q] = RANKS[q].flags.data();
+        a.ps[r].my_flags = RANKS[r].flags.data(); a.ps[r].rank = r; a.ps[r].world = WORLD;
+        a.err[r] = &RANKS[r].peer_err;
+    }
+    return emu_launch_cluster(barrier_entry, a, (unsigned)WORLD, 32);
+}
+unsigned host_md_peer_error(int rank) { return RANKS[rank].peer_err; }
 
 long long host_md_export(unsigned long long* keys, double* reg, double* strat, long long max_n) {
     unsigned long long n = 0;

@@ -3,6 +3,9 @@
   * tests/multigpu_peers_check.py: {ms_mccfr_batch, ms_mccfr_apply_peers} (the peer-memory exchange kernel) against
     {ms_mccfr_batch, NCCL all-reduce, ms_mccfr_apply} and against one GPU running every rank's traversal ids; replicas
     bit-identical; touched flags agree; no peer error;
+  * tests/multigpu_md_check.py: the multi-deal infoset table sharded over the ranks by a hash of the key (md_blocked_kernel
+    gathers regrets from / sends deltas to the owners' shards through peer memory): union of the shards == the table one
+    GPU builds from all the visits;
   * bench.py with the driver's exact N = 2 command line (default flags): exits 0 with one JSON line.
 """
 import json
@@ -42,6 +45,13 @@ def test_peer_exchange_equals_nccl_and_single_gpu():
     res = _torchrun(2, os.path.join("tests", "multigpu_peers_check.py"), env={"PEERS_CHECK_TIMING": "0"})
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "PEERS_CHECK_OK world=2" in res.stdout
+
+
+@two_gpus
+def test_sharded_multideal_table_equals_single_gpu():
+    res = _torchrun(2, os.path.join("tests", "multigpu_md_check.py"), env={"MD_CHECK_TIMING": "0"})
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "MD_CHECK_OK world=2" in res.stdout
 
 
 @two_gpus

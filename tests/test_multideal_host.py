@@ -194,3 +194,110 @@ def test_blocked_many_deals_match_oracle(md, player):
     order2 = np.argsort(okeys2, kind="stable")
     assert np.array_equal(keys2, okeys2[order2])
     _assert_tables_close(reg2, oreg2[order2], strat2, ostrat2[order2])
+
+
+# ---- the table sharded over several ranks ("shard by hash(key) % G"), ranks emulated in one process ----
+
+def create_world(md, seeds, log2_capacity, world):
+    md.host_md_world_create.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int]
+    roots, ho = [], []
+    for s in seeds:
+        cards = ora.deck(s)
+        roots.append(codec.pack_state([codec.mask_of(cards[:4]), codec.mask_of(cards[4:8])], [], [0, 0], [0, 0], 0, 0, False, 8))
+        ho.append(codec.pack_nibbles(cards[:8]))
+    roots, ho = np.array(roots, dtype=np.uint32), np.array(ho, dtype=np.uint32)
+    assert md.host_md_world_create(roots.ctypes.data, ho.ctypes.data, len(seeds), log2_capacity, world) == 0
+
+
+def export_shard(md):
+    """the selected rank's shard (ms_md_export with max_n = 0 counts)"""
+    dummy = np.zeros(4, np.uint64)
+    n = md.host_md_export(dummy.ctypes.data, dummy.ctypes.data, dummy.ctypes.data, 0)
+    keys, reg, strat = np.zeros(max(n, 1), np.uint64), np.zeros((max(n, 1), 4)), np.zeros((max(n, 1), 4))
+    assert md.host_md_export(keys.ctypes.data, reg.ctypes.data, strat.ctypes.data, n) == n
+    return keys[:n], reg[:n], strat[:n]
+
+
+def export_world(md, world):
+    parts = []
+    for r in range(world):
+        assert md.host_md_select(r) == 0
+        parts.append(export_shard(md))
+    keys = np.concatenate([p[0] for p in parts])
+    assert len(np.unique(keys)) == len(keys), "an infoset lives in two shards"
+    order = np.argsort(keys, kind="stable")
+    return (keys[order], np.concatenate([p[1] for p in parts])[order], np.concatenate([p[2] for p in parts])[order],
+            [len(p[0]) for p in parts])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_table_matches_oracle(md, world):
+    """`world` ranks, each with its shard of the table and its share of the visits of every iteration: blocked traversal
+    (gather / REDs through the peers' shards) ; barrier ; apply on the own shard ; barrier.  The union of the shards
+    equals the oracle's single table (same infoset set, 1e-9) -- i.e. the result does not depend on the number of ranks."""
+    from scopa_b200.sharding import shard_bounds
+    seeds = [42, 1, 43, 7, 2 ** 33 + 7, 12345, 99, 1000, 5, 6, 8, 9]
+    create_world(md, seeds, 14, world)
+    om = ora.MultiDealTable(seeds)
+    om.populate()
+    nu = nv = 0
+    for b in range(3):
+        for r in range(world):
+            lo, n = shard_bounds(7, r, world)
+            assert md.host_md_select(r) == 0
+            assert md.host_md_blocked(2, 7 * b + lo, n, 300, 21) == 0
+        assert md.host_md_barrier_all(-1) == 0
+        for r in range(world):
+            assert md.host_md_select(r) == 0 and md.host_md_apply() == 0
+        assert md.host_md_barrier_all(-1) == 0
+        u, v = om.batch_blocked(2, 21, 7 * b, 7, 300)
+        nu, nv = nu + u, nv + v
+        om.apply()
+    tot = {"updates": 0, "visits": 0, "infosets": 0}
+    for r in range(world):
+        md.host_md_select(r)
+        c = counters(md)
+        assert md.host_md_peer_error(r) == 0
+        for k in tot:
+            tot[k] += c[k]
+    assert (tot["updates"], tot["visits"]) == (nu, nv)
+    keys, reg, strat, sizes = export_world(md, world)
+    assert min(sizes) > 0.6 * len(keys) / world, sizes            # the owner hash spreads the infosets
+    _, okeys, oreg, ostrat, _ = om.arrays()
+    order = np.argsort(okeys, kind="stable")
+    assert np.array_equal(keys, okeys[order]), "infoset sets differ"
+    assert tot["infosets"] == len(keys)                            # every infoset was created exactly once, by some rank
+    _assert_tables_close(reg, oreg[order], strat, ostrat[order])
+    assert np.abs(reg).sum() > 0
+    # any rank can look any infoset up; the per-traversal kernel works on the sharded table too
+    md.host_md_select(world - 1)
+    q = np.ascontiguousarray(keys[::37])
+    lreg, lstrat, found = np.zeros((len(q), 4)), np.zeros((len(q), 4)), np.zeros(len(q), np.uint8)
+    assert md.host_md_lookup(q.ctypes.data, len(q), lreg.ctypes.data, lstrat.ctypes.data, found.ctypes.data) == 0
+    assert found.all() and np.array_equal(lreg, reg[::37]) and np.array_equal(lstrat, strat[::37])
+    for r in range(world):
+        lo, n = shard_bounds(600, r, world)
+        md.host_md_select(r)
+        assert md.host_md_batch(2, n, 2, 10 ** 6 + lo) == 0
+    for r in range(world):
+        md.host_md_select(r)
+        assert md.host_md_apply() == 0
+    om.batch(2, 2, 10 ** 6, 600)
+    om.apply()
+    keys2, reg2, strat2, _ = export_world(md, world)
+    _, okeys2, oreg2, ostrat2, _ = om.arrays()
+    order2 = np.argsort(okeys2, kind="stable")
+    assert np.array_equal(keys2, okeys2[order2])
+    _assert_tables_close(reg2, oreg2[order2], strat2, ostrat2[order2])
+
+
+def test_sharded_barrier_reports_an_absent_rank(md):
+    """A rank that never reaches the barrier: the others give up after the time limit and record which one was missing
+    (instead of spinning until a watchdog kills the GPU); the error is sticky."""
+    create_world(md, [42, 1], 12, 3)
+    assert md.host_md_barrier_all(-1) == 0
+    assert [md.host_md_peer_error(r) for r in range(3)] == [0, 0, 0]
+    assert md.host_md_barrier_all(1) == 0
+    assert [md.host_md_peer_error(r) for r in range(3)] == [2, 0, 2]
+    assert md.host_md_barrier_all(-1) == 0                         # ranks in error return at once
+    assert md.host_md_peer_error(0) == 2
