@@ -908,6 +908,86 @@ def section_multideal(cx):
     return {"traversal_per_thread": md_obj, "deal_blocked": mdb_obj}
 
 
+def section_multideal_sharded(cx):
+    """Multi-deal MCCFR across the GPUs of the box (last sentence): ONE infoset table sharded over the ranks by a
+    hash of the key; every rank runs its share of an iteration's visits with md_blocked_kernel, which gathers the frozen
+    regrets from and sends its deltas to the owners' shards through peer memory (the "all-to-all of deltas" is inside the
+    kernel); then a barrier, the apply step on the own shard, a barrier.  Collective-symmetric: every failure is turned
+    into a group decision before the next collective."""
+    torch, args, K, W = cx.torch, cx.args, cx.K, cx.W
+    from scopa_b200 import multideal
+    world, rank = cx.world, cx.rank
+    owner_bits = int(np.ceil(np.log2(world)))
+    lg = max(16, args.md_log2_capacity - owner_bits)          # the same total capacity as the single-GPU section
+    VIS, PPV = 148 * 4, 3072                                   # per rank and iteration: 4 visits per SM
+    seeds = np.arange(1, args.md_deals + 1)
+    res = {"metric": "mccfr_infoset_node_updates_per_sec", "unit": "infoset-node updates/s", "kernel": "md_blocked_kernel",
+           "config": {"workload": f"MCCFR (reference estimator) over {args.md_deals} deals, deal-blocked, {VIS} visits x {PPV} traversal "
+                                  f"pairs per GPU per iteration; one infoset table sharded over {world} GPUs by a hash of the key "
+                                  f"(2^{lg} x 128 B per shard), regrets gathered / deltas sent through peer memory inside the kernel",
+                      "exchange": "peer memory (CUDA IPC over NVLink / NVSwitch): remote loads + fp64 RED.ADDs in md_blocked_kernel, "
+                                  "two flag barriers per iteration (md_peer_barrier_kernel)"}}
+    sh = pv = None
+    err = None
+    try:
+        sh = multideal.MultiDealSolver(seeds, log2_capacity=lg, device=cx.dev)
+        pv = multideal.MultiDealSolver(seeds, log2_capacity=min(args.md_log2_capacity, 25), device=cx.dev)   # same per-GPU work, private table
+    except Exception as e:
+        err = f"create: {e}"
+    if cx.min_over_ranks(0.0 if err else 1.0) < 1.0:
+        res["error"] = err or "another rank could not create its table"
+        return res
+    try:
+        sh.attach_peers()
+    except Exception as e:                                     # raised on every rank (attach_peers agrees on the outcome)
+        res["error"] = f"attach_peers: {e}"
+        return res
+
+    def run(sv, sharded, it):
+        if sharded:
+            sv.iterate_blocked(VIS * world, PPV, philox_seed=args.seed, first_visit=VIS * world * it)
+        else:
+            sv.mccfr_blocked(VIS, PPV, philox_seed=args.seed, first_visit=VIS * it)
+            sv.apply()
+
+    out = {}
+    try:
+        for name, sv, sharded in (("sharded", sh, True), ("private", pv, False)):
+            for i in range(max(W, 3)):
+                run(sv, sharded, i)
+            sv.counters(reset=True)
+            torch.cuda.synchronize()
+            ev = cx.events(K)
+            if sharded:
+                sv.barrier()
+            for i in range(K):
+                ev[i][0].record()
+                run(sv, sharded, max(W, 3) + i)
+                ev[i][1].record()
+            torch.cuda.synchronize()
+            out[name] = (sum(a.elapsed_time(b) for a, b in ev) / K, sv.counters())
+        perr = sh.peer_error()
+        if perr:
+            err = f"peer barrier: rank {perr - 1} did not arrive"
+    except Exception as e:
+        err = f"timed loop: {e}"
+    if cx.min_over_ranks(0.0 if err else 1.0) < 1.0:
+        res["error"] = err or "another rank failed"
+        return res
+    ms_sh, ms_pv = cx.max_over_ranks(out["sharded"][0]), cx.max_over_ranks(out["private"][0])
+    upd_all = cx.sum_over_ranks(out["sharded"][1]["updates"]) / K
+    upd_pv = out["private"][1]["updates"] / K
+    info_all = cx.sum_over_ranks(out["sharded"][1]["infosets"])
+    res.update({"value": upd_all / (ms_sh * 1e-3), "ms_per_step": ms_sh, "infosets": int(info_all),
+                "private_table_per_gpu": {"value": upd_pv / (ms_pv * 1e-3), "ms_per_step": ms_pv,
+                                          "note": "the same per-GPU work on an unsharded table of this GPU alone (no exchange): "
+                                                  "the floor the sharded iteration is compared with"},
+                "efficiency_vs_private": (upd_all / (ms_sh * 1e-3)) / (world * upd_pv / (ms_pv * 1e-3))})
+    del sh, pv
+    torch.cuda.empty_cache()
+    return res
+
+
 def section_full(cx):
     """40-card Scopa rollouts"""
     torch, args, K, dev = cx.torch, cx.args, cx.K, cx.dev
@@ -1008,7 +1088,7 @@ def section_sdcfr(cx, sv):
         tf_peak, tf_src = 2250.0, "fallback: nominal dense bf16 (B200_PROFILING.md)"
     sd_obj["roofline"] = {"bound": "tensor", "achieved": sd_obj["bf16_tcgen05"]["algorithmic_tflops"], "peak": tf_peak,
                           "unit": "TFLOP/s", "frac": sd_obj["bf16_tcgen05"]["algorithmic_tflops"] / tf_peak, "traffic": None,
-                          "kernel": "sd_forward_kernel<1>", "peak_source": tf_src,
+                          "kernel": "sd_level_mlp_kernel<1>", "peak_source": tf_src,
                           "note": "numerator = 27 136 FLOP x inferences of WHOLE traversals (env steps, sampling, backward levels "
                                   "and sample emission included in the time), so this is a floor on the tensor-pipe share; "
                                   "K = 34 / N = 16 layers pad to MMA tiles (profiles/README.md section 3)"}
@@ -1110,6 +1190,8 @@ def run_ours(args):
 
             def extra(name, fn, *a):
                 # the default run must end within minutes whatever a section does: past the budget the rest is skipped
+                if args.only and name != args.only:
+                    return
                 if time.perf_counter() - t_ex > args.extras_budget_s:
                     extras[name] = {"skipped": f"extras wall budget of {args.extras_budget_s:.0f} s used up"}
                     return
@@ -1138,6 +1220,8 @@ def run_ours(args):
             else:
                 cpu_mccfr, cpu_env = cpu
     if world > 1:
+        if args.md_deals > 0 and not args.no_extras:
+            extras["mccfr_multi_deal_sharded"] = section_multideal_sharded(cx)      # collective-symmetric
         cx.dist.barrier()
         cx.dist.destroy_process_group()
     if rank != 0:
@@ -1371,6 +1455,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="N = 1: only the two headline sections (and the CPU leg)")
+    ap.add_argument("--only", default=None, help="N = 1: of the extra sections run only this one (profiling runs), e.g. sdcfr")
     ap.add_argument("--extras-budget-s", type=float, default=240.0,
                     help="N = 1: no further single-GPU reporting section is started after this many seconds of them")
     ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "p2p_fused", "nccl"],

@@ -1,0 +1,11 @@
+set -x
+# r02p (1 GPU): SDCFR: backward copy-out with 32-bit row offsets and float2 / float4 stores; layer-1 bias in the padding columns
+mkdir -p gpurun_out
+python profiles/summarise_capture.py x --hash-only --sources scopa_b200/csrc/ms_sdcfr.cu scopa_b200/csrc/ms_state.cuh > gpurun_out/sha_sd_r02p.txt
+timeout 900 python -m pytest tests/test_gpu_sdcfr.py tests/test_gpu_sd_train.py -m gpu -q -x 2>&1 | tail -4
+( time timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu --only sdcfr > gpurun_out/bench_r02p.json 2> gpurun_out/bench_r02p.err ) 2>&1 | tail -4; tail -5 gpurun_out/bench_r02p.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sd_ -c 120 --csv --log-file gpurun_out/launches_sd_r02p.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu --only sdcfr > gpurun_out/ncu_launches_sd_r02p.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sd_level_mlp_kernel -s 19 -c 1 -f -o gpurun_out/sd_mlp_r02p \
+    python bench.py --steps 3 --warmup 3 --no-cpu --only sdcfr > gpurun_out/ncu_sd_mlp_r02p.log 2>&1
+ls -la gpurun_out | tail -4

@@ -9,8 +9,12 @@
 //   FlexibleNet (mlp mode 34 -> 128 -> 64 -> 16, ReLU)      nets.py:151-235, 296-331
 //
 // The reference does one batch-1 MLP call (and a host<->device hop) per tree node.  Here B traversals
-// advance together, one tree level per launch: the frontier of a level (B x 1..24 nodes) is one batched
-// inference.  The recursion shape is data independent (a traverser node with h cards has exactly h
+// advance together, one tree level at a time: the frontier of a level (B x 1..24 nodes) is one batched
+// inference (sd_level_mlp_kernel: state -> features -> MLP -> 16 raw advantages per node), followed by
+// sd_expand_kernel (policy, then expansion of a traverser node / sampling at an opponent node, with the env step).
+// The two are separate launches since round 2: the tensor-core kernel holds its TMEM columns and operand buffers
+// only for the MLP, and the rule evaluation runs at full occupancy instead of at the 16 warps per SM the TMEM
+// budget allows (profiles/README.md R2.5).  The recursion shape is data independent (a traverser node with h cards has exactly h
 // children, an opponent node 1), so level arrays are dense: child index = parent index * fan-out + i,
 // no compaction and no atomics; Philox call indices (= the reference's depth-first invocation order)
 // follow from the same shape.
@@ -57,6 +61,7 @@ struct SdArgs {
     unsigned long long first_trav;
     long long n_trav;
     float* out_feat; float* out_target; float* out_mask; float* out_value;
+    float* raw;                   // [n_trav * max nodes of a level][16] raw advantages of the level in flight
 };
 
 // features of the CURRENT player's view (deep_cfr.py:304): hand one-hot[16] by action id, table
@@ -136,16 +141,30 @@ constexpr uint32_t SD_TM_COLS = 128, SD_TM_D1 = 0, SD_TM_D2 = 0, SD_TM_D3 = 0;
 constexpr int SD_TC_WG = 2, SD_TC_THREADS = SD_TC_WG * SD_TILE, SD_TC_CTAS_PER_SM = 2;
 constexpr int SD_CTAS_PER_SM = 3;   // fp32 path launch bound (its shared memory allows one)
 // bf16 operand image of one net, as it sits in shared memory (built once per call by sd_prep_kernel):
-// w1 [128 x 48] | w2 [64 x 128] | w3 [16 x 64] in the UMMA canonical layout, then the fp32 biases
+// w1 [128 x 48] | w2 [64 x 128] | w3 [16 x 64] in the UMMA canonical layout, then the BIAS OPERANDS: the biases are
+// added by the tensor cores, not by the epilogues -- each layer's accumulator is started by one extra K = 16 MMA of a
+// constant A tile `ones` [128 x 16] (columns 0 and 1 = 1.0, the rest 0) with a B tile [N x 16] whose columns 0 and 1
+// hold the bias split into two bf16 terms (hi + lo: 16 mantissa bits), so D = b + A W^T leaves the epilogue of a hidden
+// layer with a single packed convert (cvt.rn.relu.bf16x2.f32) per two activations.  Layer 1 needs no extra MMA: its
+// K = 34 operand is padded to 48, and columns 34 / 35 of W1 hold the bias terms against 1.0 in the A rows.
 constexpr int SD_IMG_W1 = 0, SD_IMG_W2 = SD_IMG_W1 + 2 * 128 * 48, SD_IMG_W3 = SD_IMG_W2 + 2 * 64 * 128,
-              SD_IMG_BIAS = SD_IMG_W3 + 2 * 16 * 64, SD_IMG_BYTES = SD_IMG_BIAS + 4 * (128 + 64 + 16);
+              SD_IMG_ONES = SD_IMG_W3 + 2 * 16 * 64, SD_IMG_BT2 = SD_IMG_ONES + 2 * 128 * 16,
+              SD_IMG_BT3 = SD_IMG_BT2 + 2 * 64 * 16, SD_IMG_BYTES = SD_IMG_BT3 + 2 * 16 * 16;
 
+// switches of the tensor-core level kernel, measured on whole traversals (profiles/README.md R2.5, prof_r02q): bit 0 = request
+// the next tile's state before the layers of the current one (no gain: four tiles in flight already hide the load), bit 1 =
+// two x32 TMEM loads per wait in the hidden epilogues (+3.5 %).  Default: 2.
+#ifndef SD_VAR_DEFAULT
+#define SD_VAR_DEFAULT 2
+#endif
 struct SdSmemTc {
     __nv_bfloat16* a;      // A operand tile, 128 rows x up to 128 k   (32 KB)
     __nv_bfloat16* w1;     // 128 x 48
     __nv_bfloat16* w2;     // 64 x 128
     __nv_bfloat16* w3;     // 16 x 64
-    float* bias;           // b1 | b2 | b3
+    __nv_bfloat16* ones;   // 128 x 16 constant A tile of the bias MMAs
+    __nv_bfloat16* bt2;    // bias operands of layers 2 and 3: 64 x 16, 16 x 16
+    __nv_bfloat16* bt3;
     unsigned long long* bar;
     uint32_t* tmem_base;
     uint32_t tm_off;       // this warpgroup's first TMEM column
@@ -226,12 +245,40 @@ __device__ __forceinline__ void sd_tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// 64 consecutive columns: two x32 loads in flight, one wait
+__device__ __forceinline__ void sd_tmem_ld64(uint32_t taddr, float* v) {
+    uint32_t r[64];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t* q = r + 32 * h;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+            : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+              "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]), "=r"(q[17]),
+              "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]), "=r"(q[25]), "=r"(q[26]),
+              "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+            : "r"(taddr + 32u * (uint32_t)h));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; i++) v[i] = __uint_as_float(r[i]);
+}
+
 // builds the shared-memory image of a net (bf16, canonical layout) in global memory, once per call
 __global__ void __launch_bounds__(256) sd_prep_kernel(const float* __restrict__ net, unsigned char* __restrict__ img) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
     for (int i = tid; i < 128 * SD_K1; i += T) {
         const int o = i / SD_K1, k = i % SD_K1;
-        *(__nv_bfloat16*)(img + SD_IMG_W1 + sd_tile_off(o, k, SD_K1)) = __float2bfloat16(k < SD_IN ? net[SD_W1 + o * SD_IN + k] : 0.f);
+        // columns 34 and 35 of the padded K = 48 operand carry the layer's bias (hi + lo bf16 terms); the A rows hold 1.0 there
+        float w = 0.f;
+        if (k < SD_IN) w = net[SD_W1 + o * SD_IN + k];
+        else if (k == SD_IN || k == SD_IN + 1) {
+            const float b = net[SD_B1 + o];
+            const float hi = __bfloat162float(__float2bfloat16(b));
+            w = k == SD_IN ? hi : b - hi;
+        }
+        *(__nv_bfloat16*)(img + SD_IMG_W1 + sd_tile_off(o, k, SD_K1)) = __float2bfloat16(w);
     }
     for (int i = tid; i < 64 * 128; i += T) {
         const int o = i / 128, k = i % 128;
@@ -241,10 +288,19 @@ __global__ void __launch_bounds__(256) sd_prep_kernel(const float* __restrict__ 
         const int o = i / 64, k = i % 64;
         *(__nv_bfloat16*)(img + SD_IMG_W3 + sd_tile_off(o, k, 64)) = __float2bfloat16(net[SD_W3 + o * 64 + k]);
     }
-    float* bias = (float*)(img + SD_IMG_BIAS);
-    for (int i = tid; i < 128; i += T) bias[i] = net[SD_B1 + i];
-    for (int i = tid; i < 64; i += T) bias[128 + i] = net[SD_B2 + i];
-    for (int i = tid; i < 16; i += T) bias[192 + i] = net[SD_B3 + i];
+    for (int i = tid; i < 128 * 16; i += T) {
+        const int m = i / 16, k = i % 16;
+        *(__nv_bfloat16*)(img + SD_IMG_ONES + sd_tile_off(m, k, 16)) = __float2bfloat16(k < 2 ? 1.f : 0.f);
+    }
+    for (int i = tid; i < (64 + 16) * 16; i += T) {
+        const int r = i / 16, k = i % 16;
+        const int layer = r < 64 ? 1 : 2, o = layer == 1 ? r : r - 64;
+        const float b = net[(layer == 1 ? SD_B2 : SD_B3) + o];
+        const __nv_bfloat16 hi = __float2bfloat16(b);
+        const __nv_bfloat16 lo = __float2bfloat16(b - __bfloat162float(hi));
+        *(__nv_bfloat16*)(img + (layer == 1 ? SD_IMG_BT2 : SD_IMG_BT3) + sd_tile_off(o, k, 16)) =
+            k == 0 ? hi : (k == 1 ? lo : __float2bfloat16(0.f));
+    }
 }
 
 __device__ __forceinline__ SdSmemTc sd_carve_tc(unsigned char* raw, const unsigned char* img) {
@@ -257,7 +313,9 @@ __device__ __forceinline__ SdSmemTc sd_carve_tc(unsigned char* raw, const unsign
     sm.w1 = (__nv_bfloat16*)(p + SD_IMG_W1);
     sm.w2 = (__nv_bfloat16*)(p + SD_IMG_W2);
     sm.w3 = (__nv_bfloat16*)(p + SD_IMG_W3);
-    sm.bias = (float*)(p + SD_IMG_BIAS); p += SD_IMG_BYTES;
+    sm.ones = (__nv_bfloat16*)(p + SD_IMG_ONES);
+    sm.bt2 = (__nv_bfloat16*)(p + SD_IMG_BT2); sm.bt3 = (__nv_bfloat16*)(p + SD_IMG_BT3);
+    p += SD_IMG_BYTES;
     unsigned long long* bars = (unsigned long long*)p; p += 8 * SD_TC_WG;
     sm.bar = bars + sm.wg;
     sm.tmem_base = (uint32_t*)p;
@@ -286,9 +344,11 @@ __device__ __forceinline__ void sd_release_tc(const SdSmemTc& sm) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(*sm.tmem_base) : "memory");
 }
 
-// one layer: D[128 x N] = A[128 x K] * W[N x K]^T on the tensor cores; all 128 threads of a warpgroup call it
-__device__ __forceinline__ void sd_layer_mma(const SdSmemTc& sm, const __nv_bfloat16* w, int K, int N, uint32_t tm_col,
-                                             uint32_t& phase) {
+// one layer: D[128 x N] = b + A[128 x K] * W[N x K]^T on the tensor cores (the bias through ones x bt, see the image
+// layout; bt == nullptr: the bias is already inside A W^T -- layer 1, whose padded operand has two spare columns);
+// all 128 threads of a warpgroup call it
+__device__ __forceinline__ void sd_layer_mma(const SdSmemTc& sm, const __nv_bfloat16* w, const __nv_bfloat16* bt, int K, int N,
+                                             uint32_t tm_col, uint32_t& phase) {
     // the A tile was written with ordinary stores: make it visible to the async (tensor core) proxy
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -297,10 +357,11 @@ __device__ __forceinline__ void sd_layer_mma(const SdSmemTc& sm, const __nv_bflo
     if ((threadIdx.x & 127) == 0) {
         const uint32_t tm = *sm.tmem_base + sm.tm_off + tm_col;
         const uint32_t idesc = sd_idesc(N);
+        if (bt) sd_mma(tm, sd_smem_desc(sm.ones, 16), sd_smem_desc(bt, 16), idesc, false);
         for (int k = 0; k < K; k += 16) {
             const uint64_t da = sd_smem_desc((const char*)sm.a + (k >> 3) * 128, K);
             const uint64_t db = sd_smem_desc((const char*)w + (k >> 3) * 128, K);
-            sd_mma(tm, da, db, idesc, k > 0);
+            sd_mma(tm, da, db, idesc, bt != nullptr || k > 0);
         }
         sd_commit(sm.bar);
     }
@@ -318,49 +379,82 @@ __device__ __forceinline__ void sd_store8(const SdSmemTc& sm, int row, int k0, i
     *(uint4*)((char*)sm.a + sd_tile_off(row, k0, K)) = q;
 }
 
-__device__ __forceinline__ void mlp_tc(const SdSmemTc& sm, const float* x, float* out, uint32_t& phase) {
+// ReLU + bf16 conversion + packing of two activations in ONE instruction (a -> upper half, b -> lower half)
+__device__ __forceinline__ uint32_t sd_relu_pack(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// hidden-layer epilogue: `cols` accumulator columns of this thread's row -> ReLU -> bf16 -> next layer's A operand
+template <int COLS, int W = 32>
+__device__ __forceinline__ void sd_hidden_epilogue(const SdSmemTc& sm, int row, uint32_t taddr) {
+#pragma unroll
+    for (int c = 0; c < COLS; c += W) {
+        float v[W];
+        if (W == 64) sd_tmem_ld64(taddr + c, v); else sd_tmem_ld32(taddr + c, v);
+#pragma unroll
+        for (int i = 0; i < W; i += 8) {
+            uint4 q;
+            q.x = sd_relu_pack(v[i], v[i + 1]); q.y = sd_relu_pack(v[i + 2], v[i + 3]);
+            q.z = sd_relu_pack(v[i + 4], v[i + 5]); q.w = sd_relu_pack(v[i + 6], v[i + 7]);
+            *(uint4*)((char*)sm.a + sd_tile_off(row, c + i, COLS)) = q;
+        }
+    }
+}
+
+// layers 1-3 on the A1 tile already in sm.a (K = 48) -> out[16] = the net's raw outputs for this thread's row
+template <int VAR = SD_VAR_DEFAULT>
+__device__ __forceinline__ void mlp_tc_layers(const SdSmemTc& sm, float* out, uint32_t& phase) {
     const int tid = threadIdx.x & 127;                             // row of this warpgroup's tile
     const uint32_t lane_base = (((uint32_t)(tid & ~31)) << 16) + sm.tm_off;   // TMEM address: lane in bits 31..16
-    // layer 1: A = features (K padded to 48)
+    constexpr int W = (VAR & 2) ? 64 : 32;
+    sd_layer_mma(sm, sm.w1, nullptr, SD_K1, SD_H1, SD_TM_D1, phase);
+    sd_hidden_epilogue<SD_H1, W>(sm, tid, *sm.tmem_base + lane_base + SD_TM_D1);
+    sd_layer_mma(sm, sm.w2, sm.bt2, SD_H1, SD_H2, SD_TM_D2, phase);
+    sd_hidden_epilogue<SD_H2, W>(sm, tid, *sm.tmem_base + lane_base + SD_TM_D2);
+    sd_layer_mma(sm, sm.w3, sm.bt3, SD_H2, SD_OUT, SD_TM_D3, phase);
+    sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D3, out);
+}
+
+// general features (ms_mlp_forward): row of A1 from 34 floats
+__device__ __forceinline__ void mlp_tc(const SdSmemTc& sm, const float* x, float* out, uint32_t& phase) {
+    const int tid = threadIdx.x & 127;
 #pragma unroll
     for (int k0 = 0; k0 < SD_K1; k0 += 8) {
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = (k0 + i < SD_IN) ? x[k0 + i] : 0.f;
+        for (int i = 0; i < 8; i++) v[i] = (k0 + i < SD_IN) ? x[k0 + i] : (k0 + i < SD_IN + 2 ? 1.f : 0.f);     // 34, 35: the bias columns
         sd_store8(sm, tid, k0, SD_K1, v);
     }
-    sd_layer_mma(sm, sm.w1, SD_K1, SD_H1, SD_TM_D1, phase);
-    const float4* bias4 = (const float4*)sm.bias;                  // 16-byte aligned inside the weight image
-    for (int c = 0; c < SD_H1; c += 32) {
-        float v[32];
-        sd_tmem_ld32(*sm.tmem_base + lane_base + SD_TM_D1 + c, v);
+    mlp_tc_layers(sm, out, phase);
+}
+
+// Features of a game state straight from its bit masks (sd_features without the detour through 34 floats): element k of
+// the row is bit k of the hand (k < 16) / of the table set (16 <= k < 32), k = 32 is the constant 1; a pair of bf16
+// values is one 32-bit word, 1.0 = 0x3F80.
+__device__ __forceinline__ uint32_t sd_bits_pair(uint32_t bits, int k) {
+    const uint32_t b = bits >> k;
+    return (b & 1u) * 0x3F80u | ((b >> 1) & 1u) * 0x3F800000u;
+}
+template <int VAR = SD_VAR_DEFAULT>
+__device__ __forceinline__ void mlp_tc_state(const SdSmemTc& sm, const MsState& s, int cp, float* out, uint32_t& phase) {
+    const int tid = threadIdx.x & 127;
+    const uint32_t hand = st_hand(s, cp);
+    const uint32_t tset = table_set(s.y, st_table_len(s));
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const float4 b = bias4[(c + i) >> 2];
-            v[i] = fmaxf(v[i] + b.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b.y, 0.f);
-            v[i + 2] = fmaxf(v[i + 2] + b.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b.w, 0.f);
+    for (int h = 0; h < 2; h++) {
+        const uint32_t bits = h == 0 ? hand : tset;
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0 += 8) {
+            uint4 q;
+            q.x = sd_bits_pair(bits, k0); q.y = sd_bits_pair(bits, k0 + 2); q.z = sd_bits_pair(bits, k0 + 4); q.w = sd_bits_pair(bits, k0 + 6);
+            *(uint4*)((char*)sm.a + sd_tile_off(tid, 16 * h + k0, SD_K1)) = q;
         }
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) sd_store8(sm, tid, c + i, SD_H1, v + i);
     }
-    sd_layer_mma(sm, sm.w2, SD_H1, SD_H2, SD_TM_D2, phase);
-    for (int c = 0; c < SD_H2; c += 32) {
-        float v[32];
-        sd_tmem_ld32(*sm.tmem_base + lane_base + SD_TM_D2 + c, v);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const float4 b = bias4[(128 + c + i) >> 2];
-            v[i] = fmaxf(v[i] + b.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b.y, 0.f);
-            v[i + 2] = fmaxf(v[i + 2] + b.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b.w, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) sd_store8(sm, tid, c + i, SD_H2, v + i);
-    }
-    sd_layer_mma(sm, sm.w3, SD_H2, SD_OUT, SD_TM_D3, phase);
-    float v[16];
-    sd_tmem_ld16(*sm.tmem_base + lane_base + SD_TM_D3, v);
-#pragma unroll
-    for (int i = 0; i < 16; i++) out[i] = v[i] + sm.bias[192 + i];
+    *(uint4*)((char*)sm.a + sd_tile_off(tid, 32, SD_K1)) = make_uint4(0x3F80u, 0x3F803F80u, 0u, 0u);   // [1.0, 0.0 | bias columns 1.0, 1.0 | 0 ..]
+    *(uint4*)((char*)sm.a + sd_tile_off(tid, 40, SD_K1)) = make_uint4(0u, 0u, 0u, 0u);
+    mlp_tc_layers<VAR>(sm, out, phase);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -380,6 +474,32 @@ __device__ __forceinline__ void sd_policy(const float* raw, uint32_t legal_mask,
     // of the 16 slots illegal that subroutine was 15 % of the forward kernel's instructions (profiles/README.md 3)
 #pragma unroll
     for (int i = 0; i < 16; i++) pol[i] = pol[i] > 0.f ? pol[i] / z : 0.f;
+}
+
+// The same policy where the traversal needs it: at the (at most four) legal actions, in legal-list order.  z is summed
+// over all 16 slots in index order like sd_policy (the masked terms are exact zeros), but only the legal slots are
+// divided: the IEEE division is a subroutine call per warp and slot -- with 16 slots and lanes holding different hands
+// a warp ran it 16 times per node, 12 of them for numerators that are zero in every lane (30 % of sd_expand_kernel's
+// instructions in profiles/sd_expand_r02m_raw.csv).  `rawp` = the node's 16 raw outputs in global memory (indexed reads).
+__device__ __forceinline__ void sd_policy_legal(const float* raw, const float* __restrict__ rawp, uint32_t legal_mask,
+                                                uint32_t list, uint32_t nl, float* p4) {
+    float z = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float m = (float)((legal_mask >> i) & 1u);
+        const float adv = raw[i] * m - 1e6f * (1.f - m);
+        z += (adv > 0.f ? adv : 0.f) * m;
+    }
+    if (z < 1e-8f) z = 1e-8f;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+        float v = 0.f;
+        if (k < nl) {
+            const float r = rawp[(list >> (4 * k)) & 0xFu];      // adv = r * 1 - 1e6 * 0 = r exactly
+            if (r > 0.f) v = r / z;
+        }
+        p4[k] = v;
+    }
 }
 
 template <int PREC>
@@ -415,12 +535,11 @@ __global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward level d: inference for every frontier node, then expand (traverser) or sample (opponent).
-template <int PREC>
-__global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1 ? SD_TC_CTAS_PER_SM : SD_CTAS_PER_SM) sd_forward_kernel(SdArgs a, int d) {
+// Forward level d, part 1: inference for every frontier node -> a.raw[g][16] (the net's outputs before masking).
+template <int PREC, int VAR = SD_VAR_DEFAULT>
+__global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1 ? SD_TC_CTAS_PER_SM : SD_CTAS_PER_SM) sd_level_mlp_kernel(SdArgs a, int d) {
     MS_DYN_SMEM(smem_raw);
     const int cp = d & 1;
-    const bool trav = (cp == a.sh.player);
     SdSmemFp32 s32{};
     SdSmemTc stc{};
     uint32_t phase = 0;
@@ -429,27 +548,62 @@ __global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1
     constexpr int NWG = PREC == 1 ? SD_TC_WG : 1;                // tiles a CTA works on side by side
     const long long total = a.n_trav * a.sh.n[d];
     const long long tiles = (total + SD_TILE - 1) / SD_TILE;
-    const int f = a.sh.f[d];
-    for (long long tile = (long long)blockIdx.x * NWG + (threadIdx.x >> 7); tile < tiles; tile += (long long)gridDim.x * NWG) {
+    const long long tstep = (long long)gridDim.x * NWG;
+    long long tile = (long long)blockIdx.x * NWG + (threadIdx.x >> 7);
+    // the state of the NEXT tile is requested before the layers of the current one: the tile loop never waits on HBM
+    MsState s_next = (tile < tiles && tile * SD_TILE + tid < total) ? a.lvl[d].state[tile * SD_TILE + tid] : make_uint4(0u, 0u, 0u, 0u);
+    for (; tile < tiles; tile += tstep) {
         const long long g = tile * SD_TILE + tid;
         const bool live = g < total;
-        MsState s = live ? a.lvl[d].state[g] : make_uint4(0u, 0u, 0u, 0u);
-        float x[SD_IN], raw[16];
-        sd_features(s, cp, x);
-        if (PREC == 0) mlp_fp32(s32, x, raw); else mlp_tc(stc, x, raw, phase);
-        if (!live) continue;
+        MsState s = s_next;
+        if (PREC == 1 && (VAR & 1)) {
+            const long long gn = g + tstep * SD_TILE;
+            s_next = (tile + tstep < tiles && gn < total) ? a.lvl[d].state[gn] : make_uint4(0u, 0u, 0u, 0u);
+        } else if (tile > (long long)blockIdx.x * NWG + (threadIdx.x >> 7)) {
+            s = live ? a.lvl[d].state[g] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        float raw[16];
+        if (PREC == 0) {
+            float x[SD_IN];
+            sd_features(s, cp, x);
+            mlp_fp32(s32, x, raw);
+        } else {
+            mlp_tc_state<VAR>(stc, s, cp, raw, phase);
+        }
+        if (live) {
+            float4* o = (float4*)(a.raw + g * 16);
+#pragma unroll
+            for (int i = 0; i < 4; i++) o[i] = make_float4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
+        }
+    }
+    if (PREC == 1) sd_release_tc(stc);
+}
+
+// Forward level d, part 2: masking + regret-matching policy, then expand (traverser: every legal action) or sample
+// (opponent: one action from the policy), with the env step.  Plain CUDA at full occupancy.
+__global__ void __launch_bounds__(256) sd_expand_kernel(SdArgs a, int d) {
+    const int cp = d & 1;
+    const bool trav = (cp == a.sh.player);
+    const long long total = a.n_trav * a.sh.n[d];
+    const int f = a.sh.f[d];
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const MsState s = a.lvl[d].state[g];
+        float raw[16];
+        {
+            const float4* r4 = (const float4*)(a.raw + g * 16);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const float4 v = r4[i]; raw[4 * i] = v.x; raw[4 * i + 1] = v.y; raw[4 * i + 2] = v.z; raw[4 * i + 3] = v.w; }
+        }
         uint32_t list;
         const uint32_t nl = legal_list(s, a.hand_order, cp, list);
         uint32_t lm = 0u;
         for (uint32_t i = 0; i < nl; i++) lm |= 1u << ((list >> (4 * i)) & 0xFu);
-        float adv[16], pol[16];
-        sd_policy(raw, lm, adv, pol);
+        float pl[4];                                             // policy at the legal actions, legal-list order
+        sd_policy_legal(raw, a.raw + g * 16, lm, list, nl, pl);
         const uint32_t call = a.lvl[d].call[g];
         if (trav) {
-            float pl[4] = {0.f, 0.f, 0.f, 0.f};
             for (int i = 0; i < f; i++) {
                 const uint32_t act = (list >> (4 * i)) & 0xFu;
-                pl[i] = pol[act];
                 MsState c = s;
                 step(c, act);
                 a.lvl[d + 1].state[g * f + i] = c;
@@ -459,7 +613,7 @@ __global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1
         } else {
             // opponent: sample one action from the policy restricted to the legal list (deep_cfr.py:347-359)
             float ap[4], sum = 0.f;
-            for (uint32_t i = 0; i < 4; i++) ap[i] = i < nl ? pol[(list >> (4 * i)) & 0xFu] : 0.f;
+            for (uint32_t i = 0; i < 4; i++) ap[i] = pl[i];
             for (uint32_t i = 0; i < nl; i++) sum += ap[i];
             const long long t = g / a.sh.n[d];
             const unsigned long long trav_id = a.first_trav + (unsigned long long)t;
@@ -482,7 +636,6 @@ __global__ void __launch_bounds__(PREC == 1 ? SD_TC_THREADS : SD_TILE, PREC == 1
             a.lvl[d + 1].call[g] = call + 1u;
         }
     }
-    if (PREC == 1) sd_release_tc(stc);
 }
 
 // Opponent level where the mover holds a single card: the move is forced, so the advantage net's
@@ -522,8 +675,10 @@ __global__ void __launch_bounds__(256) sd_terminal_kernel(SdArgs a) {
 // the launch list showed these kernels at 0.6 TB/s and 44 % of a traversal.  The rows of a warp are staged in
 // shared memory instead and written out by the whole warp, consecutive lanes on consecutive floats.
 __global__ void __launch_bounds__(256) sd_backward_kernel(SdArgs a, int d) {
-    __shared__ float stage[8][32 * 35];
-    __shared__ long long slot_s[8][32];
+    // per warp: 32 feature rows (34 floats, row stride 34: the copy-out below reads them linearly), then the 32 target
+    // and mask rows (16 + 16 floats) in the same buffer
+    __shared__ float4 stage[8][32 * 34 / 4];
+    __shared__ uint32_t rel_s[8][32];
     const int cp = d & 1;
     const bool trav = (cp == a.sh.player);
     const long long total = a.n_trav * a.sh.n[d];
@@ -534,15 +689,17 @@ __global__ void __launch_bounds__(256) sd_backward_kernel(SdArgs a, int d) {
         return;
     }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float* st = stage[wib];
-    long long* sl = slot_s[wib];
+    float* st = (float*)stage[wib];
+    uint32_t* rel = rel_s[wib];
     for (long long base = blockIdx.x * (long long)blockDim.x + 32 * wib; base < total; base += (long long)gridDim.x * blockDim.x) {
         const long long g = base + lane;
         const bool valid = g < total;
         const int nrows = (int)((total - base) < 32 ? (total - base) : 32);
+        // sample slots of the warp's rows: ascending, so a row's slot is the first row's plus a small 32-bit offset
+        const long long t0 = base / nd;
+        const long long slot0 = t0 * a.sh.samples + a.sh.sample_off[d] + (base - t0 * nd);
         float x[SD_IN], reg[16];
         uint32_t lm = 0u;
-        long long slot = 0;
         if (valid) {
             const MsState s = a.lvl[d].state[g];
             uint32_t list;
@@ -569,34 +726,41 @@ __global__ void __launch_bounds__(256) sd_backward_kernel(SdArgs a, int d) {
                 for (int i = 0; i < 16; i++) reg[i] = reg[i] != 0.f ? reg[i] / dn : reg[i];
             }
             const long long t = g / nd, j = g % nd;
-            slot = t * a.sh.samples + a.sh.sample_off[d] + j;
+            rel[lane] = (uint32_t)(t * a.sh.samples + a.sh.sample_off[d] + j - slot0);
             sd_features(s, cp, x);
         }
         __syncwarp();                       // the previous iteration's readers are done with the stage
         if (valid) {
 #pragma unroll
-            for (int i = 0; i < SD_IN; i++) st[lane * 35 + i] = x[i];
-            sl[lane] = slot;
+            for (int i = 0; i < SD_IN; i++) st[lane * SD_IN + i] = x[i];
         }
         __syncwarp();
-        for (int e = lane; e < nrows * SD_IN; e += 32) {
-            const int r = e / SD_IN, c = e - r * SD_IN;
-            a.out_feat[sl[r] * SD_IN + c] = st[r * 35 + c];
+        {   // 34 floats per row = 17 float2 (a row starts 136 bytes after the previous one: 8-byte aligned)
+            float2* fb = (float2*)(a.out_feat + slot0 * SD_IN);
+            const float2* s2 = (const float2*)st;
+            for (int e = lane; e < nrows * (SD_IN / 2); e += 32) {
+                const int r = e / (SD_IN / 2), c = e - r * (SD_IN / 2);
+                fb[rel[r] * (uint32_t)(SD_IN / 2) + (uint32_t)c] = s2[e];
+            }
         }
         __syncwarp();
         if (valid) {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                st[lane * 33 + i] = reg[i];
-                st[lane * 33 + 16 + i] = (float)((lm >> i) & 1u);
+                st[lane * 16 + i] = reg[i];
+                st[512 + lane * 16 + i] = (float)((lm >> i) & 1u);
             }
         }
         __syncwarp();
-        for (int e = lane; e < nrows * 16; e += 32) {
-            const int r = e >> 4, c = e & 15;
-            const long long o = sl[r] * 16 + c;
-            a.out_target[o] = st[r * 33 + c];
-            a.out_mask[o] = st[r * 33 + 16 + c];
+        {   // 16 floats per row = 4 float4, for the targets and for the masks
+            float4* tb = (float4*)(a.out_target + slot0 * 16);
+            float4* mb = (float4*)(a.out_mask + slot0 * 16);
+            const float4* s4 = (const float4*)st;
+            for (int e = lane; e < nrows * 4; e += 32) {
+                const uint32_t o = rel[e >> 2] * 4u + (uint32_t)(e & 3);
+                tb[o] = s4[e];
+                mb[o] = s4[128 + e];
+            }
         }
     }
 }
@@ -640,6 +804,10 @@ static size_t sd_workspace(long long n_trav, int player, SdArgs* a, char* base) 
         size_t o_img = take(SD_IMG_BYTES);
         if (a) a->img[p] = (const unsigned char*)(base + o_img);
     }
+    int widest = 1;
+    for (int d = 0; d < 8; d++) widest = sh.n[d] > widest ? sh.n[d] : widest;
+    const size_t o_raw = take(sizeof(float) * 16 * (size_t)n_trav * widest);
+    if (a) a->raw = (float*)(base + o_raw);
     if (a) a->sh = sh;
     return off;
 }
@@ -710,9 +878,9 @@ int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, c
     const uint4 root = make_uint4(h_root->hands, h_root->table, h_root->captures, h_root->meta);
     sd_init_kernel<<<grid_for(n_trav, 256, 4), 256, 0, st>>>(a, root);
     MS_LAUNCH_CHECK();
-    if (precision == 0) MS_CUDA(cudaFuncSetAttribute(sd_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_FP32));
+    if (precision == 0) MS_CUDA(cudaFuncSetAttribute(sd_level_mlp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_FP32));
     else {
-        MS_CUDA(cudaFuncSetAttribute(sd_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
+        MS_CUDA(cudaFuncSetAttribute(sd_level_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
         for (int p = 0; p < 2; p++) {
             sd_prep_kernel<<<8, 256, 0, st>>>(a.net[p], (unsigned char*)a.img[p]);
             MS_LAUNCH_CHECK();
@@ -722,11 +890,16 @@ int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, c
         const bool forced_opp = ((d & 1) != player) && (4 - d / 2 == 1);   // the opponent's last card
         if (forced_opp) {
             sd_forced_kernel<<<grid_for(n_trav * a.sh.n[d], 256, 8), 256, 0, st>>>(a, d);
-        } else if (precision == 0) {
-            sd_forward_kernel<0><<<grid_for(n_trav * a.sh.n[d], SD_TILE, 1), SD_TILE, SD_SMEM_FP32, st>>>(a, d);
-        } else {
-            sd_forward_kernel<1><<<grid_for(n_trav * a.sh.n[d], SD_TC_THREADS, SD_TC_CTAS_PER_SM), SD_TC_THREADS, SD_SMEM_TC, st>>>(a, d);
+            MS_LAUNCH_CHECK();
+            continue;
         }
+        if (precision == 0) {
+            sd_level_mlp_kernel<0><<<grid_for(n_trav * a.sh.n[d], SD_TILE, 1), SD_TILE, SD_SMEM_FP32, st>>>(a, d);
+        } else {
+            sd_level_mlp_kernel<1><<<grid_for(n_trav * a.sh.n[d], SD_TC_THREADS, SD_TC_CTAS_PER_SM), SD_TC_THREADS, SD_SMEM_TC, st>>>(a, d);
+        }
+        MS_LAUNCH_CHECK();
+        sd_expand_kernel<<<grid_for(n_trav * a.sh.n[d], 256, 8), 256, 0, st>>>(a, d);
         MS_LAUNCH_CHECK();
     }
     sd_terminal_kernel<<<grid_for(n_trav * a.sh.n[8], 256, 8), 256, 0, st>>>(a);

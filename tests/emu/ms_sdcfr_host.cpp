@@ -1,5 +1,5 @@
 // tests/emu/ms_sdcfr_host.cpp -- the PRODUCT's SDCFR kernels, fp32 path (scopa_b200/csrc/ms_sdcfr.cu: sd_mlp_kernel<0>,
-// and the level-batched external-sampling traversal sd_init_kernel / sd_forward_kernel<0> / sd_forced_kernel /
+// and the level-batched external-sampling traversal sd_init_kernel / sd_level_mlp_kernel<0> + sd_expand_kernel / sd_forced_kernel /
 // sd_terminal_kernel / sd_backward_kernel / sd_root_value_kernel) executed on the host by the CTA emulator of
 // tests/emu/cta_emu.h.  The tcgen05 / TMEM / mbarrier path (PREC = 1) is inline PTX and has no host meaning: its
 // helpers are parsed but never instantiated here.  __syncwarp is a barrier over the 32 emulated threads of a warp
@@ -46,7 +46,8 @@ int launch(K k, const A& a, unsigned grid, unsigned threads) {
 struct MlpArgs { const float* net; const float* feat; const float* mask; float* adv; float* pol; long long n; };
 void mlp_entry(MlpArgs a) { sd_mlp_kernel<0>(a.net, nullptr, a.feat, a.mask, a.adv, a.pol, a.n); }
 struct LvlArgs { SdArgs a; int d; };
-void forward_entry(LvlArgs x) { sd_forward_kernel<0>(x.a, x.d); }
+void level_mlp_entry(LvlArgs x) { sd_level_mlp_kernel<0>(x.a, x.d); }
+void expand_entry(LvlArgs x) { sd_expand_kernel(x.a, x.d); }
 void forced_entry(LvlArgs x) { sd_forced_kernel(x.a, x.d); }
 void backward_entry(LvlArgs x) { sd_backward_kernel(x.a, x.d); }
 struct InitArgs { SdArgs a; uint4 root; };
@@ -89,9 +90,12 @@ int host_sd_traverse(const uint32_t* root4, uint32_t hand_order, int player, con
     for (int d = 0; d < 8; d++) {
         const bool forced_opp = ((d & 1) != player) && (4 - d / 2 == 1);   // the opponent's last card
         LvlArgs la{a, d};
-        const int rc = forced_opp ? launch(forced_entry, la, grid_of(n_trav * a.sh.n[d], 256, 8), 256)
-                                  : launch(forward_entry, la, grid_of(n_trav * a.sh.n[d], SD_TILE, 1), SD_TILE);
-        if (rc) return -1;
+        if (forced_opp) {
+            if (launch(forced_entry, la, grid_of(n_trav * a.sh.n[d], 256, 8), 256)) return -1;
+            continue;
+        }
+        if (launch(level_mlp_entry, la, grid_of(n_trav * a.sh.n[d], SD_TILE, 1), SD_TILE)) return -1;
+        if (launch(expand_entry, la, grid_of(n_trav * a.sh.n[d], 256, 8), 256)) return -1;
     }
     if (launch(terminal_entry, a, grid_of(n_trav * a.sh.n[8], 256, 8), 256)) return -1;
     for (int d = 7; d >= 0; d--) {
