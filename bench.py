@@ -1091,7 +1091,15 @@ def section_sdcfr(cx, sv):
                           "kernel": "sd_level_mlp_kernel<1>", "peak_source": tf_src,
                           "note": "numerator = 27 136 FLOP x inferences of WHOLE traversals (env steps, sampling, backward levels "
                                   "and sample emission included in the time), so this is a floor on the tensor-pipe share; "
-                                  "K = 34 / N = 16 layers pad to MMA tiles (profiles/README.md section 3)"}
+                                  "K = 34 / N = 16 layers pad to MMA tiles; the kernel that holds the MMAs is sd_level_mlp_kernel<1> "
+                                  "(its own tensor-pipe utilisation: `capture`, profiles/README.md R2.5)"}
+    cap = load_capture("sd_level_mlp_kernel")
+    if cap:
+        keys = ("file", "commit", "source_sha16", "stale", "tensor_pipe_active_pct", "issue_slots_active_pct", "warps_active_pct",
+                "duration_us_under_ncu", "registers_per_thread", "dram_bytes_per_launch", "note")
+        sd_obj["roofline"]["capture"] = {k: cap.get(k) for k in keys}
+        if not cap["stale"]:
+            sd_obj["roofline"]["traffic"] = cap.get("dram_bytes_per_launch")
     sd_obj["train"] = guarded(bench_sd_train, dev, _lib)
     sd_obj["drop_in_train"] = guarded(bench_sd_dropin, dev)
     return sd_obj

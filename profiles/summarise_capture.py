@@ -79,6 +79,7 @@ def main():
         "fp64_pipe_pct": get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
         "lsu_pipe_pct": get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
         "warps_active_pct": get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+        "tensor_pipe_active_pct": get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
         "registers_per_thread": get("launch__registers_per_thread"),
         "threads_per_inst": get("smsp__thread_inst_executed_per_inst_executed.ratio"),
         "cas_stall_share_pct": a.cas_stall_share_pct, "note": a.note,

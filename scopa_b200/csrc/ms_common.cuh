@@ -45,6 +45,10 @@ extern std::mutex g_scratch_mu;
 int scratch_get(size_t bytes, char** out, cudaStream_t* stream);
 int host_pipe_streams(cudaStream_t out[3]);
 int64_t host_chunk();
+// Size of the pipeline stage that starts at game `lo` of `n` (ms_env.cu): full stages of host_chunk() games between a SHORT
+// first stage (the GPU starts after a quarter-size copy instead of idling through a full one) and a short last stage (the
+// device->host copy nothing overlaps with is a quarter size too).
+int64_t host_stage_size(int64_t lo, int64_t n);
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 constexpr int kNumSMs = 148;   // B200

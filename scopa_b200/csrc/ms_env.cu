@@ -554,6 +554,16 @@ int scratch_get(size_t bytes, char** out, cudaStream_t* stream) {
 constexpr int64_t MS_HOST_CHUNK_DEFAULT = 262144;
 std::atomic<int64_t> g_host_chunk{MS_HOST_CHUNK_DEFAULT};   // games per pipeline stage of the *_host rollouts
 int64_t host_chunk() { return g_host_chunk.load(); }
+int64_t host_stage_size(int64_t lo, int64_t n) {
+    const int64_t chunk = g_host_chunk.load();
+    const int64_t q = ((chunk / 4 + 127) / 128) * 128;          // stages stay 128-byte aligned slices of every array
+    const int64_t left = n - lo;
+    if (n <= chunk + 2 * q) return left < chunk ? left : chunk;  // small calls: plain chunks
+    if (lo == 0) return q;
+    if (left > chunk + q) return chunk;
+    if (left > q) return ((left - q + 127) / 128) * 128 < left ? ((left - q + 127) / 128) * 128 : left;
+    return left;
+}
 
 int host_pipe_streams(cudaStream_t out[3]) {
     static cudaStream_t pipe[64][3] = {};
@@ -782,10 +792,9 @@ int ms_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t philox_se
     cudaStream_t pipe[3];
     rc = host_pipe_streams(pipe);
     if (rc) return rc;
-    const int64_t chunk = g_host_chunk.load();
     int c = 0;
-    for (int64_t lo = 0; lo < n; lo += chunk, c++) {
-        const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
+    for (int64_t lo = 0, m = 0; lo < n; lo += m, c++) {
+        m = host_stage_size(lo, n);
         cudaStream_t st = pipe[c % 3];
         MS_CUDA(cudaMemcpyAsync(d + o_seed + 8 * lo, h_seeds + lo, 8 * m, cudaMemcpyHostToDevice, st));
         rc = ms_deal_from_seeds((const int64_t*)(d + o_seed) + lo, m, (ms_state*)(d + o_st) + lo, (uint32_t*)(d + o_ho) + lo, st);

@@ -540,10 +540,9 @@ int ms_full_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t phil
     cudaStream_t pipe[3];
     rc = host_pipe_streams(pipe);
     if (rc) return rc;
-    const int64_t chunk = host_chunk();
     int c = 0;
-    for (int64_t lo = 0; lo < n; lo += chunk, c++) {
-        const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
+    for (int64_t lo = 0, m = 0; lo < n; lo += m, c++) {
+        m = host_stage_size(lo, n);
         cudaStream_t st = pipe[c % 3];
         MS_CUDA(cudaMemcpyAsync(d + o_k + 8 * lo, h_seeds + lo, 8 * m, cudaMemcpyHostToDevice, st));
         rc = ms_full_deal_from_seeds((const int64_t*)(d + o_k) + lo, m, (ms_full_state*)(d + o_s) + lo, (ms_full_deck*)d + lo, st);
