@@ -1164,7 +1164,8 @@ def bench_sd_dropin(dev, iterations=20):
     game = pyspiel.load_game("mini_scopa")
     out = {"config": {"workload": f"DeepCFR(game).train(iterations={iterations}, advantage_epochs=10, eval_freq=5), 50 evaluation "
                                   "episodes, 1 traversal per player per iteration, fp32 inference"}}
-    for name, kw in (("default", {}), ("fused_optimizer_device_eval", {"optimizer": "fused", "device_eval": True})):
+    for name, kw in (("default", {}), ("fused_optimizer_device_eval", {"optimizer": "fused", "device_eval": True}),
+                     ("fused_cluster_optimizer_device_eval", {"optimizer": "fused-cluster", "device_eval": True})):
         torch.manual_seed(3)
         np.random.seed(3)
         d = DeepCFR(game, 2, dev, seed=3, **kw)
