@@ -307,6 +307,13 @@ int ms_sdcfr_traverse(const ms_state* h_root, uint32_t hand_order, int player, c
                       int precision, int64_t n_trav, uint64_t philox_seed, uint64_t first_trav, void* d_workspace,
                       size_t workspace_bytes, float* d_feat, float* d_target, float* d_mask, float* d_root_value,
                       void* stream);
+/* ms_sdcfr_infer_states: the inference half of one traversal level on its own (sd_level_mlp_kernel): n packed states, all
+ *   with `player_to_move` to move -> d_raw [n][16], the advantage net's outputs before masking (features of the mover's
+ *   view, deep_cfr.py:213-282).  precision 0 = fp32 CUDA cores (bit-identical to ms_mlp_forward precision 0 on the same
+ *   features), 1 = tcgen05 (bit-identical to ms_mlp_forward precision 1: same operands, same MMAs).  Used by the tests to
+ *   pin the level kernel to ms_mlp_forward. */
+int ms_sdcfr_infer_states(const ms_state* d_states, int64_t n, int player_to_move, const float* d_net, int precision,
+                          float* d_raw, void* stream);
 
 /* ms_sdcfr_train: `epochs` optimiser steps of AdvantageNetwork.train (deep_cfr.py:77-110) in ONE launch: per epoch
  *   gather the minibatch d_idx[epoch][0..batch) (rows of the replay buffer d_feat [n_rows][34], d_target / d_mask

@@ -71,6 +71,7 @@ _SIGS = {
     "ms_sdcfr_samples_per_traversal": ([C.c_int], C.c_int),
     "ms_sdcfr_workspace_bytes": ([i64], C.c_size_t),
     "ms_mlp_forward": ([vp, C.c_int, vp, vp, vp, vp, i64, vp], C.c_int),
+    "ms_sdcfr_infer_states": ([vp, i64, C.c_int, vp, C.c_int, vp, vp], C.c_int),
     "ms_sdcfr_traverse": ([vp, C.c_uint32, C.c_int, vp, vp, C.c_int, i64, u64, u64, vp, C.c_size_t, vp, vp, vp, vp, vp],
                           C.c_int),
     "ms_sdcfr_train_workspace_bytes": ([], C.c_size_t),

@@ -820,6 +820,36 @@ using namespace ms;
 
 extern "C" {
 
+int ms_sdcfr_infer_states(const ms_state* d_states, int64_t n, int player_to_move, const float* d_net, int precision,
+                          float* d_raw, void* stream) {
+    if (n < 0 || player_to_move < 0 || player_to_move > 1 || precision < 0 || precision > 1 ||
+        (n > 0 && (!d_states || !d_net || !d_raw)))
+        return fail(MS_ERR_ARG, "ms_sdcfr_infer_states: bad argument");
+    if (n == 0) return MS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SdArgs a{};
+    const int d = player_to_move;                          // level parity = player to move
+    a.sh.n[d] = 1; a.n_trav = n;
+    a.lvl[d].state = (uint4*)d_states;
+    a.net[d] = d_net; a.raw = d_raw;
+    if (precision == 0) {
+        MS_CUDA(cudaFuncSetAttribute(sd_level_mlp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_FP32));
+        sd_level_mlp_kernel<0><<<grid_for(n, SD_TILE, 1), SD_TILE, SD_SMEM_FP32, st>>>(a, d);
+        MS_LAUNCH_CHECK();
+        return MS_OK;
+    }
+    unsigned char* img = nullptr;
+    MS_CUDA(cudaMallocAsync((void**)&img, SD_IMG_BYTES, st));
+    sd_prep_kernel<<<8, 256, 0, st>>>(d_net, img);
+    MS_LAUNCH_CHECK();
+    a.img[d] = img;
+    MS_CUDA(cudaFuncSetAttribute(sd_level_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SD_SMEM_TC));
+    sd_level_mlp_kernel<1><<<grid_for(n, SD_TC_THREADS, SD_TC_CTAS_PER_SM), SD_TC_THREADS, SD_SMEM_TC, st>>>(a, d);
+    MS_LAUNCH_CHECK();
+    MS_CUDA(cudaFreeAsync(img, st));
+    return MS_OK;
+}
+
 int ms_sdcfr_samples_per_traversal(int player) {
     SdShape sh;
     sd_shape(player & 1, sh);

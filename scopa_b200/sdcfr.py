@@ -43,6 +43,20 @@ def mlp_forward(blob, feat, mask, precision=FP32):
     return adv, pol
 
 
+def infer_states(blob, states, player_to_move, precision=FP32):
+    """The inference half of one traversal level on its own (sd_level_mlp_kernel): packed states [n,4] (the uint32 words
+    as an int32 torch tensor on the device, all with `player_to_move` to move) -> the advantage net's raw outputs [n,16]
+    (before masking), features of the mover's view."""
+    lib = _lib.load()
+    states = states.contiguous()
+    n = states.shape[0]
+    raw = torch.empty((n, 16), dtype=torch.float32, device=states.device)
+    with torch.cuda.device(states.device):
+        _lib.check(lib.ms_sdcfr_infer_states(states.data_ptr(), n, int(player_to_move), blob.data_ptr(), int(precision),
+                                             raw.data_ptr(), _lib.stream_ptr()))
+    return raw
+
+
 class Traverser:
     """Reusable workspace for batches of external-sampling traversals from one root."""
 

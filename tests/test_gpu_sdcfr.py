@@ -110,3 +110,40 @@ def test_traversal_tensor_core_path_is_consistent(nets):
     # bf16 rounding can flip a near-zero advantage, which changes the sampled path; most traversals agree
     same = (value - f32[3]).abs() < 0.05
     assert same.float().mean().item() > 0.8
+
+
+@pytest.mark.parametrize("n", [1, 100, 128, 129, 4000])
+def test_level_inference_kernel_equals_mlp_forward(nets, n):
+    """sd_level_mlp_kernel (the inference half of a traversal level: packed states in, 16 raw outputs out) against
+    ms_mlp_forward on the features of the same states, bit for bit on both paths: fp32 (same summation order) and tcgen05
+    (the operand built from the state's bit masks equals the one converted from 0 / 1 floats; same MMAs)."""
+    from scopa_b200.batch import BatchedMiniScopa
+    g, blobs, _ = nets
+    b = BatchedMiniScopa("cuda").reset(np.arange(1, n + 1, dtype=np.int64))
+    rng = np.random.default_rng(n)
+    plies = int(rng.integers(0, 4)) * 2                       # an even number of random plies: player 0 to move again
+    for _ in range(plies):
+        _, ordered, count = b.legal_actions()
+        legal, cnt = ordered.cpu().numpy(), count.cpu().numpy()
+        pick = np.array([legal[i, rng.integers(0, max(1, cnt[i]))] for i in range(n)], dtype=np.uint8)
+        b.step(torch.from_numpy(pick).cuda())
+    states = b.states.clone()
+    w = states.cpu().numpy().view(np.uint32).reshape(n, 4)
+    hand0 = w[:, 0] & 0xFFFF
+    tlen = w[:, 3] & 0xF
+    feat = np.zeros((n, 34), dtype=np.float32)
+    for i in range(n):
+        for c in range(16):
+            feat[i, c] = (hand0[i] >> c) & 1
+        for j in range(int(tlen[i])):
+            feat[i, 16 + ((int(w[i, 1]) >> (4 * j)) & 0xF)] = 1.0
+    feat[:, 32] = 1.0
+    f_t = torch.from_numpy(feat).cuda()
+    ones = torch.ones((n, 16), device="cuda")
+    a32, _ = sdcfr.mlp_forward(blobs[0], f_t, ones, sdcfr.FP32)      # mask of ones: advantages == raw outputs
+    atc, _ = sdcfr.mlp_forward(blobs[0], f_t, ones, sdcfr.TENSOR_CORE)
+    r32 = sdcfr.infer_states(blobs[0], states, 0, sdcfr.FP32)
+    assert torch.equal(r32, a32)
+    rtc = sdcfr.infer_states(blobs[0], states, 0, sdcfr.TENSOR_CORE)
+    assert torch.equal(rtc, atc)
+    assert (rtc - r32).abs().max().item() < 0.03
