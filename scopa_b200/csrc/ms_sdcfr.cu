@@ -497,12 +497,13 @@ __device__ __forceinline__ void sd_policy(const float* raw, uint32_t legal_mask,
 // instructions in profiles/sd_expand_r02m_raw.csv).  `rawp` = the node's 16 raw outputs in global memory (indexed reads).
 __device__ __forceinline__ void sd_policy_legal(const float* raw, const float* __restrict__ rawp, uint32_t legal_mask,
                                                 uint32_t list, uint32_t nl, float* p4) {
+    // z = sum over the 16 slots, in index order, of max(adv, 0) * m with adv = raw * m - 1e6 * (1 - m): for a legal slot
+    // (m = 1) that is max(raw, 0) exactly, for an illegal one an exact zero, and adding zeros does not change a float sum
     float z = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const float m = (float)((legal_mask >> i) & 1u);
-        const float adv = raw[i] * m - 1e6f * (1.f - m);
-        z += (adv > 0.f ? adv : 0.f) * m;
+        const float pos = raw[i] > 0.f ? raw[i] : 0.f;
+        z += ((legal_mask >> i) & 1u) ? pos : 0.f;
     }
     if (z < 1e-8f) z = 1e-8f;
 #pragma unroll
