@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(sda::kPolThreads, 1) sd_avgpol_kernel(SdAvgPol
                 }
                 z = fmaxf(z, 1e-8f);
 #pragma unroll
-                for (int j = 0; j < kOut; ++j) out[(r0 + m) * kOut + j] = (pos[j] / z) * wk;
+                for (int j = 0; j < kOut; ++j) out[(r0 + m) * kOut + j] = ms_div_or_zero(pos[j], z) * wk;
             }
         }
     }

@@ -27,6 +27,7 @@
 // how the kernel's logic is checked against torch on machines without a GPU.  Same source, fmaf everywhere and no
 // contraction elsewhere (nvcc --fmad=false / g++ -ffp-contract=off), so the two builds agree bit for bit.
 #pragma once
+#include "ms_div.cuh"
 
 #ifndef MS_CTA_EMU
 #define MS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
@@ -256,9 +257,9 @@ __global__ void __launch_bounds__(sdt::kThreads, 1) sd_train_kernel(SdTrainArgs 
             v = v * fb2 + (w2 * g) * g;                  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
             a.adam_m[e] = m;
             a.adam_v[e] = v;
-            const float denom = sqrtf(v) / bc2_sqrt + feps;
-            float& p = S[smem_of(e)];
-            p = p - step_size * (m / denom);
+            const float denom = ms_div_or_zero(sqrtf(v), bc2_sqrt) + feps;      // v and m are exactly 0 for weights no
+            float& p = S[smem_of(e)];                                           // gradient has reached yet
+            p = p - step_size * ms_div_or_zero(m, denom);
         }
     }
     __syncthreads();

@@ -28,6 +28,7 @@
 
 #include "ms_common.cuh"
 #include "ms_state.cuh"
+#include "ms_div.cuh"
 
 #ifndef MS_DYN_SMEM   // the host emulation (tests/emu) supplies its own: one buffer per emulated block
 #define MS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
@@ -457,20 +458,6 @@ __device__ __forceinline__ void mlp_tc_state(const SdSmemTc& sm, const MsState& 
     mlp_tc_layers<VAR>(sm, out, phase);
 }
 
-// a / b in IEEE arithmetic where a may be exactly 0 (the result is then a itself, sign included).  The compiler turns a
-// guard like `a != 0 ? a / b : a` into an unconditional division plus a select, and a zero numerator sends the division
-// into its special-case subroutine -- a call the whole warp waits for (profiles/README.md R2.5: 22 % of the backward
-// kernel's instructions, 30 % of the expand kernel's).  Dividing a harmless stand-in keeps every lane on the inline path.
-__device__ __forceinline__ float sd_div_or_zero(float a, float b) {
-    const bool nz = a != 0.f;
-    float num = nz ? a : 1.f;
-#ifndef MS_CTA_EMU
-    asm("" : "+f"(num));            // opaque: otherwise the compiler folds the stand-in away and divides `a` itself again
-#endif
-    const float q = num / b;
-    return nz ? q : a;
-}
-
 // ---------------------------------------------------------------------------------------------
 // AdvantageNetwork.get_advantages masking (deep_cfr.py:66-67) + positive_regret_policy (nets.py:93-101)
 __device__ __forceinline__ void sd_policy(const float* raw, uint32_t legal_mask, float* adv, float* pol) {
@@ -487,7 +474,7 @@ __device__ __forceinline__ void sd_policy(const float* raw, uint32_t legal_mask,
     // 0 / z is exactly 0, but a zero numerator sends the IEEE division into its special-case subroutine: with 12+
     // of the 16 slots illegal that subroutine was 15 % of the forward kernel's instructions (profiles/README.md 3)
 #pragma unroll
-    for (int i = 0; i < 16; i++) pol[i] = sd_div_or_zero(pol[i], z);           // pol >= 0: exactly 0 stays 0
+    for (int i = 0; i < 16; i++) pol[i] = ms_div_or_zero(pol[i], z);           // pol >= 0: exactly 0 stays 0
 }
 
 // The same policy where the traversal needs it: at the (at most four) legal actions, in legal-list order.  z is summed
@@ -511,7 +498,7 @@ __device__ __forceinline__ void sd_policy_legal(const float* raw, const float* _
         float v = 0.f;
         if (k < nl) {
             const float r = rawp[(list >> (4 * k)) & 0xFu];      // adv = r * 1 - 1e6 * 0 = r exactly
-            v = sd_div_or_zero(r > 0.f ? r : 0.f, z);
+            v = ms_div_or_zero(r > 0.f ? r : 0.f, z);
         }
         p4[k] = v;
     }
@@ -639,7 +626,7 @@ __global__ void __launch_bounds__(256) sd_expand_kernel(SdArgs a, int d) {
             if (sum == 0.f) ai = __umulhi(w0, nl);                    // np.random.choice(legal_actions)
             else {
                 double cdf[4], acc = 0.0;
-                for (uint32_t i = 0; i < 4; i++) { if (i < nl) acc = __dadd_rn(acc, (double)sd_div_or_zero(ap[i] > 0.f ? ap[i] : 0.f, sum)); cdf[i] = acc; }
+                for (uint32_t i = 0; i < 4; i++) { if (i < nl) acc = __dadd_rn(acc, (double)ms_div_or_zero(ap[i] > 0.f ? ap[i] : 0.f, sum)); cdf[i] = acc; }
                 const double last = acc, u = u53(w0, w1);
                 ai = 0u;
                 for (uint32_t i = 0; i < nl; i++) if (__ddiv_rn(cdf[i], last) <= u) ai++;
@@ -738,7 +725,7 @@ __global__ void __launch_bounds__(256) sd_backward_kernel(SdArgs a, int d) {
             if (mx > 0.f) {
                 const float dn = mx + 1e-8f;
 #pragma unroll
-                for (int i = 0; i < 16; i++) reg[i] = sd_div_or_zero(reg[i], dn);
+                for (int i = 0; i < 16; i++) reg[i] = ms_div_or_zero(reg[i], dn);
             }
             const long long t = g / nd, j = g % nd;
             rel[lane] = (uint32_t)(t * a.sh.samples + a.sh.sample_off[d] + j - slot0);

@@ -23,7 +23,8 @@ def build_emu():
             os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_train.cuh"),
             os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_avgpol.cuh"),
             os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_train_cluster.cuh"),
-            os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_sample.cuh")]
+            os.path.join(ROOT, "scopa_b200", "csrc", "ms_sd_sample.cuh"),
+            os.path.join(ROOT, "scopa_b200", "csrc", "ms_div.cuh")]
     if _newer(EMU_LIB, deps):
         subprocess.run(["g++"] + CXXFLAGS + ["-fPIC", "-shared", "-o", EMU_LIB, deps[0]], check=True)
     return EMU_LIB
@@ -134,7 +135,7 @@ def build_sdcfr_host():
     os.makedirs(OUT, exist_ok=True)
     src = os.path.join(HERE, "ms_sdcfr_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
-    deps = [src, HOST_H, os.path.join(HERE, "cta_emu.h"), os.path.join(HERE, "cta_emu_warp.h")] + [os.path.join(csrc, f) for f in ("ms_sdcfr.cu", "ms_state.cuh", "ms_common.cuh")]
+    deps = [src, HOST_H, os.path.join(HERE, "cta_emu.h"), os.path.join(HERE, "cta_emu_warp.h")] + [os.path.join(csrc, f) for f in ("ms_sdcfr.cu", "ms_state.cuh", "ms_common.cuh", "ms_div.cuh")]
     if _newer(SD_LIB, deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
                         f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", SD_LIB, src], check=True)
