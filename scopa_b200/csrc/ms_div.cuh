@@ -11,10 +11,24 @@ namespace ms {
 __device__ __forceinline__ float ms_div_or_zero(float a, float b) {
     const bool nz = a != 0.f;
     float num = nz ? a : 1.f;
-#ifndef MS_CTA_EMU
+#ifdef __CUDA_ARCH__
     asm("" : "+f"(num));
 #endif
     const float q = num / b;
+    return nz ? q : a;
+}
+
+// the same for fp64 (regret matching divides positive parts that are often exactly 0; the reference-semantics MCCFR kernels
+// are one dependent chain per run, where a trip through the division's special-case subroutine is pure latency)
+__device__ __forceinline__ double ms_ddiv_or_zero(double a, double b) {
+    const bool nz = a != 0.0;
+    double num = nz ? a : 1.0;
+#ifdef __CUDA_ARCH__
+    asm("" : "+d"(num));
+    const double q = __ddiv_rn(num, b);
+#else
+    const double q = num / b;
+#endif
     return nz ? q : a;
 }
 

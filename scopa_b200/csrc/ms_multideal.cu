@@ -140,7 +140,7 @@ __device__ __forceinline__ void md_regret_match(const double* reg, int n, double
     }
     const double uni = __ddiv_rn(1.0, (double)n);
 #pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (norm > 0.0 ? __ddiv_rn(pos[i], norm) : uni) : 0.0;
+    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (norm > 0.0 ? ms_ddiv_or_zero(pos[i], norm) : uni) : 0.0;
 }
 
 // column of legal action k: how many cards of the hand have a smaller id

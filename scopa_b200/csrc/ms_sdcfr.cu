@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(256) sd_expand_kernel(SdArgs a, int d) {
                 for (uint32_t i = 0; i < 4; i++) { if (i < nl) acc = __dadd_rn(acc, (double)ms_div_or_zero(ap[i] > 0.f ? ap[i] : 0.f, sum)); cdf[i] = acc; }
                 const double last = acc, u = u53(w0, w1);
                 ai = 0u;
-                for (uint32_t i = 0; i < nl; i++) if (__ddiv_rn(cdf[i], last) <= u) ai++;
+                for (uint32_t i = 0; i < nl; i++) if (ms_ddiv_or_zero(cdf[i], last) <= u) ai++;
                 if (ai >= nl) ai = nl - 1u;
             }
             MsState c = s;

@@ -1528,7 +1528,7 @@ __device__ __forceinline__ void avg_policy(const SolverDev& d, int s, int kind, 
     if (kind == 0) use = tot > 0.0;                                   // LearnedCFRPolicy / InfoNode.policy
     else if (kind == 1) use = d.touched[s] && tot > 1e-12;            // ScopaLearnedPolicy (unseen key -> uniform)
     else use = false;
-    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (use ? __ddiv_rn(st[i], tot) : __ddiv_rn(1.0, (double)n)) : 0.0;
+    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (use ? ms_ddiv_or_zero(st[i], tot) : __ddiv_rn(1.0, (double)n)) : 0.0;
 }
 
 __global__ void __launch_bounds__(512, 1) best_response_kernel(SolverDev d, int n_dec, int kind, double* out2) {

@@ -5,6 +5,7 @@
 #include <cstdint>
 
 #include "ms_state.cuh"
+#include "ms_div.cuh"
 
 namespace ms {
 
@@ -19,7 +20,7 @@ __device__ __forceinline__ void regret_match(const double* reg, int n, double* o
     }
     const double uni = __ddiv_rn(1.0, (double)n);
 #pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (norm > 0.0 ? __ddiv_rn(pos[i], norm) : uni) : 0.0;
+    for (int i = 0; i < 4; i++) out[i] = (i < n) ? (norm > 0.0 ? ms_ddiv_or_zero(pos[i], norm) : uni) : 0.0;
 }
 
 // np.random.choice(legal, p=sigma): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right')
@@ -32,7 +33,7 @@ __device__ __forceinline__ int sample_action(const double* sg, int n, double u) 
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++)
-        if (i < n && __ddiv_rn(cdf[i], last) <= u) idx++;
+        if (i < n && ms_ddiv_or_zero(cdf[i], last) <= u) idx++;
     return idx < n ? idx : n - 1;
 }
 
@@ -43,7 +44,7 @@ __device__ __forceinline__ void strategy_cdf(const double* sg, int n, double* cd
     for (int i = 0; i < 4; i++) { if (i < n) acc = __dadd_rn(acc, sg[i]); cdf[i] = acc; }
     const double last = acc;
 #pragma unroll
-    for (int i = 0; i < 4; i++) cdf[i] = (i < n) ? __ddiv_rn(cdf[i], last) : 2.0;
+    for (int i = 0; i < 4; i++) cdf[i] = (i < n) ? ms_ddiv_or_zero(cdf[i], last) : 2.0;
 }
 
 struct MccfrShared {

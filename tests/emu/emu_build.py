@@ -104,7 +104,7 @@ def build_solver_host():
     src = os.path.join(HERE, "ms_solver_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
     deps = [src, HOST_H, os.path.join(HERE, "cta_emu.h"), os.path.join(HERE, "cta_emu_warp.h")] + [os.path.join(csrc, f) for f in ("ms_solver.cu", "ms_tree_walk.cuh",
-                                                                                     "ms_static_walk.cuh", "ms_state.cuh", "ms_common.cuh")]
+                                                                                     "ms_static_walk.cuh", "ms_state.cuh", "ms_common.cuh", "ms_div.cuh")]
     if _newer(SOLVER_LIB, deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
                         f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", SOLVER_LIB, src], check=True)
@@ -120,7 +120,7 @@ def build_multideal_host():
     src = os.path.join(HERE, "ms_multideal_host.cpp")
     csrc = os.path.join(ROOT, "scopa_b200", "csrc")
     deps = [src, HOST_H, os.path.join(HERE, "cta_emu.h"), os.path.join(HERE, "cta_emu_warp.h")] + [os.path.join(csrc, f) for f in ("ms_multideal.cu", "ms_tree_walk.cuh",
-                                                                                     "ms_static_walk.cuh", "ms_state.cuh", "ms_common.cuh")]
+                                                                                     "ms_static_walk.cuh", "ms_state.cuh", "ms_common.cuh", "ms_div.cuh")]
     if _newer(MD_LIB, deps):
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-pthread", "-fPIC", "-shared", "-w",
                         f"-I{_cuda_root()}/include", f"-I{HERE}", "-o", MD_LIB, src], check=True)
