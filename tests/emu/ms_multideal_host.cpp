@@ -4,7 +4,9 @@
 // tests/emu/cta_emu.h: one pthread per CUDA thread, the "HBM" table in host memory, atomicCAS / atomicAdd / atomicOr as
 // real atomics, __ldcg as a plain load, IEEE double without contraction.  The host side of the library (allocation,
 // deal of the roots, launches) is the few lines of ms_md_create / ms_md_mccfr_batch / ms_md_apply restated below;
-// the dealt roots are passed in by the test.  Test infrastructure.
+// the dealt roots are passed in by the test.  host_md_world_create emulates several RANKS sharing one sharded table (what
+// ms_md_ipc_attach sets up over CUDA IPC), host_md_barrier_all runs md_peer_barrier_kernel for all of them concurrently.
+// Test infrastructure.
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
