@@ -263,3 +263,38 @@ def test_argument_validation():
         md.mccfr_batch(10, player=3)
     md.mccfr_batch(0)
     assert md.counters()["updates"] == 0 and md.table_bytes == 4096 * 128
+
+
+def test_sharding_entry_points_in_a_world_of_one():
+    """The sharded-table entry points (ms_md_ipc_export / _attach / _peer_barrier / _peer_error) on ONE GPU: a world of
+    one rank attaches to itself (no IPC handle is opened), runs the same kernels with its barrier between them and must
+    reproduce the unattached solver bit for bit; argument and state errors are reported, never a hang.  (Two ranks on two
+    GPUs: tests/test_gpu_multigpu.py; two and three emulated ranks: tests/test_multideal_host.py.)"""
+    import ctypes as C
+    lib = _lib.load()
+    seeds = [42, 1, 43, 7, 99]
+    a = multideal.MultiDealSolver(seeds, log2_capacity=14)
+    b = multideal.MultiDealSolver(seeds, log2_capacity=14)
+    handles = (C.c_ubyte * 128)()
+    assert lib.ms_md_ipc_export(a.h, handles) == 0
+    assert lib.ms_md_ipc_attach(a.h, 0, 9, bytes(handles) * 9) == -2           # more ranks than MD_MAX_PEERS
+    assert lib.ms_md_ipc_attach(a.h, 1, 1, bytes(handles)) == -2               # rank outside the world
+    assert lib.ms_md_ipc_attach(a.h, 0, 1, bytes(handles)) == 0
+    assert lib.ms_md_ipc_attach(a.h, 0, 1, bytes(handles)) == -4               # already attached
+    with pytest.raises(_lib.MsError):
+        a.reset()                                                              # peers would still be reading the shard
+    a.rank, a.world, a.group = 0, 1, None
+    for it in range(3):
+        a.iterate_blocked(6, 256, philox_seed=4, first_visit=6 * it)           # blocked ; barrier ; apply ; barrier
+        b.mccfr_blocked(6, 256, philox_seed=4, first_visit=6 * it)
+        b.apply()
+    assert a.peer_error() == 0
+    ka, ra, sa = a.export()
+    kb, rb, sb = b.export()
+    assert np.array_equal(ka, kb)
+    np.testing.assert_allclose(ra, rb, rtol=1e-12, atol=1e-12)                 # (CTAs flush their REDs in any order)
+    np.testing.assert_allclose(sa, sb, rtol=1e-12, atol=1e-12)
+    ks, _, _ = a.export_shard()
+    assert np.array_equal(np.sort(ks), ka)
+    # attaching after the first traversal is refused: the deal descriptions already name table slots
+    assert lib.ms_md_ipc_attach(b.h, 0, 1, bytes(handles)) == -4
