@@ -71,6 +71,10 @@ int ms_debug_atomic_peaks(double h_out[3], void* stream);
 /* tuning hook: games per pipeline stage of the *_host rollout entry points (H2D / kernels / D2H of consecutive
  * stages overlap).  games <= 0 restores the default.  Returns the value now in effect. */
 int64_t ms_debug_set_host_chunk(int64_t games);
+/* size of the pipeline stage that starts at game `lo` of an n-game *_host rollout call: full stages of the chunk size between
+ * a quarter-size first and last stage (so the GPU neither idles through a full copy in nor ends on a full copy out); every
+ * stage but the last is a multiple of 128 games.  0 when lo is outside [0, n).  No device needed. */
+int64_t ms_debug_host_stage_size(int64_t lo, int64_t n);
 
 /* ms_step: MiniScopaEnv.step(action) on n independent states in place (src/envs/mini_scopa_game.py:140-167
  *   incl. play_card :93-104, card_in_table :66-91, evaluate_game :106-114).  d_rewards ([n][2] f32,

@@ -28,6 +28,7 @@ _SIGS = {
     "ms_debug_deal_slow_path": ([vp, i64, vp, vp, vp], C.c_int),
     "ms_debug_atomic_peaks": ([C.POINTER(dbl), vp], C.c_int),
     "ms_debug_set_host_chunk": ([i64], i64),
+    "ms_debug_host_stage_size": ([i64, i64], i64),
     "ms_step": ([vp, vp, vp, vp, i64, vp], C.c_int),
     "ms_legal_actions": ([vp, vp, C.c_int, vp, vp, vp, vp, i64, vp], C.c_int),
     "ms_capture": ([vp, vp, vp, i64, vp], C.c_int),

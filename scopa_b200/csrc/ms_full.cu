@@ -557,5 +557,8 @@ int ms_full_rollout_random_host(const int64_t* h_seeds, int64_t n, uint64_t phil
     return MS_OK;
 }
 
+// test hook: the stage schedule both host rollouts (this file's and ms_env.cu's) walk -- size of the stage that starts at game lo of n
+int64_t ms_debug_host_stage_size(int64_t lo, int64_t n) { return (lo < 0 || n <= lo) ? 0 : host_stage_size(lo, n); }
+
 }  // extern "C"
 #endif  // MS_HOST_RULES_ONLY

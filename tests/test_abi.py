@@ -104,3 +104,36 @@ def test_argument_validation_needs_no_gpu():
     assert lib.ms_rollout_random_host(None, 0, 0, 0, None, None) == 0
     assert lib.ms_sdcfr_samples_per_traversal(0) == 41 and lib.ms_sdcfr_samples_per_traversal(1) == 41
     assert lib.ms_sdcfr_workspace_bytes(1000) > 1000 * 129 * 16
+
+
+def test_host_pipeline_stage_schedule():
+    """The stage schedule of the *_host rollout entry points (ms_rollout_random_host, ms_full_rollout_random_host): the stages
+    tile [0, n) exactly, all but the last are multiples of 128 games (128-byte aligned slices of every array), big calls
+    start and end with a quarter-size stage, small calls are plain chunks.  Host logic: no device needed."""
+    lib = _lib.load(build_if_missing=True)
+
+    def stages(n):
+        out, lo = [], 0
+        while lo < n:
+            m = lib.ms_debug_host_stage_size(lo, n)
+            assert 0 < m <= n - lo
+            out.append(m)
+            lo += m
+        return out
+
+    assert lib.ms_debug_set_host_chunk(0) == 262144
+    try:
+        for n in (1, 127, 65537, 262144, 300000, 393216, 393217, 1_000_000, 4_000_000, 16_777_216 + 5):
+            st = stages(n)
+            assert sum(st) == n and all(m % 128 == 0 for m in st[:-1]) and max(st) <= 262144
+            if n > 262144 + 2 * 65536:
+                assert st[0] == 65536 and st[-1] <= 65536 + 127 and st.count(262144) >= len(st) - 4
+            else:
+                assert st == [262144] * (n // 262144) + ([n % 262144] if n % 262144 else [])
+        assert stages(1_000_000) == [65536, 262144, 262144, 262144, 82560, 65472]
+        assert lib.ms_debug_host_stage_size(-1, 10) == 0 and lib.ms_debug_host_stage_size(10, 10) == 0
+        assert lib.ms_debug_set_host_chunk(300) == 384              # rounded up to 128 games
+        st = stages(2000)
+        assert sum(st) == 2000 and st[0] == 128 and all(m % 128 == 0 for m in st[:-1])
+    finally:
+        assert lib.ms_debug_set_host_chunk(0) == 262144
