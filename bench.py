@@ -172,6 +172,27 @@ def dist_env():
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on the CPUs NVML names as local to that GPU, so that the pinned host buffers of the end-to-end
+    paths are first touched on the GPU's own NUMA node and eight ranks do not push their PCIe traffic through one socket's
+    memory.  -> the number of CPUs bound to, or None (NVML absent, an empty mask, affinity not permitted: nothing changes)."""
+    if os.environ.get("SCOPA_B200_BENCH_AFFINITY", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def headline_config(args, world, collective=None):
     """`config` of the JSON line: the same object for the CUDA arm and for --impl reference."""
     cfg = {"workload": "BASELINE.json configs[2]/[4]: MCCFR (the reference's estimator, mc_cfr.py:37-86), seed-42 deal, "
@@ -203,6 +224,7 @@ class Cx:
             raise SystemExit("bench.py: no CUDA device -- scopa_b200 has no CPU fallback")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.numa_cpus = bind_to_gpu_numa_node(self.local) if self.world > 1 else None
         if self.world > 1:
             # a collective mismatch must fail in minutes, not hang until the driver's limit
             dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
@@ -1250,6 +1272,10 @@ def run_ours(args):
         ("env" if primary is mccfr_obj else "mccfr"): secondary,
         "collective": mccfr_obj["config"].get("collective"),
     }
+    if world > 1:
+        line["host_binding"] = ({"cpus_per_rank": cx.numa_cpus, "note": "each rank runs on the CPUs NVML reports as local to its GPU "
+                                 "(pinned host buffers of the e2e paths are first touched on that NUMA node)"}
+                                if cx.numa_cpus else {"cpus_per_rank": None, "note": "not bound (NVML affinity unavailable or disabled)"})
     for k in ("node_visits_per_sec", "update_composition", "exchange"):
         if primary is mccfr_obj and k in mccfr_obj:
             line[k] = mccfr_obj[k]
