@@ -779,10 +779,13 @@ def section_step_api(cx):
     torch.cuda.synchronize()
     step_ms = sum(a.elapsed_time(c) for a, c in stev) / K
     gbs = 42.0 * NS / (step_ms * 1e-3) / 1e9
+    cap = load_capture("step_kernel")            # dram__bytes of one launch (16 M states), from the committed capture of this source
+    traffic = cap.get("dram_bytes_per_launch") if cap and not cap["stale"] and NS == 16_000_000 else None
     return {"kernel": "step_kernel", "env_steps_per_sec": NS / (step_ms * 1e-3), "kernel_ms": step_ms,
             "bytes_per_step": 42, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / cx.hbm_gbs,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": cx.hbm_gbs, "unit": "GB/s", "frac": gbs / cx.hbm_gbs,
-                         "traffic": None, "peak_source": cx.peak_src},
+                         "traffic": traffic, "algorithmic_bytes_per_launch": 42.0 * NS, "peak_source": cx.peak_src,
+                         "capture": ({k: cap.get(k) for k in ("file", "commit", "source_sha16", "stale", "duration_us_under_ncu")} if cap else None)},
             "note": f"{NS} states ({16 * NS >> 20} MiB, larger than L2), one ply per launch, state + action in, "
                     "state + rewards + done out"}
 
@@ -1054,12 +1057,16 @@ def section_full(cx):
         cpu_full = {"value": 200_000 * fs.PLIES / dt, "unit": "env steps/s", "cores": ncpu, "kind": "port",
                     "sample": "200 000 games x 36 plies, OpenMP over all host threads"}
     ach = FG * fs.PLIES * 65.0 / (f_ms * 1e-3) / 1e9
+    fcap = load_capture("full_rollout_kernel")
     return {"metric": "env_steps_per_sec", "unit": "env steps/s", "value": FG * fs.PLIES / (f_ms * 1e-3), "ms_per_step": f_ms,
             "e2e": {"value": FG * fs.PLIES / f_e2e, "unit": "env steps/s", "h2d_bytes_per_step": 8 * FG,
                     "d2h_bytes_per_step": (fs.PLIES + 8) * FG,
                     "what": "ms_full_rollout_random_host: FullDeck(seed) + deal + 36 plies per game, pinned host buffers in and out, "
                             "H2D / kernels / D2H pipelined over three streams"},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": cx.hbm_gbs, "unit": "GB/s", "frac": ach / cx.hbm_gbs, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": cx.hbm_gbs, "unit": "GB/s", "frac": ach / cx.hbm_gbs,
+                         "traffic": (fcap.get("dram_bytes_per_launch") if fcap and not fcap["stale"] and FG == 1_000_000 else None),
+                         "capture": ({k: fcap.get(k) for k in ("file", "commit", "source_sha16", "stale", "alu_pipe_pct",
+                                                               "issue_slots_active_pct", "duration_us_under_ncu")} if fcap else None),
                          "kernel": "full_rollout_kernel", "peak_source": cx.peak_src,
                          "note": "against the step-granular figure for this game, 65 B/step (32 B state load + 1 B action "
                                  "+ 32 B state store); the fused kernel keeps the state in registers and moves "
