@@ -99,7 +99,15 @@ def test_argument_validation_needs_no_gpu():
     assert lib.ms_sdcfr_traverse(None, 0, 0, None, None, 0, 1, 0, 0, None, 0, None, None, None, None, None) == -2
     assert lib.ms_team_step(None, None, None, None, 3, None) == -2
     assert lib.ms_cfr_iterate_many(None, 3, 1, None) == -2
+    assert lib.ms_sdcfr_infer_states(None, 5, 0, None, 0, None, None) == -2 and b"ms_sdcfr_infer_states" in lib.ms_last_error()
+    assert lib.ms_sdcfr_infer_states(p, 5, 2, p, 0, p, None) == -2                        # player to move must be 0 or 1
+    assert lib.ms_sdcfr_infer_states(p, 5, 0, p, 3, p, None) == -2                        # unknown precision
+    assert lib.ms_md_create(None, 4, 12, None, C.byref(C.c_void_p())) == -2
+    assert lib.ms_md_ipc_export(None, p) == -2 and lib.ms_md_ipc_attach(None, 0, 1, p) == -2
+    assert lib.ms_md_peer_barrier(None, None) == -2 and lib.ms_md_peer_error(None, None, None) == -2
+    assert lib.ms_md_mccfr_blocked(None, 2, 0, 1, 256, 0, None) == -2
     # empty batches succeed without touching the device
+    assert lib.ms_sdcfr_infer_states(None, 0, 0, None, 0, None, None) == 0
     assert lib.ms_step(None, None, None, None, 0, None) == 0
     assert lib.ms_rollout_random_host(None, 0, 0, 0, None, None) == 0
     assert lib.ms_sdcfr_samples_per_traversal(0) == 41 and lib.ms_sdcfr_samples_per_traversal(1) == 41
